@@ -1,0 +1,283 @@
+/*
+ * vqa_answer.h -- C ABI of the B200-native VQA answer-model hot path.
+ *
+ * This is the drop-in boundary for ONE path of HyeonwooNoh/VQA-Transfer-ExternalData: the batched
+ * forward + backward of the vqa/model_vlmap_answer* family (and vqa/model_standard), i.e. what one
+ * session.run([loss, report, optimizer]) executes in the reference (vqa/trainer.py:275-287).
+ * The reference has no FFI of its own (pure Python on TensorFlow 1.6); these entry points are what a
+ * ctypes stub inside vqa/model_vlmap_answer.py would bind.
+ *
+ * Conventions
+ *   - every function returns a VqaStatus (0 = ok, negative = error); vqa_last_error() gives the text
+ *   - plain pointers and sizes only; all tensor pointers are DEVICE pointers unless the name ends in
+ *     _host; the caller owns every buffer (the library keeps a caller-provided workspace only)
+ *   - all work is enqueued on the cudaStream_t passed as `void* stream`; no hidden synchronisation
+ *   - parameters / gradients are fp32 in TensorFlow layout ([in, out] row-major), keyed by the
+ *     reference's checkpoint variable names (comment on each field)
+ *   - one handle per GPU / host thread; entry points are re-entrant per handle
+ *   - there is NO CPU fallback: without a CUDA device every compute entry point fails
+ */
+#ifndef VQA_ANSWER_H_
+#define VQA_ANSWER_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VQA_API __attribute__((visibility("default")))
+
+typedef int32_t VqaStatus;
+enum {
+  VQA_OK = 0,
+  VQA_ERR_BAD_ARG = -1,     /* null pointer, bad enum                                     */
+  VQA_ERR_BAD_SHAPE = -2,   /* dimension not supported (see vqa_create)                   */
+  VQA_ERR_WORKSPACE = -3,   /* workspace missing or too small                             */
+  VQA_ERR_CUDA = -4,        /* a CUDA runtime / driver call failed                        */
+  VQA_ERR_NO_DEVICE = -5,   /* no sm_100 device visible                                   */
+  VQA_ERR_STATE = -6        /* call order violated (e.g. backward before forward)         */
+};
+
+/* model family members served by the same kernels (vqa/importer.py:22-51) */
+enum {
+  VQA_VARIANT_VLMAP_ANSWER = 0, /* vqa/model_vlmap_answer.py: frozen transfer head, train mask */
+  VQA_VARIANT_STANDARD = 1      /* vqa/model_standard.py: learned classifier, all trainable   */
+};
+
+/* arithmetic mode of the dense contractions */
+enum {
+  VQA_PREC_BF16 = 0, /* bf16 operands, fp32 accumulate in TMEM; activations between GEMMs bf16  */
+  VQA_PREC_FP32 = 1  /* error-compensated: each fp32 operand = bf16 hi + bf16 lo, 3 MMAs / tile */
+};
+
+typedef struct VqaConfig {
+  int32_t B;   /* max samples per step on this GPU                                            */
+  int32_t K;   /* max_box_num (boxes per image), vqa/model_vlmap_answer.py:66                 */
+  int32_t Dv;  /* vfeat_dim (2048)                                                            */
+  int32_t D;   /* V_DIM (1024), vqa/model_vlmap_answer.py:12                                  */
+  int32_t L;   /* L_DIM (1024), :11                                                           */
+  int32_t J;   /* joint dim = 2*L_DIM (2048), :177                                            */
+  int32_t A;   /* number of answers                                                           */
+  int32_t T;   /* padded question length of the batch (<= 14 in VQA v2)                       */
+  int32_t W;   /* W_DIM word-embedding dim (300), :10                                         */
+  int32_t Vq;  /* question vocabulary size                                                    */
+  int32_t num_train_answer; /* answers [0, num_train_answer) are train answers, :38-42        */
+  int32_t variant;          /* VQA_VARIANT_*                                                  */
+  int32_t precision;        /* VQA_PREC_*                                                     */
+  float keep_att;           /* attention-feature dropout keep prob (0.8), vlmap/modules.py:82 */
+  float keep_joint;         /* joint dropout keep prob (0.5), vqa/model_vlmap_answer.py:180   */
+} VqaConfig;
+
+/*
+ * Parameters (and, with the same struct, their gradients). fp32, TF layout [in, out].
+ * A NULL pointer in a gradient struct means "do not compute this gradient" (frozen variable).
+ */
+typedef struct VqaParams {
+  float* embed;       /* LearnGloVe/embed_map                        [Vq, W]      */
+  float* v_w;         /* v_linear_v/fc/weights                       [Dv, D]      */
+  float* v_b;         /* v_linear_v/fc/biases                        [D]          */
+  float* v_gamma;     /* v_linear_v/LayerNorm/gamma                  [D]          */
+  float* v_beta;      /* v_linear_v/LayerNorm/beta                   [D]          */
+  float* gru_gates_w; /* encode_L/rnn/gru_cell/gates/kernel          [W+L, 2L]    */
+  float* gru_gates_b; /* encode_L/rnn/gru_cell/gates/bias            [2L]         */
+  float* gru_cand_w;  /* encode_L/rnn/gru_cell/candidate/kernel      [W+L, L]     */
+  float* gru_cand_b;  /* encode_L/rnn/gru_cell/candidate/bias        [L]          */
+  float* qv_w;        /* q_linear_v/fc/weights                       [L, D]       */
+  float* qv_b;        /* q_linear_v/fc/biases                        [D]          */
+  float* qv_gamma;    /* q_linear_v/LayerNorm/gamma                  [D]          */
+  float* qv_beta;     /* q_linear_v/LayerNorm/beta                   [D]          */
+  float* att_w;       /* hadamard_attention/compute/score/fc/weights [D, 1]       */
+  float* att_b;       /* hadamard_attention/compute/score/fc/biases  [1]          */
+  float* pl_w;        /* (reasoning/)pooled_linear_l/fc/weights      [Dv, L]      */
+  float* pl_b;        /* (reasoning/)pooled_linear_l/fc/biases       [L]          */
+  float* pl_gamma;    /* (reasoning/)pooled_linear_l/LayerNorm/gamma [L]          */
+  float* pl_beta;     /* (reasoning/)pooled_linear_l/LayerNorm/beta  [L]          */
+  float* ql_w;        /* (reasoning/)q_linear_l/fc/weights           [L, L]       */
+  float* ql_b;        /* (reasoning/)q_linear_l/fc/biases            [L]          */
+  float* ql_gamma;    /* (reasoning/)q_linear_l/LayerNorm/gamma      [L]          */
+  float* ql_beta;     /* (reasoning/)q_linear_l/LayerNorm/beta       [L]          */
+  float* joint_w;     /* (reasoning/)joint_fc/fc/weights             [L, J]       */
+  float* joint_b;     /* (reasoning/)joint_fc/fc/biases              [J]          */
+  float* joint_gamma; /* (reasoning/)joint_fc/LayerNorm/gamma        [J]          */
+  float* joint_beta;  /* (reasoning/)joint_fc/LayerNorm/beta         [J]          */
+  float* ans_w;       /* WordWeightAnswer/fc/weights | reasoning/classifier/fc/weights [J, A] */
+  float* ans_b;       /* WordWeightAnswer/fc/biases  | reasoning/classifier/fc/biases  [A]    */
+} VqaParams;
+#define VQA_NUM_PARAM_TENSORS 29
+
+/* The feature bank the reference holds in host RAM (vqa/model_vlmap_answer.py:57-77); here in HBM. */
+typedef struct VqaFeatureBank {
+  const float* features;    /* image_features [N, K, Dv] fp32                                 */
+  const int32_t* num_boxes; /* num_boxes      [N]                                             */
+  int64_t num_images;       /* N                                                              */
+} VqaFeatureBank;
+
+/* One batch, keys as in vqa/datasets/input_ops_vqa_tf_record_memft.py:47-59 */
+typedef struct VqaBatch {
+  int32_t batch_size;          /* <= config.B (last eval batch may be smaller)                */
+  int32_t q_len_max;           /* T of this batch (<= config.T); q_intseq is [batch, T]       */
+  const int64_t* image_idx;    /* [batch] index into the feature bank                         */
+  const int32_t* q_intseq;     /* [batch, q_len_max], pad id 0                                */
+  const int32_t* q_intseq_len; /* [batch]                                                     */
+  const float* answer_target;  /* [batch, A] soft scores                                      */
+} VqaBatch;
+
+/* answer masks ([A] fp32 each), vqa/model_vlmap_answer.py:37-52 */
+typedef struct VqaAnswerMasks {
+  const float* is_object;    /* answer_dict['is_object']                                      */
+  const float* is_attribute; /* answer_dict['is_attribute']                                   */
+  const float* answer_exist; /* modules.AnswerExistMask (vlmap/modules.py:575-586)            */
+} VqaAnswerMasks;
+
+/* report scalars, order = vqa/model_vlmap_answer.py:275-288 */
+enum {
+  VQA_REPORT_ANSWER_TRAIN_LOSS = 0,
+  VQA_REPORT_ANSWER_REPORT_LOSS,
+  VQA_REPORT_ANSWER_ACC,
+  VQA_REPORT_EXIST_ACC,
+  VQA_REPORT_TEST_ACC,
+  VQA_REPORT_NORMAL_TEST_ACC,
+  VQA_REPORT_NORMAL_TEST_OBJECT_ACC,
+  VQA_REPORT_NORMAL_TEST_ATTRIBUTE_ACC,
+  VQA_REPORT_NORMAL_EXIST_ACC,
+  VQA_REPORT_NORMAL_TRAIN_EXIST_ACC,
+  VQA_REPORT_MAX_EXIST_ACC,
+  VQA_REPORT_TEST_MAX_ACC,
+  VQA_REPORT_TEST_MAX_EXIST_ACC,
+  VQA_NUM_REPORT
+};
+
+/* per-sample outputs, order = model.output keys read at vqa/evaler.py:139-156 */
+enum {
+  VQA_PS_ALL_SCORE = 0,
+  VQA_PS_MAX_TRAIN_SCORE,
+  VQA_PS_TEST_OBJ_SCORE,
+  VQA_PS_TEST_OBJ_MAX_SCORE,
+  VQA_PS_TEST_ATTR_SCORE,
+  VQA_PS_TEST_ATTR_MAX_SCORE,
+  VQA_NUM_PER_SAMPLE
+};
+
+/* Outputs of a forward pass; any pointer may be NULL (that output is then not written). */
+typedef struct VqaOutputs {
+  float* loss;        /* [1]  model.loss (= answer_train_loss)                                */
+  float* report;      /* [VQA_NUM_REPORT]                                                     */
+  float* att_score;   /* [batch, K]   model.output['att_score']                               */
+  float* logit;       /* [batch, A]   model.output['logit']                                   */
+  int32_t* pred;      /* [batch]      model.output['pred'] (argmax, first index on ties)      */
+  float* per_sample;  /* [VQA_NUM_PER_SAMPLE, batch]                                          */
+  float* condition;   /* [batch, L]   model.heavy_output['condition'] (final GRU state)       */
+  float* pooled;      /* [batch, Dv]  model.mid_result['pooled_V_ft']                         */
+} VqaOutputs;
+
+typedef struct VqaHandle_t* VqaHandle;
+
+/* ---- lifecycle -------------------------------------------------------------------------------- */
+/* Supported shapes: Dv, D, L, J, A multiples of 8; D, L, J <= 4096; K <= 256; T <= 64. */
+VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out);
+VQA_API VqaStatus vqa_destroy(VqaHandle h);
+VQA_API const char* vqa_last_error(void);
+VQA_API int32_t vqa_abi_version(void);
+/* number of kernels this library has enqueued so far in this process */
+VQA_API uint64_t vqa_launch_count(void);
+
+/* bytes of device workspace this handle needs; attach a buffer of at least that size (256-B aligned) */
+VQA_API VqaStatus vqa_workspace_bytes(VqaHandle h, uint64_t* bytes);
+VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes);
+
+/* ---- the path ---------------------------------------------------------------------------------- */
+/* Refresh the GEMM-operand shadows of the weights (bf16 [hi, lo] planes). Call after every parameter
+ * update and before the first forward. Replaces nothing in the reference (TF reads fp32 variables). */
+VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* params, void* stream);
+
+/* Forward of Model.build() (vqa/model_vlmap_answer.py:102-288): gather -> v-proj -> GRU -> attention ->
+ * pooling -> joint head -> logits -> soft-score BCE + report. Dropout always fires (tf.nn.dropout has no
+ * train switch); masks come from Philox keyed by (seed, step). Keeps what backward needs. */
+VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* params, const VqaFeatureBank* bank,
+                              const VqaBatch* batch, const VqaAnswerMasks* masks, uint64_t seed,
+                              uint64_t step, const VqaOutputs* out, void* stream);
+
+/* Backward of the same graph (tf.gradients inside optimize_loss, vqa/trainer.py:106-114) w.r.t. every
+ * non-NULL field of `grads`, for the batch of the preceding vqa_forward on this handle.
+ * loss_scale multiplies d(loss) (1/world_size under data parallelism, so that summed grads = mean). */
+VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* params, const VqaBatch* batch,
+                               const VqaParams* grads, float loss_scale, void* stream);
+
+/* Materialise the dropout masks vqa_forward(seed, step) uses, as 0/1 bytes: att [batch, K, D],
+ * joint [batch, J]. Test / parity helper (the kernels regenerate the same bits on the fly). */
+VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step,
+                                    uint8_t* att_mask, uint8_t* joint_mask, void* stream);
+
+/* ---- optimizer step (vqa/trainer.py:87-114: clip_by_global_norm(20) + Adam) ---------------------- */
+/* flat fp32 buffers of n elements (the trainable set laid out contiguously by the caller).
+ * t = 1-based step count. grad_norm_out [1] receives the pre-clip global norm. */
+VQA_API VqaStatus vqa_adam_step(VqaHandle h, float* param, const float* grad, float* m, float* v,
+                                int64_t n, float lr, float beta1, float beta2, float eps,
+                                float clip_norm, int64_t t, float* grad_norm_out, void* stream);
+
+/* ---- per-kernel entry points (unit parity tests, ncu) --------------------------------------------- */
+typedef struct VqaGemmDesc {
+  /* D[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (+addend[M,N]); operands bf16 planes (lo may be NULL).
+   * a_mn_major = 0: A stored [M, K] (K contiguous), pitch lda elements
+   * a_mn_major = 1: A stored [K, M] (M contiguous), pitch lda
+   * b_mn_major = 0: B stored [N, K] (K contiguous), pitch ldb
+   * b_mn_major = 1: B stored [K, N] (N contiguous), pitch ldb                               */
+  const void* a_hi; const void* a_lo;
+  const void* b_hi; const void* b_lo;
+  int64_t lda, ldb;
+  int32_t a_mn_major, b_mn_major;
+  int32_t M, N, K;
+  const float* bias;
+  const float* addend; int64_t ld_addend;
+  float* out_f32; int64_t ld_f32;           /* optional fp32 output                           */
+  void* out_hi; void* out_lo; int64_t ld_bf; /* optional bf16 output planes (lo = residual)    */
+  int32_t block_n;                          /* 0 = auto; else 64 / 128 / 256                  */
+} VqaGemmDesc;
+VQA_API VqaStatus vqa_gemm(VqaHandle h, const VqaGemmDesc* d, void* stream);
+
+/* fp32 [rows, cols] (pitch ld) -> bf16 hi (and lo if non-NULL) planes with pitch ld_out */
+VQA_API VqaStatus vqa_split_bf16(VqaHandle h, const float* src, int64_t rows, int64_t cols, int64_t ld,
+                                 void* hi, void* lo, int64_t ld_out, void* stream);
+
+/* attention block forward: per-sample LayerNorm(K*D)+ReLU of z, Hadamard with hq, dropout, score,
+ * masked softmax, attended pooling of the features (vlmap/modules.py:67-97, 23-39) */
+typedef struct VqaAttnFwd {
+  int32_t batch;
+  const void* z;            /* [batch*K, D] pre-LN projection; bf16 (PREC_BF16) or fp32 (PREC_FP32) */
+  const float* gamma; const float* beta; /* [D]                                               */
+  const float* hq;          /* [batch, D]                                                     */
+  const float* att_w; const float* att_b;
+  const int32_t* nbox;      /* [batch]                                                        */
+  const void* v_hi; const void* v_lo; /* gathered features [batch*K, Dv] bf16 planes          */
+  uint64_t seed, step;
+  float* att;               /* [batch, K]                                                     */
+  float* pooled;            /* [batch, Dv]                                                    */
+  void* pooled_hi; void* pooled_lo; /* bf16 planes of pooled for the next GEMM (may be NULL)   */
+  float* ln_mean; float* ln_rstd;   /* [batch] saved statistics                               */
+} VqaAttnFwd;
+VQA_API VqaStatus vqa_attn_fwd(VqaHandle h, const VqaAttnFwd* a, void* stream);
+
+typedef struct VqaAttnBwd {
+  int32_t batch;
+  const void* z; const float* gamma; const float* beta; const float* hq;
+  const float* att_w; const int32_t* nbox; const void* v_hi; const void* v_lo;
+  uint64_t seed, step;
+  const float* att; const float* ln_mean; const float* ln_rstd;
+  const float* d_pooled;    /* [batch, Dv]                                                    */
+  void* dz_hi; void* dz_lo; /* [batch*K, D] bf16 planes of d(pre-LN projection)               */
+  float* d_hq;              /* [batch, D]                                                     */
+  float* d_att_w; float* d_att_b; float* d_gamma; float* d_beta; float* d_bias; /* [D],[1],[D],[D],[D] */
+} VqaAttnBwd;
+VQA_API VqaStatus vqa_attn_bwd(VqaHandle h, const VqaAttnBwd* a, void* stream);
+
+/* soft-score BCE + argmax + report (vqa/model_vlmap_answer.py:192-288); d_logit may be NULL */
+VQA_API VqaStatus vqa_bce_metrics(VqaHandle h, int32_t batch, const float* logit, const float* target,
+                                  const VqaAnswerMasks* masks, float grad_scale, float* loss,
+                                  float* report, int32_t* pred, float* per_sample, float* d_logit,
+                                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VQA_ANSWER_H_ */

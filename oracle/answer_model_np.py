@@ -1,0 +1,349 @@
+"""ORACLE (test infrastructure, NOT product code): fp64 NumPy restatement of the reference's VQA
+answer-model hot path, forward and hand-derived backward.
+
+PARITY UNPINNED: the reference ships no tests / golden tensors for this path and its arithmetic lives
+in tensorflow-gpu==1.6.0 (requirements.txt:1), which is not vendored and cannot be installed here
+(no TF, no h5py, no Python 2, no network). This file restates the TF-1.6 op semantics the reference's
+call sites rely on; it is pinned only by (1) central finite differences on its own forward,
+(2) an independently written PyTorch-autograd twin (oracle/answer_model_torch.py), and
+(3) known-answer cases (tests/test_oracle.py). TensorFlow itself was never executed.
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may import
+this package. The product path (vqa_transfer_externaldata_b200) never does.
+
+Reference files followed (paths under /root/reference):
+  vqa/model_vlmap_answer.py:102-288   graph, loss, metrics           (variant 'vlmap_answer')
+  vqa/model_standard.py:193-376       same trunk, learned classifier  (variant 'standard')
+  vlmap/modules.py:630-650            fc_layer = fully_connected -> layer_norm -> activation
+  vlmap/modules.py:67-97              hadamard_attention
+  vlmap/modules.py:23-39              attention_pooling
+  vlmap/modules.py:124-140            encode_L (GRUCell + dynamic_rnn)
+  vlmap/modules.py:589-627            WordWeightAnswer (a fully_connected with constant init)
+  vqa/trainer.py:87-114               optimize_loss(Adam, clip_gradients=20.0)
+"""
+import numpy as np
+
+LN_EPS = 1e-12  # tf.contrib.layers.layer_norm -> tf.nn.batch_normalization variance_epsilon
+
+# C-struct field name -> TF checkpoint variable name (vlmap_answer); 'standard' nests the last four
+# scopes under reasoning/ and calls the head reasoning/classifier (vqa/model_standard.py:251-275)
+TF_NAMES = {
+    "embed": "LearnGloVe/embed_map",
+    "v_w": "v_linear_v/fc/weights", "v_b": "v_linear_v/fc/biases",
+    "v_gamma": "v_linear_v/LayerNorm/gamma", "v_beta": "v_linear_v/LayerNorm/beta",
+    "gru_gates_w": "encode_L/rnn/gru_cell/gates/kernel", "gru_gates_b": "encode_L/rnn/gru_cell/gates/bias",
+    "gru_cand_w": "encode_L/rnn/gru_cell/candidate/kernel",
+    "gru_cand_b": "encode_L/rnn/gru_cell/candidate/bias",
+    "qv_w": "q_linear_v/fc/weights", "qv_b": "q_linear_v/fc/biases",
+    "qv_gamma": "q_linear_v/LayerNorm/gamma", "qv_beta": "q_linear_v/LayerNorm/beta",
+    "att_w": "hadamard_attention/compute/score/fc/weights",
+    "att_b": "hadamard_attention/compute/score/fc/biases",
+    "pl_w": "pooled_linear_l/fc/weights", "pl_b": "pooled_linear_l/fc/biases",
+    "pl_gamma": "pooled_linear_l/LayerNorm/gamma", "pl_beta": "pooled_linear_l/LayerNorm/beta",
+    "ql_w": "q_linear_l/fc/weights", "ql_b": "q_linear_l/fc/biases",
+    "ql_gamma": "q_linear_l/LayerNorm/gamma", "ql_beta": "q_linear_l/LayerNorm/beta",
+    "joint_w": "joint_fc/fc/weights", "joint_b": "joint_fc/fc/biases",
+    "joint_gamma": "joint_fc/LayerNorm/gamma", "joint_beta": "joint_fc/LayerNorm/beta",
+    "ans_w": "WordWeightAnswer/fc/weights", "ans_b": "WordWeightAnswer/fc/biases",
+}
+PARAM_FIELDS = list(TF_NAMES.keys())
+
+# vqa/model_vlmap_answer.py:81-89 filter_train_vars: these top-level scopes are frozen
+FROZEN_SCOPES_VLMAP_ANSWER = ("q_linear_l", "pooled_linear_l", "joint_fc", "WordWeightAnswer")
+
+
+def trainable_fields(variant):
+    """Fields optimize_loss receives as `variables` (vqa/trainer.py:99-114)."""
+    if variant == "standard":  # vqa/model_standard.py:80-84: everything trains
+        return list(PARAM_FIELDS)
+    return [f for f in PARAM_FIELDS if TF_NAMES[f].split("/")[0] not in FROZEN_SCOPES_VLMAP_ANSWER]
+
+
+def sigmoid(x):
+    return 1.0 / (1.0 + np.exp(-x))
+
+
+# ------------------------------------------------------------------------------------------------
+# layers.layer_norm (vlmap/modules.py:646-647): statistics over ALL non-batch axes, gamma/beta on the
+# last axis, biased variance via moments (two-pass), eps 1e-12.   SURVEY Q1
+# ------------------------------------------------------------------------------------------------
+def layer_norm_fwd(z, gamma, beta):
+    axes = tuple(range(1, z.ndim))
+    mu = z.mean(axis=axes, keepdims=True)
+    var = ((z - mu) ** 2).mean(axis=axes, keepdims=True)
+    rstd = 1.0 / np.sqrt(var + LN_EPS)
+    xhat = (z - mu) * rstd
+    return gamma * xhat + beta, (xhat, rstd)
+
+
+def layer_norm_bwd(dy, gamma, cache):
+    xhat, rstd = cache
+    axes = tuple(range(1, dy.ndim))
+    red = tuple(range(0, dy.ndim - 1))
+    dgamma = (dy * xhat).sum(axis=red)
+    dbeta = dy.sum(axis=red)
+    dxhat = dy * gamma
+    dz = rstd * (dxhat - dxhat.mean(axis=axes, keepdims=True)
+                 - xhat * (dxhat * xhat).mean(axis=axes, keepdims=True))
+    return dz, dgamma, dbeta
+
+
+def fc_ln_relu_fwd(x, w, b, gamma, beta):
+    """modules.fc_layer(use_bias, use_ln, relu): rank>2 inputs contract the last axis."""
+    z = x @ w + b
+    y, ln_cache = layer_norm_fwd(z, gamma, beta)
+    return np.maximum(y, 0.0), (x, y, ln_cache)
+
+
+def fc_ln_relu_bwd(dh, w, gamma, cache, need_dx=True):
+    x, y, ln_cache = cache
+    dy = dh * (y > 0)
+    dz, dgamma, dbeta = layer_norm_bwd(dy, gamma, ln_cache)
+    x2 = x.reshape(-1, x.shape[-1])
+    dz2 = dz.reshape(-1, dz.shape[-1])
+    dw = x2.T @ dz2
+    db = dz2.sum(axis=0)
+    dx = dz @ w.T if need_dx else None
+    return dx, dw, db, dgamma, dbeta
+
+
+# ------------------------------------------------------------------------------------------------
+# GRU: tf.contrib.rnn.GRUCell under tf.nn.dynamic_rnn(sequence_length)  (vlmap/modules.py:131-135)
+# gates = sigmoid([x, h] Wg + bg), split (r, u); c = tanh([x, r*h] Wc + bc); h' = u*h + (1-u)*c;
+# for t >= len the state is copied through. Zero initial state.            SURVEY Q5
+# ------------------------------------------------------------------------------------------------
+def gru_fwd(E, q_len, Wg, bg, Wc, bc):
+    B, T, W = E.shape
+    L = Wc.shape[1]
+    h = np.zeros((B, L))
+    steps = []
+    for t in range(T):
+        x = E[:, t, :]
+        g = np.concatenate([x, h], axis=1) @ Wg + bg
+        r, u = sigmoid(g[:, :L]), sigmoid(g[:, L:])
+        rh = r * h
+        c = np.tanh(np.concatenate([x, rh], axis=1) @ Wc + bc)
+        hn = u * h + (1.0 - u) * c
+        valid = (t < q_len)[:, None]
+        steps.append((x, h, r, u, rh, c, valid))
+        h = np.where(valid, hn, h)
+    return h, steps
+
+
+def gru_bwd(dq, steps, Wg, Wc, W):
+    L = Wc.shape[1]
+    dWg = np.zeros_like(Wg)
+    dbg = np.zeros(Wg.shape[1])
+    dWc = np.zeros_like(Wc)
+    dbc = np.zeros(Wc.shape[1])
+    dh = dq.copy()
+    dE = []
+    for (x, h, r, u, rh, c, valid) in reversed(steps):
+        dhn = np.where(valid, dh, 0.0)        # gradient reaching h' (only valid steps used it)
+        dh_prev = np.where(valid, 0.0, dh)    # copied-through state
+        du = dhn * (h - c)
+        dc = dhn * (1.0 - u)
+        dh_prev = dh_prev + dhn * u
+        dcp = dc * (1.0 - c * c)
+        xc = np.concatenate([x, rh], axis=1)
+        dWc += xc.T @ dcp
+        dbc += dcp.sum(axis=0)
+        dxc = dcp @ Wc.T
+        dx = dxc[:, :W]
+        drh = dxc[:, W:]
+        dr = drh * h
+        dh_prev = dh_prev + drh * r
+        dg = np.concatenate([dr * r * (1.0 - r), du * u * (1.0 - u)], axis=1)
+        xg = np.concatenate([x, h], axis=1)
+        dWg += xg.T @ dg
+        dbg += dg.sum(axis=0)
+        dxg = dg @ Wg.T
+        dx = dx + dxg[:, :W]
+        dh_prev = dh_prev + dxg[:, W:]
+        dE.append(dx)
+        dh = dh_prev
+    dE = np.stack(dE[::-1], axis=1)  # [B, T, W]
+    return dE, dWg, dbg, dWc, dbc
+
+
+# ------------------------------------------------------------------------------------------------
+# loss + metrics (vqa/model_vlmap_answer.py:192-288)
+# ------------------------------------------------------------------------------------------------
+def bce_with_logits(x, z):
+    """tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x*z + log(1 + exp(-|x|))"""
+    return np.maximum(x, 0.0) - x * z + np.log1p(np.exp(-np.abs(x)))
+
+
+def answer_masks(A, num_train_answer, is_object, is_attribute, answer_exist):
+    tm = (np.arange(A) < num_train_answer).astype(np.float64)  # tf.sequence_mask, :39-42
+    return {"train": tm, "test": 1.0 - tm, "obj": np.asarray(is_object, np.float64),
+            "attr": np.asarray(is_attribute, np.float64), "exist": np.asarray(answer_exist, np.float64)}
+
+
+def _normal(num, den):
+    # tf.where(tf.equal(den, 0), den, num / den)
+    return den if den == 0 else num / den
+
+
+def metrics(logit, target, m, use_train_mask=True):
+    """returns (train_loss, report dict, per-sample dict, pred)"""
+    B, A = logit.shape
+    loss = bce_with_logits(logit, target)
+    tmask = m["train"] if use_train_mask else np.ones(A)
+    train_loss = (loss * tmask).sum(axis=1).mean()
+    report_loss = loss.sum(axis=1).mean()
+    pred = np.argmax(logit, axis=1).astype(np.int32)  # first maximal index (tf.argmax)
+    oh = np.zeros((B, A))
+    oh[np.arange(B), pred] = 1.0
+    te, ob, at, ex, tm = m["test"], m["obj"], m["attr"], m["exist"], m["train"]
+    ps = {
+        "all_score": (oh * target).sum(1),
+        "max_train_score": (target * tm).max(1),
+        "test_obj_score": (oh * target * te * ob).sum(1),
+        "test_obj_max_score": (target * te * ob).max(1),
+        "test_attr_score": (oh * target * te * at).sum(1),
+        "test_attr_max_score": (target * te * at).max(1),
+    }
+    acc = ps["all_score"].mean()
+    exist_acc = (oh * target * ex).sum(1).mean()
+    test_acc = (oh * target * te).sum(1).mean()
+    test_obj_acc = ps["test_obj_score"].mean()
+    test_attr_acc = ps["test_attr_score"].mean()
+    train_exist_acc = (oh * target * ex * tm).sum(1).mean()
+    max_exist = (target * ex).max(1).mean()
+    max_train_exist = (target * ex * tm).max(1).mean()
+    test_obj_max = ps["test_obj_max_score"].mean()
+    test_attr_max = ps["test_attr_max_score"].mean()
+    test_max = (target * te).max(1).mean()
+    test_max_exist = (target * ex * te).max(1).mean()
+    if use_train_mask:
+        report = {"answer_train_loss": train_loss, "answer_report_loss": report_loss}
+    else:  # model_standard reports a single loss (vqa/model_standard.py:283-285, 362)
+        report = {"answer_train_loss": train_loss, "answer_report_loss": report_loss}
+    report.update({
+        "answer_acc": acc, "exist_acc": exist_acc, "test_acc": test_acc,
+        "normal_test_acc": _normal(test_acc, test_max),
+        "normal_test_object_acc": _normal(test_obj_acc, test_obj_max),
+        "normal_test_attribute_acc": _normal(test_attr_acc, test_attr_max),
+        "normal_exist_acc": _normal(exist_acc, max_exist),
+        "normal_train_exist_acc": _normal(train_exist_acc, max_train_exist),
+        "max_exist_acc": max_exist, "test_max_acc": test_max, "test_max_exist_acc": test_max_exist,
+    })
+    return train_loss, report, ps, pred
+
+
+# ------------------------------------------------------------------------------------------------
+# the graph
+# ------------------------------------------------------------------------------------------------
+def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0.8, keep_joint=0.5,
+            att_mask=None, joint_mask=None):
+    """Model.build() forward. p: dict field -> fp64 array (TF layout [in,out]).
+    features [N,K,Dv], num_boxes [N]; batch: image_idx [B], q_intseq [B,T], q_intseq_len [B],
+    answer_target [B,A]; att_mask [B,K,D] / joint_mask [B,J] are the 0/1 keep masks tf.nn.dropout
+    would have drawn (None = keep everything but still scale by 1/keep as TF does with a mask of 1s).
+    Returns (outputs dict, cache for backward)."""
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    p = {k: f64(v) for k, v in p.items()}
+    idx = np.asarray(batch["image_idx"])
+    V = f64(features)[idx]                                   # model_vlmap_answer.py:110-117
+    nbox = np.asarray(num_boxes)[idx].astype(np.int64)       # :118-119
+    q_ids = np.asarray(batch["q_intseq"])
+    q_len = np.asarray(batch["q_intseq_len"])
+    target = f64(batch["answer_target"])
+    B, K, Dv = V.shape
+    W = p["embed"].shape[1]
+
+    Hv, v_cache = fc_ln_relu_fwd(V, p["v_w"], p["v_b"], p["v_gamma"], p["v_beta"])   # :126-129 (LN over K*D)
+    E = p["embed"][q_ids]                                                            # :134
+    q, gru_steps = gru_fwd(E, q_len, p["gru_gates_w"], p["gru_gates_b"], p["gru_cand_w"], p["gru_cand_b"])
+    Hq, q_cache = fc_ln_relu_fwd(q, p["qv_w"], p["qv_b"], p["qv_gamma"], p["qv_beta"])  # :142-145
+
+    # hadamard_attention (modules.py:80-97)
+    D = Hv.shape[-1]
+    am = np.ones((B, K, D)) if att_mask is None else f64(att_mask)
+    F = Hv * Hq[:, None, :] * am / keep_att                  # tf.nn.dropout(score_feat, 0.8)
+    s = F @ p["att_w"].reshape(D) + p["att_b"].reshape(())
+    box_valid = np.arange(K)[None, :] < nbox[:, None]        # tf.sequence_mask
+    s = np.where(box_valid, s, -np.inf)
+    smax = s.max(axis=1, keepdims=True)
+    e = np.exp(s - smax)
+    a = e / e.sum(axis=1, keepdims=True)                     # exact zeros at masked slots
+    P = np.einsum("bk,bkd->bd", a, V)                        # attention_pooling of the RAW features
+
+    Hp, p_cache = fc_ln_relu_fwd(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"])  # :163-167
+    Hl, l_cache = fc_ln_relu_fwd(q, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"])  # :170-174
+    X = Hp * Hl
+    Jn, j_cache = fc_ln_relu_fwd(X, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
+    jm = np.ones_like(Jn) if joint_mask is None else f64(joint_mask)
+    Jd = Jn * jm / keep_joint                                # :180
+    logit = Jd @ p["ans_w"] + p["ans_b"]                     # :183-185 / model_standard.py:272-275
+
+    use_tm = variant != "standard"
+    train_loss, report, ps, pred = metrics(logit, target, m, use_train_mask=use_tm)
+    out = {"loss": train_loss, "report": report, "att_score": a, "logit": logit, "pred": pred,
+           "per_sample": ps, "condition": q, "pooled": P}
+    cache = dict(V=V, nbox=nbox, q_ids=q_ids, q_len=q_len, target=target, v_cache=v_cache, Hv=Hv,
+                 gru_steps=gru_steps, q=q, q_cache=q_cache, Hq=Hq, am=am, F=F, a=a, P=P, p_cache=p_cache,
+                 Hp=Hp, l_cache=l_cache, Hl=Hl, X=X, j_cache=j_cache, jm=jm, Jd=Jd, logit=logit,
+                 keep_att=keep_att, keep_joint=keep_joint, use_tm=use_tm, m=m, W=W, p=p)
+    return out, cache
+
+
+def backward(cache, loss_scale=1.0):
+    """Gradients of loss_scale * train_loss w.r.t. every parameter (dict field -> array).
+    Callers drop the frozen ones (trainable_fields)."""
+    c = cache
+    p = c["p"]
+    B, A = c["logit"].shape
+    tmask = c["m"]["train"] if c["use_tm"] else np.ones(A)
+    g = {}
+    dx = (sigmoid(c["logit"]) - c["target"]) * tmask / B * loss_scale
+    g["ans_w"] = c["Jd"].T @ dx
+    g["ans_b"] = dx.sum(0)
+    dJd = dx @ p["ans_w"].T
+    dJn = dJd * c["jm"] / c["keep_joint"]
+    dX, g["joint_w"], g["joint_b"], g["joint_gamma"], g["joint_beta"] = fc_ln_relu_bwd(
+        dJn, p["joint_w"], p["joint_gamma"], c["j_cache"])
+    dHp, dHl = dX * c["Hl"], dX * c["Hp"]
+    dP, g["pl_w"], g["pl_b"], g["pl_gamma"], g["pl_beta"] = fc_ln_relu_bwd(
+        dHp, p["pl_w"], p["pl_gamma"], c["p_cache"])
+    dq, g["ql_w"], g["ql_b"], g["ql_gamma"], g["ql_beta"] = fc_ln_relu_bwd(
+        dHl, p["ql_w"], p["ql_gamma"], c["l_cache"])
+    # attention pooling + softmax + score
+    V, a = c["V"], c["a"]
+    da = np.einsum("bkd,bd->bk", V, dP)
+    ds = a * (da - (a * da).sum(axis=1, keepdims=True))      # masked slots: a = 0 -> ds = 0
+    D = c["Hv"].shape[-1]
+    w = p["att_w"].reshape(D)
+    g["att_b"] = np.array([ds.sum()])
+    g["att_w"] = np.einsum("bk,bkd->d", ds, c["F"]).reshape(D, 1)
+    dF = ds[:, :, None] * w[None, None, :] * c["am"] / c["keep_att"]
+    dHv = dF * c["Hq"][:, None, :]
+    dHq = (dF * c["Hv"]).sum(axis=1)
+    _, g["v_w"], g["v_b"], g["v_gamma"], g["v_beta"] = fc_ln_relu_bwd(
+        dHv, p["v_w"], p["v_gamma"], c["v_cache"], need_dx=False)   # V is data: no dV
+    dq2, g["qv_w"], g["qv_b"], g["qv_gamma"], g["qv_beta"] = fc_ln_relu_bwd(
+        dHq, p["qv_w"], p["qv_gamma"], c["q_cache"])
+    dq = dq + dq2
+    dE, g["gru_gates_w"], g["gru_gates_b"], g["gru_cand_w"], g["gru_cand_b"] = gru_bwd(
+        dq, c["gru_steps"], p["gru_gates_w"], p["gru_cand_w"], c["W"])
+    demb = np.zeros_like(p["embed"])
+    np.add.at(demb, c["q_ids"], dE)                          # gradient of embedding_lookup
+    g["embed"] = demb
+    return g
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer (vqa/trainer.py:106-114): clip_by_global_norm(20) over train vars, then Adam
+# ------------------------------------------------------------------------------------------------
+def clip_adam_step(params, grads, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=20.0):
+    """params/grads/m/v: dict field -> array over the trainable set; t = 1-based step. In place."""
+    gnorm = np.sqrt(sum(float((g ** 2).sum()) for g in grads.values()))
+    scale = clip / max(gnorm, clip)
+    lr_t = lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
+    for k in grads:
+        g = grads[k] * scale
+        m[k] = beta1 * m[k] + (1.0 - beta1) * g
+        v[k] = beta2 * v[k] + (1.0 - beta2) * g * g
+        params[k] = params[k] - lr_t * m[k] / (np.sqrt(v[k]) + eps)
+    return gnorm

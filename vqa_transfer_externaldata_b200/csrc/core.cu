@@ -1,0 +1,250 @@
+// Handle lifecycle, error plumbing, workspace plan and the per-kernel C-ABI entry points.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "handle.h"
+#include "internal.h"
+
+namespace vqa {
+
+namespace {
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+}  // namespace
+
+VqaStatus set_error(VqaStatus code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+VqaStatus set_cuda_error(cudaError_t e, const char* what) {
+  snprintf(g_err, sizeof(g_err), "CUDA error %d (%s) in %s", static_cast<int>(e),
+           cudaGetErrorString(e), what);
+  return VQA_ERR_CUDA;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+
+struct Bump {
+  uint8_t* base;
+  uint64_t off = 0;
+  template <typename T>
+  T* take(uint64_t count) {
+    off = (off + 255) & ~static_cast<uint64_t>(255);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += count * sizeof(T);
+    return p;
+  }
+};
+
+}  // namespace
+
+uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
+  const VqaConfig& c = h->cfg;
+  const uint64_t B = c.B, K = c.K, Dv = c.Dv, D = c.D, L = c.L, J = c.J, A = c.A, T = c.T, W = c.W;
+  const uint64_t Wp = h->Wpad;
+  const bool two = h->planes == 2;
+  Bump a{base};
+  Buffers& b = h->buf;
+  auto planes = [&](Planes& p, uint64_t n) {
+    p.hi = a.take<bf16>(n);
+    p.lo = two ? a.take<bf16>(n) : nullptr;
+  };
+  planes(b.w.v_w, Dv * D);
+  planes(b.w.gru_gates_w, (W + L) * 2 * L);
+  planes(b.w.gru_cand_w, (W + L) * L);
+  planes(b.w.qv_w, L * D);
+  planes(b.w.pl_w, Dv * L);
+  planes(b.w.ql_w, L * L);
+  planes(b.w.joint_w, L * J);
+  planes(b.w.ans_w, J * A);
+
+  planes(b.v, B * K * Dv);
+  b.nbox = a.take<int>(B);
+  planes(b.e, T * B * Wp);
+  b.z = two ? static_cast<void*>(a.take<float>(B * K * D)) : static_cast<void*>(a.take<bf16>(B * K * D));
+  b.z_planes = Planes();
+  b.lnv_mean = a.take<float>(B);
+  b.lnv_rstd = a.take<float>(B);
+
+  b.xg = a.take<float>(T * B * 2 * L);
+  b.xc = a.take<float>(T * B * L);
+  b.g_pre = a.take<float>(B * 2 * L);
+  b.c_pre = a.take<float>(B * L);
+  b.h_f32 = a.take<float>((T + 1) * B * L);
+  planes(b.h, (T + 1) * B * L);
+  planes(b.rh, T * B * L);
+  b.r = a.take<float>(T * B * L);
+  b.u = a.take<float>(T * B * L);
+  b.c = a.take<float>(T * B * L);
+
+  b.zq = a.take<float>(B * D); b.hq = a.take<float>(B * D);
+  b.lnq_mean = a.take<float>(B); b.lnq_rstd = a.take<float>(B);
+  b.zl = a.take<float>(B * L); b.hl = a.take<float>(B * L);
+  b.lnl_mean = a.take<float>(B); b.lnl_rstd = a.take<float>(B);
+  b.att = a.take<float>(B * K);
+  b.pooled = a.take<float>(B * Dv);
+  planes(b.pooled_op, B * Dv);
+  b.zp = a.take<float>(B * L); b.hp = a.take<float>(B * L);
+  b.lnp_mean = a.take<float>(B); b.lnp_rstd = a.take<float>(B);
+  planes(b.x, B * L);
+  b.zj = a.take<float>(B * J);
+  b.lnj_mean = a.take<float>(B); b.lnj_rstd = a.take<float>(B);
+  planes(b.jd, B * J);
+  b.logit = a.take<float>(B * A);
+  b.pred = a.take<int>(B);
+  b.per_sample = a.take<float>(VQA_NUM_PER_SAMPLE * B);
+  b.report = a.take<float>(VQA_NUM_REPORT);
+  b.loss = a.take<float>(1);
+
+  b.dlogit_f32 = a.take<float>(B * A);
+  planes(b.dlogit, B * A);
+  b.dJ = a.take<float>(B * J);
+  b.dzj_f32 = a.take<float>(B * J);
+  planes(b.dzj, B * J);
+  b.dX = a.take<float>(B * L);
+  b.dzp_f32 = a.take<float>(B * L);
+  planes(b.dzp, B * L);
+  b.dzl_f32 = a.take<float>(B * L);
+  planes(b.dzl, B * L);
+  b.dP = a.take<float>(B * Dv);
+  b.dq = a.take<float>(B * L);
+  b.dhq = a.take<float>(B * D);
+  b.dzq_f32 = a.take<float>(B * D);
+  planes(b.dzq, B * D);
+  planes(b.dzv, B * K * D);
+  b.attn_part = a.take<float>(attn_bwd_partial_floats(static_cast<int>(B), static_cast<int>(D)));
+  b.dh[0] = a.take<float>(B * L);
+  b.dh[1] = a.take<float>(B * L);
+  b.du = a.take<float>(B * L);
+  b.dh_part = a.take<float>(B * L);
+  b.dRH = a.take<float>(B * L);
+  b.dC_f32 = a.take<float>(T * B * L);
+  planes(b.dC, T * B * L);
+  b.dG_f32 = a.take<float>(T * B * 2 * L);
+  planes(b.dG, T * B * 2 * L);
+  b.dE = a.take<float>(T * B * Wp);
+  uint64_t maxn = D > L ? D : L;
+  if (J > maxn) maxn = J;
+  b.ln_part_g = a.take<float>(B * maxn);
+  b.ln_part_b = a.take<float>(B * maxn);
+  uint64_t maxc = 3 * L;
+  if (A > maxc) maxc = A;
+  if (J > maxc) maxc = J;
+  if (Dv > maxc) maxc = Dv;
+  b.scratch_floats = 32 * maxc + 16 * B + 4096;
+  b.scratch = a.take<float>(b.scratch_floats);
+  return (a.off + 255) & ~static_cast<uint64_t>(255);
+}
+
+}  // namespace vqa
+
+using namespace vqa;
+
+extern "C" {
+
+VQA_API int32_t vqa_abi_version(void) { return 1; }
+
+VQA_API const char* vqa_last_error(void) { return g_err; }
+
+VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
+  if (!config || !out) return set_error(VQA_ERR_BAD_ARG, "vqa_create: null argument");
+  const VqaConfig& c = *config;
+  if (c.B <= 0 || c.K <= 0 || c.T <= 0 || c.A <= 0 || c.W <= 0 || c.Vq <= 0)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: non-positive dimension");
+  if ((c.Dv & 7) || (c.D & 7) || (c.L & 7) || (c.J & 7) || (c.A & 7))
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: Dv, D, L, J, A must be multiples of 8");
+  if (c.D > 4096 || c.L > 4096 || c.J > 4096 || c.K > 256 || c.T > 64)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: D, L, J <= 4096; K <= 256; T <= 64");
+  if (c.variant != VQA_VARIANT_VLMAP_ANSWER && c.variant != VQA_VARIANT_STANDARD)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown variant %d", c.variant);
+  if (c.precision != VQA_PREC_BF16 && c.precision != VQA_PREC_FP32)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown precision %d", c.precision);
+  if (!(c.keep_att > 0.f && c.keep_att <= 1.f) || !(c.keep_joint > 0.f && c.keep_joint <= 1.f))
+    return set_error(VQA_ERR_BAD_ARG, "vqa_create: keep probabilities must be in (0, 1]");
+  if (c.num_train_answer < 0 || c.num_train_answer > c.A)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_create: num_train_answer out of range");
+
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return set_error(VQA_ERR_NO_DEVICE, "vqa_create: no CUDA device (this library has no CPU path)");
+  }
+  int dev = 0;
+  VQA_CUDA_CHECK(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  VQA_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+  if (prop.major != 10)
+    return set_error(VQA_ERR_NO_DEVICE, "vqa_create: device %d is sm_%d%d; this library is sm_100a only",
+                     dev, prop.major, prop.minor);
+
+  VqaHandle_t* h = new (std::nothrow) VqaHandle_t();
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_create: out of host memory");
+  h->cfg = c;
+  h->device = dev;
+  h->num_sms = prop.multiProcessorCount;
+  h->Wpad = (c.W + 7) & ~7;
+  h->planes = c.precision == VQA_PREC_FP32 ? 2 : 1;
+  h->ws = nullptr;
+  h->ws_bytes = 0;
+  h->params_ready = false;
+  h->fwd_valid = false;
+  h->ws_needed = plan_workspace(h, nullptr);
+  *out = h;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_destroy(VqaHandle h) {
+  delete h;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_workspace_bytes(VqaHandle h, uint64_t* bytes) {
+  if (!h || !bytes) return set_error(VQA_ERR_BAD_ARG, "vqa_workspace_bytes: null argument");
+  *bytes = h->ws_needed;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes) {
+  if (!h || !dev_ptr) return set_error(VQA_ERR_BAD_ARG, "vqa_set_workspace: null argument");
+  if (reinterpret_cast<uintptr_t>(dev_ptr) & 255)
+    return set_error(VQA_ERR_WORKSPACE, "vqa_set_workspace: pointer must be 256-byte aligned");
+  if (bytes < h->ws_needed)
+    return set_error(VQA_ERR_WORKSPACE, "vqa_set_workspace: %llu bytes given, %llu needed",
+                     static_cast<unsigned long long>(bytes),
+                     static_cast<unsigned long long>(h->ws_needed));
+  h->ws = dev_ptr;
+  h->ws_bytes = bytes;
+  plan_workspace(h, static_cast<uint8_t*>(dev_ptr));
+  h->params_ready = false;
+  h->fwd_valid = false;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_gemm(VqaHandle h, const VqaGemmDesc* d, void* stream) {
+  if (!h || !d) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: null argument");
+  return gemm_launch(*d, h->num_sms, static_cast<cudaStream_t>(stream));
+}
+
+VQA_API VqaStatus vqa_split_bf16(VqaHandle h, const float* src, int64_t rows, int64_t cols, int64_t ld,
+                                 void* hi, void* lo, int64_t ld_out, void* stream) {
+  if (!h || !src || !hi) return set_error(VQA_ERR_BAD_ARG, "vqa_split_bf16: null argument");
+  return split_bf16_launch(src, rows, cols, ld, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ld_out,
+                           static_cast<cudaStream_t>(stream));
+}
+
+/* number of kernels this library has enqueued in this process (bench.py's gpu_launches) */
+VQA_API uint64_t vqa_launch_count(void) { return launch_count(); }
+
+}  // extern "C"

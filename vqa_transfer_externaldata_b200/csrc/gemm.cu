@@ -1,0 +1,431 @@
+// tcgen05 / TMEM / TMA GEMM for the dense contractions of the answer model
+// (layers.fully_connected call sites: vlmap/modules.py:616-626, 634-641; GRUCell matmuls :131-135;
+//  and their dgrad / wgrad counterparts that tf.gradients derives).
+//
+//   D[M,N] = A[M,K] * B[N,K]^T  (+ bias[N]) (+ addend[M,N])      fp32 accumulation in TMEM
+//
+// * operands are bf16 planes. PREC_BF16: one plane per operand. PREC_FP32: two planes (hi, lo) per
+//   operand and three MMAs per k-step (hi*hi + hi*lo + lo*hi) -> ~2^-16 relative operand error.
+// * each operand may be stored K-major (contraction index contiguous) or MN-major (contraction index
+//   strided) -- forward uses TF's [in,out] weights as MN-major B, dgrad uses the same buffer as
+//   K-major B, wgrad uses activations as MN-major A and B. No transposed copies exist anywhere.
+// * one 128 x BN output tile per CTA; warp 0 = TMA producer, warp 1 = TMEM owner + MMA issuer,
+//   warps 2..5 = epilogue (TMEM -> registers -> shared staging -> coalesced 128-bit global stores).
+//   Two CTAs co-reside per SM (<= 113 KB shared, <= 256 TMEM columns each), so one CTA's epilogue
+//   overlaps the other's main loop.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <mutex>
+#include <unordered_map>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace vqa {
+
+namespace {
+
+constexpr int BM = 128;  // UMMA M (cta_group::1)
+constexpr int BK = 64;   // 64 bf16 = 128 bytes = one SWIZZLE_128B row
+constexpr int UMMA_K = 16;
+constexpr int GEMM_THREADS = 192;
+
+struct EpilogueArgs {
+  const float* bias;
+  const float* addend;
+  long long ld_addend;
+  float* out_f32;
+  long long ld_f32;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  long long ld_bf;
+};
+
+template <int BN, int SPLIT>
+struct GemmCfg {
+  static constexpr int A_TILE = BM * BK * 2;                 // bytes per plane
+  static constexpr int B_TILE = BN * BK * 2;
+  static constexpr int PLANES = (SPLIT == 3) ? 2 : 1;
+  static constexpr int STAGE_BYTES = PLANES * (A_TILE + B_TILE);
+  // keep <= ~110 KB for the bf16 path so two CTAs fit one SM; the split path takes the SM alone
+  static constexpr int STAGES = (SPLIT == 3) ? (BN == 256 ? 2 : 3)
+                                             : (BN == 256 ? 4 : (BN == 128 ? 3 : 4));
+  static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
+  static constexpr int STG_LD = BN + 4;                      // floats, padded staging row
+  static constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;  // 4 epilogue warps x 32 rows
+  static constexpr int MAIN_BYTES = PIPE_BYTES > STAGING_BYTES ? PIPE_BYTES : STAGING_BYTES;
+  static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+template <int BN, int SPLIT, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
+    const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+    const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+    EpilogueArgs ep, int M, int N, int K) {
+  using Cfg = GemmCfg<BN, SPLIT>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::MAIN_BYTES);
+  uint64_t* empty_bar = full_bar + Cfg::STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Cfg::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m0 = blockIdx.y * BM;
+  const int n0 = blockIdx.x * BN;
+  const int num_kb = (K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a_hi);
+    ptx::prefetch_tensormap(&tm_b_hi);
+    if (SPLIT == 3) {
+      ptx::prefetch_tensormap(&tm_a_lo);
+      ptx::prefetch_tensormap(&tm_b_lo);
+    }
+    for (int s = 0; s < Cfg::STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, BN);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        const int k0 = kb * BK;
+#pragma unroll
+        for (int p = 0; p < Cfg::PLANES; ++p) {
+          const CUtensorMap* ta = p ? &tm_a_lo : &tm_a_hi;
+          const CUtensorMap* tb = p ? &tm_b_lo : &tm_b_hi;
+          uint8_t* sa = st + p * Cfg::A_TILE;
+          uint8_t* sb = st + Cfg::PLANES * Cfg::A_TILE + p * Cfg::B_TILE;
+          if (A_MN) {
+            // stored [K, M]: box = 64 (m) x 64 (k); two boxes cover 128 m
+            ptx::tma_load_2d(sa, ta, &full_bar[stage], m0, k0);
+            ptx::tma_load_2d(sa + 8192, ta, &full_bar[stage], m0 + 64, k0);
+          } else {
+            // stored [M, K]: box = 64 (k) x 128 (m)
+            ptx::tma_load_2d(sa, ta, &full_bar[stage], k0, m0);
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int j = 0; j < BN / 64; ++j)
+              ptx::tma_load_2d(sb + j * 8192, tb, &full_bar[stage], n0 + 64 * j, k0);
+          } else {
+            ptx::tma_load_2d(sb, tb, &full_bar[stage], k0, n0);
+          }
+        }
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
+      // K-major: 8-row groups are 1024 B apart (SBO); a K=16 step advances 32 B inside the row.
+      // MN-major: 8-k groups are 1024 B apart (SBO); 64-element MN chunks are 8192 B apart (LBO);
+      //           a K=16 step advances two 8-k groups = 2048 B.
+      constexpr uint32_t A_LBO = A_MN ? 8192 : 16, A_STEP = A_MN ? 2048 : 32;
+      constexpr uint32_t B_LBO = B_MN ? 8192 : 16, B_STEP = B_MN ? 2048 : 32;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < num_kb; ++kb) {
+        ptx::mbar_wait(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t st = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+        const uint32_t sa_hi = st, sa_lo = st + Cfg::A_TILE;
+        const uint32_t sb_hi = st + Cfg::PLANES * Cfg::A_TILE, sb_lo = sb_hi + Cfg::B_TILE;
+#pragma unroll
+        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+          const uint64_t da_hi = ptx::make_smem_desc_sw128(sa_hi + kk * A_STEP, A_LBO, 1024);
+          const uint64_t db_hi = ptx::make_smem_desc_sw128(sb_hi + kk * B_STEP, B_LBO, 1024);
+          ptx::umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | kk) != 0);
+          if (SPLIT == 3) {
+            const uint64_t da_lo = ptx::make_smem_desc_sw128(sa_lo + kk * A_STEP, A_LBO, 1024);
+            const uint64_t db_lo = ptx::make_smem_desc_sw128(sb_lo + kk * B_STEP, B_LBO, 1024);
+            ptx::umma_f16(tmem_base, da_hi, db_lo, idesc, 1);
+            ptx::umma_f16(tmem_base, da_lo, db_hi, idesc, 1);
+          }
+        }
+        ptx::umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+        if (++stage == Cfg::STAGES) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+      ptx::umma_commit(tmem_full_bar);  // accumulator complete
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    // a warp may only touch TMEM lanes [32*(warp%4), +32)
+    const int q = warp & 3;
+    ptx::mbar_wait(tmem_full_bar, 0);
+    ptx::tc_fence_after();
+    // all MMAs have retired => pipeline smem is free: reuse it as staging
+    float* stg = reinterpret_cast<float*>(smem) + q * 32 * Cfg::STG_LD;
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t v[32];
+      ptx::tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + c, v);
+      ptx::tmem_ld_wait();
+      float4* dst = reinterpret_cast<float4*>(stg + lane * Cfg::STG_LD + c);
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+    }
+    __syncwarp();
+    // coalesced write-out: the warp walks its 32 rows; lanes cover 4 consecutive columns each
+    for (int r = 0; r < 32; ++r) {
+      const int row = m0 + q * 32 + r;
+      if (row >= M) break;
+#pragma unroll
+      for (int c4 = lane * 4; c4 < BN; c4 += 128) {
+        const int col = n0 + c4;
+        if (col >= N) continue;  // N % 4 == 0 is enforced by the launcher
+        float4 x = *reinterpret_cast<const float4*>(stg + r * Cfg::STG_LD + c4);
+        if (ep.bias) {
+          const float4 b = *reinterpret_cast<const float4*>(ep.bias + col);
+          x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+        }
+        if (ep.addend) {
+          const float4 a =
+              *reinterpret_cast<const float4*>(ep.addend + static_cast<long long>(row) * ep.ld_addend + col);
+          x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+        }
+        if (ep.out_f32)
+          *reinterpret_cast<float4*>(ep.out_f32 + static_cast<long long>(row) * ep.ld_f32 + col) = x;
+        if (ep.out_hi) {
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y),
+                              h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
+          const long long o = static_cast<long long>(row) * ep.ld_bf + col;
+          __nv_bfloat162 p0(h0, h1), p1(h2, h3);
+          uint2 pk;
+          pk.x = *reinterpret_cast<uint32_t*>(&p0);
+          pk.y = *reinterpret_cast<uint32_t*>(&p1);
+          *reinterpret_cast<uint2*>(ep.out_hi + o) = pk;
+          if (ep.out_lo) {
+            __nv_bfloat162 q0(__float2bfloat16_rn(x.x - __bfloat162float(h0)),
+                              __float2bfloat16_rn(x.y - __bfloat162float(h1)));
+            __nv_bfloat162 q1(__float2bfloat16_rn(x.z - __bfloat162float(h2)),
+                              __float2bfloat16_rn(x.w - __bfloat162float(h3)));
+            pk.x = *reinterpret_cast<uint32_t*>(&q0);
+            pk.y = *reinterpret_cast<uint32_t*>(&q1);
+            *reinterpret_cast<uint2*>(ep.out_lo + o) = pk;
+          }
+        }
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) ==
+            cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch in elements
+bool make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
+                    uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+struct TmapKey {
+  const void* base;
+  uint64_t inner, outer, pitch;
+  uint32_t bi, bo;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && inner == o.inner && outer == o.outer && pitch == o.pitch &&
+           bi == o.bi && bo == o.bo;
+  }
+};
+struct TmapKeyHash {
+  size_t operator()(const TmapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    h = h * 1000003u ^ k.inner;
+    h = h * 1000003u ^ k.outer;
+    h = h * 1000003u ^ k.pitch;
+    h = h * 1000003u ^ (static_cast<size_t>(k.bi) << 16 | k.bo);
+    return h;
+  }
+};
+
+// descriptors are pure functions of (pointer, shape, box): cache them (encode costs ~1 us each)
+bool cached_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
+                 uint32_t bi, uint32_t bo) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{base, inner, outer, pitch, bi, bo};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  CUtensorMap tm;
+  if (!make_tmap_bf16(&tm, base, inner, outer, pitch, bi, bo)) return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return true;
+}
+
+template <int BN, int SPLIT, bool A_MN, bool B_MN>
+cudaError_t launch_one(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
+                       const CUtensorMap& tb_lo, const EpilogueArgs& ep, int M, int N, int K,
+                       cudaStream_t stream) {
+  using Cfg = GemmCfg<BN, SPLIT>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, SPLIT, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e =
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
+  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K);
+  return cudaGetLastError();
+}
+
+template <int BN, int SPLIT>
+cudaError_t launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
+                         const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, const EpilogueArgs& ep,
+                         int M, int N, int K, cudaStream_t s) {
+  if (a_mn) {
+    if (b_mn) return launch_one<BN, SPLIT, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+    return launch_one<BN, SPLIT, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+  }
+  if (b_mn) return launch_one<BN, SPLIT, false, true>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+  return launch_one<BN, SPLIT, false, false>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+}
+
+}  // namespace
+
+int pick_block_n(int M, int N, int num_sms) {
+  // fill the machine first: take the widest tile that still yields >= one CTA per SM
+  const long long tm = (M + BM - 1) / BM;
+  for (int bn : {256, 128}) {
+    const long long tiles = tm * ((N + bn - 1) / bn);
+    if (tiles >= num_sms) return bn;
+  }
+  return 64;
+}
+
+VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream) {
+  if (!d.a_hi || !d.b_hi) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: null operand");
+  if (d.M <= 0 || d.N <= 0 || d.K <= 0) return set_error(VQA_ERR_BAD_SHAPE, "vqa_gemm: empty problem");
+  if ((d.N & 3) || (d.lda & 7) || (d.ldb & 7))
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_gemm: N %% 4, lda %% 8, ldb %% 8 must be 0");
+  if ((d.out_f32 && (d.ld_f32 & 3)) || (d.out_hi && (d.ld_bf & 3)) || (d.addend && (d.ld_addend & 3)))
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_gemm: output pitches must be multiples of 4");
+  const bool split = (d.a_lo != nullptr) || (d.b_lo != nullptr);
+  if (split && (!d.a_lo || !d.b_lo))
+    return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: split precision needs both lo planes");
+  int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, num_sms);
+  if (split && bn == 256) bn = 128;
+  if (bn != 64 && bn != 128 && bn != 256) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: block_n");
+
+  CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
+  bool ok = true;
+  auto map_a = [&](CUtensorMap* tm, const void* p) {
+    return d.a_mn_major ? cached_tmap(tm, p, d.M, d.K, d.lda, 64, 64)
+                        : cached_tmap(tm, p, d.K, d.M, d.lda, 64, BM);
+  };
+  auto map_b = [&](CUtensorMap* tm, const void* p) {
+    return d.b_mn_major ? cached_tmap(tm, p, d.N, d.K, d.ldb, 64, 64)
+                        : cached_tmap(tm, p, d.K, d.N, d.ldb, 64, bn);
+  };
+  ok = ok && map_a(&ta_hi, d.a_hi) && map_b(&tb_hi, d.b_hi);
+  if (split) {
+    ok = ok && map_a(&ta_lo, d.a_lo) && map_b(&tb_lo, d.b_lo);
+  } else {
+    ta_lo = ta_hi;
+    tb_lo = tb_hi;
+  }
+  if (!ok) return set_error(VQA_ERR_CUDA, "vqa_gemm: cuTensorMapEncodeTiled failed");
+
+  EpilogueArgs ep;
+  ep.bias = d.bias;
+  ep.addend = d.addend;
+  ep.ld_addend = d.ld_addend;
+  ep.out_f32 = d.out_f32;
+  ep.ld_f32 = d.ld_f32;
+  ep.out_hi = static_cast<__nv_bfloat16*>(d.out_hi);
+  ep.out_lo = static_cast<__nv_bfloat16*>(d.out_lo);
+  ep.ld_bf = d.ld_bf;
+
+  cudaError_t e;
+  const bool amn = d.a_mn_major != 0, bmn = d.b_mn_major != 0;
+  if (split) {
+    if (bn == 64) e = launch_major<64, 3>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+    else e = launch_major<128, 3>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+  } else {
+    if (bn == 64) e = launch_major<64, 1>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+    else if (bn == 128) e = launch_major<128, 1>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+    else e = launch_major<256, 1>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+  }
+  if (e != cudaSuccess) return set_cuda_error(e, "vqa_gemm launch");
+  count_launch();
+  return VQA_OK;
+}
+
+}  // namespace vqa

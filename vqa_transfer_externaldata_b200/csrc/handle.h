@@ -1,0 +1,99 @@
+// The per-GPU handle: configuration + the carve-up of the caller-provided workspace.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+
+#include "internal.h"
+
+namespace vqa {
+
+// Weight shadows in GEMM-operand form, same [in, out] layout as the fp32 TF variables.
+struct WeightShadows {
+  Planes v_w, gru_gates_w, gru_cand_w, qv_w, pl_w, ql_w, joint_w, ans_w;
+};
+
+// Everything forward keeps for backward + scratch, all inside the workspace.
+struct Buffers {
+  WeightShadows w;
+  // inputs in operand form
+  Planes v;        // [B*K, Dv] gathered features
+  int* nbox;       // [B]
+  Planes e;        // [T*B, Wpad] embedded question tokens, time-major
+  // v-projection
+  void* z;         // [B*K, D] pre-LN projection: bf16 (PREC_BF16) / fp32 (PREC_FP32)
+  Planes z_planes; // PREC_FP32 only: unused (z is consumed by the attention kernels, not by GEMMs)
+  float* lnv_mean; float* lnv_rstd;  // [B]
+  // GRU
+  float* xg;       // [T*B, 2L]  x-part of the gate pre-activations (+ bias)
+  float* xc;       // [T*B, L]   x-part of the candidate pre-activation (+ bias)
+  float* g_pre;    // [B, 2L]
+  float* c_pre;    // [B, L]
+  float* h_f32;    // [(T+1)*B, L]   h_0 .. h_T
+  Planes h;        // [(T+1)*B, L]
+  Planes rh;       // [T*B, L]
+  float* r; float* u; float* c;  // [T*B, L] each
+  // heads
+  float* zq; float* hq; float* lnq_mean; float* lnq_rstd;       // q_linear_v
+  float* zl; float* hl; float* lnl_mean; float* lnl_rstd;       // q_linear_l
+  float* att;      // [B, K]
+  float* pooled;   // [B, Dv]
+  Planes pooled_op;
+  float* zp; float* hp; float* lnp_mean; float* lnp_rstd;       // pooled_linear_l
+  Planes x;        // [B, L]  hp (.) hl
+  float* zj; float* lnj_mean; float* lnj_rstd;                  // joint_fc
+  Planes jd;       // [B, J] after dropout
+  float* logit;    // [B, A]
+  int* pred;       // [B]
+  float* per_sample;  // [6, B]
+  float* report;   // [13]
+  float* loss;     // [1]
+  // backward
+  float* dlogit_f32; Planes dlogit;  // [B, A]
+  float* dJ;       // [B, J]
+  float* dzj_f32; Planes dzj;        // [B, J]
+  float* dX;       // [B, L]
+  float* dzp_f32; Planes dzp;        // [B, L]
+  float* dzl_f32; Planes dzl;        // [B, L]
+  float* dP;       // [B, Dv]
+  float* dq;       // [B, L]
+  float* dhq;      // [B, D]
+  float* dzq_f32; Planes dzq;        // [B, D]
+  Planes dzv;      // [B*K, D]
+  float* attn_part;  // per-CTA partial sums of the attention backward
+  float* dh[2];    // [B, L] ping-pong
+  float* du; float* dh_part; float* dRH;  // [B, L]
+  float* dC_f32; Planes dC;  // [T*B, L]
+  float* dG_f32; Planes dG;  // [T*B, 2L]
+  float* dE;       // [T*B, Wpad]
+  float* ln_part_g; float* ln_part_b;  // [B, max(D,L,J)] LayerNorm gamma/beta partials
+  float* scratch;  // column-sum / loss scratch
+  size_t scratch_floats;
+};
+
+}  // namespace vqa
+
+// global scope: this is the struct the C header forward-declares
+struct VqaHandle_t {
+  VqaConfig cfg;
+  int device;
+  int num_sms;
+  int Wpad;             // W rounded up to 8 (TMA pitch must be a multiple of 16 bytes)
+  int planes;           // 1 (bf16) or 2 (fp32 = hi + lo)
+  void* ws;
+  uint64_t ws_bytes;
+  uint64_t ws_needed;
+  vqa::Buffers buf;
+  bool params_ready;
+  // state of the last forward (what backward differentiates)
+  bool fwd_valid;
+  int last_batch, last_T;
+  uint64_t last_seed, last_step;
+  VqaAnswerMasks last_masks;
+};
+
+namespace vqa {
+
+// lays out `buf` inside [base, base + bytes); with base == nullptr only measures. Returns bytes used.
+uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base);
+
+}  // namespace vqa

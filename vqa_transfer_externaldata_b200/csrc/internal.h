@@ -1,0 +1,141 @@
+// Internal (non-ABI) declarations shared by the translation units of libvqa_answer_b200.so
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../../include/vqa_answer.h"
+
+namespace vqa {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- error plumbing (thread-local message, returned by vqa_last_error) ----
+VqaStatus set_error(VqaStatus code, const char* fmt, ...);
+VqaStatus set_cuda_error(cudaError_t e, const char* what);
+void count_launch();            // one of OUR kernels was enqueued
+unsigned long long launch_count();
+
+#define VQA_CUDA_CHECK(expr)                                         \
+  do {                                                               \
+    cudaError_t _e = (expr);                                         \
+    if (_e != cudaSuccess) return ::vqa::set_cuda_error(_e, #expr);  \
+  } while (0)
+
+#define VQA_TRY(expr)                     \
+  do {                                    \
+    VqaStatus _s = (expr);                \
+    if (_s != VQA_OK) return _s;          \
+  } while (0)
+
+#define VQA_LAUNCH_CHECK(what)                                       \
+  do {                                                               \
+    cudaError_t _e = cudaGetLastError();                             \
+    if (_e != cudaSuccess) return ::vqa::set_cuda_error(_e, what);   \
+    ::vqa::count_launch();                                           \
+  } while (0)
+
+// A GEMM operand / activation in "operand form": one bf16 plane (PREC_BF16) or hi+lo (PREC_FP32)
+struct Planes {
+  bf16* hi = nullptr;
+  bf16* lo = nullptr;
+};
+
+// ---- gemm.cu ----
+VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream);
+
+// ---- elementwise.cu ----
+VqaStatus split_bf16_launch(const float* src, long long rows, long long cols, long long ld, bf16* hi,
+                            bf16* lo, long long ld_out, cudaStream_t s);
+VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const long long* image_idx,
+                                 int batch, int K, int Dv, bf16* v_hi, bf16* v_lo, int* nbox,
+                                 cudaStream_t s);
+VqaStatus embed_gather_launch(const float* embed, const int* q_intseq, int batch, int T, int Tstride,
+                              int W, int Wpad, int Bpad, bf16* e_hi, bf16* e_lo, cudaStream_t s);
+VqaStatus embed_scatter_add_launch(const float* dE, long long ld_dE, const int* q_intseq,
+                                   const int* q_len, int batch, int T, int Tstride, int W, int Bpad,
+                                   float* d_embed, cudaStream_t s);
+VqaStatus colsum_launch(const float* x, long long rows, long long cols, long long ld, float* out,
+                        float* scratch, cudaStream_t s);
+VqaStatus fill_zero_launch(void* p, size_t bytes, cudaStream_t s);
+
+// GRU cell pieces (vlmap/modules.py:124-140; TF-1.6 GRUCell: gate order (r,u), c = tanh([x, r*h] Wc))
+VqaStatus gru_gates_launch(const float* G, const float* h, int batch, int L, float* r, float* u,
+                           bf16* rh_hi, bf16* rh_lo, cudaStream_t s);
+VqaStatus gru_update_launch(const float* C, const float* h, const float* u, const int* q_len, int t,
+                            int batch, int L, float* c_out, float* h_next, bf16* hn_hi, bf16* hn_lo,
+                            cudaStream_t s);
+VqaStatus gru_bwd_update_launch(const float* dh, const float* h, const float* u, const float* c,
+                                const int* q_len, int t, int batch, int L, float* du, float* dh_part,
+                                float* dC_f32, bf16* dC_hi, bf16* dC_lo, cudaStream_t s);
+VqaStatus gru_bwd_gates_launch(const float* dRH, const float* du, const float* h, const float* r,
+                               const float* u, const int* q_len, int t, int batch, int L,
+                               float* dh_part, float* dG_f32, bf16* dG_hi, bf16* dG_lo,
+                               cudaStream_t s);
+
+// ---- rows.cu: row LayerNorm + ReLU heads (modules.fc_layer with use_ln, vlmap/modules.py:630-650) ----
+struct RowLnFwd {
+  int rows, N;
+  const float* z;        // [rows, N] pre-LN (bias already added)
+  const float* gamma;    // [N]
+  const float* beta;     // [N]
+  const float* mul;      // optional [rows, N]: output *= mul (the q (.) v Hadamard fusion)
+  float keep;            // dropout keep prob on the output (1 = none)
+  unsigned long long seed, step;
+  unsigned int stream_id;
+  float* y;              // optional fp32 [rows, N]: relu(LN(z)) BEFORE mul / dropout
+  float* out_f32;        // optional fp32 final output
+  bf16* out_hi;          // optional operand planes of the final output
+  bf16* out_lo;
+  float* mean;           // [rows]
+  float* rstd;           // [rows]
+};
+VqaStatus row_ln_relu_fwd_launch(const RowLnFwd& a, cudaStream_t s);
+
+struct RowLnBwd {
+  int rows, N;
+  const float* dout;     // [rows, N] gradient w.r.t. the final output
+  const float* z;        // pre-LN
+  const float* gamma;
+  const float* beta;
+  const float* mean;
+  const float* rstd;
+  const float* mul;      // optional: forward multiplied the activation by this
+  float* dmul;           // optional: receives dout * y (gradient w.r.t. mul)
+  float keep;
+  unsigned long long seed, step;
+  unsigned int stream_id;
+  float* dz_f32;         // optional
+  bf16* dz_hi;
+  bf16* dz_lo;
+  float* dgamma_part;    // optional [parts, N] per-CTA partials (parts = rows)
+  float* dbeta_part;
+};
+VqaStatus row_ln_relu_bwd_launch(const RowLnBwd& a, cudaStream_t s);
+
+// ---- attn.cu ----
+VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precision, float keep,
+                          cudaStream_t s);
+VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precision, float keep,
+                          float* partials, cudaStream_t s);
+size_t attn_bwd_partial_floats(int batch, int D);
+
+// ---- loss.cu ----
+VqaStatus bce_metrics_launch(int batch, int A, int num_train_answer, int use_train_mask,
+                             const float* logit, const float* target, const VqaAnswerMasks& masks,
+                             float grad_scale, float* loss, float* report, int* pred,
+                             float* per_sample, float* d_logit_f32, bf16* d_hi, bf16* d_lo,
+                             float* scratch, cudaStream_t s);
+VqaStatus dropout_mask_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
+                              unsigned long long step, unsigned int stream_id, cudaStream_t s);
+
+// ---- optim.cu ----
+VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, long long n, float lr,
+                           float beta1, float beta2, float eps, float clip_norm, long long t,
+                           float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s);
+
+// RNG stream ids (which dropout site a Philox draw belongs to)
+enum { RNG_STREAM_ATT = 1, RNG_STREAM_JOINT = 2 };
+
+}  // namespace vqa

@@ -1,0 +1,151 @@
+"""ctypes binding of the C ABI declared in include/vqa_answer.h.
+
+The shared library is built in-tree by `build.py` (nvcc, sm_100a) and loaded with ctypes.CDLL, so it
+shows up in the process' loaded-library list. There is no fallback: if the library is missing,
+`load()` raises, and every compute entry point returns an error without a B200.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libvqa_answer_b200.so")
+
+# ---- status / enums (mirror include/vqa_answer.h) ----
+VQA_OK = 0
+VQA_ERR_BAD_ARG, VQA_ERR_BAD_SHAPE, VQA_ERR_WORKSPACE = -1, -2, -3
+VQA_ERR_CUDA, VQA_ERR_NO_DEVICE, VQA_ERR_STATE = -4, -5, -6
+VARIANT_VLMAP_ANSWER, VARIANT_STANDARD = 0, 1
+PREC_BF16, PREC_FP32 = 0, 1
+
+REPORT_KEYS = [
+    "answer_train_loss", "answer_report_loss", "answer_acc", "exist_acc", "test_acc",
+    "normal_test_acc", "normal_test_object_acc", "normal_test_attribute_acc", "normal_exist_acc",
+    "normal_train_exist_acc", "max_exist_acc", "test_max_acc", "test_max_exist_acc",
+]
+PER_SAMPLE_KEYS = [
+    "all_score", "max_train_score", "test_obj_score", "test_obj_max_score", "test_attr_score",
+    "test_attr_max_score",
+]
+
+PARAM_FIELDS = [
+    "embed", "v_w", "v_b", "v_gamma", "v_beta", "gru_gates_w", "gru_gates_b", "gru_cand_w",
+    "gru_cand_b", "qv_w", "qv_b", "qv_gamma", "qv_beta", "att_w", "att_b", "pl_w", "pl_b",
+    "pl_gamma", "pl_beta", "ql_w", "ql_b", "ql_gamma", "ql_beta", "joint_w", "joint_b",
+    "joint_gamma", "joint_beta", "ans_w", "ans_b",
+]
+
+
+class VqaError(RuntimeError):
+    def __init__(self, status, msg):
+        super().__init__(f"vqa_answer error {status}: {msg}")
+        self.status = status
+
+
+class VqaConfig(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in
+                ("B", "K", "Dv", "D", "L", "J", "A", "T", "W", "Vq", "num_train_answer", "variant",
+                 "precision")] + [("keep_att", C.c_float), ("keep_joint", C.c_float)]
+
+
+class VqaParams(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+
+
+class VqaFeatureBank(C.Structure):
+    _fields_ = [("features", C.c_void_p), ("num_boxes", C.c_void_p), ("num_images", C.c_int64)]
+
+
+class VqaBatch(C.Structure):
+    _fields_ = [("batch_size", C.c_int32), ("q_len_max", C.c_int32), ("image_idx", C.c_void_p),
+                ("q_intseq", C.c_void_p), ("q_intseq_len", C.c_void_p), ("answer_target", C.c_void_p)]
+
+
+class VqaAnswerMasks(C.Structure):
+    _fields_ = [("is_object", C.c_void_p), ("is_attribute", C.c_void_p), ("answer_exist", C.c_void_p)]
+
+
+class VqaOutputs(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in
+                ("loss", "report", "att_score", "logit", "pred", "per_sample", "condition", "pooled")]
+
+
+class VqaGemmDesc(C.Structure):
+    _fields_ = [("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("b_hi", C.c_void_p), ("b_lo", C.c_void_p),
+                ("lda", C.c_int64), ("ldb", C.c_int64), ("a_mn_major", C.c_int32),
+                ("b_mn_major", C.c_int32), ("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32),
+                ("bias", C.c_void_p), ("addend", C.c_void_p), ("ld_addend", C.c_int64),
+                ("out_f32", C.c_void_p), ("ld_f32", C.c_int64), ("out_hi", C.c_void_p),
+                ("out_lo", C.c_void_p), ("ld_bf", C.c_int64), ("block_n", C.c_int32)]
+
+
+class VqaAttnFwd(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("z", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("hq", C.c_void_p), ("att_w", C.c_void_p), ("att_b", C.c_void_p), ("nbox", C.c_void_p),
+                ("v_hi", C.c_void_p), ("v_lo", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
+                ("att", C.c_void_p), ("pooled", C.c_void_p), ("pooled_hi", C.c_void_p),
+                ("pooled_lo", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p)]
+
+
+class VqaAttnBwd(C.Structure):
+    _fields_ = [("batch", C.c_int32), ("z", C.c_void_p), ("gamma", C.c_void_p), ("beta", C.c_void_p),
+                ("hq", C.c_void_p), ("att_w", C.c_void_p), ("nbox", C.c_void_p), ("v_hi", C.c_void_p),
+                ("v_lo", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64), ("att", C.c_void_p),
+                ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("d_pooled", C.c_void_p),
+                ("dz_hi", C.c_void_p), ("dz_lo", C.c_void_p), ("d_hq", C.c_void_p),
+                ("d_att_w", C.c_void_p), ("d_att_b", C.c_void_p), ("d_gamma", C.c_void_p),
+                ("d_beta", C.c_void_p), ("d_bias", C.c_void_p)]
+
+
+# every symbol include/vqa_answer.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "vqa_create": (C.c_int32, [C.POINTER(VqaConfig), C.POINTER(_P)]),
+    "vqa_destroy": (C.c_int32, [_P]),
+    "vqa_last_error": (C.c_char_p, []),
+    "vqa_abi_version": (C.c_int32, []),
+    "vqa_launch_count": (C.c_uint64, []),
+    "vqa_workspace_bytes": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
+    "vqa_set_workspace": (C.c_int32, [_P, _P, C.c_uint64]),
+    "vqa_prepare_params": (C.c_int32, [_P, C.POINTER(VqaParams), _P]),
+    "vqa_forward": (C.c_int32, [_P, C.POINTER(VqaParams), C.POINTER(VqaFeatureBank), C.POINTER(VqaBatch),
+                                C.POINTER(VqaAnswerMasks), C.c_uint64, C.c_uint64, C.POINTER(VqaOutputs),
+                                _P]),
+    "vqa_backward": (C.c_int32, [_P, C.POINTER(VqaParams), C.POINTER(VqaBatch), C.POINTER(VqaParams),
+                                 C.c_float, _P]),
+    "vqa_dropout_masks": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "vqa_adam_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_int64, _P, _P]),
+    "vqa_gemm": (C.c_int32, [_P, C.POINTER(VqaGemmDesc), _P]),
+    "vqa_split_bf16": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P]),
+    "vqa_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaAttnFwd), _P]),
+    "vqa_attn_bwd": (C.c_int32, [_P, C.POINTER(VqaAttnBwd), _P]),
+    "vqa_bce_metrics": (C.c_int32, [_P, C.c_int32, _P, _P, C.POINTER(VqaAnswerMasks), C.c_float, _P, _P,
+                                    _P, _P, _P, _P]),
+}
+
+_lib = None
+
+
+def load(path=None):
+    """Load the CUDA library. Raises if it has not been built -- there is no Python/CPU fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise ImportError(
+            f"{p} not found: build it with `python -m vqa_transfer_externaldata_b200.build` "
+            "(or __graft_entry__.build()). This package has no CPU fallback.")
+    lib = C.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def check(status):
+    if status != VQA_OK:
+        raise VqaError(status, load().vqa_last_error().decode("utf-8", "replace"))
