@@ -1,0 +1,83 @@
+"""ORACLE twin (test infrastructure, NOT product code): PyTorch-CPU restatement of the same graph as
+oracle/answer_model_np.py, written independently with torch ops and differentiated by autograd.
+
+Two jobs:
+  * cross-check of the NumPy oracle's hand-derived backward (tests/test_oracle.py);
+  * the timed CPU baseline / `bench.py --impl reference` arm: the reference's own TF-1.6 CPU path
+    cannot run in this image (no TensorFlow), so this port of the same graph (fp32, all host threads,
+    oneDNN/MKL GEMMs) stands in for it and is labelled kind="port" everywhere.
+
+PARITY UNPINNED (see answer_model_np.py header): TensorFlow was never executed.
+
+Reference files followed: vqa/model_vlmap_answer.py:102-203, vqa/model_standard.py:193-285,
+vlmap/modules.py:23-39, 67-97, 124-140, 630-650.
+"""
+import torch
+
+LN_EPS = 1e-12
+
+
+def layer_norm_all(z, gamma, beta):
+    """tf.contrib.layers.layer_norm: moments over all non-batch axes, gamma/beta on the last axis."""
+    dims = tuple(range(1, z.dim()))
+    mu = z.mean(dim=dims, keepdim=True)
+    var = (z - mu).pow(2).mean(dim=dims, keepdim=True)
+    return (z - mu) * torch.rsqrt(var + LN_EPS) * gamma + beta
+
+
+def fc_layer(x, w, b, gamma, beta):
+    return torch.relu(layer_norm_all(torch.matmul(x, w) + b, gamma, beta))
+
+
+def gru_encode(E, q_len, Wg, bg, Wc, bc):
+    B, T, _ = E.shape
+    L = Wc.shape[1]
+    h = torch.zeros(B, L, dtype=E.dtype)
+    for t in range(T):
+        x = E[:, t]
+        gates = torch.sigmoid(torch.cat([x, h], 1) @ Wg + bg)
+        r, u = gates[:, :L], gates[:, L:]
+        c = torch.tanh(torch.cat([x, r * h], 1) @ Wc + bc)
+        hn = u * h + (1 - u) * c
+        h = torch.where((t < q_len).unsqueeze(1), hn, h)
+    return h
+
+
+def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", keep_att=0.8,
+            keep_joint=0.5, att_mask=None, joint_mask=None):
+    """p: dict field -> torch tensor (requires_grad where wanted). Returns dict with loss, logit,
+    att_score, pooled, condition, pred."""
+    idx = batch["image_idx"].long()
+    V = features[idx]
+    nbox = num_boxes[idx].long()
+    B, K, _ = V.shape
+    Hv = fc_layer(V, p["v_w"], p["v_b"], p["v_gamma"], p["v_beta"])
+    E = p["embed"][batch["q_intseq"].long()]
+    q = gru_encode(E, batch["q_intseq_len"], p["gru_gates_w"], p["gru_gates_b"], p["gru_cand_w"],
+                   p["gru_cand_b"])
+    Hq = fc_layer(q, p["qv_w"], p["qv_b"], p["qv_gamma"], p["qv_beta"])
+    F = Hv * Hq.unsqueeze(1)
+    if att_mask is not None:
+        F = F * att_mask
+    F = F / keep_att
+    s = torch.matmul(F, p["att_w"]).squeeze(-1) + p["att_b"]
+    valid = torch.arange(K).unsqueeze(0) < nbox.unsqueeze(1)
+    s = torch.where(valid, s, torch.full_like(s, float("-inf")))
+    a = torch.softmax(s, dim=-1)
+    P = torch.bmm(a.unsqueeze(1), V).squeeze(1)
+    Hp = fc_layer(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"])
+    Hl = fc_layer(q, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"])
+    Jn = fc_layer(Hp * Hl, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
+    if joint_mask is not None:
+        Jn = Jn * joint_mask
+    Jd = Jn / keep_joint
+    logit = Jd @ p["ans_w"] + p["ans_b"]
+    target = batch["answer_target"].to(logit.dtype)
+    bce = torch.nn.functional.binary_cross_entropy_with_logits(logit, target, reduction="none")
+    if variant != "standard":
+        bce_train = bce * train_mask
+    else:
+        bce_train = bce
+    loss = bce_train.sum(-1).mean()
+    return {"loss": loss, "report_loss": bce.sum(-1).mean(), "logit": logit, "att_score": a, "pooled": P,
+            "condition": q, "pred": logit.argmax(-1)}

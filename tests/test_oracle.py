@@ -1,0 +1,140 @@
+"""Pins the oracle (the reference has no tests / golden vectors of its own):
+  1. central finite differences on the NumPy oracle's own forward  (hand-derived backward is right)
+  2. an independently written torch-autograd twin agrees            (two restatements cross-check)
+  3. known-answer cases from the TF op definitions
+"""
+import numpy as np
+import pytest
+
+from oracle import answer_model_np as O
+from vqa_transfer_externaldata_b200 import synthetic as S
+
+TINY = dict(B=3, K=5, Dv=16, D=8, L=8, A=11, T=4, W=6, Vq=13)
+
+
+def _setup(variant="vlmap_answer", seed=0, perturb=0.3, dims=TINY):
+    c = S.dims(**dims)
+    p, exist = S.init_params(c, seed=seed, variant=variant, perturb=perturb)
+    rng = np.random.default_rng(seed + 1)
+    p = {k: v.astype(np.float64) for k, v in p.items()}
+    if variant != "standard":
+        # use moderate biases so sigmoid gradients are not vanishing at the -100 columns only
+        p["ans_b"] = np.where(exist > 0, p["ans_b"], -100.0)
+    feats, nb = S.make_bank(c, num_images=7, seed=seed + 2, ragged_boxes=True)
+    batch = S.make_batch(c, 7, seed=seed + 3)
+    batch["q_intseq_len"] = np.array([1, 3, 4][: c["B"]], np.int32)
+    is_obj, is_attr = S.make_answer_flags(c)
+    m = O.answer_masks(c["A"], c["num_train_answer"], is_obj, is_attr, exist)
+    att_mask = (rng.uniform(size=(c["B"], c["K"], c["D"])) < 0.8).astype(np.float64)
+    joint_mask = (rng.uniform(size=(c["B"], c["J"])) < 0.5).astype(np.float64)
+    return c, p, feats.astype(np.float64), nb, batch, m, att_mask, joint_mask
+
+
+@pytest.mark.parametrize("variant", ["vlmap_answer", "standard"])
+def test_backward_matches_finite_differences(variant):
+    c, p, feats, nb, batch, m, am, jm = _setup(variant)
+    out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)
+    g = O.backward(cache)
+    rng = np.random.default_rng(5)
+    eps = 1e-6
+    for name in O.PARAM_FIELDS:
+        flat = p[name].reshape(-1)
+        picks = rng.choice(flat.size, size=min(6, flat.size), replace=False)
+        for i in picks:
+            old = flat[i]
+            flat[i] = old + eps
+            lp = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)[0]["loss"]
+            flat[i] = old - eps
+            lm = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)[0]["loss"]
+            flat[i] = old
+            fd = (lp - lm) / (2 * eps)
+            an = g[name].reshape(-1)[i]
+            assert abs(fd - an) <= 1e-6 * max(1.0, abs(fd), abs(an)) + 2e-8, (name, i, fd, an)
+
+
+@pytest.mark.parametrize("variant", ["vlmap_answer", "standard"])
+def test_numpy_oracle_matches_torch_twin(variant):
+    torch = pytest.importorskip("torch")
+    from oracle import answer_model_torch as OT
+    c, p, feats, nb, batch, m, am, jm = _setup(variant, seed=11)
+    out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)
+    g = O.backward(cache)
+    tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
+    tb = {k: torch.tensor(v) for k, v in batch.items()}
+    tout = OT.forward(tp, torch.tensor(feats), torch.tensor(nb), tb, torch.tensor(m["train"]),
+                      variant=variant, att_mask=torch.tensor(am), joint_mask=torch.tensor(jm))
+    tout["loss"].backward()
+    assert abs(tout["loss"].item() - out["loss"]) < 1e-12
+    np.testing.assert_allclose(tout["logit"].detach().numpy(), out["logit"], rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(tout["att_score"].detach().numpy(), out["att_score"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_array_equal(tout["pred"].numpy(), out["pred"])
+    for name in O.PARAM_FIELDS:
+        tg = tp[name].grad.numpy()
+        scale = np.abs(g[name]).max()
+        # att_b's gradient is identically zero (softmax is shift-invariant): absolute floor
+        assert np.abs(tg - g[name]).max() <= 1e-9 * scale + 1e-15, name
+
+
+def test_known_answers():
+    # BCE(x=0, z) = ln 2
+    assert np.allclose(O.bce_with_logits(np.zeros(3), np.array([0.0, 0.3, 1.0])), np.log(2.0))
+    # constant row => LN output = beta (variance 0, eps 1e-12 keeps it finite)
+    y, _ = O.layer_norm_fwd(np.full((2, 5), 3.0), np.arange(5.0), np.arange(5.0) * 2)
+    assert np.allclose(y, np.arange(5.0) * 2)
+    # 3-D input: statistics span the K and D axes jointly
+    rng = np.random.default_rng(0)
+    z = rng.standard_normal((2, 3, 4))
+    y, _ = O.layer_norm_fwd(z, np.ones(4), np.zeros(4))
+    assert np.allclose(y.reshape(2, -1).mean(1), 0) and np.allclose(y.reshape(2, -1).var(1), 1, atol=1e-9)
+
+
+def test_known_answers_graph():
+    c, p, feats, nb, batch, m, am, jm = _setup()
+    # nbox = 1 => attention is one-hot on box 0 and pooled = V[:, 0]
+    nb1 = np.ones_like(nb)
+    out, cache = O.forward(p, feats, nb1, batch, m, att_mask=am, joint_mask=jm)
+    assert np.array_equal(out["att_score"][:, 0], np.ones(c["B"]))
+    assert np.all(out["att_score"][:, 1:] == 0.0)
+    assert np.allclose(out["pooled"], feats[batch["image_idx"]][:, 0])
+    # masked boxes get exactly zero attention and zero gradient flows through them
+    out, cache = O.forward(p, feats, nb, batch, m, att_mask=am, joint_mask=jm)
+    nbox = nb[batch["image_idx"]]
+    for b in range(c["B"]):
+        assert np.all(out["att_score"][b, nbox[b]:] == 0.0)
+        assert abs(out["att_score"][b].sum() - 1) < 1e-12
+    # absent answer => logit is exactly -100 (weight column 0, bias -100)
+    absent = np.where(m["exist"] == 0)[0]
+    assert absent.size > 0 and np.all(out["logit"][:, absent] == -100.0)
+    # GRU: len = 0 => q = 0
+    b0 = dict(batch)
+    b0["q_intseq_len"] = np.zeros(c["B"], np.int32)
+    out0, _ = O.forward(p, feats, nb, b0, m, att_mask=am, joint_mask=jm)
+    assert np.all(out0["condition"] == 0.0)
+    # argmax ties -> lowest index
+    lg = np.zeros((2, c["A"]))
+    lg[1, 3] = lg[1, 7] = 2.0
+    _, _, _, pred = O.metrics(lg, batch["answer_target"][:2].astype(np.float64), m)
+    assert pred.tolist() == [0, 3]
+
+
+def test_frozen_set_matches_reference_filter():
+    # vqa/model_vlmap_answer.py:81-89
+    tr = O.trainable_fields("vlmap_answer")
+    assert "v_w" in tr and "embed" in tr and "gru_gates_w" in tr and "att_w" in tr and "qv_w" in tr
+    for frozen in ("pl_w", "ql_gamma", "joint_b", "ans_w", "ans_b"):
+        assert frozen not in tr
+    assert set(O.trainable_fields("standard")) == set(O.PARAM_FIELDS)
+
+
+def test_clip_adam_step():
+    rng = np.random.default_rng(3)
+    p = {"a": rng.standard_normal(5), "b": rng.standard_normal((2, 3))}
+    g = {"a": rng.standard_normal(5) * 100, "b": rng.standard_normal((2, 3)) * 100}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(v) for k, v in p.items()}
+    p0 = {k: x.copy() for k, x in p.items()}
+    gn = O.clip_adam_step(p, g, m, v, t=1)
+    assert gn > 20
+    # first Adam step moves every coordinate by ~lr in the direction of -sign(g)
+    for k in p:
+        assert np.allclose(p[k] - p0[k], -1e-3 * np.sign(g[k]), atol=1e-6)
