@@ -216,6 +216,30 @@ VQA_API VqaStatus vqa_adam_step(VqaHandle h, float* param, const float* grad, fl
                                 int64_t n, float lr, float beta1, float beta2, float eps,
                                 float clip_norm, int64_t t, float* grad_norm_out, void* stream);
 
+/* ---- per-phase device timing (bench.py roofline): CUDA events recorded on the caller's stream around
+ * the phases of vqa_forward / vqa_backward while enabled. Not for use under CUDA-graph capture. ------- */
+enum {
+  VQA_PH_GATHER = 0,   /* feature gather -> operand planes                                  */
+  VQA_PH_VPROJ_FWD,    /* Z = V Wv + bv  (tcgen05 GEMM, [B*K, Dv] x [Dv, D])                 */
+  VQA_PH_GRU_FWD,      /* embedding gather + hoisted input GEMMs + T recurrent steps        */
+  VQA_PH_QHEADS_FWD,   /* q_linear_v, q_linear_l                                            */
+  VQA_PH_ATTN_FWD,     /* attention block forward kernel                                    */
+  VQA_PH_HEAD_FWD,     /* pooled_linear_l, joint_fc, answer logits                          */
+  VQA_PH_LOSS,         /* BCE + metrics                                                     */
+  VQA_PH_HEAD_BWD,     /* d logits ... dP, dq (and the head's wgrads when trainable)        */
+  VQA_PH_ATTN_BWD,     /* attention block backward kernel (+ partial reduce)                */
+  VQA_PH_QV_BWD,       /* q_linear_v backward                                               */
+  VQA_PH_VPROJ_WGRAD,  /* dWv = V^T dZ   (tcgen05 GEMM, [Dv, B*K] x [B*K, D])                */
+  VQA_PH_GRU_BWD,      /* BPTT recurrent part                                               */
+  VQA_PH_GRU_WGRAD,    /* GRU weight / bias gradients                                       */
+  VQA_PH_EMBED_BWD,    /* dE GEMMs + scatter-add                                            */
+  VQA_NUM_PHASES
+};
+VQA_API VqaStatus vqa_profile_enable(VqaHandle h, int32_t enable);
+/* milliseconds per phase of the most recent forward+backward (synchronises on the events) */
+VQA_API VqaStatus vqa_profile_read(VqaHandle h, float* ms /* [VQA_NUM_PHASES] */);
+VQA_API const char* vqa_phase_name(int32_t phase);
+
 /* ---- per-kernel entry points (unit parity tests, ncu) --------------------------------------------- */
 typedef struct VqaGemmDesc {
   /* D[M,N] = A[M,K] * B[N,K]^T (+bias[N]) (+addend[M,N]); operands bf16 planes (lo may be NULL).

@@ -95,9 +95,15 @@ def fc_ln_relu_fwd(x, w, b, gamma, beta):
     return np.maximum(y, 0.0), (x, y, ln_cache)
 
 
-def fc_ln_relu_bwd(dh, w, gamma, cache, need_dx=True):
+def fc_ln_relu_bwd(dh, w, gamma, cache, need_dx=True, flip=None):
+    """flip: optional boolean array like y; True entries use the OPPOSITE ReLU gate. The parity tests use
+    it to bound the effect of gates whose pre-activation is zero to working precision (|y| < tau): the
+    backward pass is linear in the gates, so each undecidable gate contributes a fixed +-delta."""
     x, y, ln_cache = cache
-    dy = dh * (y > 0)
+    gate = y > 0
+    if flip is not None:
+        gate = np.logical_xor(gate, flip)
+    dy = dh * gate
     dz, dgamma, dbeta = layer_norm_bwd(dy, gamma, ln_cache)
     x2 = x.reshape(-1, x.shape[-1])
     dz2 = dz.reshape(-1, dz.shape[-1])
@@ -289,11 +295,13 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     return out, cache
 
 
-def backward(cache, loss_scale=1.0):
+def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None):
     """Gradients of loss_scale * train_loss w.r.t. every parameter (dict field -> array).
-    Callers drop the frozen ones (trainable_fields)."""
+    Callers drop the frozen ones (trainable_fields). If `intermediates` is a dict it receives the
+    activation gradients the per-kernel parity tests compare against (dP, dHq, dZv, dlogit)."""
     c = cache
     p = c["p"]
+    gf = gate_flips or {}
     B, A = c["logit"].shape
     tmask = c["m"]["train"] if c["use_tm"] else np.ones(A)
     g = {}
@@ -303,12 +311,12 @@ def backward(cache, loss_scale=1.0):
     dJd = dx @ p["ans_w"].T
     dJn = dJd * c["jm"] / c["keep_joint"]
     dX, g["joint_w"], g["joint_b"], g["joint_gamma"], g["joint_beta"] = fc_ln_relu_bwd(
-        dJn, p["joint_w"], p["joint_gamma"], c["j_cache"])
+        dJn, p["joint_w"], p["joint_gamma"], c["j_cache"], flip=gf.get("joint"))
     dHp, dHl = dX * c["Hl"], dX * c["Hp"]
     dP, g["pl_w"], g["pl_b"], g["pl_gamma"], g["pl_beta"] = fc_ln_relu_bwd(
-        dHp, p["pl_w"], p["pl_gamma"], c["p_cache"])
+        dHp, p["pl_w"], p["pl_gamma"], c["p_cache"], flip=gf.get("pl"))
     dq, g["ql_w"], g["ql_b"], g["ql_gamma"], g["ql_beta"] = fc_ln_relu_bwd(
-        dHl, p["ql_w"], p["ql_gamma"], c["l_cache"])
+        dHl, p["ql_w"], p["ql_gamma"], c["l_cache"], flip=gf.get("ql"))
     # attention pooling + softmax + score
     V, a = c["V"], c["a"]
     da = np.einsum("bkd,bd->bk", V, dP)
@@ -321,9 +329,13 @@ def backward(cache, loss_scale=1.0):
     dHv = dF * c["Hq"][:, None, :]
     dHq = (dF * c["Hv"]).sum(axis=1)
     _, g["v_w"], g["v_b"], g["v_gamma"], g["v_beta"] = fc_ln_relu_bwd(
-        dHv, p["v_w"], p["v_gamma"], c["v_cache"], need_dx=False)   # V is data: no dV
+        dHv, p["v_w"], p["v_gamma"], c["v_cache"], need_dx=False, flip=gf.get("v"))   # V is data: no dV
+    if intermediates is not None:
+        _, y_v, ln_v = c["v_cache"]
+        dZv, _, _ = layer_norm_bwd(dHv * (y_v > 0), p["v_gamma"], ln_v)
+        intermediates.update(dlogit=dx, dP=dP, dHq=dHq, dZv=dZv, ds=ds, dHv=dHv)
     dq2, g["qv_w"], g["qv_b"], g["qv_gamma"], g["qv_beta"] = fc_ln_relu_bwd(
-        dHq, p["qv_w"], p["qv_gamma"], c["q_cache"])
+        dHq, p["qv_w"], p["qv_gamma"], c["q_cache"], flip=gf.get("qv"))
     dq = dq + dq2
     dE, g["gru_gates_w"], g["gru_gates_b"], g["gru_cand_w"], g["gru_cand_b"] = gru_bwd(
         dq, c["gru_steps"], p["gru_gates_w"], p["gru_cand_w"], c["W"])
@@ -331,6 +343,28 @@ def backward(cache, loss_scale=1.0):
     np.add.at(demb, c["q_ids"], dE)                          # gradient of embedding_lookup
     g["embed"] = demb
     return g
+
+
+RELU_LAYERS = {"v": "v_cache", "qv": "q_cache", "pl": "p_cache", "ql": "l_cache", "joint": "j_cache"}
+
+
+def relu_near_ties(cache, tau):
+    """Indices of ReLU pre-activations with |y| < tau, per layer: gates a working-precision run cannot
+    be expected to reproduce."""
+    return {name: np.argwhere(np.abs(cache[key][1]) < tau) for name, key in RELU_LAYERS.items()}
+
+
+def v_layer_tie_delta(cache, dHv, idx):
+    """Exact change of (v_w, v_b, v_gamma, v_beta) when the gate of v-projection element idx=(b,k,d) is
+    flipped. V is data, so nothing else depends on that gate; only sample b's LayerNorm slab changes."""
+    p = cache["p"]
+    x, y, (xhat, rstd) = cache["v_cache"]
+    b, k, d = (int(i) for i in idx)
+    sign = -1.0 if y[b, k, d] > 0 else 1.0          # gate on -> off removes the term, off -> on adds it
+    dy = np.zeros_like(y[b:b + 1])
+    dy[0, k, d] = sign * dHv[b, k, d]
+    dz, dgamma, dbeta = layer_norm_bwd(dy, p["v_gamma"], (xhat[b:b + 1], rstd[b:b + 1]))
+    return {"v_w": x[b].T @ dz[0], "v_b": dz[0].sum(axis=0), "v_gamma": dgamma, "v_beta": dbeta}
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1,0 +1,82 @@
+"""Shared helpers of the GPU parity tests: run the CUDA path through the C ABI (Engine) and the NumPy
+oracle on the same seeded inputs and the same dropout masks."""
+import numpy as np
+
+from oracle import answer_model_np as O
+from vqa_transfer_externaldata_b200 import synthetic as S
+from vqa_transfer_externaldata_b200.engine import AnswerModelConfig, Engine
+
+
+def rel_err(x, ref):
+    """||x - ref||_inf / max(||ref||_inf, tiny): the definition SURVEY 8d fixes for the parity gates."""
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.abs(x - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+def rel_l2(x, ref):
+    x = np.asarray(x, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    return float(np.linalg.norm(x - ref) / max(np.linalg.norm(ref), 1e-30))
+
+
+def relu_tie_budget(cache, inter, ref_g, fields, tau, loss_scale=1.0, max_ties=96):
+    """Per-tensor elementwise budget sum_e |delta_e| over ReLU gates whose oracle pre-activation is within
+    tau of zero. Gradients are linear in the gates (forward values are unaffected: relu(y) ~ 0 there), so a
+    run that decides those gates differently lands within ref +- budget. Returns (budget dict, n_ties)."""
+    ties = O.relu_near_ties(cache, tau)
+    budget = {f: np.zeros_like(ref_g[f]) for f in fields}
+    n = sum(len(v) for v in ties.values())
+    if n > max_ties:
+        raise AssertionError(f"{n} near-tie ReLU gates at tau={tau}: too many to bound")
+    for idx in ties["v"]:
+        for f, dlt in O.v_layer_tie_delta(cache, inter["dHv"], idx).items():
+            if f in budget:
+                budget[f] += np.abs(dlt)
+    for layer in ("qv", "pl", "ql", "joint"):
+        for idx in ties[layer]:
+            flip = np.zeros(cache[O.RELU_LAYERS[layer]][1].shape, dtype=bool)
+            flip[tuple(idx)] = True
+            g2 = O.backward(cache, loss_scale=loss_scale, gate_flips={layer: flip})
+            for f in fields:
+                budget[f] += np.abs(g2[f] - ref_g[f])
+    return budget, n
+
+
+def build_case(dims, variant="vlmap_answer", precision="fp32", seed=0, num_images=24, ragged=True,
+               batch=None, T=None, perturb=0.2, keep_att=0.8, keep_joint=0.5):
+    c = S.dims(**dims)
+    cfg = AnswerModelConfig(variant=variant, precision=precision, keep_att=keep_att, keep_joint=keep_joint, **c)
+    params, exist = S.init_params(c, seed=seed, variant=variant, perturb=perturb)
+    feats, nb = S.make_bank(c, num_images=num_images, seed=seed + 2, ragged_boxes=ragged)
+    bt = S.make_batch(c, num_images, seed=seed + 3, batch=batch, T=T)
+    is_obj, is_attr = S.make_answer_flags(c)
+    eng = Engine(cfg)
+    eng.set_feature_bank(feats, nb)
+    eng.set_answer_masks(is_obj, is_attr, exist)
+    eng.load_params(params)
+    m = O.answer_masks(c["A"], c["num_train_answer"], is_obj, is_attr, exist)
+    return dict(c=c, cfg=cfg, params=params, feats=feats, nb=nb, batch=bt, eng=eng, m=m)
+
+
+def run_both(case, seed=777, step=3, loss_scale=1.0):
+    import torch
+    eng, cfg = case["eng"], case["cfg"]
+    eng.stage_batch(case["batch"])
+    eng.forward(seed=seed, step=step)
+    eng.backward(loss_scale=loss_scale)
+    att_mask, joint_mask = eng.dropout_masks(seed, step)
+    torch.cuda.synchronize()
+    loss, report = eng.read_scalars()
+    got = {"loss": loss, "report": report}
+    got.update({k: v.detach().cpu().numpy() for k, v in eng.outputs().items()})
+    got["condition"] = eng.o_condition[:eng.batch_size].cpu().numpy()
+    got["pooled"] = eng.o_pooled[:eng.batch_size].cpu().numpy()
+    got["grads"] = {f: g.detach().cpu().numpy() for f, g in eng.params.grad_views.items()}
+    out, cache = O.forward(case["params"], case["feats"], case["nb"], case["batch"], case["m"],
+                           variant=cfg.variant, keep_att=cfg.keep_att, keep_joint=cfg.keep_joint,
+                           att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy())
+    inter = {}
+    ref_g = O.backward(cache, loss_scale=loss_scale, intermediates=inter)
+    case["oracle_cache"], case["oracle_inter"], case["loss_scale"] = cache, inter, loss_scale
+    return got, out, ref_g

@@ -1,0 +1,612 @@
+// The memory-bound attention block, one CTA per sample.
+//
+// forward  (vlmap/modules.py:67-97 hadamard_attention, :23-39 attention_pooling, and the LayerNorm +
+//           ReLU of the producing fc_layer, :646-649, which cannot finish in the GEMM epilogue because
+//           TF normalises the [K, D] slab of a sample jointly -- SURVEY Q1):
+//   stats over the K*D pre-LN projection (one pass, Chan/Welford merge, fp32)
+//   hv = relu(LN(z));  F = dropout_0.8(hv * hq);  s_k = F_k . w + b;  s_k = -inf for k >= nbox
+//   a = softmax_K(s);  pooled = sum_k a_k V_k  (the RAW region features, not hv)
+// backward (hand-derived): da_k = <V_k, dP>; ds = a (da - sum a da);
+//   then per element dF, dhv, the ReLU gate, and the joint-(K,D) LayerNorm backward, all from the
+//   re-read z; emits dz (GEMM operand planes), dHq and per-CTA partials of dw, db, dgamma, dbeta, dbias.
+//
+// Access pattern: every global access is a 128-bit load/store of 8 bf16 (or 2x4 fp32) consecutive
+// elements, consecutive lanes on consecutive 16-byte chunks; reductions by warp shuffle.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <math_constants.h>
+
+#include "internal.h"
+#include "philox.cuh"
+
+namespace vqa {
+
+namespace {
+
+constexpr int ATT_THREADS = 256;
+constexpr int ATT_WARPS = ATT_THREADS / 32;
+
+__device__ __forceinline__ void load8(const bf16* p, float (&x)[8]) {
+  const uint4 u = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    x[2 * j] = f.x;
+    x[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const float* p, float (&x)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
+  x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+// features are streamed once per pass: read-only path
+__device__ __forceinline__ void load8_planes(const bf16* hi, const bf16* lo, long long off,
+                                             float (&x)[8]) {
+  load8(hi + off, x);
+  if (lo) {
+    float y[8];
+    load8(lo + off, y);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] += y[j];
+  }
+}
+__device__ __forceinline__ void store8_planes(bf16* hi, bf16* lo, long long off, const float (&x)[8]) {
+  __nv_bfloat162 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bf16 a = __float2bfloat16_rn(x[2 * j]), b = __float2bfloat16_rn(x[2 * j + 1]);
+    h[j] = __nv_bfloat162(a, b);
+    l[j] = __nv_bfloat162(__float2bfloat16_rn(x[2 * j] - __bfloat162float(a)),
+                          __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(b)));
+  }
+  *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<uint4*>(h);
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<uint4*>(l);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// Chan et al. pairwise merge of (count, mean, M2)
+__device__ __forceinline__ void chan_merge(float& n, float& mean, float& m2, float nb, float mb,
+                                           float m2b) {
+  const float nt = n + nb;
+  if (nt == 0.f) return;
+  const float delta = mb - mean;
+  const float f = nb / nt;
+  mean += delta * f;
+  m2 += m2b + delta * delta * n * f;
+  n = nt;
+}
+
+// mean / rstd over the K*D slab of one sample; result broadcast to the whole CTA
+template <typename ZT>
+__device__ __forceinline__ void slab_stats(const ZT* zb, int nchunks, float* red /*[3*ATT_WARPS+2]*/,
+                                           float& mean_out, float& rstd_out) {
+  float n = 0.f, mean = 0.f, m2 = 0.f;
+  for (int c = threadIdx.x; c < nchunks; c += ATT_THREADS) {
+    float x[8];
+    load8(zb + static_cast<long long>(c) * 8, x);
+    float cm = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) cm += x[j];
+    cm *= 0.125f;
+    float c2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c2 += (x[j] - cm) * (x[j] - cm);
+    chan_merge(n, mean, m2, 8.f, cm, c2);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float nb = __shfl_xor_sync(0xffffffffu, n, o);
+    const float mb = __shfl_xor_sync(0xffffffffu, mean, o);
+    const float qb = __shfl_xor_sync(0xffffffffu, m2, o);
+    chan_merge(n, mean, m2, nb, mb, qb);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) {
+    red[3 * warp] = n;
+    red[3 * warp + 1] = mean;
+    red[3 * warp + 2] = m2;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tn = 0.f, tm = 0.f, tq = 0.f;
+    for (int w = 0; w < ATT_WARPS; ++w) chan_merge(tn, tm, tq, red[3 * w], red[3 * w + 1], red[3 * w + 2]);
+    const float var = tq / tn;  // biased variance (tf.nn.moments)
+    red[3 * ATT_WARPS] = tm;
+    red[3 * ATT_WARPS + 1] = 1.0f / sqrtf(var + 1e-12f);
+  }
+  __syncthreads();
+  mean_out = red[3 * ATT_WARPS];
+  rstd_out = red[3 * ATT_WARPS + 1];
+}
+
+struct FwdArgs {
+  const void* z;
+  const float* gamma; const float* beta; const float* hq; const float* att_w; const float* att_b;
+  const int* nbox; const bf16* v_hi; const bf16* v_lo;
+  unsigned long long seed, step;
+  float* att; float* pooled; bf16* pooled_hi; bf16* pooled_lo; float* ln_mean; float* ln_rstd;
+};
+
+template <typename ZT>
+__global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(FwdArgs a, int K, int D, int Dv,
+                                                               float keep, uint32_t thr) {
+  extern __shared__ float sm[];
+  float* cA = sm;           // gamma_d * rstd
+  float* cB = cA + D;       // beta_d - mean * rstd * gamma_d
+  float* cC = cB + D;       // hq_d * w_d / keep
+  float* sc = cC + D;       // [K] scores -> attention
+  float* red = sc + K;      // [3*ATT_WARPS + 2]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int CH = D >> 3;
+  const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
+
+  float mean, rstd;
+  slab_stats<ZT>(zb, K * CH, red, mean, rstd);
+
+  const float inv_keep = 1.0f / keep;
+  for (int d = tid; d < D; d += ATT_THREADS) {
+    const float g = a.gamma[d] * rstd;
+    cA[d] = g;
+    cB[d] = a.beta[d] - mean * g;
+    cC[d] = a.hq[static_cast<long long>(b) * D + d] * a.att_w[d] * inv_keep;
+  }
+  int nb = a.nbox[b];
+  nb = nb < 0 ? 0 : (nb > K ? K : nb);
+  __syncthreads();
+
+  // scores: one warp per box row
+  const float bias = a.att_b[0];
+  for (int k = warp; k < nb; k += ATT_WARPS) {
+    const ZT* zr = zb + static_cast<long long>(k) * D;
+    const unsigned long long g0 = (static_cast<unsigned long long>(b) * K + k) * CH;
+    float acc = 0.f;
+    for (int c = lane; c < CH; c += 32) {
+      float x[8];
+      load8(zr + c * 8, x);
+      uint32_t bits = 0xFFu;
+      if (thr < 65536u) bits = philox_keep_bits(philox4x32_10(g0 + c, RNG_STREAM_ATT, a.seed, a.step), thr);
+      const int d0 = c * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float y = fmaxf(fmaf(x[j], cA[d0 + j], cB[d0 + j]), 0.f);
+        acc += ((bits >> j) & 1u) ? y * cC[d0 + j] : 0.f;
+      }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) sc[k] = acc + bias;
+  }
+  __syncthreads();
+
+  // masked softmax over boxes (tf.where(mask, s, -inf) -> tf.nn.softmax): exact zeros beyond nbox
+  if (warp == 0) {
+    float mx = -CUDART_INF_F;
+    for (int k = lane; k < nb; k += 32) mx = fmaxf(mx, sc[k]);
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int k = lane; k < nb; k += 32) {
+      const float e = expf(sc[k] - mx);
+      sc[k] = e;
+      sum += e;
+    }
+    sum = warp_sum(sum);
+    const float inv = 1.0f / sum;  // nb == 0 -> 1/0: TF yields NaN for an all-masked row as well
+    for (int k = lane; k < K; k += 32) {
+      const float p = k < nb ? sc[k] * inv : (nb == 0 ? CUDART_NAN_F : 0.f);
+      sc[k] = p;
+      if (a.att) a.att[static_cast<long long>(b) * K + k] = p;
+    }
+  }
+  __syncthreads();
+
+  // attended pooling of the raw features
+  const long long vb = static_cast<long long>(b) * K * Dv;
+  for (int c = tid; c < (Dv >> 3); c += ATT_THREADS) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    int k = 0;
+    for (; k + 4 <= nb; k += 4) {
+      float v0[8], v1[8], v2[8], v3[8];
+      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k) * Dv + c * 8, v0);
+      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k + 1) * Dv + c * 8, v1);
+      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k + 2) * Dv + c * 8, v2);
+      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k + 3) * Dv + c * 8, v3);
+      const float a0 = sc[k], a1 = sc[k + 1], a2 = sc[k + 2], a3 = sc[k + 3];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        acc[j] = fmaf(a0, v0[j], acc[j]);
+        acc[j] = fmaf(a1, v1[j], acc[j]);
+        acc[j] = fmaf(a2, v2[j], acc[j]);
+        acc[j] = fmaf(a3, v3[j], acc[j]);
+      }
+    }
+    for (; k < nb; ++k) {
+      float v0[8];
+      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k) * Dv + c * 8, v0);
+      const float a0 = sc[k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(a0, v0[j], acc[j]);
+    }
+    if (nb == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = CUDART_NAN_F;
+    }
+    const long long o = static_cast<long long>(b) * Dv + c * 8;
+    if (a.pooled) {
+      *reinterpret_cast<float4*>(a.pooled + o) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+      *reinterpret_cast<float4*>(a.pooled + o + 4) = make_float4(acc[4], acc[5], acc[6], acc[7]);
+    }
+    if (a.pooled_hi) store8_planes(a.pooled_hi, a.pooled_lo, o, acc);
+  }
+  if (tid == 0) {
+    a.ln_mean[b] = mean;
+    a.ln_rstd[b] = rstd;
+  }
+}
+
+struct BwdArgs {
+  const void* z;
+  const float* gamma; const float* beta; const float* hq; const float* att_w;
+  const int* nbox; const bf16* v_hi; const bf16* v_lo;
+  unsigned long long seed, step;
+  const float* att; const float* ln_mean; const float* ln_rstd; const float* d_pooled;
+  bf16* dz_hi; bf16* dz_lo; float* d_hq;
+  float* part;  // [batch, 4*D + 8]: T*hq/keep (dw) | dgamma | dbeta | dbias | db
+};
+
+// NCOL = column chunks (of 8) owned per thread: D <= 2048 -> 1, D <= 4096 -> 2
+template <typename ZT, int NCOL>
+__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K, int D, int Dv,
+                                                               float keep, uint32_t thr) {
+  extern __shared__ float sm[];
+  const int CH = D >> 3;
+  float* sdP = sm;                  // [Dv]
+  float* ds = sdP + Dv;             // [K] (first da, then ds)
+  float* red = ds + K;              // [40]
+  float* colacc = red + 40;         // [3][ATT_THREADS][8*NCOL] per-thread column accumulators
+  unsigned char* flags = reinterpret_cast<unsigned char*>(colacc + 3 * ATT_THREADS * 8 * NCOL);  // [K*CH]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
+  const float mean = a.ln_mean[b], rstd = a.ln_rstd[b];
+  int nb = a.nbox[b];
+  nb = nb < 0 ? 0 : (nb > K ? K : nb);
+
+  for (int d = tid * 4; d < Dv; d += ATT_THREADS * 4)
+    *reinterpret_cast<float4*>(sdP + d) =
+        *reinterpret_cast<const float4*>(a.d_pooled + static_cast<long long>(b) * Dv + d);
+  __syncthreads();
+
+  // da_k = <V_k, dP>: one warp per box row
+  const long long vb = static_cast<long long>(b) * K * Dv;
+  for (int k = warp; k < K; k += ATT_WARPS) {
+    float acc = 0.f;
+    if (k < nb) {
+      for (int c = lane; c < (Dv >> 3); c += 32) {
+        float v[8];
+        load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k) * Dv + c * 8, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc = fmaf(v[j], sdP[c * 8 + j], acc);
+      }
+      acc = warp_sum(acc);
+    }
+    if (lane == 0) ds[k] = acc;
+  }
+  __syncthreads();
+  // ds_k = a_k (da_k - sum_j a_j da_j); masked slots have a_k = 0 -> ds_k = 0
+  if (warp == 0) {
+    float dot = 0.f;
+    for (int k = lane; k < nb; k += 32) dot += a.att[static_cast<long long>(b) * K + k] * ds[k];
+    dot = warp_sum(dot);
+    float dbs = 0.f;
+    for (int k = lane; k < K; k += 32) {
+      const float v = k < nb ? a.att[static_cast<long long>(b) * K + k] * (ds[k] - dot) : 0.f;
+      ds[k] = v;
+      dbs += v;
+    }
+    dbs = warp_sum(dbs);
+    if (lane == 0) red[32] = dbs;
+  }
+  __syncthreads();
+
+  // column-owner mapping: thread (tc, tr) owns column chunks tc (+ CW) and walks rows tr, tr+RP, ...
+  const int CW = CH < ATT_THREADS ? CH : ATT_THREADS;
+  const int RP = ATT_THREADS / CW;
+  const int tc = tid % CW, tr = tid / CW;
+  const bool active = tr < RP;
+
+  float accT[NCOL][8], accU[NCOL][8], accV[NCOL][8];
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accT[i][j] = accU[i][j] = accV[i][j] = 0.f;
+
+  const float mr = mean * rstd;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int c = tc + i * CW;
+      if (c >= CH) break;
+      float g[8], bt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        g[j] = a.gamma[c * 8 + j];
+        bt[j] = a.beta[c * 8 + j];
+      }
+      for (int k = tr; k < nb; k += RP) {
+        float x[8];
+        load8(zb + static_cast<long long>(k) * D + c * 8, x);
+        uint32_t bits = 0xFFu;
+        if (thr < 65536u)
+          bits = philox_keep_bits(
+              philox4x32_10((static_cast<unsigned long long>(b) * K + k) * CH + c, RNG_STREAM_ATT,
+                            a.seed, a.step),
+              thr);
+        const float dsk = ds[k];
+        uint32_t fl = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(x[j], rstd, -mr);
+          const float y = fmaf(xh, g[j], bt[j]);
+          const bool pos = y > 0.f;
+          const bool m = (bits >> j) & 1u;
+          accT[i][j] += (m && pos) ? dsk * y : 0.f;
+          if (m && pos) {
+            fl |= 1u << j;
+            accU[i][j] = fmaf(dsk, xh, accU[i][j]);
+            accV[i][j] += dsk;
+          }
+        }
+        flags[k * CH + c] = static_cast<unsigned char>(fl);
+      }
+    }
+  }
+  // combine the RP row groups deterministically through shared memory
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      colacc[(0 * ATT_THREADS + tid) * 8 * NCOL + i * 8 + j] = accT[i][j];
+      colacc[(1 * ATT_THREADS + tid) * 8 * NCOL + i * 8 + j] = accU[i][j];
+      colacc[(2 * ATT_THREADS + tid) * 8 * NCOL + i * 8 + j] = accV[i][j];
+    }
+  __syncthreads();
+  const float inv_keep = 1.0f / keep;
+  float s1 = 0.f, s2 = 0.f;  // sum dxhat, sum dxhat * xhat over the slab
+  float* part = a.part + static_cast<long long>(b) * (4 * D + 8);
+  float G[NCOL][8];
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) G[i][j] = 0.f;
+  if (active && tr == 0) {
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int c = tc + i * CW;
+      if (c >= CH) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float T = 0.f, U = 0.f, Vv = 0.f;
+        for (int r = 0; r < RP; ++r) {
+          const int t2 = r * CW + tc;
+          T += colacc[(0 * ATT_THREADS + t2) * 8 * NCOL + i * 8 + j];
+          U += colacc[(1 * ATT_THREADS + t2) * 8 * NCOL + i * 8 + j];
+          Vv += colacc[(2 * ATT_THREADS + t2) * 8 * NCOL + i * 8 + j];
+        }
+        const int d = c * 8 + j;
+        const float w = a.att_w[d], hq = a.hq[static_cast<long long>(b) * D + d], gm = a.gamma[d];
+        const float whk = w * hq * inv_keep;
+        a.d_hq[static_cast<long long>(b) * D + d] = T * w * inv_keep;  // sum_k dF * hv
+        part[d] = T * hq * inv_keep;                                   // dw partial
+        part[D + d] = whk * U;                                         // dgamma partial
+        part[2 * D + d] = whk * Vv;                                    // dbeta partial
+        const float Gd = whk * gm;                                     // dxhat = ds_k * Gd * flag
+        G[i][j] = Gd;
+        s1 = fmaf(Gd, Vv, s1);
+        s2 = fmaf(Gd, U, s2);
+      }
+    }
+  }
+  // every thread of a column needs G: recompute it for the other row groups
+  if (active && tr != 0) {
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int c = tc + i * CW;
+      if (c >= CH) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int d = c * 8 + j;
+        G[i][j] = a.att_w[d] * a.hq[static_cast<long long>(b) * D + d] * inv_keep * a.gamma[d];
+      }
+    }
+  }
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if (lane == 0) {
+    red[warp] = s1;
+    red[8 + warp] = s2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float t1 = 0.f, t2 = 0.f;
+    for (int w = 0; w < ATT_WARPS; ++w) {
+      t1 += red[w];
+      t2 += red[8 + w];
+    }
+    const float inv_n = 1.0f / (static_cast<float>(K) * static_cast<float>(D));
+    red[16] = t1 * inv_n;
+    red[17] = t2 * inv_n;
+    part[4 * D] = red[32];  // d att_b partial
+  }
+  __syncthreads();
+  const float m1 = red[16], m2 = red[17];
+
+  // dz = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) for ALL K rows (padded rows are part
+  // of the LayerNorm slab and receive gradient through the statistics)
+  float accB[NCOL][8];
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) accB[i][j] = 0.f;
+  if (active) {
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int c = tc + i * CW;
+      if (c >= CH) break;
+      for (int k = tr; k < K; k += RP) {
+        float x[8], dz[8];
+        load8(zb + static_cast<long long>(k) * D + c * 8, x);
+        const uint32_t fl = k < nb ? flags[k * CH + c] : 0u;
+        const float dsk = ds[k];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = fmaf(x[j], rstd, -mr);
+          const float dxh = ((fl >> j) & 1u) ? dsk * G[i][j] : 0.f;
+          dz[j] = rstd * (dxh - m1 - xh * m2);
+          accB[i][j] += dz[j];
+        }
+        store8_planes(a.dz_hi, a.dz_lo, (static_cast<long long>(b) * K + k) * D + c * 8, dz);
+      }
+    }
+  }
+  __syncthreads();  // colacc reuse
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) colacc[tid * 8 * NCOL + i * 8 + j] = accB[i][j];
+  __syncthreads();
+  if (active && tr == 0) {
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int c = tc + i * CW;
+      if (c >= CH) break;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float s = 0.f;
+        for (int r = 0; r < RP; ++r) s += colacc[(r * CW + tc) * 8 * NCOL + i * 8 + j];
+        part[3 * D + c * 8 + j] = s;  // d(bias of the projection) partial
+      }
+    }
+  }
+}
+
+// out[c] = sum_b part[b, c]   (deterministic: fixed order over b)
+__global__ void attn_part_reduce_kernel(const float* __restrict__ part, int batch, int width,
+                                        float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= width) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int b = 0;
+  for (; b + 4 <= batch; b += 4) {
+    s0 += part[static_cast<long long>(b) * width + c];
+    s1 += part[static_cast<long long>(b + 1) * width + c];
+    s2 += part[static_cast<long long>(b + 2) * width + c];
+    s3 += part[static_cast<long long>(b + 3) * width + c];
+  }
+  for (; b < batch; ++b) s0 += part[static_cast<long long>(b) * width + c];
+  out[c] = (s0 + s1) + (s2 + s3);
+}
+
+}  // namespace
+
+size_t attn_bwd_partial_floats(int batch, int D) {
+  // [batch, 4D+8] per-CTA partials + [4D+8] reduced
+  return static_cast<size_t>(batch + 1) * (4 * static_cast<size_t>(D) + 8);
+}
+
+VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precision, float keep,
+                          cudaStream_t s) {
+  if (a.batch == 0) return VQA_OK;
+  if (!a.z || !a.gamma || !a.beta || !a.hq || !a.att_w || !a.att_b || !a.nbox || !a.v_hi ||
+      !a.ln_mean || !a.ln_rstd)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_attn_fwd: null argument");
+  if ((D & 7) || (Dv & 7)) return set_error(VQA_ERR_BAD_SHAPE, "vqa_attn_fwd: D, Dv must be multiples of 8");
+  FwdArgs f;
+  f.z = a.z; f.gamma = a.gamma; f.beta = a.beta; f.hq = a.hq; f.att_w = a.att_w; f.att_b = a.att_b;
+  f.nbox = a.nbox; f.v_hi = static_cast<const bf16*>(a.v_hi); f.v_lo = static_cast<const bf16*>(a.v_lo);
+  f.seed = a.seed; f.step = a.step; f.att = a.att; f.pooled = a.pooled;
+  f.pooled_hi = static_cast<bf16*>(a.pooled_hi); f.pooled_lo = static_cast<bf16*>(a.pooled_lo);
+  f.ln_mean = a.ln_mean; f.ln_rstd = a.ln_rstd;
+  const size_t smem = (3 * static_cast<size_t>(D) + K + 3 * ATT_WARPS + 2) * sizeof(float);
+  const uint32_t thr = keep_threshold(keep);
+  if (precision == VQA_PREC_FP32) {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    attn_fwd_kernel<float><<<a.batch, ATT_THREADS, smem, s>>>(f, K, D, Dv, keep, thr);
+  } else {
+    static bool set = false;
+    if (!set) { cudaFuncSetAttribute(attn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
+    attn_fwd_kernel<bf16><<<a.batch, ATT_THREADS, smem, s>>>(f, K, D, Dv, keep, thr);
+  }
+  VQA_LAUNCH_CHECK("attn_fwd");
+  return VQA_OK;
+}
+
+template <typename ZT, int NCOL>
+static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv, float keep,
+                              uint32_t thr, cudaStream_t s) {
+  const size_t smem = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float) +
+                      static_cast<size_t>(K) * (D >> 3);
+  static bool set = false;
+  if (!set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    set = true;
+  }
+  if (smem > 220 * 1024) return cudaErrorInvalidValue;
+  attn_bwd_kernel<ZT, NCOL><<<batch, ATT_THREADS, smem, s>>>(g, K, D, Dv, keep, thr);
+  return cudaGetLastError();
+}
+
+VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precision, float keep,
+                          float* partials, cudaStream_t s) {
+  if (a.batch == 0) return VQA_OK;
+  if (!a.z || !a.gamma || !a.beta || !a.hq || !a.att_w || !a.nbox || !a.v_hi || !a.att || !a.ln_mean ||
+      !a.ln_rstd || !a.d_pooled || !a.dz_hi || !a.d_hq || !partials)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_attn_bwd: null argument");
+  if ((D & 7) || (Dv & 7) || D > 4096)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_attn_bwd: D, Dv multiples of 8, D <= 4096");
+  BwdArgs g;
+  g.z = a.z; g.gamma = a.gamma; g.beta = a.beta; g.hq = a.hq; g.att_w = a.att_w; g.nbox = a.nbox;
+  g.v_hi = static_cast<const bf16*>(a.v_hi); g.v_lo = static_cast<const bf16*>(a.v_lo);
+  g.seed = a.seed; g.step = a.step; g.att = a.att; g.ln_mean = a.ln_mean; g.ln_rstd = a.ln_rstd;
+  g.d_pooled = a.d_pooled; g.dz_hi = static_cast<bf16*>(a.dz_hi); g.dz_lo = static_cast<bf16*>(a.dz_lo);
+  g.d_hq = a.d_hq; g.part = partials;
+  const uint32_t thr = keep_threshold(keep);
+  cudaError_t e;
+  const bool two = D > 2048;
+  if (precision == VQA_PREC_FP32)
+    e = two ? launch_bwd<float, 2>(g, a.batch, K, D, Dv, keep, thr, s)
+            : launch_bwd<float, 1>(g, a.batch, K, D, Dv, keep, thr, s);
+  else
+    e = two ? launch_bwd<bf16, 2>(g, a.batch, K, D, Dv, keep, thr, s)
+            : launch_bwd<bf16, 1>(g, a.batch, K, D, Dv, keep, thr, s);
+  if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd launch");
+  count_launch();
+  // reduce the per-sample partials: [dw | dgamma | dbeta | dbias | db]
+  const int width = 4 * D + 8;
+  float* reduced = partials + static_cast<size_t>(a.batch) * width;
+  attn_part_reduce_kernel<<<(width + 127) / 128, 128, 0, s>>>(partials, a.batch, width, reduced);
+  VQA_LAUNCH_CHECK("attn_part_reduce");
+  struct { float* dst; int off; int n; } outs[5] = {
+      {a.d_att_w, 0, D}, {a.d_gamma, D, D}, {a.d_beta, 2 * D, D}, {a.d_bias, 3 * D, D}, {a.d_att_b, 4 * D, 1}};
+  for (auto& o : outs)
+    if (o.dst)
+      VQA_CUDA_CHECK(cudaMemcpyAsync(o.dst, reduced + o.off, sizeof(float) * o.n, cudaMemcpyDeviceToDevice, s));
+  return VQA_OK;
+}
+
+}  // namespace vqa

@@ -200,12 +200,20 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   h->ws_bytes = 0;
   h->params_ready = false;
   h->fwd_valid = false;
+  h->profile = false;
+  h->ev_created = false;
+  for (int i = 0; i < VQA_NUM_PHASES; ++i) h->ev_used[i] = false;
   h->ws_needed = plan_workspace(h, nullptr);
   *out = h;
   return VQA_OK;
 }
 
 VQA_API VqaStatus vqa_destroy(VqaHandle h) {
+  if (h && h->ev_created)
+    for (int i = 0; i < VQA_NUM_PHASES; ++i) {
+      cudaEventDestroy(h->ev[i][0]);
+      cudaEventDestroy(h->ev[i][1]);
+    }
   delete h;
   return VQA_OK;
 }
@@ -242,6 +250,39 @@ VQA_API VqaStatus vqa_split_bf16(VqaHandle h, const float* src, int64_t rows, in
   if (!h || !src || !hi) return set_error(VQA_ERR_BAD_ARG, "vqa_split_bf16: null argument");
   return split_bf16_launch(src, rows, cols, ld, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ld_out,
                            static_cast<cudaStream_t>(stream));
+}
+
+VQA_API VqaStatus vqa_profile_enable(VqaHandle h, int32_t enable) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_profile_enable: null handle");
+  if (enable && !h->ev_created) {
+    for (int i = 0; i < VQA_NUM_PHASES; ++i) {
+      VQA_CUDA_CHECK(cudaEventCreate(&h->ev[i][0]));
+      VQA_CUDA_CHECK(cudaEventCreate(&h->ev[i][1]));
+    }
+    h->ev_created = true;
+  }
+  h->profile = enable != 0;
+  for (int i = 0; i < VQA_NUM_PHASES; ++i) h->ev_used[i] = false;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_profile_read(VqaHandle h, float* ms) {
+  if (!h || !ms) return set_error(VQA_ERR_BAD_ARG, "vqa_profile_read: null argument");
+  for (int i = 0; i < VQA_NUM_PHASES; ++i) {
+    ms[i] = 0.f;
+    if (h->ev_created && h->ev_used[i]) {
+      VQA_CUDA_CHECK(cudaEventSynchronize(h->ev[i][1]));
+      VQA_CUDA_CHECK(cudaEventElapsedTime(&ms[i], h->ev[i][0], h->ev[i][1]));
+    }
+  }
+  return VQA_OK;
+}
+
+VQA_API const char* vqa_phase_name(int32_t phase) {
+  static const char* names[VQA_NUM_PHASES] = {
+      "gather", "vproj_fwd", "gru_fwd", "qheads_fwd", "attn_fwd", "head_fwd", "loss",
+      "head_bwd", "attn_bwd", "qv_bwd", "vproj_wgrad", "gru_bwd", "gru_wgrad", "embed_bwd"};
+  return (phase >= 0 && phase < VQA_NUM_PHASES) ? names[phase] : "?";
 }
 
 /* number of kernels this library has enqueued in this process (bench.py's gpu_launches) */

@@ -89,6 +89,11 @@ struct VqaHandle_t {
   int last_batch, last_T;
   uint64_t last_seed, last_step;
   VqaAnswerMasks last_masks;
+  // optional per-phase timing
+  bool profile;
+  cudaEvent_t ev[VQA_NUM_PHASES][2];
+  bool ev_created;
+  bool ev_used[VQA_NUM_PHASES];
 };
 
 namespace vqa {

@@ -102,7 +102,6 @@ struct RowLnBwd {
   const float* mean;
   const float* rstd;
   const float* mul;      // optional: forward multiplied the activation by this
-  float* dmul;           // optional: receives dout * y (gradient w.r.t. mul)
   float keep;
   unsigned long long seed, step;
   unsigned int stream_id;
@@ -127,6 +126,9 @@ VqaStatus bce_metrics_launch(int batch, int A, int num_train_answer, int use_tra
                              float grad_scale, float* loss, float* report, int* pred,
                              float* per_sample, float* d_logit_f32, bf16* d_hi, bf16* d_lo,
                              float* scratch, cudaStream_t s);
+VqaStatus bce_grad_launch(int batch, int A, int num_train_answer, int use_train_mask,
+                          const float* logit, const float* target, float grad_scale,
+                          float* d_logit_f32, bf16* d_hi, bf16* d_lo, cudaStream_t s);
 VqaStatus dropout_mask_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
                               unsigned long long step, unsigned int stream_id, cudaStream_t s);
 

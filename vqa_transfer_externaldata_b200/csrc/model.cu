@@ -1,0 +1,447 @@
+// Forward / backward of the answer-model graph as a fixed sequence of kernel launches on the caller's
+// stream (no allocation, no synchronisation: capturable in a CUDA graph).
+//
+// Graph followed: vqa/model_vlmap_answer.py:102-203 (and model_standard.py:193-285): gather -> v_linear_v
+// -> embedding + GRU -> q_linear_v -> hadamard_attention -> attention_pooling -> pooled_linear_l,
+// q_linear_l, joint_fc (+dropout 0.5) -> WordWeightAnswer / classifier -> soft-score BCE.
+// Backward is the hand-derived chain of SURVEY Appendix A; gradients are produced only for the non-NULL
+// fields of `grads` (vlmap_answer freezes q_linear_l, pooled_linear_l, joint_fc, WordWeightAnswer --
+// vqa/model_vlmap_answer.py:81-89 -- so those layers run dgrad only).
+#include <cuda_runtime.h>
+
+#include "handle.h"
+#include "internal.h"
+
+using namespace vqa;
+
+namespace {
+
+struct GemmB {  // builder with the conventions of VqaGemmDesc
+  VqaGemmDesc d{};
+  GemmB(int M, int N, int K) {
+    d.M = M; d.N = N; d.K = K;
+  }
+  GemmB& a(const Planes& p, long long off, long long ld, bool mn_major) {
+    d.a_hi = p.hi + off;
+    d.a_lo = p.lo ? p.lo + off : nullptr;
+    d.lda = ld;
+    d.a_mn_major = mn_major;
+    return *this;
+  }
+  GemmB& b(const Planes& p, long long off, long long ld, bool mn_major) {
+    d.b_hi = p.hi + off;
+    d.b_lo = p.lo ? p.lo + off : nullptr;
+    d.ldb = ld;
+    d.b_mn_major = mn_major;
+    return *this;
+  }
+  GemmB& bias(const float* p) { d.bias = p; return *this; }
+  GemmB& addend(const float* p, long long ld) { d.addend = p; d.ld_addend = ld; return *this; }
+  GemmB& f32(float* p, long long ld) { d.out_f32 = p; d.ld_f32 = ld; return *this; }
+  GemmB& planes(const Planes& p, long long off, long long ld) {
+    d.out_hi = p.hi + off;
+    d.out_lo = p.lo ? p.lo + off : nullptr;
+    d.ld_bf = ld;
+    return *this;
+  }
+  VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s); }
+};
+
+VqaStatus check_ready(VqaHandle h, const char* who) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "%s: null handle", who);
+  if (!h->ws) return set_error(VQA_ERR_WORKSPACE, "%s: no workspace attached (vqa_set_workspace)", who);
+  return VQA_OK;
+}
+
+// per-phase event markers (no-ops unless vqa_profile_enable(h, 1))
+#define PH_BEGIN(tag)                                                               \
+  do {                                                                              \
+    if (h->profile) VQA_CUDA_CHECK(cudaEventRecord(h->ev[tag][0], s));              \
+  } while (0)
+#define PH_END(tag)                                                                 \
+  do {                                                                              \
+    if (h->profile) {                                                               \
+      VQA_CUDA_CHECK(cudaEventRecord(h->ev[tag][1], s));                            \
+      h->ev_used[tag] = true;                                                       \
+    }                                                                               \
+  } while (0)
+
+VqaStatus copy_out(void* dst, const void* src, size_t bytes, cudaStream_t s) {
+  if (!dst || bytes == 0) return VQA_OK;
+  VQA_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+  return VQA_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_prepare_params"));
+  if (!p) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: null params");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const VqaConfig& c = h->cfg;
+  WeightShadows& w = h->buf.w;
+  struct Item { const float* src; Planes* dst; long long rows, cols; } items[] = {
+      {p->v_w, &w.v_w, c.Dv, c.D},
+      {p->gru_gates_w, &w.gru_gates_w, c.W + c.L, 2LL * c.L},
+      {p->gru_cand_w, &w.gru_cand_w, c.W + c.L, c.L},
+      {p->qv_w, &w.qv_w, c.L, c.D},
+      {p->pl_w, &w.pl_w, c.Dv, c.L},
+      {p->ql_w, &w.ql_w, c.L, c.L},
+      {p->joint_w, &w.joint_w, c.L, c.J},
+      {p->ans_w, &w.ans_w, c.J, c.A},
+  };
+  for (auto& it : items) {
+    if (!it.src) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: null weight pointer");
+    VQA_TRY(split_bf16_launch(it.src, it.rows, it.cols, it.cols, it.dst->hi, it.dst->lo, it.cols, s));
+  }
+  h->params_ready = true;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureBank* bank,
+                              const VqaBatch* batch, const VqaAnswerMasks* masks, uint64_t seed,
+                              uint64_t step, const VqaOutputs* out, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_forward"));
+  if (!p || !bank || !batch || !masks) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: null argument");
+  if (!h->params_ready) return set_error(VQA_ERR_STATE, "vqa_forward: call vqa_prepare_params first");
+  const VqaConfig& c = h->cfg;
+  const int Bn = batch->batch_size, T = batch->q_len_max;
+  if (Bn < 0 || Bn > c.B || T <= 0 || T > c.T)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_forward: batch_size %d (max %d) / q_len_max %d (max %d)", Bn,
+                     c.B, T, c.T);
+  if (!bank->features || !bank->num_boxes || !batch->image_idx || !batch->q_intseq ||
+      !batch->q_intseq_len || !batch->answer_target)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_forward: null batch / bank pointer");
+  h->fwd_valid = false;
+  if (Bn == 0) return VQA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Buffers& b = h->buf;
+  const int K = c.K, Dv = c.Dv, D = c.D, L = c.L, J = c.J, A = c.A, W = c.W, Wp = h->Wpad;
+  const bool fp32 = c.precision == VQA_PREC_FP32;
+  const long long BL = static_cast<long long>(Bn) * L;
+
+  PH_BEGIN(VQA_PH_GATHER);
+  // a0: V = features[image_idx], nbox = num_boxes[image_idx]      (model_vlmap_answer.py:110-123)
+  VQA_TRY(gather_features_launch(bank->features, bank->num_boxes,
+                                 reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi,
+                                 b.v.lo, b.nbox, s));
+  PH_END(VQA_PH_GATHER);
+  PH_BEGIN(VQA_PH_VPROJ_FWD);
+  // a1: Z = V Wv + bv (LayerNorm over (K, D) + ReLU are applied inside the attention kernels)
+  {
+    GemmB g(Bn * K, D, Dv);
+    g.a(b.v, 0, Dv, false).b(b.w.v_w, 0, D, true).bias(p->v_b);
+    if (fp32) g.f32(static_cast<float*>(b.z), D);
+    else { Planes zp; zp.hi = static_cast<bf16*>(b.z); g.planes(zp, 0, D); }
+    VQA_TRY(g.run(h, s));
+  }
+  PH_END(VQA_PH_VPROJ_FWD);
+  PH_BEGIN(VQA_PH_GRU_FWD);
+  // a2: embedding lookup + GRU                                     (:134-137, modules.py:124-140)
+  VQA_TRY(embed_gather_launch(p->embed, batch->q_intseq, Bn, T, T, W, Wp, Bn, b.e.hi, b.e.lo, s));
+  VQA_TRY(GemmB(T * Bn, 2 * L, W).a(b.e, 0, Wp, false).b(b.w.gru_gates_w, 0, 2 * L, true)
+              .bias(p->gru_gates_b).f32(b.xg, 2 * L).run(h, s));
+  VQA_TRY(GemmB(T * Bn, L, W).a(b.e, 0, Wp, false).b(b.w.gru_cand_w, 0, L, true)
+              .bias(p->gru_cand_b).f32(b.xc, L).run(h, s));
+  VQA_TRY(fill_zero_launch(b.h_f32, sizeof(float) * BL, s));
+  VQA_TRY(fill_zero_launch(b.h.hi, sizeof(bf16) * BL, s));
+  if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, s));
+  for (int t = 0; t < T; ++t) {
+    VQA_TRY(GemmB(Bn, 2 * L, L).a(b.h, t * BL, L, false)
+                .b(b.w.gru_gates_w, static_cast<long long>(W) * 2 * L, 2 * L, true)
+                .addend(b.xg + static_cast<long long>(t) * Bn * 2 * L, 2 * L).f32(b.g_pre, 2 * L).run(h, s));
+    VQA_TRY(gru_gates_launch(b.g_pre, b.h_f32 + t * BL, Bn, L, b.r + t * BL, b.u + t * BL,
+                             b.rh.hi + t * BL, b.rh.lo ? b.rh.lo + t * BL : nullptr, s));
+    VQA_TRY(GemmB(Bn, L, L).a(b.rh, t * BL, L, false)
+                .b(b.w.gru_cand_w, static_cast<long long>(W) * L, L, true)
+                .addend(b.xc + static_cast<long long>(t) * Bn * L, L).f32(b.c_pre, L).run(h, s));
+    VQA_TRY(gru_update_launch(b.c_pre, b.h_f32 + t * BL, b.u + t * BL, batch->q_intseq_len, t, Bn, L,
+                              b.c + t * BL, b.h_f32 + (t + 1) * BL, b.h.hi + (t + 1) * BL,
+                              b.h.lo ? b.h.lo + (t + 1) * BL : nullptr, s));
+  }
+  const float* q = b.h_f32 + T * BL;
+  const long long q_off = T * BL;
+
+  PH_END(VQA_PH_GRU_FWD);
+  PH_BEGIN(VQA_PH_QHEADS_FWD);
+  // a3: Hq = relu(LN(q Wqv + b))                                    (:142-145)
+  VQA_TRY(GemmB(Bn, D, L).a(b.h, q_off, L, false).b(b.w.qv_w, 0, D, true).bias(p->qv_b).f32(b.zq, D).run(h, s));
+  {
+    RowLnFwd r{};
+    r.rows = Bn; r.N = D; r.z = b.zq; r.gamma = p->qv_gamma; r.beta = p->qv_beta; r.keep = 1.f;
+    r.y = b.hq; r.mean = b.lnq_mean; r.rstd = b.lnq_rstd;
+    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+  }
+  // a6 (question half): Hl = relu(LN(q Wl + b))                      (:170-174)
+  VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.ql_w, 0, L, true).bias(p->ql_b).f32(b.zl, L).run(h, s));
+  {
+    RowLnFwd r{};
+    r.rows = Bn; r.N = L; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta; r.keep = 1.f;
+    r.y = b.hl; r.mean = b.lnl_mean; r.rstd = b.lnl_rstd;
+    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+  }
+  PH_END(VQA_PH_QHEADS_FWD);
+  PH_BEGIN(VQA_PH_ATTN_FWD);
+  // a4 + a5: attention + pooling                                     (:151-156)
+  {
+    VqaAttnFwd a{};
+    a.batch = Bn; a.z = b.z; a.gamma = p->v_gamma; a.beta = p->v_beta; a.hq = b.hq;
+    a.att_w = p->att_w; a.att_b = p->att_b; a.nbox = b.nbox; a.v_hi = b.v.hi; a.v_lo = b.v.lo;
+    a.seed = seed; a.step = step; a.att = b.att; a.pooled = b.pooled; a.pooled_hi = b.pooled_op.hi;
+    a.pooled_lo = b.pooled_op.lo; a.ln_mean = b.lnv_mean; a.ln_rstd = b.lnv_rstd;
+    VQA_TRY(attn_fwd_launch(a, K, D, Dv, c.precision, c.keep_att, s));
+  }
+  PH_END(VQA_PH_ATTN_FWD);
+  PH_BEGIN(VQA_PH_HEAD_FWD);
+  // a6: Hp = relu(LN(P Wp + b)); X = Hp (.) Hl; Jd = dropout(relu(LN(X Wj + b)), 0.5)   (:163-181)
+  VQA_TRY(GemmB(Bn, L, Dv).a(b.pooled_op, 0, Dv, false).b(b.w.pl_w, 0, L, true).bias(p->pl_b).f32(b.zp, L).run(h, s));
+  {
+    RowLnFwd r{};
+    r.rows = Bn; r.N = L; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta; r.keep = 1.f;
+    r.mul = b.hl; r.y = b.hp; r.out_hi = b.x.hi; r.out_lo = b.x.lo; r.mean = b.lnp_mean; r.rstd = b.lnp_rstd;
+    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+  }
+  VQA_TRY(GemmB(Bn, J, L).a(b.x, 0, L, false).b(b.w.joint_w, 0, J, true).bias(p->joint_b).f32(b.zj, J).run(h, s));
+  {
+    RowLnFwd r{};
+    r.rows = Bn; r.N = J; r.z = b.zj; r.gamma = p->joint_gamma; r.beta = p->joint_beta;
+    r.keep = c.keep_joint; r.seed = seed; r.step = step; r.stream_id = RNG_STREAM_JOINT;
+    r.out_hi = b.jd.hi; r.out_lo = b.jd.lo; r.mean = b.lnj_mean; r.rstd = b.lnj_rstd;
+    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+  }
+  // a7: logits against the (exported vlmap word) weights              (:183-185)
+  VQA_TRY(GemmB(Bn, A, J).a(b.jd, 0, J, false).b(b.w.ans_w, 0, A, true).bias(p->ans_b).f32(b.logit, A).run(h, s));
+  PH_END(VQA_PH_HEAD_FWD);
+  PH_BEGIN(VQA_PH_LOSS);
+  // a8 + a9: loss, pred, report                                       (:192-288)
+  const int use_tm = c.variant == VQA_VARIANT_VLMAP_ANSWER;
+  VQA_TRY(bce_metrics_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target, *masks, 0.f,
+                             b.loss, b.report, b.pred, b.per_sample, nullptr, nullptr, nullptr, b.scratch, s));
+  PH_END(VQA_PH_LOSS);
+  if (out) {
+    VQA_TRY(copy_out(out->loss, b.loss, sizeof(float), s));
+    VQA_TRY(copy_out(out->report, b.report, sizeof(float) * VQA_NUM_REPORT, s));
+    VQA_TRY(copy_out(out->att_score, b.att, sizeof(float) * Bn * K, s));
+    VQA_TRY(copy_out(out->logit, b.logit, sizeof(float) * Bn * A, s));
+    VQA_TRY(copy_out(out->pred, b.pred, sizeof(int) * Bn, s));
+    VQA_TRY(copy_out(out->per_sample, b.per_sample, sizeof(float) * VQA_NUM_PER_SAMPLE * Bn, s));
+    VQA_TRY(copy_out(out->condition, q, sizeof(float) * BL, s));
+    VQA_TRY(copy_out(out->pooled, b.pooled, sizeof(float) * Bn * Dv, s));
+  }
+  h->fwd_valid = true;
+  h->last_batch = Bn;
+  h->last_T = T;
+  h->last_seed = seed;
+  h->last_step = step;
+  h->last_masks = *masks;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* batch,
+                               const VqaParams* g, float loss_scale, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_backward"));
+  if (!p || !batch || !g) return set_error(VQA_ERR_BAD_ARG, "vqa_backward: null argument");
+  if (!h->fwd_valid) return set_error(VQA_ERR_STATE, "vqa_backward: no forward pass to differentiate");
+  const VqaConfig& c = h->cfg;
+  const int Bn = h->last_batch, T = h->last_T;
+  if (batch->batch_size != Bn || batch->q_len_max != T)
+    return set_error(VQA_ERR_STATE, "vqa_backward: batch differs from the one given to vqa_forward");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Buffers& b = h->buf;
+  const int K = c.K, Dv = c.Dv, D = c.D, L = c.L, J = c.J, A = c.A, W = c.W, Wp = h->Wpad;
+  const long long BL = static_cast<long long>(Bn) * L;
+  const uint64_t seed = h->last_seed, step = h->last_step;
+  const int use_tm = c.variant == VQA_VARIANT_VLMAP_ANSWER;
+  const long long q_off = T * BL;
+
+  PH_BEGIN(VQA_PH_HEAD_BWD);
+  // d logit = (sigmoid(x) - z) * train_mask / B
+  VQA_TRY(bce_grad_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target,
+                          loss_scale / static_cast<float>(Bn), b.dlogit_f32, b.dlogit.hi, b.dlogit.lo, s));
+  if (g->ans_w)
+    VQA_TRY(GemmB(J, A, Bn).a(b.jd, 0, J, true).b(b.dlogit, 0, A, true).f32(g->ans_w, A).run(h, s));
+  if (g->ans_b) VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->ans_b, b.scratch, s));
+  // dJd = dlogit Wa^T
+  VQA_TRY(GemmB(Bn, J, A).a(b.dlogit, 0, A, false).b(b.w.ans_w, 0, A, false).f32(b.dJ, J).run(h, s));
+  // joint_fc: dropout, ReLU, LN backward
+  {
+    RowLnBwd r{};
+    r.rows = Bn; r.N = J; r.dout = b.dJ; r.z = b.zj; r.gamma = p->joint_gamma; r.beta = p->joint_beta;
+    r.mean = b.lnj_mean; r.rstd = b.lnj_rstd; r.keep = c.keep_joint; r.seed = seed; r.step = step;
+    r.stream_id = RNG_STREAM_JOINT; r.dz_f32 = b.dzj_f32; r.dz_hi = b.dzj.hi; r.dz_lo = b.dzj.lo;
+    if (g->joint_gamma || g->joint_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (g->joint_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, J, J, g->joint_gamma, b.scratch, s));
+    if (g->joint_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, J, J, g->joint_beta, b.scratch, s));
+  }
+  if (g->joint_w) VQA_TRY(GemmB(L, J, Bn).a(b.x, 0, L, true).b(b.dzj, 0, J, true).f32(g->joint_w, J).run(h, s));
+  if (g->joint_b) VQA_TRY(colsum_launch(b.dzj_f32, Bn, J, J, g->joint_b, b.scratch, s));
+  // dX = dZj Wj^T ; dHp = dX (.) Hl ; dHl = dX (.) Hp
+  VQA_TRY(GemmB(Bn, L, J).a(b.dzj, 0, J, false).b(b.w.joint_w, 0, J, false).f32(b.dX, L).run(h, s));
+  {
+    RowLnBwd r{};
+    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = b.hl; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta;
+    r.mean = b.lnp_mean; r.rstd = b.lnp_rstd; r.keep = 1.f; r.dz_f32 = b.dzp_f32; r.dz_hi = b.dzp.hi;
+    r.dz_lo = b.dzp.lo;
+    if (g->pl_gamma || g->pl_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (g->pl_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->pl_gamma, b.scratch, s));
+    if (g->pl_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->pl_beta, b.scratch, s));
+  }
+  {
+    RowLnBwd r{};
+    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
+    r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi;
+    r.dz_lo = b.dzl.lo;
+    if (g->ql_gamma || g->ql_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (g->ql_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->ql_gamma, b.scratch, s));
+    if (g->ql_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->ql_beta, b.scratch, s));
+  }
+  if (g->pl_w) VQA_TRY(GemmB(Dv, L, Bn).a(b.pooled_op, 0, Dv, true).b(b.dzp, 0, L, true).f32(g->pl_w, L).run(h, s));
+  if (g->pl_b) VQA_TRY(colsum_launch(b.dzp_f32, Bn, L, L, g->pl_b, b.scratch, s));
+  if (g->ql_w) VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dzl, 0, L, true).f32(g->ql_w, L).run(h, s));
+  if (g->ql_b) VQA_TRY(colsum_launch(b.dzl_f32, Bn, L, L, g->ql_b, b.scratch, s));
+  // dP = dZp Wp^T ; dq = dZl Wl^T
+  VQA_TRY(GemmB(Bn, Dv, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Dv).run(h, s));
+  VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, s));
+  PH_END(VQA_PH_HEAD_BWD);
+  PH_BEGIN(VQA_PH_ATTN_BWD);
+  // attention block backward
+  {
+    VqaAttnBwd a{};
+    a.batch = Bn; a.z = b.z; a.gamma = p->v_gamma; a.beta = p->v_beta; a.hq = b.hq; a.att_w = p->att_w;
+    a.nbox = b.nbox; a.v_hi = b.v.hi; a.v_lo = b.v.lo; a.seed = seed; a.step = step; a.att = b.att;
+    a.ln_mean = b.lnv_mean; a.ln_rstd = b.lnv_rstd; a.d_pooled = b.dP; a.dz_hi = b.dzv.hi;
+    a.dz_lo = b.dzv.lo; a.d_hq = b.dhq; a.d_att_w = g->att_w; a.d_att_b = g->att_b;
+    a.d_gamma = g->v_gamma; a.d_beta = g->v_beta; a.d_bias = g->v_b;
+    VQA_TRY(attn_bwd_launch(a, K, D, Dv, c.precision, c.keep_att, b.attn_part, s));
+  }
+  PH_END(VQA_PH_ATTN_BWD);
+  PH_BEGIN(VQA_PH_QV_BWD);
+  // q_linear_v backward
+  {
+    RowLnBwd r{};
+    r.rows = Bn; r.N = D; r.dout = b.dhq; r.z = b.zq; r.gamma = p->qv_gamma; r.beta = p->qv_beta;
+    r.mean = b.lnq_mean; r.rstd = b.lnq_rstd; r.keep = 1.f; r.dz_f32 = b.dzq_f32; r.dz_hi = b.dzq.hi;
+    r.dz_lo = b.dzq.lo;
+    if (g->qv_gamma || g->qv_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (g->qv_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, D, D, g->qv_gamma, b.scratch, s));
+    if (g->qv_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, D, D, g->qv_beta, b.scratch, s));
+  }
+  if (g->qv_w) VQA_TRY(GemmB(L, D, Bn).a(b.h, q_off, L, true).b(b.dzq, 0, D, true).f32(g->qv_w, D).run(h, s));
+  if (g->qv_b) VQA_TRY(colsum_launch(b.dzq_f32, Bn, D, D, g->qv_b, b.scratch, s));
+  VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
+  PH_END(VQA_PH_QV_BWD);
+  // dWv = V^T dZv   (the largest weight gradient: [Dv, D] over B*K rows)
+  PH_BEGIN(VQA_PH_VPROJ_WGRAD);
+  if (g->v_w) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, s));
+  PH_END(VQA_PH_VPROJ_WGRAD);
+
+  // GRU: back-propagation through time from dq
+  const bool need_gru = g->gru_gates_w || g->gru_gates_b || g->gru_cand_w || g->gru_cand_b || g->embed;
+  if (need_gru) {
+    PH_BEGIN(VQA_PH_GRU_BWD);
+    float* dh_cur = b.dq;
+    int pp = 0;
+    for (int t = T - 1; t >= 0; --t) {
+      VQA_TRY(gru_bwd_update_launch(dh_cur, b.h_f32 + t * BL, b.u + t * BL, b.c + t * BL,
+                                    batch->q_intseq_len, t, Bn, L, b.du, b.dh_part, b.dC_f32 + t * BL,
+                                    b.dC.hi + t * BL, b.dC.lo ? b.dC.lo + t * BL : nullptr, s));
+      VQA_TRY(GemmB(Bn, L, L).a(b.dC, t * BL, L, false)
+                  .b(b.w.gru_cand_w, static_cast<long long>(W) * L, L, false).f32(b.dRH, L).run(h, s));
+      VQA_TRY(gru_bwd_gates_launch(b.dRH, b.du, b.h_f32 + t * BL, b.r + t * BL, b.u + t * BL,
+                                   batch->q_intseq_len, t, Bn, L, b.dh_part, b.dG_f32 + 2 * t * BL,
+                                   b.dG.hi + 2 * t * BL, b.dG.lo ? b.dG.lo + 2 * t * BL : nullptr, s));
+      float* dh_next = b.dh[pp];
+      pp ^= 1;
+      VQA_TRY(GemmB(Bn, L, 2 * L).a(b.dG, 2 * t * BL, 2 * L, false)
+                  .b(b.w.gru_gates_w, static_cast<long long>(W) * 2 * L, 2 * L, false)
+                  .addend(b.dh_part, L).f32(dh_next, L).run(h, s));
+      dh_cur = dh_next;
+    }
+    PH_END(VQA_PH_GRU_BWD);
+    PH_BEGIN(VQA_PH_GRU_WGRAD);
+    const int TB = T * Bn;
+    if (g->gru_gates_w) {
+      VQA_TRY(GemmB(L, 2 * L, TB).a(b.h, 0, L, true).b(b.dG, 0, 2 * L, true)
+                  .f32(g->gru_gates_w + static_cast<long long>(W) * 2 * L, 2 * L).run(h, s));
+      VQA_TRY(GemmB(W, 2 * L, TB).a(b.e, 0, Wp, true).b(b.dG, 0, 2 * L, true).f32(g->gru_gates_w, 2 * L).run(h, s));
+    }
+    if (g->gru_cand_w) {
+      VQA_TRY(GemmB(L, L, TB).a(b.rh, 0, L, true).b(b.dC, 0, L, true)
+                  .f32(g->gru_cand_w + static_cast<long long>(W) * L, L).run(h, s));
+      VQA_TRY(GemmB(W, L, TB).a(b.e, 0, Wp, true).b(b.dC, 0, L, true).f32(g->gru_cand_w, L).run(h, s));
+    }
+    if (g->gru_gates_b) VQA_TRY(colsum_launch(b.dG_f32, TB, 2 * L, 2 * L, g->gru_gates_b, b.scratch, s));
+    if (g->gru_cand_b) VQA_TRY(colsum_launch(b.dC_f32, TB, L, L, g->gru_cand_b, b.scratch, s));
+    PH_END(VQA_PH_GRU_WGRAD);
+    PH_BEGIN(VQA_PH_EMBED_BWD);
+    if (g->embed) {
+      // dE = dG Wg[:W]^T + dC Wc[:W]^T ; d embed = scatter_add(q_intseq, dE)
+      VQA_TRY(GemmB(TB, W, 2 * L).a(b.dG, 0, 2 * L, false).b(b.w.gru_gates_w, 0, 2 * L, false)
+                  .f32(b.dE, Wp).run(h, s));
+      VQA_TRY(GemmB(TB, W, L).a(b.dC, 0, L, false).b(b.w.gru_cand_w, 0, L, false).addend(b.dE, Wp)
+                  .f32(b.dE, Wp).run(h, s));
+      VQA_TRY(fill_zero_launch(g->embed, sizeof(float) * c.Vq * W, s));
+      VQA_TRY(embed_scatter_add_launch(b.dE, Wp, batch->q_intseq, batch->q_intseq_len, Bn, T, T, W, Bn,
+                                       g->embed, s));
+    }
+    PH_END(VQA_PH_EMBED_BWD);
+  }
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step,
+                                    uint8_t* att_mask, uint8_t* joint_mask, void* stream) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_dropout_masks: null handle");
+  const VqaConfig& c = h->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (att_mask)
+    VQA_TRY(dropout_mask_launch(att_mask, static_cast<long long>(batch) * c.K * c.D, c.keep_att, seed, step,
+                                RNG_STREAM_ATT, s));
+  if (joint_mask)
+    VQA_TRY(dropout_mask_launch(joint_mask, static_cast<long long>(batch) * c.J, c.keep_joint, seed, step,
+                                RNG_STREAM_JOINT, s));
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_adam_step(VqaHandle h, float* param, const float* grad, float* m, float* v, int64_t n,
+                                float lr, float beta1, float beta2, float eps, float clip_norm, int64_t t,
+                                float* grad_norm_out, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_adam_step"));
+  return adam_step_launch(param, grad, m, v, n, lr, beta1, beta2, eps, clip_norm, t, grad_norm_out,
+                          h->buf.scratch, h->num_sms, static_cast<cudaStream_t>(stream));
+}
+
+VQA_API VqaStatus vqa_attn_fwd(VqaHandle h, const VqaAttnFwd* a, void* stream) {
+  if (!h || !a) return set_error(VQA_ERR_BAD_ARG, "vqa_attn_fwd: null argument");
+  const VqaConfig& c = h->cfg;
+  return attn_fwd_launch(*a, c.K, c.D, c.Dv, c.precision, c.keep_att, static_cast<cudaStream_t>(stream));
+}
+
+VQA_API VqaStatus vqa_attn_bwd(VqaHandle h, const VqaAttnBwd* a, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_attn_bwd"));
+  if (!a) return set_error(VQA_ERR_BAD_ARG, "vqa_attn_bwd: null argument");
+  const VqaConfig& c = h->cfg;
+  if (a->batch > c.B) return set_error(VQA_ERR_BAD_SHAPE, "vqa_attn_bwd: batch exceeds config.B");
+  return attn_bwd_launch(*a, c.K, c.D, c.Dv, c.precision, c.keep_att, h->buf.attn_part,
+                         static_cast<cudaStream_t>(stream));
+}
+
+VQA_API VqaStatus vqa_bce_metrics(VqaHandle h, int32_t batch, const float* logit, const float* target,
+                                  const VqaAnswerMasks* masks, float grad_scale, float* loss, float* report,
+                                  int32_t* pred, float* per_sample, float* d_logit, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_bce_metrics"));
+  if (!masks) return set_error(VQA_ERR_BAD_ARG, "vqa_bce_metrics: null masks");
+  const VqaConfig& c = h->cfg;
+  if (batch > c.B) return set_error(VQA_ERR_BAD_SHAPE, "vqa_bce_metrics: batch exceeds config.B");
+  return bce_metrics_launch(batch, c.A, c.num_train_answer, c.variant == VQA_VARIANT_VLMAP_ANSWER, logit, target,
+                            *masks, grad_scale, loss, report, pred, per_sample, d_logit, nullptr, nullptr,
+                            h->buf.scratch, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,328 @@
+"""Host-side runtime over the C ABI: one `Engine` per GPU / process.
+
+PyTorch is plumbing here (device memory, streams, pinned staging buffers, torch.distributed); every
+kernel on the path is in libvqa_answer_b200.so and is reached through ctypes with raw pointers.
+"""
+import ctypes as C
+from dataclasses import dataclass, asdict
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+# TF checkpoint variable names (vqa/model_vlmap_answer.py scopes via vlmap/modules.py:78-86,126,596,632-647)
+TF_NAMES = {
+    "embed": "LearnGloVe/embed_map",
+    "v_w": "v_linear_v/fc/weights", "v_b": "v_linear_v/fc/biases",
+    "v_gamma": "v_linear_v/LayerNorm/gamma", "v_beta": "v_linear_v/LayerNorm/beta",
+    "gru_gates_w": "encode_L/rnn/gru_cell/gates/kernel", "gru_gates_b": "encode_L/rnn/gru_cell/gates/bias",
+    "gru_cand_w": "encode_L/rnn/gru_cell/candidate/kernel", "gru_cand_b": "encode_L/rnn/gru_cell/candidate/bias",
+    "qv_w": "q_linear_v/fc/weights", "qv_b": "q_linear_v/fc/biases",
+    "qv_gamma": "q_linear_v/LayerNorm/gamma", "qv_beta": "q_linear_v/LayerNorm/beta",
+    "att_w": "hadamard_attention/compute/score/fc/weights",
+    "att_b": "hadamard_attention/compute/score/fc/biases",
+    "pl_w": "pooled_linear_l/fc/weights", "pl_b": "pooled_linear_l/fc/biases",
+    "pl_gamma": "pooled_linear_l/LayerNorm/gamma", "pl_beta": "pooled_linear_l/LayerNorm/beta",
+    "ql_w": "q_linear_l/fc/weights", "ql_b": "q_linear_l/fc/biases",
+    "ql_gamma": "q_linear_l/LayerNorm/gamma", "ql_beta": "q_linear_l/LayerNorm/beta",
+    "joint_w": "joint_fc/fc/weights", "joint_b": "joint_fc/fc/biases",
+    "joint_gamma": "joint_fc/LayerNorm/gamma", "joint_beta": "joint_fc/LayerNorm/beta",
+    "ans_w": "WordWeightAnswer/fc/weights", "ans_b": "WordWeightAnswer/fc/biases",
+}
+_REASONING = ("pl_", "ql_", "joint_")
+
+
+def tf_name(field, variant):
+    """Checkpoint variable name of a parameter field for a model_type."""
+    if variant == "standard":  # vqa/model_standard.py:251-275
+        if field.startswith(_REASONING):
+            return "reasoning/" + TF_NAMES[field]
+        if field == "ans_w":
+            return "reasoning/classifier/fc/weights"
+        if field == "ans_b":
+            return "reasoning/classifier/fc/biases"
+    return TF_NAMES[field]
+
+
+@dataclass
+class AnswerModelConfig:
+    B: int = 512
+    K: int = 36
+    Dv: int = 2048
+    D: int = 1024          # V_DIM
+    L: int = 1024          # L_DIM
+    J: int = 2048
+    A: int = 3000
+    T: int = 14
+    W: int = 300           # W_DIM
+    Vq: int = 8192
+    num_train_answer: int = 2250
+    variant: str = "vlmap_answer"   # vqa/importer.py model_type: 'vlmap_answer' | 'standard'
+    precision: str = "bf16"         # 'bf16' | 'fp32'
+    keep_att: float = 0.8
+    keep_joint: float = 0.5
+
+    def shape(self, field):
+        c = asdict(self)
+        from .synthetic import PARAM_SHAPES
+        return PARAM_SHAPES[field](c)
+
+    def to_c(self):
+        return L.VqaConfig(
+            B=self.B, K=self.K, Dv=self.Dv, D=self.D, L=self.L, J=self.J, A=self.A, T=self.T, W=self.W,
+            Vq=self.Vq, num_train_answer=self.num_train_answer,
+            variant={"vlmap_answer": L.VARIANT_VLMAP_ANSWER, "standard": L.VARIANT_STANDARD}[self.variant],
+            precision={"bf16": L.PREC_BF16, "fp32": L.PREC_FP32}[self.precision],
+            keep_att=self.keep_att, keep_joint=self.keep_joint)
+
+
+def frozen_fields(variant):
+    """filter_train_vars: vqa/model_vlmap_answer.py:81-89 drops q_linear_l, pooled_linear_l, joint_fc,
+    WordWeightAnswer; vqa/model_standard.py:80-84 trains everything."""
+    if variant == "standard":
+        return set()
+    return {f for f in L.PARAM_FIELDS if TF_NAMES[f].split("/")[0] in
+            ("q_linear_l", "pooled_linear_l", "joint_fc", "WordWeightAnswer")}
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class ParamStore:
+    """fp32 master parameters in TF layout inside ONE flat device buffer: trainable tensors first (so the
+    gradient all-reduce and the fused clip+Adam step run over one contiguous slice), frozen after."""
+
+    def __init__(self, cfg, device):
+        self.cfg = cfg
+        frozen = frozen_fields(cfg.variant)
+        self.trainable = [f for f in L.PARAM_FIELDS if f not in frozen]
+        self.frozen = [f for f in L.PARAM_FIELDS if f in frozen]
+        self.offsets, off = {}, 0
+        for f in self.trainable:
+            n = int(np.prod(cfg.shape(f)))
+            self.offsets[f] = (off, n)
+            off += _align(n)  # 256-byte aligned starts (float4 / TMA friendly)
+        self.n_train = off
+        for f in self.frozen:
+            n = int(np.prod(cfg.shape(f)))
+            self.offsets[f] = (off, n)
+            off += _align(n)
+        self.n_total = off
+        self.flat = torch.zeros(self.n_total, dtype=torch.float32, device=device)
+        self.grad = torch.zeros(self.n_train, dtype=torch.float32, device=device)
+        self.adam_m = None
+        self.adam_v = None
+        self.views = {f: self.flat[o:o + n].view(cfg.shape(f)) for f, (o, n) in self.offsets.items()}
+        self.grad_views = {f: self.grad[self.offsets[f][0]:self.offsets[f][0] + self.offsets[f][1]]
+                           .view(cfg.shape(f)) for f in self.trainable}
+
+    def load(self, params):
+        """params: dict field -> array-like (numpy / torch), fp32, TF layout."""
+        for f in L.PARAM_FIELDS:
+            t = torch.as_tensor(np.asarray(params[f], dtype=np.float32))
+            if tuple(t.shape) != tuple(self.cfg.shape(f)):
+                raise ValueError(f"{f}: shape {tuple(t.shape)} != {tuple(self.cfg.shape(f))}")
+            self.views[f].copy_(t)
+
+    def by_tf_name(self):
+        return {tf_name(f, self.cfg.variant): self.views[f] for f in L.PARAM_FIELDS}
+
+    def c_params(self):
+        p = L.VqaParams()
+        for f in L.PARAM_FIELDS:
+            setattr(p, f, self.views[f].data_ptr())
+        return p
+
+    def c_grads(self):
+        g = L.VqaParams()
+        for f in L.PARAM_FIELDS:
+            setattr(g, f, self.grad_views[f].data_ptr() if f in self.grad_views else None)
+        return g
+
+
+class Engine:
+    """Owns the C handle, its workspace, the parameter store, the feature bank and static batch buffers."""
+
+    def __init__(self, cfg, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("vqa_transfer_externaldata_b200 needs a CUDA (sm_100a) device; there is no CPU path")
+        self.lib = L.load()
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        torch.cuda.set_device(self.device)
+        self._cfg_c = cfg.to_c()
+        self.h = C.c_void_p()
+        L.check(self.lib.vqa_create(C.byref(self._cfg_c), C.byref(self.h)))
+        nbytes = C.c_uint64()
+        L.check(self.lib.vqa_workspace_bytes(self.h, C.byref(nbytes)))
+        self.workspace = torch.empty(nbytes.value + 256, dtype=torch.uint8, device=self.device)
+        base = (self.workspace.data_ptr() + 255) // 256 * 256
+        L.check(self.lib.vqa_set_workspace(self.h, C.c_void_p(base), nbytes.value))
+        self.params = ParamStore(cfg, self.device)
+        self._p = self.params.c_params()
+        self._g = self.params.c_grads()
+        dev = self.device
+        # static device-side batch (addresses stay fixed -> the whole step can be captured in a CUDA graph)
+        self.d_image_idx = torch.zeros(cfg.B, dtype=torch.int64, device=dev)
+        self.d_q = torch.zeros(cfg.B * cfg.T, dtype=torch.int32, device=dev)
+        self.d_qlen = torch.zeros(cfg.B, dtype=torch.int32, device=dev)
+        self.d_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32, device=dev)
+        # pinned host staging for the per-step H2D copies
+        self.h_image_idx = torch.zeros(cfg.B, dtype=torch.int64).pin_memory()
+        self.h_q = torch.zeros(cfg.B * cfg.T, dtype=torch.int32).pin_memory()
+        self.h_qlen = torch.zeros(cfg.B, dtype=torch.int32).pin_memory()
+        self.h_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32).pin_memory()
+        # outputs
+        self.o_loss = torch.zeros(1, device=dev)
+        self.o_report = torch.zeros(len(L.REPORT_KEYS), device=dev)
+        self.o_att = torch.zeros(cfg.B, cfg.K, device=dev)
+        self.o_logit = torch.zeros(cfg.B, cfg.A, device=dev)
+        self.o_pred = torch.zeros(cfg.B, dtype=torch.int32, device=dev)
+        self.o_per_sample = torch.zeros(len(L.PER_SAMPLE_KEYS) * cfg.B, device=dev)
+        self.o_condition = torch.zeros(cfg.B, cfg.L, device=dev)
+        self.o_pooled = torch.zeros(cfg.B, cfg.Dv, device=dev)
+        self.h_scalars = torch.zeros(1 + len(L.REPORT_KEYS)).pin_memory()
+        self.grad_norm = torch.zeros(1, device=dev)
+        self._outs = L.VqaOutputs(
+            loss=self.o_loss.data_ptr(), report=self.o_report.data_ptr(), att_score=self.o_att.data_ptr(),
+            logit=self.o_logit.data_ptr(), pred=self.o_pred.data_ptr(),
+            per_sample=self.o_per_sample.data_ptr(), condition=self.o_condition.data_ptr(),
+            pooled=self.o_pooled.data_ptr())
+        self._outs_min = L.VqaOutputs(loss=self.o_loss.data_ptr(), report=self.o_report.data_ptr())
+        self.bank = None
+        self.masks = None
+        self.batch_size = 0
+        self.q_len_max = cfg.T
+        self.adam_t = 0
+
+    def close(self):
+        if self.h:
+            self.lib.vqa_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- residents ------------------------------------------------------------------------------
+    def set_feature_bank(self, features, num_boxes):
+        """image_features [N,K,Dv] fp32 + num_boxes [N] -> HBM once (the reference keeps them in host RAM
+        and ships 151 MB per step, vqa/model_vlmap_answer.py:57-70,110-117)."""
+        f = torch.as_tensor(features)
+        if f.dim() != 3 or f.shape[1] != self.cfg.K or f.shape[2] != self.cfg.Dv:
+            raise ValueError(f"feature bank shape {tuple(f.shape)} != [N, {self.cfg.K}, {self.cfg.Dv}]")
+        self.bank_features = f.to(self.device, dtype=torch.float32).contiguous()
+        self.bank_num_boxes = torch.as_tensor(np.asarray(num_boxes)).to(self.device, dtype=torch.int32).contiguous()
+        self.bank = L.VqaFeatureBank(features=self.bank_features.data_ptr(),
+                                     num_boxes=self.bank_num_boxes.data_ptr(),
+                                     num_images=self.bank_features.shape[0])
+
+    def set_answer_masks(self, is_object, is_attribute, answer_exist):
+        dev = self.device
+        self._m = [torch.as_tensor(np.asarray(x, dtype=np.float32)).to(dev).contiguous()
+                   for x in (is_object, is_attribute, answer_exist)]
+        for m in self._m:
+            if m.numel() != self.cfg.A:
+                raise ValueError("answer mask length != A")
+        self.masks = L.VqaAnswerMasks(is_object=self._m[0].data_ptr(), is_attribute=self._m[1].data_ptr(),
+                                      answer_exist=self._m[2].data_ptr())
+
+    def load_params(self, params):
+        self.params.load(params)
+        self.prepare_params()
+
+    def prepare_params(self):
+        L.check(self.lib.vqa_prepare_params(self.h, C.byref(self._p), self._stream()))
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    # ---- batch ----------------------------------------------------------------------------------
+    def stage_batch(self, batch):
+        """Host batch dict (keys of input_ops_vqa_tf_record_memft.py:47-59) -> pinned staging -> device.
+        Returns (h2d_bytes). Asynchronous on the current stream."""
+        idx = np.asarray(batch["image_idx"], dtype=np.int64)
+        q = np.asarray(batch["q_intseq"], dtype=np.int32)
+        ql = np.asarray(batch["q_intseq_len"], dtype=np.int32)
+        tg = np.asarray(batch["answer_target"], dtype=np.float32)
+        Bn, T = q.shape
+        if Bn > self.cfg.B or T > self.cfg.T:
+            raise ValueError(f"batch [{Bn}, T={T}] exceeds config (B={self.cfg.B}, T={self.cfg.T})")
+        if tg.shape != (Bn, self.cfg.A):
+            raise ValueError(f"answer_target shape {tg.shape} != ({Bn}, {self.cfg.A})")
+        self.h_image_idx[:Bn].copy_(torch.from_numpy(idx))
+        self.h_q[:Bn * T].copy_(torch.from_numpy(q.reshape(-1)))
+        self.h_qlen[:Bn].copy_(torch.from_numpy(ql))
+        self.h_target[:Bn * self.cfg.A].copy_(torch.from_numpy(tg.reshape(-1)))
+        return self.upload_staged(Bn, T)
+
+    def upload_staged(self, Bn, T):
+        A = self.cfg.A
+        self.d_image_idx[:Bn].copy_(self.h_image_idx[:Bn], non_blocking=True)
+        self.d_q[:Bn * T].copy_(self.h_q[:Bn * T], non_blocking=True)
+        self.d_qlen[:Bn].copy_(self.h_qlen[:Bn], non_blocking=True)
+        self.d_target[:Bn * A].copy_(self.h_target[:Bn * A], non_blocking=True)
+        self.batch_size, self.q_len_max = Bn, T
+        return Bn * 8 + Bn * T * 4 + Bn * 4 + Bn * A * 4
+
+    def _c_batch(self):
+        return L.VqaBatch(batch_size=self.batch_size, q_len_max=self.q_len_max,
+                          image_idx=self.d_image_idx.data_ptr(), q_intseq=self.d_q.data_ptr(),
+                          q_intseq_len=self.d_qlen.data_ptr(), answer_target=self.d_target.data_ptr())
+
+    # ---- the path -------------------------------------------------------------------------------
+    def forward(self, seed=0, step=0, full_outputs=True):
+        if self.bank is None or self.masks is None:
+            raise RuntimeError("set_feature_bank() and set_answer_masks() first")
+        b = self._c_batch()
+        outs = self._outs if full_outputs else self._outs_min
+        L.check(self.lib.vqa_forward(self.h, C.byref(self._p), C.byref(self.bank), C.byref(b),
+                                     C.byref(self.masks), C.c_uint64(seed), C.c_uint64(step), C.byref(outs),
+                                     self._stream()))
+
+    def backward(self, loss_scale=1.0):
+        b = self._c_batch()
+        L.check(self.lib.vqa_backward(self.h, C.byref(self._p), C.byref(b), C.byref(self._g),
+                                      C.c_float(loss_scale), self._stream()))
+
+    def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip_norm=20.0):
+        """optimize_loss(Adam, clip_gradients=20.0) over the trainable slice (vqa/trainer.py:106-114)."""
+        ps = self.params
+        if ps.adam_m is None:
+            ps.adam_m = torch.zeros_like(ps.grad)
+            ps.adam_v = torch.zeros_like(ps.grad)
+        self.adam_t += 1
+        L.check(self.lib.vqa_adam_step(self.h, ps.flat.data_ptr(), ps.grad.data_ptr(), ps.adam_m.data_ptr(),
+                                       ps.adam_v.data_ptr(), ps.n_train, lr, beta1, beta2, eps, clip_norm,
+                                       self.adam_t, self.grad_norm.data_ptr(), self._stream()))
+        self.prepare_params()
+
+    def dropout_masks(self, seed, step, batch=None):
+        Bn = self.batch_size if batch is None else batch
+        att = torch.empty(Bn, self.cfg.K, self.cfg.D, dtype=torch.uint8, device=self.device)
+        joint = torch.empty(Bn, self.cfg.J, dtype=torch.uint8, device=self.device)
+        L.check(self.lib.vqa_dropout_masks(self.h, Bn, C.c_uint64(seed), C.c_uint64(step), att.data_ptr(),
+                                           joint.data_ptr(), self._stream()))
+        return att, joint
+
+    def read_scalars(self):
+        """D2H of loss + report (pinned, synchronises the current stream)."""
+        self.h_scalars[:1].copy_(self.o_loss, non_blocking=True)
+        self.h_scalars[1:].copy_(self.o_report, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        vals = self.h_scalars.tolist()
+        return vals[0], dict(zip(L.REPORT_KEYS, vals[1:]))
+
+    def outputs(self):
+        Bn = self.batch_size
+        ps = self.o_per_sample[:len(L.PER_SAMPLE_KEYS) * Bn].view(len(L.PER_SAMPLE_KEYS), Bn)
+        out = {"att_score": self.o_att[:Bn], "logit": self.o_logit[:Bn], "pred": self.o_pred[:Bn]}
+        out.update({k: ps[i] for i, k in enumerate(L.PER_SAMPLE_KEYS)})
+        return out
+
+    def launch_count(self):
+        return int(self.lib.vqa_launch_count())

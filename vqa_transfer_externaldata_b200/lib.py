@@ -27,6 +27,8 @@ PER_SAMPLE_KEYS = [
     "test_attr_max_score",
 ]
 
+NUM_PHASES = 14
+
 PARAM_FIELDS = [
     "embed", "v_w", "v_b", "v_gamma", "v_beta", "gru_gates_w", "gru_gates_b", "gru_cand_w",
     "gru_cand_b", "qv_w", "qv_b", "qv_gamma", "qv_beta", "att_w", "att_b", "pl_w", "pl_b",
@@ -115,6 +117,9 @@ SYMBOLS = {
     "vqa_dropout_masks": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P]),
     "vqa_adam_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int64, _P, _P]),
+    "vqa_profile_enable": (C.c_int32, [_P, C.c_int32]),
+    "vqa_profile_read": (C.c_int32, [_P, C.POINTER(C.c_float)]),
+    "vqa_phase_name": (C.c_char_p, [C.c_int32]),
     "vqa_gemm": (C.c_int32, [_P, C.POINTER(VqaGemmDesc), _P]),
     "vqa_split_bf16": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P]),
     "vqa_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaAttnFwd), _P]),

@@ -1,0 +1,224 @@
+"""`Model`: the host-side mirror of the reference's model classes for this path.
+
+Same constructor signature and attributes as vqa/model_vlmap_answer.py:17-79 / vqa/model_standard.py:
+    Model(batch, config, is_train=True, image_features=None)
+    .loss .losses .report .output .mid_result .heavy_output .vocab .answer_dict
+    filter_train_vars(vars), filter_transfer_vars(vars)
+The reference builds a TF graph and evaluates it with session.run; here `forward()` / `backward()` /
+`train_step()` run the CUDA path eagerly on the batch bound at construction (or one passed in).
+"""
+import os
+import pickle
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+from . import lib as L
+from .engine import AnswerModelConfig, Engine, TF_NAMES, frozen_fields, tf_name
+from . import wordweights
+
+W_DIM = 300   # vqa/model_vlmap_answer.py:10-12
+L_DIM = 1024
+V_DIM = 1024
+
+
+def _load_pickle(path):
+    """vocab.pkl / answer_dict.pkl are Python-2 cPickle files (vqa/model_vlmap_answer.py:34-36)."""
+    with open(path, "rb") as f:
+        return pickle.load(f, encoding="latin1")
+
+
+def get_dummy_data():
+    """util.get_dummy_data (util/__init__.py:5-17): the --debug fixture, 500 x 36 x 2048 zeros, 1 box each."""
+    bn, bs, dim = 500, 36, 2048
+    return {"features": np.zeros([bn, bs, dim], np.float32), "spatials": np.zeros([bn, bs, 6], np.float32),
+            "normal_boxes": np.zeros([bn, bs, 4], np.float32), "num_boxes": np.ones([bn], np.int32),
+            "max_box_num": bs, "vfeat_dim": dim}
+
+
+class Model(object):
+    MODEL_TYPE = "vlmap_answer"
+
+    def __init__(self, batch, config, is_train=True, image_features=None):
+        self.batch = batch
+        self.config = config
+        self.image_dir = getattr(config, "image_dir", None)
+        self.is_train = is_train
+        self.word_weight_dir = getattr(config, "vlmap_word_weight_dir", None)
+        self.losses, self.report, self.mid_result = {}, {}, {}
+        self.output, self.heavy_output, self.vis_image = {}, {}, {}
+        self.loss = None
+
+        # vocab / answer_dict: pickles when paths are given (reference), objects otherwise (synthetic)
+        self.vocab = getattr(config, "vocab", None)
+        if self.vocab is None:
+            self.vocab = _load_pickle(config.vocab_path)
+        self.answer_dict = getattr(config, "answer_dict", None)
+        if self.answer_dict is None:
+            self.answer_dict = _load_pickle(os.path.join(config.tf_record_dir, "answer_dict.pkl"))
+        self.num_answer = len(self.answer_dict["vocab"])
+        self.num_train_answer = int(self.answer_dict["num_train_answer"])
+        A = self.num_answer
+        self.train_answer_mask = (np.arange(A) < self.num_train_answer).astype(np.float32)[None]
+        self.test_answer_mask = 1.0 - self.train_answer_mask
+        self.obj_answer_mask = np.asarray(self.answer_dict["is_object"], np.float32)[None]
+        self.attr_answer_mask = np.asarray(self.answer_dict["is_attribute"], np.float32)[None]
+        self.answer_exist_mask = wordweights.answer_exist_mask(self.answer_dict, self.word_weight_dir)[None]
+
+        # feature bank (vqa/model_vlmap_answer.py:54-77)
+        if getattr(config, "debug", False):
+            image_features = get_dummy_data()
+        elif image_features is None:
+            image_features = wordweights.load_feature_bank(config.vfeat_path)
+        self.features = image_features["features"]
+        self.num_boxes = image_features["num_boxes"]
+        self.max_box_num = int(image_features["max_box_num"])
+        self.vfeat_dim = int(image_features["vfeat_dim"])
+        self.spatials = image_features.get("spatials")
+        self.normal_boxes = image_features.get("normal_boxes")
+
+        self.build()
+
+    # ---- reference API: which variables train / transfer (by top-level scope) ------------------
+    def filter_train_vars(self, trainable_vars):
+        frozen_scopes = {TF_NAMES[f].split("/")[0] for f in frozen_fields(self.MODEL_TYPE)}
+        return [v for v in trainable_vars if _name(v).split("/")[0] not in frozen_scopes]
+
+    def filter_transfer_vars(self, all_vars):
+        if self.MODEL_TYPE == "standard":  # vqa/model_standard.py:86-93
+            scopes = ("encode_L", "GloVe")
+        else:  # vqa/model_vlmap_answer.py:91-100
+            scopes = ("q_linear_l", "pooled_linear_l", "joint_fc")
+        return [v for v in all_vars if _name(v).split("/")[0] in scopes]
+
+    # ---- graph construction == engine construction ---------------------------------------------
+    def build(self):
+        cfgd = self.config
+        T = int(getattr(cfgd, "max_q_len", 14))
+        B = int(getattr(cfgd, "batch_size", 512))
+        self.engine_config = AnswerModelConfig(
+            B=B, K=self.max_box_num, Dv=self.vfeat_dim, D=int(getattr(cfgd, "v_dim", V_DIM)),
+            L=int(getattr(cfgd, "l_dim", L_DIM)), J=2 * int(getattr(cfgd, "l_dim", L_DIM)),
+            A=self.num_answer, T=T, W=int(getattr(cfgd, "w_dim", W_DIM)), Vq=len(self.vocab["vocab"]),
+            num_train_answer=self.num_train_answer, variant=self.MODEL_TYPE,
+            precision=getattr(cfgd, "precision", "bf16"))
+        self.engine = Engine(self.engine_config, device=getattr(cfgd, "device", None))
+        self.engine.set_feature_bank(self.features, self.num_boxes)
+        self.engine.set_answer_masks(self.obj_answer_mask[0], self.attr_answer_mask[0], self.answer_exist_mask[0])
+        params = getattr(cfgd, "init_params", None)
+        if params is None:
+            params = self.initial_params(seed=int(getattr(cfgd, "seed", 123)))
+        self.engine.load_params(params)
+        self.seed = int(getattr(cfgd, "seed", 123))
+        self.global_step = 0
+        self._dp = None
+        return self.loss
+
+    def initial_params(self, seed):
+        """TF-default initialisers + the WordWeightAnswer remap from the exported word weights."""
+        from .synthetic import init_params
+        c = {k: getattr(self.engine_config, k) for k in
+             ("B", "K", "Dv", "D", "L", "J", "A", "T", "W", "Vq", "num_train_answer")}
+        p, _ = init_params(c, seed=seed, variant="standard")  # Xavier head; replaced below for vlmap_answer
+        glove = getattr(self.config, "glove_embed", None)
+        if glove is not None:  # LearnGloVe (vlmap/modules.py:415-448): rows by vocabulary word
+            p["embed"] = np.asarray(glove, np.float32)
+        if self.MODEL_TYPE != "standard":
+            w, b = wordweights.word_weight_answer(self.engine_config.J, self.answer_dict, self.word_weight_dir)
+            p["ans_w"], p["ans_b"] = w, b
+        return p
+
+    # ---- checkpoint contract: tensors keyed by TF variable names ---------------------------------
+    def state_dict(self):
+        return {k: v.detach().cpu().numpy().copy() for k, v in self.engine.params.by_tf_name().items()}
+
+    def load_state_dict(self, state, strict=True):
+        fields = {tf_name(f, self.MODEL_TYPE): f for f in L.PARAM_FIELDS}
+        missing = [n for n in fields if n not in state]
+        if strict and missing:
+            raise KeyError(f"missing variables: {missing}")
+        for name, f in fields.items():
+            if name in state:
+                self.engine.params.views[f].copy_(torch.as_tensor(np.asarray(state[name], np.float32)))
+        self.engine.prepare_params()
+
+    # ---- running the path --------------------------------------------------------------------------
+    def attach_data_parallel(self, dp):
+        self._dp = dp
+
+    def forward(self, batch=None, full_outputs=True):
+        """session.run([loss, report, output]) of the reference (vqa/evaler.py:118-123). Returns h2d bytes."""
+        b = self.batch if batch is None else batch
+        nbytes = self.engine.stage_batch(b)
+        rank = self._dp.rank if self._dp is not None else 0
+        self.engine.forward(seed=self.seed + 7919 * rank, step=self.global_step, full_outputs=full_outputs)
+        self._bind_outputs()
+        return nbytes
+
+    def backward(self):
+        ws = self._dp.world_size if self._dp is not None else 1
+        self.engine.backward(loss_scale=1.0 / ws)
+        if self._dp is not None:
+            self._dp.all_reduce_gradients(self.engine)
+
+    def train_step(self, batch=None, lr=1e-3, clip_norm=20.0, apply_optimizer=True):
+        """run_train_step of vqa/trainer.py:275-287: forward + backward (+ all-reduce) + clip + Adam.
+        Returns (loss, h2d_bytes, d2h_bytes); the loss read is the step's device->host copy."""
+        h2d = self.forward(batch, full_outputs=False)
+        self.backward()
+        if apply_optimizer:
+            self.engine.adam_step(lr=lr, clip_norm=clip_norm)
+        self.global_step += 1
+        loss, report = self.engine.read_scalars()
+        self.loss = loss
+        self.losses["answer"] = loss
+        self.report = report
+        return loss, h2d, 4 * (1 + len(L.REPORT_KEYS))
+
+    def _bind_outputs(self):
+        e = self.engine
+        Bn = e.batch_size
+        self.output = e.outputs()
+        self.mid_result = {"att_score": self.output["att_score"], "logit": self.output["logit"],
+                           "pred": self.output["pred"], "pooled_V_ft": e.o_pooled[:Bn]}
+        self.heavy_output = {"condition": e.o_condition[:Bn]}
+
+    def fetch(self):
+        """Synchronise and return (loss, report) of the last forward."""
+        self.loss, self.report = self.engine.read_scalars()
+        self.losses["answer"] = self.loss
+        return self.loss, self.report
+
+
+class StandardModel(Model):
+    """vqa/model_standard.py: same trunk, learned reasoning/classifier head, everything trainable."""
+    MODEL_TYPE = "standard"
+
+
+def _name(v):
+    n = v if isinstance(v, str) else getattr(v, "name")
+    return n.split(":")[0]
+
+
+def make_synthetic_config(dims, variant="vlmap_answer", precision="bf16", seed=4321, num_images=64,
+                          batch_size=None, ragged_boxes=False):
+    """A reference-shaped `config` + `image_features` + `batch` built from synthetic data (no files)."""
+    from . import synthetic as S
+    c = S.dims(**dims)
+    params, exist = S.init_params(c, seed=seed, variant=variant)
+    feats, nb = S.make_bank(c, num_images=num_images, seed=seed + 1, ragged_boxes=ragged_boxes)
+    is_obj, is_attr = S.make_answer_flags(c)
+    vocab = {"vocab": [f"w{i}" for i in range(c["Vq"])]}
+    vocab["dict"] = {w: i for i, w in enumerate(vocab["vocab"])}
+    answers = [f"a{i}" for i in range(c["A"])]
+    answer_dict = {"vocab": answers, "dict": {a: i for i, a in enumerate(answers)},
+                   "num_train_answer": c["num_train_answer"], "is_object": is_obj, "is_attribute": is_attr}
+    config = SimpleNamespace(
+        vocab=vocab, answer_dict=answer_dict, vlmap_word_weight_dir=None, image_dir=None, debug=False,
+        batch_size=c["B"] if batch_size is None else batch_size, max_q_len=c["T"], v_dim=c["D"], l_dim=c["L"],
+        w_dim=c["W"], precision=precision, init_params=params, seed=seed, model_type=variant)
+    image_features = {"features": feats, "num_boxes": nb, "max_box_num": c["K"], "vfeat_dim": c["Dv"],
+                      "spatials": None, "normal_boxes": None}
+    batch = S.make_batch(c, num_images, seed=seed + 2, batch=batch_size)
+    return config, image_features, batch, exist
