@@ -1,0 +1,337 @@
+#!/usr/bin/env python
+"""bench.py -- the reference's headline workload (BASELINE.json configs[0]/[1] shapes) on N B200s.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...   # CPU arm (see below)
+
+A "step" is one train step of vqa/trainer.py:275-287 on one synthetic batch: forward + backward of the
+vlmap_answer model at B 512 x K 36 x Dv 2048 (T 14, A 3000) + gradient all-reduce (N > 1) + global-norm
+clip + Adam + refresh of the bf16 weight shadows.  `value` times it with the batch already in HBM;
+`e2e` times Model.train_step() fed from pinned HOST buffers (H2D of the batch + D2H of loss/report
+inside the timed region).  Timing is CUDA events on the launching stream, max over ranks.
+
+Reference arm: the reference's TF-1.6 graph cannot run here (no TensorFlow in the image), so
+`--impl reference` times the oracle's PyTorch-CPU port of the same graph (oracle/answer_model_torch.py,
+fp32, all host threads) on a bounded sample of the same workload; kind = "port".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG1 = dict(B=512, K=36, Dv=2048, D=1024, L=1024, A=3000, T=14, W=300, Vq=8192)
+WORKLOAD = "cfg1 vlmap_answer train step fwd+bwd+clip+adam, B512 x K36 x Dv2048, T14, A3000"
+METRIC = "train samples/sec fwd+bwd bs512x36x2048"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        # samples under load only: the SM clock idles low between regions
+        load = [s for s, p in zip(sm, power) if p > 300.0] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle's torch port of the same graph
+# ------------------------------------------------------------------------------------------------------
+def cpu_port_rate(sample_b, steps, warmup, seed=0):
+    """samples/sec of fwd+bwd of the torch-CPU port at cfg1 layer sizes on a batch of sample_b."""
+    import torch
+    from oracle import answer_model_torch as OT
+    from vqa_transfer_externaldata_b200 import synthetic as S
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    c = S.dims(**dict(CFG1, B=sample_b))
+    params, _ = S.init_params(c, seed=4321)
+    feats, nb = S.make_bank(c, num_images=sample_b, seed=99)
+    batch = S.make_batch(c, sample_b, seed=1234)
+    tp = {k: torch.tensor(v, requires_grad=True) for k, v in params.items()}
+    for k in ("pl_w", "pl_b", "pl_gamma", "pl_beta", "ql_w", "ql_b", "ql_gamma", "ql_beta", "joint_w",
+              "joint_b", "joint_gamma", "joint_beta", "ans_w", "ans_b"):
+        tp[k].requires_grad_(False)  # frozen transfer head (vqa/model_vlmap_answer.py:81-89)
+    tb = {k: torch.tensor(v) for k, v in batch.items()}
+    tf, tn = torch.tensor(feats), torch.tensor(nb)
+    tm = torch.tensor((np.arange(c["A"]) < c["num_train_answer"]).astype(np.float32))
+    g = torch.Generator().manual_seed(seed)
+    times = []
+    for i in range(warmup + steps):
+        am = (torch.rand(sample_b, c["K"], c["D"], generator=g) < 0.8).float()
+        jm = (torch.rand(sample_b, c["J"], generator=g) < 0.5).float()
+        t0 = time.perf_counter()
+        out = OT.forward(tp, tf, tn, tb, tm, att_mask=am, joint_mask=jm)
+        out["loss"].backward()
+        for p in tp.values():
+            p.grad = None
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sample_b / float(np.median(times)), threads, float(np.sum(times))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    sample_b = 128
+    rate, threads, busy = cpu_port_rate(sample_b, max(1, args.steps), max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample_b / rate,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "note": "CPU arm; each step = a 128-sample slice of the 512 batch"},
+        "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                         "sample": f"fwd+bwd of oracle/answer_model_torch.py at cfg1 layer sizes, batch {sample_b}, "
+                                   f"{args.steps} timed steps ({busy:.1f} s CPU wall)"},
+        "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    from vqa_transfer_externaldata_b200 import lib as L
+    from vqa_transfer_externaldata_b200 import synthetic as S
+    from vqa_transfer_externaldata_b200.dp import DataParallel
+    from vqa_transfer_externaldata_b200.model import Model, make_synthetic_config
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this repo has no CPU path (use --impl reference for the CPU arm)")
+    dp = DataParallel()
+    rank, world = dp.rank, dp.world_size
+    torch.cuda.set_device(dp.local_rank)
+    dev = torch.device(f"cuda:{dp.local_rank}")
+    peaks = load_peaks()
+    c = S.dims(**CFG1)
+    B = c["B"]
+
+    # synthetic bank generated ON the device (1.2 GB, larger than the 126 MB L2), params / batches in NumPy
+    n_img = args.bank_images
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    bank = torch.randn(n_img, c["K"], c["Dv"], device=dev, generator=g).abs_().mul_(0.5)
+    config, image_features, _, _ = make_synthetic_config(CFG1, variant="vlmap_answer", precision=args.precision,
+                                                         seed=4321, num_images=2)
+    image_features = {"features": bank, "num_boxes": np.full(n_img, c["K"], np.int32),
+                      "max_box_num": c["K"], "vfeat_dim": c["Dv"]}
+    config.device = dev
+    R = 4
+    host_batches = [S.make_batch(c, n_img, seed=1234 + 17 * r + 1000 * rank) for r in range(R)]
+    model = Model(host_batches[0], config, is_train=True, image_features=image_features)
+    model.attach_data_parallel(dp if world > 1 else None)
+    eng = model.engine
+    dp.broadcast_params(eng)
+    lib = eng.lib
+
+    # device-resident copies of the R batches for the `value` loop
+    dev_batches = []
+    for hb in host_batches:
+        dev_batches.append((torch.from_numpy(hb["image_idx"]).to(dev), torch.from_numpy(hb["q_intseq"].reshape(-1)).to(dev),
+                            torch.from_numpy(hb["q_intseq_len"]).to(dev),
+                            torch.from_numpy(hb["answer_target"].reshape(-1)).to(dev)))
+
+    def step_resident(i):
+        idx, q, ql, tg = dev_batches[i % R]
+        eng.d_image_idx.copy_(idx); eng.d_q.copy_(q); eng.d_qlen.copy_(ql); eng.d_target.copy_(tg)
+        eng.batch_size, eng.q_len_max = B, c["T"]
+        rk = dp.rank if world > 1 else 0
+        eng.forward(seed=model.seed + 7919 * rk, step=model.global_step, full_outputs=False)
+        model.backward()
+        eng.adam_step(lr=1e-3, clip_norm=20.0)
+        model.global_step += 1
+
+    def timed(fn, steps):
+        dp.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = eng.launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        dp.barrier()
+        ms = dp.max_over_ranks(e0.elapsed_time(e1))
+        return ms, eng.launch_count() - n0
+
+    W = max(3, args.warmup)
+    for i in range(W):
+        step_resident(i)
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(dp.local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ms_value, launches = timed(step_resident, args.steps)
+
+    h2d = d2h = 0
+
+    def step_e2e(i):
+        nonlocal h2d, d2h
+        _, a, b = model.train_step(host_batches[i % R])
+        h2d, d2h = a, b
+
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # per-phase device times inside the real step (CUDA events recorded by the library on this stream)
+    L.check(lib.vqa_profile_enable(eng.h, 1))
+    import ctypes as C
+    acc = np.zeros(L.NUM_PHASES)
+    PROF_STEPS = 5
+    for i in range(PROF_STEPS):
+        step_resident(i)
+        buf = (C.c_float * L.NUM_PHASES)()
+        L.check(lib.vqa_profile_read(eng.h, buf))
+        acc += np.array(list(buf))
+    L.check(lib.vqa_profile_enable(eng.h, 0))
+    phase_ms = {lib.vqa_phase_name(i).decode(): float(acc[i] / PROF_STEPS) for i in range(L.NUM_PHASES)}
+
+    samples = world * B * args.steps
+    value = samples / (ms_value * 1e-3)
+    e2e_value = samples / (ms_e2e * 1e-3)
+
+    # rooflines. Dominant kernel = the v-projection GEMM pair (fwd: [B*K,Dv]x[Dv,D], wgrad: [Dv,B*K]x[B*K,D]),
+    # each ONE launch of gemm_bf16_tcgen05_kernel; algorithmic FLOPs = 2*M*N*K (77.31 GF each).
+    K_, Dv, D = c["K"], c["Dv"], c["D"]
+    gemm_flops = 2.0 * B * K_ * Dv * D * (3 if args.precision == "fp32" else 1)
+    dom = "vproj_wgrad" if phase_ms["vproj_wgrad"] >= phase_ms["vproj_fwd"] else "vproj_fwd"
+    ach = gemm_flops / (phase_ms[dom] * 1e-3) / 1e12
+    peak_tc = peaks["bf16_tflops_sustained"]
+    roofline = {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05_kernel ({dom})", "achieved": ach, "peak": peak_tc,
+                "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": None,
+                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)"}
+    zb = 2 if args.precision == "bf16" else 4     # bytes / element of the stored pre-LN projection
+    vb = 2 if args.precision == "bf16" else 4     # gathered features: bf16 plane (fp32 mode: hi + lo planes)
+    att_fwd_bytes = B * (K_ * D * zb + K_ * Dv * vb + D * 4 + Dv * 4 + Dv * vb + K_ * 4)
+    att_bwd_bytes = B * (K_ * Dv * vb + K_ * D * zb + Dv * 4 + D * 4 + K_ * 4 + K_ * D * vb + D * 4 + (4 * D + 8) * 4)
+    attn = {
+        "fwd": {"ms": phase_ms["attn_fwd"], "bytes": att_fwd_bytes,
+                "GBps": att_fwd_bytes / (phase_ms["attn_fwd"] * 1e-3) / 1e9},
+        "bwd": {"ms": phase_ms["attn_bwd"], "bytes": att_bwd_bytes,
+                "GBps": att_bwd_bytes / (phase_ms["attn_bwd"] * 1e-3) / 1e9},
+        "peak_GBps": peaks["hbm_gbs"],
+    }
+    attn["fwd"]["frac"] = attn["fwd"]["GBps"] / peaks["hbm_gbs"]
+    attn["bwd"]["frac"] = attn["bwd"]["GBps"] / peaks["hbm_gbs"]
+    # whole-step roofline of BASELINE.md section 3 (cfg1: 356.1 GF + 543.4 MB + 18.4 MB -> 340 us on 1 GPU)
+    t_roof_ms = (356.1e9 / (peaks["bf16_tflops_sustained"] * 1e12) + (543.4e6 + 18.4e6) / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    step_frac = t_roof_ms / (ms_value / args.steps)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, threads, busy = cpu_port_rate(64, 3, 1)
+        cpu_baseline = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
+                        "sample": f"fwd+bwd of the oracle's torch-CPU port at cfg1 layer sizes, batch 64, 3 timed "
+                                  f"steps ({busy:.1f} s); the reference's TF-1.6 CPU path cannot run in this image"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": W, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
+                       "precision": args.precision, "parallelism": f"dp{world}",
+                       "l2_policy": f"inputs larger than L2: {n_img}-image fp32 feature bank "
+                                    f"({bank.numel() * 4 / 1e9:.2f} GB) indexed at random, ~0.7 GB touched per step"},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "step_roofline": {"t_roof_ms": t_roof_ms, "frac": step_frac,
+                              "model": "356.1 GF / bf16 sustained + 561.8 MB / HBM (BASELINE.md section 3)"},
+            "attn_hbm": attn,
+            "phase_ms": phase_ms,
+            "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    dp.close()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--bank-images", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -143,6 +143,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   if (A > maxc) maxc = A;
   if (J > maxc) maxc = J;
   if (Dv > maxc) maxc = Dv;
+  b.gru_counter = a.take<unsigned int>(64);
   b.scratch_floats = 32 * maxc + 16 * B + 4096;
   b.scratch = a.take<float>(b.scratch_floats);
   return (a.off + 255) & ~static_cast<uint64_t>(255);

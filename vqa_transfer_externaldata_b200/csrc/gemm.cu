@@ -200,43 +200,75 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
     }
     __syncwarp();
-    // coalesced write-out: the warp walks its 32 rows; lanes cover 4 consecutive columns each
-    for (int r = 0; r < 32; ++r) {
-      const int row = m0 + q * 32 + r;
-      if (row >= M) break;
+    // coalesced write-out: the warp walks its 32 rows; each lane owns NV fixed groups of 4 columns.
+    // Rows go in batches of RB: all global loads of a batch (addend) are issued before its stores, so
+    // the load latencies overlap instead of serialising row by row (the output may alias the addend
+    // element-for-element, which keeps the compiler from reordering them on its own).
+    constexpr int NV = (BN + 127) / 128;          // float4 groups per lane per row
+    constexpr int RB = (NV == 1) ? 16 : 8;        // rows per batch
+    float4 bias_v[NV];
+    bool col_ok[NV];
 #pragma unroll
-      for (int c4 = lane * 4; c4 < BN; c4 += 128) {
-        const int col = n0 + c4;
-        if (col >= N) continue;  // N % 4 == 0 is enforced by the launcher
-        float4 x = *reinterpret_cast<const float4*>(stg + r * Cfg::STG_LD + c4);
-        if (ep.bias) {
-          const float4 b = *reinterpret_cast<const float4*>(ep.bias + col);
-          x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+    for (int v = 0; v < NV; ++v) {
+      const int c4 = lane * 4 + v * 128;
+      const int col = n0 + c4;
+      col_ok[v] = (c4 < BN) && (col < N);  // N % 4 == 0 is enforced by the launcher
+      bias_v[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (col_ok[v] && ep.bias) bias_v[v] = *reinterpret_cast<const float4*>(ep.bias + col);
+    }
+    const int row0 = m0 + q * 32;
+#pragma unroll 1
+    for (int rb = 0; rb < 32; rb += RB) {
+      if (row0 + rb >= M) break;
+      float4 x[RB][NV];
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + rb + r;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          const int c4 = lane * 4 + v * 128;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (col_ok[v]) {
+            t = *reinterpret_cast<const float4*>(stg + (rb + r) * Cfg::STG_LD + c4);
+            t.x += bias_v[v].x; t.y += bias_v[v].y; t.z += bias_v[v].z; t.w += bias_v[v].w;
+            if (ep.addend && row < M) {
+              const float4 a = *(reinterpret_cast<const float4*>(
+                  ep.addend + static_cast<long long>(row) * ep.ld_addend + n0 + c4));
+              t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+            }
+          }
+          x[r][v] = t;
         }
-        if (ep.addend) {
-          const float4 a =
-              *reinterpret_cast<const float4*>(ep.addend + static_cast<long long>(row) * ep.ld_addend + col);
-          x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
-        }
-        if (ep.out_f32)
-          *reinterpret_cast<float4*>(ep.out_f32 + static_cast<long long>(row) * ep.ld_f32 + col) = x;
-        if (ep.out_hi) {
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y),
-                              h2 = __float2bfloat16_rn(x.z), h3 = __float2bfloat16_rn(x.w);
-          const long long o = static_cast<long long>(row) * ep.ld_bf + col;
-          __nv_bfloat162 p0(h0, h1), p1(h2, h3);
-          uint2 pk;
-          pk.x = *reinterpret_cast<uint32_t*>(&p0);
-          pk.y = *reinterpret_cast<uint32_t*>(&p1);
-          *reinterpret_cast<uint2*>(ep.out_hi + o) = pk;
-          if (ep.out_lo) {
-            __nv_bfloat162 q0(__float2bfloat16_rn(x.x - __bfloat162float(h0)),
-                              __float2bfloat16_rn(x.y - __bfloat162float(h1)));
-            __nv_bfloat162 q1(__float2bfloat16_rn(x.z - __bfloat162float(h2)),
-                              __float2bfloat16_rn(x.w - __bfloat162float(h3)));
-            pk.x = *reinterpret_cast<uint32_t*>(&q0);
-            pk.y = *reinterpret_cast<uint32_t*>(&q1);
-            *reinterpret_cast<uint2*>(ep.out_lo + o) = pk;
+      }
+#pragma unroll
+      for (int r = 0; r < RB; ++r) {
+        const int row = row0 + rb + r;
+        if (row >= M) break;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          if (!col_ok[v]) continue;
+          const int col = n0 + lane * 4 + v * 128;
+          const float4 t = x[r][v];
+          if (ep.out_f32)
+            *reinterpret_cast<float4*>(ep.out_f32 + static_cast<long long>(row) * ep.ld_f32 + col) = t;
+          if (ep.out_hi) {
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(t.x), h1 = __float2bfloat16_rn(t.y),
+                                h2 = __float2bfloat16_rn(t.z), h3 = __float2bfloat16_rn(t.w);
+            const long long o = static_cast<long long>(row) * ep.ld_bf + col;
+            __nv_bfloat162 p0(h0, h1), p1(h2, h3);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0);
+            pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(ep.out_hi + o) = pk;
+            if (ep.out_lo) {
+              __nv_bfloat162 q0(__float2bfloat16_rn(t.x - __bfloat162float(h0)),
+                                __float2bfloat16_rn(t.y - __bfloat162float(h1)));
+              __nv_bfloat162 q1(__float2bfloat16_rn(t.z - __bfloat162float(h2)),
+                                __float2bfloat16_rn(t.w - __bfloat162float(h3)));
+              pk.x = *reinterpret_cast<uint32_t*>(&q0);
+              pk.y = *reinterpret_cast<uint32_t*>(&q1);
+              *reinterpret_cast<uint2*>(ep.out_lo + o) = pk;
+            }
           }
         }
       }

@@ -66,6 +66,7 @@ struct Buffers {
   float* dG_f32; Planes dG;  // [T*B, 2L]
   float* dE;       // [T*B, Wpad]
   float* ln_part_g; float* ln_part_b;  // [B, max(D,L,J)] LayerNorm gamma/beta partials
+  unsigned int* gru_counter;  // device-wide phase counter of the persistent GRU kernels
   float* scratch;  // column-sum / loss scratch
   size_t scratch_floats;
 };

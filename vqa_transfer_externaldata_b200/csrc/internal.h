@@ -74,6 +74,31 @@ VqaStatus gru_bwd_gates_launch(const float* dRH, const float* du, const float* h
                                float* dh_part, float* dG_f32, bf16* dG_hi, bf16* dG_lo,
                                cudaStream_t s);
 
+// ---- gru.cu: persistent recurrent kernels (one cooperative launch for all T steps) ----
+struct GruFwdPersistent {
+  int B, L, T;
+  const int* q_len;
+  unsigned int* counter;
+  const float* xg; const float* xc;      // hoisted x-parts (+bias): [T*B, 2L], [T*B, L]
+  float* h_f32; bf16* h_bf;              // [(T+1)*B, L], block 0 = zero initial state
+  bf16* rh_bf;                           // [T*B, L]
+  float* r; float* u; float* c;          // [T*B, L]
+  const bf16* wg_h; const bf16* wc_h;    // bf16 shadows of the h-rows of the TF kernels: [L, 2L], [L, L]
+};
+struct GruBwdPersistent {
+  int B, L, T;
+  const int* q_len;
+  unsigned int* counter;
+  const float* h_f32; const float* r; const float* u; const float* c;
+  float* du; float* dh_part;             // [B, L]; hold the element-wise head of step T-1 on entry
+  float* dG_f32; bf16* dG_bf;            // [T*B, 2L]
+  float* dC_f32; bf16* dC_bf;            // [T*B, L]; block T-1 filled on entry
+  const bf16* wg_h; const bf16* wc_h;
+};
+bool gru_persistent_supported(int B, int L, int precision, int num_sms);
+VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, cudaStream_t s);
+VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, cudaStream_t s);
+
 // ---- rows.cu: row LayerNorm + ReLU heads (modules.fc_layer with use_ln, vlmap/modules.py:630-650) ----
 struct RowLnFwd {
   int rows, N;

@@ -148,18 +148,29 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   VQA_TRY(fill_zero_launch(b.h_f32, sizeof(float) * BL, s));
   VQA_TRY(fill_zero_launch(b.h.hi, sizeof(bf16) * BL, s));
   if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, s));
-  for (int t = 0; t < T; ++t) {
-    VQA_TRY(GemmB(Bn, 2 * L, L).a(b.h, t * BL, L, false)
-                .b(b.w.gru_gates_w, static_cast<long long>(W) * 2 * L, 2 * L, true)
-                .addend(b.xg + static_cast<long long>(t) * Bn * 2 * L, 2 * L).f32(b.g_pre, 2 * L).run(h, s));
-    VQA_TRY(gru_gates_launch(b.g_pre, b.h_f32 + t * BL, Bn, L, b.r + t * BL, b.u + t * BL,
-                             b.rh.hi + t * BL, b.rh.lo ? b.rh.lo + t * BL : nullptr, s));
-    VQA_TRY(GemmB(Bn, L, L).a(b.rh, t * BL, L, false)
-                .b(b.w.gru_cand_w, static_cast<long long>(W) * L, L, true)
-                .addend(b.xc + static_cast<long long>(t) * Bn * L, L).f32(b.c_pre, L).run(h, s));
-    VQA_TRY(gru_update_launch(b.c_pre, b.h_f32 + t * BL, b.u + t * BL, batch->q_intseq_len, t, Bn, L,
-                              b.c + t * BL, b.h_f32 + (t + 1) * BL, b.h.hi + (t + 1) * BL,
-                              b.h.lo ? b.h.lo + (t + 1) * BL : nullptr, s));
+  const bool persistent = gru_persistent_supported(Bn, L, c.precision, h->num_sms);
+  if (persistent) {
+    GruFwdPersistent a{};
+    a.B = Bn; a.L = L; a.T = T; a.q_len = batch->q_intseq_len; a.counter = b.gru_counter;
+    a.xg = b.xg; a.xc = b.xc; a.h_f32 = b.h_f32; a.h_bf = b.h.hi; a.rh_bf = b.rh.hi;
+    a.r = b.r; a.u = b.u; a.c = b.c;
+    a.wg_h = b.w.gru_gates_w.hi + static_cast<long long>(W) * 2 * L;
+    a.wc_h = b.w.gru_cand_w.hi + static_cast<long long>(W) * L;
+    VQA_TRY(gru_fwd_persistent_launch(a, s));
+  } else {
+    for (int t = 0; t < T; ++t) {
+      VQA_TRY(GemmB(Bn, 2 * L, L).a(b.h, t * BL, L, false)
+                  .b(b.w.gru_gates_w, static_cast<long long>(W) * 2 * L, 2 * L, true)
+                  .addend(b.xg + static_cast<long long>(t) * Bn * 2 * L, 2 * L).f32(b.g_pre, 2 * L).run(h, s));
+      VQA_TRY(gru_gates_launch(b.g_pre, b.h_f32 + t * BL, Bn, L, b.r + t * BL, b.u + t * BL,
+                               b.rh.hi + t * BL, b.rh.lo ? b.rh.lo + t * BL : nullptr, s));
+      VQA_TRY(GemmB(Bn, L, L).a(b.rh, t * BL, L, false)
+                  .b(b.w.gru_cand_w, static_cast<long long>(W) * L, L, true)
+                  .addend(b.xc + static_cast<long long>(t) * Bn * L, L).f32(b.c_pre, L).run(h, s));
+      VQA_TRY(gru_update_launch(b.c_pre, b.h_f32 + t * BL, b.u + t * BL, batch->q_intseq_len, t, Bn, L,
+                                b.c + t * BL, b.h_f32 + (t + 1) * BL, b.h.hi + (t + 1) * BL,
+                                b.h.lo ? b.h.lo + (t + 1) * BL : nullptr, s));
+    }
   }
   const float* q = b.h_f32 + T * BL;
   const long long q_off = T * BL;
@@ -347,21 +358,37 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     PH_BEGIN(VQA_PH_GRU_BWD);
     float* dh_cur = b.dq;
     int pp = 0;
-    for (int t = T - 1; t >= 0; --t) {
+    if (gru_persistent_supported(Bn, L, c.precision, h->num_sms)) {
+      // element-wise head of step T-1 from dq, then one cooperative launch for all 2T dependent GEMMs
+      const int t = T - 1;
       VQA_TRY(gru_bwd_update_launch(dh_cur, b.h_f32 + t * BL, b.u + t * BL, b.c + t * BL,
                                     batch->q_intseq_len, t, Bn, L, b.du, b.dh_part, b.dC_f32 + t * BL,
-                                    b.dC.hi + t * BL, b.dC.lo ? b.dC.lo + t * BL : nullptr, s));
-      VQA_TRY(GemmB(Bn, L, L).a(b.dC, t * BL, L, false)
-                  .b(b.w.gru_cand_w, static_cast<long long>(W) * L, L, false).f32(b.dRH, L).run(h, s));
-      VQA_TRY(gru_bwd_gates_launch(b.dRH, b.du, b.h_f32 + t * BL, b.r + t * BL, b.u + t * BL,
-                                   batch->q_intseq_len, t, Bn, L, b.dh_part, b.dG_f32 + 2 * t * BL,
-                                   b.dG.hi + 2 * t * BL, b.dG.lo ? b.dG.lo + 2 * t * BL : nullptr, s));
-      float* dh_next = b.dh[pp];
-      pp ^= 1;
-      VQA_TRY(GemmB(Bn, L, 2 * L).a(b.dG, 2 * t * BL, 2 * L, false)
-                  .b(b.w.gru_gates_w, static_cast<long long>(W) * 2 * L, 2 * L, false)
-                  .addend(b.dh_part, L).f32(dh_next, L).run(h, s));
-      dh_cur = dh_next;
+                                    b.dC.hi + t * BL, nullptr, s));
+      GruBwdPersistent a{};
+      a.B = Bn; a.L = L; a.T = T; a.q_len = batch->q_intseq_len; a.counter = b.gru_counter;
+      a.h_f32 = b.h_f32; a.r = b.r; a.u = b.u; a.c = b.c; a.du = b.du; a.dh_part = b.dh_part;
+      a.dG_f32 = b.dG_f32; a.dG_bf = b.dG.hi; a.dC_f32 = b.dC_f32; a.dC_bf = b.dC.hi;
+      a.wg_h = b.w.gru_gates_w.hi + static_cast<long long>(W) * 2 * L;
+      a.wc_h = b.w.gru_cand_w.hi + static_cast<long long>(W) * L;
+      VQA_TRY(gru_bwd_persistent_launch(a, s));
+      (void)pp;
+    } else {
+      for (int t = T - 1; t >= 0; --t) {
+        VQA_TRY(gru_bwd_update_launch(dh_cur, b.h_f32 + t * BL, b.u + t * BL, b.c + t * BL,
+                                      batch->q_intseq_len, t, Bn, L, b.du, b.dh_part, b.dC_f32 + t * BL,
+                                      b.dC.hi + t * BL, b.dC.lo ? b.dC.lo + t * BL : nullptr, s));
+        VQA_TRY(GemmB(Bn, L, L).a(b.dC, t * BL, L, false)
+                    .b(b.w.gru_cand_w, static_cast<long long>(W) * L, L, false).f32(b.dRH, L).run(h, s));
+        VQA_TRY(gru_bwd_gates_launch(b.dRH, b.du, b.h_f32 + t * BL, b.r + t * BL, b.u + t * BL,
+                                     batch->q_intseq_len, t, Bn, L, b.dh_part, b.dG_f32 + 2 * t * BL,
+                                     b.dG.hi + 2 * t * BL, b.dG.lo ? b.dG.lo + 2 * t * BL : nullptr, s));
+        float* dh_next = b.dh[pp];
+        pp ^= 1;
+        VQA_TRY(GemmB(Bn, L, 2 * L).a(b.dG, 2 * t * BL, 2 * L, false)
+                    .b(b.w.gru_gates_w, static_cast<long long>(W) * 2 * L, 2 * L, false)
+                    .addend(b.dh_part, L).f32(dh_next, L).run(h, s));
+        dh_cur = dh_next;
+      }
     }
     PH_END(VQA_PH_GRU_BWD);
     PH_BEGIN(VQA_PH_GRU_WGRAD);

@@ -1,0 +1,61 @@
+"""Batch-sharded data parallelism: one process per GPU, one all-reduce(sum) of the flat trainable-gradient
+buffer per step (the reference has no distributed code at all: one process per GPU via
+CUDA_VISIBLE_DEVICES, run.py:25-46). Each rank scales d(loss) by 1/world_size so the summed gradient is the
+gradient of the global-batch mean loss. Inference shards the batch with no collective."""
+import os
+
+import torch
+import torch.distributed as dist
+
+
+class DataParallel:
+    def __init__(self, backend=None, bucket_bytes=32 << 20):
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.bucket_elems = bucket_bytes // 4
+        self.owns_group = False
+        if self.world_size > 1 and not dist.is_initialized():
+            backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend=backend)
+            self.owns_group = True
+
+    def shard(self, n_global):
+        """[start, end) of this rank's contiguous slice of a global batch of n_global samples."""
+        per = (n_global + self.world_size - 1) // self.world_size
+        s = min(self.rank * per, n_global)
+        return s, min(s + per, n_global)
+
+    def all_reduce_flat(self, flat):
+        """Sum `flat` (1-D tensor) over ranks in place, bucketed."""
+        if self.world_size == 1:
+            return
+        n = flat.numel()
+        for s in range(0, n, self.bucket_elems):
+            dist.all_reduce(flat[s:min(s + self.bucket_elems, n)], op=dist.ReduceOp.SUM)
+
+    def all_reduce_gradients(self, engine):
+        self.all_reduce_flat(engine.params.grad)
+
+    def barrier(self):
+        if self.world_size > 1:
+            dist.barrier()
+
+    def max_over_ranks(self, value):
+        if self.world_size == 1:
+            return value
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor([value], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def broadcast_params(self, engine, src=0):
+        if self.world_size > 1:
+            dist.broadcast(engine.params.flat, src=src)
+            engine.prepare_params()
+
+    def close(self):
+        if self.owns_group and dist.is_initialized():
+            dist.destroy_process_group()

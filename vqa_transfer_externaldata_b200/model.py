@@ -64,7 +64,10 @@ class Model(object):
         self.test_answer_mask = 1.0 - self.train_answer_mask
         self.obj_answer_mask = np.asarray(self.answer_dict["is_object"], np.float32)[None]
         self.attr_answer_mask = np.asarray(self.answer_dict["is_attribute"], np.float32)[None]
-        self.answer_exist_mask = wordweights.answer_exist_mask(self.answer_dict, self.word_weight_dir)[None]
+        exist = getattr(config, "answer_exist_mask", None)  # synthetic configs carry it explicitly
+        if exist is None:
+            exist = wordweights.answer_exist_mask(self.answer_dict, self.word_weight_dir)
+        self.answer_exist_mask = np.asarray(exist, np.float32)[None]
 
         # feature bank (vqa/model_vlmap_answer.py:54-77)
         if getattr(config, "debug", False):
@@ -217,7 +220,8 @@ def make_synthetic_config(dims, variant="vlmap_answer", precision="bf16", seed=4
     config = SimpleNamespace(
         vocab=vocab, answer_dict=answer_dict, vlmap_word_weight_dir=None, image_dir=None, debug=False,
         batch_size=c["B"] if batch_size is None else batch_size, max_q_len=c["T"], v_dim=c["D"], l_dim=c["L"],
-        w_dim=c["W"], precision=precision, init_params=params, seed=seed, model_type=variant)
+        w_dim=c["W"], precision=precision, init_params=params, seed=seed, model_type=variant,
+        answer_exist_mask=exist)
     image_features = {"features": feats, "num_boxes": nb, "max_box_num": c["K"], "vfeat_dim": c["Dv"],
                       "spatials": None, "normal_boxes": None}
     batch = S.make_batch(c, num_images, seed=seed + 2, batch=batch_size)
