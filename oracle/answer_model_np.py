@@ -63,6 +63,21 @@ def sigmoid(x):
     return 1.0 / (1.0 + np.exp(-x))
 
 
+def round_bf16(x):
+    """Round-to-nearest-even to bfloat16 (returned as float64). Used by forward(operand_round=round_bf16) to
+    restate the MIXED-PRECISION arithmetic the bf16 mode of the CUDA path specifies: every GEMM operand (and
+    the stored pre-LN v-projection) is a bf16 value, everything else is fp32/fp64. With it the oracle makes
+    the same ReLU gate decisions as the device, so bf16-mode gradients can be held to the 2e-2 gate."""
+    a = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    u = a.view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32).reshape(a.shape).astype(np.float64)
+
+
+def _ident(x):
+    return x
+
+
 # ------------------------------------------------------------------------------------------------
 # layers.layer_norm (vlmap/modules.py:646-647): statistics over ALL non-batch axes, gamma/beta on the
 # last axis, biased variance via moments (two-pass), eps 1e-12.   SURVEY Q1
@@ -88,9 +103,11 @@ def layer_norm_bwd(dy, gamma, cache):
     return dz, dgamma, dbeta
 
 
-def fc_ln_relu_fwd(x, w, b, gamma, beta):
-    """modules.fc_layer(use_bias, use_ln, relu): rank>2 inputs contract the last axis."""
-    z = x @ w + b
+def fc_ln_relu_fwd(x, w, b, gamma, beta, q=_ident, qz=_ident):
+    """modules.fc_layer(use_bias, use_ln, relu): rank>2 inputs contract the last axis.
+    q rounds the GEMM input operand (w is passed in already rounded), qz the stored pre-LN output."""
+    x = q(x)
+    z = qz(x @ w + b)
     y, ln_cache = layer_norm_fwd(z, gamma, beta)
     return np.maximum(y, 0.0), (x, y, ln_cache)
 
@@ -118,20 +135,23 @@ def fc_ln_relu_bwd(dh, w, gamma, cache, need_dx=True, flip=None):
 # gates = sigmoid([x, h] Wg + bg), split (r, u); c = tanh([x, r*h] Wc + bc); h' = u*h + (1-u)*c;
 # for t >= len the state is copied through. Zero initial state.            SURVEY Q5
 # ------------------------------------------------------------------------------------------------
-def gru_fwd(E, q_len, Wg, bg, Wc, bc):
+def gru_fwd(E, q_len, Wg, bg, Wc, bc, q=_ident):
+    """q rounds the matmul operands h and r*h (E, Wg, Wc arrive already rounded); the element-wise gate math
+    always uses the unrounded state."""
     B, T, W = E.shape
     L = Wc.shape[1]
     h = np.zeros((B, L))
     steps = []
     for t in range(T):
         x = E[:, t, :]
-        g = np.concatenate([x, h], axis=1) @ Wg + bg
+        h_op = q(h)
+        g = np.concatenate([x, h_op], axis=1) @ Wg + bg
         r, u = sigmoid(g[:, :L]), sigmoid(g[:, L:])
-        rh = r * h
-        c = np.tanh(np.concatenate([x, rh], axis=1) @ Wc + bc)
+        rh_op = q(r * h)
+        c = np.tanh(np.concatenate([x, rh_op], axis=1) @ Wc + bc)
         hn = u * h + (1.0 - u) * c
         valid = (t < q_len)[:, None]
-        steps.append((x, h, r, u, rh, c, valid))
+        steps.append((x, h, r, u, rh_op, c, valid, h_op))
         h = np.where(valid, hn, h)
     return h, steps
 
@@ -144,7 +164,7 @@ def gru_bwd(dq, steps, Wg, Wc, W):
     dbc = np.zeros(Wc.shape[1])
     dh = dq.copy()
     dE = []
-    for (x, h, r, u, rh, c, valid) in reversed(steps):
+    for (x, h, r, u, rh, c, valid, h_op) in reversed(steps):
         dhn = np.where(valid, dh, 0.0)        # gradient reaching h' (only valid steps used it)
         dh_prev = np.where(valid, 0.0, dh)    # copied-through state
         du = dhn * (h - c)
@@ -160,7 +180,7 @@ def gru_bwd(dq, steps, Wg, Wc, W):
         dr = drh * h
         dh_prev = dh_prev + drh * r
         dg = np.concatenate([dr * r * (1.0 - r), du * u * (1.0 - u)], axis=1)
-        xg = np.concatenate([x, h], axis=1)
+        xg = np.concatenate([x, h_op], axis=1)
         dWg += xg.T @ dg
         dbg += dg.sum(axis=0)
         dxg = dg @ Wg.T
@@ -241,17 +261,25 @@ def metrics(logit, target, m, use_train_mask=True):
 # ------------------------------------------------------------------------------------------------
 # the graph
 # ------------------------------------------------------------------------------------------------
+GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joint_w", "ans_w")
+
+
 def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0.8, keep_joint=0.5,
-            att_mask=None, joint_mask=None):
+            att_mask=None, joint_mask=None, operand_round=None):
     """Model.build() forward. p: dict field -> fp64 array (TF layout [in,out]).
     features [N,K,Dv], num_boxes [N]; batch: image_idx [B], q_intseq [B,T], q_intseq_len [B],
     answer_target [B,A]; att_mask [B,K,D] / joint_mask [B,J] are the 0/1 keep masks tf.nn.dropout
     would have drawn (None = keep everything but still scale by 1/keep as TF does with a mask of 1s).
+    operand_round: None = the reference's plain arithmetic; round_bf16 = the CUDA path's bf16 mode (GEMM
+    operands and the stored pre-LN v-projection rounded to bf16, see round_bf16).
     Returns (outputs dict, cache for backward)."""
     f64 = lambda a: np.asarray(a, dtype=np.float64)
+    q = operand_round or _ident
     p = {k: f64(v) for k, v in p.items()}
+    if operand_round is not None:
+        p.update({k: q(p[k]) for k in GEMM_WEIGHTS})
     idx = np.asarray(batch["image_idx"])
-    V = f64(features)[idx]                                   # model_vlmap_answer.py:110-117
+    V = q(f64(features)[idx])                                # model_vlmap_answer.py:110-117
     nbox = np.asarray(num_boxes)[idx].astype(np.int64)       # :118-119
     q_ids = np.asarray(batch["q_intseq"])
     q_len = np.asarray(batch["q_intseq_len"])
@@ -259,10 +287,10 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     B, K, Dv = V.shape
     W = p["embed"].shape[1]
 
-    Hv, v_cache = fc_ln_relu_fwd(V, p["v_w"], p["v_b"], p["v_gamma"], p["v_beta"])   # :126-129 (LN over K*D)
-    E = p["embed"][q_ids]                                                            # :134
-    q, gru_steps = gru_fwd(E, q_len, p["gru_gates_w"], p["gru_gates_b"], p["gru_cand_w"], p["gru_cand_b"])
-    Hq, q_cache = fc_ln_relu_fwd(q, p["qv_w"], p["qv_b"], p["qv_gamma"], p["qv_beta"])  # :142-145
+    Hv, v_cache = fc_ln_relu_fwd(V, p["v_w"], p["v_b"], p["v_gamma"], p["v_beta"], qz=q)  # :126-129 (LN over K*D)
+    E = q(p["embed"][q_ids])                                                         # :134
+    qs, gru_steps = gru_fwd(E, q_len, p["gru_gates_w"], p["gru_gates_b"], p["gru_cand_w"], p["gru_cand_b"], q=q)
+    Hq, q_cache = fc_ln_relu_fwd(qs, p["qv_w"], p["qv_b"], p["qv_gamma"], p["qv_beta"], q=q)  # :142-145
 
     # hadamard_attention (modules.py:80-97)
     D = Hv.shape[-1]
@@ -276,20 +304,20 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     a = e / e.sum(axis=1, keepdims=True)                     # exact zeros at masked slots
     P = np.einsum("bk,bkd->bd", a, V)                        # attention_pooling of the RAW features
 
-    Hp, p_cache = fc_ln_relu_fwd(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"])  # :163-167
-    Hl, l_cache = fc_ln_relu_fwd(q, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"])  # :170-174
+    Hp, p_cache = fc_ln_relu_fwd(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"], q=q)   # :163-167
+    Hl, l_cache = fc_ln_relu_fwd(qs, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"], q=q)  # :170-174
     X = Hp * Hl
-    Jn, j_cache = fc_ln_relu_fwd(X, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
+    Jn, j_cache = fc_ln_relu_fwd(X, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"], q=q)
     jm = np.ones_like(Jn) if joint_mask is None else f64(joint_mask)
-    Jd = Jn * jm / keep_joint                                # :180
+    Jd = q(Jn * jm / keep_joint)                             # :180
     logit = Jd @ p["ans_w"] + p["ans_b"]                     # :183-185 / model_standard.py:272-275
 
     use_tm = variant != "standard"
     train_loss, report, ps, pred = metrics(logit, target, m, use_train_mask=use_tm)
     out = {"loss": train_loss, "report": report, "att_score": a, "logit": logit, "pred": pred,
-           "per_sample": ps, "condition": q, "pooled": P}
+           "per_sample": ps, "condition": qs, "pooled": P}
     cache = dict(V=V, nbox=nbox, q_ids=q_ids, q_len=q_len, target=target, v_cache=v_cache, Hv=Hv,
-                 gru_steps=gru_steps, q=q, q_cache=q_cache, Hq=Hq, am=am, F=F, a=a, P=P, p_cache=p_cache,
+                 gru_steps=gru_steps, q=qs, q_cache=q_cache, Hq=Hq, am=am, F=F, a=a, P=P, p_cache=p_cache,
                  Hp=Hp, l_cache=l_cache, Hl=Hl, X=X, j_cache=j_cache, jm=jm, Jd=Jd, logit=logit,
                  keep_att=keep_att, keep_joint=keep_joint, use_tm=use_tm, m=m, W=W, p=p)
     return out, cache

@@ -59,7 +59,9 @@ def build_case(dims, variant="vlmap_answer", precision="fp32", seed=0, num_image
     return dict(c=c, cfg=cfg, params=params, feats=feats, nb=nb, batch=bt, eng=eng, m=m)
 
 
-def run_both(case, seed=777, step=3, loss_scale=1.0):
+def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
+    """emulate: None = restate the device's operand rounding when the case runs in bf16 mode (the oracle then
+    makes the same ReLU gate decisions), False = always the reference's plain arithmetic."""
     import torch
     eng, cfg = case["eng"], case["cfg"]
     eng.stage_batch(case["batch"])
@@ -73,9 +75,16 @@ def run_both(case, seed=777, step=3, loss_scale=1.0):
     got["condition"] = eng.o_condition[:eng.batch_size].cpu().numpy()
     got["pooled"] = eng.o_pooled[:eng.batch_size].cpu().numpy()
     got["grads"] = {f: g.detach().cpu().numpy() for f, g in eng.params.grad_views.items()}
+    if emulate is None:
+        emulate = cfg.precision == "bf16"
     out, cache = O.forward(case["params"], case["feats"], case["nb"], case["batch"], case["m"],
                            variant=cfg.variant, keep_att=cfg.keep_att, keep_joint=cfg.keep_joint,
-                           att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy())
+                           att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy(),
+                           operand_round=O.round_bf16 if emulate else None)
+    if emulate:  # the reference's own arithmetic, for the forward gates of the north star
+        case["plain_out"], _ = O.forward(case["params"], case["feats"], case["nb"], case["batch"], case["m"],
+                                         variant=cfg.variant, keep_att=cfg.keep_att, keep_joint=cfg.keep_joint,
+                                         att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy())
     inter = {}
     ref_g = O.backward(cache, loss_scale=loss_scale, intermediates=inter)
     case["oracle_cache"], case["oracle_inter"], case["loss_scale"] = cache, inter, loss_scale

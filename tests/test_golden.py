@@ -1,0 +1,88 @@
+"""Golden vectors: (1) published Philox4x32-10 known answers pin the dropout bit source; (2) the committed
+oracle outputs (tests/golden/answer_model_small.npz, made by tests/golden/make_golden.py) pin the oracle;
+(3) on the GPU, vqa_dropout_masks() equals the NumPy Philox bit for bit and the CUDA path in fp32 mode
+reproduces the golden outputs through the C ABI."""
+import importlib.util
+import os
+
+import numpy as np
+import pytest
+
+from oracle import answer_model_np as O
+from oracle import philox_np as PH
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+_spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+MG = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(MG)
+GOLD = np.load(os.path.join(HERE, "golden", "answer_model_small.npz"))
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors, philox4x32 with 10 rounds."""
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+        ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+        ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)),
+    ]
+    for ctr, key, want in kat:
+        got = PH.philox4x32_10(*[np.array([c], np.uint64) for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == want
+
+
+def test_keep_mask_statistics_and_edges():
+    m = PH.keep_mask(1 << 18, 0.8, 777, 3, PH.SITE_ATT)
+    assert abs(m.mean() - 0.8) < 5e-3
+    assert PH.keep_mask(64, 1.0, 1, 2, 1).all()
+    a, b = PH.keep_mask(4096, 0.5, 1, 2, PH.SITE_ATT), PH.keep_mask(4096, 0.5, 1, 2, PH.SITE_JOINT)
+    assert (a != b).any()
+    assert np.array_equal(a, PH.keep_mask(4096, 0.5, 1, 2, PH.SITE_ATT))
+
+
+@pytest.mark.parametrize("variant", sorted(MG.CASES))
+def test_oracle_reproduces_golden(variant):
+    out, g = MG.run(variant, MG.CASES[variant])
+    assert abs(out["loss"] - float(GOLD[f"{variant}/loss"])) < 1e-12
+    np.testing.assert_allclose(out["logit"], GOLD[f"{variant}/logit"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(out["att_score"], GOLD[f"{variant}/att_score"], rtol=0, atol=1e-12)
+    assert np.array_equal(out["pred"], GOLD[f"{variant}/pred"])
+    for f, v in g.items():
+        ref = GOLD[f"{variant}/grad/{f}"]
+        np.testing.assert_allclose(v, ref, rtol=1e-6, atol=1e-7 * max(np.abs(ref).max(), 1e-30))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", sorted(MG.CASES))
+def test_cuda_path_matches_golden_fp32(variant):
+    import torch
+    from parity_util import rel_err
+    from vqa_transfer_externaldata_b200.engine import AnswerModelConfig, Engine
+    c, params, exist, feats, nb, batch, (is_obj, is_attr), m, am, jm = MG.inputs(variant, MG.CASES[variant])
+    eng = Engine(AnswerModelConfig(variant=variant, precision="fp32", **c))
+    eng.set_feature_bank(feats, nb)
+    eng.set_answer_masks(is_obj, is_attr, exist)
+    eng.load_params(params)
+    eng.stage_batch(batch)
+    eng.forward(seed=MG.SEED, step=MG.STEP)
+    eng.backward()
+    d_am, d_jm = eng.dropout_masks(MG.SEED, MG.STEP)
+    torch.cuda.synchronize()
+    # integer work: bit-exact
+    assert np.array_equal(d_am.cpu().numpy(), am)
+    assert np.array_equal(d_jm.cpu().numpy(), jm)
+    assert int(d_am.sum().item()) == int(GOLD[f"{variant}/att_mask_sum"])
+    loss, _ = eng.read_scalars()
+    out = eng.outputs()
+    live = exist > 0
+    assert abs(loss - float(GOLD[f"{variant}/loss"])) / abs(float(GOLD[f"{variant}/loss"])) < 1e-4
+    assert rel_err(out["logit"].cpu().numpy()[:, live], GOLD[f"{variant}/logit"][:, live]) < 1e-4
+    assert rel_err(out["att_score"].cpu().numpy(), GOLD[f"{variant}/att_score"]) < 1e-4
+    assert np.array_equal(out["pred"].cpu().numpy(), GOLD[f"{variant}/pred"])
+    assert rel_err(eng.o_condition[:c["B"]].cpu().numpy(), GOLD[f"{variant}/condition"]) < 1e-4
+    for f in O.trainable_fields(variant):
+        ref = GOLD[f"{variant}/grad/{f}"]
+        if np.abs(ref).max() > 1e-12:
+            # near-tie ReLU gates are handled in test_model_gpu (oracle-bounded); here a looser 1e-3 catches
+            # structural errors against the committed file
+            assert rel_err(eng.params.grad_views[f].cpu().numpy(), ref) < 1e-3, f

@@ -10,13 +10,14 @@ Definition of "relative" fixed here:
     fp32-mode gradients may additionally deviate by the exact effect of ReLU gates whose oracle
     pre-activation is zero to working precision (|y| < 5e-5): d relu is discontinuous there and the
     gradient is linear in each gate, so the oracle itself bounds that effect (parity_util.relu_tie_budget).
-  * bf16-mode gradients: ||x - ref||_2 / ||ref||_2 per tensor <= 0.15 (NOT 2e-2). With bf16 operands the
-    pre-activations carry ~2e-3 relative error, so 0.2-0.5 % of the ReLU gates flip against an fp64 oracle;
-    each flip is a 100 % error on that element and the gradient is linear in the gates, which alone gives
-    3-15 % relative-L2 error in exact arithmetic (reproduced on the oracle by
-    tests/test_oracle.py::test_relu_gate_flip_noise_model). The 2e-2 gate of the north star is therefore met
-    on logits / loss / attention / pooled, and is not reachable for gradients by ANY bf16-operand
-    implementation of this ReLU network; the same kernels are held to 1e-4 in fp32 mode.
+  * bf16 mode, forward tensors: compared with the reference's PLAIN arithmetic (fp64 oracle) at 2e-2.
+  * bf16 mode, gradients: compared at 2e-2 (max-norm) with the oracle restating the mode's mixed-precision
+    arithmetic (oracle.round_bf16 on every GEMM operand and on the stored pre-LN v-projection), which makes
+    the same ReLU gate decisions as the device. Against the plain fp64 oracle 0.2-0.5 % of the gates flip
+    (pre-activations carry ~2e-3 relative error); each flip is a 100 % error on that element and the gradient
+    is linear in the gates, so no bf16-operand implementation can hold 2e-2 there
+    (tests/test_oracle.py::test_relu_gate_flip_noise_model reproduces 3-15 % relative-L2 on the oracle alone).
+    The same kernels are held to 1e-4 against the plain oracle in fp32 mode.
 """
 import numpy as np
 import pytest
@@ -32,13 +33,20 @@ SMALL = dict(B=16, K=12, Dv=256, D=128, L=128, A=200, T=6, W=20, Vq=50)
 MID = dict(B=48, K=36, Dv=2048, D=1024, L=1024, A=3000, T=14, W=300, Vq=512)
 FP32_TOL = 1e-4
 BF16_TOL = 2e-2
-# bf16-mode gradients: relative-L2 bound. A flipped ReLU gate is a 100 % error on that element, so a flip
-# fraction f (0.2-0.5 % with 8-bit-mantissa pre-activations) alone gives 3-15 % relative-L2 gradient error
-# in exact arithmetic (tests/test_oracle.py::test_relu_gate_flip_noise_model reproduces this on the oracle).
-BF16_GRAD_L2 = 0.15
 # ReLU gates whose oracle pre-activation is below this are undecidable at fp32-mode working precision
 # (the pre-LN projection carries ~1e-5 relative error from the hi/lo bf16 operand split)
 FP32_TIE_TAU = 5e-5
+
+
+def _check_forward_plain(case, got, tol):
+    """bf16 mode against the reference's plain arithmetic: logits, loss, attention, pooled, condition."""
+    ref = case["plain_out"]
+    live = case["m"]["exist"] > 0
+    assert rel_err(got["logit"][:, live], ref["logit"][:, live]) < tol
+    assert abs(got["loss"] - ref["loss"]) / abs(ref["loss"]) < tol
+    assert rel_err(got["att_score"], ref["att_score"]) < tol
+    assert rel_err(got["pooled"], ref["pooled"]) < tol
+    assert rel_err(got["condition"], ref["condition"]) < tol
 
 
 def _check(case, got, ref, ref_g, tol, exact_pred=True, grad_metric="max", grad_tol=None):
@@ -99,8 +107,10 @@ def test_fp32_small(variant):
 def test_bf16_small(variant):
     case = build_case(SMALL, variant=variant, precision="bf16", seed=2)
     got, ref, ref_g = run_both(case)
-    _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False, grad_metric="l2", grad_tol=BF16_GRAD_L2)
-    assert (got["pred"] == ref["pred"]).mean() >= 0.9
+    _check_forward_plain(case, got, BF16_TOL)
+    worst = _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
+    print("bf16 max-norm gradient errors vs the mixed-precision oracle:", {k: f"{v:.2e}" for k, v in worst.items()})
+    assert (got["pred"] == case["plain_out"]["pred"]).mean() >= 0.9
 
 
 def test_fp32_reference_shapes():
@@ -115,9 +125,10 @@ def test_fp32_reference_shapes():
 def test_bf16_reference_shapes_top1():
     case = build_case(MID, precision="bf16", seed=4, num_images=40)
     got, ref, ref_g = run_both(case)
-    worst = _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False, grad_metric="l2", grad_tol=BF16_GRAD_L2)
-    print("bf16 relative-L2 gradient errors:", {k: f"{v:.2e}" for k, v in worst.items()})
-    print("bf16 max-norm gradient errors:", {k: f"{rel_err(got['grads'][k], ref_g[k]):.2e}" for k in worst})
+    _check_forward_plain(case, got, BF16_TOL)
+    worst = _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
+    print("bf16 max-norm gradient errors vs the mixed-precision oracle:", {k: f"{v:.2e}" for k, v in worst.items()})
+    ref = case["plain_out"]
     agree = (got["pred"] == ref["pred"]).mean()
     # 48 samples cannot resolve 99.9 %: require all to agree unless the oracle's own top-2 gap is below
     # the bf16 tolerance
