@@ -209,6 +209,19 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* params, const VqaBa
 VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step,
                                     uint8_t* att_mask, uint8_t* joint_mask, void* stream);
 
+/* Device pointers of activations the last vqa_forward saved in the workspace (read-only; parity tests use
+ * them to account for ReLU gates decided differently at working precision). `bytes` = extent for the last
+ * batch. */
+enum {
+  VQA_ACT_HQ = 0,   /* relu(LN(q Wqv + b))            [batch, D]  fp32                            */
+  VQA_ACT_HL,       /* relu(LN(q Wl + b))             [batch, L]  fp32                            */
+  VQA_ACT_HP,       /* relu(LN(P Wp + b))             [batch, L]  fp32                            */
+  VQA_ACT_JD,       /* dropout(relu(LN(X Wj + b)))    [batch, J]  bf16 (hi plane)                 */
+  VQA_ACT_Z,        /* pre-LN v-projection            [batch*K, D] bf16 (PREC_BF16) / fp32        */
+  VQA_NUM_ACT
+};
+VQA_API VqaStatus vqa_peek_activation(VqaHandle h, int32_t which, const void** dev_ptr, uint64_t* bytes);
+
 /* ---- optimizer step (vqa/trainer.py:87-114: clip_by_global_norm(20) + Adam) ---------------------- */
 /* flat fp32 buffers of n elements (the trainable set laid out contiguously by the caller).
  * t = 1-based step count. grad_norm_out [1] receives the pre-clip global norm. */

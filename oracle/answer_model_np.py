@@ -112,12 +112,15 @@ def fc_ln_relu_fwd(x, w, b, gamma, beta, q=_ident, qz=_ident):
     return np.maximum(y, 0.0), (x, y, ln_cache)
 
 
-def fc_ln_relu_bwd(dh, w, gamma, cache, need_dx=True, flip=None):
+def fc_ln_relu_bwd(dh, w, gamma, cache, need_dx=True, flip=None, gate=None):
     """flip: optional boolean array like y; True entries use the OPPOSITE ReLU gate. The parity tests use
     it to bound the effect of gates whose pre-activation is zero to working precision (|y| < tau): the
     backward pass is linear in the gates, so each undecidable gate contributes a fixed +-delta."""
     x, y, ln_cache = cache
-    gate = y > 0
+    if gate is None:
+        gate = y > 0
+    else:  # ReLU gates decided elsewhere (the device's own decisions: the backward pass is linear in them)
+        gate = np.asarray(gate, dtype=bool).reshape(y.shape)
     if flip is not None:
         gate = np.logical_xor(gate, flip)
     dy = dh * gate
@@ -323,13 +326,14 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     return out, cache
 
 
-def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None):
+def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_override=None):
     """Gradients of loss_scale * train_loss w.r.t. every parameter (dict field -> array).
     Callers drop the frozen ones (trainable_fields). If `intermediates` is a dict it receives the
     activation gradients the per-kernel parity tests compare against (dP, dHq, dZv, dlogit)."""
     c = cache
     p = c["p"]
     gf = gate_flips or {}
+    go = gate_override or {}
     B, A = c["logit"].shape
     tmask = c["m"]["train"] if c["use_tm"] else np.ones(A)
     g = {}
@@ -339,12 +343,12 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None):
     dJd = dx @ p["ans_w"].T
     dJn = dJd * c["jm"] / c["keep_joint"]
     dX, g["joint_w"], g["joint_b"], g["joint_gamma"], g["joint_beta"] = fc_ln_relu_bwd(
-        dJn, p["joint_w"], p["joint_gamma"], c["j_cache"], flip=gf.get("joint"))
+        dJn, p["joint_w"], p["joint_gamma"], c["j_cache"], flip=gf.get("joint"), gate=go.get("joint"))
     dHp, dHl = dX * c["Hl"], dX * c["Hp"]
     dP, g["pl_w"], g["pl_b"], g["pl_gamma"], g["pl_beta"] = fc_ln_relu_bwd(
-        dHp, p["pl_w"], p["pl_gamma"], c["p_cache"], flip=gf.get("pl"))
+        dHp, p["pl_w"], p["pl_gamma"], c["p_cache"], flip=gf.get("pl"), gate=go.get("pl"))
     dq, g["ql_w"], g["ql_b"], g["ql_gamma"], g["ql_beta"] = fc_ln_relu_bwd(
-        dHl, p["ql_w"], p["ql_gamma"], c["l_cache"], flip=gf.get("ql"))
+        dHl, p["ql_w"], p["ql_gamma"], c["l_cache"], flip=gf.get("ql"), gate=go.get("ql"))
     # attention pooling + softmax + score
     V, a = c["V"], c["a"]
     da = np.einsum("bkd,bd->bk", V, dP)
@@ -357,13 +361,13 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None):
     dHv = dF * c["Hq"][:, None, :]
     dHq = (dF * c["Hv"]).sum(axis=1)
     _, g["v_w"], g["v_b"], g["v_gamma"], g["v_beta"] = fc_ln_relu_bwd(
-        dHv, p["v_w"], p["v_gamma"], c["v_cache"], need_dx=False, flip=gf.get("v"))   # V is data: no dV
+        dHv, p["v_w"], p["v_gamma"], c["v_cache"], need_dx=False, flip=gf.get("v"), gate=go.get("v"))   # V is data: no dV
     if intermediates is not None:
         _, y_v, ln_v = c["v_cache"]
         dZv, _, _ = layer_norm_bwd(dHv * (y_v > 0), p["v_gamma"], ln_v)
         intermediates.update(dlogit=dx, dP=dP, dHq=dHq, dZv=dZv, ds=ds, dHv=dHv)
     dq2, g["qv_w"], g["qv_b"], g["qv_gamma"], g["qv_beta"] = fc_ln_relu_bwd(
-        dHq, p["qv_w"], p["qv_gamma"], c["q_cache"], flip=gf.get("qv"))
+        dHq, p["qv_w"], p["qv_gamma"], c["q_cache"], flip=gf.get("qv"), gate=go.get("qv"))
     dq = dq + dq2
     dE, g["gru_gates_w"], g["gru_gates_b"], g["gru_cand_w"], g["gru_cand_b"] = gru_bwd(
         dq, c["gru_steps"], p["gru_gates_w"], p["gru_cand_w"], c["W"])

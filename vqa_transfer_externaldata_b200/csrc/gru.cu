@@ -1,16 +1,19 @@
 // Persistent recurrent kernels for the GRU question encoder (vlmap/modules.py:124-140: GRUCell under
 // dynamic_rnn) -- forward over T steps and back-propagation through time -- each as ONE cooperative launch.
 //
-// Why: a step is two DEPENDENT [B, L] x [L, 2L | L] matmuls with element-wise gate math in between; as
-// separate launches each 1-2 GFLOP GEMM costs ~20 us of fixed overhead (launch gap, TMEM alloc, barrier
-// init, pipeline fill), 65 % of the whole train step in the first profile. Here every CTA keeps its TMEM
-// allocation, mbarrier ring and tensor maps for the whole sequence, owns a fixed 128 x 64 output tile, and
-// walks the 2T phases; the gate math is the GEMM epilogue; phases are separated by a device-wide barrier
-// (all CTAs are co-resident: cooperative launch, grid <= #SMs).
-//
-// Per phase and CTA: TMA (128B-swizzled 2-D tiles, 6-stage mbarrier ring) -> tcgen05.mma (128x64x16, bf16,
-// fp32 accumulate in TMEM) -> tcgen05.ld -> epilogue math -> global stores -> release on the grid counter.
-// Weight tiles of the next phase are requested BEFORE waiting on the barrier (they do not depend on it).
+// A step is two DEPENDENT [B, L] x [L, *] matmuls with element-wise gate math in between. Design:
+//   * unit-slice ownership: CTA (s, m) owns hidden units [32 s, 32 s + 32) for batch rows [128 m, 128 m + 128).
+//     Everything element-wise about a unit (r, u, c, h and their gradients) is computed by the same lane of
+//     the same warp in every step, so the recurrent state (h, u / dh, du) lives in REGISTERS for the whole
+//     sequence and never round-trips through memory.
+//   * the CTA's weight slice (96 rows x L, bf16, 192 KB at L = 1024) is loaded into shared memory ONCE and
+//     stays resident; per phase only the activation operand (h_t / r.h / dC / dG, produced by the other CTAs
+//     of the same row tile) streams in through a TMA ring, so L2 traffic per phase is the A operand only.
+//   * per phase: TMA (128B-swizzled tiles) -> tcgen05.mma (M 128, N 64 | 32, bf16, fp32 accumulate in TMEM)
+//     -> tcgen05.ld -> swizzled shared-memory transpose -> gate math with lane = unit (all global accesses
+//     coalesced, operands of the epilogue prefetched before the MMA finishes) -> release on a per-row-tile
+//     counter. Row tiles are independent: only the CTAs sharing rows synchronise.
+//   * bias gradients are accumulated in registers across all steps (no fp32 copies of dG / dC exist).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -22,18 +25,25 @@ namespace vqa {
 
 namespace {
 
-constexpr int R_BM = 128, R_BN = 64, R_BK = 64;
-constexpr int R_STAGES = 6;
-constexpr int R_A_TILE = R_BM * R_BK * 2;  // 16 KB
-constexpr int R_B_TILE = R_BN * R_BK * 2;  // 8 KB
-constexpr int R_STAGE_BYTES = R_A_TILE + R_B_TILE;
+constexpr int R_BM = 128;   // batch rows per CTA (UMMA M)
+constexpr int R_JN = 32;    // hidden units per CTA
+constexpr int R_BK = 64;    // k-block: 64 bf16 = one 128-byte swizzle row
+constexpr int R_STAGES = 2;
+constexpr int R_A_TILE = R_BM * R_BK * 2;      // 16 KB
+constexpr int R_RING = R_STAGES * R_A_TILE;    // 32 KB: the A ring, reused as the epilogue's transpose buffer
 constexpr int R_THREADS = 192;
-constexpr int R_SMEM = R_STAGES * R_STAGE_BYTES + 1024 + 256;
+constexpr int R_TMEM_COLS = 128;               // gates accumulator at column 0 (64 wide), candidate at 64 (32 wide)
+
+__host__ __device__ constexpr int wres_bytes(int L) { return 3 * R_JN * L * 2; }
+__host__ __device__ constexpr int smem_bytes(int L) { return wres_bytes(L) + R_RING + 128 + 1024; }
 
 struct GruArgs {
-  int B, L, T;
+  int B;        // rows per time block (row stride between steps)
+  int row0;     // first batch row of this launch
+  int row_end;  // one past the last batch row of this launch
+  int L, T;
   const int* q_len;
-  unsigned int* counter;  // device-wide phase counter, zeroed before launch
+  unsigned int* counter;   // [gridDim.y] phase counters, zeroed before launch
   // forward
   const float* xg;   // [T*B, 2L] x-part of the gate pre-activations (+bias)
   const float* xc;   // [T*B, L]
@@ -42,12 +52,10 @@ struct GruArgs {
   bf16* rh_bf;       // [T*B, L]
   float* r; float* u; float* c;  // [T*B, L]
   // backward
-  float* du;         // [B, L]
-  float* dh_part;    // [B, L]
-  float* dG_f32;     // [T*B, 2L]
+  const float* dq;   // [B, L] gradient of the final state
   bf16* dG_bf;       // [T*B, 2L]
-  float* dC_f32;     // [T*B, L]
   bf16* dC_bf;       // [T*B, L]
+  float* bias_part;  // [ceil(B/128), 3L] per-row-tile partial sums of (d gates_bias | d candidate_bias)
 };
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
@@ -74,86 +82,78 @@ __device__ __forceinline__ void epi_bar_sync() {  // the 4 epilogue warps only
 }
 __device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
-// thread-private row segment helpers: 16 consecutive floats / bf16 of one row
-__device__ __forceinline__ void ld16(const float* p, float (&x)[16]) {
+// TMEM -> registers: this warp's 32 lanes (rows) x 32 consecutive fp32 columns, then into the warp's
+// transpose buffer. Row stride = NCH 16-byte chunks; chunk index XOR (row & 7) keeps both the row-per-lane
+// float4 writes and the unit-per-lane scalar reads bank-conflict free.
+template <int NCH>
+__device__ __forceinline__ void stage_cols32(uint32_t taddr, float* stg, int lane, int chunk0) {
+  uint32_t v[32];
+  ptx::tmem_ld_32x32(taddr, v);
+  ptx::tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float4 v = *reinterpret_cast<const float4*>(p + 4 * j);
-    x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+  for (int j = 0; j < 8; ++j) {
+    const int ch = chunk0 + j;
+    const int phys = (ch & ~7) | ((ch ^ lane) & 7);
+    *reinterpret_cast<float4*>(stg + (lane * NCH + phys) * 4) =
+        make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                    __uint_as_float(v[4 * j + 3]));
   }
 }
-__device__ __forceinline__ void st16(float* p, const float (&x)[16]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    *reinterpret_cast<float4*>(p + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-}
-__device__ __forceinline__ void st16_bf(bf16* p, const float (&x)[16]) {
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    __nv_bfloat162 h[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q)
-      h[q] = __nv_bfloat162(__float2bfloat16_rn(x[8 * j + 2 * q]), __float2bfloat16_rn(x[8 * j + 2 * q + 1]));
-    *reinterpret_cast<uint4*>(p + 8 * j) = *reinterpret_cast<uint4*>(h);
-  }
-}
-// TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&x)[16]) {
-  uint32_t v[16];
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+template <int NCH>
+__device__ __forceinline__ float stg_read(const float* stg, int rr, int col) {
+  const int ch = col >> 2;
+  const int phys = (ch & ~7) | ((ch ^ rr) & 7);
+  return stg[(rr * NCH + phys) * 4 + (col & 3)];
 }
 
-// MODE 0: forward. phase 2t: G = h_t Wg_h (+xg) -> r,u,rh ; phase 2t+1: C = rh_t Wc_h (+xc) -> c, h_{t+1}
-// MODE 1: BPTT.    phase 2i: dRH = dC_t Wc_h^T -> dG_t, dh_part ; phase 2i+1: dh = dG_t Wg_h^T + dh_part ->
-//                  (prepare step t-1) du, dC_{t-1}, dh_part          with t = T-1-i
+// MODE 0: forward.  phase 2t  : G = h_t Wg_h (+xg) -> r, u, r.h        (skipped matmul at t = 0: h_0 = 0)
+//                   phase 2t+1: C = (r.h) Wc_h (+xc) -> c, h_{t+1}
+// MODE 1: BPTT.     phase 0   : element-wise head of step T-1 from dq -> du, dC_{T-1}, dh_part
+//                   phase 1+2i: dRH = dC_t Wc_h^T -> dG_t, dh_part           (t = T-1-i)
+//                   phase 2+2i: dh  = dG_t Wg_h^T + dh_part -> head of step t-1   (not run for t = 0)
 template <int MODE>
 __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
     const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
-    const __grid_constant__ CUtensorMap tm_b0, const __grid_constant__ CUtensorMap tm_b1, GruArgs g) {
+    const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1, GruArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + R_STAGES * R_STAGE_BYTES);
+  const int L = g.L, T = g.T, B = g.B;
+  uint8_t* wres = smem;                       // resident weight tiles
+  uint8_t* ring = smem + wres_bytes(L);       // A ring / transpose buffer
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + R_RING);
   uint64_t* empty_bar = full_bar + R_STAGES;
   uint64_t* tmem_full_bar = empty_bar + R_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* w_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ni = blockIdx.x, mi = blockIdx.y;
-  const int m0 = mi * R_BM, n0 = ni * R_BN;
-  const unsigned int ncta = gridDim.x * gridDim.y;
-  const int B = g.B, L = g.L, T = g.T;
-  const int num_phases = 2 * T;
-  // output tiles per phase kind: forward gates 2L/64, everything else L/64
-  const int ntiles0 = (MODE == 0) ? (2 * L) / R_BN : L / R_BN;
-  const int ntiles1 = L / R_BN;
-  const int kb0 = L / R_BK;
-  const int kb1 = (MODE == 0) ? L / R_BK : (2 * L) / R_BK;
-  constexpr bool B_MN = (MODE == 0);  // forward reads TF [in,out] weights as MN-major B; BPTT as K-major B
+  const int slice = blockIdx.x, mi = blockIdx.y;
+  const int j0 = slice * R_JN;
+  const int m0 = g.row0 + mi * R_BM;
+  const unsigned int nslices = gridDim.x;
+  unsigned int* counter = g.counter + mi;
+  const int KB = L / R_BK;  // k-blocks over L
+  // resident layout. forward: [KB gates tiles of 64 rows (8 KB)] [KB candidate tiles of 32 rows (4 KB)]
+  //                  BPTT   : [KB Wc tiles of 32 rows (4 KB)]     [2 KB Wg tiles of 32 rows (4 KB)]
+  const int w1_off = (MODE == 0) ? KB * 8192 : KB * 4096;
+  const int num_phases = (MODE == 0) ? 2 * T : 2 * T;  // BPTT: 1 head + 2T - 1 matmul phases
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a0);
     ptx::prefetch_tensormap(&tm_a1);
-    ptx::prefetch_tensormap(&tm_b0);
-    ptx::prefetch_tensormap(&tm_b1);
+    ptx::prefetch_tensormap(&tm_w0);
+    ptx::prefetch_tensormap(&tm_w1);
     for (int s = 0; s < R_STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
     ptx::mbar_init(tmem_full_bar, 1);
+    ptx::mbar_init(w_bar, 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, R_BN);
+    ptx::tmem_alloc(tmem_slot, R_TMEM_COLS);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -161,33 +161,52 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // phase p -> (has matmul, which operand / weight set, time step)
+  auto phase_info = [&](int p, bool& mm, int& kind, int& t) {
+    if (MODE == 0) {
+      t = p >> 1;
+      kind = p & 1;
+      mm = t > 0;  // h_0 = 0: both products of step 0 vanish
+    } else {
+      if (p == 0) { mm = false; kind = 1; t = T; return; }  // head only; "t" = T means dh comes from dq
+      const int i = (p - 1) >> 1;
+      t = T - 1 - i;
+      kind = (p - 1) & 1;
+      mm = true;
+    }
+  };
+
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
+      // resident weights, once
+      ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(wres_bytes(L)));
+      if (MODE == 0) {
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::tma_load_2d(wres + kb * 8192, &tm_w0, w_bar, kb * R_BK, slice * 96);
+          ptx::tma_load_2d(wres + w1_off + kb * 4096, &tm_w1, w_bar, kb * R_BK, slice * 96 + 64);
+        }
+      } else {
+        for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(wres + kb * 4096, &tm_w0, w_bar, kb * R_BK, j0);
+        for (int kb = 0; kb < 2 * KB; ++kb)
+          ptx::tma_load_2d(wres + w1_off + kb * 4096, &tm_w1, w_bar, kb * R_BK, j0);
+      }
       int stage = 0;
       uint32_t phase_bit = 0;
       for (int p = 0; p < num_phases; ++p) {
-        const int kind = p & 1;
-        if (ni >= (kind ? ntiles1 : ntiles0)) continue;  // idle in this phase
-        const int step = p >> 1;
-        const int t = (MODE == 0) ? step : (T - 1 - step);
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        if (!mm) continue;
+        // the A operand of this phase was written by the epilogues of phase p-1 (all CTAs of this row tile)
+        wait_counter(counter, static_cast<unsigned int>(p) * nslices);
+        fence_proxy_async_all();
         const CUtensorMap* ta = kind ? &tm_a1 : &tm_a0;
-        const CUtensorMap* tb = kind ? &tm_b1 : &tm_b0;
-        const int nkb = kind ? kb1 : kb0;
+        const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
         const int arow = t * B + m0;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase_bit ^ 1);
-          uint8_t* st = smem + stage * R_STAGE_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], R_STAGE_BYTES);
-          // weights first: independent of the previous phase
-          if (B_MN) ptx::tma_load_2d(st + R_A_TILE, tb, &full_bar[stage], n0, kb * R_BK);
-          else ptx::tma_load_2d(st + R_A_TILE, tb, &full_bar[stage], kb * R_BK, n0);
-          if (kb == 0 && p > 0) {
-            // the A operand of this phase was written by the epilogues of phase p-1 (all CTAs)
-            wait_counter(g.counter, static_cast<unsigned int>(p) * ncta);
-            fence_proxy_async_all();
-          }
-          ptx::tma_load_2d(st, ta, &full_bar[stage], kb * R_BK, arow);
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], R_A_TILE);
+          ptx::tma_load_2d(ring + stage * R_A_TILE, ta, &full_bar[stage], kb * R_BK, arow);
           if (++stage == R_STAGES) {
             stage = 0;
             phase_bit ^= 1;
@@ -198,24 +217,31 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16(R_BM, R_BN, false, B_MN);
-      constexpr uint32_t B_LBO = B_MN ? 8192 : 16, B_STEP = B_MN ? 2048 : 32;
+      constexpr uint32_t idesc64 = ptx::make_idesc_bf16(R_BM, 64, false, false);
+      constexpr uint32_t idesc32 = ptx::make_idesc_bf16(R_BM, 32, false, false);
+      ptx::mbar_wait(w_bar, 0);
       int stage = 0;
       uint32_t phase_bit = 0;
       for (int p = 0; p < num_phases; ++p) {
-        const int kind = p & 1;
-        if (ni >= (kind ? ntiles1 : ntiles0)) continue;
-        const int nkb = kind ? kb1 : kb0;
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        if (!mm) continue;
+        const bool wide = (MODE == 0 && kind == 0);  // N = 64 (r | u columns)
+        const uint32_t idesc = wide ? idesc64 : idesc32;
+        const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
+        const uint32_t wbase = ptx::smem_u32(wres) + (kind ? w1_off : 0);
+        const uint32_t wtile = wide ? 8192 : 4096;
+        const uint32_t d_tmem = tmem_base + ((MODE == 0 && kind == 1) ? 64 : 0);
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase_bit);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(smem + stage * R_STAGE_BYTES);
-          const uint32_t sb = sa + R_A_TILE;
+          const uint32_t sa = ptx::smem_u32(ring + stage * R_A_TILE);
+          const uint32_t sb = wbase + kb * wtile;
 #pragma unroll
           for (int kk = 0; kk < R_BK / 16; ++kk) {
             const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, 1024);
-            const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * B_STEP, B_LBO, 1024);
-            ptx::umma_f16(tmem_base, da, db, idesc, (kb | kk) != 0);
+            const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 32, 16, 1024);
+            ptx::umma_f16(d_tmem, da, db, idesc, (kb | kk) != 0);
           }
           ptx::umma_commit(&empty_bar[stage]);
           if (++stage == R_STAGES) {
@@ -224,133 +250,212 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
           }
         }
         ptx::umma_commit(tmem_full_bar);
-        // the accumulator is overwritten by the next active phase only after the device-wide barrier,
-        // which this CTA's own epilogue reaches after draining TMEM: no tmem_empty barrier needed
+        // the accumulator is overwritten only after the next counter wait, which this CTA's own epilogue
+        // reaches after draining TMEM: no tmem_empty barrier needed
       }
     }
   } else {
-    // ===================== epilogue warps =====================
-    const int q = warp & 3;                 // TMEM lane quarter of this warp
-    const int row = m0 + q * 32 + lane;     // sample index
-    const bool row_ok = row < B;
-    const int et = threadIdx.x - 64;        // 0..127 within the epilogue group
+    // ===================== epilogue warps: lane = hidden unit, loop over the warp's 32 rows ============
+    const int q = warp & 3;                       // TMEM lane quarter of this warp
+    const int rbase = m0 + q * 32;                // first batch row of this warp
+    const int unit = j0 + lane;
+    float* stg = reinterpret_cast<float*>(ring) + q * (32 * 64);  // 8 KB per warp
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const int my_row = rbase + lane;
+    const int my_len = my_row < g.row_end ? g.q_len[my_row] : 0;
     uint32_t tfull_phase = 0;
-    for (int p = 0; p < num_phases; ++p) {
-      const int kind = p & 1;
-      const int step = p >> 1;
-      const int t = (MODE == 0) ? step : (T - 1 - step);
-      const bool active = ni < (kind ? ntiles1 : ntiles0);
-      // nobody may arrive for phase p before every CTA has arrived for phase p-1 (monotonic counter)
-      if (p > 0) {
-        if (lane == 0) wait_counter(g.counter, static_cast<unsigned int>(p) * ncta);
-        __syncwarp();
-      }
-      if (active) {
-        ptx::mbar_wait(tmem_full_bar, tfull_phase);
-        tfull_phase ^= 1;
-        ptx::tc_fence_after();
-        const long long trow = static_cast<long long>(t) * B + row;
-        const long long brow = static_cast<long long>(row) * L;
-        const bool valid = row_ok && (t < g.q_len[row_ok ? row : 0]);
-        const bool pvalid = row_ok && ((t - 1) < g.q_len[row_ok ? row : 0]);
-        const uint32_t trow_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-        for (int c0 = 0; c0 < R_BN; c0 += 16) {
-          float acc[16];
-          tmem_ld16(trow_addr + c0, acc);  // warp-collective: all lanes, also for masked rows
-          if (!row_ok) continue;
-          const int col = n0 + c0;
-          if (MODE == 0) {
-            if (kind == 0) {
-              float x[16];
-              ld16(g.xg + trow * 2 * L + col, x);
-              if (n0 < L) {  // reset-gate columns: r = sigmoid(.), rh = r * h_t
-                float hh[16];
-                ld16(g.h_f32 + trow * L + col, hh);
+
+    if (MODE == 0) {
+      float h[32], u[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  x[j] = sigm(acc[j] + x[j]);
-                  hh[j] *= x[j];
-                }
-                st16(g.r + trow * L + col, x);
-                st16_bf(g.rh_bf + trow * L + col, hh);
-              } else {       // update-gate columns
+      for (int rr = 0; rr < 32; ++rr) h[rr] = 0.f, u[rr] = 0.f;
+      for (int p = 0; p < num_phases; ++p) {
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        const long long tb = static_cast<long long>(t) * B;
+        if (kind == 0) {
+          float xr[32], xu[32];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) x[j] = sigm(acc[j] + x[j]);
-                st16(g.u + trow * L + (col - L), x);
-              }
-            } else {
-              float x[16], hh[16], uu[16];
-              ld16(g.xc + trow * L + col, x);
-              ld16(g.h_f32 + trow * L + col, hh);
-              ld16(g.u + trow * L + col, uu);
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float cc = tanhf(acc[j] + x[j]);
-                x[j] = cc;
-                hh[j] = valid ? uu[j] * hh[j] + (1.0f - uu[j]) * cc : hh[j];
-              }
-              st16(g.c + trow * L + col, x);
-              st16(g.h_f32 + (trow + B) * L + col, hh);
-              st16_bf(g.h_bf + (trow + B) * L + col, hh);
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            xr[rr] = xu[rr] = 0.f;
+            if (row < g.row_end) {
+              const float* x = g.xg + (tb + row) * 2 * L + unit;
+              xr[rr] = x[0];
+              xu[rr] = x[L];
             }
-          } else {
-            if (kind == 0) {
-              // dRH = acc. dr = dRH*h ; dh_part += dRH*r ; dG = [dr r(1-r), du u(1-u)]
-              float hh[16], rr[16], dp[16];
-              ld16(g.h_f32 + trow * L + col, hh);
-              ld16(g.r + trow * L + col, rr);
-              ld16(g.dh_part + brow + col, dp);
+          }
+          if (mm) {
+            ptx::mbar_wait(tmem_full_bar, tfull_phase);
+            tfull_phase ^= 1;
+            ptx::tc_fence_after();
+            stage_cols32<16>(t_lane, stg, lane, 0);
+            stage_cols32<16>(t_lane + 32, stg, lane, 8);
+            ptx::tc_fence_before();
+            __syncwarp();
+          }
 #pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float d = valid ? acc[j] : 0.f;
-                dp[j] += d * rr[j];
-                hh[j] = d * hh[j] * rr[j] * (1.f - rr[j]);
-              }
-              st16(g.dh_part + brow + col, dp);
-              st16(g.dG_f32 + trow * 2 * L + col, hh);
-              st16_bf(g.dG_bf + trow * 2 * L + col, hh);
-              float uu[16], dd[16];
-              ld16(g.u + trow * L + col, uu);
-              ld16(g.du + brow + col, dd);
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            if (row < g.row_end) {
+              const float ar = mm ? stg_read<16>(stg, rr, lane) : 0.f;
+              const float au = mm ? stg_read<16>(stg, rr, 32 + lane) : 0.f;
+              const float rv = sigm(ar + xr[rr]);
+              const float uv = sigm(au + xu[rr]);
+              u[rr] = uv;
+              const long long o = (tb + row) * L + unit;
+              g.r[o] = rv;
+              g.u[o] = uv;
+              g.rh_bf[o] = __float2bfloat16_rn(rv * h[rr]);
+            }
+          }
+        } else {
+          float xc[32];
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dd[j] = valid ? dd[j] * uu[j] * (1.f - uu[j]) : 0.f;
-              st16(g.dG_f32 + trow * 2 * L + L + col, dd);
-              st16_bf(g.dG_bf + trow * 2 * L + L + col, dd);
-            } else {
-              // dh_t = acc + dh_part ; then the element-wise head of step t-1
-              float dp[16];
-              ld16(g.dh_part + brow + col, dp);
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            xc[rr] = (row < g.row_end) ? g.xc[(tb + row) * L + unit] : 0.f;
+          }
+          if (mm) {
+            ptx::mbar_wait(tmem_full_bar, tfull_phase);
+            tfull_phase ^= 1;
+            ptx::tc_fence_after();
+            stage_cols32<8>(t_lane + 64, stg, lane, 0);
+            ptx::tc_fence_before();
+            __syncwarp();
+          }
 #pragma unroll
-              for (int j = 0; j < 16; ++j) dp[j] += acc[j];
-              if (t > 0) {
-                const long long prow = trow - B;
-                float hh[16], uu[16], cc[16], o_du[16];
-                ld16(g.h_f32 + prow * L + col, hh);
-                ld16(g.u + prow * L + col, uu);
-                ld16(g.c + prow * L + col, cc);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                  const float gdh = dp[j];
-                  o_du[j] = pvalid ? gdh * (hh[j] - cc[j]) : 0.f;
-                  hh[j] = pvalid ? gdh * (1.f - uu[j]) * (1.f - cc[j] * cc[j]) : 0.f;  // dC_{t-1}
-                  dp[j] = pvalid ? gdh * uu[j] : gdh;                                   // dh_part
-                }
-                st16(g.du + brow + col, o_du);
-                st16(g.dC_f32 + prow * L + col, hh);
-                st16_bf(g.dC_bf + prow * L + col, hh);
-              }
-              st16(g.dh_part + brow + col, dp);
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            if (row < g.row_end) {
+              const float ac = mm ? stg_read<8>(stg, rr, lane) : 0.f;
+              const float cv = tanhf(ac + xc[rr]);
+              const bool valid = t < __shfl_sync(0xffffffffu, my_len, rr);
+              const float hn = valid ? u[rr] * h[rr] + (1.0f - u[rr]) * cv : h[rr];
+              h[rr] = hn;
+              const long long o = (tb + row) * L + unit;
+              g.c[o] = cv;
+              g.h_f32[o + static_cast<long long>(B) * L] = hn;
+              g.h_bf[o + static_cast<long long>(B) * L] = __float2bfloat16_rn(hn);
             }
           }
         }
-        ptx::tc_fence_before();
+        // publish: generic-proxy stores -> visible device-wide and to the async proxy (TMA) of other SMs
+        __threadfence();
+        fence_proxy_async_all();
+        epi_bar_sync();
+        if (threadIdx.x == 64) red_release_add(counter, 1u);
+        if (p + 1 < num_phases) {
+          // nobody may overwrite what this phase's readers still use before every CTA has arrived: the next
+          // phase's epilogue writes r/u/rh or c/h of a NEW time block, so only the transpose buffer needs
+          // the wait -- it is refilled after the next tmem_full, which itself follows the producer's wait.
+        }
       }
-      // publish: generic-proxy stores -> visible device-wide and to the async proxy (TMA) of other SMs
-      __threadfence();
-      fence_proxy_async_all();
+    } else {
+      float dhp[32], du[32];   // dh_part, du of the current step, rows of this warp
+      float db_r = 0.f, db_u = 0.f, db_c = 0.f;
+#pragma unroll
+      for (int rr = 0; rr < 32; ++rr) dhp[rr] = 0.f, du[rr] = 0.f;
+      for (int p = 0; p < num_phases; ++p) {
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        if (kind == 0) {
+          // dRH = acc ;  dG_r = dRH h r (1-r) ; dG_u = du u (1-u) ; dh_part += dRH r
+          const long long tb = static_cast<long long>(t) * B;
+          float hh[32], rv[32], uv[32];
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            hh[rr] = rv[rr] = uv[rr] = 0.f;
+            if (row < g.row_end) {
+              const long long o = (tb + row) * L + unit;
+              hh[rr] = g.h_f32[o];
+              rv[rr] = g.r[o];
+              uv[rr] = g.u[o];
+            }
+          }
+          ptx::mbar_wait(tmem_full_bar, tfull_phase);
+          tfull_phase ^= 1;
+          ptx::tc_fence_after();
+          stage_cols32<8>(t_lane, stg, lane, 0);
+          ptx::tc_fence_before();
+          __syncwarp();
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            if (row < g.row_end) {
+              const float drh = stg_read<8>(stg, rr, lane);   // zero for steps beyond the question length
+              const float dgr = drh * hh[rr] * rv[rr] * (1.0f - rv[rr]);
+              const float dgu = du[rr] * uv[rr] * (1.0f - uv[rr]);
+              dhp[rr] = fmaf(drh, rv[rr], dhp[rr]);
+              db_r += dgr;
+              db_u += dgu;
+              const long long o = (tb + row) * 2 * L + unit;
+              g.dG_bf[o] = __float2bfloat16_rn(dgr);
+              g.dG_bf[o + L] = __float2bfloat16_rn(dgu);
+            }
+          }
+        } else {
+          // dh = acc + dh_part (or dq) ; element-wise head of step tp = t - 1
+          const int tp = t - 1;
+          const long long tb = static_cast<long long>(tp) * B;
+          float hh[32], uv[32], cv[32];
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            hh[rr] = uv[rr] = cv[rr] = 0.f;
+            if (row < g.row_end) {
+              const long long o = (tb + row) * L + unit;
+              hh[rr] = g.h_f32[o];
+              uv[rr] = g.u[o];
+              cv[rr] = g.c[o];
+              if (!mm) dhp[rr] = g.dq[static_cast<long long>(row) * L + unit];
+            }
+          }
+          if (mm) {
+            ptx::mbar_wait(tmem_full_bar, tfull_phase);
+            tfull_phase ^= 1;
+            ptx::tc_fence_after();
+            stage_cols32<8>(t_lane, stg, lane, 0);
+            ptx::tc_fence_before();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int row = rbase + rr;
+            if (row < g.row_end) {
+              const float dh = (mm ? stg_read<8>(stg, rr, lane) : 0.f) + dhp[rr];
+              const bool pvalid = tp < __shfl_sync(0xffffffffu, my_len, rr);
+              const float dcv = pvalid ? dh * (1.0f - uv[rr]) * (1.0f - cv[rr] * cv[rr]) : 0.f;
+              du[rr] = pvalid ? dh * (hh[rr] - cv[rr]) : 0.f;
+              dhp[rr] = pvalid ? dh * uv[rr] : dh;
+              db_c += dcv;
+              g.dC_bf[(tb + row) * L + unit] = __float2bfloat16_rn(dcv);
+            }
+          }
+        }
+        __threadfence();
+        fence_proxy_async_all();
+        epi_bar_sync();
+        if (threadIdx.x == 64) red_release_add(counter, 1u);
+      }
+      // bias gradients: sum the 4 warps of this CTA (fixed order), one partial row per row tile
+      float* red = reinterpret_cast<float*>(ring);  // transpose buffer is free now
       epi_bar_sync();
-      if (et == 0) red_release_add(g.counter, 1u);
+      red[(q * 3 + 0) * 32 + lane] = db_r;
+      red[(q * 3 + 1) * 32 + lane] = db_u;
+      red[(q * 3 + 2) * 32 + lane] = db_c;
+      epi_bar_sync();
+      if (q == 0) {
+        float* out = g.bias_part + static_cast<long long>(m0 / R_BM) * 3 * L;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          float s = 0.f;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) s += red[(w * 3 + k) * 32 + lane];
+          out[k * L + unit] = s;
+        }
+      }
     }
   }
 
@@ -358,8 +463,27 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
   __syncthreads();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, R_BN);
+    ptx::tmem_dealloc(tmem_base, R_TMEM_COLS);
   }
+}
+
+// WT_pack[s][rr][k], s = unit slice, k = input unit (K-major B operand of the forward matmuls):
+//   rr in [0,32): Wg_h[k, 32 s + rr] (reset gate) ; [32,64): Wg_h[k, L + 32 s + rr - 32] (update gate) ;
+//   [64,96): Wc_h[k, 32 s + rr - 64] (candidate).   wg_h / wc_h: bf16 rows W.. of the TF kernels, [L, 2L] / [L, L].
+__global__ void gru_pack_weights_kernel(const bf16* __restrict__ wg_h, const bf16* __restrict__ wc_h, int L,
+                                        bf16* __restrict__ out) {
+  __shared__ bf16 tile[32][33];
+  const int s = blockIdx.x;          // slice
+  const int part = blockIdx.y;       // 0 r, 1 u, 2 c
+  const int k0 = blockIdx.z * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+  const bf16* src = part == 2 ? wc_h : wg_h;
+  const int ld = part == 2 ? L : 2 * L;
+  const int col0 = (part == 1 ? L : 0) + 32 * s;
+  for (int i = ty; i < 32; i += 8) tile[i][tx] = src[static_cast<long long>(k0 + i) * ld + col0 + tx];
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8)
+    out[(static_cast<long long>(s) * 96 + part * 32 + i) * L + k0 + tx] = tile[tx][i];
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -388,64 +512,83 @@ bool encode_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 }
 
 template <int MODE>
-VqaStatus launch_persistent(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b0,
-                            const CUtensorMap& b1, const GruArgs& g, dim3 grid, cudaStream_t s) {
+VqaStatus launch_persistent(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0,
+                            const CUtensorMap& w1, GruArgs g, int num_sms, cudaStream_t s) {
   auto kern = gru_persistent_kernel<MODE>;
-  static bool set = false;
-  if (!set) {
-    VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM));
-    set = true;
+  const int smem = smem_bytes(g.L);
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    smem_set = smem;
   }
-  VQA_CUDA_CHECK(cudaMemsetAsync(g.counter, 0, sizeof(unsigned int), s));
-  void* args[] = {const_cast<CUtensorMap*>(&a0), const_cast<CUtensorMap*>(&a1), const_cast<CUtensorMap*>(&b0),
-                  const_cast<CUtensorMap*>(&b1), const_cast<GruArgs*>(&g)};
-  // cooperative launch: fails instead of deadlocking if the grid cannot be co-resident
-  VQA_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), grid, dim3(R_THREADS), args, R_SMEM, s));
-  count_launch();
+  const int slices = g.L / R_JN;
+  const int tiles_per_launch = num_sms / slices;  // co-resident row tiles
+  const int Bn = g.row_end;
+  for (int row0 = 0; row0 < Bn; row0 += tiles_per_launch * R_BM) {
+    GruArgs a = g;
+    a.row0 = row0;
+    a.row_end = Bn < row0 + tiles_per_launch * R_BM ? Bn : row0 + tiles_per_launch * R_BM;
+    const int mt = (a.row_end - row0 + R_BM - 1) / R_BM;
+    VQA_CUDA_CHECK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * mt, s));
+    void* args[] = {const_cast<CUtensorMap*>(&a0), const_cast<CUtensorMap*>(&a1), const_cast<CUtensorMap*>(&w0),
+                    const_cast<CUtensorMap*>(&w1), &a};
+    // cooperative launch: fails instead of deadlocking if the grid cannot be co-resident
+    VQA_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(slices, mt), dim3(R_THREADS),
+                                               args, smem, s));
+    count_launch();
+  }
   return VQA_OK;
 }
 
 }  // namespace
 
 bool gru_persistent_supported(int B, int L, int precision, int num_sms) {
+  (void)B;
   if (precision != VQA_PREC_BF16) return false;
   if (L % 64 != 0 || L < 64) return false;
-  const int mt = (B + R_BM - 1) / R_BM;
-  return mt * ((2 * L) / R_BN) <= num_sms;
+  if (smem_bytes(L) > 227 * 1024) return false;  // the weight slice must fit shared memory (L <= 1024)
+  return L / R_JN <= num_sms;
 }
 
-VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, cudaStream_t s) {
+size_t gru_pack_elems(int L) { return static_cast<size_t>(3) * L * L; }
+size_t gru_bias_part_floats(int B, int L) { return static_cast<size_t>((B + R_BM - 1) / R_BM + 1) * 3 * L; }
+
+VqaStatus gru_pack_weights_launch(const bf16* wg_h, const bf16* wc_h, int L, bf16* out, cudaStream_t s) {
+  gru_pack_weights_kernel<<<dim3(L / 32, 3, L / 32), dim3(32, 8), 0, s>>>(wg_h, wc_h, L, out);
+  VQA_LAUNCH_CHECK("gru_pack_weights");
+  return VQA_OK;
+}
+
+VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
   CUtensorMap tm_h, tm_rh, tm_wg, tm_wc;
+  const uint64_t prow = static_cast<uint64_t>(L / R_JN) * 96;
   bool ok = encode_bf16(&tm_h, a.h_bf, L, static_cast<uint64_t>(T + 1) * B, L, 64, R_BM) &&
             encode_bf16(&tm_rh, a.rh_bf, L, static_cast<uint64_t>(T) * B, L, 64, R_BM) &&
-            // weights: TF [in, out] rows W.. (the h part), read as MN-major B: inner = out columns
-            encode_bf16(&tm_wg, a.wg_h, 2 * L, L, 2 * L, 64, 64) &&
-            encode_bf16(&tm_wc, a.wc_h, L, L, L, 64, 64);
+            encode_bf16(&tm_wg, a.w_pack, L, prow, L, 64, 64) &&
+            encode_bf16(&tm_wc, a.w_pack, L, prow, L, 64, 32);
   if (!ok) return set_error(VQA_ERR_CUDA, "gru_fwd_persistent: cuTensorMapEncodeTiled failed");
   GruArgs g{};
-  g.B = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter; g.xg = a.xg; g.xc = a.xc;
-  g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
-  dim3 grid((2 * L) / R_BN, (B + R_BM - 1) / R_BM);
-  return launch_persistent<0>(tm_h, tm_rh, tm_wg, tm_wc, g, grid, s);
+  g.B = B; g.row0 = 0; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
+  g.xg = a.xg; g.xc = a.xc; g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
+  return launch_persistent<0>(tm_h, tm_rh, tm_wg, tm_wc, g, num_sms, s);
 }
 
-VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, cudaStream_t s) {
+VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
   CUtensorMap tm_dc, tm_dg, tm_wc, tm_wg;
   bool ok = encode_bf16(&tm_dc, a.dC_bf, L, static_cast<uint64_t>(T) * B, L, 64, R_BM) &&
             encode_bf16(&tm_dg, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B, 2 * L, 64, R_BM) &&
-            // weights as K-major B: rows = input unit (N'), contiguous = output column (K')
-            encode_bf16(&tm_wc, a.wc_h, L, L, L, 64, 64) &&
-            encode_bf16(&tm_wg, a.wg_h, 2 * L, L, 2 * L, 64, 64);
+            // weights in TF layout [in, out]: row = input unit (the N of these products), contiguous = output
+            // column (their K): K-major B operands as they are
+            encode_bf16(&tm_wc, a.wc_h, L, L, L, 64, 32) &&
+            encode_bf16(&tm_wg, a.wg_h, 2 * L, L, 2 * L, 64, 32);
   if (!ok) return set_error(VQA_ERR_CUDA, "gru_bwd_persistent: cuTensorMapEncodeTiled failed");
   GruArgs g{};
-  g.B = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
+  g.B = B; g.row0 = 0; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
   g.h_f32 = const_cast<float*>(a.h_f32); g.r = const_cast<float*>(a.r); g.u = const_cast<float*>(a.u);
-  g.c = const_cast<float*>(a.c); g.du = a.du; g.dh_part = a.dh_part; g.dG_f32 = a.dG_f32; g.dG_bf = a.dG_bf;
-  g.dC_f32 = a.dC_f32; g.dC_bf = a.dC_bf;
-  dim3 grid(L / R_BN, (B + R_BM - 1) / R_BM);
-  return launch_persistent<1>(tm_dc, tm_dg, tm_wc, tm_wg, g, grid, s);
+  g.c = const_cast<float*>(a.c); g.dq = a.dq; g.dG_bf = a.dG_bf; g.dC_bf = a.dC_bf; g.bias_part = a.bias_part;
+  return launch_persistent<1>(tm_dc, tm_dg, tm_wc, tm_wg, g, num_sms, s);
 }
 
 }  // namespace vqa

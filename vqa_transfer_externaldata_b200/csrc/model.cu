@@ -436,6 +436,24 @@ VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, u
   return VQA_OK;
 }
 
+VQA_API VqaStatus vqa_peek_activation(VqaHandle h, int32_t which, const void** dev_ptr, uint64_t* bytes) {
+  VQA_TRY(check_ready(h, "vqa_peek_activation"));
+  if (!dev_ptr || !bytes) return set_error(VQA_ERR_BAD_ARG, "vqa_peek_activation: null argument");
+  if (!h->fwd_valid) return set_error(VQA_ERR_STATE, "vqa_peek_activation: no forward pass yet");
+  const VqaConfig& c = h->cfg;
+  const uint64_t Bn = static_cast<uint64_t>(h->last_batch);
+  const Buffers& b = h->buf;
+  switch (which) {
+    case VQA_ACT_HQ: *dev_ptr = b.hq; *bytes = Bn * c.D * 4; break;
+    case VQA_ACT_HL: *dev_ptr = b.hl; *bytes = Bn * c.L * 4; break;
+    case VQA_ACT_HP: *dev_ptr = b.hp; *bytes = Bn * c.L * 4; break;
+    case VQA_ACT_JD: *dev_ptr = b.jd.hi; *bytes = Bn * c.J * 2; break;
+    case VQA_ACT_Z: *dev_ptr = b.z; *bytes = Bn * c.K * c.D * (c.precision == VQA_PREC_FP32 ? 4 : 2); break;
+    default: return set_error(VQA_ERR_BAD_ARG, "vqa_peek_activation: unknown activation %d", which);
+  }
+  return VQA_OK;
+}
+
 VQA_API VqaStatus vqa_adam_step(VqaHandle h, float* param, const float* grad, float* m, float* v, int64_t n,
                                 float lr, float beta1, float beta2, float eps, float clip_norm, int64_t t,
                                 float* grad_norm_out, void* stream) {

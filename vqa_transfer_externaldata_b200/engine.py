@@ -309,6 +309,13 @@ class Engine:
                                            joint.data_ptr(), self._stream()))
         return att, joint
 
+    def peek_activation(self, which, dtype, shape):
+        """Copy of an activation the last forward saved in the workspace (vqa_peek_activation)."""
+        ptr, nbytes = C.c_void_p(), C.c_uint64()
+        L.check(self.lib.vqa_peek_activation(self.h, which, C.byref(ptr), C.byref(nbytes)))
+        off = ptr.value - self.workspace.data_ptr()
+        return self.workspace[off:off + nbytes.value].view(dtype).view(shape).clone()
+
     def read_scalars(self):
         """D2H of loss + report (pinned, synchronises the current stream)."""
         self.h_scalars[:1].copy_(self.o_loss, non_blocking=True)

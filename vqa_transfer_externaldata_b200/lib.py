@@ -28,6 +28,7 @@ PER_SAMPLE_KEYS = [
 ]
 
 NUM_PHASES = 14
+ACT_HQ, ACT_HL, ACT_HP, ACT_JD, ACT_Z = range(5)
 
 PARAM_FIELDS = [
     "embed", "v_w", "v_b", "v_gamma", "v_beta", "gru_gates_w", "gru_gates_b", "gru_cand_w",
@@ -115,6 +116,7 @@ SYMBOLS = {
     "vqa_backward": (C.c_int32, [_P, C.POINTER(VqaParams), C.POINTER(VqaBatch), C.POINTER(VqaParams),
                                  C.c_float, _P]),
     "vqa_dropout_masks": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P]),
+    "vqa_peek_activation": (C.c_int32, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "vqa_adam_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int64, _P, _P]),
     "vqa_profile_enable": (C.c_int32, [_P, C.c_int32]),
