@@ -144,6 +144,8 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   if (J > maxc) maxc = J;
   if (Dv > maxc) maxc = Dv;
   b.gru_counter = a.take<unsigned int>(64);
+  b.gru_pack = a.take<bf16>(gru_pack_elems(static_cast<int>(L)));
+  b.gru_bias_part = a.take<float>(gru_bias_part_floats(static_cast<int>(B), static_cast<int>(L)));
   b.scratch_floats = 32 * maxc + 16 * B + 4096;
   b.scratch = a.take<float>(b.scratch_floats);
   return (a.off + 255) & ~static_cast<uint64_t>(255);

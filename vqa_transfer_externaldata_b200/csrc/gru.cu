@@ -28,13 +28,17 @@ namespace {
 constexpr int R_BM = 128;   // batch rows per CTA (UMMA M)
 constexpr int R_JN = 32;    // hidden units per CTA
 constexpr int R_BK = 64;    // k-block: 64 bf16 = one 128-byte swizzle row
-constexpr int R_STAGES = 2;
-constexpr int R_A_TILE = R_BM * R_BK * 2;      // 16 KB
-constexpr int R_RING = R_STAGES * R_A_TILE;    // 32 KB: the A ring, reused as the epilogue's transpose buffer
-constexpr int R_THREADS = 192;
+constexpr int R_STAGES = 4;
+constexpr int R_A_TILE = R_BM * R_BK * 2;      // 16 KB activation tile
+constexpr int R_W_TILE = R_JN * R_BK * 2;      // 4 KB streamed weight tile (32 rows)
+constexpr int R_STAGE = R_A_TILE + R_W_TILE;   // 20 KB
+constexpr int R_RING = R_STAGES * R_STAGE;     // 80 KB: the ring, reused as the epilogue's transpose buffer
+constexpr int R_EPI_WARPS = 16;                // 4 per TMEM lane quarter, 8 rows each
+constexpr int R_THREADS = 64 + 32 * R_EPI_WARPS;
 constexpr int R_TMEM_COLS = 128;               // gates accumulator at column 0 (64 wide), candidate at 64 (32 wide)
 
-__host__ __device__ constexpr int wres_bytes(int L) { return 3 * R_JN * L * 2; }
+// resident weights: forward = the gate columns (64 rows x L), BPTT = the Wg rows (32 rows x 2L): 128 L bytes
+__host__ __device__ constexpr int wres_bytes(int L) { return 2 * R_JN * L * 2; }
 __host__ __device__ constexpr int smem_bytes(int L) { return wres_bytes(L) + R_RING + 128 + 1024; }
 
 struct GruArgs {
@@ -56,7 +60,20 @@ struct GruArgs {
   bf16* dG_bf;       // [T*B, 2L]
   bf16* dC_bf;       // [T*B, L]
   float* bias_part;  // [ceil(B/128), 3L] per-row-tile partial sums of (d gates_bias | d candidate_bias)
+  unsigned long long* trace;  // optional [num_ctas, num_phases, 4] globaltimer stamps (scripts/gpu_gru_trace.py)
 };
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GRU_TRACE(p, k)                                                                                   \
+  do {                                                                                                    \
+    if (g.trace)                                                                                          \
+      g.trace[((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * num_phases + (p)) * 4 + (k)] = \
+          gtimer();                                                                                       \
+  } while (0)
 
 __device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
   unsigned int v;
@@ -77,22 +94,38 @@ __device__ __forceinline__ void wait_counter(const unsigned int* p, unsigned int
 __device__ __forceinline__ void fence_proxy_async_all() {
   asm volatile("fence.proxy.async;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {  // the 4 epilogue warps only
-  asm volatile("bar.sync 1, 128;" ::: "memory");
+__device__ __forceinline__ void epi_bar_all() {  // all epilogue warps
+  asm volatile("bar.sync 1, %0;" ::"n"(32 * R_EPI_WARPS) : "memory");
 }
-__device__ __forceinline__ float sigm(float x) { return 1.0f / (1.0f + __expf(-x)); }
+__device__ __forceinline__ void epi_bar_quarter(int q) {  // the 4 warps sharing a TMEM lane quarter
+  asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
+}
+__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
 
-// TMEM -> registers: this warp's 32 lanes (rows) x 32 consecutive fp32 columns, then into the warp's
-// transpose buffer. Row stride = NCH 16-byte chunks; chunk index XOR (row & 7) keeps both the row-per-lane
-// float4 writes and the unit-per-lane scalar reads bank-conflict free.
-template <int NCH>
-__device__ __forceinline__ void stage_cols32(uint32_t taddr, float* stg, int lane, int chunk0) {
-  uint32_t v[32];
-  ptx::tmem_ld_32x32(taddr, v);
+// Transpose buffer of one lane quarter: 32 rows x NCH 16-byte chunks of fp32; chunk index XOR (row & 7) keeps
+// both the row-per-lane float4 writes and the unit-per-lane scalar reads bank-conflict free.
+// stage_cols<NC>: this warp's 32 TMEM lanes (rows) x NC consecutive fp32 columns starting at column col0.
+template <int NCH, int NC>
+__device__ __forceinline__ void stage_cols(uint32_t taddr, float* stg, int lane, int col0) {
+  uint32_t v[NC];
+  if constexpr (NC == 16) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr + col0)
+        : "memory");
+  } else {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr + col0)
+                 : "memory");
+  }
   ptx::tmem_ld_wait();
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int ch = chunk0 + j;
+  for (int j = 0; j < NC / 4; ++j) {
+    const int ch = col0 / 4 + j;
     const int phys = (ch & ~7) | ((ch ^ lane) & 7);
     *reinterpret_cast<float4*>(stg + (lane * NCH + phys) * 4) =
         make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
@@ -100,10 +133,10 @@ __device__ __forceinline__ void stage_cols32(uint32_t taddr, float* stg, int lan
   }
 }
 template <int NCH>
-__device__ __forceinline__ float stg_read(const float* stg, int rr, int col) {
+__device__ __forceinline__ float stg_read(const float* stg, int row, int col) {
   const int ch = col >> 2;
-  const int phys = (ch & ~7) | ((ch ^ rr) & 7);
-  return stg[(rr * NCH + phys) * 4 + (col & 3)];
+  const int phys = (ch & ~7) | ((ch ^ row) & 7);
+  return stg[(row * NCH + phys) * 4 + (col & 3)];
 }
 
 // MODE 0: forward.  phase 2t  : G = h_t Wg_h (+xg) -> r, u, r.h        (skipped matmul at t = 0: h_0 = 0)
@@ -111,6 +144,8 @@ __device__ __forceinline__ float stg_read(const float* stg, int rr, int col) {
 // MODE 1: BPTT.     phase 0   : element-wise head of step T-1 from dq -> du, dC_{T-1}, dh_part
 //                   phase 1+2i: dRH = dC_t Wc_h^T -> dG_t, dh_part           (t = T-1-i)
 //                   phase 2+2i: dh  = dG_t Wg_h^T + dh_part -> head of step t-1   (not run for t = 0)
+// Weights: the larger matrix of the pair stays resident in shared memory (forward: the gate columns, used by
+// kind 0; BPTT: the Wg rows, used by kind 1); the smaller one (32 rows) streams through the ring next to A.
 template <int MODE>
 __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
     const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
@@ -120,7 +155,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
                                              ~static_cast<uintptr_t>(1023));
   const int L = g.L, T = g.T, B = g.B;
   uint8_t* wres = smem;                       // resident weight tiles
-  uint8_t* ring = smem + wres_bytes(L);       // A ring / transpose buffer
+  uint8_t* ring = smem + wres_bytes(L);       // ring / transpose buffer
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + R_RING);
   uint64_t* empty_bar = full_bar + R_STAGES;
   uint64_t* tmem_full_bar = empty_bar + R_STAGES;
@@ -134,10 +169,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
   const unsigned int nslices = gridDim.x;
   unsigned int* counter = g.counter + mi;
   const int KB = L / R_BK;  // k-blocks over L
-  // resident layout. forward: [KB gates tiles of 64 rows (8 KB)] [KB candidate tiles of 32 rows (4 KB)]
-  //                  BPTT   : [KB Wc tiles of 32 rows (4 KB)]     [2 KB Wg tiles of 32 rows (4 KB)]
-  const int w1_off = (MODE == 0) ? KB * 8192 : KB * 4096;
-  const int num_phases = (MODE == 0) ? 2 * T : 2 * T;  // BPTT: 1 head + 2T - 1 matmul phases
+  constexpr int RES_KIND = (MODE == 0) ? 0 : 1;  // the phase kind whose weights are resident
+  const int num_phases = 2 * T;                  // BPTT: 1 head + 2T - 1 matmul phases
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a0);
@@ -182,14 +215,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
       // resident weights, once
       ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(wres_bytes(L)));
       if (MODE == 0) {
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::tma_load_2d(wres + kb * 8192, &tm_w0, w_bar, kb * R_BK, slice * 96);
-          ptx::tma_load_2d(wres + w1_off + kb * 4096, &tm_w1, w_bar, kb * R_BK, slice * 96 + 64);
-        }
+        for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(wres + kb * 8192, &tm_w0, w_bar, kb * R_BK, slice * 96);
       } else {
-        for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(wres + kb * 4096, &tm_w0, w_bar, kb * R_BK, j0);
-        for (int kb = 0; kb < 2 * KB; ++kb)
-          ptx::tma_load_2d(wres + w1_off + kb * 4096, &tm_w1, w_bar, kb * R_BK, j0);
+        for (int kb = 0; kb < 2 * KB; ++kb) ptx::tma_load_2d(wres + kb * 4096, &tm_w1, w_bar, kb * R_BK, j0);
       }
       int stage = 0;
       uint32_t phase_bit = 0;
@@ -197,16 +225,25 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
         if (!mm) continue;
-        // the A operand of this phase was written by the epilogues of phase p-1 (all CTAs of this row tile)
-        wait_counter(counter, static_cast<unsigned int>(p) * nslices);
-        fence_proxy_async_all();
+        const bool streamed = kind != RES_KIND;
         const CUtensorMap* ta = kind ? &tm_a1 : &tm_a0;
+        const CUtensorMap* tw = (MODE == 0) ? &tm_w1 : &tm_w0;
+        const int wrow = (MODE == 0) ? slice * 96 + 64 : j0;
         const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
         const int arow = t * B + m0;
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase_bit ^ 1);
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], R_A_TILE);
-          ptx::tma_load_2d(ring + stage * R_A_TILE, ta, &full_bar[stage], kb * R_BK, arow);
+          uint8_t* st = ring + stage * R_STAGE;
+          if (kb == 0) {
+            // the A operand of this phase was written by the epilogues of phase p-1 (all CTAs of this row
+            // tile); the ring itself doubles as their transpose buffer, so nothing may land in it earlier
+            wait_counter(counter, static_cast<unsigned int>(p) * nslices);
+            fence_proxy_async_all();
+            GRU_TRACE(p, 0);
+          }
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], streamed ? R_STAGE : R_A_TILE);
+          if (streamed) ptx::tma_load_2d(st + R_A_TILE, tw, &full_bar[stage], kb * R_BK, wrow);
+          ptx::tma_load_2d(st, ta, &full_bar[stage], kb * R_BK, arow);
           if (++stage == R_STAGES) {
             stage = 0;
             phase_bit ^= 1;
@@ -226,17 +263,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
         if (!mm) continue;
+        const bool streamed = kind != RES_KIND;
         const bool wide = (MODE == 0 && kind == 0);  // N = 64 (r | u columns)
         const uint32_t idesc = wide ? idesc64 : idesc32;
         const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
-        const uint32_t wbase = ptx::smem_u32(wres) + (kind ? w1_off : 0);
         const uint32_t wtile = wide ? 8192 : 4096;
         const uint32_t d_tmem = tmem_base + ((MODE == 0 && kind == 1) ? 64 : 0);
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase_bit);
           ptx::tc_fence_after();
-          const uint32_t sa = ptx::smem_u32(ring + stage * R_A_TILE);
-          const uint32_t sb = wbase + kb * wtile;
+          if (kb == 0) GRU_TRACE(p, 1);
+          const uint32_t sa = ptx::smem_u32(ring + stage * R_STAGE);
+          const uint32_t sb = streamed ? sa + R_A_TILE : ptx::smem_u32(wres) + kb * wtile;
 #pragma unroll
           for (int kk = 0; kk < R_BK / 16; ++kk) {
             const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, 1024);
@@ -255,204 +293,235 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
       }
     }
   } else {
-    // ===================== epilogue warps: lane = hidden unit, loop over the warp's 32 rows ============
-    const int q = warp & 3;                       // TMEM lane quarter of this warp
-    const int rbase = m0 + q * 32;                // first batch row of this warp
+    // ===================== epilogue warps: lane = hidden unit, 8 rows per warp =========================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may read
+    const int sub = (warp - 2) >> 2;              // which 8 rows of the quarter / which column group to stage
+    const int rbase = m0 + q * 32 + sub * 8;      // first batch row of this warp
     const int unit = j0 + lane;
-    float* stg = reinterpret_cast<float*>(ring) + q * (32 * 64);  // 8 KB per warp
+    float* stg = reinterpret_cast<float*>(ring) + q * (32 * 64);  // 8 KB per quarter
     const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const int my_row = rbase + lane;
-    const int my_len = my_row < g.row_end ? g.q_len[my_row] : 0;
+    const int my_row = rbase + (lane & 7);
+    const int my_len = my_row < g.row_end ? g.q_len[my_row] : 0;   // lanes 0..7 hold the lengths of the 8 rows
+    const bool leader = threadIdx.x == 64;
     uint32_t tfull_phase = 0;
+    constexpr int NR = 8;
 
     if (MODE == 0) {
-      float h[32], u[32];
+      float h[NR], u[NR];
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) h[rr] = 0.f, u[rr] = 0.f;
+      for (int rr = 0; rr < NR; ++rr) h[rr] = 0.f, u[rr] = 0.f;
       for (int p = 0; p < num_phases; ++p) {
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
         const long long tb = static_cast<long long>(t) * B;
         if (kind == 0) {
-          float xr[32], xu[32];
+          float xr[NR], xu[NR], ar[NR], au[NR];
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
-            xr[rr] = xu[rr] = 0.f;
+            xr[rr] = xu[rr] = ar[rr] = au[rr] = 0.f;
             if (row < g.row_end) {
               const float* x = g.xg + (tb + row) * 2 * L + unit;
-              xr[rr] = x[0];
-              xu[rr] = x[L];
+              xr[rr] = __ldg(x);
+              xu[rr] = __ldg(x + L);
             }
           }
           if (mm) {
             ptx::mbar_wait(tmem_full_bar, tfull_phase);
             tfull_phase ^= 1;
             ptx::tc_fence_after();
-            stage_cols32<16>(t_lane, stg, lane, 0);
-            stage_cols32<16>(t_lane + 32, stg, lane, 8);
+            if (leader) GRU_TRACE(p, 2);
+            stage_cols<16, 16>(t_lane, stg, lane, sub * 16);
             ptx::tc_fence_before();
-            __syncwarp();
+            epi_bar_quarter(q);
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) {
+              ar[rr] = stg_read<16>(stg, sub * 8 + rr, lane);
+              au[rr] = stg_read<16>(stg, sub * 8 + rr, 32 + lane);
+            }
+          }
+          float rv[NR], rh[NR];
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) {
+            rv[rr] = sigm(ar[rr] + xr[rr]);
+            u[rr] = sigm(au[rr] + xu[rr]);
+            rh[rr] = rv[rr] * h[rr];
           }
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
             if (row < g.row_end) {
-              const float ar = mm ? stg_read<16>(stg, rr, lane) : 0.f;
-              const float au = mm ? stg_read<16>(stg, rr, 32 + lane) : 0.f;
-              const float rv = sigm(ar + xr[rr]);
-              const float uv = sigm(au + xu[rr]);
-              u[rr] = uv;
               const long long o = (tb + row) * L + unit;
-              g.r[o] = rv;
-              g.u[o] = uv;
-              g.rh_bf[o] = __float2bfloat16_rn(rv * h[rr]);
+              g.r[o] = rv[rr];
+              g.u[o] = u[rr];
+              g.rh_bf[o] = __float2bfloat16_rn(rh[rr]);
             }
           }
         } else {
-          float xc[32];
+          float xc[NR], ac[NR];
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
-            xc[rr] = (row < g.row_end) ? g.xc[(tb + row) * L + unit] : 0.f;
+            ac[rr] = 0.f;
+            xc[rr] = (row < g.row_end) ? __ldg(g.xc + (tb + row) * L + unit) : 0.f;
           }
           if (mm) {
             ptx::mbar_wait(tmem_full_bar, tfull_phase);
             tfull_phase ^= 1;
             ptx::tc_fence_after();
-            stage_cols32<8>(t_lane + 64, stg, lane, 0);
+            if (leader) GRU_TRACE(p, 2);
+            stage_cols<8, 8>(t_lane + 64, stg, lane, sub * 8);
             ptx::tc_fence_before();
-            __syncwarp();
+            epi_bar_quarter(q);
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) ac[rr] = stg_read<8>(stg, sub * 8 + rr, lane);
+          }
+          float cv[NR];
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) {
+            cv[rr] = tanhf(ac[rr] + xc[rr]);
+            const bool valid = t < __shfl_sync(0xffffffffu, my_len, rr);
+            h[rr] = valid ? u[rr] * h[rr] + (1.0f - u[rr]) * cv[rr] : h[rr];
           }
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
             if (row < g.row_end) {
-              const float ac = mm ? stg_read<8>(stg, rr, lane) : 0.f;
-              const float cv = tanhf(ac + xc[rr]);
-              const bool valid = t < __shfl_sync(0xffffffffu, my_len, rr);
-              const float hn = valid ? u[rr] * h[rr] + (1.0f - u[rr]) * cv : h[rr];
-              h[rr] = hn;
               const long long o = (tb + row) * L + unit;
-              g.c[o] = cv;
-              g.h_f32[o + static_cast<long long>(B) * L] = hn;
-              g.h_bf[o + static_cast<long long>(B) * L] = __float2bfloat16_rn(hn);
+              g.c[o] = cv[rr];
+              g.h_f32[o + static_cast<long long>(B) * L] = h[rr];
+              g.h_bf[o + static_cast<long long>(B) * L] = __float2bfloat16_rn(h[rr]);
             }
           }
         }
         // publish: generic-proxy stores -> visible device-wide and to the async proxy (TMA) of other SMs
         __threadfence();
         fence_proxy_async_all();
-        epi_bar_sync();
-        if (threadIdx.x == 64) red_release_add(counter, 1u);
-        if (p + 1 < num_phases) {
-          // nobody may overwrite what this phase's readers still use before every CTA has arrived: the next
-          // phase's epilogue writes r/u/rh or c/h of a NEW time block, so only the transpose buffer needs
-          // the wait -- it is refilled after the next tmem_full, which itself follows the producer's wait.
+        epi_bar_all();
+        if (leader) {
+          red_release_add(counter, 1u);
+          GRU_TRACE(p, 3);
         }
       }
     } else {
-      float dhp[32], du[32];   // dh_part, du of the current step, rows of this warp
+      float dhp[NR], du[NR];   // dh_part, du of the current step, rows of this warp
       float db_r = 0.f, db_u = 0.f, db_c = 0.f;
 #pragma unroll
-      for (int rr = 0; rr < 32; ++rr) dhp[rr] = 0.f, du[rr] = 0.f;
+      for (int rr = 0; rr < NR; ++rr) dhp[rr] = 0.f, du[rr] = 0.f;
       for (int p = 0; p < num_phases; ++p) {
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
         if (kind == 0) {
           // dRH = acc ;  dG_r = dRH h r (1-r) ; dG_u = du u (1-u) ; dh_part += dRH r
           const long long tb = static_cast<long long>(t) * B;
-          float hh[32], rv[32], uv[32];
+          float hh[NR], rv[NR], uv[NR], acc[NR];
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
             hh[rr] = rv[rr] = uv[rr] = 0.f;
             if (row < g.row_end) {
               const long long o = (tb + row) * L + unit;
-              hh[rr] = g.h_f32[o];
-              rv[rr] = g.r[o];
-              uv[rr] = g.u[o];
+              hh[rr] = __ldg(g.h_f32 + o);
+              rv[rr] = __ldg(g.r + o);
+              uv[rr] = __ldg(g.u + o);
             }
           }
           ptx::mbar_wait(tmem_full_bar, tfull_phase);
           tfull_phase ^= 1;
           ptx::tc_fence_after();
-          stage_cols32<8>(t_lane, stg, lane, 0);
+          if (leader) GRU_TRACE(p, 2);
+          stage_cols<8, 8>(t_lane, stg, lane, sub * 8);
           ptx::tc_fence_before();
-          __syncwarp();
+          epi_bar_quarter(q);
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) acc[rr] = stg_read<8>(stg, sub * 8 + rr, lane);
+          float dgr[NR], dgu[NR];
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) {
+            const float drh = acc[rr];   // zero for steps beyond the question length (dC is zero there)
+            dgr[rr] = drh * hh[rr] * rv[rr] * (1.0f - rv[rr]);
+            dgu[rr] = du[rr] * uv[rr] * (1.0f - uv[rr]);
+            dhp[rr] = fmaf(drh, rv[rr], dhp[rr]);
+          }
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
             if (row < g.row_end) {
-              const float drh = stg_read<8>(stg, rr, lane);   // zero for steps beyond the question length
-              const float dgr = drh * hh[rr] * rv[rr] * (1.0f - rv[rr]);
-              const float dgu = du[rr] * uv[rr] * (1.0f - uv[rr]);
-              dhp[rr] = fmaf(drh, rv[rr], dhp[rr]);
-              db_r += dgr;
-              db_u += dgu;
+              db_r += dgr[rr];
+              db_u += dgu[rr];
               const long long o = (tb + row) * 2 * L + unit;
-              g.dG_bf[o] = __float2bfloat16_rn(dgr);
-              g.dG_bf[o + L] = __float2bfloat16_rn(dgu);
+              g.dG_bf[o] = __float2bfloat16_rn(dgr[rr]);
+              g.dG_bf[o + L] = __float2bfloat16_rn(dgu[rr]);
             }
           }
         } else {
           // dh = acc + dh_part (or dq) ; element-wise head of step tp = t - 1
           const int tp = t - 1;
           const long long tb = static_cast<long long>(tp) * B;
-          float hh[32], uv[32], cv[32];
+          float hh[NR], uv[NR], cv[NR], acc[NR];
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
-            hh[rr] = uv[rr] = cv[rr] = 0.f;
+            hh[rr] = uv[rr] = cv[rr] = acc[rr] = 0.f;
             if (row < g.row_end) {
               const long long o = (tb + row) * L + unit;
-              hh[rr] = g.h_f32[o];
-              uv[rr] = g.u[o];
-              cv[rr] = g.c[o];
-              if (!mm) dhp[rr] = g.dq[static_cast<long long>(row) * L + unit];
+              hh[rr] = __ldg(g.h_f32 + o);
+              uv[rr] = __ldg(g.u + o);
+              cv[rr] = __ldg(g.c + o);
+              if (!mm) dhp[rr] = __ldg(g.dq + static_cast<long long>(row) * L + unit);
             }
           }
           if (mm) {
             ptx::mbar_wait(tmem_full_bar, tfull_phase);
             tfull_phase ^= 1;
             ptx::tc_fence_after();
-            stage_cols32<8>(t_lane, stg, lane, 0);
+            if (leader) GRU_TRACE(p, 2);
+            stage_cols<8, 8>(t_lane, stg, lane, sub * 8);
             ptx::tc_fence_before();
-            __syncwarp();
+            epi_bar_quarter(q);
+#pragma unroll
+            for (int rr = 0; rr < NR; ++rr) acc[rr] = stg_read<8>(stg, sub * 8 + rr, lane);
+          }
+          float dcv[NR];
+#pragma unroll
+          for (int rr = 0; rr < NR; ++rr) {
+            const float dh = acc[rr] + dhp[rr];
+            const bool pvalid = tp < __shfl_sync(0xffffffffu, my_len, rr);
+            dcv[rr] = pvalid ? dh * (1.0f - uv[rr]) * (1.0f - cv[rr] * cv[rr]) : 0.f;
+            du[rr] = pvalid ? dh * (hh[rr] - cv[rr]) : 0.f;
+            dhp[rr] = pvalid ? dh * uv[rr] : dh;
           }
 #pragma unroll
-          for (int rr = 0; rr < 32; ++rr) {
+          for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
             if (row < g.row_end) {
-              const float dh = (mm ? stg_read<8>(stg, rr, lane) : 0.f) + dhp[rr];
-              const bool pvalid = tp < __shfl_sync(0xffffffffu, my_len, rr);
-              const float dcv = pvalid ? dh * (1.0f - uv[rr]) * (1.0f - cv[rr] * cv[rr]) : 0.f;
-              du[rr] = pvalid ? dh * (hh[rr] - cv[rr]) : 0.f;
-              dhp[rr] = pvalid ? dh * uv[rr] : dh;
-              db_c += dcv;
-              g.dC_bf[(tb + row) * L + unit] = __float2bfloat16_rn(dcv);
+              db_c += dcv[rr];
+              g.dC_bf[(tb + row) * L + unit] = __float2bfloat16_rn(dcv[rr]);
             }
           }
         }
         __threadfence();
         fence_proxy_async_all();
-        epi_bar_sync();
-        if (threadIdx.x == 64) red_release_add(counter, 1u);
+        epi_bar_all();
+        if (leader) {
+          red_release_add(counter, 1u);
+          GRU_TRACE(p, 3);
+        }
       }
-      // bias gradients: sum the 4 warps of this CTA (fixed order), one partial row per row tile
-      float* red = reinterpret_cast<float*>(ring);  // transpose buffer is free now
-      epi_bar_sync();
-      red[(q * 3 + 0) * 32 + lane] = db_r;
-      red[(q * 3 + 1) * 32 + lane] = db_u;
-      red[(q * 3 + 2) * 32 + lane] = db_c;
-      epi_bar_sync();
-      if (q == 0) {
+      // bias gradients: sum the 16 warps of this CTA (fixed order), one partial row per row tile
+      float* red = reinterpret_cast<float*>(ring);  // the ring is free now
+      const int e = warp - 2;
+      red[(e * 3 + 0) * 32 + lane] = db_r;
+      red[(e * 3 + 1) * 32 + lane] = db_u;
+      red[(e * 3 + 2) * 32 + lane] = db_c;
+      epi_bar_all();
+      if (e == 0) {
         float* out = g.bias_part + static_cast<long long>(m0 / R_BM) * 3 * L;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           float s = 0.f;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) s += red[(w * 3 + k) * 32 + lane];
+          for (int w = 0; w < R_EPI_WARPS; ++w) s += red[(w * 3 + k) * 32 + lane];
           out[k * L + unit] = s;
         }
       }
@@ -511,6 +580,8 @@ bool encode_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+unsigned long long* g_trace = nullptr;
+
 template <int MODE>
 VqaStatus launch_persistent(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0,
                             const CUtensorMap& w1, GruArgs g, int num_sms, cudaStream_t s) {
@@ -526,6 +597,7 @@ VqaStatus launch_persistent(const CUtensorMap& a0, const CUtensorMap& a1, const 
   const int Bn = g.row_end;
   for (int row0 = 0; row0 < Bn; row0 += tiles_per_launch * R_BM) {
     GruArgs a = g;
+    a.trace = g_trace ? g_trace + (MODE ? 1 : 0) * (1 << 17) : nullptr;
     a.row0 = row0;
     a.row_end = Bn < row0 + tiles_per_launch * R_BM ? Bn : row0 + tiles_per_launch * R_BM;
     const int mt = (a.row_end - row0 + R_BM - 1) / R_BM;
@@ -541,6 +613,11 @@ VqaStatus launch_persistent(const CUtensorMap& a0, const CUtensorMap& a1, const 
 }
 
 }  // namespace
+
+// debugging aid (not part of the ABI header): device buffer of 2 x 2^17 u64 receiving per-phase time stamps
+extern "C" __attribute__((visibility("default"))) void vqa_internal_set_gru_trace(void* dev_ptr) {
+  g_trace = static_cast<unsigned long long*>(dev_ptr);
+}
 
 bool gru_persistent_supported(int B, int L, int precision, int num_sms) {
   (void)B;

@@ -66,7 +66,9 @@ struct Buffers {
   float* dG_f32; Planes dG;  // [T*B, 2L]
   float* dE;       // [T*B, Wpad]
   float* ln_part_g; float* ln_part_b;  // [B, max(D,L,J)] LayerNorm gamma/beta partials
-  unsigned int* gru_counter;  // device-wide phase counter of the persistent GRU kernels
+  unsigned int* gru_counter;  // per-row-tile phase counters of the persistent GRU kernels
+  bf16* gru_pack;             // [L/32][96][L] packed weight slices of the forward recurrent kernel
+  float* gru_bias_part;       // [ceil(B/128)+1, 3L] partial bias gradients of the BPTT kernel
   float* scratch;  // column-sum / loss scratch
   size_t scratch_floats;
 };

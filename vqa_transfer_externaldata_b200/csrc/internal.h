@@ -74,7 +74,7 @@ VqaStatus gru_bwd_gates_launch(const float* dRH, const float* du, const float* h
                                float* dh_part, float* dG_f32, bf16* dG_hi, bf16* dG_lo,
                                cudaStream_t s);
 
-// ---- gru.cu: persistent recurrent kernels (one cooperative launch for all T steps) ----
+// ---- gru.cu: persistent recurrent kernels (one cooperative launch per <= num_sms/(L/32) row tiles) ----
 struct GruFwdPersistent {
   int B, L, T;
   const int* q_len;
@@ -83,21 +83,25 @@ struct GruFwdPersistent {
   float* h_f32; bf16* h_bf;              // [(T+1)*B, L], block 0 = zero initial state
   bf16* rh_bf;                           // [T*B, L]
   float* r; float* u; float* c;          // [T*B, L]
-  const bf16* wg_h; const bf16* wc_h;    // bf16 shadows of the h-rows of the TF kernels: [L, 2L], [L, L]
+  const bf16* w_pack;                    // [L/32][96][L] packed K-major weight slices (gru_pack_weights_launch)
 };
 struct GruBwdPersistent {
   int B, L, T;
   const int* q_len;
   unsigned int* counter;
   const float* h_f32; const float* r; const float* u; const float* c;
-  float* du; float* dh_part;             // [B, L]; hold the element-wise head of step T-1 on entry
-  float* dG_f32; bf16* dG_bf;            // [T*B, 2L]
-  float* dC_f32; bf16* dC_bf;            // [T*B, L]; block T-1 filled on entry
-  const bf16* wg_h; const bf16* wc_h;
+  const float* dq;                       // [B, L] gradient of the final state
+  bf16* dG_bf;                           // [T*B, 2L]
+  bf16* dC_bf;                           // [T*B, L]
+  float* bias_part;                      // [ceil(B/128), 3L] partial bias gradients (gates r | gates u | candidate)
+  const bf16* wg_h; const bf16* wc_h;    // bf16 shadows of the h-rows of the TF kernels: [L, 2L], [L, L]
 };
 bool gru_persistent_supported(int B, int L, int precision, int num_sms);
-VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, cudaStream_t s);
-VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, cudaStream_t s);
+size_t gru_pack_elems(int L);
+size_t gru_bias_part_floats(int B, int L);
+VqaStatus gru_pack_weights_launch(const bf16* wg_h, const bf16* wc_h, int L, bf16* out, cudaStream_t s);
+VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cudaStream_t s);
+VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cudaStream_t s);
 
 // ---- rows.cu: row LayerNorm + ReLU heads (modules.fc_layer with use_ln, vlmap/modules.py:630-650) ----
 struct RowLnFwd {

@@ -96,6 +96,9 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
     if (!it.src) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: null weight pointer");
     VQA_TRY(split_bf16_launch(it.src, it.rows, it.cols, it.cols, it.dst->hi, it.dst->lo, it.cols, s));
   }
+  if (gru_persistent_supported(c.B, c.L, c.precision, h->num_sms))
+    VQA_TRY(gru_pack_weights_launch(w.gru_gates_w.hi + static_cast<long long>(c.W) * 2 * c.L,
+                                    w.gru_cand_w.hi + static_cast<long long>(c.W) * c.L, c.L, h->buf.gru_pack, s));
   h->params_ready = true;
   return VQA_OK;
 }
@@ -154,9 +157,8 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     a.B = Bn; a.L = L; a.T = T; a.q_len = batch->q_intseq_len; a.counter = b.gru_counter;
     a.xg = b.xg; a.xc = b.xc; a.h_f32 = b.h_f32; a.h_bf = b.h.hi; a.rh_bf = b.rh.hi;
     a.r = b.r; a.u = b.u; a.c = b.c;
-    a.wg_h = b.w.gru_gates_w.hi + static_cast<long long>(W) * 2 * L;
-    a.wc_h = b.w.gru_cand_w.hi + static_cast<long long>(W) * L;
-    VQA_TRY(gru_fwd_persistent_launch(a, s));
+    a.w_pack = b.gru_pack;
+    VQA_TRY(gru_fwd_persistent_launch(a, h->num_sms, s));
   } else {
     for (int t = 0; t < T; ++t) {
       VQA_TRY(GemmB(Bn, 2 * L, L).a(b.h, t * BL, L, false)
@@ -358,19 +360,16 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     PH_BEGIN(VQA_PH_GRU_BWD);
     float* dh_cur = b.dq;
     int pp = 0;
-    if (gru_persistent_supported(Bn, L, c.precision, h->num_sms)) {
-      // element-wise head of step T-1 from dq, then one cooperative launch for all 2T dependent GEMMs
-      const int t = T - 1;
-      VQA_TRY(gru_bwd_update_launch(dh_cur, b.h_f32 + t * BL, b.u + t * BL, b.c + t * BL,
-                                    batch->q_intseq_len, t, Bn, L, b.du, b.dh_part, b.dC_f32 + t * BL,
-                                    b.dC.hi + t * BL, nullptr, s));
+    const bool persistent = gru_persistent_supported(Bn, L, c.precision, h->num_sms);
+    if (persistent) {
+      // one cooperative launch: head of step T-1 from dq, then all 2T-1 dependent matmuls
       GruBwdPersistent a{};
       a.B = Bn; a.L = L; a.T = T; a.q_len = batch->q_intseq_len; a.counter = b.gru_counter;
-      a.h_f32 = b.h_f32; a.r = b.r; a.u = b.u; a.c = b.c; a.du = b.du; a.dh_part = b.dh_part;
-      a.dG_f32 = b.dG_f32; a.dG_bf = b.dG.hi; a.dC_f32 = b.dC_f32; a.dC_bf = b.dC.hi;
+      a.h_f32 = b.h_f32; a.r = b.r; a.u = b.u; a.c = b.c; a.dq = dh_cur;
+      a.dG_bf = b.dG.hi; a.dC_bf = b.dC.hi; a.bias_part = b.gru_bias_part;
       a.wg_h = b.w.gru_gates_w.hi + static_cast<long long>(W) * 2 * L;
       a.wc_h = b.w.gru_cand_w.hi + static_cast<long long>(W) * L;
-      VQA_TRY(gru_bwd_persistent_launch(a, s));
+      VQA_TRY(gru_bwd_persistent_launch(a, h->num_sms, s));
       (void)pp;
     } else {
       for (int t = T - 1; t >= 0; --t) {
@@ -403,8 +402,14 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
                   .f32(g->gru_cand_w + static_cast<long long>(W) * L, L).run(h, s));
       VQA_TRY(GemmB(W, L, TB).a(b.e, 0, Wp, true).b(b.dC, 0, L, true).f32(g->gru_cand_w, L).run(h, s));
     }
-    if (g->gru_gates_b) VQA_TRY(colsum_launch(b.dG_f32, TB, 2 * L, 2 * L, g->gru_gates_b, b.scratch, s));
-    if (g->gru_cand_b) VQA_TRY(colsum_launch(b.dC_f32, TB, L, L, g->gru_cand_b, b.scratch, s));
+    if (persistent) {
+      const int mt = (Bn + 127) / 128;  // row tiles of the BPTT kernel
+      if (g->gru_gates_b) VQA_TRY(colsum_launch(b.gru_bias_part, mt, 2 * L, 3 * L, g->gru_gates_b, b.scratch, s));
+      if (g->gru_cand_b) VQA_TRY(colsum_launch(b.gru_bias_part + 2 * L, mt, L, 3 * L, g->gru_cand_b, b.scratch, s));
+    } else {
+      if (g->gru_gates_b) VQA_TRY(colsum_launch(b.dG_f32, TB, 2 * L, 2 * L, g->gru_gates_b, b.scratch, s));
+      if (g->gru_cand_b) VQA_TRY(colsum_launch(b.dC_f32, TB, L, L, g->gru_cand_b, b.scratch, s));
+    }
     PH_END(VQA_PH_GRU_WGRAD);
     PH_BEGIN(VQA_PH_EMBED_BWD);
     if (g->embed) {
