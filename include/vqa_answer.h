@@ -187,8 +187,9 @@ VQA_API VqaStatus vqa_workspace_bytes(VqaHandle h, uint64_t* bytes);
 VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes);
 
 /* ---- the path ---------------------------------------------------------------------------------- */
-/* Refresh the GEMM-operand shadows of the weights (bf16 [hi, lo] planes). Call after every parameter
- * update and before the first forward. Replaces nothing in the reference (TF reads fp32 variables). */
+/* Refresh the GEMM-operand shadows of the weights (bf16 [hi, lo] planes). Call before the first forward and
+ * after every parameter update; weight matrices whose pointer is NULL are left as they are (after an
+ * optimizer step only the trainable ones changed). Replaces nothing in the reference (TF reads fp32 variables). */
 VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* params, void* stream);
 
 /* Forward of Model.build() (vqa/model_vlmap_answer.py:102-288): gather -> v-proj -> GRU -> attention ->

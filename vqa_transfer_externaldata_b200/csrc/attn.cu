@@ -502,28 +502,11 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K,
   }
 }
 
-// out[c] = sum_b part[b, c]   (deterministic: fixed order over b)
-__global__ void attn_part_reduce_kernel(const float* __restrict__ part, int batch, int width,
-                                        float* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= width) return;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-  int b = 0;
-  for (; b + 4 <= batch; b += 4) {
-    s0 += part[static_cast<long long>(b) * width + c];
-    s1 += part[static_cast<long long>(b + 1) * width + c];
-    s2 += part[static_cast<long long>(b + 2) * width + c];
-    s3 += part[static_cast<long long>(b + 3) * width + c];
-  }
-  for (; b < batch; ++b) s0 += part[static_cast<long long>(b) * width + c];
-  out[c] = (s0 + s1) + (s2 + s3);
-}
-
 }  // namespace
 
 size_t attn_bwd_partial_floats(int batch, int D) {
-  // [batch, 4D+8] per-CTA partials + [4D+8] reduced
-  return static_cast<size_t>(batch + 1) * (4 * static_cast<size_t>(D) + 8);
+  // [batch, 4D+8] per-CTA partials + [4D+8] reduced + [32, 4D+8] scratch of the two-pass column sum
+  return static_cast<size_t>(batch + 1 + 32) * (4 * static_cast<size_t>(D) + 8);
 }
 
 VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precision, float keep,
@@ -599,8 +582,7 @@ VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precisi
   // reduce the per-sample partials: [dw | dgamma | dbeta | dbias | db]
   const int width = 4 * D + 8;
   float* reduced = partials + static_cast<size_t>(a.batch) * width;
-  attn_part_reduce_kernel<<<(width + 127) / 128, 128, 0, s>>>(partials, a.batch, width, reduced);
-  VQA_LAUNCH_CHECK("attn_part_reduce");
+  VQA_TRY(colsum_launch(partials, a.batch, width, width, reduced, reduced + width, s));
   struct { float* dst; int off; int n; } outs[5] = {
       {a.d_att_w, 0, D}, {a.d_gamma, D, D}, {a.d_beta, 2 * D, D}, {a.d_bias, 3 * D, D}, {a.d_att_b, 4 * D, 1}};
   for (auto& o : outs)

@@ -147,7 +147,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   b.gru_pack = a.take<bf16>(gru_pack_elems(static_cast<int>(L)));
   b.gru_bias_part = a.take<float>(gru_bias_part_floats(static_cast<int>(B), static_cast<int>(L)));
   b.scratch_floats = 32 * maxc + 16 * B + 4096;
-  b.scratch = a.take<float>(b.scratch_floats);
+  b.scratch = a.take<float>(b.scratch_floats * (1 + VqaHandle_t::kAux));
   return (a.off + 255) & ~static_cast<uint64_t>(255);
 }
 
@@ -206,6 +206,16 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   h->profile = false;
   h->ev_created = false;
   for (int i = 0; i < VQA_NUM_PHASES; ++i) h->ev_used[i] = false;
+  h->aux_created = false;
+  for (int i = 0; i < VqaHandle_t::kAux; ++i) {
+    if (cudaStreamCreateWithFlags(&h->aux[i], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join[i], cudaEventDisableTiming) != cudaSuccess) {
+      delete h;
+      return set_error(VQA_ERR_CUDA, "vqa_create: could not create the auxiliary streams");
+    }
+  }
+  h->aux_created = true;
   h->ws_needed = plan_workspace(h, nullptr);
   *out = h;
   return VQA_OK;
@@ -216,6 +226,12 @@ VQA_API VqaStatus vqa_destroy(VqaHandle h) {
     for (int i = 0; i < VQA_NUM_PHASES; ++i) {
       cudaEventDestroy(h->ev[i][0]);
       cudaEventDestroy(h->ev[i][1]);
+    }
+  if (h && h->aux_created)
+    for (int i = 0; i < VqaHandle_t::kAux; ++i) {
+      cudaStreamDestroy(h->aux[i]);
+      cudaEventDestroy(h->ev_fork[i]);
+      cudaEventDestroy(h->ev_join[i]);
     }
   delete h;
   return VQA_OK;

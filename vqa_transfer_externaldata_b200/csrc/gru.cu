@@ -71,7 +71,7 @@ __device__ __forceinline__ unsigned long long gtimer() {
 #define GRU_TRACE(p, k)                                                                                   \
   do {                                                                                                    \
     if (g.trace)                                                                                          \
-      g.trace[((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * num_phases + (p)) * 4 + (k)] = \
+      g.trace[((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * num_phases + (p)) * 8 + (k)] = \
           gtimer();                                                                                       \
   } while (0)
 
@@ -100,7 +100,17 @@ __device__ __forceinline__ void epi_bar_all() {  // all epilogue warps
 __device__ __forceinline__ void epi_bar_quarter(int q) {  // the 4 warps sharing a TMEM lane quarter
   asm volatile("bar.sync %0, 128;" ::"r"(2 + q) : "memory");
 }
-__device__ __forceinline__ float sigm(float x) { return __fdividef(1.0f, 1.0f + __expf(-x)); }
+// the persistent kernels exist in bf16 mode only: MUFU.TANH (2^-11 relative) is far inside its operand rounding
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void red_relaxed_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // Transpose buffer of one lane quarter: 32 rows x NCH 16-byte chunks of fp32; chunk index XOR (row & 7) keeps
 // both the row-per-lane float4 writes and the unit-per-lane scalar reads bank-conflict free.
@@ -314,6 +324,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
         const long long tb = static_cast<long long>(t) * B;
+        float sv[NR];   // r (kind 0) or c (kind 1) of this phase
         if (kind == 0) {
           float xr[NR], xu[NR], ar[NR], au[NR];
 #pragma unroll
@@ -339,24 +350,20 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
               ar[rr] = stg_read<16>(stg, sub * 8 + rr, lane);
               au[rr] = stg_read<16>(stg, sub * 8 + rr, 32 + lane);
             }
+            if (leader) GRU_TRACE(p, 4);
           }
-          float rv[NR], rh[NR];
 #pragma unroll
           for (int rr = 0; rr < NR; ++rr) {
-            rv[rr] = sigm(ar[rr] + xr[rr]);
+            sv[rr] = sigm(ar[rr] + xr[rr]);
             u[rr] = sigm(au[rr] + xu[rr]);
-            rh[rr] = rv[rr] * h[rr];
           }
+          // the operand the other CTAs wait for goes out first; r / u (kept for BPTT) after the arrival
 #pragma unroll
           for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
-            if (row < g.row_end) {
-              const long long o = (tb + row) * L + unit;
-              g.r[o] = rv[rr];
-              g.u[o] = u[rr];
-              g.rh_bf[o] = __float2bfloat16_rn(rh[rr]);
-            }
+            if (row < g.row_end) g.rh_bf[(tb + row) * L + unit] = __float2bfloat16_rn(sv[rr] * h[rr]);
           }
+          if (leader) GRU_TRACE(p, 5);
         } else {
           float xc[NR], ac[NR];
 #pragma unroll
@@ -376,31 +383,43 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
 #pragma unroll
             for (int rr = 0; rr < NR; ++rr) ac[rr] = stg_read<8>(stg, sub * 8 + rr, lane);
           }
-          float cv[NR];
 #pragma unroll
           for (int rr = 0; rr < NR; ++rr) {
-            cv[rr] = tanhf(ac[rr] + xc[rr]);
+            sv[rr] = tanh_fast(ac[rr] + xc[rr]);
             const bool valid = t < __shfl_sync(0xffffffffu, my_len, rr);
-            h[rr] = valid ? u[rr] * h[rr] + (1.0f - u[rr]) * cv[rr] : h[rr];
+            h[rr] = valid ? u[rr] * h[rr] + (1.0f - u[rr]) * sv[rr] : h[rr];
           }
 #pragma unroll
           for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
-            if (row < g.row_end) {
-              const long long o = (tb + row) * L + unit;
-              g.c[o] = cv[rr];
-              g.h_f32[o + static_cast<long long>(B) * L] = h[rr];
-              g.h_bf[o + static_cast<long long>(B) * L] = __float2bfloat16_rn(h[rr]);
-            }
+            if (row < g.row_end) g.h_bf[(tb + B + row) * L + unit] = __float2bfloat16_rn(h[rr]);
           }
         }
-        // publish: generic-proxy stores -> visible device-wide and to the async proxy (TMA) of other SMs
-        __threadfence();
-        fence_proxy_async_all();
+        // publish (the pattern of a grid barrier: CTA barrier, then ONE thread fences and releases): the
+        // stores of all epilogue threads become visible device-wide and to the async proxy (TMA) of other SMs
         epi_bar_all();
         if (leader) {
-          red_release_add(counter, 1u);
+          GRU_TRACE(p, 6);
+          fence_acq_rel_gpu();
+          fence_proxy_async_all();
+          GRU_TRACE(p, 7);
+          red_relaxed_add(counter, 1u);
           GRU_TRACE(p, 3);
+        }
+        // what only BPTT reads goes out off the critical path
+#pragma unroll
+        for (int rr = 0; rr < NR; ++rr) {
+          const int row = rbase + rr;
+          if (row < g.row_end) {
+            const long long o = (tb + row) * L + unit;
+            if (kind == 0) {
+              g.r[o] = sv[rr];
+              g.u[o] = u[rr];
+            } else {
+              g.c[o] = sv[rr];
+              g.h_f32[o + static_cast<long long>(B) * L] = h[rr];
+            }
+          }
         }
       }
     } else {
@@ -500,11 +519,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
             }
           }
         }
-        __threadfence();
-        fence_proxy_async_all();
         epi_bar_all();
         if (leader) {
-          red_release_add(counter, 1u);
+          fence_acq_rel_gpu();
+          fence_proxy_async_all();
+          red_relaxed_add(counter, 1u);
           GRU_TRACE(p, 3);
         }
       }

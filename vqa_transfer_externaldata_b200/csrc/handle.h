@@ -69,7 +69,7 @@ struct Buffers {
   unsigned int* gru_counter;  // per-row-tile phase counters of the persistent GRU kernels
   bf16* gru_pack;             // [L/32][96][L] packed weight slices of the forward recurrent kernel
   float* gru_bias_part;       // [ceil(B/128)+1, 3L] partial bias gradients of the BPTT kernel
-  float* scratch;  // column-sum / loss scratch
+  float* scratch;  // column-sum / loss scratch: (1 + kAux) regions of scratch_floats, one per stream
   size_t scratch_floats;
 };
 
@@ -92,6 +92,12 @@ struct VqaHandle_t {
   int last_batch, last_T;
   uint64_t last_seed, last_step;
   VqaAnswerMasks last_masks;
+  // auxiliary streams: independent branches of the graph (x-projections vs v-projection, the weight-gradient
+  // GEMMs) are forked off the caller's stream and joined back with events -- capturable in a CUDA graph
+  static constexpr int kAux = 3;
+  cudaStream_t aux[kAux];
+  cudaEvent_t ev_fork[kAux], ev_join[kAux];
+  bool aux_created;
   // optional per-phase timing
   bool profile;
   cudaEvent_t ev[VQA_NUM_PHASES][2];

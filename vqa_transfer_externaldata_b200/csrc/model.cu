@@ -66,6 +66,22 @@ VqaStatus check_ready(VqaHandle h, const char* who) {
     }                                                                               \
   } while (0)
 
+// fork an independent branch onto auxiliary stream i (returns the caller's stream when serialised for
+// per-phase profiling); join makes the caller's stream wait for it
+VqaStatus fork_stream(VqaHandle h, int i, cudaStream_t s, cudaStream_t* out) {
+  if (h->profile) { *out = s; return VQA_OK; }
+  VQA_CUDA_CHECK(cudaEventRecord(h->ev_fork[i], s));
+  VQA_CUDA_CHECK(cudaStreamWaitEvent(h->aux[i], h->ev_fork[i], 0));
+  *out = h->aux[i];
+  return VQA_OK;
+}
+VqaStatus join_stream(VqaHandle h, int i, cudaStream_t s) {
+  if (h->profile) return VQA_OK;
+  VQA_CUDA_CHECK(cudaEventRecord(h->ev_join[i], h->aux[i]));
+  VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join[i], 0));
+  return VQA_OK;
+}
+
 VqaStatus copy_out(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   if (!dst || bytes == 0) return VQA_OK;
   VQA_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
@@ -93,10 +109,13 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
       {p->ans_w, &w.ans_w, c.J, c.A},
   };
   for (auto& it : items) {
-    if (!it.src) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: null weight pointer");
+    if (!it.src) {
+      if (!h->params_ready) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: the first call needs every weight");
+      continue;  // unchanged since the last call
+    }
     VQA_TRY(split_bf16_launch(it.src, it.rows, it.cols, it.cols, it.dst->hi, it.dst->lo, it.cols, s));
   }
-  if (gru_persistent_supported(c.B, c.L, c.precision, h->num_sms))
+  if ((p->gru_gates_w || p->gru_cand_w) && gru_persistent_supported(c.B, c.L, c.precision, h->num_sms))
     VQA_TRY(gru_pack_weights_launch(w.gru_gates_w.hi + static_cast<long long>(c.W) * 2 * c.L,
                                     w.gru_cand_w.hi + static_cast<long long>(c.W) * c.L, c.L, h->buf.gru_pack, s));
   h->params_ready = true;
@@ -125,6 +144,25 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   const bool fp32 = c.precision == VQA_PREC_FP32;
   const long long BL = static_cast<long long>(Bn) * L;
 
+  // branch 0 (auxiliary stream): embedding lookup + the hoisted x-parts of the GRU pre-activations; it is
+  // epilogue/store-bound and overlaps the MMA-bound v-projection below      (:134-137, modules.py:124-140)
+  cudaStream_t s1 = s;
+  auto gru_inputs = [&](cudaStream_t st) -> VqaStatus {
+    VQA_TRY(embed_gather_launch(p->embed, batch->q_intseq, Bn, T, T, W, Wp, Bn, b.e.hi, b.e.lo, st));
+    VQA_TRY(GemmB(T * Bn, 2 * L, W).a(b.e, 0, Wp, false).b(b.w.gru_gates_w, 0, 2 * L, true)
+                .bias(p->gru_gates_b).f32(b.xg, 2 * L).run(h, st));
+    VQA_TRY(GemmB(T * Bn, L, W).a(b.e, 0, Wp, false).b(b.w.gru_cand_w, 0, L, true)
+                .bias(p->gru_cand_b).f32(b.xc, L).run(h, st));
+    VQA_TRY(fill_zero_launch(b.h_f32, sizeof(float) * BL, st));
+    VQA_TRY(fill_zero_launch(b.h.hi, sizeof(bf16) * BL, st));
+    if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, st));
+    return VQA_OK;
+  };
+  if (!h->profile) {
+    VQA_TRY(fork_stream(h, 0, s, &s1));
+    VQA_TRY(gru_inputs(s1));
+  }
+
   PH_BEGIN(VQA_PH_GATHER);
   // a0: V = features[image_idx], nbox = num_boxes[image_idx]      (model_vlmap_answer.py:110-123)
   VQA_TRY(gather_features_launch(bank->features, bank->num_boxes,
@@ -141,16 +179,10 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(g.run(h, s));
   }
   PH_END(VQA_PH_VPROJ_FWD);
+  VQA_TRY(join_stream(h, 0, s));
   PH_BEGIN(VQA_PH_GRU_FWD);
-  // a2: embedding lookup + GRU                                     (:134-137, modules.py:124-140)
-  VQA_TRY(embed_gather_launch(p->embed, batch->q_intseq, Bn, T, T, W, Wp, Bn, b.e.hi, b.e.lo, s));
-  VQA_TRY(GemmB(T * Bn, 2 * L, W).a(b.e, 0, Wp, false).b(b.w.gru_gates_w, 0, 2 * L, true)
-              .bias(p->gru_gates_b).f32(b.xg, 2 * L).run(h, s));
-  VQA_TRY(GemmB(T * Bn, L, W).a(b.e, 0, Wp, false).b(b.w.gru_cand_w, 0, L, true)
-              .bias(p->gru_cand_b).f32(b.xc, L).run(h, s));
-  VQA_TRY(fill_zero_launch(b.h_f32, sizeof(float) * BL, s));
-  VQA_TRY(fill_zero_launch(b.h.hi, sizeof(bf16) * BL, s));
-  if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, s));
+  if (h->profile) VQA_TRY(gru_inputs(s));  // serialised for per-phase timing
+  // a2: the recurrent part of the GRU
   const bool persistent = gru_persistent_supported(Bn, L, c.precision, h->num_sms);
   if (persistent) {
     GruFwdPersistent a{};
@@ -179,20 +211,21 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
 
   PH_END(VQA_PH_GRU_FWD);
   PH_BEGIN(VQA_PH_QHEADS_FWD);
+  // a6 (question half) on the auxiliary stream: Hl = relu(LN(q Wl + b))   (:170-174); needed only by the joint head
+  VQA_TRY(fork_stream(h, 0, s, &s1));
+  VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.ql_w, 0, L, true).bias(p->ql_b).f32(b.zl, L).run(h, s1));
+  {
+    RowLnFwd r{};
+    r.rows = Bn; r.N = L; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta; r.keep = 1.f;
+    r.y = b.hl; r.mean = b.lnl_mean; r.rstd = b.lnl_rstd;
+    VQA_TRY(row_ln_relu_fwd_launch(r, s1));
+  }
   // a3: Hq = relu(LN(q Wqv + b))                                    (:142-145)
   VQA_TRY(GemmB(Bn, D, L).a(b.h, q_off, L, false).b(b.w.qv_w, 0, D, true).bias(p->qv_b).f32(b.zq, D).run(h, s));
   {
     RowLnFwd r{};
     r.rows = Bn; r.N = D; r.z = b.zq; r.gamma = p->qv_gamma; r.beta = p->qv_beta; r.keep = 1.f;
     r.y = b.hq; r.mean = b.lnq_mean; r.rstd = b.lnq_rstd;
-    VQA_TRY(row_ln_relu_fwd_launch(r, s));
-  }
-  // a6 (question half): Hl = relu(LN(q Wl + b))                      (:170-174)
-  VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.ql_w, 0, L, true).bias(p->ql_b).f32(b.zl, L).run(h, s));
-  {
-    RowLnFwd r{};
-    r.rows = Bn; r.N = L; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta; r.keep = 1.f;
-    r.y = b.hl; r.mean = b.lnl_mean; r.rstd = b.lnl_rstd;
     VQA_TRY(row_ln_relu_fwd_launch(r, s));
   }
   PH_END(VQA_PH_QHEADS_FWD);
@@ -210,6 +243,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_BEGIN(VQA_PH_HEAD_FWD);
   // a6: Hp = relu(LN(P Wp + b)); X = Hp (.) Hl; Jd = dropout(relu(LN(X Wj + b)), 0.5)   (:163-181)
   VQA_TRY(GemmB(Bn, L, Dv).a(b.pooled_op, 0, Dv, false).b(b.w.pl_w, 0, L, true).bias(p->pl_b).f32(b.zp, L).run(h, s));
+  VQA_TRY(join_stream(h, 0, s));  // Hl
   {
     RowLnFwd r{};
     r.rows = Bn; r.N = L; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta; r.keep = 1.f;
@@ -349,11 +383,13 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   if (g->qv_b) VQA_TRY(colsum_launch(b.dzq_f32, Bn, D, D, g->qv_b, b.scratch, s));
   VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
   PH_END(VQA_PH_QV_BWD);
-  // dWv = V^T dZv   (the largest weight gradient: [Dv, D] over B*K rows)
-  PH_BEGIN(VQA_PH_VPROJ_WGRAD);
-  if (g->v_w) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, s));
-  PH_END(VQA_PH_VPROJ_WGRAD);
-
+  // dWv = V^T dZv (the largest weight gradient: [Dv, D] over B*K rows). Independent of everything below: it
+  // runs on an auxiliary stream next to the GRU weight-gradient GEMMs (after BPTT, whose cooperative grid
+  // needs the SMs to itself)
+  auto vproj_wgrad = [&](cudaStream_t st) -> VqaStatus {
+    if (g->v_w) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, st));
+    return VQA_OK;
+  };
   // GRU: back-propagation through time from dq
   const bool need_gru = g->gru_gates_w || g->gru_gates_b || g->gru_cand_w || g->gru_cand_b || g->embed;
   if (need_gru) {
@@ -390,39 +426,75 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       }
     }
     PH_END(VQA_PH_GRU_BWD);
-    PH_BEGIN(VQA_PH_GRU_WGRAD);
     const int TB = T * Bn;
-    if (g->gru_gates_w) {
-      VQA_TRY(GemmB(L, 2 * L, TB).a(b.h, 0, L, true).b(b.dG, 0, 2 * L, true)
-                  .f32(g->gru_gates_w + static_cast<long long>(W) * 2 * L, 2 * L).run(h, s));
-      VQA_TRY(GemmB(W, 2 * L, TB).a(b.e, 0, Wp, true).b(b.dG, 0, 2 * L, true).f32(g->gru_gates_w, 2 * L).run(h, s));
-    }
-    if (g->gru_cand_w) {
-      VQA_TRY(GemmB(L, L, TB).a(b.rh, 0, L, true).b(b.dC, 0, L, true)
-                  .f32(g->gru_cand_w + static_cast<long long>(W) * L, L).run(h, s));
-      VQA_TRY(GemmB(W, L, TB).a(b.e, 0, Wp, true).b(b.dC, 0, L, true).f32(g->gru_cand_w, L).run(h, s));
-    }
-    if (persistent) {
-      const int mt = (Bn + 127) / 128;  // row tiles of the BPTT kernel
-      if (g->gru_gates_b) VQA_TRY(colsum_launch(b.gru_bias_part, mt, 2 * L, 3 * L, g->gru_gates_b, b.scratch, s));
-      if (g->gru_cand_b) VQA_TRY(colsum_launch(b.gru_bias_part + 2 * L, mt, L, 3 * L, g->gru_cand_b, b.scratch, s));
+    float* scratch1 = b.scratch + b.scratch_floats;       // per-stream column-sum scratch
+    float* scratch2 = b.scratch + 2 * b.scratch_floats;
+    auto gates_wgrad = [&](cudaStream_t st, float* scr) -> VqaStatus {
+      if (g->gru_gates_w) {
+        VQA_TRY(GemmB(L, 2 * L, TB).a(b.h, 0, L, true).b(b.dG, 0, 2 * L, true)
+                    .f32(g->gru_gates_w + static_cast<long long>(W) * 2 * L, 2 * L).run(h, st));
+        VQA_TRY(GemmB(W, 2 * L, TB).a(b.e, 0, Wp, true).b(b.dG, 0, 2 * L, true).f32(g->gru_gates_w, 2 * L).run(h, st));
+      }
+      if (g->gru_gates_b) {
+        if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part, (Bn + 127) / 128, 2 * L, 3 * L, g->gru_gates_b, scr, st));
+        else VQA_TRY(colsum_launch(b.dG_f32, TB, 2 * L, 2 * L, g->gru_gates_b, scr, st));
+      }
+      return VQA_OK;
+    };
+    auto cand_wgrad = [&](cudaStream_t st, float* scr) -> VqaStatus {
+      if (g->gru_cand_w) {
+        VQA_TRY(GemmB(L, L, TB).a(b.rh, 0, L, true).b(b.dC, 0, L, true)
+                    .f32(g->gru_cand_w + static_cast<long long>(W) * L, L).run(h, st));
+        VQA_TRY(GemmB(W, L, TB).a(b.e, 0, Wp, true).b(b.dC, 0, L, true).f32(g->gru_cand_w, L).run(h, st));
+      }
+      if (g->gru_cand_b) {
+        if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part + 2 * L, (Bn + 127) / 128, L, 3 * L, g->gru_cand_b, scr, st));
+        else VQA_TRY(colsum_launch(b.dC_f32, TB, L, L, g->gru_cand_b, scr, st));
+      }
+      return VQA_OK;
+    };
+    auto embed_bwd = [&](cudaStream_t st) -> VqaStatus {
+      if (g->embed) {
+        // dE = dG Wg[:W]^T + dC Wc[:W]^T ; d embed = scatter_add(q_intseq, dE)
+        VQA_TRY(GemmB(TB, W, 2 * L).a(b.dG, 0, 2 * L, false).b(b.w.gru_gates_w, 0, 2 * L, false)
+                    .f32(b.dE, Wp).run(h, st));
+        VQA_TRY(GemmB(TB, W, L).a(b.dC, 0, L, false).b(b.w.gru_cand_w, 0, L, false).addend(b.dE, Wp)
+                    .f32(b.dE, Wp).run(h, st));
+        VQA_TRY(fill_zero_launch(g->embed, sizeof(float) * c.Vq * W, st));
+        VQA_TRY(embed_scatter_add_launch(b.dE, Wp, batch->q_intseq, batch->q_intseq_len, Bn, T, T, W, Bn,
+                                         g->embed, st));
+      }
+      return VQA_OK;
+    };
+    if (h->profile) {  // serialised, one phase after the other
+      PH_BEGIN(VQA_PH_VPROJ_WGRAD);
+      VQA_TRY(vproj_wgrad(s));
+      PH_END(VQA_PH_VPROJ_WGRAD);
+      PH_BEGIN(VQA_PH_GRU_WGRAD);
+      VQA_TRY(gates_wgrad(s, b.scratch));
+      VQA_TRY(cand_wgrad(s, b.scratch));
+      PH_END(VQA_PH_GRU_WGRAD);
+      PH_BEGIN(VQA_PH_EMBED_BWD);
+      VQA_TRY(embed_bwd(s));
+      PH_END(VQA_PH_EMBED_BWD);
     } else {
-      if (g->gru_gates_b) VQA_TRY(colsum_launch(b.dG_f32, TB, 2 * L, 2 * L, g->gru_gates_b, b.scratch, s));
-      if (g->gru_cand_b) VQA_TRY(colsum_launch(b.dC_f32, TB, L, L, g->gru_cand_b, b.scratch, s));
+      // four independent branches: the SMs are shared by GEMMs with different tile counts and bottlenecks
+      cudaStream_t a0, a1, a2;
+      VQA_TRY(fork_stream(h, 0, s, &a0));
+      VQA_TRY(fork_stream(h, 1, s, &a1));
+      VQA_TRY(fork_stream(h, 2, s, &a2));
+      VQA_TRY(vproj_wgrad(a0));
+      VQA_TRY(gates_wgrad(a1, scratch1));
+      VQA_TRY(cand_wgrad(a2, scratch2));
+      VQA_TRY(embed_bwd(s));
+      VQA_TRY(join_stream(h, 0, s));
+      VQA_TRY(join_stream(h, 1, s));
+      VQA_TRY(join_stream(h, 2, s));
     }
-    PH_END(VQA_PH_GRU_WGRAD);
-    PH_BEGIN(VQA_PH_EMBED_BWD);
-    if (g->embed) {
-      // dE = dG Wg[:W]^T + dC Wc[:W]^T ; d embed = scatter_add(q_intseq, dE)
-      VQA_TRY(GemmB(TB, W, 2 * L).a(b.dG, 0, 2 * L, false).b(b.w.gru_gates_w, 0, 2 * L, false)
-                  .f32(b.dE, Wp).run(h, s));
-      VQA_TRY(GemmB(TB, W, L).a(b.dC, 0, L, false).b(b.w.gru_cand_w, 0, L, false).addend(b.dE, Wp)
-                  .f32(b.dE, Wp).run(h, s));
-      VQA_TRY(fill_zero_launch(g->embed, sizeof(float) * c.Vq * W, s));
-      VQA_TRY(embed_scatter_add_launch(b.dE, Wp, batch->q_intseq, batch->q_intseq_len, Bn, T, T, W, Bn,
-                                       g->embed, s));
-    }
-    PH_END(VQA_PH_EMBED_BWD);
+  } else {
+    PH_BEGIN(VQA_PH_VPROJ_WGRAD);
+    VQA_TRY(vproj_wgrad(s));
+    PH_END(VQA_PH_VPROJ_WGRAD);
   }
   return VQA_OK;
 }

@@ -235,8 +235,14 @@ class Engine:
         self.params.load(params)
         self.prepare_params()
 
-    def prepare_params(self):
-        L.check(self.lib.vqa_prepare_params(self.h, C.byref(self._p), self._stream()))
+    def prepare_params(self, trainable_only=False):
+        """Refresh the bf16 operand shadows; after an optimizer step only the trainable weights changed."""
+        p = self._p
+        if trainable_only:
+            p = L.VqaParams()
+            for f in self.params.trainable:
+                setattr(p, f, self.params.views[f].data_ptr())
+        L.check(self.lib.vqa_prepare_params(self.h, C.byref(p), self._stream()))
 
     def _stream(self):
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
@@ -299,7 +305,7 @@ class Engine:
         L.check(self.lib.vqa_adam_step(self.h, ps.flat.data_ptr(), ps.grad.data_ptr(), ps.adam_m.data_ptr(),
                                        ps.adam_v.data_ptr(), ps.n_train, lr, beta1, beta2, eps, clip_norm,
                                        self.adam_t, self.grad_norm.data_ptr(), self._stream()))
-        self.prepare_params()
+        self.prepare_params(trainable_only=True)
 
     def dropout_masks(self, seed, step, batch=None):
         Bn = self.batch_size if batch is None else batch
