@@ -18,6 +18,7 @@
 
 #include "internal.h"
 #include "philox.cuh"
+#include "ptx.cuh"
 
 namespace vqa {
 
@@ -66,6 +67,25 @@ __device__ __forceinline__ void store8_planes(bf16* hi, bf16* lo, long long off,
   if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<uint4*>(l);
 }
 
+// 1-D bulk async copy global -> shared (TMA), completion on an mbarrier; size % 16 == 0, 16-byte aligned
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   ptx::smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(ptx::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
+// the [K, D] pre-LN slab of one sample -> shared memory, in pieces of <= 32 KB (one thread issues)
+__device__ __forceinline__ void slab_to_smem(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  ptx::mbar_arrive_expect_tx(bar, bytes);
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    bulk_load(static_cast<uint8_t*>(smem_dst) + off, static_cast<const uint8_t*>(gsrc) + off, n, bar);
+  }
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -94,17 +114,29 @@ template <typename ZT>
 __device__ __forceinline__ void slab_stats(const ZT* zb, int nchunks, float* red /*[3*ATT_WARPS+2]*/,
                                            float& mean_out, float& rstd_out) {
   float n = 0.f, mean = 0.f, m2 = 0.f;
-  for (int c = threadIdx.x; c < nchunks; c += ATT_THREADS) {
-    float x[8];
-    load8(zb + static_cast<long long>(c) * 8, x);
-    float cm = 0.f;
+  // loads go out in batches of U before any arithmetic: the pass is latency-bound otherwise
+  constexpr int U = 6;
+  for (int c0 = threadIdx.x; c0 < nchunks; c0 += U * ATT_THREADS) {
+    float x[U][8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) cm += x[j];
-    cm *= 0.125f;
-    float c2 = 0.f;
+    for (int i = 0; i < U; ++i) {
+      const int c = c0 + i * ATT_THREADS;
+      if (c < nchunks) load8(zb + static_cast<long long>(c) * 8, x[i]);
+    }
 #pragma unroll
-    for (int j = 0; j < 8; ++j) c2 += (x[j] - cm) * (x[j] - cm);
-    chan_merge(n, mean, m2, 8.f, cm, c2);
+    for (int i = 0; i < U; ++i) {
+      const int c = c0 + i * ATT_THREADS;
+      if (c < nchunks) {
+        float cm = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cm += x[i][j];
+        cm *= 0.125f;
+        float c2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) c2 += (x[i][j] - cm) * (x[i][j] - cm);
+        chan_merge(n, mean, m2, 8.f, cm, c2);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -140,10 +172,12 @@ struct FwdArgs {
   float* att; float* pooled; bf16* pooled_hi; bf16* pooled_lo; float* ln_mean; float* ln_rstd;
 };
 
-template <typename ZT>
+// SLAB: the sample's [K, D] pre-LN slab is brought into shared memory by ONE bulk async copy and both passes
+// over it (statistics, scores) read shared memory; the feature slab is prefetched into L2 meanwhile.
+template <typename ZT, bool SLAB>
 __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(FwdArgs a, int K, int D, int Dv,
                                                                float keep, uint32_t thr) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   float* cA = sm;           // gamma_d * rstd
   float* cB = cA + D;       // beta_d - mean * rstd * gamma_d
   float* cC = cB + D;       // hq_d * w_d / keep
@@ -152,6 +186,24 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(FwdArgs a, int K,
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int CH = D >> 3;
   const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
+  if (SLAB) {
+    const int head = ((3 * D + K + 3 * ATT_WARPS + 2) * 4 + 15) & ~15;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm) + head);
+    ZT* zs = reinterpret_cast<ZT*>(bar + 2);
+    if (tid == 0) {
+      ptx::mbar_init(bar, 1);
+      ptx::fence_barrier_init();
+      slab_to_smem(zs, zb, static_cast<uint32_t>(K) * D * sizeof(ZT), bar);
+      // the raw features of this sample are streamed later by the pooling pass: start them towards L2 now
+      const uint8_t* vsrc = reinterpret_cast<const uint8_t*>(a.v_hi + static_cast<long long>(b) * K * Dv);
+      const uint32_t vbytes = static_cast<uint32_t>(K) * Dv * 2;
+      for (uint32_t off = 0; off < vbytes; off += 65536u)
+        bulk_prefetch_l2(vsrc + off, vbytes - off < 65536u ? vbytes - off : 65536u);
+    }
+    __syncthreads();
+    ptx::mbar_wait(bar, 0);
+    zb = zs;
+  }
 
   float mean, rstd;
   slab_stats<ZT>(zb, K * CH, red, mean, rstd);
@@ -173,16 +225,33 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(FwdArgs a, int K,
     const ZT* zr = zb + static_cast<long long>(k) * D;
     const unsigned long long g0 = (static_cast<unsigned long long>(b) * K + k) * CH;
     float acc = 0.f;
-    for (int c = lane; c < CH; c += 32) {
-      float x[8];
-      load8(zr + c * 8, x);
-      uint32_t bits = 0xFFu;
-      if (thr < 65536u) bits = philox_keep_bits(philox4x32_10(g0 + c, RNG_STREAM_ATT, a.seed, a.step), thr);
-      const int d0 = c * 8;
+    constexpr int U2 = 4;
+    for (int c0 = lane; c0 < CH; c0 += 32 * U2) {
+      float x[U2][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float y = fmaxf(fmaf(x[j], cA[d0 + j], cB[d0 + j]), 0.f);
-        acc += ((bits >> j) & 1u) ? y * cC[d0 + j] : 0.f;
+      for (int i = 0; i < U2; ++i) {
+        const int c = c0 + 32 * i;
+        if (c < CH) load8(zr + c * 8, x[i]);
+      }
+#pragma unroll
+      for (int i = 0; i < U2; ++i) {
+        const int c = c0 + 32 * i;
+        if (c < CH) {
+          uint32_t bits = 0xFFu;
+          if (thr < 65536u) bits = philox_keep_bits(philox4x32_10(g0 + c, RNG_STREAM_ATT, a.seed, a.step), thr);
+          const int d0 = c * 8;
+          const float4 a0 = *reinterpret_cast<const float4*>(cA + d0), a1 = *reinterpret_cast<const float4*>(cA + d0 + 4);
+          const float4 b0 = *reinterpret_cast<const float4*>(cB + d0), b1 = *reinterpret_cast<const float4*>(cB + d0 + 4);
+          const float4 w0 = *reinterpret_cast<const float4*>(cC + d0), w1 = *reinterpret_cast<const float4*>(cC + d0 + 4);
+          const float ca[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float cb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float cw[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float y = fmaxf(fmaf(x[i][j], ca[j], cb[j]), 0.f);
+            acc += ((bits >> j) & 1u) ? y * cw[j] : 0.f;
+          }
+        }
       }
     }
     acc = warp_sum(acc);
@@ -218,19 +287,17 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(FwdArgs a, int K,
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
     int k = 0;
-    for (; k + 4 <= nb; k += 4) {
-      float v0[8], v1[8], v2[8], v3[8];
-      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k) * Dv + c * 8, v0);
-      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k + 1) * Dv + c * 8, v1);
-      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k + 2) * Dv + c * 8, v2);
-      load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k + 3) * Dv + c * 8, v3);
-      const float a0 = sc[k], a1 = sc[k + 1], a2 = sc[k + 2], a3 = sc[k + 3];
+    constexpr int UP = 6;
+    for (; k + UP <= nb; k += UP) {
+      float v[UP][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        acc[j] = fmaf(a0, v0[j], acc[j]);
-        acc[j] = fmaf(a1, v1[j], acc[j]);
-        acc[j] = fmaf(a2, v2[j], acc[j]);
-        acc[j] = fmaf(a3, v3[j], acc[j]);
+      for (int i = 0; i < UP; ++i)
+        load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k + i) * Dv + c * 8, v[i]);
+#pragma unroll
+      for (int i = 0; i < UP; ++i) {
+        const float ai = sc[k + i];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(ai, v[i][j], acc[j]);
       }
     }
     for (; k < nb; ++k) {
@@ -268,10 +335,10 @@ struct BwdArgs {
 };
 
 // NCOL = column chunks (of 8) owned per thread: D <= 2048 -> 1, D <= 4096 -> 2
-template <typename ZT, int NCOL>
-__global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K, int D, int Dv,
-                                                               float keep, uint32_t thr) {
-  extern __shared__ float sm[];
+template <typename ZT, int NCOL, bool SLAB>
+__global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(BwdArgs a, int K, int D, int Dv,
+                                                                             float keep, uint32_t thr) {
+  extern __shared__ __align__(16) float sm[];
   const int CH = D >> 3;
   float* sdP = sm;                  // [Dv]
   float* ds = sdP + Dv;             // [K] (first da, then ds)
@@ -280,6 +347,20 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K,
   unsigned char* flags = reinterpret_cast<unsigned char*>(colacc + 3 * ATT_THREADS * 8 * NCOL);  // [K*CH]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
+  uint64_t* zbar = nullptr;
+  if (SLAB) {
+    // the slab copy is in flight while the feature rows are reduced against dP below
+    const size_t head = ((static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * 4 +
+                         static_cast<size_t>(K) * CH + 15) & ~static_cast<size_t>(15);
+    zbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm) + head);
+    ZT* zs = reinterpret_cast<ZT*>(zbar + 2);
+    if (tid == 0) {
+      ptx::mbar_init(zbar, 1);
+      ptx::fence_barrier_init();
+      slab_to_smem(zs, zb, static_cast<uint32_t>(K) * D * sizeof(ZT), zbar);
+    }
+    zb = zs;
+  }
   const float mean = a.ln_mean[b], rstd = a.ln_rstd[b];
   int nb = a.nbox[b];
   nb = nb < 0 ? 0 : (nb > K ? K : nb);
@@ -294,11 +375,26 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K,
   for (int k = warp; k < K; k += ATT_WARPS) {
     float acc = 0.f;
     if (k < nb) {
-      for (int c = lane; c < (Dv >> 3); c += 32) {
-        float v[8];
-        load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k) * Dv + c * 8, v);
+      constexpr int UB = 4;
+      for (int c0 = lane; c0 < (Dv >> 3); c0 += 32 * UB) {
+        float v[UB][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc = fmaf(v[j], sdP[c * 8 + j], acc);
+        for (int i = 0; i < UB; ++i) {
+          const int c = c0 + 32 * i;
+          if (c < (Dv >> 3)) load8_planes(a.v_hi, a.v_lo, vb + static_cast<long long>(k) * Dv + c * 8, v[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < UB; ++i) {
+          const int c = c0 + 32 * i;
+          if (c < (Dv >> 3)) {
+            const float4 p0 = *reinterpret_cast<const float4*>(sdP + c * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(sdP + c * 8 + 4);
+            acc = fmaf(v[i][0], p0.x, acc); acc = fmaf(v[i][1], p0.y, acc);
+            acc = fmaf(v[i][2], p0.z, acc); acc = fmaf(v[i][3], p0.w, acc);
+            acc = fmaf(v[i][4], p1.x, acc); acc = fmaf(v[i][5], p1.y, acc);
+            acc = fmaf(v[i][6], p1.z, acc); acc = fmaf(v[i][7], p1.w, acc);
+          }
+        }
       }
       acc = warp_sum(acc);
     }
@@ -321,6 +417,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K,
   }
   __syncthreads();
 
+  if (SLAB) ptx::mbar_wait(zbar, 0);  // (the mbarrier init was published by the __syncthreads above)
   // column-owner mapping: thread (tc, tr) owns column chunks tc (+ CW) and walks rows tr, tr+RP, ...
   const int CW = CH < ATT_THREADS ? CH : ATT_THREADS;
   const int RP = ATT_THREADS / CW;
@@ -345,31 +442,41 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K,
         g[j] = a.gamma[c * 8 + j];
         bt[j] = a.beta[c * 8 + j];
       }
-      for (int k = tr; k < nb; k += RP) {
-        float x[8];
-        load8(zb + static_cast<long long>(k) * D + c * 8, x);
-        uint32_t bits = 0xFFu;
-        if (thr < 65536u)
-          bits = philox_keep_bits(
-              philox4x32_10((static_cast<unsigned long long>(b) * K + k) * CH + c, RNG_STREAM_ATT,
-                            a.seed, a.step),
-              thr);
-        const float dsk = ds[k];
-        uint32_t fl = 0;
+      constexpr int UD = SLAB ? 2 : 3;
+      for (int k0 = tr; k0 < nb; k0 += RP * UD) {
+        float xb[UD][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = fmaf(x[j], rstd, -mr);
-          const float y = fmaf(xh, g[j], bt[j]);
-          const bool pos = y > 0.f;
-          const bool m = (bits >> j) & 1u;
-          accT[i][j] += (m && pos) ? dsk * y : 0.f;
-          if (m && pos) {
-            fl |= 1u << j;
-            accU[i][j] = fmaf(dsk, xh, accU[i][j]);
-            accV[i][j] += dsk;
-          }
+        for (int u = 0; u < UD; ++u) {
+          const int k = k0 + u * RP;
+          if (k < nb) load8(zb + static_cast<long long>(k) * D + c * 8, xb[u]);
         }
-        flags[k * CH + c] = static_cast<unsigned char>(fl);
+#pragma unroll
+        for (int u = 0; u < UD; ++u) {
+          const int k = k0 + u * RP;
+          if (k >= nb) break;
+          uint32_t bits = 0xFFu;
+          if (thr < 65536u)
+            bits = philox_keep_bits(
+                philox4x32_10((static_cast<unsigned long long>(b) * K + k) * CH + c, RNG_STREAM_ATT,
+                              a.seed, a.step),
+                thr);
+          const float dsk = ds[k];
+          uint32_t fl = 0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(xb[u][j], rstd, -mr);
+            const float y = fmaf(xh, g[j], bt[j]);
+            const bool pos = y > 0.f;
+            const bool m = (bits >> j) & 1u;
+            accT[i][j] += (m && pos) ? dsk * y : 0.f;
+            if (m && pos) {
+              fl |= 1u << j;
+              accU[i][j] = fmaf(dsk, xh, accU[i][j]);
+              accV[i][j] += dsk;
+            }
+          }
+          flags[k * CH + c] = static_cast<unsigned char>(fl);
+        }
       }
     }
   }
@@ -465,19 +572,30 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_bwd_kernel(BwdArgs a, int K,
     for (int i = 0; i < NCOL; ++i) {
       const int c = tc + i * CW;
       if (c >= CH) break;
-      for (int k = tr; k < K; k += RP) {
-        float x[8], dz[8];
-        load8(zb + static_cast<long long>(k) * D + c * 8, x);
-        const uint32_t fl = k < nb ? flags[k * CH + c] : 0u;
-        const float dsk = ds[k];
+      constexpr int UF = SLAB ? 2 : 3;
+      for (int k0 = tr; k0 < K; k0 += RP * UF) {
+        float xb[UF][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float xh = fmaf(x[j], rstd, -mr);
-          const float dxh = ((fl >> j) & 1u) ? dsk * G[i][j] : 0.f;
-          dz[j] = rstd * (dxh - m1 - xh * m2);
-          accB[i][j] += dz[j];
+        for (int u = 0; u < UF; ++u) {
+          const int k = k0 + u * RP;
+          if (k < K) load8(zb + static_cast<long long>(k) * D + c * 8, xb[u]);
         }
-        store8_planes(a.dz_hi, a.dz_lo, (static_cast<long long>(b) * K + k) * D + c * 8, dz);
+#pragma unroll
+        for (int u = 0; u < UF; ++u) {
+          const int k = k0 + u * RP;
+          if (k >= K) break;
+          float dz[8];
+          const uint32_t fl = k < nb ? flags[k * CH + c] : 0u;
+          const float dsk = ds[k];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float xh = fmaf(xb[u][j], rstd, -mr);
+            const float dxh = ((fl >> j) & 1u) ? dsk * G[i][j] : 0.f;
+            dz[j] = rstd * (dxh - m1 - xh * m2);
+            accB[i][j] += dz[j];
+          }
+          store8_planes(a.dz_hi, a.dz_lo, (static_cast<long long>(b) * K + k) * D + c * 8, dz);
+        }
       }
     }
   }
@@ -522,16 +640,22 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
   f.seed = a.seed; f.step = a.step; f.att = a.att; f.pooled = a.pooled;
   f.pooled_hi = static_cast<bf16*>(a.pooled_hi); f.pooled_lo = static_cast<bf16*>(a.pooled_lo);
   f.ln_mean = a.ln_mean; f.ln_rstd = a.ln_rstd;
-  const size_t smem = (3 * static_cast<size_t>(D) + K + 3 * ATT_WARPS + 2) * sizeof(float);
+  const size_t head = (3 * static_cast<size_t>(D) + K + 3 * ATT_WARPS + 2) * sizeof(float);
   const uint32_t thr = keep_threshold(keep);
+  const size_t slab = static_cast<size_t>(K) * D * (precision == VQA_PREC_FP32 ? 4 : 2);
+  const size_t smem_slab = ((head + 15) & ~static_cast<size_t>(15)) + 16 + slab;
+  // two CTAs per SM must still fit, and the slab copy needs 16-byte granularity
+  const bool use_slab = smem_slab <= 110 * 1024 && (slab & 15) == 0 && !a.v_lo;
+  auto launch = [&](auto kern, size_t smem) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    kern<<<a.batch, ATT_THREADS, smem, s>>>(f, K, D, Dv, keep, thr);
+  };
   if (precision == VQA_PREC_FP32) {
-    static bool set = false;
-    if (!set) { cudaFuncSetAttribute(attn_fwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
-    attn_fwd_kernel<float><<<a.batch, ATT_THREADS, smem, s>>>(f, K, D, Dv, keep, thr);
+    if (use_slab) launch(attn_fwd_kernel<float, true>, smem_slab);
+    else launch(attn_fwd_kernel<float, false>, head);
   } else {
-    static bool set = false;
-    if (!set) { cudaFuncSetAttribute(attn_fwd_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); set = true; }
-    attn_fwd_kernel<bf16><<<a.batch, ATT_THREADS, smem, s>>>(f, K, D, Dv, keep, thr);
+    if (use_slab) launch(attn_fwd_kernel<bf16, true>, smem_slab);
+    else launch(attn_fwd_kernel<bf16, false>, head);
   }
   VQA_LAUNCH_CHECK("attn_fwd");
   return VQA_OK;
@@ -540,17 +664,22 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
 template <typename ZT, int NCOL>
 static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv, float keep,
                               uint32_t thr, cudaStream_t s) {
-  const size_t smem = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float) +
+  const size_t head = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float) +
                       static_cast<size_t>(K) * (D >> 3);
-  static bool set = false;
-  if (!set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  const size_t slab = static_cast<size_t>(K) * D * sizeof(ZT);
+  const size_t smem_slab = ((head + 15) & ~static_cast<size_t>(15)) + 16 + slab;
+  const bool use_slab = smem_slab <= 112 * 1024 && (slab & 15) == 0;
+  if (head > 220 * 1024) return cudaErrorInvalidValue;
+  cudaError_t e;
+  if (use_slab) {
+    e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
-    set = true;
+    attn_bwd_kernel<ZT, NCOL, true><<<batch, ATT_THREADS, smem_slab, s>>>(g, K, D, Dv, keep, thr);
+  } else {
+    e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) return e;
+    attn_bwd_kernel<ZT, NCOL, false><<<batch, ATT_THREADS, head, s>>>(g, K, D, Dv, keep, thr);
   }
-  if (smem > 220 * 1024) return cudaErrorInvalidValue;
-  attn_bwd_kernel<ZT, NCOL><<<batch, ATT_THREADS, smem, s>>>(g, K, D, Dv, keep, thr);
   return cudaGetLastError();
 }
 

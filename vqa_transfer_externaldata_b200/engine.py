@@ -142,6 +142,43 @@ class ParamStore:
         return g
 
 
+class PendingScalars:
+    _pool = {}
+
+    def __init__(self, eng):
+        slots = PendingScalars._pool.setdefault(id(eng), [])
+        self.buf = slots.pop() if slots else torch.zeros(1 + len(L.REPORT_KEYS)).pin_memory()
+        self._slots = slots
+        self.buf[:1].copy_(eng.o_loss, non_blocking=True)
+        self.buf[1:].copy_(eng.o_report, non_blocking=True)
+        self.event = torch.cuda.Event()
+        self.event.record(torch.cuda.current_stream(eng.device))
+        self.nbytes = 4 * (1 + len(L.REPORT_KEYS))
+
+    def get(self):
+        self.event.synchronize()
+        vals = self.buf.tolist()
+        self._slots.append(self.buf)
+        return vals[0], dict(zip(L.REPORT_KEYS, vals[1:]))
+
+
+class BatchSet:
+    """One set of static batch buffers: pinned host staging + device (fixed addresses)."""
+
+    def __init__(self, cfg, dev):
+        self.d_image_idx = torch.zeros(cfg.B, dtype=torch.int64, device=dev)
+        self.d_q = torch.zeros(cfg.B * cfg.T, dtype=torch.int32, device=dev)
+        self.d_qlen = torch.zeros(cfg.B, dtype=torch.int32, device=dev)
+        self.d_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32, device=dev)
+        self.h_image_idx = torch.zeros(cfg.B, dtype=torch.int64).pin_memory()
+        self.h_q = torch.zeros(cfg.B * cfg.T, dtype=torch.int32).pin_memory()
+        self.h_qlen = torch.zeros(cfg.B, dtype=torch.int32).pin_memory()
+        self.h_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32).pin_memory()
+        self.batch_size, self.q_len_max = 0, cfg.T
+        self.ready = torch.cuda.Event()
+        self.source = None   # the host batch object this set was filled from (prefetch bookkeeping)
+
+
 class Engine:
     """Owns the C handle, its workspace, the parameter store, the feature bank and static batch buffers."""
 
@@ -164,16 +201,11 @@ class Engine:
         self._p = self.params.c_params()
         self._g = self.params.c_grads()
         dev = self.device
-        # static device-side batch (addresses stay fixed -> the whole step can be captured in a CUDA graph)
-        self.d_image_idx = torch.zeros(cfg.B, dtype=torch.int64, device=dev)
-        self.d_q = torch.zeros(cfg.B * cfg.T, dtype=torch.int32, device=dev)
-        self.d_qlen = torch.zeros(cfg.B, dtype=torch.int32, device=dev)
-        self.d_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32, device=dev)
-        # pinned host staging for the per-step H2D copies
-        self.h_image_idx = torch.zeros(cfg.B, dtype=torch.int64).pin_memory()
-        self.h_q = torch.zeros(cfg.B * cfg.T, dtype=torch.int32).pin_memory()
-        self.h_qlen = torch.zeros(cfg.B, dtype=torch.int32).pin_memory()
-        self.h_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32).pin_memory()
+        # two sets of static batch buffers (addresses stay fixed -> capturable): while a step computes on one
+        # set, the next batch is uploaded into the other on a copy stream (prefetch_batch)
+        self._sets = [BatchSet(cfg, dev), BatchSet(cfg, dev)]
+        self._cur = 0
+        self.copy_stream = torch.cuda.Stream(device=dev)
         # outputs
         self.o_loss = torch.zeros(1, device=dev)
         self.o_report = torch.zeros(len(L.REPORT_KEYS), device=dev)
@@ -193,8 +225,6 @@ class Engine:
         self._outs_min = L.VqaOutputs(loss=self.o_loss.data_ptr(), report=self.o_report.data_ptr())
         self.bank = None
         self.masks = None
-        self.batch_size = 0
-        self.q_len_max = cfg.T
         self.adam_t = 0
 
     def close(self):
@@ -248,37 +278,101 @@ class Engine:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     # ---- batch ----------------------------------------------------------------------------------
+    @property
+    def cur(self):
+        return self._sets[self._cur]
+
+    # the active set's buffers under their historical names
+    d_image_idx = property(lambda self: self.cur.d_image_idx)
+    d_q = property(lambda self: self.cur.d_q)
+    d_qlen = property(lambda self: self.cur.d_qlen)
+    d_target = property(lambda self: self.cur.d_target)
+    h_image_idx = property(lambda self: self.cur.h_image_idx)
+    h_q = property(lambda self: self.cur.h_q)
+    h_qlen = property(lambda self: self.cur.h_qlen)
+    h_target = property(lambda self: self.cur.h_target)
+
+    @property
+    def batch_size(self):
+        return self.cur.batch_size
+
+    @batch_size.setter
+    def batch_size(self, v):
+        self.cur.batch_size = v
+
+    @property
+    def q_len_max(self):
+        return self.cur.q_len_max
+
+    @q_len_max.setter
+    def q_len_max(self, v):
+        self.cur.q_len_max = v
+
+    def _fill(self, bs, batch):
+        """Host batch dict (keys of input_ops_vqa_tf_record_memft.py:47-59) -> device buffers of set `bs`,
+        asynchronously on the current stream. Values may be NumPy arrays (staged through pinned memory) or
+        pinned torch tensors of the right dtype (copied directly). Returns the h2d byte count."""
+        cfg = self.cfg
+        q = batch["q_intseq"]
+        Bn, T = int(q.shape[0]), int(q.shape[1])
+        if Bn > cfg.B or T > cfg.T:
+            raise ValueError(f"batch [{Bn}, T={T}] exceeds config (B={cfg.B}, T={cfg.T})")
+        if tuple(batch["answer_target"].shape) != (Bn, cfg.A):
+            raise ValueError(f"answer_target shape {tuple(batch['answer_target'].shape)} != ({Bn}, {cfg.A})")
+        items = (("image_idx", bs.h_image_idx, bs.d_image_idx, torch.int64, np.int64, Bn),
+                 ("q_intseq", bs.h_q, bs.d_q, torch.int32, np.int32, Bn * T),
+                 ("q_intseq_len", bs.h_qlen, bs.d_qlen, torch.int32, np.int32, Bn),
+                 ("answer_target", bs.h_target, bs.d_target, torch.float32, np.float32, Bn * cfg.A))
+        nbytes = 0
+        for key, hbuf, dbuf, tdt, ndt, n in items:
+            v = batch[key]
+            if isinstance(v, torch.Tensor) and v.dtype == tdt and v.is_pinned() and v.is_contiguous():
+                src = v.view(-1)
+            else:
+                hbuf[:n].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=ndt)).reshape(-1)))
+                src = hbuf[:n]
+            dbuf[:n].copy_(src, non_blocking=True)
+            nbytes += n * dbuf.element_size()
+        bs.batch_size, bs.q_len_max = Bn, T
+        return nbytes
+
     def stage_batch(self, batch):
-        """Host batch dict (keys of input_ops_vqa_tf_record_memft.py:47-59) -> pinned staging -> device.
-        Returns (h2d_bytes). Asynchronous on the current stream."""
-        idx = np.asarray(batch["image_idx"], dtype=np.int64)
-        q = np.asarray(batch["q_intseq"], dtype=np.int32)
-        ql = np.asarray(batch["q_intseq_len"], dtype=np.int32)
-        tg = np.asarray(batch["answer_target"], dtype=np.float32)
-        Bn, T = q.shape
-        if Bn > self.cfg.B or T > self.cfg.T:
-            raise ValueError(f"batch [{Bn}, T={T}] exceeds config (B={self.cfg.B}, T={self.cfg.T})")
-        if tg.shape != (Bn, self.cfg.A):
-            raise ValueError(f"answer_target shape {tg.shape} != ({Bn}, {self.cfg.A})")
-        self.h_image_idx[:Bn].copy_(torch.from_numpy(idx))
-        self.h_q[:Bn * T].copy_(torch.from_numpy(q.reshape(-1)))
-        self.h_qlen[:Bn].copy_(torch.from_numpy(ql))
-        self.h_target[:Bn * self.cfg.A].copy_(torch.from_numpy(tg.reshape(-1)))
-        return self.upload_staged(Bn, T)
+        """Upload `batch` into the active set on the current stream (or adopt it if prefetch_batch already
+        put this very object into the other set). Returns h2d bytes."""
+        other = self._sets[1 - self._cur]
+        if other.source is not None and other.source is batch:
+            other.source = None
+            self._cur = 1 - self._cur
+            torch.cuda.current_stream(self.device).wait_event(other.ready)
+            return other.nbytes
+        return self._fill(self.cur, batch)
+
+    def prefetch_batch(self, batch):
+        """Start uploading the NEXT batch into the inactive set on the copy stream; the following
+        stage_batch(batch) with the same object adopts it. The inactive set must not be in use: its last
+        reader (the step before the current one) has been enqueued on the compute stream before this call."""
+        other = self._sets[1 - self._cur]
+        self.copy_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.copy_stream):
+            other.nbytes = self._fill(other, batch)
+            other.ready.record(self.copy_stream)
+        other.source = batch
 
     def upload_staged(self, Bn, T):
         A = self.cfg.A
-        self.d_image_idx[:Bn].copy_(self.h_image_idx[:Bn], non_blocking=True)
-        self.d_q[:Bn * T].copy_(self.h_q[:Bn * T], non_blocking=True)
-        self.d_qlen[:Bn].copy_(self.h_qlen[:Bn], non_blocking=True)
-        self.d_target[:Bn * A].copy_(self.h_target[:Bn * A], non_blocking=True)
-        self.batch_size, self.q_len_max = Bn, T
+        bs = self.cur
+        bs.d_image_idx[:Bn].copy_(bs.h_image_idx[:Bn], non_blocking=True)
+        bs.d_q[:Bn * T].copy_(bs.h_q[:Bn * T], non_blocking=True)
+        bs.d_qlen[:Bn].copy_(bs.h_qlen[:Bn], non_blocking=True)
+        bs.d_target[:Bn * A].copy_(bs.h_target[:Bn * A], non_blocking=True)
+        bs.batch_size, bs.q_len_max = Bn, T
         return Bn * 8 + Bn * T * 4 + Bn * 4 + Bn * A * 4
 
     def _c_batch(self):
-        return L.VqaBatch(batch_size=self.batch_size, q_len_max=self.q_len_max,
-                          image_idx=self.d_image_idx.data_ptr(), q_intseq=self.d_q.data_ptr(),
-                          q_intseq_len=self.d_qlen.data_ptr(), answer_target=self.d_target.data_ptr())
+        bs = self.cur
+        return L.VqaBatch(batch_size=bs.batch_size, q_len_max=bs.q_len_max,
+                          image_idx=bs.d_image_idx.data_ptr(), q_intseq=bs.d_q.data_ptr(),
+                          q_intseq_len=bs.d_qlen.data_ptr(), answer_target=bs.d_target.data_ptr())
 
     # ---- the path -------------------------------------------------------------------------------
     def forward(self, seed=0, step=0, full_outputs=True):
@@ -329,6 +423,11 @@ class Engine:
         torch.cuda.current_stream(self.device).synchronize()
         vals = self.h_scalars.tolist()
         return vals[0], dict(zip(L.REPORT_KEYS, vals[1:]))
+
+    def read_scalars_async(self):
+        """Enqueue the D2H of loss + report into a fresh pinned slot and return a handle; handle.get() waits for
+        THAT copy only, so the host can run one step ahead of the device (asynchronous dispatch)."""
+        return PendingScalars(self)
 
     def outputs(self):
         Bn = self.batch_size

@@ -165,14 +165,23 @@ class Model(object):
         if self._dp is not None:
             self._dp.all_reduce_gradients(self.engine)
 
-    def train_step(self, batch=None, lr=1e-3, clip_norm=20.0, apply_optimizer=True):
+    def train_step(self, batch=None, lr=1e-3, clip_norm=20.0, apply_optimizer=True, next_batch=None, sync=True):
         """run_train_step of vqa/trainer.py:275-287: forward + backward (+ all-reduce) + clip + Adam.
-        Returns (loss, h2d_bytes, d2h_bytes); the loss read is the step's device->host copy."""
+        Returns (loss, h2d_bytes, d2h_bytes); the loss read is the step's device->host copy.
+        next_batch: host batch of the FOLLOWING step; its upload starts now on a copy stream and overlaps this
+        step's kernels (the reference's tf.data pipeline prefetches the same way).
+        sync=False: asynchronous dispatch -- `loss` is a handle whose .get() -> (loss, report) waits for this
+        step only, so the host can enqueue step i+1 while the device runs step i."""
         h2d = self.forward(batch, full_outputs=False)
+        if next_batch is not None:
+            self.engine.prefetch_batch(next_batch)
         self.backward()
         if apply_optimizer:
             self.engine.adam_step(lr=lr, clip_norm=clip_norm)
         self.global_step += 1
+        if not sync:
+            pending = self.engine.read_scalars_async()
+            return pending, h2d, pending.nbytes
         loss, report = self.engine.read_scalars()
         self.loss = loss
         self.losses["answer"] = loss
