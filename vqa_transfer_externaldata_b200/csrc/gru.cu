@@ -18,6 +18,9 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstdio>
+#include <cstdlib>
+
 #include "internal.h"
 #include "ptx.cuh"
 
@@ -156,7 +159,11 @@ __device__ __forceinline__ float stg_read(const float* stg, int row, int col) {
 //                   phase 2+2i: dh  = dG_t Wg_h^T + dh_part -> head of step t-1   (not run for t = 0)
 // Weights: the larger matrix of the pair stays resident in shared memory (forward: the gate columns, used by
 // kind 0; BPTT: the Wg rows, used by kind 1); the smaller one (32 rows) streams through the ring next to A.
-template <int MODE>
+// CL > 1: the CL CTAs of a cluster own adjacent unit slices of the SAME row tile, so they consume identical
+// activation tiles: each loads 1/CL of every tile and multicasts it to all (L2 reads of A drop CL-fold; the
+// kernel is bound by exactly that traffic). Stage hand-back is cluster-wide: every consumer's tcgen05.commit
+// arrives on the empty barrier of every CTA.
+template <int MODE, int CL>
 __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
     const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
     const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1, GruArgs g) {
@@ -189,7 +196,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
     ptx::prefetch_tensormap(&tm_w1);
     for (int s = 0; s < R_STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], CL);
     }
     ptx::mbar_init(tmem_full_bar, 1);
     ptx::mbar_init(w_bar, 1);
@@ -201,8 +208,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // peers' barriers exist before anything is multicast at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t crank = (CL > 1) ? ptx::cluster_ctarank() : 0;
+  constexpr uint16_t kMask = static_cast<uint16_t>((1u << CL) - 1);
 
   // phase p -> (has matmul, which operand / weight set, time step)
   auto phase_info = [&](int p, bool& mm, int& kind, int& t) {
@@ -253,7 +263,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
           }
           ptx::mbar_arrive_expect_tx(&full_bar[stage], streamed ? R_STAGE : R_A_TILE);
           if (streamed) ptx::tma_load_2d(st + R_A_TILE, tw, &full_bar[stage], kb * R_BK, wrow);
-          ptx::tma_load_2d(st, ta, &full_bar[stage], kb * R_BK, arow);
+          if (CL > 1)
+            ptx::tma_load_2d_multicast(st + crank * (R_A_TILE / CL), ta, &full_bar[stage], kb * R_BK,
+                                       arow + static_cast<int>(crank) * (R_BM / CL), kMask);
+          else
+            ptx::tma_load_2d(st, ta, &full_bar[stage], kb * R_BK, arow);
           if (++stage == R_STAGES) {
             stage = 0;
             phase_bit ^= 1;
@@ -291,7 +305,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
             const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 32, 16, 1024);
             ptx::umma_f16(d_tmem, da, db, idesc, (kb | kk) != 0);
           }
-          ptx::umma_commit(&empty_bar[stage]);
+          if (CL > 1) ptx::umma_commit_multicast(&empty_bar[stage], kMask);
+          else ptx::umma_commit(&empty_bar[stage]);
           if (++stage == R_STAGES) {
             stage = 0;
             phase_bit ^= 1;
@@ -549,6 +564,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CL > 1) ptx::cluster_sync_all();  // no CTA leaves while peers may still signal its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, R_TMEM_COLS);
@@ -601,16 +617,48 @@ bool encode_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
 
 unsigned long long* g_trace = nullptr;
 
-template <int MODE>
-VqaStatus launch_persistent(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0,
-                            const CUtensorMap& w1, GruArgs g, int num_sms, cudaStream_t s) {
-  auto kern = gru_persistent_kernel<MODE>;
-  const int smem = smem_bytes(g.L);
+constexpr int R_CL = 4;       // cluster size of the multicast variant
+// Measured on B200 (profiles/r01_gru_trace.md): multicasting the activation tiles inside 4-CTA clusters leaves the
+// per-phase main loop at 5.1 us -- the bound is the ~50 GB/s each SM can ingest, not the L2 read rate -- so the
+// cluster variant is opt-in (VQA_GRU_CLUSTER=1) and the plain variant is the default.
+bool g_cluster_off = getenv("VQA_GRU_CLUSTER") == nullptr;
+
+template <int MODE, int CL>
+cudaError_t launch_one(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
+                       GruArgs& a, dim3 grid, int smem, cudaStream_t s) {
+  auto kern = gru_persistent_kernel<MODE, CL>;
   static int smem_set = 0;
   if (smem_set < smem) {
-    VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
     smem_set = smem;
   }
+  void* args[] = {const_cast<CUtensorMap*>(&a0), const_cast<CUtensorMap*>(&a1), const_cast<CUtensorMap*>(&w0),
+                  const_cast<CUtensorMap*>(&w1), &a};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(R_THREADS);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  // cooperative: fails instead of deadlocking if the grid cannot be co-resident
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = CL;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = CL > 1 ? 2 : 1;
+  return cudaLaunchKernelExC(&cfg, reinterpret_cast<void*>(kern), args);
+}
+
+// a0 / a1: the two activation operands ([rows, inner] bf16, row pitch = inner); w0 / w1: weight tensor maps
+template <int MODE>
+VqaStatus launch_persistent(const void* a0_ptr, uint64_t a0_inner, uint64_t a0_rows, const void* a1_ptr,
+                            uint64_t a1_inner, uint64_t a1_rows, const CUtensorMap& w0, const CUtensorMap& w1,
+                            GruArgs g, int num_sms, cudaStream_t s) {
+  const int smem = smem_bytes(g.L);
   const int slices = g.L / R_JN;
   const int tiles_per_launch = num_sms / slices;  // co-resident row tiles
   const int Bn = g.row_end;
@@ -621,11 +669,27 @@ VqaStatus launch_persistent(const CUtensorMap& a0, const CUtensorMap& a1, const 
     a.row_end = Bn < row0 + tiles_per_launch * R_BM ? Bn : row0 + tiles_per_launch * R_BM;
     const int mt = (a.row_end - row0 + R_BM - 1) / R_BM;
     VQA_CUDA_CHECK(cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * mt, s));
-    void* args[] = {const_cast<CUtensorMap*>(&a0), const_cast<CUtensorMap*>(&a1), const_cast<CUtensorMap*>(&w0),
-                    const_cast<CUtensorMap*>(&w1), &a};
-    // cooperative launch: fails instead of deadlocking if the grid cannot be co-resident
-    VQA_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(kern), dim3(slices, mt), dim3(R_THREADS),
-                                               args, smem, s));
+    bool done = false;
+    if (!g_cluster_off && slices % R_CL == 0) {
+      CUtensorMap a0, a1;
+      if (!encode_bf16(&a0, a0_ptr, a0_inner, a0_rows, a0_inner, 64, R_BM / R_CL) ||
+          !encode_bf16(&a1, a1_ptr, a1_inner, a1_rows, a1_inner, 64, R_BM / R_CL))
+        return set_error(VQA_ERR_CUDA, "gru_persistent: cuTensorMapEncodeTiled failed");
+      cudaError_t e = launch_one<MODE, R_CL>(a0, a1, w0, w1, a, dim3(slices, mt), smem, s);
+      if (e == cudaSuccess) done = true;
+      else {
+        cudaGetLastError();  // the cluster variant cannot be scheduled on this device / partition
+        g_cluster_off = true;
+        if (getenv("VQA_VERBOSE")) fprintf(stderr, "[vqa] GRU cluster launch refused (%s): using the unicast variant\n", cudaGetErrorString(e));
+      }
+    }
+    if (!done) {
+      CUtensorMap a0, a1;
+      if (!encode_bf16(&a0, a0_ptr, a0_inner, a0_rows, a0_inner, 64, R_BM) ||
+          !encode_bf16(&a1, a1_ptr, a1_inner, a1_rows, a1_inner, 64, R_BM))
+        return set_error(VQA_ERR_CUDA, "gru_persistent: cuTensorMapEncodeTiled failed");
+      VQA_CUDA_CHECK((launch_one<MODE, 1>(a0, a1, w0, w1, a, dim3(slices, mt), smem, s)));
+    }
     count_launch();
   }
   return VQA_OK;
@@ -657,25 +721,22 @@ VqaStatus gru_pack_weights_launch(const bf16* wg_h, const bf16* wc_h, int L, bf1
 
 VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
-  CUtensorMap tm_h, tm_rh, tm_wg, tm_wc;
+  CUtensorMap tm_wg, tm_wc;
   const uint64_t prow = static_cast<uint64_t>(L / R_JN) * 96;
-  bool ok = encode_bf16(&tm_h, a.h_bf, L, static_cast<uint64_t>(T + 1) * B, L, 64, R_BM) &&
-            encode_bf16(&tm_rh, a.rh_bf, L, static_cast<uint64_t>(T) * B, L, 64, R_BM) &&
-            encode_bf16(&tm_wg, a.w_pack, L, prow, L, 64, 64) &&
+  bool ok = encode_bf16(&tm_wg, a.w_pack, L, prow, L, 64, 64) &&
             encode_bf16(&tm_wc, a.w_pack, L, prow, L, 64, 32);
   if (!ok) return set_error(VQA_ERR_CUDA, "gru_fwd_persistent: cuTensorMapEncodeTiled failed");
   GruArgs g{};
   g.B = B; g.row0 = 0; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
   g.xg = a.xg; g.xc = a.xc; g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
-  return launch_persistent<0>(tm_h, tm_rh, tm_wg, tm_wc, g, num_sms, s);
+  return launch_persistent<0>(a.h_bf, L, static_cast<uint64_t>(T + 1) * B, a.rh_bf, L, static_cast<uint64_t>(T) * B,
+                              tm_wg, tm_wc, g, num_sms, s);
 }
 
 VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
-  CUtensorMap tm_dc, tm_dg, tm_wc, tm_wg;
-  bool ok = encode_bf16(&tm_dc, a.dC_bf, L, static_cast<uint64_t>(T) * B, L, 64, R_BM) &&
-            encode_bf16(&tm_dg, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B, 2 * L, 64, R_BM) &&
-            // weights in TF layout [in, out]: row = input unit (the N of these products), contiguous = output
+  CUtensorMap tm_wc, tm_wg;
+  bool ok =  // weights in TF layout [in, out]: row = input unit (the N of these products), contiguous = output
             // column (their K): K-major B operands as they are
             encode_bf16(&tm_wc, a.wc_h, L, L, L, 64, 32) &&
             encode_bf16(&tm_wg, a.wg_h, 2 * L, L, 2 * L, 64, 32);
@@ -684,7 +745,8 @@ VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cuda
   g.B = B; g.row0 = 0; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
   g.h_f32 = const_cast<float*>(a.h_f32); g.r = const_cast<float*>(a.r); g.u = const_cast<float*>(a.u);
   g.c = const_cast<float*>(a.c); g.dq = a.dq; g.dG_bf = a.dG_bf; g.dC_bf = a.dC_bf; g.bias_part = a.bias_part;
-  return launch_persistent<1>(tm_dc, tm_dg, tm_wc, tm_wg, g, num_sms, s);
+  return launch_persistent<1>(a.dC_bf, L, static_cast<uint64_t>(T) * B, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B,
+                              tm_wc, tm_wg, g, num_sms, s);
 }
 
 }  // namespace vqa
