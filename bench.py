@@ -147,7 +147,7 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     return 0
 
 
@@ -334,9 +334,19 @@ def run_ours(args):
             "phase_ms": phase_ms,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        _emit(line)
     dp.close()
     return 0
+
+
+def _emit(line):
+    """The ONE JSON line goes to the real stdout; everything libraries print (NCCL's version banner, warnings)
+    was diverted to stderr at start-up."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
