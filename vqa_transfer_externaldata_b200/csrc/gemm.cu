@@ -107,14 +107,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int kb = 0; kb < num_kb; ++kb) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
         const int k0 = kb * BK;
+        if (ptx::elect_one()) {
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
 #pragma unroll
         for (int p = 0; p < Cfg::PLANES; ++p) {
           const CUtensorMap* ta = p ? &tm_a_lo : &tm_a_hi;
@@ -137,6 +138,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
             ptx::tma_load_2d(sb, tb, &full_bar[stage], k0, n0);
           }
         }
+        }
+        __syncwarp();
         if (++stage == Cfg::STAGES) {
           stage = 0;
           phase ^= 1;
@@ -144,8 +147,8 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc = ptx::make_idesc_bf16(BM, BN, A_MN, B_MN);
       // K-major: 8-row groups are 1024 B apart (SBO); a K=16 step advances 32 B inside the row.
       // MN-major: 8-k groups are 1024 B apart (SBO); 64-element MN chunks are 8192 B apart (LBO);
@@ -160,6 +163,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
         const uint32_t st = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
         const uint32_t sa_hi = st, sa_lo = st + Cfg::A_TILE;
         const uint32_t sb_hi = st + Cfg::PLANES * Cfg::A_TILE, sb_lo = sb_hi + Cfg::B_TILE;
+        if (ptx::elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint64_t da_hi = ptx::make_smem_desc_sw128(sa_hi + kk * A_STEP, A_LBO, 1024);
@@ -173,12 +177,15 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
           }
         }
         ptx::umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
+        }
+        __syncwarp();
         if (++stage == Cfg::STAGES) {
           stage = 0;
           phase ^= 1;
         }
       }
-      ptx::umma_commit(tmem_full_bar);  // accumulator complete
+      if (ptx::elect_one()) ptx::umma_commit(tmem_full_bar);  // accumulator complete
+      __syncwarp();
     }
   } else {
     // ===================== epilogue (warps 2..5) =====================

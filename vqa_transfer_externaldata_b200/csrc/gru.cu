@@ -230,15 +230,18 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
   };
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (warp-uniform loop, one elected lane issues) =====================
+    {
       // resident weights, once
-      ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(wres_bytes(L)));
-      if (MODE == 0) {
-        for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(wres + kb * 8192, &tm_w0, w_bar, kb * R_BK, slice * 96);
-      } else {
-        for (int kb = 0; kb < 2 * KB; ++kb) ptx::tma_load_2d(wres + kb * 4096, &tm_w1, w_bar, kb * R_BK, j0);
+      if (lane == 0) {
+        ptx::mbar_arrive_expect_tx(w_bar, static_cast<uint32_t>(wres_bytes(L)));
+        if (MODE == 0) {
+          for (int kb = 0; kb < KB; ++kb) ptx::tma_load_2d(wres + kb * 8192, &tm_w0, w_bar, kb * R_BK, slice * 96);
+        } else {
+          for (int kb = 0; kb < 2 * KB; ++kb) ptx::tma_load_2d(wres + kb * 4096, &tm_w1, w_bar, kb * R_BK, j0);
+        }
       }
+      __syncwarp();
       int stage = 0;
       uint32_t phase_bit = 0;
       for (int p = 0; p < num_phases; ++p) {
@@ -259,15 +262,19 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
             // tile); the ring itself doubles as their transpose buffer, so nothing may land in it earlier
             wait_counter(counter, static_cast<unsigned int>(p) * nslices);
             fence_proxy_async_all();
-            GRU_TRACE(p, 0);
+            if (lane == 0) GRU_TRACE(p, 0);
+            __syncwarp();
           }
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], streamed ? R_STAGE : R_A_TILE);
-          if (streamed) ptx::tma_load_2d(st + R_A_TILE, tw, &full_bar[stage], kb * R_BK, wrow);
-          if (CL > 1)
-            ptx::tma_load_2d_multicast(st + crank * (R_A_TILE / CL), ta, &full_bar[stage], kb * R_BK,
-                                       arow + static_cast<int>(crank) * (R_BM / CL), kMask);
-          else
-            ptx::tma_load_2d(st, ta, &full_bar[stage], kb * R_BK, arow);
+          if (ptx::elect_one()) {
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], streamed ? R_STAGE : R_A_TILE);
+            if (streamed) ptx::tma_load_2d(st + R_A_TILE, tw, &full_bar[stage], kb * R_BK, wrow);
+            if (CL > 1)
+              ptx::tma_load_2d_multicast(st + crank * (R_A_TILE / CL), ta, &full_bar[stage], kb * R_BK,
+                                         arow + static_cast<int>(crank) * (R_BM / CL), kMask);
+            else
+              ptx::tma_load_2d(st, ta, &full_bar[stage], kb * R_BK, arow);
+          }
+          __syncwarp();
           if (++stage == R_STAGES) {
             stage = 0;
             phase_bit ^= 1;
@@ -276,8 +283,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (warp-uniform loop, one elected lane issues) =====================
+    {
       constexpr uint32_t idesc64 = ptx::make_idesc_bf16(R_BM, 64, false, false);
       constexpr uint32_t idesc32 = ptx::make_idesc_bf16(R_BM, 32, false, false);
       ptx::mbar_wait(w_bar, 0);
@@ -296,23 +303,27 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
         for (int kb = 0; kb < nkb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase_bit);
           ptx::tc_fence_after();
-          if (kb == 0) GRU_TRACE(p, 1);
+          if (kb == 0 && lane == 0) GRU_TRACE(p, 1);
           const uint32_t sa = ptx::smem_u32(ring + stage * R_STAGE);
           const uint32_t sb = streamed ? sa + R_A_TILE : ptx::smem_u32(wres) + kb * wtile;
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int kk = 0; kk < R_BK / 16; ++kk) {
-            const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, 1024);
-            const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 32, 16, 1024);
-            ptx::umma_f16(d_tmem, da, db, idesc, (kb | kk) != 0);
+            for (int kk = 0; kk < R_BK / 16; ++kk) {
+              const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+              const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 32, 16, 1024);
+              ptx::umma_f16(d_tmem, da, db, idesc, (kb | kk) != 0);
+            }
+            if (CL > 1) ptx::umma_commit_multicast(&empty_bar[stage], kMask);
+            else ptx::umma_commit(&empty_bar[stage]);
           }
-          if (CL > 1) ptx::umma_commit_multicast(&empty_bar[stage], kMask);
-          else ptx::umma_commit(&empty_bar[stage]);
+          __syncwarp();
           if (++stage == R_STAGES) {
             stage = 0;
             phase_bit ^= 1;
           }
         }
-        ptx::umma_commit(tmem_full_bar);
+        if (ptx::elect_one()) ptx::umma_commit(tmem_full_bar);
+        __syncwarp();
         // the accumulator is overwritten only after the next counter wait, which this CTA's own epilogue
         // reaches after draining TMEM: no tmem_empty barrier needed
       }

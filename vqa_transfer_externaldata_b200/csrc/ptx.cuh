@@ -64,6 +64,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane of a CONVERGED warp is elected. Role loops run warp-uniform (every lane waits on the barrier) and only
+// the issue itself sits under this predicate: the compiler then keeps descriptors and addresses in uniform
+// registers, instead of wrapping every UTCHMMA / UTMALDG in a vector-to-uniform broadcast loop as it must under a
+// divergent `lane == 0` branch (measured: ~200 cycles per issued MMA there).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ----------------------------------------------------------------------------------------------
 // TMA
 // ----------------------------------------------------------------------------------------------
