@@ -270,7 +270,8 @@ typedef struct VqaGemmDesc {
   const float* addend; int64_t ld_addend;
   float* out_f32; int64_t ld_f32;           /* optional fp32 output                           */
   void* out_hi; void* out_lo; int64_t ld_bf; /* optional bf16 output planes (lo = residual)    */
-  int32_t block_n;                          /* 0 = auto; else 64 / 128 / 256                  */
+  int32_t block_n;                          /* 0 = auto; 64 / 128 / 256 = single-CTA tile width;
+                                             * -128 / -256 = force the CTA-pair kernel (256 x |block_n| tiles, bf16 only) */
 } VqaGemmDesc;
 VQA_API VqaStatus vqa_gemm(VqaHandle h, const VqaGemmDesc* d, void* stream);
 

@@ -23,8 +23,15 @@ def handle():
                       variant=0, precision=0, keep_att=0.8, keep_joint=0.5)
     h = C.c_void_p()
     L.check(lib.vqa_create(C.byref(cfg), C.byref(h)))
+    # a workspace gives the CTA-pair kernel its split-K hand-over semaphores
+    nbytes = C.c_uint64()
+    L.check(lib.vqa_workspace_bytes(h, C.byref(nbytes)))
+    ws = torch.empty(nbytes.value + 256, dtype=torch.uint8, device="cuda")
+    base = (ws.data_ptr() + 255) // 256 * 256
+    L.check(lib.vqa_set_workspace(h, C.c_void_p(base), C.c_uint64(nbytes.value)))
     yield lib, h
     lib.vqa_destroy(h)
+    del ws
 
 
 def _planes(x, split):
@@ -33,7 +40,7 @@ def _planes(x, split):
     return hi, lo
 
 
-def _run(lib, h, M, N, K, a_mn, b_mn, split, block_n=0, bias=False, addend=False, seed=0):
+def _run(lib, h, M, N, K, a_mn, b_mn, split, block_n=0, bias=False, addend=False, seed=0, want_bf=True):
     g = torch.Generator(device="cuda").manual_seed(seed)
     A = torch.randn(M, K, device="cuda", generator=g)
     B = torch.randn(N, K, device="cuda", generator=g)
@@ -59,7 +66,7 @@ def _run(lib, h, M, N, K, a_mn, b_mn, split, block_n=0, bias=False, addend=False
                       lda=lda, ldb=ldb, a_mn_major=int(a_mn), b_mn_major=int(b_mn), M=M, N=N, K=K,
                       bias=bias_t.data_ptr() if bias else None,
                       addend=add_t.data_ptr() if addend else None, ld_addend=N,
-                      out_f32=out.data_ptr(), ld_f32=N, out_hi=out_hi.data_ptr(),
+                      out_f32=out.data_ptr(), ld_f32=N, out_hi=out_hi.data_ptr() if want_bf else None,
                       out_lo=out_lo.data_ptr() if split else None, ld_bf=N, block_n=block_n)
     L.check(lib.vqa_gemm(h, C.byref(d), None))
     torch.cuda.synchronize()
@@ -75,7 +82,7 @@ def _run(lib, h, M, N, K, a_mn, b_mn, split, block_n=0, bias=False, addend=False
     err = (out.double() - ref).abs().max().item() / scale
     # bf16 output planes reproduce the fp32 output
     rec = out_hi.double() + (out_lo.double() if split else 0)
-    err_planes = (rec - out.double()).abs().max().item() / scale
+    err_planes = (rec - out.double()).abs().max().item() / scale if want_bf else 0.0
     return err, err_planes
 
 
@@ -109,6 +116,43 @@ def test_gemm_split_fp32(handle, shape, a_mn, b_mn):
     err, err_p = _run(lib, h, M, N, K, a_mn, b_mn, split=True, bias=True)
     assert err < 5e-5, (shape, a_mn, b_mn, err)
     assert err_p < 5e-5
+
+
+# CTA-pair kernel (csrc/gemm_pair.cu): 256 x |block_n| tiles, persistent; row / column / k tails, all operand
+# layouts, bias + addend, bf16 output
+@pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
+@pytest.mark.parametrize("shape", [(256, 256, 256), (512, 1024, 1024), (600, 1000, 520), (300, 200, 300),
+                                   (130, 3000, 520), (4608, 512, 320)])
+@pytest.mark.parametrize("block_n", [-256, -128])
+def test_gemm_pair_layouts(handle, shape, a_mn, b_mn, block_n):
+    lib, h = handle
+    M, N, K = shape
+    err, err_p = _run(lib, h, M, N, K, a_mn, b_mn, split=False, block_n=block_n, bias=True, addend=True)
+    assert err < 2e-5, (shape, a_mn, b_mn, block_n, err)
+    assert err_p < 4e-3
+
+
+# split-K with the fixed-order hand-over (fp32 output only): few tiles, long K -- the weight-gradient shapes
+@pytest.mark.parametrize("a_mn,b_mn", [(True, True), (False, False)])
+@pytest.mark.parametrize("shape", [(1024, 512, 4096), (300, 2048, 1792), (512, 3000, 2048), (2048, 1024, 4608)])
+def test_gemm_pair_split_k(handle, shape, a_mn, b_mn):
+    lib, h = handle
+    M, N, K = shape
+    err, _ = _run(lib, h, M, N, K, a_mn, b_mn, split=False, block_n=-256, bias=True, addend=True, want_bf=False)
+    assert err < 2e-5, (shape, a_mn, b_mn, err)
+    # the reduction order is fixed: two runs give the same bits
+    outs = []
+    for _ in range(2):
+        g = torch.Generator(device="cuda").manual_seed(5)
+        A = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+        B = torch.randn(N, K, device="cuda", generator=g).to(torch.bfloat16)
+        out = torch.empty(M, N, device="cuda")
+        d = L.VqaGemmDesc(a_hi=A.data_ptr(), b_hi=B.data_ptr(), lda=K, ldb=K, M=M, N=N, K=K,
+                          out_f32=out.data_ptr(), ld_f32=N, block_n=-256)
+        L.check(lib.vqa_gemm(h, C.byref(d), None))
+        torch.cuda.synchronize()
+        outs.append(out.clone())
+    assert torch.equal(outs[0], outs[1])
 
 
 def test_gemm_rejects_bad_pitch(handle):

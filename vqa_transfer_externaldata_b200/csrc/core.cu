@@ -143,6 +143,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   if (A > maxc) maxc = A;
   if (J > maxc) maxc = J;
   if (Dv > maxc) maxc = Dv;
+  b.gemm_sem = a.take<unsigned int>(VqaHandle_t::kGemmSemRegions * VqaHandle_t::kGemmSemElems);
   b.gru_counter = a.take<unsigned int>(64);
   b.gru_pack = a.take<bf16>(gru_pack_elems(static_cast<int>(L)));
   b.gru_bias_part = a.take<float>(gru_bias_part_floats(static_cast<int>(B), static_cast<int>(L)));
@@ -254,6 +255,12 @@ VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes) 
   h->ws = dev_ptr;
   h->ws_bytes = bytes;
   plan_workspace(h, static_cast<uint8_t*>(dev_ptr));
+  VQA_CUDA_CHECK(cudaMemset(h->buf.gemm_sem, 0,
+                            sizeof(unsigned int) * VqaHandle_t::kGemmSemRegions * VqaHandle_t::kGemmSemElems));
+  h->gemm_ctx.sem = h->buf.gemm_sem;
+  h->gemm_ctx.regions = VqaHandle_t::kGemmSemRegions;
+  h->gemm_ctx.region_elems = VqaHandle_t::kGemmSemElems;
+  h->gemm_ctx.next_region = 0;
   h->params_ready = false;
   h->fwd_valid = false;
   return VQA_OK;
@@ -261,7 +268,7 @@ VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes) 
 
 VQA_API VqaStatus vqa_gemm(VqaHandle h, const VqaGemmDesc* d, void* stream) {
   if (!h || !d) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: null argument");
-  return gemm_launch(*d, h->num_sms, static_cast<cudaStream_t>(stream));
+  return gemm_launch(*d, h->num_sms, static_cast<cudaStream_t>(stream), h->ws ? &h->gemm_ctx : nullptr);
 }
 
 VQA_API VqaStatus vqa_split_bf16(VqaHandle h, const float* src, int64_t rows, int64_t cols, int64_t ld,

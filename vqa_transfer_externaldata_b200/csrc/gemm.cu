@@ -312,17 +312,20 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// 2-D bf16 tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch in elements
-bool make_tmap_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t outer,
-                    uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
+// 2-D tensor map: inner (contiguous) extent `inner`, outer extent `outer`, row pitch in elements
+// kind: 0 = bf16 / 128-byte swizzle (MMA operands), 1 = fp32 / 128-byte swizzle, 2 = bf16 / no swizzle (stores)
+bool make_tmap(CUtensorMap* tm, const void* base, int kind, uint64_t inner, uint64_t outer,
+               uint64_t pitch_elems, uint32_t box_inner, uint32_t box_outer) {
   EncodeTiledFn fn = get_encode_fn();
   if (!fn) return false;
+  const uint64_t esz = kind == 1 ? 4 : 2;
   cuuint64_t dims[2] = {inner, outer};
-  cuuint64_t strides[1] = {pitch_elems * 2};
+  cuuint64_t strides[1] = {pitch_elems * esz};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
-                  box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = fn(tm, kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                  const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  kind == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
@@ -331,9 +334,10 @@ struct TmapKey {
   const void* base;
   uint64_t inner, outer, pitch;
   uint32_t bi, bo;
+  int kind;
   bool operator==(const TmapKey& o) const {
     return base == o.base && inner == o.inner && outer == o.outer && pitch == o.pitch &&
-           bi == o.bi && bo == o.bo;
+           bi == o.bi && bo == o.bo && kind == o.kind;
   }
 };
 struct TmapKeyHash {
@@ -343,16 +347,19 @@ struct TmapKeyHash {
     h = h * 1000003u ^ k.outer;
     h = h * 1000003u ^ k.pitch;
     h = h * 1000003u ^ (static_cast<size_t>(k.bi) << 16 | k.bo);
+    h = h * 1000003u ^ static_cast<size_t>(k.kind);
     return h;
   }
 };
 
-// descriptors are pure functions of (pointer, shape, box): cache them (encode costs ~1 us each)
-bool cached_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
-                 uint32_t bi, uint32_t bo) {
+}  // namespace
+
+// descriptors are pure functions of (pointer, shape, box, kind): cache them (encode costs ~1 us each)
+bool cached_tmap_kind(CUtensorMap* out, const void* base, int kind, uint64_t inner, uint64_t outer, uint64_t pitch,
+                      uint32_t bi, uint32_t bo) {
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
   static std::mutex mu;
-  TmapKey key{base, inner, outer, pitch, bi, bo};
+  TmapKey key{base, inner, outer, pitch, bi, bo, kind};
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) {
@@ -360,12 +367,18 @@ bool cached_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ou
     return true;
   }
   CUtensorMap tm;
-  if (!make_tmap_bf16(&tm, base, inner, outer, pitch, bi, bo)) return false;
+  if (!make_tmap(&tm, base, kind, inner, outer, pitch, bi, bo)) return false;
   if (cache.size() > 4096) cache.clear();
   cache.emplace(key, tm);
   *out = tm;
   return true;
 }
+bool cached_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
+                 uint32_t bi, uint32_t bo) {
+  return cached_tmap_kind(out, base, 0, inner, outer, pitch, bi, bo);
+}
+
+namespace {
 
 template <int BN, int SPLIT, bool A_MN, bool B_MN>
 cudaError_t launch_one(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
@@ -409,7 +422,7 @@ int pick_block_n(int M, int N, int num_sms) {
   return 64;
 }
 
-VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream) {
+VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx) {
   if (!d.a_hi || !d.b_hi) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: null operand");
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return set_error(VQA_ERR_BAD_SHAPE, "vqa_gemm: empty problem");
   if ((d.N & 3) || (d.lda & 7) || (d.ldb & 7))
@@ -419,6 +432,11 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream) {
   const bool split = (d.a_lo != nullptr) || (d.b_lo != nullptr);
   if (split && (!d.a_lo || !d.b_lo))
     return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: split precision needs both lo planes");
+  if (d.block_n <= 0) {
+    int pbn = 0, psplits = 1;
+    if (gemm_pair_plan(d, num_sms, ctx, &pbn, &psplits)) return gemm_pair_launch(d, num_sms, pbn, psplits, ctx, stream);
+    if (d.block_n < 0) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: the CTA-pair kernel takes one bf16 plane per operand and block_n -128 / -256");
+  }
   int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, num_sms);
   if (split && bn == 256) bn = 128;
   if (bn != 64 && bn != 128 && bn != 256) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: block_n");

@@ -66,6 +66,7 @@ struct Buffers {
   float* dG_f32; Planes dG;  // [T*B, 2L]
   float* dE;       // [T*B, Wpad]
   float* ln_part_g; float* ln_part_b;  // [B, max(D,L,J)] LayerNorm gamma/beta partials
+  unsigned int* gemm_sem;     // split-K hand-over semaphores of the pair GEMM (kGemmSemRegions x kGemmSemElems)
   unsigned int* gru_counter;  // per-row-tile phase counters of the persistent GRU kernels
   bf16* gru_pack;             // [L/32][96][L] packed weight slices of the forward recurrent kernel
   float* gru_bias_part;       // [ceil(B/128)+1, 3L] partial bias gradients of the BPTT kernel
@@ -86,6 +87,8 @@ struct VqaHandle_t {
   uint64_t ws_bytes;
   uint64_t ws_needed;
   vqa::Buffers buf;
+  vqa::GemmCtx gemm_ctx;
+  static constexpr int kGemmSemRegions = 64, kGemmSemElems = 1024;
   bool params_ready;
   // state of the last forward (what backward differentiates)
   bool fwd_valid;

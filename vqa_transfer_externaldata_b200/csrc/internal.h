@@ -5,6 +5,8 @@
 
 #include <cstdint>
 
+struct CUtensorMap_st;
+
 #include "../../include/vqa_answer.h"
 
 namespace vqa {
@@ -42,8 +44,24 @@ struct Planes {
   bf16* lo = nullptr;
 };
 
-// ---- gemm.cu ----
-VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream);
+// ---- gemm.cu / gemm_pair.cu ----
+// split-K hand-over semaphores of the pair kernel: a ring of regions inside the workspace (zeroed when the
+// workspace is attached; every launch leaves its region zero again), one region per in-flight launch
+struct GemmCtx {
+  unsigned int* sem = nullptr;
+  int regions = 0;
+  int region_elems = 0;
+  int next_region = 0;
+};
+VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx = nullptr);
+bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int* bn_out, int* splits_out);
+VqaStatus gemm_pair_launch(const VqaGemmDesc& d, int num_sms, int bn, int splits, GemmCtx* ctx, cudaStream_t stream);
+// cached cuTensorMapEncodeTiled: 2-D bf16, 128-byte swizzle, inner extent `inner` (contiguous), row pitch in elements
+bool cached_tmap(CUtensorMap_st* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
+                 uint32_t box_inner, uint32_t box_outer);
+// kind: 0 = bf16 / 128-byte swizzle (operands), 1 = fp32 / 128-byte swizzle, 2 = bf16 / no swizzle (TMA stores)
+bool cached_tmap_kind(CUtensorMap_st* out, const void* base, int kind, uint64_t inner, uint64_t outer,
+                      uint64_t pitch, uint32_t box_inner, uint32_t box_outer);
 
 // ---- elementwise.cu ----
 VqaStatus split_bf16_launch(const float* src, long long rows, long long cols, long long ld, bf16* hi,

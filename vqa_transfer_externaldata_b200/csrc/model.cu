@@ -44,7 +44,7 @@ struct GemmB {  // builder with the conventions of VqaGemmDesc
     d.ld_bf = ld;
     return *this;
   }
-  VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s); }
+  VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s, &h->gemm_ctx); }
 };
 
 VqaStatus check_ready(VqaHandle h, const char* who) {
