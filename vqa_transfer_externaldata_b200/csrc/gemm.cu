@@ -422,7 +422,7 @@ int pick_block_n(int M, int N, int num_sms) {
   return 64;
 }
 
-VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx) {
+VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx, int narrow) {
   if (!d.a_hi || !d.b_hi) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: null operand");
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return set_error(VQA_ERR_BAD_SHAPE, "vqa_gemm: empty problem");
   if ((d.N & 3) || (d.lda & 7) || (d.ldb & 7))
@@ -434,7 +434,7 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, Ge
     return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: split precision needs both lo planes");
   if (d.block_n <= 0) {
     int pbn = 0, psplits = 1;
-    if (gemm_pair_plan(d, num_sms, ctx, &pbn, &psplits)) return gemm_pair_launch(d, num_sms, pbn, psplits, ctx, stream);
+    if (gemm_pair_plan(d, num_sms, ctx, narrow, &pbn, &psplits)) return gemm_pair_launch(d, num_sms, pbn, psplits, ctx, stream);
     if (d.block_n < 0) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: the CTA-pair kernel takes one bf16 plane per operand and block_n -128 / -256");
   }
   int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, num_sms);

@@ -375,7 +375,7 @@ cudaError_t launch_pair_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const
 
 // Is the pair kernel the better choice for this problem, and with which tile width / split count?
 // (single bf16 plane only: the hi + lo split-precision path stays on the single-CTA kernel)
-bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int* bn_out, int* splits_out) {
+bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int narrow, int* bn_out, int* splits_out) {
   static const int mode = getenv("VQA_GEMM_PAIR") ? atoi(getenv("VQA_GEMM_PAIR")) : 1;
   const bool forced = d.block_n < 0;   // block_n = -128 / -256: the caller insists on the pair kernel
   if (!forced && (mode == 0 || d.block_n != 0)) return false;
@@ -384,20 +384,22 @@ bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int* 
   if (d.out_hi && ((d.ld_bf & 7) || (reinterpret_cast<uintptr_t>(d.out_hi) & 15))) return false;
   if (d.out_f32 && (reinterpret_cast<uintptr_t>(d.out_f32) & 15)) return false;
   if (forced && d.block_n != -128 && d.block_n != -256) return false;
-  // M <= 512 (the heads): 128 x 64 single-CTA tiles put more SMs to work than two rows of pair tiles (measured)
-  if (!forced && (d.M < 1024 || d.N < 128 || d.K < 256) && !(mode == 2 && d.M >= 256)) return false;
+  // M <= 512 with a short K (the heads): 128 x 64 single-CTA tiles put more SMs to work than two rows of pair
+  // tiles (measured); a long K (weight gradients) is split instead
+  if (!forced && mode == 1 && !(d.M >= 1024 || (d.M >= 256 && d.K >= 4096))) return false;
+  if (!forced && (d.M < 256 || d.N < 128 || d.K < 256)) return false;
   const int pairs = num_sms / 2;
   const int bn = forced ? -d.block_n : (d.N >= 256 ? 256 : 128);
   const long long tiles = static_cast<long long>((d.M + 255) / 256) * ((d.N + bn - 1) / bn);
   const int num_kb = (d.K + P_BK - 1) / P_BK;
   int splits = 1;
-  if (!d.out_hi && d.out_f32 && ctx && ctx->sem && tiles < pairs && tiles <= ctx->region_elems) {
+  if (!narrow && !d.out_hi && d.out_f32 && ctx && ctx->sem && tiles < pairs && tiles <= ctx->region_elems) {
     splits = static_cast<int>(pairs / tiles);
     if (splits > 4) splits = 4;
     while (splits > 1 && num_kb / splits < 8) --splits;   // keep >= 8 k-blocks per item
   }
   // M = 512 heads with a short K: the 128 x 64 single-CTA tiles start sooner than 2 x 256-row pair tiles fill
-  if (!forced && mode == 1 && tiles * splits < pairs / 2) return false;
+  if (!forced && !narrow && mode == 1 && tiles * splits < pairs / 2) return false;
   *bn_out = bn;
   *splits_out = splits;
   return true;

@@ -97,7 +97,7 @@ struct VqaHandle_t {
   VqaAnswerMasks last_masks;
   // auxiliary streams: independent branches of the graph (x-projections vs v-projection, the weight-gradient
   // GEMMs) are forked off the caller's stream and joined back with events -- capturable in a CUDA graph
-  static constexpr int kAux = 3;
+  static constexpr int kAux = 4;
   cudaStream_t aux[kAux];
   cudaEvent_t ev_fork[kAux], ev_join[kAux];
   bool aux_created;

@@ -53,8 +53,10 @@ struct GemmCtx {
   int region_elems = 0;
   int next_region = 0;
 };
-VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx = nullptr);
-bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int* bn_out, int* splits_out);
+// narrow = 1: one pair per output tile and no split-K, for GEMMs that run NEXT TO others on forked streams (the
+// GRU weight gradients): together they fill the SMs, and no reduction chain is needed
+VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx = nullptr, int narrow = 0);
+bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int narrow, int* bn_out, int* splits_out);
 VqaStatus gemm_pair_launch(const VqaGemmDesc& d, int num_sms, int bn, int splits, GemmCtx* ctx, cudaStream_t stream);
 // cached cuTensorMapEncodeTiled: 2-D bf16, 128-byte swizzle, inner extent `inner` (contiguous), row pitch in elements
 bool cached_tmap(CUtensorMap_st* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,

@@ -44,7 +44,9 @@ struct GemmB {  // builder with the conventions of VqaGemmDesc
     d.ld_bf = ld;
     return *this;
   }
-  VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s, &h->gemm_ctx); }
+  int narrow_ = 0;
+  GemmB& narrow() { narrow_ = 1; return *this; }
+  VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s, &h->gemm_ctx, narrow_); }
 };
 
 VqaStatus check_ready(VqaHandle h, const char* who) {
@@ -429,28 +431,34 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     const int TB = T * Bn;
     float* scratch1 = b.scratch + b.scratch_floats;       // per-stream column-sum scratch
     float* scratch2 = b.scratch + 2 * b.scratch_floats;
-    auto gates_wgrad = [&](cudaStream_t st, float* scr) -> VqaStatus {
-      if (g->gru_gates_w) {
+    // the four GRU weight gradients: x-rows (K = T*B, M = W) and h-rows (M = L) of the gate and candidate kernels.
+    // Each runs "narrow" (one CTA pair per output tile, no split-K): 32 + 16 + 16 + 8 pairs fit the machine side by
+    // side, so on forked streams they overlap instead of queueing four split-K reduction chains
+    auto gates_h_wgrad = [&](cudaStream_t st, float* scr) -> VqaStatus {
+      if (g->gru_gates_w)
         VQA_TRY(GemmB(L, 2 * L, TB).a(b.h, 0, L, true).b(b.dG, 0, 2 * L, true)
-                    .f32(g->gru_gates_w + static_cast<long long>(W) * 2 * L, 2 * L).run(h, st));
-        VQA_TRY(GemmB(W, 2 * L, TB).a(b.e, 0, Wp, true).b(b.dG, 0, 2 * L, true).f32(g->gru_gates_w, 2 * L).run(h, st));
-      }
+                    .f32(g->gru_gates_w + static_cast<long long>(W) * 2 * L, 2 * L).narrow().run(h, st));
       if (g->gru_gates_b) {
         if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part, (Bn + 127) / 128, 2 * L, 3 * L, g->gru_gates_b, scr, st));
         else VQA_TRY(colsum_launch(b.dG_f32, TB, 2 * L, 2 * L, g->gru_gates_b, scr, st));
       }
       return VQA_OK;
     };
-    auto cand_wgrad = [&](cudaStream_t st, float* scr) -> VqaStatus {
-      if (g->gru_cand_w) {
+    auto cand_h_wgrad = [&](cudaStream_t st, float* scr) -> VqaStatus {
+      if (g->gru_cand_w)
         VQA_TRY(GemmB(L, L, TB).a(b.rh, 0, L, true).b(b.dC, 0, L, true)
-                    .f32(g->gru_cand_w + static_cast<long long>(W) * L, L).run(h, st));
-        VQA_TRY(GemmB(W, L, TB).a(b.e, 0, Wp, true).b(b.dC, 0, L, true).f32(g->gru_cand_w, L).run(h, st));
-      }
+                    .f32(g->gru_cand_w + static_cast<long long>(W) * L, L).narrow().run(h, st));
       if (g->gru_cand_b) {
         if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part + 2 * L, (Bn + 127) / 128, L, 3 * L, g->gru_cand_b, scr, st));
         else VQA_TRY(colsum_launch(b.dC_f32, TB, L, L, g->gru_cand_b, scr, st));
       }
+      return VQA_OK;
+    };
+    auto x_wgrad = [&](cudaStream_t st) -> VqaStatus {
+      if (g->gru_gates_w)
+        VQA_TRY(GemmB(W, 2 * L, TB).a(b.e, 0, Wp, true).b(b.dG, 0, 2 * L, true).f32(g->gru_gates_w, 2 * L).narrow().run(h, st));
+      if (g->gru_cand_w)
+        VQA_TRY(GemmB(W, L, TB).a(b.e, 0, Wp, true).b(b.dC, 0, L, true).f32(g->gru_cand_w, L).narrow().run(h, st));
       return VQA_OK;
     };
     auto embed_bwd = [&](cudaStream_t st) -> VqaStatus {
@@ -471,25 +479,29 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       VQA_TRY(vproj_wgrad(s));
       PH_END(VQA_PH_VPROJ_WGRAD);
       PH_BEGIN(VQA_PH_GRU_WGRAD);
-      VQA_TRY(gates_wgrad(s, b.scratch));
-      VQA_TRY(cand_wgrad(s, b.scratch));
+      VQA_TRY(gates_h_wgrad(s, b.scratch));
+      VQA_TRY(cand_h_wgrad(s, b.scratch));
+      VQA_TRY(x_wgrad(s));
       PH_END(VQA_PH_GRU_WGRAD);
       PH_BEGIN(VQA_PH_EMBED_BWD);
       VQA_TRY(embed_bwd(s));
       PH_END(VQA_PH_EMBED_BWD);
     } else {
-      // four independent branches: the SMs are shared by GEMMs with different tile counts and bottlenecks
-      cudaStream_t a0, a1, a2;
+      // five independent branches
+      cudaStream_t a0, a1, a2, a3;
       VQA_TRY(fork_stream(h, 0, s, &a0));
       VQA_TRY(fork_stream(h, 1, s, &a1));
       VQA_TRY(fork_stream(h, 2, s, &a2));
+      VQA_TRY(fork_stream(h, 3, s, &a3));
+      VQA_TRY(gates_h_wgrad(a1, scratch1));
+      VQA_TRY(cand_h_wgrad(a2, scratch2));
+      VQA_TRY(x_wgrad(a3));
       VQA_TRY(vproj_wgrad(a0));
-      VQA_TRY(gates_wgrad(a1, scratch1));
-      VQA_TRY(cand_wgrad(a2, scratch2));
       VQA_TRY(embed_bwd(s));
       VQA_TRY(join_stream(h, 0, s));
       VQA_TRY(join_stream(h, 1, s));
       VQA_TRY(join_stream(h, 2, s));
+      VQA_TRY(join_stream(h, 3, s));
     }
   } else {
     PH_BEGIN(VQA_PH_VPROJ_WGRAD);
