@@ -42,6 +42,20 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_traffic(dom):
+    """DRAM bytes of the dominant launch from the committed `ncu --set full` capture (None if absent)."""
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary.json")
+    want = "v_linear_v wgrad" if dom == "vproj_wgrad" else "v_linear_v forward"
+    try:
+        with open(p) as f:
+            for k in json.load(f)["kernels"]:
+                if k["role"].startswith(want):
+                    return k["dram_traffic_bytes"]
+    except (OSError, KeyError, ValueError):
+        pass
+    return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
 
@@ -281,14 +295,16 @@ def run_ours(args):
     e2e_value = samples / (ms_e2e * 1e-3)
 
     # rooflines. Dominant kernel = the v-projection GEMM pair (fwd: [B*K,Dv]x[Dv,D], wgrad: [Dv,B*K]x[B*K,D]),
-    # each ONE launch of gemm_bf16_tcgen05_kernel; algorithmic FLOPs = 2*M*N*K (77.31 GF each).
+    # each ONE launch of gemm_pair_kernel (bf16 mode); algorithmic FLOPs = 2*M*N*K (77.31 GF each).
     K_, Dv, D = c["K"], c["Dv"], c["D"]
     gemm_flops = 2.0 * B * K_ * Dv * D * (3 if args.precision == "fp32" else 1)
     dom = "vproj_wgrad" if phase_ms["vproj_wgrad"] >= phase_ms["vproj_fwd"] else "vproj_fwd"
     ach = gemm_flops / (phase_ms[dom] * 1e-3) / 1e12
     peak_tc = peaks["bf16_tflops_sustained"]
-    roofline = {"bound": "tensor", "kernel": f"gemm_bf16_tcgen05_kernel ({dom})", "achieved": ach, "peak": peak_tc,
-                "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": None,
+    kern = "gemm_pair_kernel" if args.precision == "bf16" else "gemm_bf16_tcgen05_kernel"
+    roofline = {"bound": "tensor", "kernel": f"{kern} ({dom})", "achieved": ach, "peak": peak_tc,
+                "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": ncu_traffic(dom) if args.precision == "bf16" else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch, profiles/r01_ncu_full_summary.json",
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)"}
     zb = 2 if args.precision == "bf16" else 4     # bytes / element of the stored pre-LN projection
     vb = 2 if args.precision == "bf16" else 4     # gathered features: bf16 plane (fp32 mode: hi + lo planes)

@@ -36,7 +36,7 @@ for mode, name in ((0, "forward"), (1, "BPTT")):
         st = np.median(a[:, 0][a[:, 0] > 0]) if (a[:, 0] > 0).any() else np.nan
         f = lambda x, y: np.median((a[:, y] - a[:, x])[(a[:, x] > 0) & (a[:, y] > 0)]) / 1e3 if ((a[:, x] > 0) & (a[:, y] > 0)).any() else float("nan")
         if mode == 0 and p % 2 == 0 and p > 0:
-            print(f"      fwd kind0 detail: acc->smem read {f(2, 4):.2f}  ->stores issued {f(4, 5):.2f}  ->bar_all {f(5, 6):.2f}  "
-                  f"->fenced {f(6, 7):.2f}  ->red {f(7, 3):.2f}")
+            print(f"      fwd kind0 detail: acc->staged {f(2, 5):.2f}  ->bar_all {f(5, 6):.2f}  ->stored {f(6, 4):.2f}  "
+                  f"->fenced {f(4, 7):.2f}  ->red {f(7, 3):.2f}")
         print(f"{p:4d}  {(st - t0) / 1e3:9.2f}  {f(0, 1):10.2f}  {f(1, 2):10.2f}  {f(2, 3):10.2f}      "
               f"{(a[:, 3].max() - a[:, 3].min()) / 1e3:6.2f}   arrive@{(np.median(a[:, 3]) - t0) / 1e3:8.2f}")

@@ -19,6 +19,8 @@ Definition of "relative" fixed here:
     (tests/test_oracle.py::test_relu_gate_flip_noise_model reproduces 3-15 % relative-L2 on the oracle alone).
     The same kernels are held to 1e-4 against the plain oracle in fp32 mode.
 """
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -114,6 +116,41 @@ def test_bf16_small(variant):
     worst = _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
     print("bf16 max-norm gradient errors vs the mixed-precision oracle:", {k: f"{v:.2e}" for k, v in worst.items()})
     assert (got["pred"] == case["plain_out"]["pred"]).mean() >= 0.9
+
+
+def test_bf16_full_row_tiles():
+    """Batch 192 = three full 64-row tiles over two 128-row tiles: the CTA-pair GRU kernels publish their operand
+    tiles through TMA stores (B % 64 == 0), one CTA of the second row tile lies wholly beyond the batch."""
+    dims = dict(SMALL, B=192, L=128)
+    case = build_case(dims, precision="bf16", seed=8, num_images=64)
+    got, ref, ref_g = run_both(case)
+    _check_forward_plain(case, got, BF16_TOL)
+    _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
+
+
+def test_gru_pair_kernels_match_single_cta_kernels_at_full_size():
+    """cfg1 layer sizes and batch (B 512, L 1024, T 14): the CTA-pair GRU kernels (TMA-store publication, k-block
+    boxes) against the single-CTA kernels on the same inputs. Both round operands to bf16 at the same points and
+    accumulate every dot product in the same k order, so states and gradients must agree to fp32 rounding."""
+    dims = dict(B=512, K=8, Dv=256, D=1024, L=1024, A=200, T=14, W=300, Vq=512)
+    case = build_case(dims, precision="bf16", seed=9, num_images=32)
+    eng = case["eng"]
+    eng.stage_batch(case["batch"])
+    res = {}
+    for on in (1, 0):
+        eng.lib.vqa_internal_set_gru_pair(C.c_int(on))
+        eng.forward(seed=3, step=1)
+        eng.backward()
+        torch.cuda.synchronize()
+        res[on] = (eng.o_condition.clone(), {k: v.clone() for k, v in eng.params.grad_views.items()})
+    eng.lib.vqa_internal_set_gru_pair(C.c_int(1))
+    q1, g1 = res[1]
+    q0, g0 = res[0]
+    assert torch.isfinite(q1).all()
+    assert (q1 - q0).abs().max().item() <= 1e-5 * q0.abs().max().item()
+    for k in ("gru_gates_w", "gru_gates_b", "gru_cand_w", "gru_cand_b", "embed"):
+        scale = g0[k].abs().max().item()
+        assert (g1[k] - g0[k]).abs().max().item() <= 2e-4 * scale, k
 
 
 def test_fp32_reference_shapes():

@@ -378,6 +378,39 @@ bool cached_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ou
   return cached_tmap_kind(out, base, 0, inner, outer, pitch, bi, bo);
 }
 
+// K-major bf16 operand [rows, K] seen as {64 k, rows, K / 64 k-blocks} (strides: pitch, 128 bytes), box
+// {64, box_rows, box_kb}: ONE TMA operation brings box_kb consecutive k-block tiles, each in the 128-byte-swizzled
+// layout the MMA descriptors expect, back to back. An SM completes only ~4 TMA operations per microsecond whatever
+// their size (scripts/probes/tma_ingest.cu: 8 KB -> 33 GB/s, 32 KB -> 124 GB/s, 64 KB -> 141 GB/s per SM), so
+// operand tiles have to arrive in few, large operations.
+bool cached_tmap_kblocks(CUtensorMap* out, const void* base, uint64_t K, uint64_t rows, uint64_t pitch,
+                         uint32_t box_rows, uint32_t box_kb) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{base, K, rows, pitch, box_rows, box_kb, 3};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[3] = {64, rows, (K + 63) / 64};
+  cuuint64_t strides[2] = {pitch * 2, 128};
+  cuuint32_t box[3] = {64, box_rows, box_kb};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap tm;
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return true;
+}
+
 namespace {
 
 template <int BN, int SPLIT, bool A_MN, bool B_MN>

@@ -26,6 +26,8 @@
 
 namespace vqa {
 
+unsigned long long* g_gru_trace = nullptr;   // debugging aid, see vqa_internal_set_gru_trace
+
 namespace {
 
 constexpr int R_BM = 128;   // batch rows per CTA (UMMA M)
@@ -561,13 +563,15 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
       red[(e * 3 + 2) * 32 + lane] = db_c;
       epi_bar_all();
       if (e == 0) {
-        float* out = g.bias_part + static_cast<long long>(m0 / R_BM) * 3 * L;
+        // two partial rows per row tile (the CTA-pair variant fills both; here the second one is zero)
+        float* out = g.bias_part + static_cast<long long>(m0 / R_BM) * 2 * 3 * L;
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
           float s = 0.f;
 #pragma unroll
           for (int w = 0; w < R_EPI_WARPS; ++w) s += red[(w * 3 + k) * 32 + lane];
           out[k * L + unit] = s;
+          out[3 * L + k * L + unit] = 0.f;
         }
       }
     }
@@ -626,7 +630,8 @@ bool encode_bf16(CUtensorMap* tm, const void* base, uint64_t inner, uint64_t out
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-unsigned long long* g_trace = nullptr;
+bool g_pair_refused = false;
+bool g_fwd_was_pair = false;   // the forward recurrence left r / u / c / h_t in the pair kernels' private layout
 
 constexpr int R_CL = 4;       // cluster size of the multicast variant
 // Measured on B200 (profiles/r01_gru_trace.md): multicasting the activation tiles inside 4-CTA clusters leaves the
@@ -675,7 +680,7 @@ VqaStatus launch_persistent(const void* a0_ptr, uint64_t a0_inner, uint64_t a0_r
   const int Bn = g.row_end;
   for (int row0 = 0; row0 < Bn; row0 += tiles_per_launch * R_BM) {
     GruArgs a = g;
-    a.trace = g_trace ? g_trace + (MODE ? 1 : 0) * (1 << 17) : nullptr;
+    a.trace = g_gru_trace ? g_gru_trace + (MODE ? 1 : 0) * (1 << 17) : nullptr;
     a.row0 = row0;
     a.row_end = Bn < row0 + tiles_per_launch * R_BM ? Bn : row0 + tiles_per_launch * R_BM;
     const int mt = (a.row_end - row0 + R_BM - 1) / R_BM;
@@ -710,7 +715,7 @@ VqaStatus launch_persistent(const void* a0_ptr, uint64_t a0_inner, uint64_t a0_r
 
 // debugging aid (not part of the ABI header): device buffer of 2 x 2^17 u64 receiving per-phase time stamps
 extern "C" __attribute__((visibility("default"))) void vqa_internal_set_gru_trace(void* dev_ptr) {
-  g_trace = static_cast<unsigned long long*>(dev_ptr);
+  g_gru_trace = static_cast<unsigned long long*>(dev_ptr);
 }
 
 bool gru_persistent_supported(int B, int L, int precision, int num_sms) {
@@ -722,7 +727,8 @@ bool gru_persistent_supported(int B, int L, int precision, int num_sms) {
 }
 
 size_t gru_pack_elems(int L) { return static_cast<size_t>(3) * L * L; }
-size_t gru_bias_part_floats(int B, int L) { return static_cast<size_t>((B + R_BM - 1) / R_BM + 1) * 3 * L; }
+size_t gru_bias_part_floats(int B, int L) { return static_cast<size_t>(2 * ((B + R_BM - 1) / R_BM) + 2) * 3 * L; }
+int gru_bias_part_rows(int B) { return 2 * ((B + R_BM - 1) / R_BM); }
 
 VqaStatus gru_pack_weights_launch(const bf16* wg_h, const bf16* wc_h, int L, bf16* out, cudaStream_t s) {
   gru_pack_weights_kernel<<<dim3(L / 32, 3, L / 32), dim3(32, 8), 0, s>>>(wg_h, wc_h, L, out);
@@ -730,8 +736,26 @@ VqaStatus gru_pack_weights_launch(const bf16* wg_h, const bf16* wc_h, int L, bf1
   return VQA_OK;
 }
 
+// the CTA-pair kernels (gru_pair.cu) first; if their cluster + cooperative launch is refused on this device /
+// partition, the single-CTA kernels below take over for the rest of the process
+static bool try_pair(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) {
+    count_launch();
+    return true;
+  }
+  cudaGetLastError();
+  if (getenv("VQA_VERBOSE")) fprintf(stderr, "[vqa] %s: pair launch refused (%s): single-CTA kernels from now on\n", what, cudaGetErrorString(e));
+  g_pair_refused = true;
+  return false;
+}
+
 VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
+  g_fwd_was_pair = false;
+  if (!g_pair_refused && gru_pair_supported(B, L, num_sms) && try_pair(gru_pair_fwd(a, s), "gru forward")) {
+    g_fwd_was_pair = true;
+    return VQA_OK;
+  }
   CUtensorMap tm_wg, tm_wc;
   const uint64_t prow = static_cast<uint64_t>(L / R_JN) * 96;
   bool ok = encode_bf16(&tm_wg, a.w_pack, L, prow, L, 64, 64) &&
@@ -746,6 +770,13 @@ VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cuda
 
 VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
+  if (g_fwd_was_pair) {
+    // the saved state is in the pair kernels' layout: only the pair BPTT kernel can read it
+    cudaError_t e = gru_pair_bwd(a, s);
+    if (e != cudaSuccess) return set_cuda_error(e, "gru BPTT (pair) launch");
+    count_launch();
+    return VQA_OK;
+  }
   CUtensorMap tm_wc, tm_wg;
   bool ok =  // weights in TF layout [in, out]: row = input unit (the N of these products), contiguous = output
             // column (their K): K-major B operands as they are

@@ -1,0 +1,704 @@
+// CTA-pair variant of the persistent GRU kernels (forward recurrence and BPTT of vlmap/modules.py:124-140, one
+// cooperative launch each). Same algorithm and phase structure as gru.cu; what changes is the tiling:
+//
+//   gru.cu      : CTA = 128 rows x 32 units, M = 128 MMAs of one CTA. Every phase the CTA pulls its 128 rows of
+//                 the activation operand (256 KB at L = 1024) plus a streamed weight tile from L2, and an SM ingests
+//                 only ~67 GB/s (measured: profiles/r01_launch_summary_v3.md) -> 3.8 us per phase in the main loop.
+//   this file   : a PAIR of CTAs (tcgen05 cta_group::2, M = 128) = 128 rows x 64 units. Each CTA supplies 64 rows of
+//                 the activation operand (128 KB per phase) and HALF of the weight columns of the pair. The main loop
+//                 turned out to be bound by bytes IN FLIGHT (ring depth x tile / ~0.9 us TMA round trip under load),
+//                 so the larger weight matrix stays resident (128 KB) and the ring is 8 stages deep (96 KB).
+//                 The operand tiles the other CTAs wait for (r.h, h, dG, dC) leave through ONE TMA store of full
+//                 128-byte rows followed by its completion wait, instead of scattered 16-byte stores and a
+//                 device-wide fence (2.6 us -> see profiles/).
+//
+// Accumulator layout of M = 128 / cta_group::2 (each CTA holds 64 rows x N columns, folded "2 x 2": columns
+// [0, N/2) on TMEM lanes 0..63, columns [N/2, N) on lanes 64..127, both in TMEM columns [0, N/2)). The weight rows
+// are ordered so that the first half of the N columns belongs to the first 32 units of the pair and the second half
+// to the other 32; a thread therefore owns ONE batch row and 8 units, reads its accumulators straight from TMEM
+// (no shared-memory transpose), and keeps the recurrent state (h, u / dh, du) of those 8 elements in registers for
+// the whole sequence.
+//
+// Dependencies: a CTA's activation rows are produced by the 16 CTAs of the same (row tile, rank); they synchronise
+// through one global counter per (row tile, rank).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+
+#include "internal.h"
+#include "ptx.cuh"
+
+namespace vqa {
+
+namespace {
+
+constexpr int Q_ROWS = 64;                      // batch rows per CTA
+constexpr int Q_UNITS = 32;                     // hidden units whose weights this CTA holds (64 per pair)
+constexpr int Q_BK = 64;
+constexpr int Q_STAGES = 2;
+constexpr int Q_KBS = 4;                        // k-blocks per stage = per TMA operation (fewer when L / 64 is not a multiple)
+constexpr int Q_A_TILE = Q_ROWS * Q_BK * 2;     // 8 KB activation tile of one k-block
+constexpr int Q_W_TILE = Q_UNITS * Q_BK * 2;    // 4 KB streamed weight tile (32 rows) of one k-block
+constexpr int Q_STAGE = Q_KBS * (Q_A_TILE + Q_W_TILE);    // 48 KB: [kbs activation tiles | kbs weight tiles]
+constexpr int Q_EPI_WARPS = 16;
+constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS;
+constexpr int Q_TMEM_COLS = 128;                // forward: gates at column 0 (64 wide), candidate at 64 (32 wide)
+constexpr int NU = 8;                           // units per epilogue thread
+
+// resident weights: forward = this CTA's gate rows (64 x L), BPTT = its Wg_h rows (32 x 2L): 128 L bytes
+__host__ __device__ constexpr int q_wres_bytes(int L) { return 2 * Q_UNITS * L * 2; }
+__host__ __device__ constexpr int q_smem_bytes(int L) { return q_wres_bytes(L) + Q_STAGES * Q_STAGE + 256 + 1024; }
+
+struct PairGruArgs {
+  int B, row_end, L, T;
+  const int* q_len;
+  unsigned int* counter;   // [2 * row tiles]
+  const float* xg; const float* xc;
+  float* h_f32; bf16* h_bf; bf16* rh_bf;
+  float* r; float* u; float* c;
+  const float* dq;
+  bf16* dG_bf; bf16* dC_bf;
+  float* bias_part;        // [2 * row tiles, 3L]
+  int kbs;                 // k-blocks per stage / TMA operation (4, 2 or 1)
+  int dbg;                 // timing experiments only (results wrong): 1 = no MMA issued, 2 = no TMA issued
+  int tma_out;             // B % 64 == 0: operand tiles leave through TMA stores (the tensor map of the phase that reads them)
+  unsigned long long* trace;   // optional [num_ctas, num_phases, 8] globaltimer stamps (scripts/gpu_gru_trace.py)
+};
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define GRU_TRACE(p, k)                                                                                   \
+  do {                                                                                                    \
+    if (g.trace)                                                                                          \
+      g.trace[((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * num_phases + (p)) * 8 + (k)] = \
+          gtimer();                                                                                       \
+  } while (0)
+
+
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void wait_counter(const unsigned int* p, unsigned int target) {
+  if (ld_acquire_u32(p) >= target) return;
+  const long long t0 = clock64();
+  while (ld_acquire_u32(p) < target) {
+    if (clock64() - t0 > 4000000000LL) __trap();   // a lost arrival becomes a launch failure, never a hung GPU
+  }
+}
+__device__ __forceinline__ void epi_bar_all() { asm volatile("bar.sync 1, %0;" ::"n"(32 * Q_EPI_WARPS) : "memory"); }
+__device__ __forceinline__ float tanh_fast(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigm(float x) { return fmaf(0.5f, tanh_fast(0.5f * x), 0.5f); }
+__device__ __forceinline__ void red_relaxed_add(unsigned int* p, unsigned int v) {
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+// this warp's 32 TMEM lanes x 8 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[NU]) {
+  uint32_t u[NU];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+               : "r"(taddr)
+               : "memory");
+  ptx::tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < NU; ++j) v[j] = __uint_as_float(u[j]);
+}
+__device__ __forceinline__ void load8f(const float* p, float (&v)[NU]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+__device__ __forceinline__ void store8f(float* p, const float (&v)[NU]) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void store8bf(bf16* p, const float (&v)[NU]) {
+  __nv_bfloat162 a(__float2bfloat16_rn(v[0]), __float2bfloat16_rn(v[1]));
+  __nv_bfloat162 b(__float2bfloat16_rn(v[2]), __float2bfloat16_rn(v[3]));
+  __nv_bfloat162 c(__float2bfloat16_rn(v[4]), __float2bfloat16_rn(v[5]));
+  __nv_bfloat162 d(__float2bfloat16_rn(v[6]), __float2bfloat16_rn(v[7]));
+  uint4 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&a); pk.y = *reinterpret_cast<uint32_t*>(&b);
+  pk.z = *reinterpret_cast<uint32_t*>(&c); pk.w = *reinterpret_cast<uint32_t*>(&d);
+  *reinterpret_cast<uint4*>(p) = pk;
+}
+
+// 8 bf16 values -> this thread's 16-byte chunk of a staged 64 x 64 tile (128-byte rows, SWIZZLE_128B)
+__device__ __forceinline__ void stage8bf(uint32_t tile, int r, int chunk, const float (&v)[NU]) {
+  __nv_bfloat162 a(__float2bfloat16_rn(v[0]), __float2bfloat16_rn(v[1]));
+  __nv_bfloat162 b(__float2bfloat16_rn(v[2]), __float2bfloat16_rn(v[3]));
+  __nv_bfloat162 c(__float2bfloat16_rn(v[4]), __float2bfloat16_rn(v[5]));
+  __nv_bfloat162 d(__float2bfloat16_rn(v[6]), __float2bfloat16_rn(v[7]));
+  ptx::st_shared_v4_b32(tile + r * 128 + ((chunk ^ (r & 7)) << 4), *reinterpret_cast<uint32_t*>(&a),
+                        *reinterpret_cast<uint32_t*>(&b), *reinterpret_cast<uint32_t*>(&c),
+                        *reinterpret_cast<uint32_t*>(&d));
+}
+
+// MODE 0: forward.  phase 2t  : G = h_t Wg_h (+xg) -> r, u, r.h        (no matmul at t = 0: h_0 = 0)
+//                   phase 2t+1: C = (r.h) Wc_h (+xc) -> c, h_{t+1}
+// MODE 1: BPTT.     phase 0   : element-wise head of step T-1 from dq -> du, dC_{T-1}, dh_part
+//                   phase 1+2i: dRH = dC_t Wc_h^T -> dG_t, dh_part           (t = T-1-i)
+//                   phase 2+2i: dh  = dG_t Wg_h^T + dh_part -> head of step t-1   (not run for t = 0)
+// tm_a0 / tm_a1: activation operands of phase kind 0 / 1 (k-block boxes: 64 k x 64 rows x kbs k-blocks);
+// tm_o0 / tm_o1: the tensors phase kind 0 / 1 PRODUCES (= the operand of the other kind), 64 x 64 boxes for TMA stores;
+// tm_w0 / tm_w1: this CTA's weight rows of kind 0 / 1 (forward: packed slices, box 64 x 64 and 64 x 32;
+//                BPTT: Wc_h rows and Wg_h rows in TF layout, box 64 x 32 both).
+template <int MODE>
+__global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
+    const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
+    const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
+    const __grid_constant__ CUtensorMap tm_o0, const __grid_constant__ CUtensorMap tm_o1, PairGruArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int L = g.L, T = g.T, B = g.B;
+  const int KB = L / Q_BK;
+  constexpr int RES_KIND = (MODE == 0) ? 0 : 1;   // the phase kind whose weights are resident
+  // resident weights: forward kind 0 = gate rows (64 x L: KB tiles of 8 KB); BPTT kind 1 = Wg_h rows (32 x 2L:
+  // 2 KB tiles of 4 KB). The other matrix (32 rows) streams through the ring next to the activation tiles.
+  uint8_t* wres = smem;
+  uint8_t* ring = smem + q_wres_bytes(L);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + Q_STAGES * Q_STAGE);
+  uint64_t* empty_bar = full_bar + Q_STAGES;
+  uint64_t* tmem_full_bar = empty_bar + Q_STAGES;
+  uint64_t* w_bar = tmem_full_bar + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int slice32 = blockIdx.x;               // 32-unit slice whose weights this CTA holds (= 2 * pair + rank)
+  const int mi = blockIdx.y;
+  const int j0 = slice32 * Q_UNITS;
+  const int m0 = mi * 128 + static_cast<int>(rank) * Q_ROWS;   // first batch row of this CTA
+  const unsigned int nprod = gridDim.x >> 1;    // CTAs producing this CTA's activation rows (same row tile and rank)
+  unsigned int* counter = g.counter + 2 * mi + rank;
+  const int num_phases = 2 * T;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tensormap(&tm_a0);
+    ptx::prefetch_tensormap(&tm_a1);
+    ptx::prefetch_tensormap(&tm_w0);
+    ptx::prefetch_tensormap(&tm_w1);
+    for (int s = 0; s < Q_STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, Q_TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto phase_info = [&](int p, bool& mm, int& kind, int& t) {
+    if (MODE == 0) {
+      t = p >> 1;
+      kind = p & 1;
+      mm = t > 0;
+    } else {
+      if (p == 0) { mm = false; kind = 1; t = T; return; }
+      const int i = (p - 1) >> 1;
+      t = T - 1 - i;
+      kind = (p - 1) & 1;
+      mm = true;
+    }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    const uint32_t lw = ptx::mapa_u32(ptx::smem_u32(w_bar), 0);
+    if (lane == 0) {
+      // resident weights of BOTH CTAs complete on the leader's barrier (it issues the MMAs that read them)
+      if (rank == 0) ptx::mbar_arrive_expect_tx(w_bar, 2u * static_cast<uint32_t>(q_wres_bytes(L)));
+      // (the weight maps have 32-row boxes of g.kbs k-blocks: tiles of one k-block stay kbs * 4 KB apart per op)
+      if (MODE == 0) {
+        // gate rows: r (32 rows) and u (32 rows) of this slice, k-block tile = [r rows | u rows] = 8 KB
+        for (int kb = 0; kb < KB; ++kb) {
+          ptx::tma_load_2d_pair(wres + kb * 8192, &tm_w0, lw, kb * Q_BK, slice32 * 96);
+        }
+      } else {
+        for (int kb = 0; kb < 2 * KB; ++kb) ptx::tma_load_2d_pair(wres + kb * 4096, &tm_w1, lw, kb * Q_BK, j0);
+      }
+    }
+    __syncwarp();
+    int stage = 0;
+    uint32_t phase_bit = 0;
+    for (int p = 0; p < num_phases; ++p) {
+      bool mm; int kind, t;
+      phase_info(p, mm, kind, t);
+      if (!mm) continue;
+      const bool streamed = kind != RES_KIND;
+      const CUtensorMap* ta = kind ? &tm_a1 : &tm_a0;
+      const CUtensorMap* tw = (MODE == 0) ? &tm_w1 : &tm_w0;
+      const int wrow = (MODE == 0) ? slice32 * 96 + 64 : j0;
+      const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
+      const int arow = t * B + m0;
+      const int kbs = g.kbs;
+      const uint32_t a_bytes = kbs * Q_A_TILE, w_bytes = kbs * Q_W_TILE;
+      for (int kb = 0; kb < nkb; kb += kbs) {
+        ptx::mbar_wait(&empty_bar[stage], phase_bit ^ 1);
+        const uint32_t lf = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
+        uint8_t* st = ring + stage * Q_STAGE;
+        const bool first = kb == 0;
+        // the streamed weights do not depend on the other CTAs: for the first stage they go out BEFORE the counter
+        // wait (stage 0 doubles as the epilogue's TMA-store staging, but only its activation area)
+        if (ptx::elect_one() && g.dbg != 2) {
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + (streamed ? w_bytes : 0)));
+          if (streamed) ptx::tma_load_3d_pair(st + a_bytes, tw, lf, 0, wrow, kb);
+        }
+        __syncwarp();
+        if (first) {
+          // this phase's operand rows were written by the epilogues of phase p - 1 of the CTAs sharing our rows
+          wait_counter(counter, static_cast<unsigned int>(p) * nprod);
+          ptx::fence_proxy_async_full();
+          if (lane == 0) GRU_TRACE(p, 0);
+          __syncwarp();
+        }
+        if (ptx::elect_one()) {
+          if (g.dbg == 2) {
+            if (rank == 0) ptx::mbar_arrive(&full_bar[stage]);
+          } else {
+            ptx::tma_load_3d_pair(st, ta, lf, 0, arow, kb);
+          }
+        }
+        __syncwarp();
+        if (++stage == Q_STAGES) {
+          stage = 0;
+          phase_bit ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA of the pair) =====================
+    if (rank == 0) {
+      constexpr uint32_t idesc128 = ptx::make_idesc_bf16(128, 128, false, false);   // forward gates: r|u of 64 units
+      constexpr uint32_t idesc64 = ptx::make_idesc_bf16(128, 64, false, false);
+      ptx::mbar_wait(w_bar, 0);
+      int stage = 0;
+      uint32_t phase_bit = 0;
+      for (int p = 0; p < num_phases; ++p) {
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        if (!mm) continue;
+        const bool streamed = kind != RES_KIND;
+        const bool wide = (MODE == 0 && kind == 0);
+        const uint32_t idesc = wide ? idesc128 : idesc64;
+        const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
+        const uint32_t wtile = wide ? 8192 : 4096;
+        const uint32_t d_tmem = tmem_base + ((MODE == 0 && kind == 1) ? 64 : 0);
+        const int kbs = g.kbs;
+        for (int kb = 0; kb < nkb; kb += kbs) {
+          ptx::mbar_wait(&full_bar[stage], phase_bit);
+          ptx::tc_fence_after();
+          if (kb == 0 && lane == 0) GRU_TRACE(p, 1);
+          const uint32_t sa0 = ptx::smem_u32(ring + stage * Q_STAGE);
+          const uint32_t sw0 = sa0 + kbs * Q_A_TILE;
+          if (ptx::elect_one()) {
+            if (g.dbg != 1)
+            for (int i = 0; i < kbs; ++i) {
+              const uint32_t sa = sa0 + i * Q_A_TILE;
+              const uint32_t sb = streamed ? sw0 + i * Q_W_TILE : ptx::smem_u32(wres) + (kb + i) * wtile;
+#pragma unroll
+              for (int kk = 0; kk < Q_BK / 16; ++kk) {
+                const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+                const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 32, 16, 1024);
+                ptx::umma_f16_pair(d_tmem, da, db, idesc, (kb | i | kk) != 0);
+              }
+            }
+            ptx::umma_commit_pair(&empty_bar[stage], 3);
+          }
+          __syncwarp();
+          if (++stage == Q_STAGES) {
+            stage = 0;
+            phase_bit ^= 1;
+          }
+        }
+        if (ptx::elect_one()) ptx::umma_commit_pair(tmem_full_bar, 3);
+        __syncwarp();
+        // the accumulators are overwritten only after both CTAs' next counter waits, which their own epilogues
+        // reach after draining TMEM: no tmem_empty barrier needed
+      }
+    }
+  } else {
+    // ===================== epilogue warps: thread = (batch row, 8 units) =====================
+    const int q = warp & 3;                          // TMEM lane quarter this warp may read
+    const int sub = (warp - 2) >> 2;                 // which 8 of the 32 units of the half
+    const int uhalf = q >> 1;                        // lanes 0..63: first 32 units of the pair, 64..127: the others
+    const int row = m0 + (q & 1) * 32 + lane;
+    const bool row_ok = row < g.row_end;
+    const int unit = (slice32 & ~1) * Q_UNITS + uhalf * 32 + sub * NU;   // first of this thread's 8 units
+    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sub * NU;
+    const int my_len = row_ok ? g.q_len[row] : 0;
+    const bool leader = threadIdx.x == 64;
+    uint32_t tfull_phase = 0;
+    // TMA-store staging: the A areas of ring stages 0 and 1 (idle between the last MMA of a phase and the next
+    // phase's first load, which waits for this CTA's own arrival below)
+    const uint32_t stg0 = ptx::smem_u32(ring), stg1 = ptx::smem_u32(ring + Q_STAGE);
+    const int srow = (q & 1) * 32 + lane;         // row inside the CTA's 64-row tile
+    const int schunk = uhalf * 4 + sub;           // 16-byte chunk inside the 128-byte row of 64 units
+    const int ucol = (slice32 >> 1) * 64;         // first unit of the pair
+    const bool tma_out = g.tma_out != 0;
+    // fp32 state kept for BPTT (r, u, c, h_t): with full 64-row tiles it lives in a layout private to these two
+    // kernels, [t][64-row tile][unit / 8][row % 64][unit % 8], in which the 32 bytes of the lanes of a warp are
+    // consecutive (1 KB per warp access instead of 32 sectors 4 KB apart). The final state h_T stays row-major:
+    // it is the model's `condition` output.
+    const int nt64 = (B + Q_ROWS - 1) / Q_ROWS;
+    auto priv = [&](int tblock) -> long long {
+      if (tma_out)
+        return ((static_cast<long long>(tblock) * nt64 + (m0 >> 6)) * (L >> 3) + (unit >> 3)) * (Q_ROWS * NU) + srow * NU;
+      return (static_cast<long long>(tblock) * B + row) * L + unit;
+    };
+    // publish: CTA barrier, then ONE thread hands the staged tile(s) to the TMA, waits for the writes to be
+    // performed, fences and releases the counter
+    auto publish = [&](int p, const CUtensorMap* tm, int ntiles, int col1, long long grow) {
+      if (tma_out) ptx::fence_proxy_async();
+      if (leader) GRU_TRACE(p, 5);
+      epi_bar_all();
+      if (leader) {
+        GRU_TRACE(p, 6);
+        if (tma_out) {
+          // The tile(s) leave through the async proxy and bulk_wait<0> returns once the writes are PERFORMED (at
+          // L2, where the consumers' TMA loads read them), so the relaxed arrival below is ordered after them by
+          // this thread's program order alone. No gpu-scope fence: it would also wait for the scattered fp32
+          // stores of r / u / c (needed only by the BPTT launch), which was 2.6 us of every phase.
+          if (m0 < g.row_end) {   // (B % 64 == 0: a CTA's 64 rows are all valid or all beyond the batch)
+            ptx::tma_store_2d(tm, stg0, ucol, static_cast<int>(grow));
+            if (ntiles == 2) ptx::tma_store_2d(tm, stg1, col1, static_cast<int>(grow));
+            ptx::bulk_commit();
+            ptx::bulk_wait<0>();
+          }
+          GRU_TRACE(p, 4);
+        } else {
+          GRU_TRACE(p, 4);
+          asm volatile("fence.acq_rel.gpu;" ::: "memory");
+          ptx::fence_proxy_async_full();
+        }
+        GRU_TRACE(p, 7);
+        red_relaxed_add(counter, 1u);
+        GRU_TRACE(p, 3);
+      }
+    };
+
+    if (MODE == 0) {
+      float h[NU], u[NU];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) h[j] = 0.f, u[j] = 0.f;
+      for (int p = 0; p < num_phases; ++p) {
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        const long long tb = static_cast<long long>(t) * B;
+        float sv[NU];   // r (kind 0) or c (kind 1)
+        if (kind == 0) {
+          float xr[NU], xu[NU], ar[NU], au[NU];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) xr[j] = xu[j] = ar[j] = au[j] = 0.f;
+          if (row_ok) {
+            const float* x = g.xg + (tb + row) * 2 * L + unit;
+            load8f(x, xr);
+            load8f(x + L, xu);
+          }
+          if (mm) {
+            ptx::mbar_wait(tmem_full_bar, tfull_phase);
+            tfull_phase ^= 1;
+            ptx::tc_fence_after();
+            if (leader) GRU_TRACE(p, 2);
+            tmem_ld8(t_lane, ar);
+            tmem_ld8(t_lane + 32, au);
+            ptx::tc_fence_before();
+          }
+          float rh[NU];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            sv[j] = sigm(ar[j] + xr[j]);
+            u[j] = sigm(au[j] + xu[j]);
+            rh[j] = sv[j] * h[j];
+          }
+          // the operand the other CTAs wait for goes out first; r / u (kept for BPTT) after the arrival
+          if (tma_out) stage8bf(stg0, srow, schunk, rh);
+          else if (row_ok) store8bf(g.rh_bf + (tb + row) * L + unit, rh);
+        } else {
+          float xc[NU], ac[NU];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) xc[j] = ac[j] = 0.f;
+          if (row_ok) load8f(g.xc + (tb + row) * L + unit, xc);
+          if (mm) {
+            ptx::mbar_wait(tmem_full_bar, tfull_phase);
+            tfull_phase ^= 1;
+            ptx::tc_fence_after();
+            if (leader) GRU_TRACE(p, 2);
+            tmem_ld8(t_lane + 64, ac);
+            ptx::tc_fence_before();
+          }
+          const bool valid = t < my_len;
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            sv[j] = tanh_fast(ac[j] + xc[j]);
+            h[j] = valid ? u[j] * h[j] + (1.0f - u[j]) * sv[j] : h[j];
+          }
+          if (tma_out) stage8bf(stg0, srow, schunk, h);
+          else if (row_ok) store8bf(g.h_bf + (tb + B + row) * L + unit, h);
+        }
+        // r.h is the operand of the candidate phase (tm_a1), h_{t+1} the operand of the next gate phase (tm_a0)
+        publish(p, kind == 0 ? &tm_o0 : &tm_o1, 1, 0, kind == 0 ? tb + m0 : tb + B + m0);
+        // what only BPTT reads goes out off the critical path
+        if (row_ok) {
+          const long long o = priv(t);
+          if (kind == 0) {
+            store8f(g.r + o, sv);
+            store8f(g.u + o, u);
+          } else {
+            store8f(g.c + o, sv);
+            if (t + 1 == T) store8f(g.h_f32 + (tb + B + row) * L + unit, h);
+            else store8f(g.h_f32 + priv(t + 1), h);
+          }
+        }
+      }
+    } else {
+      float dhp[NU], du[NU];
+      float db_r[NU], db_u[NU], db_c[NU];
+#pragma unroll
+      for (int j = 0; j < NU; ++j) dhp[j] = du[j] = db_r[j] = db_u[j] = db_c[j] = 0.f;
+      for (int p = 0; p < num_phases; ++p) {
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        if (kind == 0) {
+          // dRH = acc ;  dG_r = dRH h r (1-r) ; dG_u = du u (1-u) ; dh_part += dRH r
+          const long long tb = static_cast<long long>(t) * B;
+          float hh[NU], rv[NU], uv[NU], acc[NU];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) hh[j] = rv[j] = uv[j] = acc[j] = 0.f;
+          if (row_ok) {
+            const long long o = priv(t);
+            if (t > 0) load8f(g.h_f32 + o, hh);   // h_0 = 0 (block 0 is never written in the private layout)
+            load8f(g.r + o, rv);
+            load8f(g.u + o, uv);
+          }
+          ptx::mbar_wait(tmem_full_bar, tfull_phase);
+          tfull_phase ^= 1;
+          ptx::tc_fence_after();
+          if (leader) GRU_TRACE(p, 2);
+          tmem_ld8(t_lane, acc);
+          ptx::tc_fence_before();
+          float dgr[NU], dgu[NU];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            const float drh = acc[j];   // zero for steps beyond the question length (dC is zero there)
+            dgr[j] = drh * hh[j] * rv[j] * (1.0f - rv[j]);
+            dgu[j] = du[j] * uv[j] * (1.0f - uv[j]);
+            dhp[j] = fmaf(drh, rv[j], dhp[j]);
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+              db_r[j] += dgr[j];
+              db_u[j] += dgu[j];
+            }
+            if (!tma_out) {
+              const long long o = (tb + row) * 2 * L + unit;
+              store8bf(g.dG_bf + o, dgr);
+              store8bf(g.dG_bf + o + L, dgu);
+            }
+          }
+          if (tma_out) {
+            stage8bf(stg0, srow, schunk, dgr);
+            stage8bf(stg1, srow, schunk, dgu);
+          }
+          publish(p, &tm_o0, 2, L + ucol, tb + m0);   // dG_t = [dG_r | dG_u]: operand of the next phase
+        } else {
+          // dh = acc + dh_part (or dq) ; element-wise head of step tp = t - 1
+          const int tp = t - 1;
+          const long long tb = static_cast<long long>(tp) * B;
+          float hh[NU], uv[NU], cv[NU], acc[NU];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) hh[j] = uv[j] = cv[j] = acc[j] = 0.f;
+          if (row_ok) {
+            const long long o = priv(tp);
+            if (tp > 0) load8f(g.h_f32 + o, hh);
+            load8f(g.u + o, uv);
+            load8f(g.c + o, cv);
+            if (!mm) load8f(g.dq + static_cast<long long>(row) * L + unit, dhp);
+          }
+          if (mm) {
+            ptx::mbar_wait(tmem_full_bar, tfull_phase);
+            tfull_phase ^= 1;
+            ptx::tc_fence_after();
+            if (leader) GRU_TRACE(p, 2);
+            tmem_ld8(t_lane, acc);
+            ptx::tc_fence_before();
+          }
+          const bool pvalid = tp < my_len;
+          float dcv[NU];
+#pragma unroll
+          for (int j = 0; j < NU; ++j) {
+            const float dh = acc[j] + dhp[j];
+            dcv[j] = pvalid ? dh * (1.0f - uv[j]) * (1.0f - cv[j] * cv[j]) : 0.f;
+            du[j] = pvalid ? dh * (hh[j] - cv[j]) : 0.f;
+            dhp[j] = pvalid ? dh * uv[j] : dh;
+          }
+          if (row_ok) {
+#pragma unroll
+            for (int j = 0; j < NU; ++j) db_c[j] += dcv[j];
+            if (!tma_out) store8bf(g.dC_bf + (tb + row) * L + unit, dcv);
+          }
+          if (tma_out) stage8bf(stg0, srow, schunk, dcv);
+          publish(p, &tm_o1, 1, 0, tb + m0);          // dC_{t-1}: operand of the next phase
+        }
+      }
+      // bias gradients: sum over the 32 rows of the warp (fixed butterfly order), then over the two row-warps
+      // that share these units; one partial row of [3L] per CTA
+#pragma unroll
+      for (int j = 0; j < NU; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          db_r[j] += __shfl_xor_sync(0xffffffffu, db_r[j], o);
+          db_u[j] += __shfl_xor_sync(0xffffffffu, db_u[j], o);
+          db_c[j] += __shfl_xor_sync(0xffffffffu, db_c[j], o);
+        }
+      }
+      float* red = reinterpret_cast<float*>(ring);   // the ring is free now: [16 warps][3][8]
+      if (lane == 0) {
+#pragma unroll
+        for (int j = 0; j < NU; ++j) {
+          red[((warp - 2) * 3 + 0) * NU + j] = db_r[j];
+          red[((warp - 2) * 3 + 1) * NU + j] = db_u[j];
+          red[((warp - 2) * 3 + 2) * NU + j] = db_c[j];
+        }
+      }
+      epi_bar_all();
+      // warps with (q & 1) == 0 combine with their partner (q | 1, same sub) and write
+      if ((q & 1) == 0 && lane < 3 * NU) {
+        const int k = lane / NU, j = lane % NU;
+        const float s = red[((warp - 2) * 3 + k) * NU + j] + red[((warp - 2 + 1) * 3 + k) * NU + j];
+        float* out = g.bias_part + static_cast<long long>(2 * mi + rank) * 3 * L;
+        out[k * L + unit + j] = s;
+      }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, Q_TMEM_COLS);
+  }
+}
+
+template <int MODE>
+cudaError_t launch_pair_gru(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
+                            const CUtensorMap& o0, const CUtensorMap& o1, PairGruArgs& a, dim3 grid, int smem,
+                            cudaStream_t s) {
+  auto kern = gru_pair_kernel<MODE>;
+  static int smem_set = 0;
+  if (smem_set < smem) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) return e;
+    smem_set = smem;
+  }
+  void* args[] = {const_cast<CUtensorMap*>(&a0), const_cast<CUtensorMap*>(&a1), const_cast<CUtensorMap*>(&w0),
+                  const_cast<CUtensorMap*>(&w1), const_cast<CUtensorMap*>(&o0), const_cast<CUtensorMap*>(&o1), &a};
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(Q_THREADS);
+  cfg.dynamicSmemBytes = static_cast<size_t>(smem);
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeCooperative;   // fails instead of deadlocking if the grid cannot be co-resident
+  at[0].val.cooperative = 1;
+  at[1].id = cudaLaunchAttributeClusterDimension;
+  at[1].val.clusterDim.x = 2;
+  at[1].val.clusterDim.y = 1;
+  at[1].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 2;
+  return cudaLaunchKernelExC(&cfg, reinterpret_cast<void*>(kern), args);
+}
+
+int pick_kbs(int L) {
+  const int KB = L / Q_BK;
+  return KB % 4 == 0 ? 4 : (KB % 2 == 0 ? 2 : 1);
+}
+
+bool g_pair_off = getenv("VQA_GRU_PAIR") != nullptr && atoi(getenv("VQA_GRU_PAIR")) == 0;
+
+}  // namespace
+
+// testing aid (not part of the ABI header): 0 = single-CTA kernels of gru.cu, 1 = the CTA-pair kernels
+extern "C" __attribute__((visibility("default"))) void vqa_internal_set_gru_pair(int on) { g_pair_off = on == 0; }
+
+bool gru_pair_supported(int B, int L, int num_sms) {
+  if (g_pair_off) return false;
+  if (L % 64 != 0 || L < 64) return false;
+  if (q_smem_bytes(L) > 227 * 1024) return false;
+  const int row_tiles = (B + 127) / 128;
+  return (L / Q_UNITS) * row_tiles <= num_sms && 2 * row_tiles <= 64;   // one wave, counters fit
+}
+
+// returns cudaSuccess, or the launch error (the caller falls back to the single-CTA kernels)
+cudaError_t gru_pair_fwd(const GruFwdPersistent& a, cudaStream_t s) {
+  const int B = a.B, L = a.L, T = a.T;
+  CUtensorMap tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h;
+  const uint64_t prow = static_cast<uint64_t>(L / 32) * 96;
+  const int kbs = pick_kbs(L);
+  if (!cached_tmap_kblocks(&tm_h, a.h_bf, L, static_cast<uint64_t>(T + 1) * B, L, Q_ROWS, kbs) ||
+      !cached_tmap_kblocks(&tm_rh, a.rh_bf, L, static_cast<uint64_t>(T) * B, L, Q_ROWS, kbs) ||
+      !cached_tmap(&tm_wg, a.w_pack, L, prow, L, 64, 64) || !cached_tmap_kblocks(&tm_wc, a.w_pack, L, prow, L, 32, kbs) ||
+      !cached_tmap(&to_rh, a.rh_bf, L, static_cast<uint64_t>(T) * B, L, 64, Q_ROWS) ||
+      !cached_tmap(&to_h, a.h_bf, L, static_cast<uint64_t>(T + 1) * B, L, 64, Q_ROWS))
+    return cudaErrorInvalidValue;
+  PairGruArgs g{};
+  g.B = B; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
+  g.xg = a.xg; g.xc = a.xc; g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
+  g.trace = g_gru_trace;
+  g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
+  g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;
+  g.kbs = kbs;
+  const int row_tiles = (B + 127) / 128;
+  cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * 2 * row_tiles, s);
+  if (e != cudaSuccess) return e;
+  return launch_pair_gru<0>(tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h, g, dim3(L / Q_UNITS, row_tiles), q_smem_bytes(L), s);
+}
+
+cudaError_t gru_pair_bwd(const GruBwdPersistent& a, cudaStream_t s) {
+  const int B = a.B, L = a.L, T = a.T;
+  CUtensorMap tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc;
+  const int kbs = pick_kbs(L);
+  if (!cached_tmap_kblocks(&tm_dc, a.dC_bf, L, static_cast<uint64_t>(T) * B, L, Q_ROWS, kbs) ||
+      !cached_tmap_kblocks(&tm_dg, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B, 2 * L, Q_ROWS, kbs) ||
+      !cached_tmap_kblocks(&tm_wc, a.wc_h, L, L, L, 32, kbs) || !cached_tmap(&tm_wg, a.wg_h, 2 * L, L, 2 * L, 64, 32) ||
+      !cached_tmap(&to_dg, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B, 2 * L, 64, Q_ROWS) ||
+      !cached_tmap(&to_dc, a.dC_bf, L, static_cast<uint64_t>(T) * B, L, 64, Q_ROWS))
+    return cudaErrorInvalidValue;
+  PairGruArgs g{};
+  g.B = B; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
+  g.h_f32 = const_cast<float*>(a.h_f32); g.r = const_cast<float*>(a.r); g.u = const_cast<float*>(a.u);
+  g.c = const_cast<float*>(a.c); g.dq = a.dq; g.dG_bf = a.dG_bf; g.dC_bf = a.dC_bf; g.bias_part = a.bias_part;
+  g.trace = g_gru_trace ? g_gru_trace + (1 << 17) : nullptr;
+  g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
+  g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;
+  g.kbs = kbs;
+  const int row_tiles = (B + 127) / 128;
+  cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * 2 * row_tiles, s);
+  if (e != cudaSuccess) return e;
+  return launch_pair_gru<1>(tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc, g, dim3(L / Q_UNITS, row_tiles), q_smem_bytes(L), s);
+}
+
+}  // namespace vqa

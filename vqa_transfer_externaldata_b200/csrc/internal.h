@@ -62,6 +62,9 @@ VqaStatus gemm_pair_launch(const VqaGemmDesc& d, int num_sms, int bn, int splits
 bool cached_tmap(CUtensorMap_st* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch,
                  uint32_t box_inner, uint32_t box_outer);
 // kind: 0 = bf16 / 128-byte swizzle (operands), 1 = fp32 / 128-byte swizzle, 2 = bf16 / no swizzle (TMA stores)
+// K-major bf16 [rows, K] as {64 k, rows, k-blocks}: box {64, box_rows, box_kb} = box_kb swizzled k-block tiles per TMA
+bool cached_tmap_kblocks(CUtensorMap_st* out, const void* base, uint64_t K, uint64_t rows, uint64_t pitch,
+                         uint32_t box_rows, uint32_t box_kb);
 bool cached_tmap_kind(CUtensorMap_st* out, const void* base, int kind, uint64_t inner, uint64_t outer,
                       uint64_t pitch, uint32_t box_inner, uint32_t box_outer);
 
@@ -113,12 +116,17 @@ struct GruBwdPersistent {
   const float* dq;                       // [B, L] gradient of the final state
   bf16* dG_bf;                           // [T*B, 2L]
   bf16* dC_bf;                           // [T*B, L]
-  float* bias_part;                      // [ceil(B/128), 3L] partial bias gradients (gates r | gates u | candidate)
+  float* bias_part;                      // [2 * ceil(B/128), 3L] partial bias gradients (gates r | gates u | candidate)
   const bf16* wg_h; const bf16* wc_h;    // bf16 shadows of the h-rows of the TF kernels: [L, 2L], [L, L]
 };
 bool gru_persistent_supported(int B, int L, int precision, int num_sms);
 size_t gru_pack_elems(int L);
 size_t gru_bias_part_floats(int B, int L);
+int gru_bias_part_rows(int B);   // partial rows of [3L] the BPTT kernels write (two per 128-row tile)
+extern unsigned long long* g_gru_trace;
+bool gru_pair_supported(int B, int L, int num_sms);
+cudaError_t gru_pair_fwd(const GruFwdPersistent& a, cudaStream_t s);
+cudaError_t gru_pair_bwd(const GruBwdPersistent& a, cudaStream_t s);
 VqaStatus gru_pack_weights_launch(const bf16* wg_h, const bf16* wc_h, int L, bf16* out, cudaStream_t s);
 VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cudaStream_t s);
 VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cudaStream_t s);

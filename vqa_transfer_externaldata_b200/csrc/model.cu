@@ -439,7 +439,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
         VQA_TRY(GemmB(L, 2 * L, TB).a(b.h, 0, L, true).b(b.dG, 0, 2 * L, true)
                     .f32(g->gru_gates_w + static_cast<long long>(W) * 2 * L, 2 * L).narrow().run(h, st));
       if (g->gru_gates_b) {
-        if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part, (Bn + 127) / 128, 2 * L, 3 * L, g->gru_gates_b, scr, st));
+        if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part, gru_bias_part_rows(Bn), 2 * L, 3 * L, g->gru_gates_b, scr, st));
         else VQA_TRY(colsum_launch(b.dG_f32, TB, 2 * L, 2 * L, g->gru_gates_b, scr, st));
       }
       return VQA_OK;
@@ -449,7 +449,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
         VQA_TRY(GemmB(L, L, TB).a(b.rh, 0, L, true).b(b.dC, 0, L, true)
                     .f32(g->gru_cand_w + static_cast<long long>(W) * L, L).narrow().run(h, st));
       if (g->gru_cand_b) {
-        if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part + 2 * L, (Bn + 127) / 128, L, 3 * L, g->gru_cand_b, scr, st));
+        if (persistent) VQA_TRY(colsum_launch(b.gru_bias_part + 2 * L, gru_bias_part_rows(Bn), L, 3 * L, g->gru_cand_b, scr, st));
         else VQA_TRY(colsum_launch(b.dC_f32, TB, L, L, g->gru_cand_b, scr, st));
       }
       return VQA_OK;
