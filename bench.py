@@ -287,8 +287,17 @@ def run_ours(args):
         buf = (C.c_float * L.NUM_PHASES)()
         L.check(lib.vqa_profile_read(eng.h, buf))
         acc += np.array(list(buf))
-    L.check(lib.vqa_profile_enable(eng.h, 0))
     phase_ms = {lib.vqa_phase_name(i).decode(): float(acc[i] / PROF_STEPS) for i in range(L.NUM_PHASES)}
+    # the same events with the forked branches kept: sections of the main stream's critical path in the REAL step
+    L.check(lib.vqa_profile_enable(eng.h, 2))
+    acc2 = np.zeros(L.NUM_PHASES)
+    for i in range(PROF_STEPS):
+        step_resident(i)
+        buf = (C.c_float * L.NUM_PHASES)()
+        L.check(lib.vqa_profile_read(eng.h, buf))
+        acc2 += np.array(list(buf))
+    L.check(lib.vqa_profile_enable(eng.h, 0))
+    critical_ms = {lib.vqa_phase_name(i).decode(): float(acc2[i] / PROF_STEPS) for i in range(L.NUM_PHASES)}
 
     samples = world * B * args.steps
     value = samples / (ms_value * 1e-3)
@@ -348,6 +357,7 @@ def run_ours(args):
                               "model": "356.1 GF / bf16 sustained + 561.8 MB / HBM (BASELINE.md section 3)"},
             "attn_hbm": attn,
             "phase_ms": phase_ms,
+            "critical_path_ms": critical_ms,
             "cpu_baseline": cpu_baseline,
         }
         _emit(line)

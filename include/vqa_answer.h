@@ -249,6 +249,9 @@ enum {
   VQA_PH_EMBED_BWD,    /* dE GEMMs + scatter-add                                            */
   VQA_NUM_PHASES
 };
+/* enable: 0 = off; 1 = per-phase events with every branch SERIALISED on the caller's stream (isolated phase times);
+ * 2 = events with the auxiliary-stream forks kept (sections of the real critical path; the concurrent weight-gradient
+ *     section is reported as GRU_WGRAD, VPROJ_WGRAD / EMBED_BWD read 0) */
 VQA_API VqaStatus vqa_profile_enable(VqaHandle h, int32_t enable);
 /* milliseconds per phase of the most recent forward+backward (synchronises on the events) */
 VQA_API VqaStatus vqa_profile_read(VqaHandle h, float* ms /* [VQA_NUM_PHASES] */);

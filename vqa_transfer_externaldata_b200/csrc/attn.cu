@@ -634,6 +634,20 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
       !a.ln_mean || !a.ln_rstd)
     return set_error(VQA_ERR_BAD_ARG, "vqa_attn_fwd: null argument");
   if ((D & 7) || (Dv & 7)) return set_error(VQA_ERR_BAD_SHAPE, "vqa_attn_fwd: D, Dv must be multiples of 8");
+  {
+    // the persistent pipelined kernel (attn_pipe.cu) whenever its buffers fit one SM
+    size_t psmem = 0;
+    int rv = 0;
+    if (attn_fwd_pipe_supported(K, D, Dv, precision, a.v_lo != nullptr, &psmem, &rv)) {
+      static int num_sms = 0;
+      if (num_sms == 0) {
+        int dev = 0;
+        VQA_CUDA_CHECK(cudaGetDevice(&dev));
+        VQA_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+      }
+      return attn_fwd_pipe_launch(a, K, D, Dv, keep, psmem, rv, num_sms, s);
+    }
+  }
   FwdArgs f;
   f.z = a.z; f.gamma = a.gamma; f.beta = a.beta; f.hq = a.hq; f.att_w = a.att_w; f.att_b = a.att_b;
   f.nbox = a.nbox; f.v_hi = static_cast<const bf16*>(a.v_hi); f.v_lo = static_cast<const bf16*>(a.v_lo);

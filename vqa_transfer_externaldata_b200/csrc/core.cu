@@ -205,6 +205,7 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   h->params_ready = false;
   h->fwd_valid = false;
   h->profile = false;
+  h->profile_overlapped = false;
   h->ev_created = false;
   for (int i = 0; i < VQA_NUM_PHASES; ++i) h->ev_used[i] = false;
   h->aux_created = false;
@@ -288,6 +289,7 @@ VQA_API VqaStatus vqa_profile_enable(VqaHandle h, int32_t enable) {
     h->ev_created = true;
   }
   h->profile = enable != 0;
+  h->profile_overlapped = enable == 2;   // 2: keep the auxiliary-stream forks (see vqa_answer.h)
   for (int i = 0; i < VQA_NUM_PHASES; ++i) h->ev_used[i] = false;
   return VQA_OK;
 }

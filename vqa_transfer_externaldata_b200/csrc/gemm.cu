@@ -383,6 +383,39 @@ bool cached_tmap(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ou
 // layout the MMA descriptors expect, back to back. An SM completes only ~4 TMA operations per microsecond whatever
 // their size (scripts/probes/tma_ingest.cu: 8 KB -> 33 GB/s, 32 KB -> 124 GB/s, 64 KB -> 141 GB/s per SM), so
 // operand tiles have to arrive in few, large operations.
+// MN-major bf16 operand stored [K, MN] (MN contiguous) seen as {64 mn, 64 k, MN / 64 mn-blocks, K / 64 k-blocks}
+// (strides: pitch, 128 bytes, 64 * pitch), box {64, 64, box_mnb, box_kb}: ONE operation brings box_kb k-block tiles,
+// each made of box_mnb swizzled [64 k x 64 mn] blocks 8 KB apart -- the layout the MN-major MMA descriptors use.
+// Requires K % 64 == 0 (nothing clips k inside a block); mn beyond MN reads neighbouring data, which only feeds
+// output rows / columns that are never stored.
+bool cached_tmap_mnblocks(CUtensorMap* out, const void* base, uint64_t MN, uint64_t K, uint64_t pitch,
+                          uint32_t box_mnb, uint32_t box_kb) {
+  static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;
+  static std::mutex mu;
+  TmapKey key{base, MN, K, pitch, box_mnb, box_kb, 4};
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) {
+    *out = it->second;
+    return true;
+  }
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[4] = {64, 64, (MN + 63) / 64, K / 64};
+  cuuint64_t strides[3] = {pitch * 2, 128, 64 * pitch * 2};
+  cuuint32_t box[4] = {64, 64, box_mnb, box_kb};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUtensorMap tm;
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return false;
+  if (cache.size() > 4096) cache.clear();
+  cache.emplace(key, tm);
+  *out = tm;
+  return true;
+}
+
 bool cached_tmap_kblocks(CUtensorMap* out, const void* base, uint64_t K, uint64_t rows, uint64_t pitch,
                          uint32_t box_rows, uint32_t box_kb) {
   static std::unordered_map<TmapKey, CUtensorMap, TmapKeyHash> cache;

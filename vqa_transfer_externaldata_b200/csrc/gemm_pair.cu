@@ -35,10 +35,14 @@ template <int BN>
 struct PairCfg {
   static constexpr int A_TILE = 128 * P_BK * 2;          // this CTA's 128 rows of A
   static constexpr int B_TILE = (BN / 2) * P_BK * 2;     // this CTA's half of the B columns
-  static constexpr int STAGE = A_TILE + B_TILE;
-  static constexpr int STAGES = (BN == 256) ? 4 : 6;     // 128 / 144 KB in flight
+  // a stage holds TWO k-blocks of each operand: [A kb0 | A kb1 | B kb0 | B kb1]. An SM completes only ~4 TMA
+  // operations per microsecond whatever their size (scripts/probes/tma_ingest.cu), so each operand arrives as ONE
+  // 3-D / 4-D box of two k-block tiles (32 KB) instead of 2 - 4 separate boxes per k-block.
+  static constexpr int KBS = 2;
+  static constexpr int STAGE = KBS * (A_TILE + B_TILE);
+  static constexpr int STAGES = (BN == 256) ? 3 : 4;     // 192 KB in flight
   static constexpr int STG_CHUNK = 32 * 32 * 4;          // one 32 x 32 fp32 chunk (the source box of a TMA store)
-  static constexpr int STG_WARP = 2 * STG_CHUNK;         // double-buffered per epilogue warp
+  static constexpr int STG_WARP = STG_CHUNK;             // one staging chunk per epilogue warp
   static constexpr int SMEM = STAGES * STAGE + 8 * STG_WARP + 1024 + 256;
 };
 
@@ -52,6 +56,7 @@ struct PairArgs {
   long long ld_bf;
   int M, N, K;
   int splits;
+  int big_a, big_b;    // operand arrives as one multi-k-block box per stage (needs K % 64 == 0), else 2-D boxes per k-block
   unsigned int* sem;   // [tiles] split hand-over counters (zero on entry, zero again on exit)
 };
 
@@ -65,6 +70,8 @@ __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_constant__ CUtensorMap tm_a,
                                                                  const __grid_constant__ CUtensorMap tm_b,
+                                                                 const __grid_constant__ CUtensorMap tm_a2,
+                                                                 const __grid_constant__ CUtensorMap tm_b2,
                                                                  const __grid_constant__ CUtensorMap tm_of,
                                                                  const __grid_constant__ CUtensorMap tm_ob,
                                                                  PairArgs g) {
@@ -86,10 +93,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
   const int tiles = ((g.M + 255) / 256) * num_nt;
   const int items = tiles * g.splits;
   const int num_kb = (g.K + P_BK - 1) / P_BK;
+  const int num_kp = (num_kb + Cfg::KBS - 1) / Cfg::KBS;   // stages (k-block pairs) over K
 
   if (warp == 0 && lane == 0) {
-    ptx::prefetch_tensormap(&tm_a);
-    ptx::prefetch_tensormap(&tm_b);
+    ptx::prefetch_tensormap(g.big_a ? &tm_a2 : &tm_a);
+    ptx::prefetch_tensormap(g.big_b ? &tm_b2 : &tm_b);
     for (int s = 0; s < Cfg::STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
@@ -118,27 +126,46 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
       const int split = w / tiles, tile = w - split * tiles;
       const int m0 = (tile / num_nt) * 256 + static_cast<int>(rank) * 128;
       const int n0 = (tile % num_nt) * BN + static_cast<int>(rank) * (BN / 2);
-      const int kb0 = static_cast<int>(static_cast<long long>(num_kb) * split / g.splits);
-      const int kb1 = static_cast<int>(static_cast<long long>(num_kb) * (split + 1) / g.splits);
-      for (int kb = kb0; kb < kb1; ++kb) {
+      const int kp0 = static_cast<int>(static_cast<long long>(num_kp) * split / g.splits);
+      const int kp1 = static_cast<int>(static_cast<long long>(num_kp) * (split + 1) / g.splits);
+      for (int kp = kp0; kp < kp1; ++kp) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sa = smem + stage * Cfg::STAGE;
-        uint8_t* sb = sa + Cfg::A_TILE;
+        uint8_t* sb = sa + Cfg::KBS * Cfg::A_TILE;
         const uint32_t lf = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);   // the leader's barrier
-        const int k0 = kb * P_BK;
+        const int kb = kp * Cfg::KBS;
         if (ptx::elect_one()) {
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::STAGE);
-          if (A_MN) {
-            ptx::tma_load_2d_pair(sa, &tm_a, lf, m0, k0);
-            ptx::tma_load_2d_pair(sa + 8192, &tm_a, lf, m0 + 64, k0);
+          if (g.big_a) {
+            if (A_MN) ptx::tma_load_4d_pair(sa, &tm_a2, lf, 0, 0, m0 >> 6, kb);
+            else ptx::tma_load_3d_pair(sa, &tm_a2, lf, 0, m0, kb);
           } else {
-            ptx::tma_load_2d_pair(sa, &tm_a, lf, k0, m0);
-          }
-          if (B_MN) {
 #pragma unroll
-            for (int j = 0; j < BN / 128; ++j) ptx::tma_load_2d_pair(sb + j * 8192, &tm_b, lf, n0 + 64 * j, k0);
+            for (int i = 0; i < Cfg::KBS; ++i) {   // k-blocks beyond K are zero-filled by the tensor map
+              const int k0 = (kb + i) * P_BK;
+              if (A_MN) {
+                ptx::tma_load_2d_pair(sa + i * Cfg::A_TILE, &tm_a, lf, m0, k0);
+                ptx::tma_load_2d_pair(sa + i * Cfg::A_TILE + 8192, &tm_a, lf, m0 + 64, k0);
+              } else {
+                ptx::tma_load_2d_pair(sa + i * Cfg::A_TILE, &tm_a, lf, k0, m0);
+              }
+            }
+          }
+          if (g.big_b) {
+            if (B_MN) ptx::tma_load_4d_pair(sb, &tm_b2, lf, 0, 0, n0 >> 6, kb);
+            else ptx::tma_load_3d_pair(sb, &tm_b2, lf, 0, n0, kb);
           } else {
-            ptx::tma_load_2d_pair(sb, &tm_b, lf, k0, n0);
+#pragma unroll
+            for (int i = 0; i < Cfg::KBS; ++i) {
+              const int k0 = (kb + i) * P_BK;
+              if (B_MN) {
+#pragma unroll
+                for (int j = 0; j < BN / 128; ++j)
+                  ptx::tma_load_2d_pair(sb + i * Cfg::B_TILE + j * 8192, &tm_b, lf, n0 + 64 * j, k0);
+              } else {
+                ptx::tma_load_2d_pair(sb + i * Cfg::B_TILE, &tm_b, lf, k0, n0);
+              }
+            }
           }
         }
         __syncwarp();
@@ -159,23 +186,26 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
       int it = 0;
       for (int w = pair; w < items; w += num_pairs, ++it) {
         const int split = w / tiles;
-        const int kb0 = static_cast<int>(static_cast<long long>(num_kb) * split / g.splits);
-        const int kb1 = static_cast<int>(static_cast<long long>(num_kb) * (split + 1) / g.splits);
+        const int kp0 = static_cast<int>(static_cast<long long>(num_kp) * split / g.splits);
+        const int kp1 = static_cast<int>(static_cast<long long>(num_kp) * (split + 1) / g.splits);
         const int acc = it & 1;
         ptx::mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);   // both epilogues drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = kb0; kb < kb1; ++kb) {
+        for (int kp = kp0; kp < kp1; ++kp) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
           const uint32_t sa = ptx::smem_u32(smem + stage * Cfg::STAGE);
-          const uint32_t sb = sa + Cfg::A_TILE;
+          const uint32_t sb = sa + Cfg::KBS * Cfg::A_TILE;
           if (ptx::elect_one()) {
 #pragma unroll
-            for (int kk = 0; kk < P_BK / 16; ++kk) {
-              const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * A_STEP, A_LBO, 1024);
-              const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * B_STEP, B_LBO, 1024);
-              ptx::umma_f16_pair(d_tmem, da, db, idesc, (kb > kb0) || (kk > 0));
+            for (int i = 0; i < Cfg::KBS; ++i) {
+#pragma unroll
+              for (int kk = 0; kk < P_BK / 16; ++kk) {
+                const uint64_t da = ptx::make_smem_desc_sw128(sa + i * Cfg::A_TILE + kk * A_STEP, A_LBO, 1024);
+                const uint64_t db = ptx::make_smem_desc_sw128(sb + i * Cfg::B_TILE + kk * B_STEP, B_LBO, 1024);
+                ptx::umma_f16_pair(d_tmem, da, db, idesc, (kp > kp0) || (i > 0) || (kk > 0));
+              }
             }
             ptx::umma_commit_pair(&empty_bar[stage], 3);   // frees this stage in BOTH CTAs
           }
@@ -203,7 +233,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
       if (g.out_bf) ptx::prefetch_tensormap(&tm_ob);
     }
     int it = 0;
-    int buf = 0;
     for (int w = pair; w < items; w += num_pairs, ++it) {
       const int split = w / tiles, tile = w - split * tiles;
       const int row0 = (tile / num_nt) * 256 + static_cast<int>(rank) * 128 + q * 32;
@@ -264,12 +293,12 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
             }
           }
         }
-        // Every store is its own bulk group and the two staging buffers alternate, so "at most one group still
-        // reading" means the buffer about to be overwritten (used two stores ago) is free.
+        // one staging chunk per warp: the previous store must have finished READING it (its writes may still be in
+        // flight) before it is overwritten
         if (g.out_f32) {
-          if (lane == 0) ptx::bulk_wait_read<1>();
+          if (lane == 0) ptx::bulk_wait_read<0>();
           __syncwarp();
-          const uint32_t sb = stg + buf * Cfg::STG_CHUNK;
+          const uint32_t sb = stg;
           // row r of the box at r * 128 bytes, its 16-byte chunk j at position j ^ (r & 7): SWIZZLE_128B
 #pragma unroll
           for (int j = 0; j < 8; ++j)
@@ -281,12 +310,11 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
             else ptx::tma_reduce_add_2d(&tm_of, sb, col0, row0);
             ptx::bulk_commit();
           }
-          buf ^= 1;
         }
         if (g.out_bf) {
-          if (lane == 0) ptx::bulk_wait_read<1>();
+          if (lane == 0) ptx::bulk_wait_read<0>();
           __syncwarp();
-          const uint32_t sb = stg + buf * Cfg::STG_CHUNK;
+          const uint32_t sb = stg;
           // bf16 box: 64-byte rows, not swizzled
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -304,7 +332,6 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
             ptx::tma_store_2d(&tm_ob, sb, col0, row0);
             ptx::bulk_commit();
           }
-          buf ^= 1;
         }
       }
       if (g.splits > 1) {
@@ -334,8 +361,8 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
 }
 
 template <int BN, bool A_MN, bool B_MN>
-cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tof, const CUtensorMap& tob,
-                        const PairArgs& g, int pairs, cudaStream_t s) {
+cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& ta2, const CUtensorMap& tb2,
+                        const CUtensorMap& tof, const CUtensorMap& tob, const PairArgs& g, int pairs, cudaStream_t s) {
   using Cfg = PairCfg<BN>;
   auto kern = gemm_pair_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
@@ -356,19 +383,19 @@ cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  return cudaLaunchKernelEx(&cfg, kern, ta, tb, tof, tob, g);
+  return cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, tb2, tof, tob, g);
 }
 
 template <int BN>
 cudaError_t launch_pair_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb,
-                              const CUtensorMap& tof, const CUtensorMap& tob, const PairArgs& g, int pairs,
-                              cudaStream_t s) {
+                              const CUtensorMap& ta2, const CUtensorMap& tb2, const CUtensorMap& tof,
+                              const CUtensorMap& tob, const PairArgs& g, int pairs, cudaStream_t s) {
   if (a_mn) {
-    if (b_mn) return launch_pair<BN, true, true>(ta, tb, tof, tob, g, pairs, s);
-    return launch_pair<BN, true, false>(ta, tb, tof, tob, g, pairs, s);
+    if (b_mn) return launch_pair<BN, true, true>(ta, tb, ta2, tb2, tof, tob, g, pairs, s);
+    return launch_pair<BN, true, false>(ta, tb, ta2, tb2, tof, tob, g, pairs, s);
   }
-  if (b_mn) return launch_pair<BN, false, true>(ta, tb, tof, tob, g, pairs, s);
-  return launch_pair<BN, false, false>(ta, tb, tof, tob, g, pairs, s);
+  if (b_mn) return launch_pair<BN, false, true>(ta, tb, ta2, tb2, tof, tob, g, pairs, s);
+  return launch_pair<BN, false, false>(ta, tb, ta2, tb2, tof, tob, g, pairs, s);
 }
 
 }  // namespace
@@ -411,6 +438,13 @@ VqaStatus gemm_pair_launch(const VqaGemmDesc& d, int num_sms, int bn, int splits
                                 : cached_tmap(&ta, d.a_hi, d.K, d.M, d.lda, 64, 128)) &&
                   (d.b_mn_major ? cached_tmap(&tb, d.b_hi, d.N, d.K, d.ldb, 64, 64)
                                 : cached_tmap(&tb, d.b_hi, d.K, d.N, d.ldb, 64, bn / 2));
+  // multi-k-block boxes (one TMA operation per operand per stage) whenever nothing inside a k-block needs clipping
+  CUtensorMap ta2 = ta, tb2 = tb;
+  const bool big = (d.K % 64) == 0 && !getenv("VQA_PAIR_SMALL_BOXES");
+  const bool big_a = big && (d.a_mn_major ? cached_tmap_mnblocks(&ta2, d.a_hi, d.M, d.K, d.lda, 2, 2)
+                                          : cached_tmap_kblocks(&ta2, d.a_hi, d.K, d.M, d.lda, 128, 2));
+  const bool big_b = big && (d.b_mn_major ? cached_tmap_mnblocks(&tb2, d.b_hi, d.N, d.K, d.ldb, bn / 128, 2)
+                                          : cached_tmap_kblocks(&tb2, d.b_hi, d.K, d.N, d.ldb, bn / 2, 2));
   CUtensorMap tof = ta, tob = ta;   // placeholders when an output is absent (never dereferenced)
   const bool ok2 = (!d.out_f32 || cached_tmap_kind(&tof, d.out_f32, 1, d.N, d.M, d.ld_f32, 32, 32)) &&
                    (!d.out_hi || cached_tmap_kind(&tob, d.out_hi, 2, d.N, d.M, d.ld_bf, 32, 32));
@@ -420,6 +454,7 @@ VqaStatus gemm_pair_launch(const VqaGemmDesc& d, int num_sms, int bn, int splits
   g.out_f32 = d.out_f32; g.ld_f32 = d.ld_f32;
   g.out_bf = static_cast<bf16*>(d.out_hi); g.ld_bf = d.ld_bf;
   g.M = d.M; g.N = d.N; g.K = d.K; g.splits = splits;
+  g.big_a = big_a; g.big_b = big_b;
 
   const long long tiles = static_cast<long long>((d.M + 255) / 256) * ((d.N + bn - 1) / bn);
   g.sem = nullptr;
@@ -433,8 +468,8 @@ VqaStatus gemm_pair_launch(const VqaGemmDesc& d, int num_sms, int bn, int splits
   int pairs = num_sms / 2;
   if (items < pairs) pairs = static_cast<int>(items);
   const bool amn = d.a_mn_major != 0, bmn = d.b_mn_major != 0;
-  cudaError_t e = bn == 256 ? launch_pair_major<256>(amn, bmn, ta, tb, tof, tob, g, pairs, stream)
-                            : launch_pair_major<128>(amn, bmn, ta, tb, tof, tob, g, pairs, stream);
+  cudaError_t e = bn == 256 ? launch_pair_major<256>(amn, bmn, ta, tb, ta2, tb2, tof, tob, g, pairs, stream)
+                            : launch_pair_major<128>(amn, bmn, ta, tb, ta2, tb2, tof, tob, g, pairs, stream);
   if (e != cudaSuccess) return set_cuda_error(e, "vqa_gemm (pair) launch");
   count_launch();
   return VQA_OK;

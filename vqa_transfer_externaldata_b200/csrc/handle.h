@@ -103,6 +103,7 @@ struct VqaHandle_t {
   bool aux_created;
   // optional per-phase timing
   bool profile;
+  bool profile_overlapped;   // events are recorded but the branches still fork: sections of the main stream's critical path
   cudaEvent_t ev[VQA_NUM_PHASES][2];
   bool ev_created;
   bool ev_used[VQA_NUM_PHASES];

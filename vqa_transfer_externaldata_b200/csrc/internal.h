@@ -65,6 +65,9 @@ bool cached_tmap(CUtensorMap_st* out, const void* base, uint64_t inner, uint64_t
 // K-major bf16 [rows, K] as {64 k, rows, k-blocks}: box {64, box_rows, box_kb} = box_kb swizzled k-block tiles per TMA
 bool cached_tmap_kblocks(CUtensorMap_st* out, const void* base, uint64_t K, uint64_t rows, uint64_t pitch,
                          uint32_t box_rows, uint32_t box_kb);
+// MN-major bf16 [K, MN] as {64 mn, 64 k, mn-blocks, k-blocks}: box {64, 64, box_mnb, box_kb} (K % 64 == 0)
+bool cached_tmap_mnblocks(CUtensorMap_st* out, const void* base, uint64_t MN, uint64_t K, uint64_t pitch,
+                          uint32_t box_mnb, uint32_t box_kb);
 bool cached_tmap_kind(CUtensorMap_st* out, const void* base, int kind, uint64_t inner, uint64_t outer,
                       uint64_t pitch, uint32_t box_inner, uint32_t box_outer);
 
@@ -176,6 +179,10 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
 VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precision, float keep,
                           float* partials, cudaStream_t s);
 size_t attn_bwd_partial_floats(int batch, int D);
+// attn_pipe.cu: persistent, software-pipelined forward (bf16 mode, buffers must fit one SM)
+bool attn_fwd_pipe_supported(int K, int D, int Dv, int precision, bool has_v_lo, size_t* smem_out, int* rv_out);
+VqaStatus attn_fwd_pipe_launch(const VqaAttnFwd& a, int K, int D, int Dv, float keep, size_t smem, int rv,
+                               int num_sms, cudaStream_t s);
 
 // ---- loss.cu ----
 VqaStatus bce_metrics_launch(int batch, int A, int num_train_answer, int use_train_mask,

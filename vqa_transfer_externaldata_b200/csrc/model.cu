@@ -71,14 +71,14 @@ VqaStatus check_ready(VqaHandle h, const char* who) {
 // fork an independent branch onto auxiliary stream i (returns the caller's stream when serialised for
 // per-phase profiling); join makes the caller's stream wait for it
 VqaStatus fork_stream(VqaHandle h, int i, cudaStream_t s, cudaStream_t* out) {
-  if (h->profile) { *out = s; return VQA_OK; }
+  if (h->profile && !h->profile_overlapped) { *out = s; return VQA_OK; }
   VQA_CUDA_CHECK(cudaEventRecord(h->ev_fork[i], s));
   VQA_CUDA_CHECK(cudaStreamWaitEvent(h->aux[i], h->ev_fork[i], 0));
   *out = h->aux[i];
   return VQA_OK;
 }
 VqaStatus join_stream(VqaHandle h, int i, cudaStream_t s) {
-  if (h->profile) return VQA_OK;
+  if (h->profile && !h->profile_overlapped) return VQA_OK;
   VQA_CUDA_CHECK(cudaEventRecord(h->ev_join[i], h->aux[i]));
   VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_join[i], 0));
   return VQA_OK;
@@ -160,7 +160,8 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, st));
     return VQA_OK;
   };
-  if (!h->profile) {
+  const bool serial = h->profile && !h->profile_overlapped;
+  if (!serial) {
     VQA_TRY(fork_stream(h, 0, s, &s1));
     VQA_TRY(gru_inputs(s1));
   }
@@ -183,7 +184,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_END(VQA_PH_VPROJ_FWD);
   VQA_TRY(join_stream(h, 0, s));
   PH_BEGIN(VQA_PH_GRU_FWD);
-  if (h->profile) VQA_TRY(gru_inputs(s));  // serialised for per-phase timing
+  if (serial) VQA_TRY(gru_inputs(s));  // serialised for per-phase timing
   // a2: the recurrent part of the GRU
   const bool persistent = gru_persistent_supported(Bn, L, c.precision, h->num_sms);
   if (persistent) {
@@ -474,7 +475,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       }
       return VQA_OK;
     };
-    if (h->profile) {  // serialised, one phase after the other
+    if (h->profile && !h->profile_overlapped) {  // serialised, one phase after the other
       PH_BEGIN(VQA_PH_VPROJ_WGRAD);
       VQA_TRY(vproj_wgrad(s));
       PH_END(VQA_PH_VPROJ_WGRAD);
@@ -487,7 +488,8 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       VQA_TRY(embed_bwd(s));
       PH_END(VQA_PH_EMBED_BWD);
     } else {
-      // five independent branches
+      // five independent branches (profile mode 2 times the whole section as GRU_WGRAD on the main stream)
+      PH_BEGIN(VQA_PH_GRU_WGRAD);
       cudaStream_t a0, a1, a2, a3;
       VQA_TRY(fork_stream(h, 0, s, &a0));
       VQA_TRY(fork_stream(h, 1, s, &a1));
@@ -502,6 +504,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       VQA_TRY(join_stream(h, 1, s));
       VQA_TRY(join_stream(h, 2, s));
       VQA_TRY(join_stream(h, 3, s));
+      PH_END(VQA_PH_GRU_WGRAD);
     }
   } else {
     PH_BEGIN(VQA_PH_VPROJ_WGRAD);
