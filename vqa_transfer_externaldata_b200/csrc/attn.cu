@@ -698,7 +698,7 @@ static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv,
 }
 
 VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precision, float keep,
-                          float* partials, cudaStream_t s) {
+                          float* partials, cudaStream_t s, cudaStream_t reduce_stream, cudaEvent_t kernel_done) {
   if (a.batch == 0) return VQA_OK;
   if (!a.z || !a.gamma || !a.beta || !a.hq || !a.att_w || !a.nbox || !a.v_hi || !a.att || !a.ln_mean ||
       !a.ln_rstd || !a.d_pooled || !a.dz_hi || !a.d_hq || !partials)
@@ -722,7 +722,13 @@ VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precisi
             : launch_bwd<bf16, 1>(g, a.batch, K, D, Dv, keep, thr, s);
   if (e != cudaSuccess) return set_cuda_error(e, "attn_bwd launch");
   count_launch();
-  // reduce the per-sample partials: [dw | dgamma | dbeta | dbias | db]
+  // reduce the per-sample partials: [dw | dgamma | dbeta | dbias | db] -- nothing downstream but the optimizer
+  // reads them, so the caller may move this off the critical path
+  if (reduce_stream && kernel_done) {
+    VQA_CUDA_CHECK(cudaEventRecord(kernel_done, s));
+    VQA_CUDA_CHECK(cudaStreamWaitEvent(reduce_stream, kernel_done, 0));
+    s = reduce_stream;
+  }
   const int width = 4 * D + 8;
   float* reduced = partials + static_cast<size_t>(a.batch) * width;
   VQA_TRY(colsum_launch(partials, a.batch, width, width, reduced, reduced + width, s));

@@ -120,6 +120,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   planes(b.dzl, B * L);
   b.dP = a.take<float>(B * Dv);
   b.dq = a.take<float>(B * L);
+  b.dq2 = a.take<float>(B * L);
   b.dhq = a.take<float>(B * D);
   b.dzq_f32 = a.take<float>(B * D);
   planes(b.dzq, B * D);

@@ -62,6 +62,7 @@ struct GruArgs {
   float* r; float* u; float* c;  // [T*B, L]
   // backward
   const float* dq;   // [B, L] gradient of the final state
+  const float* dq2;  // optional second addend
   bf16* dG_bf;       // [T*B, 2L]
   bf16* dC_bf;       // [T*B, L]
   float* bias_part;  // [ceil(B/128), 3L] per-row-tile partial sums of (d gates_bias | d candidate_bias)
@@ -515,7 +516,10 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
               hh[rr] = __ldg(g.h_f32 + o);
               uv[rr] = __ldg(g.u + o);
               cv[rr] = __ldg(g.c + o);
-              if (!mm) dhp[rr] = __ldg(g.dq + static_cast<long long>(row) * L + unit);
+              if (!mm) {
+                dhp[rr] = __ldg(g.dq + static_cast<long long>(row) * L + unit);
+                if (g.dq2) dhp[rr] += __ldg(g.dq2 + static_cast<long long>(row) * L + unit);
+              }
             }
           }
           if (mm) {
@@ -786,7 +790,7 @@ VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cuda
   GruArgs g{};
   g.B = B; g.row0 = 0; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
   g.h_f32 = const_cast<float*>(a.h_f32); g.r = const_cast<float*>(a.r); g.u = const_cast<float*>(a.u);
-  g.c = const_cast<float*>(a.c); g.dq = a.dq; g.dG_bf = a.dG_bf; g.dC_bf = a.dC_bf; g.bias_part = a.bias_part;
+  g.c = const_cast<float*>(a.c); g.dq = a.dq; g.dq2 = a.dq2; g.dG_bf = a.dG_bf; g.dC_bf = a.dC_bf; g.bias_part = a.bias_part;
   return launch_persistent<1>(a.dC_bf, L, static_cast<uint64_t>(T) * B, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B,
                               tm_wc, tm_wg, g, num_sms, s);
 }

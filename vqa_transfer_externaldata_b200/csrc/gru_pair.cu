@@ -59,7 +59,7 @@ struct PairGruArgs {
   const float* xg; const float* xc;
   float* h_f32; bf16* h_bf; bf16* rh_bf;
   float* r; float* u; float* c;
-  const float* dq;
+  const float* dq; const float* dq2;
   bf16* dG_bf; bf16* dC_bf;
   float* bias_part;        // [2 * row tiles, 3L]
   int kbs;                 // k-blocks per stage / TMA operation (4, 2 or 1)
@@ -534,7 +534,15 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
             if (tp > 0) load8f(g.h_f32 + o, hh);
             load8f(g.u + o, uv);
             load8f(g.c + o, cv);
-            if (!mm) load8f(g.dq + static_cast<long long>(row) * L + unit, dhp);
+            if (!mm) {
+              load8f(g.dq + static_cast<long long>(row) * L + unit, dhp);
+              if (g.dq2) {
+                float d2[NU];
+                load8f(g.dq2 + static_cast<long long>(row) * L + unit, d2);
+#pragma unroll
+                for (int j = 0; j < NU; ++j) dhp[j] += d2[j];
+              }
+            }
           }
           if (mm) {
             ptx::mbar_wait(tmem_full_bar, tfull_phase);
@@ -690,7 +698,7 @@ cudaError_t gru_pair_bwd(const GruBwdPersistent& a, cudaStream_t s) {
   PairGruArgs g{};
   g.B = B; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
   g.h_f32 = const_cast<float*>(a.h_f32); g.r = const_cast<float*>(a.r); g.u = const_cast<float*>(a.u);
-  g.c = const_cast<float*>(a.c); g.dq = a.dq; g.dG_bf = a.dG_bf; g.dC_bf = a.dC_bf; g.bias_part = a.bias_part;
+  g.c = const_cast<float*>(a.c); g.dq = a.dq; g.dq2 = a.dq2; g.dG_bf = a.dG_bf; g.dC_bf = a.dC_bf; g.bias_part = a.bias_part;
   g.trace = g_gru_trace ? g_gru_trace + (1 << 17) : nullptr;
   g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
   g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;

@@ -55,7 +55,8 @@ struct Buffers {
   float* dzp_f32; Planes dzp;        // [B, L]
   float* dzl_f32; Planes dzl;        // [B, L]
   float* dP;       // [B, Dv]
-  float* dq;       // [B, L]
+  float* dq;       // [B, L]  from q_linear_l
+  float* dq2;      // [B, L]  from q_linear_v (the BPTT kernels add the two)
   float* dhq;      // [B, D]
   float* dzq_f32; Planes dzq;        // [B, D]
   Planes dzv;      // [B*K, D]

@@ -117,6 +117,7 @@ struct GruBwdPersistent {
   unsigned int* counter;
   const float* h_f32; const float* r; const float* u; const float* c;
   const float* dq;                       // [B, L] gradient of the final state
+  const float* dq2;                      // optional second addend of that gradient (the two heads reading q)
   bf16* dG_bf;                           // [T*B, 2L]
   bf16* dC_bf;                           // [T*B, L]
   float* bias_part;                      // [2 * ceil(B/128), 3L] partial bias gradients (gates r | gates u | candidate)
@@ -176,8 +177,11 @@ VqaStatus row_ln_relu_bwd_launch(const RowLnBwd& a, cudaStream_t s);
 // ---- attn.cu ----
 VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precision, float keep,
                           cudaStream_t s);
+// reduce_stream: where the reduction of the per-sample partials (d att_w / gamma / beta / bias / att_b) runs; the
+// caller has made it wait for nothing -- attn_bwd_launch orders it after the kernel itself (nullptr = s)
 VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precision, float keep,
-                          float* partials, cudaStream_t s);
+                          float* partials, cudaStream_t s, cudaStream_t reduce_stream = nullptr,
+                          cudaEvent_t kernel_done = nullptr);
 size_t attn_bwd_partial_floats(int batch, int D);
 // attn_pipe.cu: persistent, software-pipelined forward (bf16 mode, buffers must fit one SM)
 bool attn_fwd_pipe_supported(int K, int D, int Dv, int precision, bool has_v_lo, size_t* smem_out, int* rv_out);

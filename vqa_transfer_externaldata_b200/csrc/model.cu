@@ -367,11 +367,14 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     a.ln_mean = b.lnv_mean; a.ln_rstd = b.lnv_rstd; a.d_pooled = b.dP; a.dz_hi = b.dzv.hi;
     a.dz_lo = b.dzv.lo; a.d_hq = b.dhq; a.d_att_w = g->att_w; a.d_att_b = g->att_b;
     a.d_gamma = g->v_gamma; a.d_beta = g->v_beta; a.d_bias = g->v_b;
-    VQA_TRY(attn_bwd_launch(a, K, D, Dv, c.precision, c.keep_att, b.attn_part, s));
+    const bool side = !(h->profile && !h->profile_overlapped);
+    VQA_TRY(attn_bwd_launch(a, K, D, Dv, c.precision, c.keep_att, b.attn_part, s, side ? h->aux[3] : nullptr,
+                            side ? h->ev_fork[3] : nullptr));
   }
   PH_END(VQA_PH_ATTN_BWD);
   PH_BEGIN(VQA_PH_QV_BWD);
-  // q_linear_v backward
+  // q_linear_v backward. Only the data gradient dq2 = dZqv Wqv^T is on the critical path (the BPTT kernel adds it to
+  // dq itself); the parameter gradients go to auxiliary stream 3, which the weight-gradient section joins later.
   {
     RowLnBwd r{};
     r.rows = Bn; r.N = D; r.dout = b.dhq; r.z = b.zq; r.gamma = p->qv_gamma; r.beta = p->qv_beta;
@@ -379,12 +382,28 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.dz_lo = b.dzq.lo;
     if (g->qv_gamma || g->qv_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
     VQA_TRY(row_ln_relu_bwd_launch(r, s));
-    if (g->qv_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, D, D, g->qv_gamma, b.scratch, s));
-    if (g->qv_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, D, D, g->qv_beta, b.scratch, s));
   }
-  if (g->qv_w) VQA_TRY(GemmB(L, D, Bn).a(b.h, q_off, L, true).b(b.dzq, 0, D, true).f32(g->qv_w, D).run(h, s));
-  if (g->qv_b) VQA_TRY(colsum_launch(b.dzq_f32, Bn, D, D, g->qv_b, b.scratch, s));
-  VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
+  {
+    cudaStream_t sp = s;
+    float* scr = b.scratch;
+    const bool side = !(h->profile && !h->profile_overlapped);
+    if (side) {
+      // aux[3] may still be reducing the attention partials: stream order keeps both correct
+      VQA_CUDA_CHECK(cudaEventRecord(h->ev_fork[3], s));
+      VQA_CUDA_CHECK(cudaStreamWaitEvent(h->aux[3], h->ev_fork[3], 0));
+      sp = h->aux[3];
+      scr = b.scratch + 4 * b.scratch_floats;
+    }
+    if (g->qv_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, D, D, g->qv_gamma, scr, sp));
+    if (g->qv_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, D, D, g->qv_beta, scr, sp));
+    if (g->qv_w) VQA_TRY(GemmB(L, D, Bn).a(b.h, q_off, L, true).b(b.dzq, 0, D, true).f32(g->qv_w, D).run(h, sp));
+    if (g->qv_b) VQA_TRY(colsum_launch(b.dzq_f32, Bn, D, D, g->qv_b, scr, sp));
+  }
+  if (gru_persistent_supported(Bn, L, c.precision, h->num_sms)) {
+    VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).f32(b.dq2, L).run(h, s));
+  } else {  // the per-step fallback kernels take one gradient tensor: accumulate into dq
+    VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
+  }
   PH_END(VQA_PH_QV_BWD);
   // dWv = V^T dZv (the largest weight gradient: [Dv, D] over B*K rows). Independent of everything below: it
   // runs on an auxiliary stream next to the GRU weight-gradient GEMMs (after BPTT, whose cooperative grid
@@ -404,7 +423,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       // one cooperative launch: head of step T-1 from dq, then all 2T-1 dependent matmuls
       GruBwdPersistent a{};
       a.B = Bn; a.L = L; a.T = T; a.q_len = batch->q_intseq_len; a.counter = b.gru_counter;
-      a.h_f32 = b.h_f32; a.r = b.r; a.u = b.u; a.c = b.c; a.dq = dh_cur;
+      a.h_f32 = b.h_f32; a.r = b.r; a.u = b.u; a.c = b.c; a.dq = dh_cur; a.dq2 = b.dq2;   // dq (q_linear_l) + dq2 (q_linear_v)
       a.dG_bf = b.dG.hi; a.dC_bf = b.dC.hi; a.bias_part = b.gru_bias_part;
       a.wg_h = b.w.gru_gates_w.hi + static_cast<long long>(W) * 2 * L;
       a.wc_h = b.w.gru_cand_w.hi + static_cast<long long>(W) * L;
