@@ -110,16 +110,33 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
       {p->joint_w, &w.joint_w, c.L, c.J},
       {p->ans_w, &w.ans_w, c.J, c.A},
   };
+  // the refreshes are independent small memory-bound kernels: spread them over the auxiliary streams instead of
+  // queueing them behind one another (they sit between the optimizer and the next step's first GEMM)
+  int lane_i = 0;
+  bool forked[VqaHandle_t::kAux] = {};
+  cudaStream_t gru_stream = s;
   for (auto& it : items) {
     if (!it.src) {
       if (!h->params_ready) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: the first call needs every weight");
       continue;  // unchanged since the last call
     }
-    VQA_TRY(split_bf16_launch(it.src, it.rows, it.cols, it.cols, it.dst->hi, it.dst->lo, it.cols, s));
+    const bool is_gru = it.src == p->gru_gates_w || it.src == p->gru_cand_w;
+    int ai = is_gru ? 0 : 1 + (lane_i++ % (VqaHandle_t::kAux - 1));   // both GRU matrices on aux 0: the pack follows them
+    cudaStream_t st;
+    if (!forked[ai]) {
+      VQA_TRY(fork_stream(h, ai, s, &st));
+      forked[ai] = true;
+    } else {
+      st = (h->profile && !h->profile_overlapped) ? s : h->aux[ai];
+    }
+    if (is_gru) gru_stream = st;
+    VQA_TRY(split_bf16_launch(it.src, it.rows, it.cols, it.cols, it.dst->hi, it.dst->lo, it.cols, st));
   }
   if ((p->gru_gates_w || p->gru_cand_w) && gru_persistent_supported(c.B, c.L, c.precision, h->num_sms))
     VQA_TRY(gru_pack_weights_launch(w.gru_gates_w.hi + static_cast<long long>(c.W) * 2 * c.L,
-                                    w.gru_cand_w.hi + static_cast<long long>(c.W) * c.L, c.L, h->buf.gru_pack, s));
+                                    w.gru_cand_w.hi + static_cast<long long>(c.W) * c.L, c.L, h->buf.gru_pack, gru_stream));
+  for (int i = 0; i < VqaHandle_t::kAux; ++i)
+    if (forked[i]) VQA_TRY(join_stream(h, i, s));
   h->params_ready = true;
   return VQA_OK;
 }
