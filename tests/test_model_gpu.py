@@ -178,6 +178,58 @@ def test_bf16_reference_shapes_top1():
     assert np.all((got["pred"] == ref["pred"]) | close), agree
 
 
+# ---- the other BASELINE.json configs as parity cases (sizes the oracle finishes in seconds) ----
+def test_cfg2_standard_reference_shapes_bf16():
+    """BASELINE cfg 2: vqa/model_standard (learned reasoning/classifier head, every parameter trainable, no train
+    mask) at the reference's layer sizes."""
+    case = build_case(MID, variant="standard", precision="bf16", seed=10, num_images=40, batch=32)
+    got, ref, ref_g = run_both(case)
+    _check_forward_plain(case, got, BF16_TOL)
+    _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", FP32_TOL), ("bf16", BF16_TOL)])
+def test_cfg3_grid_features_196_cells(precision, tol):
+    """BASELINE cfg 3: attention over 196 cells of 2048-d grid features (the [K, D] slab no longer fits shared
+    memory: the attention kernels take their streaming path), all cells valid."""
+    dims = dict(B=8, K=196, Dv=2048, D=1024, L=1024, A=3000, T=14, W=300, Vq=512)
+    case = build_case(dims, precision=precision, seed=11, num_images=8, ragged=False)
+    got, ref, ref_g = run_both(case)
+    if precision == "bf16":
+        _check_forward_plain(case, got, tol)
+    _check(case, got, ref, ref_g, tol, exact_pred=precision == "fp32")
+
+
+@pytest.mark.parametrize("batch", [64, 37, 1])
+def test_cfg5_masked_inference_100_boxes(batch):
+    """BASELINE cfg 5: forward-only inference, K = 100 padded boxes with 10..100 valid per image, full and tail
+    batches: logits / attention / pooled within tolerance, zero attention beyond nbox, top-1 agreement."""
+    dims = dict(B=64, K=100, Dv=2048, D=1024, L=1024, A=3000, T=14, W=300, Vq=512)
+    case = build_case(dims, precision="bf16", seed=12, num_images=80, batch=batch)
+    nb = case["nb"]
+    assert nb.min() >= 1 and nb.max() <= 100
+    eng = case["eng"]
+    eng.stage_batch(case["batch"])
+    eng.forward(seed=5, step=2)
+    att_mask, joint_mask = eng.dropout_masks(5, 2)
+    torch.cuda.synchronize()
+    out, _ = O.forward(case["params"], case["feats"], case["nb"], case["batch"], case["m"], variant="vlmap_answer",
+                       keep_att=0.8, keep_joint=0.5, att_mask=att_mask.cpu().numpy(),
+                       joint_mask=joint_mask.cpu().numpy())
+    got = {k: v.detach().cpu().numpy() for k, v in eng.outputs().items()}
+    live = case["m"]["exist"] > 0
+    assert got["logit"].shape == (batch, 3000)
+    assert rel_err(got["logit"][:, live], out["logit"][:, live]) < BF16_TOL
+    assert rel_err(got["att_score"], out["att_score"]) < BF16_TOL
+    nbox = nb[case["batch"]["image_idx"]]
+    for b in range(batch):
+        assert np.all(got["att_score"][b, nbox[b]:] == 0.0)
+        assert abs(got["att_score"][b].sum() - 1.0) < 1e-3
+    srt = np.sort(out["logit"], axis=1)
+    close = (srt[:, -1] - srt[:, -2]) < BF16_TOL * np.abs(out["logit"][:, live]).max()
+    assert np.all((got["pred"] == out["pred"]) | close)
+
+
 def test_dropout_off_and_loss_scale():
     case = build_case(SMALL, precision="fp32", seed=5, keep_att=1.0, keep_joint=1.0)
     got, ref, ref_g = run_both(case, loss_scale=0.125)
