@@ -207,6 +207,14 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* params, const VqaBa
 
 /* Materialise the dropout masks vqa_forward(seed, step) uses, as 0/1 bytes: att [batch, K, D],
  * joint [batch, J]. Test / parity helper (the kernels regenerate the same bits on the fly). */
+/* Data-parallel overlap (vqa/trainer.py has no distributed code; this is the B200 side of SURVEY 8e).
+ * With early gradients enabled, vqa_backward produces the gradients of everything EXCEPT the embedding and the GRU
+ * (v_linear_v, q_linear_v, the attention score layer, and the trainable heads of model_standard) BEFORE the GRU's
+ * back-propagation through time and records an event there; vqa_stream_wait_early_gradients makes `stream` wait for
+ * that event of the most recent vqa_backward, so an all-reduce of that slice can run under the BPTT kernels. */
+VQA_API VqaStatus vqa_set_early_gradients(VqaHandle h, int32_t enable);
+VQA_API VqaStatus vqa_stream_wait_early_gradients(VqaHandle h, void* stream);
+
 VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step,
                                     uint8_t* att_mask, uint8_t* joint_mask, void* stream);
 

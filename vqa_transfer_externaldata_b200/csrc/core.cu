@@ -219,6 +219,11 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
     }
   }
   h->aux_created = true;
+  h->early_grads = false;
+  if (cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess) {
+    delete h;
+    return set_error(VQA_ERR_CUDA, "vqa_create: could not create the early-gradient event");
+  }
   h->ws_needed = plan_workspace(h, nullptr);
   *out = h;
   return VQA_OK;
@@ -230,6 +235,7 @@ VQA_API VqaStatus vqa_destroy(VqaHandle h) {
       cudaEventDestroy(h->ev[i][0]);
       cudaEventDestroy(h->ev[i][1]);
     }
+  if (h && h->aux_created) cudaEventDestroy(h->ev_early);
   if (h && h->aux_created)
     for (int i = 0; i < VqaHandle_t::kAux; ++i) {
       cudaStreamDestroy(h->aux[i]);

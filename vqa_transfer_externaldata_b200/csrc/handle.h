@@ -102,6 +102,8 @@ struct VqaHandle_t {
   cudaStream_t aux[kAux];
   cudaEvent_t ev_fork[kAux], ev_join[kAux];
   bool aux_created;
+  bool early_grads;        // vqa_set_early_gradients
+  cudaEvent_t ev_early;    // recorded by vqa_backward once the non-GRU gradients are complete
   // optional per-phase timing
   bool profile;
   bool profile_overlapped;   // events are recorded but the branches still fork: sections of the main stream's critical path

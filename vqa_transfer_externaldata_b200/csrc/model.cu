@@ -389,6 +389,10 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
                             side ? h->ev_fork[3] : nullptr));
   }
   PH_END(VQA_PH_ATTN_BWD);
+  // data-parallel runs take dWv here, ahead of the BPTT, so that its all-reduce can overlap the recurrent kernels
+  const bool early = h->early_grads && !(h->profile && !h->profile_overlapped);
+  if (early && g->v_w)
+    VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, s));
   PH_BEGIN(VQA_PH_QV_BWD);
   // q_linear_v backward. Only the data gradient dq2 = dZqv Wqv^T is on the critical path (the BPTT kernel adds it to
   // dq itself); the parameter gradients go to auxiliary stream 3, which the weight-gradient section joins later.
@@ -422,11 +426,16 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
   }
   PH_END(VQA_PH_QV_BWD);
+  if (early) {
+    // every gradient but the embedding's and the GRU's is complete once auxiliary stream 3 has caught up
+    VQA_TRY(join_stream(h, 3, s));
+    VQA_CUDA_CHECK(cudaEventRecord(h->ev_early, s));
+  }
   // dWv = V^T dZv (the largest weight gradient: [Dv, D] over B*K rows). Independent of everything below: it
   // runs on an auxiliary stream next to the GRU weight-gradient GEMMs (after BPTT, whose cooperative grid
   // needs the SMs to itself)
   auto vproj_wgrad = [&](cudaStream_t st) -> VqaStatus {
-    if (g->v_w) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, st));
+    if (g->v_w && !early) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, st));
     return VQA_OK;
   };
   // GRU: back-propagation through time from dq
@@ -547,6 +556,19 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(vproj_wgrad(s));
     PH_END(VQA_PH_VPROJ_WGRAD);
   }
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_set_early_gradients(VqaHandle h, int32_t enable) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_set_early_gradients: null handle");
+  h->early_grads = enable != 0;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_stream_wait_early_gradients(VqaHandle h, void* stream) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_stream_wait_early_gradients: null handle");
+  if (!h->early_grads) return set_error(VQA_ERR_STATE, "vqa_stream_wait_early_gradients: enable early gradients first");
+  VQA_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->ev_early, 0));
   return VQA_OK;
 }
 

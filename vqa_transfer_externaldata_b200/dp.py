@@ -9,12 +9,13 @@ import torch.distributed as dist
 
 
 class DataParallel:
-    def __init__(self, backend=None, bucket_bytes=32 << 20):
+    def __init__(self, backend=None, bucket_bytes=64 << 20):
         self.rank = int(os.environ.get("RANK", "0"))
         self.world_size = int(os.environ.get("WORLD_SIZE", "1"))
         self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
         self.bucket_elems = bucket_bytes // 4
         self.owns_group = False
+        self._side = None
         if self.world_size > 1 and not dist.is_initialized():
             backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
             if backend == "nccl":
@@ -37,7 +38,26 @@ class DataParallel:
             dist.all_reduce(flat[s:min(s + self.bucket_elems, n)], op=dist.ReduceOp.SUM)
 
     def all_reduce_gradients(self, engine):
-        self.all_reduce_flat(engine.params.grad)
+        """One all-reduce(sum) of the trainable gradients. With early gradients enabled on the engine the slice that
+        is complete before the GRU's back-propagation through time (everything but the embedding and the GRU) is
+        reduced on a side stream as soon as the device reaches that point -- under the recurrent kernels -- and only
+        the rest waits for the end of the backward pass."""
+        g = engine.params.grad
+        if self.world_size == 1:
+            return
+        n_early = engine.params.n_early if getattr(engine, "early_gradients", False) else 0
+        if n_early == 0 or dist.get_backend() != "nccl":
+            self.all_reduce_flat(g)
+            return
+        if self._side is None:
+            self._side = torch.cuda.Stream(device=g.device)
+        engine.stream_wait_early_gradients(self._side)
+        with torch.cuda.stream(self._side):
+            w1 = dist.all_reduce(g[:n_early], op=dist.ReduceOp.SUM, async_op=True)
+        w2 = dist.all_reduce(g[n_early:], op=dist.ReduceOp.SUM, async_op=True) if n_early < g.numel() else None
+        w1.wait()
+        if w2 is not None:
+            w2.wait()
 
     def barrier(self):
         if self.world_size > 1:

@@ -90,6 +90,9 @@ def _align(n, a=64):
     return (n + a - 1) // a * a
 
 
+LATE_GRAD_FIELDS = ("embed", "gru_gates_w", "gru_gates_b", "gru_cand_w", "gru_cand_b")
+
+
 class ParamStore:
     """fp32 master parameters in TF layout inside ONE flat device buffer: trainable tensors first (so the
     gradient all-reduce and the fused clip+Adam step run over one contiguous slice), frozen after."""
@@ -97,13 +100,20 @@ class ParamStore:
     def __init__(self, cfg, device):
         self.cfg = cfg
         frozen = frozen_fields(cfg.variant)
-        self.trainable = [f for f in L.PARAM_FIELDS if f not in frozen]
+        trainable = [f for f in L.PARAM_FIELDS if f not in frozen]
+        # gradients complete BEFORE the GRU's BPTT first (everything but the embedding and the GRU): with early
+        # gradients enabled that slice is all-reduced under the recurrent kernels (dp.DataParallel)
+        early = [f for f in trainable if f not in LATE_GRAD_FIELDS]
+        self.trainable = early + [f for f in trainable if f in LATE_GRAD_FIELDS]
         self.frozen = [f for f in L.PARAM_FIELDS if f in frozen]
         self.offsets, off = {}, 0
+        self.n_early = 0
         for f in self.trainable:
             n = int(np.prod(cfg.shape(f)))
             self.offsets[f] = (off, n)
             off += _align(n)  # 256-byte aligned starts (float4 / TMA friendly)
+            if f in early:
+                self.n_early = off
         self.n_train = off
         for f in self.frozen:
             n = int(np.prod(cfg.shape(f)))
@@ -226,6 +236,7 @@ class Engine:
         self.bank = None
         self.masks = None
         self.adam_t = 0
+        self.early_gradients = False
 
     def close(self):
         if self.h:
@@ -388,6 +399,14 @@ class Engine:
         b = self._c_batch()
         L.check(self.lib.vqa_backward(self.h, C.byref(self._p), C.byref(b), C.byref(self._g),
                                       C.c_float(loss_scale), self._stream()))
+
+    def set_early_gradients(self, enable=True):
+        """Data-parallel overlap: produce the non-GRU gradients before the BPTT (vqa_set_early_gradients)."""
+        L.check(self.lib.vqa_set_early_gradients(self.h, int(bool(enable))))
+        self.early_gradients = bool(enable)
+
+    def stream_wait_early_gradients(self, stream):
+        L.check(self.lib.vqa_stream_wait_early_gradients(self.h, C.c_void_p(stream.cuda_stream)))
 
     def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip_norm=20.0):
         """optimize_loss(Adam, clip_gradients=20.0) over the trainable slice (vqa/trainer.py:106-114)."""
