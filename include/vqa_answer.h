@@ -215,6 +215,14 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* params, const VqaBa
 VQA_API VqaStatus vqa_set_early_gradients(VqaHandle h, int32_t enable);
 VQA_API VqaStatus vqa_stream_wait_early_gradients(VqaHandle h, void* stream);
 
+/* In-switch all-reduce(sum) of n floats that every rank holds at the same offset of a symmetric allocation mapped
+ * as one NVSwitch multicast object (`multicast_ptr` = the multicast address of element 0; torch's
+ * _symmetric_memory.rendezvous provides it). Rank r reduces and re-broadcasts elements [r, r + 1) * n / world with
+ * multimem.ld_reduce / multimem.st. The caller must put a cross-rank barrier before (all gradients written) and
+ * after (all slices broadcast) on the same stream. num_ctas = 0 picks a default. */
+VQA_API VqaStatus vqa_multimem_all_reduce(void* multicast_ptr, int64_t n, int32_t rank, int32_t world,
+                                          int32_t num_ctas, void* stream);
+
 VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step,
                                     uint8_t* att_mask, uint8_t* joint_mask, void* stream);
 

@@ -16,6 +16,7 @@ class DataParallel:
         self.bucket_elems = bucket_bytes // 4
         self.owns_group = False
         self._side = None
+        self._mc = None
         if self.world_size > 1 and not dist.is_initialized():
             backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
             if backend == "nccl":
@@ -37,6 +38,29 @@ class DataParallel:
         for s in range(0, n, self.bucket_elems):
             dist.all_reduce(flat[s:min(s + self.bucket_elems, n)], op=dist.ReduceOp.SUM)
 
+    def use_multicast_gradients(self, engine):
+        """Put the engine's flat gradient buffer into symmetric memory mapped as one NVSwitch multicast object, so that
+        all_reduce_gradients can run the library's in-switch all-reduce kernel (vqa_multimem_all_reduce) instead of
+        NCCL's ring. Returns False (and changes nothing) when the platform has no multicast support."""
+        if self.world_size == 1 or not dist.is_initialized() or dist.get_backend() != "nccl":
+            return False
+        if os.environ.get("VQA_DP_MULTICAST", "1") == "0":
+            return False
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            n = (engine.params.n_train + 1023) // 1024 * 1024
+            buf = symm_mem.empty(n, dtype=torch.float32, device=engine.device)
+            hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
+            if not hdl.has_multicast_support or not hdl.multicast_ptr:
+                return False
+        except Exception as e:  # noqa: BLE001 -- any failure here just means "keep using NCCL"
+            if self.rank == 0:
+                print(f"[dp] multicast gradients unavailable ({e!r}); using NCCL all-reduce", flush=True)
+            return False
+        engine.rebind_gradients(buf)
+        self._mc = (hdl, buf, engine.params.n_train)
+        return True
+
     def all_reduce_gradients(self, engine):
         """One all-reduce(sum) of the trainable gradients. With early gradients enabled on the engine the slice that
         is complete before the GRU's back-propagation through time (everything but the embedding and the GRU) is
@@ -44,6 +68,16 @@ class DataParallel:
         the rest waits for the end of the backward pass."""
         g = engine.params.grad
         if self.world_size == 1:
+            return
+        if self._mc is not None:
+            hdl, buf, n = self._mc
+            from . import lib as L
+            n4 = (n + 3) // 4 * 4
+            stream = torch.cuda.current_stream(g.device)
+            hdl.barrier(channel=0)   # every rank's gradients are complete (stream-ordered, system scope)
+            L.check(engine.lib.vqa_multimem_all_reduce(hdl.multicast_ptr, n4, self.rank, self.world_size, 0,
+                                                       stream.cuda_stream))
+            hdl.barrier(channel=1)   # every slice has been broadcast
             return
         n_early = engine.params.n_early if getattr(engine, "early_gradients", False) else 0
         if n_early == 0 or dist.get_backend() != "nccl":

@@ -128,6 +128,14 @@ class ParamStore:
         self.grad_views = {f: self.grad[self.offsets[f][0]:self.offsets[f][0] + self.offsets[f][1]]
                            .view(cfg.shape(f)) for f in self.trainable}
 
+    def rebind_grad(self, new_grad):
+        """Move the flat gradient buffer (e.g. into symmetric memory for the multicast all-reduce)."""
+        assert new_grad.numel() >= self.n_train and new_grad.dtype == torch.float32
+        new_grad[:self.n_train].zero_()
+        self.grad = new_grad[:self.n_train]
+        self.grad_views = {f: self.grad[self.offsets[f][0]:self.offsets[f][0] + self.offsets[f][1]]
+                           .view(self.cfg.shape(f)) for f in self.trainable}
+
     def load(self, params):
         """params: dict field -> array-like (numpy / torch), fp32, TF layout."""
         for f in L.PARAM_FIELDS:
@@ -399,6 +407,11 @@ class Engine:
         b = self._c_batch()
         L.check(self.lib.vqa_backward(self.h, C.byref(self._p), C.byref(b), C.byref(self._g),
                                       C.c_float(loss_scale), self._stream()))
+
+    def rebind_gradients(self, new_grad):
+        """Use `new_grad` (>= n_train fp32 elements) as the flat gradient buffer from now on."""
+        self.params.rebind_grad(new_grad)
+        self._g = self.params.c_grads()
 
     def set_early_gradients(self, enable=True):
         """Data-parallel overlap: produce the non-GRU gradients before the BPTT (vqa_set_early_gradients)."""

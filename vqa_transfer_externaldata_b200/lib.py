@@ -124,6 +124,7 @@ SYMBOLS = {
     "vqa_phase_name": (C.c_char_p, [C.c_int32]),
     "vqa_gemm": (C.c_int32, [_P, C.POINTER(VqaGemmDesc), _P]),
     "vqa_split_bf16": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P]),
+    "vqa_multimem_all_reduce": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vqa_set_early_gradients": (C.c_int32, [_P, C.c_int32]),
     "vqa_stream_wait_early_gradients": (C.c_int32, [_P, _P]),
     "vqa_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaAttnFwd), _P]),

@@ -153,6 +153,8 @@ class Model(object):
         # it. Measured on 8 x B200 it LOSES (1.385 -> 1.439 ms/step): dWv leaves the concurrent weight-gradient
         # section for the critical path and the NCCL kernel delays the cooperative BPTT launch; so it is off.
         import os
+        if dp is not None and dp.world_size > 1:
+            dp.use_multicast_gradients(self.engine)   # in-switch all-reduce when NVSwitch multicast is available
         self.engine.set_early_gradients(dp is not None and dp.world_size > 1 and os.environ.get("VQA_DP_EARLY") == "1")
 
     def forward(self, batch=None, full_outputs=True):
