@@ -49,6 +49,12 @@ def bench(name, M, N, K, a_mn, b_mn, block_n, out="f32", iters=15, do_flush=True
 
 
 P = 74
+if os.environ.get("HEADS"):
+    for (M, N, K, amn, bmn) in ((512, 1024, 1024, False, True), (512, 1024, 2048, False, True), (512, 2048, 1024, False, True),
+                                (512, 3008, 2048, False, True), (512, 2048, 3008, False, False), (512, 1024, 2048, False, False)):
+        bench("head auto", M, N, K, amn, bmn, 0, do_flush=False)
+        bench("head 128x64 per-kb", M, N, K, amn, bmn, 64, do_flush=False)
+    sys.exit(0)
 if os.environ.get("QUICK"):
     bench("one round", 256 * P, 256, 64, False, True, -256)
     bench("four rounds", 256 * P, 1024, 64, False, True, -256)

@@ -45,15 +45,19 @@ struct EpilogueArgs {
   long long ld_bf;
 };
 
-template <int BN, int SPLIT>
+// KBS > 1 (bf16 mode only): a stage holds KBS k-blocks of each operand, [A kb0..kb(KBS-1) | B kb0..], and each
+// operand arrives as ONE multi-k-block TMA box (cached_tmap_kblocks / cached_tmap_mnblocks): an SM completes only
+// ~4 TMA operations per microsecond whatever their size, which is what bounds the latency of the M = 512 heads.
+template <int BN, int SPLIT, int KBS = 1>
 struct GemmCfg {
   static constexpr int A_TILE = BM * BK * 2;                 // bytes per plane
   static constexpr int B_TILE = BN * BK * 2;
   static constexpr int PLANES = (SPLIT == 3) ? 2 : 1;
-  static constexpr int STAGE_BYTES = PLANES * (A_TILE + B_TILE);
+  static constexpr int STAGE_BYTES = KBS * PLANES * (A_TILE + B_TILE);
   // keep <= ~110 KB for the bf16 path so two CTAs fit one SM; the split path takes the SM alone
-  static constexpr int STAGES = (SPLIT == 3) ? (BN == 256 ? 2 : 3)
-                                             : (BN == 256 ? 4 : (BN == 128 ? 3 : 4));
+  static constexpr int STAGES = KBS > 1 ? 2
+                                : (SPLIT == 3) ? (BN == 256 ? 2 : 3)
+                                               : (BN == 256 ? 4 : (BN == 128 ? 3 : 4));
   static constexpr int PIPE_BYTES = STAGES * STAGE_BYTES;
   static constexpr int STG_LD = BN + 4;                      // floats, padded staging row
   static constexpr int STAGING_BYTES = 4 * 32 * STG_LD * 4;  // 4 epilogue warps x 32 rows
@@ -61,12 +65,14 @@ struct GemmCfg {
   static constexpr int SMEM_BYTES = MAIN_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-template <int BN, int SPLIT, bool A_MN, bool B_MN>
+// KBS > 1: tm_a_lo / tm_b_lo carry the multi-k-block maps of the (single) bf16 plane
+template <int BN, int SPLIT, bool A_MN, bool B_MN, int KBS = 1>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
     const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
     EpilogueArgs ep, int M, int N, int K) {
-  using Cfg = GemmCfg<BN, SPLIT>;
+  static_assert(KBS == 1 || SPLIT == 1, "multi-k-block stages exist for the single-plane mode only");
+  using Cfg = GemmCfg<BN, SPLIT, KBS>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -110,12 +116,20 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
     {
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; kb += KBS) {
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         const int k0 = kb * BK;
         if (ptx::elect_one()) {
         ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        if (KBS > 1) {
+          uint8_t* sa = st;
+          uint8_t* sb = st + KBS * Cfg::A_TILE;
+          if (A_MN) ptx::tma_load_4d(sa, &tm_a_lo, &full_bar[stage], 0, 0, m0 >> 6, kb);
+          else ptx::tma_load_3d(sa, &tm_a_lo, &full_bar[stage], 0, m0, kb);
+          if (B_MN) ptx::tma_load_4d(sb, &tm_b_lo, &full_bar[stage], 0, 0, n0 >> 6, kb);
+          else ptx::tma_load_3d(sb, &tm_b_lo, &full_bar[stage], 0, n0, kb);
+        } else
 #pragma unroll
         for (int p = 0; p < Cfg::PLANES; ++p) {
           const CUtensorMap* ta = p ? &tm_a_lo : &tm_a_hi;
@@ -157,24 +171,27 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
       constexpr uint32_t B_LBO = B_MN ? 8192 : 16, B_STEP = B_MN ? 2048 : 32;
       int stage = 0;
       uint32_t phase = 0;
-      for (int kb = 0; kb < num_kb; ++kb) {
+      for (int kb = 0; kb < num_kb; kb += KBS) {
         ptx::mbar_wait(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint32_t st = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-        const uint32_t sa_hi = st, sa_lo = st + Cfg::A_TILE;
-        const uint32_t sb_hi = st + Cfg::PLANES * Cfg::A_TILE, sb_lo = sb_hi + Cfg::B_TILE;
         if (ptx::elect_one()) {
+#pragma unroll
+        for (int i = 0; i < KBS; ++i) {
+        const uint32_t sa_hi = st + i * Cfg::A_TILE, sa_lo = st + Cfg::A_TILE;
+        const uint32_t sb_hi = st + KBS * Cfg::PLANES * Cfg::A_TILE + i * Cfg::B_TILE, sb_lo = sb_hi + Cfg::B_TILE;
 #pragma unroll
         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
           const uint64_t da_hi = ptx::make_smem_desc_sw128(sa_hi + kk * A_STEP, A_LBO, 1024);
           const uint64_t db_hi = ptx::make_smem_desc_sw128(sb_hi + kk * B_STEP, B_LBO, 1024);
-          ptx::umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | kk) != 0);
+          ptx::umma_f16(tmem_base, da_hi, db_hi, idesc, (kb | i | kk) != 0);
           if (SPLIT == 3) {
             const uint64_t da_lo = ptx::make_smem_desc_sw128(sa_lo + kk * A_STEP, A_LBO, 1024);
             const uint64_t db_lo = ptx::make_smem_desc_sw128(sb_lo + kk * B_STEP, B_LBO, 1024);
             ptx::umma_f16(tmem_base, da_hi, db_lo, idesc, 1);
             ptx::umma_f16(tmem_base, da_lo, db_hi, idesc, 1);
           }
+        }
         }
         ptx::umma_commit(&empty_bar[stage]);  // frees this smem stage once the MMAs retire
         }
@@ -446,12 +463,12 @@ bool cached_tmap_kblocks(CUtensorMap* out, const void* base, uint64_t K, uint64_
 
 namespace {
 
-template <int BN, int SPLIT, bool A_MN, bool B_MN>
+template <int BN, int SPLIT, bool A_MN, bool B_MN, int KBS = 1>
 cudaError_t launch_one(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const CUtensorMap& tb_hi,
                        const CUtensorMap& tb_lo, const EpilogueArgs& ep, int M, int N, int K,
                        cudaStream_t stream) {
-  using Cfg = GemmCfg<BN, SPLIT>;
-  auto kern = gemm_bf16_tcgen05_kernel<BN, SPLIT, A_MN, B_MN>;
+  using Cfg = GemmCfg<BN, SPLIT, KBS>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, SPLIT, A_MN, B_MN, KBS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -464,16 +481,16 @@ cudaError_t launch_one(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
   return cudaGetLastError();
 }
 
-template <int BN, int SPLIT>
+template <int BN, int SPLIT, int KBS = 1>
 cudaError_t launch_major(bool a_mn, bool b_mn, const CUtensorMap& ta_hi, const CUtensorMap& ta_lo,
                          const CUtensorMap& tb_hi, const CUtensorMap& tb_lo, const EpilogueArgs& ep,
                          int M, int N, int K, cudaStream_t s) {
   if (a_mn) {
-    if (b_mn) return launch_one<BN, SPLIT, true, true>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
-    return launch_one<BN, SPLIT, true, false>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+    if (b_mn) return launch_one<BN, SPLIT, true, true, KBS>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+    return launch_one<BN, SPLIT, true, false, KBS>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
   }
-  if (b_mn) return launch_one<BN, SPLIT, false, true>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
-  return launch_one<BN, SPLIT, false, false>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+  if (b_mn) return launch_one<BN, SPLIT, false, true, KBS>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
+  return launch_one<BN, SPLIT, false, false, KBS>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K, s);
 }
 
 }  // namespace
@@ -505,6 +522,16 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, Ge
   }
   int bn = d.block_n ? d.block_n : pick_block_n(d.M, d.N, num_sms);
   if (split && bn == 256) bn = 128;
+  // latency-bound shapes (a wave or less of tiles): multi-k-block stages, 4 k-blocks per TMA operation with
+  // 128 x 64 tiles, 2 with 128 x 128 tiles when 64-wide tiles would need a second wave
+  static const bool big_off = getenv("VQA_GEMM_SMALL_BOXES") != nullptr;
+  int kbs = 1;
+  if (!split && !d.block_n && !big_off && (d.K % 64) == 0 && d.K >= 256) {
+    const long long tm = (d.M + BM - 1) / BM;
+    const long long t64 = tm * ((d.N + 63) / 64), t128 = tm * ((d.N + 127) / 128);
+    if (t64 <= num_sms) { bn = 64; kbs = 4; }
+    else if (t128 <= num_sms) { bn = 128; kbs = 2; }
+  }
   if (bn != 64 && bn != 128 && bn != 256) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: block_n");
 
   CUtensorMap ta_hi, ta_lo, tb_hi, tb_lo;
@@ -520,6 +547,11 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, Ge
   ok = ok && map_a(&ta_hi, d.a_hi) && map_b(&tb_hi, d.b_hi);
   if (split) {
     ok = ok && map_a(&ta_lo, d.a_lo) && map_b(&tb_lo, d.b_lo);
+  } else if (kbs > 1) {
+    ok = ok && (d.a_mn_major ? cached_tmap_mnblocks(&ta_lo, d.a_hi, d.M, d.K, d.lda, 2, kbs)
+                             : cached_tmap_kblocks(&ta_lo, d.a_hi, d.K, d.M, d.lda, BM, kbs)) &&
+         (d.b_mn_major ? cached_tmap_mnblocks(&tb_lo, d.b_hi, d.N, d.K, d.ldb, bn / 64, kbs)
+                       : cached_tmap_kblocks(&tb_lo, d.b_hi, d.K, d.N, d.ldb, bn, kbs));
   } else {
     ta_lo = ta_hi;
     tb_lo = tb_hi;
@@ -542,7 +574,9 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, Ge
     if (bn == 64) e = launch_major<64, 3>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
     else e = launch_major<128, 3>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
   } else {
-    if (bn == 64) e = launch_major<64, 1>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+    if (kbs == 4) e = launch_major<64, 1, 4>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+    else if (kbs == 2) e = launch_major<128, 1, 2>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
+    else if (bn == 64) e = launch_major<64, 1>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
     else if (bn == 128) e = launch_major<128, 1>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
     else e = launch_major<256, 1>(amn, bmn, ta_hi, ta_lo, tb_hi, tb_lo, ep, d.M, d.N, d.K, stream);
   }
