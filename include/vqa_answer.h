@@ -42,7 +42,11 @@ enum {
 /* model family members served by the same kernels (vqa/importer.py:22-51) */
 enum {
   VQA_VARIANT_VLMAP_ANSWER = 0, /* vqa/model_vlmap_answer.py: frozen transfer head, train mask */
-  VQA_VARIANT_STANDARD = 1      /* vqa/model_standard.py: learned classifier, all trainable   */
+  VQA_VARIANT_STANDARD = 1,     /* vqa/model_standard.py: learned classifier, all trainable   */
+  /* vqa/model_vlmap_answer2.py:127-131,164: q_L_ft2 = tanh(LN(FC(q))) feeds q_linear_l and is the `condition` output */
+  VQA_VARIANT_VLMAP_ANSWER2 = 2,
+  /* vqa/model_vlmap_answer_no_noise.py:122-125,157: q_L_mean = FC(q) (no LayerNorm, no activation) feeds q_linear_l */
+  VQA_VARIANT_VLMAP_ANSWER_NO_NOISE = 3
 };
 
 /* arithmetic mode of the dense contractions */
@@ -103,6 +107,11 @@ typedef struct VqaParams {
   float* joint_beta;  /* (reasoning/)joint_fc/LayerNorm/beta         [J]          */
   float* ans_w;       /* WordWeightAnswer/fc/weights | reasoning/classifier/fc/weights [J, A] */
   float* ans_b;       /* WordWeightAnswer/fc/biases  | reasoning/classifier/fc/biases  [A]    */
+  /* the extra question layer of the answer2 / no_noise variants (NULL otherwise); L must equal D there */
+  float* qp_w;        /* q_L_ft2/fc/weights | q_L_mean/fc/weights     [L, L]       */
+  float* qp_b;        /* q_L_ft2/fc/biases  | q_L_mean/fc/biases      [L]          */
+  float* qp_gamma;    /* q_L_ft2/LayerNorm/gamma (answer2 only)       [L]          */
+  float* qp_beta;     /* q_L_ft2/LayerNorm/beta  (answer2 only)       [L]          */
 } VqaParams;
 #define VQA_NUM_PARAM_TENSORS 29
 

@@ -14,6 +14,8 @@ this package. The product path (vqa_transfer_externaldata_b200) never does.
 Reference files followed (paths under /root/reference):
   vqa/model_vlmap_answer.py:102-288   graph, loss, metrics           (variant 'vlmap_answer')
   vqa/model_standard.py:193-376       same trunk, learned classifier  (variant 'standard')
+  vqa/model_vlmap_answer2.py:127-131,164         q_L_ft2 = tanh(LN(FC(q))) feeds q_linear_l  ('vlmap_answer2')
+  vqa/model_vlmap_answer_no_noise.py:122-125,157 q_L_mean = FC(q) feeds q_linear_l            ('vlmap_answer_no_noise')
   vlmap/modules.py:630-650            fc_layer = fully_connected -> layer_norm -> activation
   vlmap/modules.py:67-97              hadamard_attention
   vlmap/modules.py:23-39              attention_pooling
@@ -52,11 +54,21 @@ PARAM_FIELDS = list(TF_NAMES.keys())
 FROZEN_SCOPES_VLMAP_ANSWER = ("q_linear_l", "pooled_linear_l", "joint_fc", "WordWeightAnswer")
 
 
+# extra question layer of the two variants (scope q_L_ft2 / q_L_mean: trained, never frozen)
+EXTRA_FIELDS = {"vlmap_answer2": ["qp_w", "qp_b", "qp_gamma", "qp_beta"], "vlmap_answer_no_noise": ["qp_w", "qp_b"]}
+
+
+def param_fields(variant):
+    return PARAM_FIELDS + EXTRA_FIELDS.get(variant, [])
+
+
 def trainable_fields(variant):
     """Fields optimize_loss receives as `variables` (vqa/trainer.py:99-114)."""
     if variant == "standard":  # vqa/model_standard.py:80-84: everything trains
         return list(PARAM_FIELDS)
-    return [f for f in PARAM_FIELDS if TF_NAMES[f].split("/")[0] not in FROZEN_SCOPES_VLMAP_ANSWER]
+    # vlmap_answer (:81-89), vlmap_answer2 (:69-78), vlmap_answer_no_noise (:66-74): same four frozen scopes
+    return [f for f in PARAM_FIELDS if TF_NAMES[f].split("/")[0] not in FROZEN_SCOPES_VLMAP_ANSWER] + \
+        EXTRA_FIELDS.get(variant, [])
 
 
 def sigmoid(x):
@@ -264,7 +276,7 @@ def metrics(logit, target, m, use_train_mask=True):
 # ------------------------------------------------------------------------------------------------
 # the graph
 # ------------------------------------------------------------------------------------------------
-GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joint_w", "ans_w")
+GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joint_w", "ans_w", "qp_w")
 
 
 def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0.8, keep_joint=0.5,
@@ -280,7 +292,7 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     q = operand_round or _ident
     p = {k: f64(v) for k, v in p.items()}
     if operand_round is not None:
-        p.update({k: q(p[k]) for k in GEMM_WEIGHTS})
+        p.update({k: q(p[k]) for k in GEMM_WEIGHTS if k in p})
     idx = np.asarray(batch["image_idx"])
     V = q(f64(features)[idx])                                # model_vlmap_answer.py:110-117
     nbox = np.asarray(num_boxes)[idx].astype(np.int64)       # :118-119
@@ -308,7 +320,20 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     P = np.einsum("bk,bkd->bd", a, V)                        # attention_pooling of the RAW features
 
     Hp, p_cache = fc_ln_relu_fwd(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"], q=q)   # :163-167
-    Hl, l_cache = fc_ln_relu_fwd(qs, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"], q=q)  # :170-174
+    # the variants put one more layer between the GRU state and q_linear_l
+    qp_cache, cond = None, qs
+    ql_in = qs
+    if variant == "vlmap_answer2":        # q_L_ft2 = tanh(LN(q W2 + b2)), model_vlmap_answer2.py:127-130
+        xq = q(qs)
+        zq, ln_q = layer_norm_fwd(xq @ p["qp_w"] + p["qp_b"], p["qp_gamma"], p["qp_beta"])
+        ql_in = np.tanh(zq)
+        qp_cache = (xq, ql_in, ln_q)
+        cond = ql_in                      # heavy_output['condition'] = q_L_ft2 (:131)
+    elif variant == "vlmap_answer_no_noise":   # q_L_mean = q Wm + bm, model_vlmap_answer_no_noise.py:122-125
+        xq = q(qs)
+        ql_in = xq @ p["qp_w"] + p["qp_b"]
+        qp_cache = (xq, None, None)
+    Hl, l_cache = fc_ln_relu_fwd(ql_in, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"], q=q)  # :170-174
     X = Hp * Hl
     Jn, j_cache = fc_ln_relu_fwd(X, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"], q=q)
     jm = np.ones_like(Jn) if joint_mask is None else f64(joint_mask)
@@ -318,11 +343,12 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     use_tm = variant != "standard"
     train_loss, report, ps, pred = metrics(logit, target, m, use_train_mask=use_tm)
     out = {"loss": train_loss, "report": report, "att_score": a, "logit": logit, "pred": pred,
-           "per_sample": ps, "condition": qs, "pooled": P}
+           "per_sample": ps, "condition": cond, "pooled": P}
     cache = dict(V=V, nbox=nbox, q_ids=q_ids, q_len=q_len, target=target, v_cache=v_cache, Hv=Hv,
                  gru_steps=gru_steps, q=qs, q_cache=q_cache, Hq=Hq, am=am, F=F, a=a, P=P, p_cache=p_cache,
                  Hp=Hp, l_cache=l_cache, Hl=Hl, X=X, j_cache=j_cache, jm=jm, Jd=Jd, logit=logit,
-                 keep_att=keep_att, keep_joint=keep_joint, use_tm=use_tm, m=m, W=W, p=p)
+                 keep_att=keep_att, keep_joint=keep_joint, use_tm=use_tm, m=m, W=W, p=p, variant=variant,
+                 qp_cache=qp_cache)
     return out, cache
 
 
@@ -349,6 +375,15 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
         dHp, p["pl_w"], p["pl_gamma"], c["p_cache"], flip=gf.get("pl"), gate=go.get("pl"))
     dq, g["ql_w"], g["ql_b"], g["ql_gamma"], g["ql_beta"] = fc_ln_relu_bwd(
         dHl, p["ql_w"], p["ql_gamma"], c["l_cache"], flip=gf.get("ql"), gate=go.get("ql"))
+    if c.get("qp_cache") is not None:     # back through q_L_ft2 / q_L_mean: dq is the gradient of ITS output so far
+        xq, yq, ln_q = c["qp_cache"]
+        if c["variant"] == "vlmap_answer2":
+            dzq, g["qp_gamma"], g["qp_beta"] = layer_norm_bwd(dq * (1.0 - yq * yq), p["qp_gamma"], ln_q)
+        else:
+            dzq = dq
+        g["qp_w"] = xq.T @ dzq
+        g["qp_b"] = dzq.sum(axis=0)
+        dq = dzq @ p["qp_w"].T
     # attention pooling + softmax + score
     V, a = c["V"], c["a"]
     da = np.einsum("bkd,bd->bk", V, dP)

@@ -66,7 +66,13 @@ def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", k
     a = torch.softmax(s, dim=-1)
     P = torch.bmm(a.unsqueeze(1), V).squeeze(1)
     Hp = fc_layer(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"])
-    Hl = fc_layer(q, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"])
+    ql_in, cond = q, q
+    if variant == "vlmap_answer2":         # vqa/model_vlmap_answer2.py:127-131
+        ql_in = torch.tanh(layer_norm_all(q @ p["qp_w"] + p["qp_b"], p["qp_gamma"], p["qp_beta"]))
+        cond = ql_in
+    elif variant == "vlmap_answer_no_noise":  # vqa/model_vlmap_answer_no_noise.py:122-125
+        ql_in = q @ p["qp_w"] + p["qp_b"]
+    Hl = fc_layer(ql_in, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"])
     Jn = fc_layer(Hp * Hl, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
     if joint_mask is not None:
         Jn = Jn * joint_mask
@@ -80,4 +86,4 @@ def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", k
         bce_train = bce
     loss = bce_train.sum(-1).mean()
     return {"loss": loss, "report_loss": bce.sum(-1).mean(), "logit": logit, "att_score": a, "pooled": P,
-            "condition": q, "pred": logit.argmax(-1)}
+            "condition": cond, "pred": logit.argmax(-1)}

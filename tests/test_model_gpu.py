@@ -153,6 +153,22 @@ def test_gru_pair_kernels_match_single_cta_kernels_at_full_size():
         assert (g1[k] - g0[k]).abs().max().item() <= 2e-4 * scale, k
 
 
+# ---- family variants: one more layer between the GRU state and q_linear_l ----
+@pytest.mark.parametrize("variant", ["vlmap_answer2", "vlmap_answer_no_noise"])
+def test_fp32_variants_small(variant):
+    case = build_case(SMALL, variant=variant, precision="fp32", seed=21)
+    got, ref, ref_g = run_both(case)
+    _check(case, got, ref, ref_g, FP32_TOL)
+
+
+@pytest.mark.parametrize("variant", ["vlmap_answer2", "vlmap_answer_no_noise"])
+def test_bf16_variants_reference_shapes(variant):
+    case = build_case(MID, variant=variant, precision="bf16", seed=22, num_images=40, batch=24)
+    got, ref, ref_g = run_both(case)
+    _check_forward_plain(case, got, BF16_TOL)
+    _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
+
+
 def test_fp32_reference_shapes():
     """The reference's layer sizes (K 36, Dv 2048, D/L 1024, A 3000, T 14, W 300) at a batch the oracle
     finishes in seconds; ragged boxes, tail batch (B < config.B) and short T."""

@@ -30,14 +30,17 @@ def _setup(variant="vlmap_answer", seed=0, perturb=0.3, dims=TINY):
     return c, p, feats.astype(np.float64), nb, batch, m, att_mask, joint_mask
 
 
-@pytest.mark.parametrize("variant", ["vlmap_answer", "standard"])
+VARIANTS = ["vlmap_answer", "standard", "vlmap_answer2", "vlmap_answer_no_noise"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_backward_matches_finite_differences(variant):
     c, p, feats, nb, batch, m, am, jm = _setup(variant)
     out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)
     g = O.backward(cache)
     rng = np.random.default_rng(5)
     eps = 1e-6
-    for name in O.PARAM_FIELDS:
+    for name in O.param_fields(variant):
         flat = p[name].reshape(-1)
         picks = rng.choice(flat.size, size=min(6, flat.size), replace=False)
         for i in picks:
@@ -52,7 +55,7 @@ def test_backward_matches_finite_differences(variant):
             assert abs(fd - an) <= 1e-6 * max(1.0, abs(fd), abs(an)) + 2e-8, (name, i, fd, an)
 
 
-@pytest.mark.parametrize("variant", ["vlmap_answer", "standard"])
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_numpy_oracle_matches_torch_twin(variant):
     torch = pytest.importorskip("torch")
     from oracle import answer_model_torch as OT
@@ -68,7 +71,8 @@ def test_numpy_oracle_matches_torch_twin(variant):
     np.testing.assert_allclose(tout["logit"].detach().numpy(), out["logit"], rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(tout["att_score"].detach().numpy(), out["att_score"], rtol=1e-10, atol=1e-14)
     np.testing.assert_array_equal(tout["pred"].numpy(), out["pred"])
-    for name in O.PARAM_FIELDS:
+    np.testing.assert_allclose(tout["condition"].detach().numpy(), out["condition"], rtol=1e-10, atol=1e-12)
+    for name in O.param_fields(variant):
         tg = tp[name].grad.numpy()
         scale = np.abs(g[name]).max()
         # att_b's gradient is identically zero (softmax is shift-invariant): absolute floor
@@ -115,6 +119,19 @@ def test_known_answers_graph():
     lg[1, 3] = lg[1, 7] = 2.0
     _, _, _, pred = O.metrics(lg, batch["answer_target"][:2].astype(np.float64), m)
     assert pred.tolist() == [0, 3]
+
+
+def test_variant_question_layers():
+    """vlmap_answer2 reports q_L_ft2 = tanh(...) as `condition` (model_vlmap_answer2.py:131): bounded by 1; the
+    extra layer of both variants trains while the transfer head stays frozen (:69-78, no_noise :66-74)."""
+    c, p, feats, nb, batch, m, am, jm = _setup("vlmap_answer2")
+    out, _ = O.forward(p, feats, nb, batch, m, variant="vlmap_answer2", att_mask=am, joint_mask=jm)
+    assert np.all(np.abs(out["condition"]) < 1.0)
+    for v in ("vlmap_answer2", "vlmap_answer_no_noise"):
+        tr = O.trainable_fields(v)
+        assert "qp_w" in tr and "qp_b" in tr and "ql_w" not in tr and "ans_w" not in tr
+    assert "qp_gamma" in O.trainable_fields("vlmap_answer2")
+    assert "qp_gamma" not in O.trainable_fields("vlmap_answer_no_noise")
 
 
 def test_frozen_set_matches_reference_filter():

@@ -44,7 +44,10 @@ def test_tf_names_and_frozen_sets():
 
 
 def test_importer_names():
-    assert importer.get_model_types() == ["vlmap_answer", "standard"]
+    assert importer.get_model_types() == ["vlmap_answer", "vlmap_answer2", "vlmap_answer_no_noise", "standard"]
+    from vqa_transfer_externaldata_b200 import model as M
+    assert importer.get_model_class("vlmap_answer2") is M.Answer2Model
+    assert importer.get_model_class("vlmap_answer_no_noise") is M.NoNoiseModel
     import pytest
     with pytest.raises(ValueError):
         importer.get_model_class("nope")

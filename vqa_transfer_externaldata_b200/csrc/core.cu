@@ -69,6 +69,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   planes(b.w.ql_w, L * L);
   planes(b.w.joint_w, L * J);
   planes(b.w.ans_w, J * A);
+  planes(b.w.qp_w, L * L);
 
   planes(b.v, B * K * Dv);
   b.nbox = a.take<int>(B);
@@ -91,6 +92,12 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
 
   b.zq = a.take<float>(B * D); b.hq = a.take<float>(B * D);
   b.lnq_mean = a.take<float>(B); b.lnq_rstd = a.take<float>(B);
+  b.zqp = a.take<float>(B * L); b.qp_f32 = a.take<float>(B * L);
+  planes(b.qp, B * L);
+  b.lnqp_mean = a.take<float>(B); b.lnqp_rstd = a.take<float>(B);
+  b.dqp = a.take<float>(B * L);
+  b.dzqp_f32 = a.take<float>(B * L);
+  planes(b.dzqp, B * L);
   b.zl = a.take<float>(B * L); b.hl = a.take<float>(B * L);
   b.lnl_mean = a.take<float>(B); b.lnl_rstd = a.take<float>(B);
   b.att = a.take<float>(B * K);
@@ -172,8 +179,10 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
     return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: Dv, D, L, J, A must be multiples of 8");
   if (c.D > 4096 || c.L > 4096 || c.J > 4096 || c.K > 256 || c.T > 64)
     return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: D, L, J <= 4096; K <= 256; T <= 64");
-  if (c.variant != VQA_VARIANT_VLMAP_ANSWER && c.variant != VQA_VARIANT_STANDARD)
+  if (c.variant < VQA_VARIANT_VLMAP_ANSWER || c.variant > VQA_VARIANT_VLMAP_ANSWER_NO_NOISE)
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown variant %d", c.variant);
+  if ((c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE) && c.D != c.L)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: the answer2 / no_noise variants need D == L (V_DIM == L_DIM as in the reference)");
   if (c.precision != VQA_PREC_BF16 && c.precision != VQA_PREC_FP32)
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown precision %d", c.precision);
   if (!(c.keep_att > 0.f && c.keep_att <= 1.f) || !(c.keep_joint > 0.f && c.keep_joint <= 1.f))

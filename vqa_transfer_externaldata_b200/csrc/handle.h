@@ -9,7 +9,7 @@ namespace vqa {
 
 // Weight shadows in GEMM-operand form, same [in, out] layout as the fp32 TF variables.
 struct WeightShadows {
-  Planes v_w, gru_gates_w, gru_cand_w, qv_w, pl_w, ql_w, joint_w, ans_w;
+  Planes v_w, gru_gates_w, gru_cand_w, qv_w, pl_w, ql_w, joint_w, ans_w, qp_w;
 };
 
 // Everything forward keeps for backward + scratch, all inside the workspace.
@@ -35,6 +35,10 @@ struct Buffers {
   // heads
   float* zq; float* hq; float* lnq_mean; float* lnq_rstd;       // q_linear_v
   float* zl; float* hl; float* lnl_mean; float* lnl_rstd;       // q_linear_l
+  // extra question layer of the answer2 / no_noise variants: pre-activation, output (fp32 + operand planes), LN stats
+  float* zqp; float* qp_f32; Planes qp; float* lnqp_mean; float* lnqp_rstd;
+  float* dqp;                        // [B, L] gradient w.r.t. that layer's output
+  float* dzqp_f32; Planes dzqp;      // [B, L] gradient w.r.t. its pre-activation
   float* att;      // [B, K]
   float* pooled;   // [B, Dv]
   Planes pooled_op;

@@ -151,6 +151,7 @@ struct RowLnFwd {
   bf16* out_lo;
   float* mean;           // [rows]
   float* rstd;           // [rows]
+  int act;               // 0 = ReLU (fc_layer's default here), 1 = tanh (q_L_ft2 of model_vlmap_answer2)
 };
 VqaStatus row_ln_relu_fwd_launch(const RowLnFwd& a, cudaStream_t s);
 
@@ -171,6 +172,7 @@ struct RowLnBwd {
   bf16* dz_lo;
   float* dgamma_part;    // optional [parts, N] per-CTA partials (parts = rows)
   float* dbeta_part;
+  int act;               // as in RowLnFwd
 };
 VqaStatus row_ln_relu_bwd_launch(const RowLnBwd& a, cudaStream_t s);
 

@@ -109,6 +109,7 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
       {p->ql_w, &w.ql_w, c.L, c.L},
       {p->joint_w, &w.joint_w, c.L, c.J},
       {p->ans_w, &w.ans_w, c.J, c.A},
+      {p->qp_w, &w.qp_w, c.L, c.L},   // answer2 / no_noise only (NULL otherwise)
   };
   // the refreshes are independent small memory-bound kernels: spread them over the auxiliary streams instead of
   // queueing them behind one another (they sit between the optimizer and the next step's first GEMM)
@@ -116,6 +117,8 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
   bool forked[VqaHandle_t::kAux] = {};
   cudaStream_t gru_stream = s;
   for (auto& it : items) {
+    const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE;
+    if (it.dst == &w.qp_w && !has_qp) continue;   // the base variants have no such layer
     if (!it.src) {
       if (!h->params_ready) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: the first call needs every weight");
       continue;  // unchanged since the last call
@@ -233,7 +236,26 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_BEGIN(VQA_PH_QHEADS_FWD);
   // a6 (question half) on the auxiliary stream: Hl = relu(LN(q Wl + b))   (:170-174); needed only by the joint head
   VQA_TRY(fork_stream(h, 0, s, &s1));
-  VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.ql_w, 0, L, true).bias(p->ql_b).f32(b.zl, L).run(h, s1));
+  const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE;
+  if (has_qp) {
+    if (!p->qp_w || !p->qp_b) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: this variant needs qp_w / qp_b");
+    if (c.variant == VQA_VARIANT_VLMAP_ANSWER2) {
+      // q_L_ft2 = tanh(LN(q W2 + b2))           (vqa/model_vlmap_answer2.py:127-130)
+      if (!p->qp_gamma || !p->qp_beta) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: answer2 needs qp_gamma / qp_beta");
+      VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.qp_w, 0, L, true).bias(p->qp_b).f32(b.zqp, L).run(h, s1));
+      RowLnFwd r{};
+      r.rows = Bn; r.N = L; r.z = b.zqp; r.gamma = p->qp_gamma; r.beta = p->qp_beta; r.keep = 1.f; r.act = 1;
+      r.y = b.qp_f32; r.out_hi = b.qp.hi; r.out_lo = b.qp.lo; r.mean = b.lnqp_mean; r.rstd = b.lnqp_rstd;
+      VQA_TRY(row_ln_relu_fwd_launch(r, s1));
+    } else {
+      // q_L_mean = q Wm + bm: no LayerNorm, no activation   (vqa/model_vlmap_answer_no_noise.py:122-125)
+      VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.qp_w, 0, L, true).bias(p->qp_b).f32(b.qp_f32, L)
+                  .planes(b.qp, 0, L).run(h, s1));
+    }
+  }
+  const Planes& ql_in = has_qp ? b.qp : b.h;
+  const long long ql_in_off = has_qp ? 0 : T * BL;
+  VQA_TRY(GemmB(Bn, L, L).a(ql_in, ql_in_off, L, false).b(b.w.ql_w, 0, L, true).bias(p->ql_b).f32(b.zl, L).run(h, s1));
   {
     RowLnFwd r{};
     r.rows = Bn; r.N = L; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta; r.keep = 1.f;
@@ -283,7 +305,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_END(VQA_PH_HEAD_FWD);
   PH_BEGIN(VQA_PH_LOSS);
   // a8 + a9: loss, pred, report                                       (:192-288)
-  const int use_tm = c.variant == VQA_VARIANT_VLMAP_ANSWER;
+  const int use_tm = c.variant != VQA_VARIANT_STANDARD;  // every vlmap_answer* variant masks the loss to the train answers
   VQA_TRY(bce_metrics_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target, *masks, 0.f,
                              b.loss, b.report, b.pred, b.per_sample, nullptr, nullptr, nullptr, b.scratch, s));
   PH_END(VQA_PH_LOSS);
@@ -294,7 +316,8 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(copy_out(out->logit, b.logit, sizeof(float) * Bn * A, s));
     VQA_TRY(copy_out(out->pred, b.pred, sizeof(int) * Bn, s));
     VQA_TRY(copy_out(out->per_sample, b.per_sample, sizeof(float) * VQA_NUM_PER_SAMPLE * Bn, s));
-    VQA_TRY(copy_out(out->condition, q, sizeof(float) * BL, s));
+    // heavy_output['condition']: q (base), q_L_ft2 (vqa/model_vlmap_answer2.py:131)
+    VQA_TRY(copy_out(out->condition, c.variant == VQA_VARIANT_VLMAP_ANSWER2 ? b.qp_f32 : q, sizeof(float) * BL, s));
     VQA_TRY(copy_out(out->pooled, b.pooled, sizeof(float) * Bn * Dv, s));
   }
   h->fwd_valid = true;
@@ -320,7 +343,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   const int K = c.K, Dv = c.Dv, D = c.D, L = c.L, J = c.J, A = c.A, W = c.W, Wp = h->Wpad;
   const long long BL = static_cast<long long>(Bn) * L;
   const uint64_t seed = h->last_seed, step = h->last_step;
-  const int use_tm = c.variant == VQA_VARIANT_VLMAP_ANSWER;
+  const int use_tm = c.variant != VQA_VARIANT_STANDARD;  // every vlmap_answer* variant masks the loss to the train answers
   const long long q_off = T * BL;
 
   PH_BEGIN(VQA_PH_HEAD_BWD);
@@ -369,11 +392,38 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   }
   if (g->pl_w) VQA_TRY(GemmB(Dv, L, Bn).a(b.pooled_op, 0, Dv, true).b(b.dzp, 0, L, true).f32(g->pl_w, L).run(h, s));
   if (g->pl_b) VQA_TRY(colsum_launch(b.dzp_f32, Bn, L, L, g->pl_b, b.scratch, s));
-  if (g->ql_w) VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dzl, 0, L, true).f32(g->ql_w, L).run(h, s));
+  const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE;
+  {
+    const Planes& ql_in = has_qp ? b.qp : b.h;   // q_linear_l reads the extra layer's output in those variants
+    if (g->ql_w)
+      VQA_TRY(GemmB(L, L, Bn).a(ql_in, has_qp ? 0 : q_off, L, true).b(b.dzl, 0, L, true).f32(g->ql_w, L).run(h, s));
+  }
   if (g->ql_b) VQA_TRY(colsum_launch(b.dzl_f32, Bn, L, L, g->ql_b, b.scratch, s));
   // dP = dZp Wp^T ; dq = dZl Wl^T
   VQA_TRY(GemmB(Bn, Dv, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Dv).run(h, s));
-  VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, s));
+  if (!has_qp) {
+    VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, s));
+  } else if (c.variant == VQA_VARIANT_VLMAP_ANSWER2) {
+    // d(q_L_ft2) -> tanh / LayerNorm backward -> parameter gradients of q_L_ft2 -> dq
+    VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dqp, L).run(h, s));
+    RowLnBwd r{};
+    r.rows = Bn; r.N = L; r.dout = b.dqp; r.z = b.zqp; r.gamma = p->qp_gamma; r.beta = p->qp_beta;
+    r.mean = b.lnqp_mean; r.rstd = b.lnqp_rstd; r.keep = 1.f; r.act = 1; r.dz_f32 = b.dzqp_f32;
+    r.dz_hi = b.dzqp.hi; r.dz_lo = b.dzqp.lo;
+    if (g->qp_gamma || g->qp_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (g->qp_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->qp_gamma, b.scratch, s));
+    if (g->qp_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->qp_beta, b.scratch, s));
+  } else {
+    // q_L_mean is linear: the gradient of its output IS the gradient of its pre-activation
+    VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dzqp_f32, L).planes(b.dzqp, 0, L)
+                .run(h, s));
+  }
+  if (has_qp) {
+    if (g->qp_w) VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dzqp, 0, L, true).f32(g->qp_w, L).run(h, s));
+    if (g->qp_b) VQA_TRY(colsum_launch(b.dzqp_f32, Bn, L, L, g->qp_b, b.scratch, s));
+    VQA_TRY(GemmB(Bn, L, L).a(b.dzqp, 0, L, false).b(b.w.qp_w, 0, L, false).f32(b.dq, L).run(h, s));
+  }
   PH_END(VQA_PH_HEAD_BWD);
   PH_BEGIN(VQA_PH_ATTN_BWD);
   // attention block backward
@@ -634,7 +684,7 @@ VQA_API VqaStatus vqa_bce_metrics(VqaHandle h, int32_t batch, const float* logit
   if (!masks) return set_error(VQA_ERR_BAD_ARG, "vqa_bce_metrics: null masks");
   const VqaConfig& c = h->cfg;
   if (batch > c.B) return set_error(VQA_ERR_BAD_SHAPE, "vqa_bce_metrics: batch exceeds config.B");
-  return bce_metrics_launch(batch, c.A, c.num_train_answer, c.variant == VQA_VARIANT_VLMAP_ANSWER, logit, target,
+  return bce_metrics_launch(batch, c.A, c.num_train_answer, c.variant != VQA_VARIANT_STANDARD, logit, target,
                             *masks, grad_scale, loss, report, pred, per_sample, d_logit, nullptr, nullptr,
                             h->buf.scratch, static_cast<cudaStream_t>(stream));
 }

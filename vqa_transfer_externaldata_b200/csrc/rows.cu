@@ -87,7 +87,10 @@ __global__ void __launch_bounds__(ROW_THREADS) row_ln_relu_fwd_kernel(RowLnFwd a
       ld8(a.gamma + c * 8, g);
       ld8(a.beta + c * 8, bt);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) y[j] = fmaxf(fmaf((x[i][j] - mean) * rstd, g[j], bt[j]), 0.f);
+      for (int j = 0; j < 8; ++j) {
+        const float ypre = fmaf((x[i][j] - mean) * rstd, g[j], bt[j]);
+        y[j] = a.act == 1 ? tanhf(ypre) : fmaxf(ypre, 0.f);
+      }
       if (a.y) st8(a.y + base + c * 8, y);
       if (a.mul) {
         float m[8];
@@ -151,7 +154,13 @@ __global__ void __launch_bounds__(ROW_THREADS) row_ln_relu_bwd_kernel(RowLnBwd a
       for (int j = 0; j < 8; ++j) {
         xh[i][j] = (z[j] - mean) * rstd;
         const float ypre = fmaf(xh[i][j], g[j], bt[j]);
-        const float dy = ypre > 0.f ? d[j] : 0.f;
+        float dy;
+        if (a.act == 1) {
+          const float t = tanhf(ypre);
+          dy = d[j] * (1.0f - t * t);
+        } else {
+          dy = ypre > 0.f ? d[j] : 0.f;
+        }
         dg[j] = dy * xh[i][j];
         db[j] = dy;
         dxh[i][j] = dy * g[j];

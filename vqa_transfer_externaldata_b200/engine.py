@@ -33,8 +33,14 @@ TF_NAMES = {
 _REASONING = ("pl_", "ql_", "joint_")
 
 
+_QP_SCOPE = {"vlmap_answer2": "q_L_ft2", "vlmap_answer_no_noise": "q_L_mean"}   # model_vlmap_answer2.py:127-130 / _no_noise.py:122-125
+_QP_LEAF = {"qp_w": "fc/weights", "qp_b": "fc/biases", "qp_gamma": "LayerNorm/gamma", "qp_beta": "LayerNorm/beta"}
+
+
 def tf_name(field, variant):
     """Checkpoint variable name of a parameter field for a model_type."""
+    if field in _QP_LEAF:
+        return _QP_SCOPE[variant] + "/" + _QP_LEAF[field]
     if variant == "standard":  # vqa/model_standard.py:251-275
         if field.startswith(_REASONING):
             return "reasoning/" + TF_NAMES[field]
@@ -72,7 +78,7 @@ class AnswerModelConfig:
         return L.VqaConfig(
             B=self.B, K=self.K, Dv=self.Dv, D=self.D, L=self.L, J=self.J, A=self.A, T=self.T, W=self.W,
             Vq=self.Vq, num_train_answer=self.num_train_answer,
-            variant={"vlmap_answer": L.VARIANT_VLMAP_ANSWER, "standard": L.VARIANT_STANDARD}[self.variant],
+            variant=L.VARIANTS[self.variant],
             precision={"bf16": L.PREC_BF16, "fp32": L.PREC_FP32}[self.precision],
             keep_att=self.keep_att, keep_joint=self.keep_joint)
 
@@ -82,6 +88,8 @@ def frozen_fields(variant):
     WordWeightAnswer; vqa/model_standard.py:80-84 trains everything."""
     if variant == "standard":
         return set()
+    # vlmap_answer, vlmap_answer2 (model_vlmap_answer2.py:69-78) and vlmap_answer_no_noise (:66-74) freeze the same
+    # four scopes; their extra question layer trains
     return {f for f in L.PARAM_FIELDS if TF_NAMES[f].split("/")[0] in
             ("q_linear_l", "pooled_linear_l", "joint_fc", "WordWeightAnswer")}
 
@@ -100,12 +108,13 @@ class ParamStore:
     def __init__(self, cfg, device):
         self.cfg = cfg
         frozen = frozen_fields(cfg.variant)
-        trainable = [f for f in L.PARAM_FIELDS if f not in frozen]
+        self.fields = L.param_fields(cfg.variant)
+        trainable = [f for f in self.fields if f not in frozen]
         # gradients complete BEFORE the GRU's BPTT first (everything but the embedding and the GRU): with early
         # gradients enabled that slice is all-reduced under the recurrent kernels (dp.DataParallel)
         early = [f for f in trainable if f not in LATE_GRAD_FIELDS]
         self.trainable = early + [f for f in trainable if f in LATE_GRAD_FIELDS]
-        self.frozen = [f for f in L.PARAM_FIELDS if f in frozen]
+        self.frozen = [f for f in self.fields if f in frozen]
         self.offsets, off = {}, 0
         self.n_early = 0
         for f in self.trainable:
@@ -138,24 +147,24 @@ class ParamStore:
 
     def load(self, params):
         """params: dict field -> array-like (numpy / torch), fp32, TF layout."""
-        for f in L.PARAM_FIELDS:
+        for f in self.fields:
             t = torch.as_tensor(np.asarray(params[f], dtype=np.float32))
             if tuple(t.shape) != tuple(self.cfg.shape(f)):
                 raise ValueError(f"{f}: shape {tuple(t.shape)} != {tuple(self.cfg.shape(f))}")
             self.views[f].copy_(t)
 
     def by_tf_name(self):
-        return {tf_name(f, self.cfg.variant): self.views[f] for f in L.PARAM_FIELDS}
+        return {tf_name(f, self.cfg.variant): self.views[f] for f in self.fields}
 
     def c_params(self):
         p = L.VqaParams()
-        for f in L.PARAM_FIELDS:
+        for f in self.fields:
             setattr(p, f, self.views[f].data_ptr())
         return p
 
     def c_grads(self):
         g = L.VqaParams()
-        for f in L.PARAM_FIELDS:
+        for f in self.fields:
             setattr(g, f, self.grad_views[f].data_ptr() if f in self.grad_views else None)
         return g
 

@@ -14,7 +14,8 @@ LIB_PATH = os.path.join(HERE, "libvqa_answer_b200.so")
 VQA_OK = 0
 VQA_ERR_BAD_ARG, VQA_ERR_BAD_SHAPE, VQA_ERR_WORKSPACE = -1, -2, -3
 VQA_ERR_CUDA, VQA_ERR_NO_DEVICE, VQA_ERR_STATE = -4, -5, -6
-VARIANT_VLMAP_ANSWER, VARIANT_STANDARD = 0, 1
+VARIANT_VLMAP_ANSWER, VARIANT_STANDARD, VARIANT_VLMAP_ANSWER2, VARIANT_VLMAP_ANSWER_NO_NOISE = 0, 1, 2, 3
+VARIANTS = {"vlmap_answer": 0, "standard": 1, "vlmap_answer2": 2, "vlmap_answer_no_noise": 3}
 PREC_BF16, PREC_FP32 = 0, 1
 
 REPORT_KEYS = [
@@ -50,8 +51,22 @@ class VqaConfig(C.Structure):
                  "precision")] + [("keep_att", C.c_float), ("keep_joint", C.c_float)]
 
 
+# the extra question layer of model_vlmap_answer2 (q_L_ft2: FC + LayerNorm + tanh) and model_vlmap_answer_no_noise
+# (q_L_mean: FC only); NULL in the struct for the other variants
+EXTRA_FIELDS = ["qp_w", "qp_b", "qp_gamma", "qp_beta"]
+
+
+def param_fields(variant):
+    """Parameter fields a model_type owns, in struct order."""
+    if variant == "vlmap_answer2":
+        return PARAM_FIELDS + EXTRA_FIELDS
+    if variant == "vlmap_answer_no_noise":
+        return PARAM_FIELDS + EXTRA_FIELDS[:2]
+    return list(PARAM_FIELDS)
+
+
 class VqaParams(C.Structure):
-    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS]
+    _fields_ = [(n, C.c_void_p) for n in PARAM_FIELDS + EXTRA_FIELDS]
 
 
 class VqaFeatureBank(C.Structure):

@@ -124,6 +124,8 @@ class Model(object):
         c = {k: getattr(self.engine_config, k) for k in
              ("B", "K", "Dv", "D", "L", "J", "A", "T", "W", "Vq", "num_train_answer")}
         p, _ = init_params(c, seed=seed, variant="standard")  # Xavier head; replaced below for vlmap_answer
+        extra, _ = init_params(c, seed=seed + 1, variant=self.MODEL_TYPE)
+        p.update({k: v for k, v in extra.items() if k.startswith("qp_")})   # q_L_ft2 / q_L_mean of the variants
         glove = getattr(self.config, "glove_embed", None)
         if glove is not None:  # LearnGloVe (vlmap/modules.py:415-448): rows by vocabulary word
             p["embed"] = np.asarray(glove, np.float32)
@@ -137,7 +139,7 @@ class Model(object):
         return {k: v.detach().cpu().numpy().copy() for k, v in self.engine.params.by_tf_name().items()}
 
     def load_state_dict(self, state, strict=True):
-        fields = {tf_name(f, self.MODEL_TYPE): f for f in L.PARAM_FIELDS}
+        fields = {tf_name(f, self.MODEL_TYPE): f for f in L.param_fields(self.MODEL_TYPE)}
         missing = [n for n in fields if n not in state]
         if strict and missing:
             raise KeyError(f"missing variables: {missing}")
@@ -208,6 +210,16 @@ class Model(object):
         self.loss, self.report = self.engine.read_scalars()
         self.losses["answer"] = self.loss
         return self.loss, self.report
+
+
+class Answer2Model(Model):
+    """vqa/model_vlmap_answer2.py: q_L_ft2 = tanh(LN(FC(q))) feeds q_linear_l and is heavy_output['condition']."""
+    MODEL_TYPE = "vlmap_answer2"
+
+
+class NoNoiseModel(Model):
+    """vqa/model_vlmap_answer_no_noise.py: q_L_mean = FC(q) (linear) feeds q_linear_l."""
+    MODEL_TYPE = "vlmap_answer_no_noise"
 
 
 class StandardModel(Model):

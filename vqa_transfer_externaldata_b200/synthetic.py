@@ -26,7 +26,11 @@ PARAM_SHAPES = {
     "joint_w": lambda c: (c["L"], c["J"]), "joint_b": lambda c: (c["J"],),
     "joint_gamma": lambda c: (c["J"],), "joint_beta": lambda c: (c["J"],),
     "ans_w": lambda c: (c["J"], c["A"]), "ans_b": lambda c: (c["A"],),
+    # extra question layer of vlmap_answer2 (q_L_ft2) / vlmap_answer_no_noise (q_L_mean); V_DIM == L_DIM there
+    "qp_w": lambda c: (c["L"], c["L"]), "qp_b": lambda c: (c["L"],),
+    "qp_gamma": lambda c: (c["L"],), "qp_beta": lambda c: (c["L"],),
 }
+EXTRA_FIELDS = {"vlmap_answer2": ("qp_w", "qp_b", "qp_gamma", "qp_beta"), "vlmap_answer_no_noise": ("qp_w", "qp_b")}
 
 
 def dims(B=512, K=36, Dv=2048, D=1024, L=1024, J=None, A=3000, T=14, W=300, Vq=8192,
@@ -47,6 +51,8 @@ def init_params(c, seed=4321, variant="vlmap_answer", perturb=0.0, present_frac=
     rng = np.random.default_rng(seed)
     p = {}
     for name, shp in PARAM_SHAPES.items():
+        if name.startswith("qp_") and name not in EXTRA_FIELDS.get(variant, ()):
+            continue
         shape = shp(c)
         if name == "embed":
             p[name] = (rng.standard_normal(shape) * 0.4).astype(np.float32)  # GloVe-like scale
