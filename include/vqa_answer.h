@@ -46,7 +46,11 @@ enum {
   /* vqa/model_vlmap_answer2.py:127-131,164: q_L_ft2 = tanh(LN(FC(q))) feeds q_linear_l and is the `condition` output */
   VQA_VARIANT_VLMAP_ANSWER2 = 2,
   /* vqa/model_vlmap_answer_no_noise.py:122-125,157: q_L_mean = FC(q) (no LayerNorm, no activation) feeds q_linear_l */
-  VQA_VARIANT_VLMAP_ANSWER_NO_NOISE = 3
+  VQA_VARIANT_VLMAP_ANSWER_NO_NOISE = 3,
+  /* vqa/model_vlmap_answer_noc.py:177-203 (model_vlmap_answer_nocarch.py is the same graph): no Hadamard fusion;
+   * pooled_linear_l -> joint_v -> WordWeightAnswerV and q_linear_l -> joint_l -> WordWeightAnswerL, each with its own
+   * dropout(0.5), logits added; both heads frozen */
+  VQA_VARIANT_VLMAP_ANSWER_NOC = 4
 };
 
 /* arithmetic mode of the dense contractions */
@@ -112,6 +116,14 @@ typedef struct VqaParams {
   float* qp_b;        /* q_L_ft2/fc/biases  | q_L_mean/fc/biases      [L]          */
   float* qp_gamma;    /* q_L_ft2/LayerNorm/gamma (answer2 only)       [L]          */
   float* qp_beta;     /* q_L_ft2/LayerNorm/beta  (answer2 only)       [L]          */
+  /* second branch of the noc / nocarch variants (NULL otherwise); there joint_* is scope joint_v and ans_* is
+   * WordWeightAnswerV */
+  float* jl_w;        /* joint_l/fc/weights                           [L, J]       */
+  float* jl_b;        /* joint_l/fc/biases                            [J]          */
+  float* jl_gamma;    /* joint_l/LayerNorm/gamma                      [J]          */
+  float* jl_beta;     /* joint_l/LayerNorm/beta                       [J]          */
+  float* al_w;        /* WordWeightAnswerL/fc/weights                 [J, A]       */
+  float* al_b;        /* WordWeightAnswerL/fc/biases                  [A]          */
 } VqaParams;
 #define VQA_NUM_PARAM_TENSORS 29
 
@@ -216,6 +228,11 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* params, const VqaBa
 
 /* Materialise the dropout masks vqa_forward(seed, step) uses, as 0/1 bytes: att [batch, K, D],
  * joint [batch, J]. Test / parity helper (the kernels regenerate the same bits on the fly). */
+/* One dropout site's keep mask (0 / 1 bytes) for (seed, step): site 1 = attention features [batch, K, D],
+ * 2 = joint (joint_v in noc) [batch, J], 3 = joint_l of the noc variants [batch, J]. */
+VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch, uint64_t seed, uint64_t step,
+                                        uint8_t* mask, void* stream);
+
 /* Data-parallel overlap (vqa/trainer.py has no distributed code; this is the B200 side of SURVEY 8e).
  * With early gradients enabled, vqa_backward produces the gradients of everything EXCEPT the embedding and the GRU
  * (v_linear_v, q_linear_v, the attention score layer, and the trainable heads of model_standard) BEFORE the GRU's
@@ -244,6 +261,7 @@ enum {
   VQA_ACT_HP,       /* relu(LN(P Wp + b))             [batch, L]  fp32                            */
   VQA_ACT_JD,       /* dropout(relu(LN(X Wj + b)))    [batch, J]  bf16 (hi plane)                 */
   VQA_ACT_Z,        /* pre-LN v-projection            [batch*K, D] bf16 (PREC_BF16) / fp32        */
+  VQA_ACT_JDL,      /* noc: dropout(relu(LN(Hl Wjl + b))) [batch, J]  bf16 (hi plane)                 */
   VQA_NUM_ACT
 };
 VQA_API VqaStatus vqa_peek_activation(VqaHandle h, int32_t which, const void** dev_ptr, uint64_t* bytes);

@@ -16,6 +16,7 @@ Reference files followed (paths under /root/reference):
   vqa/model_standard.py:193-376       same trunk, learned classifier  (variant 'standard')
   vqa/model_vlmap_answer2.py:127-131,164         q_L_ft2 = tanh(LN(FC(q))) feeds q_linear_l  ('vlmap_answer2')
   vqa/model_vlmap_answer_no_noise.py:122-125,157 q_L_mean = FC(q) feeds q_linear_l            ('vlmap_answer_no_noise')
+  vqa/model_vlmap_answer_noc.py:177-203 (= _nocarch.py) two heads joint_v / joint_l, logits summed ('vlmap_answer_noc')
   vlmap/modules.py:630-650            fc_layer = fully_connected -> layer_norm -> activation
   vlmap/modules.py:67-97              hadamard_attention
   vlmap/modules.py:23-39              attention_pooling
@@ -55,7 +56,9 @@ FROZEN_SCOPES_VLMAP_ANSWER = ("q_linear_l", "pooled_linear_l", "joint_fc", "Word
 
 
 # extra question layer of the two variants (scope q_L_ft2 / q_L_mean: trained, never frozen)
-EXTRA_FIELDS = {"vlmap_answer2": ["qp_w", "qp_b", "qp_gamma", "qp_beta"], "vlmap_answer_no_noise": ["qp_w", "qp_b"]}
+NOC_FIELDS = ["jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b"]   # joint_l and WordWeightAnswerL (frozen)
+EXTRA_FIELDS = {"vlmap_answer2": ["qp_w", "qp_b", "qp_gamma", "qp_beta"], "vlmap_answer_no_noise": ["qp_w", "qp_b"],
+                "vlmap_answer_noc": NOC_FIELDS, "vlmap_answer_nocarch": NOC_FIELDS}
 
 
 def param_fields(variant):
@@ -67,8 +70,10 @@ def trainable_fields(variant):
     if variant == "standard":  # vqa/model_standard.py:80-84: everything trains
         return list(PARAM_FIELDS)
     # vlmap_answer (:81-89), vlmap_answer2 (:69-78), vlmap_answer_no_noise (:66-74): same four frozen scopes
-    return [f for f in PARAM_FIELDS if TF_NAMES[f].split("/")[0] not in FROZEN_SCOPES_VLMAP_ANSWER] + \
-        EXTRA_FIELDS.get(variant, [])
+    base = [f for f in PARAM_FIELDS if TF_NAMES[f].split("/")[0] not in FROZEN_SCOPES_VLMAP_ANSWER]
+    if variant in ("vlmap_answer_noc", "vlmap_answer_nocarch"):   # model_vlmap_answer_noc.py:78-88: both heads frozen
+        return base
+    return base + EXTRA_FIELDS.get(variant, [])
 
 
 def sigmoid(x):
@@ -276,11 +281,11 @@ def metrics(logit, target, m, use_train_mask=True):
 # ------------------------------------------------------------------------------------------------
 # the graph
 # ------------------------------------------------------------------------------------------------
-GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joint_w", "ans_w", "qp_w")
+GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joint_w", "ans_w", "qp_w", "jl_w", "al_w")
 
 
 def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0.8, keep_joint=0.5,
-            att_mask=None, joint_mask=None, operand_round=None):
+            att_mask=None, joint_mask=None, operand_round=None, joint_l_mask=None):
     """Model.build() forward. p: dict field -> fp64 array (TF layout [in,out]).
     features [N,K,Dv], num_boxes [N]; batch: image_idx [B], q_intseq [B,T], q_intseq_len [B],
     answer_target [B,A]; att_mask [B,K,D] / joint_mask [B,J] are the 0/1 keep masks tf.nn.dropout
@@ -334,11 +339,25 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
         ql_in = xq @ p["qp_w"] + p["qp_b"]
         qp_cache = (xq, None, None)
     Hl, l_cache = fc_ln_relu_fwd(ql_in, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"], q=q)  # :170-174
-    X = Hp * Hl
-    Jn, j_cache = fc_ln_relu_fwd(X, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"], q=q)
-    jm = np.ones_like(Jn) if joint_mask is None else f64(joint_mask)
-    Jd = q(Jn * jm / keep_joint)                             # :180
-    logit = Jd @ p["ans_w"] + p["ans_b"]                     # :183-185 / model_standard.py:272-275
+    noc = variant in ("vlmap_answer_noc", "vlmap_answer_nocarch")
+    jl_cache, jlm, Jld = None, None, None
+    if not noc:
+        X = Hp * Hl
+        Jn, j_cache = fc_ln_relu_fwd(X, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"], q=q)
+        jm = np.ones_like(Jn) if joint_mask is None else f64(joint_mask)
+        Jd = q(Jn * jm / keep_joint)                             # :180
+        logit = Jd @ p["ans_w"] + p["ans_b"]                     # :183-185 / model_standard.py:272-275
+    else:
+        # model_vlmap_answer_noc.py:177-203: no Hadamard; each branch has its own joint layer, dropout and
+        # word-weight head, and the two logits are added
+        X = Hp
+        Jn, j_cache = fc_ln_relu_fwd(Hp, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"], q=q)   # joint_v
+        jm = np.ones_like(Jn) if joint_mask is None else f64(joint_mask)
+        Jd = q(Jn * jm / keep_joint)
+        Jln, jl_cache = fc_ln_relu_fwd(Hl, p["jl_w"], p["jl_b"], p["jl_gamma"], p["jl_beta"], q=q)             # joint_l
+        jlm = np.ones_like(Jln) if joint_l_mask is None else f64(joint_l_mask)
+        Jld = q(Jln * jlm / keep_joint)
+        logit = (Jd @ p["ans_w"] + p["ans_b"]) + (Jld @ p["al_w"] + p["al_b"])
 
     use_tm = variant != "standard"
     train_loss, report, ps, pred = metrics(logit, target, m, use_train_mask=use_tm)
@@ -348,7 +367,7 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
                  gru_steps=gru_steps, q=qs, q_cache=q_cache, Hq=Hq, am=am, F=F, a=a, P=P, p_cache=p_cache,
                  Hp=Hp, l_cache=l_cache, Hl=Hl, X=X, j_cache=j_cache, jm=jm, Jd=Jd, logit=logit,
                  keep_att=keep_att, keep_joint=keep_joint, use_tm=use_tm, m=m, W=W, p=p, variant=variant,
-                 qp_cache=qp_cache)
+                 qp_cache=qp_cache, jl_cache=jl_cache, jlm=jlm, Jld=Jld, noc=noc)
     return out, cache
 
 
@@ -370,7 +389,15 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
     dJn = dJd * c["jm"] / c["keep_joint"]
     dX, g["joint_w"], g["joint_b"], g["joint_gamma"], g["joint_beta"] = fc_ln_relu_bwd(
         dJn, p["joint_w"], p["joint_gamma"], c["j_cache"], flip=gf.get("joint"), gate=go.get("joint"))
-    dHp, dHl = dX * c["Hl"], dX * c["Hp"]
+    if not c.get("noc"):
+        dHp, dHl = dX * c["Hl"], dX * c["Hp"]
+    else:
+        dHp = dX
+        g["al_w"] = c["Jld"].T @ dx
+        g["al_b"] = dx.sum(0)
+        dJln = (dx @ p["al_w"].T) * c["jlm"] / c["keep_joint"]
+        dHl, g["jl_w"], g["jl_b"], g["jl_gamma"], g["jl_beta"] = fc_ln_relu_bwd(
+            dJln, p["jl_w"], p["jl_gamma"], c["jl_cache"], flip=gf.get("jl"), gate=go.get("jl"))
     dP, g["pl_w"], g["pl_b"], g["pl_gamma"], g["pl_beta"] = fc_ln_relu_bwd(
         dHp, p["pl_w"], p["pl_gamma"], c["p_cache"], flip=gf.get("pl"), gate=go.get("pl"))
     dq, g["ql_w"], g["ql_b"], g["ql_gamma"], g["ql_beta"] = fc_ln_relu_bwd(
@@ -412,13 +439,14 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
     return g
 
 
-RELU_LAYERS = {"v": "v_cache", "qv": "q_cache", "pl": "p_cache", "ql": "l_cache", "joint": "j_cache"}
+RELU_LAYERS = {"v": "v_cache", "qv": "q_cache", "pl": "p_cache", "ql": "l_cache", "joint": "j_cache", "jl": "jl_cache"}
 
 
 def relu_near_ties(cache, tau):
     """Indices of ReLU pre-activations with |y| < tau, per layer: gates a working-precision run cannot
     be expected to reproduce."""
-    return {name: np.argwhere(np.abs(cache[key][1]) < tau) for name, key in RELU_LAYERS.items()}
+    return {name: (np.argwhere(np.abs(cache[key][1]) < tau) if cache.get(key) is not None else np.zeros((0, 2), int))
+            for name, key in RELU_LAYERS.items()}
 
 
 def v_layer_tie_delta(cache, dHv, idx):

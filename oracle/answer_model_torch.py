@@ -44,7 +44,7 @@ def gru_encode(E, q_len, Wg, bg, Wc, bc):
 
 
 def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", keep_att=0.8,
-            keep_joint=0.5, att_mask=None, joint_mask=None):
+            keep_joint=0.5, att_mask=None, joint_mask=None, joint_l_mask=None):
     """p: dict field -> torch tensor (requires_grad where wanted). Returns dict with loss, logit,
     att_score, pooled, condition, pred."""
     idx = batch["image_idx"].long()
@@ -73,11 +73,20 @@ def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", k
     elif variant == "vlmap_answer_no_noise":  # vqa/model_vlmap_answer_no_noise.py:122-125
         ql_in = q @ p["qp_w"] + p["qp_b"]
     Hl = fc_layer(ql_in, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"])
-    Jn = fc_layer(Hp * Hl, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
-    if joint_mask is not None:
-        Jn = Jn * joint_mask
-    Jd = Jn / keep_joint
-    logit = Jd @ p["ans_w"] + p["ans_b"]
+    if variant in ("vlmap_answer_noc", "vlmap_answer_nocarch"):   # vqa/model_vlmap_answer_noc.py:177-203
+        Jv = fc_layer(Hp, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
+        Jl = fc_layer(Hl, p["jl_w"], p["jl_b"], p["jl_gamma"], p["jl_beta"])
+        if joint_mask is not None:
+            Jv = Jv * joint_mask
+        if joint_l_mask is not None:
+            Jl = Jl * joint_l_mask
+        logit = (Jv / keep_joint) @ p["ans_w"] + p["ans_b"] + (Jl / keep_joint) @ p["al_w"] + p["al_b"]
+    else:
+        Jn = fc_layer(Hp * Hl, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
+        if joint_mask is not None:
+            Jn = Jn * joint_mask
+        Jd = Jn / keep_joint
+        logit = Jd @ p["ans_w"] + p["ans_b"]
     target = batch["answer_target"].to(logit.dtype)
     bce = torch.nn.functional.binary_cross_entropy_with_logits(logit, target, reduction="none")
     if variant != "standard":

@@ -36,7 +36,7 @@ def relu_tie_budget(cache, inter, ref_g, fields, tau, loss_scale=1.0, max_ties=9
         for f, dlt in O.v_layer_tie_delta(cache, inter["dHv"], idx).items():
             if f in budget:
                 budget[f] += np.abs(dlt)
-    for layer in ("qv", "pl", "ql", "joint"):
+    for layer in ("qv", "pl", "ql", "joint", "jl"):
         for idx in ties[layer]:
             flip = np.zeros(cache[O.RELU_LAYERS[layer]][1].shape, dtype=bool)
             flip[tuple(idx)] = True
@@ -71,6 +71,12 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
     eng.forward(seed=seed, step=step)
     eng.backward(loss_scale=loss_scale)
     att_mask, joint_mask = eng.dropout_masks(seed, step)
+    noc = cfg.variant in ("vlmap_answer_noc", "vlmap_answer_nocarch")
+    jl_kw = {}
+    if noc:  # the language branch draws its own dropout mask (a second tf.nn.dropout call)
+        from vqa_transfer_externaldata_b200 import lib as L_
+        jl_mask = eng.dropout_mask_site(L_.SITE_JOINT_L, seed, step)
+        jl_kw = {"joint_l_mask": jl_mask.cpu().numpy()}
     torch.cuda.synchronize()
     loss, report = eng.read_scalars()
     got = {"loss": loss, "report": report}
@@ -83,11 +89,11 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
     out, cache = O.forward(case["params"], case["feats"], case["nb"], case["batch"], case["m"],
                            variant=cfg.variant, keep_att=cfg.keep_att, keep_joint=cfg.keep_joint,
                            att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy(),
-                           operand_round=O.round_bf16 if emulate else None)
+                           operand_round=O.round_bf16 if emulate else None, **jl_kw)
     if emulate:  # the reference's own arithmetic, for the forward gates of the north star
         case["plain_out"], _ = O.forward(case["params"], case["feats"], case["nb"], case["batch"], case["m"],
                                          variant=cfg.variant, keep_att=cfg.keep_att, keep_joint=cfg.keep_joint,
-                                         att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy())
+                                         att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy(), **jl_kw)
     inter = {}
     gates = None
     if emulate:
@@ -102,12 +108,17 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
         hp = eng.peek_activation(L.ACT_HP, torch.float32, (Bn, cfg.L)).cpu().numpy()
         jd = eng.peek_activation(L.ACT_JD, torch.bfloat16, (Bn, cfg.J)).float().cpu().numpy()
         gates = {"qv": hq > 0, "ql": hl > 0, "pl": hp > 0, "joint": (jd > 0) | (joint_mask.cpu().numpy() == 0)}
+        drop = {"joint": joint_mask.cpu().numpy() == 0}
+        if noc:
+            jdl = eng.peek_activation(L.ACT_JDL, torch.bfloat16, (Bn, cfg.J)).float().cpu().numpy()
+            gates["jl"] = (jdl > 0) | (jl_kw["joint_l_mask"] == 0)
+            drop["jl"] = jl_kw["joint_l_mask"] == 0
         n_diff, n_all = 0, 0
         for layer, gate in gates.items():
             y = cache[O.RELU_LAYERS[layer]][1]
             own = y > 0
-            if layer == "joint":
-                own = own | (joint_mask.cpu().numpy() == 0)
+            if layer in drop:
+                own = own | drop[layer]
             diff = own != gate
             n_diff += int(diff.sum())
             n_all += diff.size

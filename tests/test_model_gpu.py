@@ -154,14 +154,17 @@ def test_gru_pair_kernels_match_single_cta_kernels_at_full_size():
 
 
 # ---- family variants: one more layer between the GRU state and q_linear_l ----
-@pytest.mark.parametrize("variant", ["vlmap_answer2", "vlmap_answer_no_noise"])
+VARIANTS = ["vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc"]
+
+
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_fp32_variants_small(variant):
     case = build_case(SMALL, variant=variant, precision="fp32", seed=21)
     got, ref, ref_g = run_both(case)
     _check(case, got, ref, ref_g, FP32_TOL)
 
 
-@pytest.mark.parametrize("variant", ["vlmap_answer2", "vlmap_answer_no_noise"])
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_bf16_variants_reference_shapes(variant):
     case = build_case(MID, variant=variant, precision="bf16", seed=22, num_images=40, batch=24)
     got, ref, ref_g = run_both(case)

@@ -27,10 +27,12 @@ def _setup(variant="vlmap_answer", seed=0, perturb=0.3, dims=TINY):
     m = O.answer_masks(c["A"], c["num_train_answer"], is_obj, is_attr, exist)
     att_mask = (rng.uniform(size=(c["B"], c["K"], c["D"])) < 0.8).astype(np.float64)
     joint_mask = (rng.uniform(size=(c["B"], c["J"])) < 0.5).astype(np.float64)
+    if "al_b" in p:   # noc: two heads add up; keep the absent columns at -100 in total like a single head would
+        p["al_b"] = np.where(exist > 0, p["al_b"], 0.0)
     return c, p, feats.astype(np.float64), nb, batch, m, att_mask, joint_mask
 
 
-VARIANTS = ["vlmap_answer", "standard", "vlmap_answer2", "vlmap_answer_no_noise"]
+VARIANTS = ["vlmap_answer", "standard", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -169,6 +171,8 @@ def test_relu_gate_flip_noise_model():
     rng = np.random.default_rng(0)
     flips, total, count = {}, 0, 0
     for name, key in O.RELU_LAYERS.items():
+        if cache.get(key) is None:   # layers of other variants (joint_l of noc)
+            continue
         y = cache[key][1]
         noise = 2e-3 * 3 * np.abs(y).mean() * rng.standard_normal(y.shape)
         flips[name] = (y > 0) != ((y + noise) > 0)

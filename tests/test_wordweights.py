@@ -44,7 +44,9 @@ def test_tf_names_and_frozen_sets():
 
 
 def test_importer_names():
-    assert importer.get_model_types() == ["vlmap_answer", "vlmap_answer2", "vlmap_answer_no_noise", "standard"]
+    assert importer.get_model_types() == ["vlmap_answer", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc",
+                                          "vlmap_answer_nocarch", "standard"]
+    assert issubclass(importer.get_model_class("vlmap_answer_nocarch"), importer.get_model_class("vlmap_answer_noc"))
     from vqa_transfer_externaldata_b200 import model as M
     assert importer.get_model_class("vlmap_answer2") is M.Answer2Model
     assert importer.get_model_class("vlmap_answer_no_noise") is M.NoNoiseModel

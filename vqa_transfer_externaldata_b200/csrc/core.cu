@@ -70,6 +70,8 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   planes(b.w.joint_w, L * J);
   planes(b.w.ans_w, J * A);
   planes(b.w.qp_w, L * L);
+  planes(b.w.jl_w, L * J);
+  planes(b.w.al_w, J * A);
 
   planes(b.v, B * K * Dv);
   b.nbox = a.take<int>(B);
@@ -92,6 +94,14 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
 
   b.zq = a.take<float>(B * D); b.hq = a.take<float>(B * D);
   b.lnq_mean = a.take<float>(B); b.lnq_rstd = a.take<float>(B);
+  planes(b.hl_op, B * L);
+  b.zjl = a.take<float>(B * J);
+  b.lnjl_mean = a.take<float>(B); b.lnjl_rstd = a.take<float>(B);
+  planes(b.jdl, B * J);
+  b.dJl = a.take<float>(B * J);
+  b.dzjl_f32 = a.take<float>(B * J);
+  planes(b.dzjl, B * J);
+  b.dXl = a.take<float>(B * L);
   b.zqp = a.take<float>(B * L); b.qp_f32 = a.take<float>(B * L);
   planes(b.qp, B * L);
   b.lnqp_mean = a.take<float>(B); b.lnqp_rstd = a.take<float>(B);
@@ -179,7 +189,7 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
     return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: Dv, D, L, J, A must be multiples of 8");
   if (c.D > 4096 || c.L > 4096 || c.J > 4096 || c.K > 256 || c.T > 64)
     return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: D, L, J <= 4096; K <= 256; T <= 64");
-  if (c.variant < VQA_VARIANT_VLMAP_ANSWER || c.variant > VQA_VARIANT_VLMAP_ANSWER_NO_NOISE)
+  if (c.variant < VQA_VARIANT_VLMAP_ANSWER || c.variant > VQA_VARIANT_VLMAP_ANSWER_NOC)
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown variant %d", c.variant);
   if ((c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE) && c.D != c.L)
     return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: the answer2 / no_noise variants need D == L (V_DIM == L_DIM as in the reference)");

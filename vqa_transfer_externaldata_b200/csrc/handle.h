@@ -9,7 +9,7 @@ namespace vqa {
 
 // Weight shadows in GEMM-operand form, same [in, out] layout as the fp32 TF variables.
 struct WeightShadows {
-  Planes v_w, gru_gates_w, gru_cand_w, qv_w, pl_w, ql_w, joint_w, ans_w, qp_w;
+  Planes v_w, gru_gates_w, gru_cand_w, qv_w, pl_w, ql_w, joint_w, ans_w, qp_w, jl_w, al_w;
 };
 
 // Everything forward keeps for backward + scratch, all inside the workspace.
@@ -38,6 +38,9 @@ struct Buffers {
   // extra question layer of the answer2 / no_noise variants: pre-activation, output (fp32 + operand planes), LN stats
   float* zqp; float* qp_f32; Planes qp; float* lnqp_mean; float* lnqp_rstd;
   float* dqp;                        // [B, L] gradient w.r.t. that layer's output
+  // second branch of the noc variants: Hl as a GEMM operand, joint_l pre-LN / stats / output, and its gradients
+  Planes hl_op; float* zjl; float* lnjl_mean; float* lnjl_rstd; Planes jdl;
+  float* dJl; float* dzjl_f32; Planes dzjl; float* dXl;
   float* dzqp_f32; Planes dzqp;      // [B, L] gradient w.r.t. its pre-activation
   float* att;      // [B, K]
   float* pooled;   // [B, Dv]

@@ -208,6 +208,6 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
                            float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s);
 
 // RNG stream ids (which dropout site a Philox draw belongs to)
-enum { RNG_STREAM_ATT = 1, RNG_STREAM_JOINT = 2 };
+enum { RNG_STREAM_ATT = 1, RNG_STREAM_JOINT = 2, RNG_STREAM_JOINT_L = 3 };
 
 }  // namespace vqa

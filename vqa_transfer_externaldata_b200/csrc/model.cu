@@ -110,6 +110,8 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
       {p->joint_w, &w.joint_w, c.L, c.J},
       {p->ans_w, &w.ans_w, c.J, c.A},
       {p->qp_w, &w.qp_w, c.L, c.L},   // answer2 / no_noise only (NULL otherwise)
+      {p->jl_w, &w.jl_w, c.L, c.J},   // noc only
+      {p->al_w, &w.al_w, c.J, c.A},   // noc only
   };
   // the refreshes are independent small memory-bound kernels: spread them over the auxiliary streams instead of
   // queueing them behind one another (they sit between the optimizer and the next step's first GEMM)
@@ -119,6 +121,7 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
   for (auto& it : items) {
     const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE;
     if (it.dst == &w.qp_w && !has_qp) continue;   // the base variants have no such layer
+    if ((it.dst == &w.jl_w || it.dst == &w.al_w) && c.variant != VQA_VARIANT_VLMAP_ANSWER_NOC) continue;
     if (!it.src) {
       if (!h->params_ready) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: the first call needs every weight");
       continue;  // unchanged since the last call
@@ -260,6 +263,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     RowLnFwd r{};
     r.rows = Bn; r.N = L; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta; r.keep = 1.f;
     r.y = b.hl; r.mean = b.lnl_mean; r.rstd = b.lnl_rstd;
+    if (c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC) { r.out_hi = b.hl_op.hi; r.out_lo = b.hl_op.lo; }   // joint_l reads Hl
     VQA_TRY(row_ln_relu_fwd_launch(r, s1));
   }
   // a3: Hq = relu(LN(q Wqv + b))                                    (:142-145)
@@ -289,7 +293,8 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   {
     RowLnFwd r{};
     r.rows = Bn; r.N = L; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta; r.keep = 1.f;
-    r.mul = b.hl; r.y = b.hp; r.out_hi = b.x.hi; r.out_lo = b.x.lo; r.mean = b.lnp_mean; r.rstd = b.lnp_rstd;
+    const bool noc_f = c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC;   // noc: no Hadamard, joint_v reads Hp itself
+    r.mul = noc_f ? nullptr : b.hl; r.y = b.hp; r.out_hi = b.x.hi; r.out_lo = b.x.lo; r.mean = b.lnp_mean; r.rstd = b.lnp_rstd;
     VQA_TRY(row_ln_relu_fwd_launch(r, s));
   }
   VQA_TRY(GemmB(Bn, J, L).a(b.x, 0, L, false).b(b.w.joint_w, 0, J, true).bias(p->joint_b).f32(b.zj, J).run(h, s));
@@ -302,6 +307,19 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   }
   // a7: logits against the (exported vlmap word) weights              (:183-185)
   VQA_TRY(GemmB(Bn, A, J).a(b.jd, 0, J, false).b(b.w.ans_w, 0, A, true).bias(p->ans_b).f32(b.logit, A).run(h, s));
+  if (c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC) {
+    // second branch (model_vlmap_answer_noc.py:184-203): Jl = dropout(relu(LN(Hl Wjl + b))), logit += Jl Wal + bal
+    if (!p->jl_w || !p->jl_b || !p->jl_gamma || !p->jl_beta || !p->al_w || !p->al_b)
+      return set_error(VQA_ERR_BAD_ARG, "vqa_forward: the noc variant needs jl_* and al_*");
+    VQA_TRY(GemmB(Bn, J, L).a(b.hl_op, 0, L, false).b(b.w.jl_w, 0, J, true).bias(p->jl_b).f32(b.zjl, J).run(h, s));
+    RowLnFwd r{};
+    r.rows = Bn; r.N = J; r.z = b.zjl; r.gamma = p->jl_gamma; r.beta = p->jl_beta;
+    r.keep = c.keep_joint; r.seed = seed; r.step = step; r.stream_id = RNG_STREAM_JOINT_L;
+    r.out_hi = b.jdl.hi; r.out_lo = b.jdl.lo; r.mean = b.lnjl_mean; r.rstd = b.lnjl_rstd;
+    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+    VQA_TRY(GemmB(Bn, A, J).a(b.jdl, 0, J, false).b(b.w.al_w, 0, A, true).bias(p->al_b).addend(b.logit, A)
+                .f32(b.logit, A).run(h, s));
+  }
   PH_END(VQA_PH_HEAD_FWD);
   PH_BEGIN(VQA_PH_LOSS);
   // a8 + a9: loss, pred, report                                       (:192-288)
@@ -368,11 +386,31 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   }
   if (g->joint_w) VQA_TRY(GemmB(L, J, Bn).a(b.x, 0, L, true).b(b.dzj, 0, J, true).f32(g->joint_w, J).run(h, s));
   if (g->joint_b) VQA_TRY(colsum_launch(b.dzj_f32, Bn, J, J, g->joint_b, b.scratch, s));
-  // dX = dZj Wj^T ; dHp = dX (.) Hl ; dHl = dX (.) Hp
+  // dX = dZj Wj^T ; dHp = dX (.) Hl ; dHl = dX (.) Hp   (noc: dHp = dX, dHl comes from the joint_l branch)
+  const bool noc = c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC;
   VQA_TRY(GemmB(Bn, L, J).a(b.dzj, 0, J, false).b(b.w.joint_w, 0, J, false).f32(b.dX, L).run(h, s));
+  const float* d_hl_src = b.dX;
+  if (noc) {
+    // joint_l branch: dJl = dlogit Wal^T -> dropout / ReLU / LN backward -> dHl = dZjl Wjl^T
+    if (g->al_w) VQA_TRY(GemmB(J, A, Bn).a(b.jdl, 0, J, true).b(b.dlogit, 0, A, true).f32(g->al_w, A).run(h, s));
+    if (g->al_b) VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->al_b, b.scratch, s));
+    VQA_TRY(GemmB(Bn, J, A).a(b.dlogit, 0, A, false).b(b.w.al_w, 0, A, false).f32(b.dJl, J).run(h, s));
+    RowLnBwd r{};
+    r.rows = Bn; r.N = J; r.dout = b.dJl; r.z = b.zjl; r.gamma = p->jl_gamma; r.beta = p->jl_beta;
+    r.mean = b.lnjl_mean; r.rstd = b.lnjl_rstd; r.keep = c.keep_joint; r.seed = seed; r.step = step;
+    r.stream_id = RNG_STREAM_JOINT_L; r.dz_f32 = b.dzjl_f32; r.dz_hi = b.dzjl.hi; r.dz_lo = b.dzjl.lo;
+    if (g->jl_gamma || g->jl_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (g->jl_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, J, J, g->jl_gamma, b.scratch, s));
+    if (g->jl_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, J, J, g->jl_beta, b.scratch, s));
+    if (g->jl_w) VQA_TRY(GemmB(L, J, Bn).a(b.hl_op, 0, L, true).b(b.dzjl, 0, J, true).f32(g->jl_w, J).run(h, s));
+    if (g->jl_b) VQA_TRY(colsum_launch(b.dzjl_f32, Bn, J, J, g->jl_b, b.scratch, s));
+    VQA_TRY(GemmB(Bn, L, J).a(b.dzjl, 0, J, false).b(b.w.jl_w, 0, J, false).f32(b.dXl, L).run(h, s));
+    d_hl_src = b.dXl;
+  }
   {
     RowLnBwd r{};
-    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = b.hl; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta;
+    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = noc ? nullptr : b.hl; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta;
     r.mean = b.lnp_mean; r.rstd = b.lnp_rstd; r.keep = 1.f; r.dz_f32 = b.dzp_f32; r.dz_hi = b.dzp.hi;
     r.dz_lo = b.dzp.lo;
     if (g->pl_gamma || g->pl_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
@@ -382,7 +420,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   }
   {
     RowLnBwd r{};
-    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
+    r.rows = Bn; r.N = L; r.dout = d_hl_src; r.mul = noc ? nullptr : b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
     r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi;
     r.dz_lo = b.dzl.lo;
     if (g->ql_gamma || g->ql_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
@@ -609,6 +647,23 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   return VQA_OK;
 }
 
+VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch, uint64_t seed, uint64_t step,
+                                        uint8_t* mask, void* stream) {
+  if (!h || !mask) return set_error(VQA_ERR_BAD_ARG, "vqa_dropout_mask_site: null argument");
+  const VqaConfig& c = h->cfg;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  switch (site) {
+    case RNG_STREAM_ATT:
+      return dropout_mask_launch(mask, static_cast<long long>(batch) * c.K * c.D, c.keep_att, seed, step, RNG_STREAM_ATT, s);
+    case RNG_STREAM_JOINT:
+    case RNG_STREAM_JOINT_L:
+      return dropout_mask_launch(mask, static_cast<long long>(batch) * c.J, c.keep_joint, seed, step,
+                                 static_cast<unsigned int>(site), s);
+    default:
+      return set_error(VQA_ERR_BAD_ARG, "vqa_dropout_mask_site: unknown site %d", site);
+  }
+}
+
 VQA_API VqaStatus vqa_set_early_gradients(VqaHandle h, int32_t enable) {
   if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_set_early_gradients: null handle");
   h->early_grads = enable != 0;
@@ -648,6 +703,7 @@ VQA_API VqaStatus vqa_peek_activation(VqaHandle h, int32_t which, const void** d
     case VQA_ACT_HL: *dev_ptr = b.hl; *bytes = Bn * c.L * 4; break;
     case VQA_ACT_HP: *dev_ptr = b.hp; *bytes = Bn * c.L * 4; break;
     case VQA_ACT_JD: *dev_ptr = b.jd.hi; *bytes = Bn * c.J * 2; break;
+    case VQA_ACT_JDL: *dev_ptr = b.jdl.hi; *bytes = Bn * c.J * 2; break;
     case VQA_ACT_Z: *dev_ptr = b.z; *bytes = Bn * c.K * c.D * (c.precision == VQA_PREC_FP32 ? 4 : 2); break;
     default: return set_error(VQA_ERR_BAD_ARG, "vqa_peek_activation: unknown activation %d", which);
   }

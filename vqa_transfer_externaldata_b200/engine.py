@@ -37,8 +37,21 @@ _QP_SCOPE = {"vlmap_answer2": "q_L_ft2", "vlmap_answer_no_noise": "q_L_mean"}   
 _QP_LEAF = {"qp_w": "fc/weights", "qp_b": "fc/biases", "qp_gamma": "LayerNorm/gamma", "qp_beta": "LayerNorm/beta"}
 
 
+_NOC_NAMES = {   # vqa/model_vlmap_answer_noc.py:177-203
+    "joint_w": "joint_v/fc/weights", "joint_b": "joint_v/fc/biases",
+    "joint_gamma": "joint_v/LayerNorm/gamma", "joint_beta": "joint_v/LayerNorm/beta",
+    "jl_w": "joint_l/fc/weights", "jl_b": "joint_l/fc/biases",
+    "jl_gamma": "joint_l/LayerNorm/gamma", "jl_beta": "joint_l/LayerNorm/beta",
+    "ans_w": "WordWeightAnswerV/fc/weights", "ans_b": "WordWeightAnswerV/fc/biases",
+    "al_w": "WordWeightAnswerL/fc/weights", "al_b": "WordWeightAnswerL/fc/biases",
+}
+_NOC = ("vlmap_answer_noc", "vlmap_answer_nocarch")
+
+
 def tf_name(field, variant):
     """Checkpoint variable name of a parameter field for a model_type."""
+    if variant in _NOC and field in _NOC_NAMES:
+        return _NOC_NAMES[field]
     if field in _QP_LEAF:
         return _QP_SCOPE[variant] + "/" + _QP_LEAF[field]
     if variant == "standard":  # vqa/model_standard.py:251-275
@@ -90,8 +103,11 @@ def frozen_fields(variant):
         return set()
     # vlmap_answer, vlmap_answer2 (model_vlmap_answer2.py:69-78) and vlmap_answer_no_noise (:66-74) freeze the same
     # four scopes; their extra question layer trains
-    return {f for f in L.PARAM_FIELDS if TF_NAMES[f].split("/")[0] in
-            ("q_linear_l", "pooled_linear_l", "joint_fc", "WordWeightAnswer")}
+    fz = {f for f in L.PARAM_FIELDS if TF_NAMES[f].split("/")[0] in
+          ("q_linear_l", "pooled_linear_l", "joint_fc", "WordWeightAnswer")}
+    if variant in _NOC:   # model_vlmap_answer_noc.py:78-88: joint_v, joint_l, WordWeightAnswerV/L frozen as well
+        fz |= {"jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b"}
+    return fz
 
 
 def _align(n, a=64):
@@ -449,6 +465,15 @@ class Engine:
         L.check(self.lib.vqa_dropout_masks(self.h, Bn, C.c_uint64(seed), C.c_uint64(step), att.data_ptr(),
                                            joint.data_ptr(), self._stream()))
         return att, joint
+
+    def dropout_mask_site(self, site, seed, step, batch=None):
+        """0 / 1 keep mask of one dropout site (L.SITE_*) for (seed, step)."""
+        Bn = self.batch_size if batch is None else batch
+        shape = (Bn, self.cfg.K, self.cfg.D) if site == L.SITE_ATT else (Bn, self.cfg.J)
+        out = torch.empty(*shape, dtype=torch.uint8, device=self.device)
+        L.check(self.lib.vqa_dropout_mask_site(self.h, site, Bn, C.c_uint64(seed), C.c_uint64(step), out.data_ptr(),
+                                               self._stream()))
+        return out
 
     def peek_activation(self, which, dtype, shape):
         """Copy of an activation the last forward saved in the workspace (vqa_peek_activation)."""

@@ -3,10 +3,10 @@
 Only the hot-path family is served; the other names of the reference raise NotImplementedError naming the
 scope decision instead of silently mapping to something else."""
 
-SUPPORTED = ("vlmap_answer", "vlmap_answer2", "vlmap_answer_no_noise", "standard")
+SUPPORTED = ("vlmap_answer", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc", "vlmap_answer_nocarch",
+             "standard")
 # re-wirings of the same kernels planned next (SURVEY 8a-11); not built yet
-PLANNED = ("vlmap_answer_adapt", "vlmap_answer_noc",
-           "vlmap_answer_nocarch", "vlmap_answer_full", "vlmap_answer_ent", "vlmap_answer_vqa_all",
+PLANNED = ("vlmap_answer_adapt", "vlmap_answer_full", "vlmap_answer_ent", "vlmap_answer_vqa_all",
            "vlmap_answer_vqa_all2")
 OUT_OF_SCOPE = ("vqa", "standard_testmask", "standard_word2vec", "vlmap_only", "vlmap_finetune")
 
@@ -16,7 +16,11 @@ def get_model_types():
 
 
 def get_model_class(model_type="vlmap_answer"):
-    from .model import Answer2Model, Model, NoNoiseModel, StandardModel
+    from .model import Answer2Model, Model, NocArchModel, NocModel, NoNoiseModel, StandardModel
+    if model_type == "vlmap_answer_noc":
+        return NocModel
+    if model_type == "vlmap_answer_nocarch":
+        return NocArchModel
     if model_type == "vlmap_answer":
         return Model
     if model_type == "vlmap_answer2":

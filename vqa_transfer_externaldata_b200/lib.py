@@ -14,8 +14,9 @@ LIB_PATH = os.path.join(HERE, "libvqa_answer_b200.so")
 VQA_OK = 0
 VQA_ERR_BAD_ARG, VQA_ERR_BAD_SHAPE, VQA_ERR_WORKSPACE = -1, -2, -3
 VQA_ERR_CUDA, VQA_ERR_NO_DEVICE, VQA_ERR_STATE = -4, -5, -6
-VARIANT_VLMAP_ANSWER, VARIANT_STANDARD, VARIANT_VLMAP_ANSWER2, VARIANT_VLMAP_ANSWER_NO_NOISE = 0, 1, 2, 3
-VARIANTS = {"vlmap_answer": 0, "standard": 1, "vlmap_answer2": 2, "vlmap_answer_no_noise": 3}
+VARIANT_VLMAP_ANSWER, VARIANT_STANDARD, VARIANT_VLMAP_ANSWER2, VARIANT_VLMAP_ANSWER_NO_NOISE, VARIANT_VLMAP_ANSWER_NOC = range(5)
+VARIANTS = {"vlmap_answer": 0, "standard": 1, "vlmap_answer2": 2, "vlmap_answer_no_noise": 3,
+            "vlmap_answer_noc": 4, "vlmap_answer_nocarch": 4}   # nocarch is the same graph (model_vlmap_answer_nocarch.py)
 PREC_BF16, PREC_FP32 = 0, 1
 
 REPORT_KEYS = [
@@ -29,7 +30,8 @@ PER_SAMPLE_KEYS = [
 ]
 
 NUM_PHASES = 14
-ACT_HQ, ACT_HL, ACT_HP, ACT_JD, ACT_Z = range(5)
+ACT_HQ, ACT_HL, ACT_HP, ACT_JD, ACT_Z, ACT_JDL = range(6)
+SITE_ATT, SITE_JOINT, SITE_JOINT_L = 1, 2, 3   # dropout sites of vqa_dropout_mask_site
 
 PARAM_FIELDS = [
     "embed", "v_w", "v_b", "v_gamma", "v_beta", "gru_gates_w", "gru_gates_b", "gru_cand_w",
@@ -53,15 +55,17 @@ class VqaConfig(C.Structure):
 
 # the extra question layer of model_vlmap_answer2 (q_L_ft2: FC + LayerNorm + tanh) and model_vlmap_answer_no_noise
 # (q_L_mean: FC only); NULL in the struct for the other variants
-EXTRA_FIELDS = ["qp_w", "qp_b", "qp_gamma", "qp_beta"]
+EXTRA_FIELDS = ["qp_w", "qp_b", "qp_gamma", "qp_beta", "jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b"]
 
 
 def param_fields(variant):
     """Parameter fields a model_type owns, in struct order."""
     if variant == "vlmap_answer2":
-        return PARAM_FIELDS + EXTRA_FIELDS
+        return PARAM_FIELDS + EXTRA_FIELDS[:4]
     if variant == "vlmap_answer_no_noise":
         return PARAM_FIELDS + EXTRA_FIELDS[:2]
+    if variant in ("vlmap_answer_noc", "vlmap_answer_nocarch"):   # joint_l + WordWeightAnswerL
+        return PARAM_FIELDS + EXTRA_FIELDS[4:]
     return list(PARAM_FIELDS)
 
 
@@ -139,6 +143,7 @@ SYMBOLS = {
     "vqa_phase_name": (C.c_char_p, [C.c_int32]),
     "vqa_gemm": (C.c_int32, [_P, C.POINTER(VqaGemmDesc), _P]),
     "vqa_split_bf16": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P]),
+    "vqa_dropout_mask_site": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "vqa_multimem_all_reduce": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vqa_set_early_gradients": (C.c_int32, [_P, C.c_int32]),
     "vqa_stream_wait_early_gradients": (C.c_int32, [_P, _P]),

@@ -125,13 +125,20 @@ class Model(object):
              ("B", "K", "Dv", "D", "L", "J", "A", "T", "W", "Vq", "num_train_answer")}
         p, _ = init_params(c, seed=seed, variant="standard")  # Xavier head; replaced below for vlmap_answer
         extra, _ = init_params(c, seed=seed + 1, variant=self.MODEL_TYPE)
-        p.update({k: v for k, v in extra.items() if k.startswith("qp_")})   # q_L_ft2 / q_L_mean of the variants
+        p.update({k: v for k, v in extra.items() if k.startswith(("qp_", "jl_", "al_"))})   # layers of the variants
         glove = getattr(self.config, "glove_embed", None)
         if glove is not None:  # LearnGloVe (vlmap/modules.py:415-448): rows by vocabulary word
             p["embed"] = np.asarray(glove, np.float32)
         if self.MODEL_TYPE != "standard":
-            w, b = wordweights.word_weight_answer(self.engine_config.J, self.answer_dict, self.word_weight_dir)
-            p["ans_w"], p["ans_b"] = w, b
+            if self.MODEL_TYPE in ("vlmap_answer_noc", "vlmap_answer_nocarch"):
+                # vqa/model_vlmap_answer_noc.py:189-201: v_class_* / l_class_* of export_noc_word_weights.py:74-82
+                p["ans_w"], p["ans_b"] = wordweights.word_weight_answer(
+                    self.engine_config.J, self.answer_dict, self.word_weight_dir, "v_class_weights", "v_class_biases")
+                p["al_w"], p["al_b"] = wordweights.word_weight_answer(
+                    self.engine_config.J, self.answer_dict, self.word_weight_dir, "l_class_weights", "l_class_biases")
+            else:
+                w, b = wordweights.word_weight_answer(self.engine_config.J, self.answer_dict, self.word_weight_dir)
+                p["ans_w"], p["ans_b"] = w, b
         return p
 
     # ---- checkpoint contract: tensors keyed by TF variable names ---------------------------------
@@ -220,6 +227,17 @@ class Answer2Model(Model):
 class NoNoiseModel(Model):
     """vqa/model_vlmap_answer_no_noise.py: q_L_mean = FC(q) (linear) feeds q_linear_l."""
     MODEL_TYPE = "vlmap_answer_no_noise"
+
+
+class NocModel(Model):
+    """vqa/model_vlmap_answer_noc.py (and the identical model_vlmap_answer_nocarch.py): no Hadamard fusion; a visual
+    branch (pooled_linear_l -> joint_v -> WordWeightAnswerV) and a language branch (q_linear_l -> joint_l ->
+    WordWeightAnswerL), logits added; heads initialised from v_/l_class_weights of export_noc_word_weights.py."""
+    MODEL_TYPE = "vlmap_answer_noc"
+
+
+class NocArchModel(NocModel):
+    MODEL_TYPE = "vlmap_answer_nocarch"
 
 
 class StandardModel(Model):

@@ -29,8 +29,14 @@ PARAM_SHAPES = {
     # extra question layer of vlmap_answer2 (q_L_ft2) / vlmap_answer_no_noise (q_L_mean); V_DIM == L_DIM there
     "qp_w": lambda c: (c["L"], c["L"]), "qp_b": lambda c: (c["L"],),
     "qp_gamma": lambda c: (c["L"],), "qp_beta": lambda c: (c["L"],),
+    # second branch of vlmap_answer_noc / nocarch: joint_l and WordWeightAnswerL
+    "jl_w": lambda c: (c["L"], c["J"]), "jl_b": lambda c: (c["J"],),
+    "jl_gamma": lambda c: (c["J"],), "jl_beta": lambda c: (c["J"],),
+    "al_w": lambda c: (c["J"], c["A"]), "al_b": lambda c: (c["A"],),
 }
-EXTRA_FIELDS = {"vlmap_answer2": ("qp_w", "qp_b", "qp_gamma", "qp_beta"), "vlmap_answer_no_noise": ("qp_w", "qp_b")}
+_NOC = ("jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b")
+EXTRA_FIELDS = {"vlmap_answer2": ("qp_w", "qp_b", "qp_gamma", "qp_beta"), "vlmap_answer_no_noise": ("qp_w", "qp_b"),
+                "vlmap_answer_noc": _NOC, "vlmap_answer_nocarch": _NOC}
 
 
 def dims(B=512, K=36, Dv=2048, D=1024, L=1024, J=None, A=3000, T=14, W=300, Vq=8192,
@@ -51,7 +57,7 @@ def init_params(c, seed=4321, variant="vlmap_answer", perturb=0.0, present_frac=
     rng = np.random.default_rng(seed)
     p = {}
     for name, shp in PARAM_SHAPES.items():
-        if name.startswith("qp_") and name not in EXTRA_FIELDS.get(variant, ()):
+        if name.startswith(("qp_", "jl_", "al_")) and name not in EXTRA_FIELDS.get(variant, ()):
             continue
         shape = shp(c)
         if name == "embed":
@@ -73,12 +79,18 @@ def init_params(c, seed=4321, variant="vlmap_answer", perturb=0.0, present_frac=
         w[:, ~present] = 0.0
         b[~present] = -100.0
         p["ans_w"], p["ans_b"] = w, b
+        if "al_w" in p:   # the L head is remapped from l_class_weights of the same export: same absent answers
+            wl = (rng.standard_normal((c["J"], c["A"])) * 0.05).astype(np.float32)
+            bl = (rng.standard_normal(c["A"]) * 0.5).astype(np.float32)
+            wl[:, ~present] = 0.0
+            bl[~present] = -100.0
+            p["al_w"], p["al_b"] = wl, bl
         exist = present.astype(np.float32)
     if perturb > 0:
         for name in p:
             if name.endswith("_gamma"):
                 p[name] = (p[name] + perturb * rng.standard_normal(p[name].shape)).astype(np.float32)
-            elif name.endswith(("_beta", "_b")) and name != "ans_b":
+            elif name.endswith(("_beta", "_b")) and name not in ("ans_b", "al_b"):
                 p[name] = (p[name] + perturb * rng.standard_normal(p[name].shape)).astype(np.float32)
     return p, exist
 
