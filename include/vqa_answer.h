@@ -50,7 +50,21 @@ enum {
   /* vqa/model_vlmap_answer_noc.py:177-203 (model_vlmap_answer_nocarch.py is the same graph): no Hadamard fusion;
    * pooled_linear_l -> joint_v -> WordWeightAnswerV and q_linear_l -> joint_l -> WordWeightAnswerL, each with its own
    * dropout(0.5), logits added; both heads frozen */
-  VQA_VARIANT_VLMAP_ANSWER_NOC = 4
+  VQA_VARIANT_VLMAP_ANSWER_NOC = 4,
+  /* vqa/model_vlmap_answer_full.py:124-134,166,217-223,272-276: q_linear_l reads q_L_mean + N(0,1) * sqrt(exp(
+   * q_L_log_sigma_sq)) (both linear layers of q, trained); loss += 0.1 * KL(q_L_mean, q_L_log_sigma_sq) */
+  VQA_VARIANT_VLMAP_ANSWER_FULL = 5,
+  /* vqa/model_vlmap_answer_vqa_all.py:188-244: frozen word-weight logits with the absent answers filled by the row
+   * minimum, plus TunedWordWeightAnswer(joint) (trained; :215-216 feeds `joint`, not tuned_joint); loss =
+   * (BCE(fixed) + BCE(fixed + tuned)) * train_mask; logit / pred from fixed + tuned */
+  VQA_VARIANT_VLMAP_ANSWER_VQA_ALL = 6,
+  /* vqa/model_vlmap_answer_vqa_all2.py:188-243: no fill; loss = BCE(fixed) * train_mask + BCE(tuned); pred =
+   * argmax(fixed * test_mask + tuned * train_mask); logit = fixed + tuned */
+  VQA_VARIANT_VLMAP_ANSWER_VQA_ALL2 = 7,
+  /* vqa/model_vlmap_answer_adapt.py:132-142: attention pools v_adapt = relu(LN(FC(V))) [K, D] (trained) instead of
+   * the raw features, so the pooled vector is D-wide and pooled_linear_l/fc/weights is [D, L] */
+  VQA_VARIANT_VLMAP_ANSWER_ADAPT = 8,
+  VQA_NUM_VARIANTS
 };
 
 /* arithmetic mode of the dense contractions */
@@ -124,6 +138,17 @@ typedef struct VqaParams {
   float* jl_beta;     /* joint_l/LayerNorm/beta                       [J]          */
   float* al_w;        /* WordWeightAnswerL/fc/weights                 [J, A]       */
   float* al_b;        /* WordWeightAnswerL/fc/biases                  [A]          */
+  /* full: the log-variance layer next to q_L_mean (= qp_w / qp_b)                    */
+  float* qs_w;        /* q_L_log_sigma_sq/fc/weights                  [L, L]       */
+  float* qs_b;        /* q_L_log_sigma_sq/fc/biases                   [L]          */
+  /* vqa_all / vqa_all2: the tuned head (trained)                                     */
+  float* tw_w;        /* TunedWordWeightAnswer/fc/weights             [J, A]       */
+  float* tw_b;        /* TunedWordWeightAnswer/fc/biases              [A]          */
+  /* adapt: the pooled projection (trained); pl_w is [D, L] in that variant           */
+  float* va_w;        /* v_adapt/fc/weights                           [Dv, D]      */
+  float* va_b;        /* v_adapt/fc/biases                            [D]          */
+  float* va_gamma;    /* v_adapt/LayerNorm/gamma                      [D]          */
+  float* va_beta;     /* v_adapt/LayerNorm/beta                       [D]          */
 } VqaParams;
 #define VQA_NUM_PARAM_TENSORS 29
 
@@ -166,6 +191,9 @@ enum {
   VQA_REPORT_MAX_EXIST_ACC,
   VQA_REPORT_TEST_MAX_ACC,
   VQA_REPORT_TEST_MAX_EXIST_ACC,
+  /* vqa/model_vlmap_answer_full.py:221-223 (0 for every other variant) */
+  VQA_REPORT_LATENT_LOSS,
+  VQA_REPORT_TRAIN_LATENT_LOSS,
   VQA_NUM_REPORT
 };
 
@@ -189,7 +217,7 @@ typedef struct VqaOutputs {
   int32_t* pred;      /* [batch]      model.output['pred'] (argmax, first index on ties)      */
   float* per_sample;  /* [VQA_NUM_PER_SAMPLE, batch]                                          */
   float* condition;   /* [batch, L]   model.heavy_output['condition'] (final GRU state)       */
-  float* pooled;      /* [batch, Dv]  model.mid_result['pooled_V_ft']                         */
+  float* pooled;      /* [batch, Dv]  model.mid_result['pooled_V_ft'] ([batch, D] in the adapt variant) */
 } VqaOutputs;
 
 typedef struct VqaHandle_t* VqaHandle;
@@ -249,6 +277,12 @@ VQA_API VqaStatus vqa_stream_wait_early_gradients(VqaHandle h, void* stream);
 VQA_API VqaStatus vqa_multimem_all_reduce(void* multicast_ptr, int64_t n, int32_t rank, int32_t world,
                                           int32_t num_ctas, void* stream);
 
+/* The N(0, 1) draw of the full variant's reparameterisation for (seed, step): noise [batch, L] fp32 (Philox4x32-10
+ * + Box-Muller; tf.random_normal(seed=123) of vqa/model_vlmap_answer_full.py:133 is not bit-reproducible outside TF,
+ * so parity tests feed the oracle this very draw, as they do with the dropout masks). */
+VQA_API VqaStatus vqa_reparam_noise(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step, float* noise,
+                                    void* stream);
+
 VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step,
                                     uint8_t* att_mask, uint8_t* joint_mask, void* stream);
 
@@ -262,6 +296,7 @@ enum {
   VQA_ACT_JD,       /* dropout(relu(LN(X Wj + b)))    [batch, J]  bf16 (hi plane)                 */
   VQA_ACT_Z,        /* pre-LN v-projection            [batch*K, D] bf16 (PREC_BF16) / fp32        */
   VQA_ACT_JDL,      /* noc: dropout(relu(LN(Hl Wjl + b))) [batch, J]  bf16 (hi plane)                 */
+  VQA_ACT_VA,       /* adapt: v_adapt = relu(LN(V Wa + b)) [batch*K, D] bf16 (hi plane)           */
   VQA_NUM_ACT
 };
 VQA_API VqaStatus vqa_peek_activation(VqaHandle h, int32_t which, const void** dev_ptr, uint64_t* bytes);

@@ -17,6 +17,13 @@ Reference files followed (paths under /root/reference):
   vqa/model_vlmap_answer2.py:127-131,164         q_L_ft2 = tanh(LN(FC(q))) feeds q_linear_l  ('vlmap_answer2')
   vqa/model_vlmap_answer_no_noise.py:122-125,157 q_L_mean = FC(q) feeds q_linear_l            ('vlmap_answer_no_noise')
   vqa/model_vlmap_answer_noc.py:177-203 (= _nocarch.py) two heads joint_v / joint_l, logits summed ('vlmap_answer_noc')
+  vqa/model_vlmap_answer_full.py:124-134,166,217-223,272-276  q_L_mean + noise * sqrt(exp(q_L_log_sigma_sq)) feeds
+                                      q_linear_l; loss += 0.1 * KL                                ('vlmap_answer_full')
+  vqa/model_vlmap_answer_vqa_all.py:188-244   frozen head with min-logit fill of absent answers + TunedWordWeightAnswer
+                                      on the SAME joint (:215-216), two BCE terms                 ('vlmap_answer_vqa_all')
+  vqa/model_vlmap_answer_vqa_all2.py:188-243  same without the fill; BCE(tuned) unmasked; pred from
+                                      logit * test_mask + tuned * train_mask                       ('vlmap_answer_vqa_all2')
+  vqa/model_vlmap_answer_adapt.py:132-142     v_adapt = relu(LN(FC(V))) is what attention pools     ('vlmap_answer_adapt')
   vlmap/modules.py:630-650            fc_layer = fully_connected -> layer_norm -> activation
   vlmap/modules.py:67-97              hadamard_attention
   vlmap/modules.py:23-39              attention_pooling
@@ -57,8 +64,20 @@ FROZEN_SCOPES_VLMAP_ANSWER = ("q_linear_l", "pooled_linear_l", "joint_fc", "Word
 
 # extra question layer of the two variants (scope q_L_ft2 / q_L_mean: trained, never frozen)
 NOC_FIELDS = ["jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b"]   # joint_l and WordWeightAnswerL (frozen)
+TUNED_FIELDS = ["tw_w", "tw_b"]                     # TunedWordWeightAnswer (trained), model_vlmap_answer_vqa_all.py:215-219
+ADAPT_FIELDS = ["va_w", "va_b", "va_gamma", "va_beta"]   # v_adapt (trained), model_vlmap_answer_adapt.py:132-135
 EXTRA_FIELDS = {"vlmap_answer2": ["qp_w", "qp_b", "qp_gamma", "qp_beta"], "vlmap_answer_no_noise": ["qp_w", "qp_b"],
-                "vlmap_answer_noc": NOC_FIELDS, "vlmap_answer_nocarch": NOC_FIELDS}
+                "vlmap_answer_noc": NOC_FIELDS, "vlmap_answer_nocarch": NOC_FIELDS,
+                "vlmap_answer_full": ["qp_w", "qp_b", "qs_w", "qs_b"],   # q_L_mean, q_L_log_sigma_sq (:124-131)
+                "vlmap_answer_vqa_all": TUNED_FIELDS, "vlmap_answer_vqa_all2": TUNED_FIELDS,
+                "vlmap_answer_adapt": ADAPT_FIELDS}
+EXTRA_TF_NAMES = {
+    "qs_w": "q_L_log_sigma_sq/fc/weights", "qs_b": "q_L_log_sigma_sq/fc/biases",
+    "tw_w": "TunedWordWeightAnswer/fc/weights", "tw_b": "TunedWordWeightAnswer/fc/biases",
+    "va_w": "v_adapt/fc/weights", "va_b": "v_adapt/fc/biases",
+    "va_gamma": "v_adapt/LayerNorm/gamma", "va_beta": "v_adapt/LayerNorm/beta",
+}
+LATENT_LOSS_WEIGHT = 0.1   # model_vlmap_answer_full.py:33
 
 
 def param_fields(variant):
@@ -231,14 +250,21 @@ def _normal(num, den):
     return den if den == 0 else num / den
 
 
-def metrics(logit, target, m, use_train_mask=True):
-    """returns (train_loss, report dict, per-sample dict, pred)"""
+def metrics(logit, target, m, use_train_mask=True, loss_terms=None, pred_logit=None):
+    """returns (train_loss, report dict, per-sample dict, pred).
+    loss_terms: list of (logits, masked) -- the BCE terms that are summed (vqa_all: two terms, both train-masked,
+    model_vlmap_answer_vqa_all.py:234-243; vqa_all2: untuned masked + tuned unmasked, _vqa_all2.py:231-239);
+    default = one term on `logit`. pred_logit: what argmax runs on (default `logit`)."""
     B, A = logit.shape
-    loss = bce_with_logits(logit, target)
-    tmask = m["train"] if use_train_mask else np.ones(A)
-    train_loss = (loss * tmask).sum(axis=1).mean()
-    report_loss = loss.sum(axis=1).mean()
-    pred = np.argmax(logit, axis=1).astype(np.int32)  # first maximal index (tf.argmax)
+    if loss_terms is None:
+        loss_terms = [(logit, use_train_mask)]
+    train_loss, report_loss = 0.0, 0.0
+    for x, masked in loss_terms:
+        loss = bce_with_logits(x, target)
+        tmask = m["train"] if masked else np.ones(A)
+        train_loss = train_loss + (loss * tmask).sum(axis=1).mean()
+        report_loss = report_loss + loss.sum(axis=1).mean()
+    pred = np.argmax(logit if pred_logit is None else pred_logit, axis=1).astype(np.int32)  # first maximal index (tf.argmax)
     oh = np.zeros((B, A))
     oh[np.arange(B), pred] = 1.0
     te, ob, at, ex, tm = m["test"], m["obj"], m["attr"], m["exist"], m["train"]
@@ -281,11 +307,12 @@ def metrics(logit, target, m, use_train_mask=True):
 # ------------------------------------------------------------------------------------------------
 # the graph
 # ------------------------------------------------------------------------------------------------
-GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joint_w", "ans_w", "qp_w", "jl_w", "al_w")
+GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joint_w", "ans_w", "qp_w", "jl_w", "al_w",
+                "qs_w", "tw_w", "va_w")
 
 
 def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0.8, keep_joint=0.5,
-            att_mask=None, joint_mask=None, operand_round=None, joint_l_mask=None):
+            att_mask=None, joint_mask=None, operand_round=None, joint_l_mask=None, noise=None):
     """Model.build() forward. p: dict field -> fp64 array (TF layout [in,out]).
     features [N,K,Dv], num_boxes [N]; batch: image_idx [B], q_intseq [B,T], q_intseq_len [B],
     answer_target [B,A]; att_mask [B,K,D] / joint_mask [B,J] are the 0/1 keep masks tf.nn.dropout
@@ -322,7 +349,11 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     smax = s.max(axis=1, keepdims=True)
     e = np.exp(s - smax)
     a = e / e.sum(axis=1, keepdims=True)                     # exact zeros at masked slots
-    P = np.einsum("bk,bkd->bd", a, V)                        # attention_pooling of the RAW features
+    va_cache, Vp = None, V
+    if variant == "vlmap_answer_adapt":   # model_vlmap_answer_adapt.py:132-142: pool relu(LN(FC(V))) instead of V
+        Vp, va_cache = fc_ln_relu_fwd(V, p["va_w"], p["va_b"], p["va_gamma"], p["va_beta"], qz=q)
+        Vp = q(Vp)                       # the device stores v_adapt as the pooling kernel's operand plane
+    P = np.einsum("bk,bkd->bd", a, Vp)                       # attention_pooling of the RAW features
 
     Hp, p_cache = fc_ln_relu_fwd(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"], q=q)   # :163-167
     # the variants put one more layer between the GRU state and q_linear_l
@@ -338,6 +369,14 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
         xq = q(qs)
         ql_in = xq @ p["qp_w"] + p["qp_b"]
         qp_cache = (xq, None, None)
+    elif variant == "vlmap_answer_full":       # model_vlmap_answer_full.py:124-134
+        xq = q(qs)
+        mean = xq @ p["qp_w"] + p["qp_b"]
+        lss = xq @ p["qs_w"] + p["qs_b"]
+        sigma = np.sqrt(np.exp(lss))
+        nz = np.zeros_like(mean) if noise is None else f64(noise)
+        ql_in = mean + nz * sigma
+        qp_cache = (xq, mean, (lss, sigma, nz))
     Hl, l_cache = fc_ln_relu_fwd(ql_in, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"], q=q)  # :170-174
     noc = variant in ("vlmap_answer_noc", "vlmap_answer_nocarch")
     jl_cache, jlm, Jld = None, None, None
@@ -360,14 +399,41 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
         logit = (Jd @ p["ans_w"] + p["ans_b"]) + (Jld @ p["al_w"] + p["al_b"])
 
     use_tm = variant != "standard"
-    train_loss, report, ps, pred = metrics(logit, target, m, use_train_mask=use_tm)
-    out = {"loss": train_loss, "report": report, "att_score": a, "logit": logit, "pred": pred,
+    tuned_cache = None
+    if variant in ("vlmap_answer_vqa_all", "vlmap_answer_vqa_all2"):
+        logit0 = logit
+        ex = m["exist"]
+        if variant == "vlmap_answer_vqa_all":   # _vqa_all.py:192-194: absent answers take the row minimum
+            mn = logit0.min(axis=1, keepdims=True)
+            L1 = logit0 * ex + mn * (1.0 - ex)
+        else:
+            L1 = logit0
+        tuned = Jd @ p["tw_w"] + p["tw_b"]      # fc_layer(joint, ...) -- `joint`, not tuned_joint (:215-216)
+        logit = L1 + tuned                      # output['logit'] (:225)
+        if variant == "vlmap_answer_vqa_all":
+            terms, pred_logit = [(L1, True), (logit, True)], logit
+        else:
+            terms = [(L1, True), (tuned, False)]
+            pred_logit = L1 * m["test"] + tuned * m["train"]
+        tuned_cache = (logit0, L1, tuned)
+        train_loss, report, ps, pred = metrics(logit, target, m, loss_terms=terms, pred_logit=pred_logit)
+    else:
+        train_loss, report, ps, pred = metrics(logit, target, m, use_train_mask=use_tm)
+    total_loss = train_loss
+    if variant == "vlmap_answer_full":          # _full.py:217-223, 272-276
+        _, mean, (lss, _, _) = qp_cache
+        latent = -0.5 * (1.0 + lss - mean ** 2 - np.exp(lss)).sum(axis=1).mean()
+        report["latent_loss"] = latent
+        report["train_latent_loss"] = LATENT_LOSS_WEIGHT * latent
+        total_loss = train_loss + LATENT_LOSS_WEIGHT * latent
+    out = {"loss": total_loss, "report": report, "att_score": a, "logit": logit, "pred": pred,
            "per_sample": ps, "condition": cond, "pooled": P}
     cache = dict(V=V, nbox=nbox, q_ids=q_ids, q_len=q_len, target=target, v_cache=v_cache, Hv=Hv,
                  gru_steps=gru_steps, q=qs, q_cache=q_cache, Hq=Hq, am=am, F=F, a=a, P=P, p_cache=p_cache,
                  Hp=Hp, l_cache=l_cache, Hl=Hl, X=X, j_cache=j_cache, jm=jm, Jd=Jd, logit=logit,
                  keep_att=keep_att, keep_joint=keep_joint, use_tm=use_tm, m=m, W=W, p=p, variant=variant,
-                 qp_cache=qp_cache, jl_cache=jl_cache, jlm=jlm, Jld=Jld, noc=noc)
+                 qp_cache=qp_cache, jl_cache=jl_cache, jlm=jlm, Jld=Jld, noc=noc, tuned_cache=tuned_cache,
+                 va_cache=va_cache, Vp=Vp)
     return out, cache
 
 
@@ -382,10 +448,29 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
     B, A = c["logit"].shape
     tmask = c["m"]["train"] if c["use_tm"] else np.ones(A)
     g = {}
-    dx = (sigmoid(c["logit"]) - c["target"]) * tmask / B * loss_scale
+    if c.get("tuned_cache") is not None:
+        logit0, L1, tuned = c["tuned_cache"]
+        z, ex = c["target"], c["m"]["exist"]
+        if c["variant"] == "vlmap_answer_vqa_all":
+            d_tuned = (sigmoid(L1 + tuned) - z) * tmask / B * loss_scale
+            dL1 = d_tuned + (sigmoid(L1) - z) * tmask / B * loss_scale
+            # tf.reduce_min gradient: shared equally by the minimal entries (math_grad._MinOrMaxGrad)
+            ind = (logit0 == logit0.min(axis=1, keepdims=True)).astype(np.float64)
+            dmin = (dL1 * (1.0 - ex)).sum(axis=1, keepdims=True)
+            dx = dL1 * ex + ind / ind.sum(axis=1, keepdims=True) * dmin
+        else:
+            dx = (sigmoid(L1) - z) * tmask / B * loss_scale
+            d_tuned = (sigmoid(tuned) - z) / B * loss_scale
+        g["tw_w"] = c["Jd"].T @ d_tuned
+        g["tw_b"] = d_tuned.sum(0)
+    else:
+        dx = (sigmoid(c["logit"]) - c["target"]) * tmask / B * loss_scale
+        d_tuned = None
     g["ans_w"] = c["Jd"].T @ dx
     g["ans_b"] = dx.sum(0)
     dJd = dx @ p["ans_w"].T
+    if d_tuned is not None:
+        dJd = dJd + d_tuned @ p["tw_w"].T
     dJn = dJd * c["jm"] / c["keep_joint"]
     dX, g["joint_w"], g["joint_b"], g["joint_gamma"], g["joint_beta"] = fc_ln_relu_bwd(
         dJn, p["joint_w"], p["joint_gamma"], c["j_cache"], flip=gf.get("joint"), gate=go.get("joint"))
@@ -406,14 +491,28 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
         xq, yq, ln_q = c["qp_cache"]
         if c["variant"] == "vlmap_answer2":
             dzq, g["qp_gamma"], g["qp_beta"] = layer_norm_bwd(dq * (1.0 - yq * yq), p["qp_gamma"], ln_q)
+        elif c["variant"] == "vlmap_answer_full":
+            # ql_in = mean + noise * exp(lss / 2); KL = -0.5 mean_b sum(1 + lss - mean^2 - exp(lss)), weight 0.1
+            mean, (lss, sigma, nz) = yq, ln_q
+            kw = LATENT_LOSS_WEIGHT * loss_scale / B
+            dzq = dq + kw * mean
+            dlss = dq * nz * sigma * 0.5 - 0.5 * kw * (1.0 - np.exp(lss))
+            g["qs_w"] = xq.T @ dlss
+            g["qs_b"] = dlss.sum(axis=0)
         else:
             dzq = dq
         g["qp_w"] = xq.T @ dzq
         g["qp_b"] = dzq.sum(axis=0)
         dq = dzq @ p["qp_w"].T
+        if c["variant"] == "vlmap_answer_full":
+            dq = dq + dlss @ p["qs_w"].T
     # attention pooling + softmax + score
     V, a = c["V"], c["a"]
-    da = np.einsum("bkd,bd->bk", V, dP)
+    da = np.einsum("bkd,bd->bk", c.get("Vp", V), dP)
+    if c.get("va_cache") is not None:   # adapt: the pooled tensor is a trained layer's output: d v_adapt = a (x) dP
+        dVp = a[:, :, None] * dP[:, None, :]
+        _, g["va_w"], g["va_b"], g["va_gamma"], g["va_beta"] = fc_ln_relu_bwd(
+            dVp, p["va_w"], p["va_gamma"], c["va_cache"], need_dx=False, flip=gf.get("va"), gate=go.get("va"))
     ds = a * (da - (a * da).sum(axis=1, keepdims=True))      # masked slots: a = 0 -> ds = 0
     D = c["Hv"].shape[-1]
     w = p["att_w"].reshape(D)
@@ -439,7 +538,8 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
     return g
 
 
-RELU_LAYERS = {"v": "v_cache", "qv": "q_cache", "pl": "p_cache", "ql": "l_cache", "joint": "j_cache", "jl": "jl_cache"}
+RELU_LAYERS = {"v": "v_cache", "qv": "q_cache", "pl": "p_cache", "ql": "l_cache", "joint": "j_cache", "jl": "jl_cache",
+               "va": "va_cache"}
 
 
 def relu_near_ties(cache, tau):

@@ -44,7 +44,7 @@ def gru_encode(E, q_len, Wg, bg, Wc, bc):
 
 
 def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", keep_att=0.8,
-            keep_joint=0.5, att_mask=None, joint_mask=None, joint_l_mask=None):
+            keep_joint=0.5, att_mask=None, joint_mask=None, joint_l_mask=None, noise=None, exist=None):
     """p: dict field -> torch tensor (requires_grad where wanted). Returns dict with loss, logit,
     att_score, pooled, condition, pred."""
     idx = batch["image_idx"].long()
@@ -64,7 +64,10 @@ def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", k
     valid = torch.arange(K).unsqueeze(0) < nbox.unsqueeze(1)
     s = torch.where(valid, s, torch.full_like(s, float("-inf")))
     a = torch.softmax(s, dim=-1)
-    P = torch.bmm(a.unsqueeze(1), V).squeeze(1)
+    Vp = V
+    if variant == "vlmap_answer_adapt":        # vqa/model_vlmap_answer_adapt.py:132-142
+        Vp = fc_layer(V, p["va_w"], p["va_b"], p["va_gamma"], p["va_beta"])
+    P = torch.bmm(a.unsqueeze(1), Vp).squeeze(1)
     Hp = fc_layer(P, p["pl_w"], p["pl_b"], p["pl_gamma"], p["pl_beta"])
     ql_in, cond = q, q
     if variant == "vlmap_answer2":         # vqa/model_vlmap_answer2.py:127-131
@@ -72,6 +75,10 @@ def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", k
         cond = ql_in
     elif variant == "vlmap_answer_no_noise":  # vqa/model_vlmap_answer_no_noise.py:122-125
         ql_in = q @ p["qp_w"] + p["qp_b"]
+    elif variant == "vlmap_answer_full":      # vqa/model_vlmap_answer_full.py:124-134
+        q_mean = q @ p["qp_w"] + p["qp_b"]
+        q_lss = q @ p["qs_w"] + p["qs_b"]
+        ql_in = q_mean + (noise if noise is not None else 0.0) * torch.sqrt(torch.exp(q_lss))
     Hl = fc_layer(ql_in, p["ql_w"], p["ql_b"], p["ql_gamma"], p["ql_beta"])
     if variant in ("vlmap_answer_noc", "vlmap_answer_nocarch"):   # vqa/model_vlmap_answer_noc.py:177-203
         Jv = fc_layer(Hp, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
@@ -88,11 +95,29 @@ def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", k
         Jd = Jn / keep_joint
         logit = Jd @ p["ans_w"] + p["ans_b"]
     target = batch["answer_target"].to(logit.dtype)
-    bce = torch.nn.functional.binary_cross_entropy_with_logits(logit, target, reduction="none")
-    if variant != "standard":
-        bce_train = bce * train_mask
+    BCE = lambda x: torch.nn.functional.binary_cross_entropy_with_logits(x, target, reduction="none")
+    pred_logit = logit
+    if variant in ("vlmap_answer_vqa_all", "vlmap_answer_vqa_all2"):
+        # vqa/model_vlmap_answer_vqa_all.py:188-244 / _vqa_all2.py:188-243
+        if variant == "vlmap_answer_vqa_all":
+            mn = logit.min(dim=1, keepdim=True).values
+            logit = logit * exist + mn * (1 - exist)
+        tuned = Jd @ p["tw_w"] + p["tw_b"]
+        if variant == "vlmap_answer_vqa_all":
+            bce_train = (BCE(logit) + BCE(logit + tuned)) * train_mask
+            bce = BCE(logit) + BCE(logit + tuned)
+            pred_logit = logit + tuned
+        else:
+            bce_train = BCE(logit) * train_mask + BCE(tuned)
+            bce = BCE(logit) + BCE(tuned)
+            pred_logit = logit * (1 - train_mask) + tuned * train_mask
+        logit = logit + tuned
     else:
-        bce_train = bce
+        bce = BCE(logit)
+        bce_train = bce * train_mask if variant != "standard" else bce
     loss = bce_train.sum(-1).mean()
+    if variant == "vlmap_answer_full":        # latent_loss, weight 0.1 (:33, 217-223, 272-276)
+        latent = -0.5 * (1 + q_lss - q_mean.pow(2) - torch.exp(q_lss)).sum(-1).mean()
+        loss = loss + 0.1 * latent
     return {"loss": loss, "report_loss": bce.sum(-1).mean(), "logit": logit, "att_score": a, "pooled": P,
-            "condition": cond, "pred": logit.argmax(-1)}
+            "condition": cond, "pred": pred_logit.argmax(-1)}

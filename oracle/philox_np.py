@@ -49,3 +49,25 @@ def keep_mask(n, keep, seed, step, site):
         u = (w[j >> 1] >> np.uint64((j & 1) * 16)) & np.uint64(0xFFFF)
         out[:, j] = u < np.uint64(thr)
     return out.reshape(n)
+
+
+SITE_NOISE = 4
+
+
+def normal_draw(n, seed, step):
+    """The N(0, 1) draw of the 'full' variant's reparameterisation (csrc/variants.cu normal4; replaces
+    tf.random_normal(seed=123) of vqa/model_vlmap_answer_full.py:133, which only TF can reproduce): elements in
+    groups of 4; group g draws philox4x32_10 at site 4; u_i = ((w_i >> 8) + 0.5) / 2^24; Box-Muller on (u0, u1) and
+    (u2, u3): sqrt(-2 ln u0) * (cos, sin)(2 pi u1), sqrt(-2 ln u2) * (cos, sin)(2 pi u3). float64 here; the device
+    evaluates the same formula in fp32."""
+    assert n % 4 == 0
+    g = np.arange(n // 4, dtype=np.uint64)
+    k0 = seed & 0xFFFFFFFF
+    k1 = ((seed >> 32) ^ (step >> 32)) & 0xFFFFFFFF
+    w = philox4x32_10(g & MASK32, g >> np.uint64(32), np.full_like(g, SITE_NOISE), np.full_like(g, step & 0xFFFFFFFF),
+                      k0, k1)
+    u = [((x >> np.uint64(8)).astype(np.float64) + 0.5) / 16777216.0 for x in w]
+    r0, r1 = np.sqrt(-2.0 * np.log(u[0])), np.sqrt(-2.0 * np.log(u[2]))
+    out = np.stack([r0 * np.cos(2 * np.pi * u[1]), r0 * np.sin(2 * np.pi * u[1]),
+                    r1 * np.cos(2 * np.pi * u[3]), r1 * np.sin(2 * np.pi * u[3])], axis=1)
+    return out.reshape(n)

@@ -36,7 +36,7 @@ def relu_tie_budget(cache, inter, ref_g, fields, tau, loss_scale=1.0, max_ties=9
         for f, dlt in O.v_layer_tie_delta(cache, inter["dHv"], idx).items():
             if f in budget:
                 budget[f] += np.abs(dlt)
-    for layer in ("qv", "pl", "ql", "joint", "jl"):
+    for layer in ("qv", "pl", "ql", "joint", "jl", "va"):
         for idx in ties[layer]:
             flip = np.zeros(cache[O.RELU_LAYERS[layer]][1].shape, dtype=bool)
             flip[tuple(idx)] = True
@@ -77,6 +77,8 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
         from vqa_transfer_externaldata_b200 import lib as L_
         jl_mask = eng.dropout_mask_site(L_.SITE_JOINT_L, seed, step)
         jl_kw = {"joint_l_mask": jl_mask.cpu().numpy()}
+    if cfg.variant == "vlmap_answer_full":   # the reparameterisation noise the device drew for (seed, step)
+        jl_kw = {"noise": eng.reparam_noise(seed, step).cpu().numpy()}
     torch.cuda.synchronize()
     loss, report = eng.read_scalars()
     got = {"loss": loss, "report": report}
@@ -113,6 +115,9 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
             jdl = eng.peek_activation(L.ACT_JDL, torch.bfloat16, (Bn, cfg.J)).float().cpu().numpy()
             gates["jl"] = (jdl > 0) | (jl_kw["joint_l_mask"] == 0)
             drop["jl"] = jl_kw["joint_l_mask"] == 0
+        if cfg.variant == "vlmap_answer_adapt":   # v_adapt's gates from the device's own pooling operand
+            va = eng.peek_activation(L.ACT_VA, torch.bfloat16, (Bn, cfg.K, cfg.D)).float().cpu().numpy()
+            gates["va"] = va > 0
         n_diff, n_all = 0, 0
         for layer, gate in gates.items():
             y = cache[O.RELU_LAYERS[layer]][1]

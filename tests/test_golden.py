@@ -40,6 +40,28 @@ def test_keep_mask_statistics_and_edges():
     assert np.array_equal(a, PH.keep_mask(4096, 0.5, 1, 2, PH.SITE_ATT))
 
 
+def test_normal_draw_statistics():
+    """Box-Muller over Philox words: moments of N(0, 1), no non-finite values, reproducible, step-dependent."""
+    z = PH.normal_draw(1 << 18, 777, 3)
+    assert np.isfinite(z).all()
+    assert abs(z.mean()) < 1e-2 and abs(z.var() - 1.0) < 1e-2
+    assert abs((z ** 3).mean()) < 3e-2 and abs((z ** 4).mean() - 3.0) < 1e-1
+    assert np.array_equal(z, PH.normal_draw(1 << 18, 777, 3))
+    assert (z[:4096] != PH.normal_draw(4096, 777, 4)).any()
+
+
+@pytest.mark.gpu
+def test_device_noise_matches_numpy_restatement():
+    import torch
+    from vqa_transfer_externaldata_b200.engine import AnswerModelConfig, Engine
+    from vqa_transfer_externaldata_b200 import synthetic as S
+    c = S.dims(B=16, K=12, Dv=256, D=128, L=128, A=200, T=6, W=20, Vq=50)
+    eng = Engine(AnswerModelConfig(variant="vlmap_answer_full", precision="fp32", **c))
+    z = eng.reparam_noise(777, 3, batch=16).cpu().numpy()
+    ref = PH.normal_draw(16 * 128, 777, 3).reshape(16, 128)
+    assert np.abs(z - ref).max() < 2e-5     # fp32 log / sincospi against float64
+
+
 @pytest.mark.parametrize("variant", sorted(MG.CASES))
 def test_oracle_reproduces_golden(variant):
     out, g = MG.run(variant, MG.CASES[variant])

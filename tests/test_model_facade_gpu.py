@@ -1,0 +1,61 @@
+"""The reference-facing plugin interface on the GPU: importer.get_model_class(model_type)(batch, config, is_train,
+image_features) for every model_type served, one train step each, and the dict keys a reference caller reads
+(vqa/trainer.py:275-287, vqa/evaler.py:139-162) under the names that model_type uses in the reference."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from vqa_transfer_externaldata_b200 import importer  # noqa: E402
+from vqa_transfer_externaldata_b200.model import make_synthetic_config  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+SMALL = dict(B=16, K=12, Dv=256, D=128, L=128, A=200, T=6, W=20, Vq=50)
+BASE_REPORT = {"answer_train_loss", "answer_report_loss", "answer_acc", "exist_acc", "test_acc", "normal_test_acc",
+               "normal_test_object_acc", "normal_test_attribute_acc", "normal_exist_acc", "normal_train_exist_acc",
+               "max_exist_acc", "test_max_acc", "test_max_exist_acc"}                 # model_vlmap_answer.py:275-288
+OLD_REPORT = {"answer_train_loss", "answer_report_loss", "answer_accuracy", "exist_answer_accuracy",
+              "test_answer_accuracy", "normal_test_answer_accuracy", "max_exist_answer_accuracy",
+              "test_max_answer_accuracy", "test_max_exist_answer_accuracy"}          # model_vlmap_answer_no_noise.py:211-219
+OUTPUT_KEYS = {"att_score", "logit", "pred", "all_score", "max_train_score", "test_obj_score", "test_obj_max_score",
+               "test_attr_score", "test_attr_max_score"}                              # evaler.py:139-156
+
+
+@pytest.mark.parametrize("model_type", importer.get_model_types())
+def test_train_step_through_the_plugin_interface(model_type):
+    config, feats, batch, _ = make_synthetic_config(SMALL, variant=model_type, precision="bf16", seed=5, num_images=16)
+    cls = importer.get_model_class(model_type)
+    model = cls(batch, config, is_train=True, image_features=feats)
+    before = {k: v.copy() for k, v in model.state_dict().items()}
+    loss, h2d, d2h = model.train_step()
+    assert np.isfinite(loss) and h2d > 0 and d2h > 0
+    want = OLD_REPORT if cls.OLD_REPORT else BASE_REPORT
+    if model_type == "vlmap_answer_full":      # model_vlmap_answer_full.py:33-35, 221-223
+        want = want | {"latent_loss", "train_latent_loss", "latent_loss_weight"}
+        assert abs(model.losses["answer"] + model.losses["latent"] - loss) < 1e-4 * max(1.0, abs(loss))
+        assert abs(model.report["train_latent_loss"] - 0.1 * model.report["latent_loss"]) < 1e-6
+    assert set(model.report) == want
+    assert OUTPUT_KEYS <= set(model.output)
+    assert model.output["logit"].shape == (SMALL["B"], SMALL["A"])
+    assert model.heavy_output["condition"].shape == (SMALL["B"], SMALL["L"])
+    pooled_dim = SMALL["D"] if model_type == "vlmap_answer_adapt" else SMALL["Dv"]
+    assert model.mid_result["pooled_V_ft"].shape == (SMALL["B"], pooled_dim)
+    after = model.state_dict()
+    names = list(after)
+    trained = {n.split("/")[0] for n in model.filter_train_vars(names)}
+    frozen = {n.split("/")[0] for n in names} - trained
+    if model_type != "standard":
+        assert {"q_linear_l", "pooled_linear_l", "joint_fc"} <= frozen
+    changed = {n.split("/")[0] for n in names if not np.array_equal(before[n], after[n])}
+    assert changed and changed <= trained, (changed - trained)
+    if model_type in ("vlmap_answer_vqa_all", "vlmap_answer_vqa_all2"):
+        # created by the reference, never reached by the loss (model_vlmap_answer_vqa_all.py:199-216): kept, unchanged
+        assert "tuned_joint_fc/fc/weights" in after and "tuned_q_linear_l/LayerNorm/gamma" in after
+        assert "TunedWordWeightAnswer" in changed
+    if model_type == "vlmap_answer_adapt":
+        assert "v_adapt" in changed and after["pooled_linear_l/fc/weights"].shape == (SMALL["D"], SMALL["L"])
+    if model_type == "vlmap_answer_full":
+        assert {"q_L_mean", "q_L_log_sigma_sq"} <= changed
+    # a checkpoint round trip by variable name
+    model.load_state_dict(after)

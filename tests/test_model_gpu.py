@@ -154,7 +154,8 @@ def test_gru_pair_kernels_match_single_cta_kernels_at_full_size():
 
 
 # ---- family variants: one more layer between the GRU state and q_linear_l ----
-VARIANTS = ["vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc"]
+VARIANTS = ["vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc", "vlmap_answer_full", "vlmap_answer_vqa_all",
+            "vlmap_answer_vqa_all2", "vlmap_answer_adapt"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

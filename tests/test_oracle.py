@@ -32,13 +32,22 @@ def _setup(variant="vlmap_answer", seed=0, perturb=0.3, dims=TINY):
     return c, p, feats.astype(np.float64), nb, batch, m, att_mask, joint_mask
 
 
-VARIANTS = ["vlmap_answer", "standard", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc"]
+VARIANTS = ["vlmap_answer", "standard", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc",
+            "vlmap_answer_full", "vlmap_answer_vqa_all", "vlmap_answer_vqa_all2", "vlmap_answer_adapt"]
+
+
+def _extra_kw(variant, c, seed=3):
+    """the N(0,1) draw of the 'full' variant's reparameterisation"""
+    if variant == "vlmap_answer_full":
+        return {"noise": np.random.default_rng(seed).standard_normal((c["B"], c["L"]))}
+    return {}
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
 def test_backward_matches_finite_differences(variant):
     c, p, feats, nb, batch, m, am, jm = _setup(variant)
-    out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)
+    kw = _extra_kw(variant, c)
+    out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm, **kw)
     g = O.backward(cache)
     rng = np.random.default_rng(5)
     eps = 1e-6
@@ -48,9 +57,9 @@ def test_backward_matches_finite_differences(variant):
         for i in picks:
             old = flat[i]
             flat[i] = old + eps
-            lp = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)[0]["loss"]
+            lp = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm, **kw)[0]["loss"]
             flat[i] = old - eps
-            lm = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)[0]["loss"]
+            lm = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm, **kw)[0]["loss"]
             flat[i] = old
             fd = (lp - lm) / (2 * eps)
             an = g[name].reshape(-1)[i]
@@ -62,12 +71,14 @@ def test_numpy_oracle_matches_torch_twin(variant):
     torch = pytest.importorskip("torch")
     from oracle import answer_model_torch as OT
     c, p, feats, nb, batch, m, am, jm = _setup(variant, seed=11)
-    out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm)
+    kw = _extra_kw(variant, c)
+    out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm, **kw)
     g = O.backward(cache)
     tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
     tb = {k: torch.tensor(v) for k, v in batch.items()}
     tout = OT.forward(tp, torch.tensor(feats), torch.tensor(nb), tb, torch.tensor(m["train"]),
-                      variant=variant, att_mask=torch.tensor(am), joint_mask=torch.tensor(jm))
+                      variant=variant, att_mask=torch.tensor(am), joint_mask=torch.tensor(jm),
+                      exist=torch.tensor(m["exist"]), **{k: torch.tensor(v) for k, v in kw.items()})
     tout["loss"].backward()
     assert abs(tout["loss"].item() - out["loss"]) < 1e-12
     np.testing.assert_allclose(tout["logit"].detach().numpy(), out["logit"], rtol=1e-10, atol=1e-12)

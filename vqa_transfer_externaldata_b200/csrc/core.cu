@@ -61,17 +61,25 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
     p.hi = a.take<bf16>(n);
     p.lo = two ? a.take<bf16>(n) : nullptr;
   };
+  const bool v_full = c.variant == VQA_VARIANT_VLMAP_ANSWER_FULL;
+  const bool v_tuned = c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL || c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL2;
+  const bool v_adapt = c.variant == VQA_VARIANT_VLMAP_ANSWER_ADAPT;
+  const uint64_t Pd = v_adapt ? D : Dv;           // width of the pooled vector
+  const uint64_t Pmax = D > Dv ? D : Dv;
   planes(b.w.v_w, Dv * D);
   planes(b.w.gru_gates_w, (W + L) * 2 * L);
   planes(b.w.gru_cand_w, (W + L) * L);
   planes(b.w.qv_w, L * D);
-  planes(b.w.pl_w, Dv * L);
+  planes(b.w.pl_w, Pd * L);
   planes(b.w.ql_w, L * L);
   planes(b.w.joint_w, L * J);
   planes(b.w.ans_w, J * A);
   planes(b.w.qp_w, L * L);
   planes(b.w.jl_w, L * J);
   planes(b.w.al_w, J * A);
+  planes(b.w.qs_w, v_full ? L * L : 0);
+  planes(b.w.tw_w, v_tuned ? J * A : 0);
+  planes(b.w.va_w, v_adapt ? Dv * D : 0);
 
   planes(b.v, B * K * Dv);
   b.nbox = a.take<int>(B);
@@ -110,9 +118,26 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   planes(b.dzqp, B * L);
   b.zl = a.take<float>(B * L); b.hl = a.take<float>(B * L);
   b.lnl_mean = a.take<float>(B); b.lnl_rstd = a.take<float>(B);
+  b.lss = a.take<float>(v_full ? B * L : 0);
+  b.kl_rows = a.take<float>(v_full ? B : 0);
+  b.dlss_f32 = a.take<float>(v_full ? B * L : 0);
+  planes(b.dlss, v_full ? B * L : 0);
+  b.tuned = a.take<float>(v_tuned ? B * A : 0);
+  b.logit1 = a.take<float>(v_tuned ? B * A : 0);
+  b.logit_total = a.take<float>(v_tuned ? B * A : 0);
+  b.pred_logit = a.take<float>(v_tuned ? B * A : 0);
+  b.dtuned_f32 = a.take<float>(v_tuned ? B * A : 0);
+  planes(b.dtuned, v_tuned ? B * A : 0);
+  const uint64_t nza = v_adapt ? B * K * D : 0;
+  b.za = two ? static_cast<void*>(a.take<float>(nza)) : static_cast<void*>(a.take<bf16>(nza));
+  planes(b.va, nza);
+  b.lnva_mean = a.take<float>(v_adapt ? B : 0);
+  b.lnva_rstd = a.take<float>(v_adapt ? B : 0);
+  planes(b.dza, nza);
+  b.va_part = a.take<float>(v_adapt ? B * 3 * D : 0);
   b.att = a.take<float>(B * K);
-  b.pooled = a.take<float>(B * Dv);
-  planes(b.pooled_op, B * Dv);
+  b.pooled = a.take<float>(B * Pmax);
+  planes(b.pooled_op, B * Pmax);
   b.zp = a.take<float>(B * L); b.hp = a.take<float>(B * L);
   b.lnp_mean = a.take<float>(B); b.lnp_rstd = a.take<float>(B);
   planes(b.x, B * L);
@@ -135,7 +160,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   planes(b.dzp, B * L);
   b.dzl_f32 = a.take<float>(B * L);
   planes(b.dzl, B * L);
-  b.dP = a.take<float>(B * Dv);
+  b.dP = a.take<float>(B * Pmax);
   b.dq = a.take<float>(B * L);
   b.dq2 = a.take<float>(B * L);
   b.dhq = a.take<float>(B * D);
@@ -189,10 +214,11 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
     return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: Dv, D, L, J, A must be multiples of 8");
   if (c.D > 4096 || c.L > 4096 || c.J > 4096 || c.K > 256 || c.T > 64)
     return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: D, L, J <= 4096; K <= 256; T <= 64");
-  if (c.variant < VQA_VARIANT_VLMAP_ANSWER || c.variant > VQA_VARIANT_VLMAP_ANSWER_NOC)
+  if (c.variant < VQA_VARIANT_VLMAP_ANSWER || c.variant >= VQA_NUM_VARIANTS)
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown variant %d", c.variant);
-  if ((c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE) && c.D != c.L)
-    return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: the answer2 / no_noise variants need D == L (V_DIM == L_DIM as in the reference)");
+  if ((c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE ||
+       c.variant == VQA_VARIANT_VLMAP_ANSWER_FULL) && c.D != c.L)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: the answer2 / no_noise / full variants need D == L (V_DIM == L_DIM as in the reference)");
   if (c.precision != VQA_PREC_BF16 && c.precision != VQA_PREC_FP32)
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown precision %d", c.precision);
   if (!(c.keep_att > 0.f && c.keep_att <= 1.f) || !(c.keep_joint > 0.f && c.keep_joint <= 1.f))

@@ -9,7 +9,7 @@ namespace vqa {
 
 // Weight shadows in GEMM-operand form, same [in, out] layout as the fp32 TF variables.
 struct WeightShadows {
-  Planes v_w, gru_gates_w, gru_cand_w, qv_w, pl_w, ql_w, joint_w, ans_w, qp_w, jl_w, al_w;
+  Planes v_w, gru_gates_w, gru_cand_w, qv_w, pl_w, ql_w, joint_w, ans_w, qp_w, jl_w, al_w, qs_w, tw_w, va_w;
 };
 
 // Everything forward keeps for backward + scratch, all inside the workspace.
@@ -42,8 +42,15 @@ struct Buffers {
   Planes hl_op; float* zjl; float* lnjl_mean; float* lnjl_rstd; Planes jdl;
   float* dJl; float* dzjl_f32; Planes dzjl; float* dXl;
   float* dzqp_f32; Planes dzqp;      // [B, L] gradient w.r.t. its pre-activation
+  // full: log-variance layer output, per-sample KL sums, gradient w.r.t. the log-variance
+  float* lss; float* kl_rows; float* dlss_f32; Planes dlss;
+  // vqa_all / vqa_all2: tuned logits, word-weight logits after the fill, their sum, vqa_all2's argmax input, d tuned
+  float* tuned; float* logit1; float* logit_total; float* pred_logit; float* dtuned_f32; Planes dtuned;
+  // adapt: pre-LN v_adapt projection (bf16 / fp32 like z), v_adapt as the pooling operand, LN stats, gradient planes,
+  // per-sample partials [B, 3, D]
+  void* za; Planes va; float* lnva_mean; float* lnva_rstd; Planes dza; float* va_part;
   float* att;      // [B, K]
-  float* pooled;   // [B, Dv]
+  float* pooled;   // [B, Dv]  ([B, D] in the adapt variant)
   Planes pooled_op;
   float* zp; float* hp; float* lnp_mean; float* lnp_rstd;       // pooled_linear_l
   Planes x;        // [B, L]  hp (.) hl

@@ -196,18 +196,89 @@ VqaStatus bce_metrics_launch(int batch, int A, int num_train_answer, int use_tra
                              float grad_scale, float* loss, float* report, int* pred,
                              float* per_sample, float* d_logit_f32, bf16* d_hi, bf16* d_lo,
                              float* scratch, cudaStream_t s);
+// two-term form (vqa_all / vqa_all2): loss_b = logits of a second BCE term (mask_b: train-masked or not),
+// pred_logit = what the argmax runs on (NULL = logit)
+VqaStatus bce_metrics2_launch(int batch, int A, int num_train_answer, int use_train_mask, const float* logit,
+                              const float* loss_b, int mask_b, const float* pred_logit, const float* target,
+                              const VqaAnswerMasks& masks, float* loss, float* report, int* pred, float* per_sample,
+                              float* scratch, cudaStream_t s);
 VqaStatus bce_grad_launch(int batch, int A, int num_train_answer, int use_train_mask,
                           const float* logit, const float* target, float grad_scale,
                           float* d_logit_f32, bf16* d_hi, bf16* d_lo, cudaStream_t s);
 VqaStatus dropout_mask_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
                               unsigned long long step, unsigned int stream_id, cudaStream_t s);
 
+// ---- variants.cu: kernels of the later family members (vqa_all / vqa_all2, full, adapt) ----
+struct TunedHeadFwd {
+  int batch, A, num_train_answer;
+  int fill_min;            // 1 = vqa_all (absent answers take the row minimum), 0 = vqa_all2
+  const float* logit0;     // [batch, A] word-weight logits
+  const float* tuned;      // [batch, A] TunedWordWeightAnswer logits
+  const float* exist;      // [A]
+  float* l1;               // [batch, A] word-weight logits after the fill
+  float* total;            // [batch, A] l1 + tuned  (model.output['logit'])
+  float* pred_logit;       // optional [batch, A]: l1 * test_mask + tuned * train_mask (vqa_all2's argmax input)
+};
+VqaStatus tuned_combine_launch(const TunedHeadFwd& a, cudaStream_t s);
+struct TunedHeadBwd {
+  int batch, A, num_train_answer, fill_min;
+  const float* logit0; const float* l1; const float* total; const float* tuned;
+  const float* target; const float* exist;
+  float grad_scale;        // loss_scale / batch
+  float* d_logit0_f32; bf16* d_logit0_hi; bf16* d_logit0_lo;
+  float* d_tuned_f32; bf16* d_tuned_hi; bf16* d_tuned_lo;
+};
+VqaStatus tuned_grad_launch(const TunedHeadBwd& a, cudaStream_t s);
+
+struct ReparamFwd {
+  int batch, L;
+  const float* mean; const float* lss;   // [batch, L] q_L_mean, q_L_log_sigma_sq
+  unsigned long long seed, step;
+  float* out_f32; bf16* out_hi; bf16* out_lo;   // mean + noise * sqrt(exp(lss))
+  float* kl_rows;                         // [batch] sum_l (1 + lss - mean^2 - exp(lss))
+};
+VqaStatus reparam_fwd_launch(const ReparamFwd& a, cudaStream_t s);
+VqaStatus latent_finalize_launch(const float* kl_rows, int batch, float weight, float* loss, float* report,
+                                 cudaStream_t s);
+struct ReparamBwd {
+  int batch, L;
+  const float* d_out; const float* mean; const float* lss;
+  unsigned long long seed, step;
+  float kl_scale;                         // latent weight * loss_scale / batch
+  float* d_mean_f32; bf16* d_mean_hi; bf16* d_mean_lo;
+  float* d_lss_f32; bf16* d_lss_hi; bf16* d_lss_lo;
+};
+VqaStatus reparam_bwd_launch(const ReparamBwd& a, cudaStream_t s);
+VqaStatus reparam_noise_launch(float* out, long long n, unsigned long long seed, unsigned long long step,
+                               cudaStream_t s);
+
+struct SlabLnFwd {
+  int batch, K, D;
+  const void* z;                          // [batch, K, D] pre-LN: bf16 (PREC_BF16) / fp32 (PREC_FP32)
+  const float* gamma; const float* beta;  // [D]
+  bf16* out_hi; bf16* out_lo;             // relu(LN_{K,D}(z)) as operand planes
+  float* mean; float* rstd;               // [batch]
+};
+VqaStatus slab_ln_relu_fwd_launch(const SlabLnFwd& a, int precision, cudaStream_t s);
+struct SlabLnBwd {
+  int batch, K, D;
+  const void* z; const float* gamma; const float* beta; const float* mean; const float* rstd;
+  const float* att;                       // [batch, K]
+  const float* d_pooled;                  // [batch, D]
+  bf16* dz_hi; bf16* dz_lo;               // [batch, K, D]
+  float* part;                            // [batch, 3, D] per-sample partials: d gamma | d beta | d bias
+};
+VqaStatus slab_ln_relu_bwd_launch(const SlabLnBwd& a, int precision, cudaStream_t s);
+
 // ---- optim.cu ----
 VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, long long n, float lr,
                            float beta1, float beta2, float eps, float clip_norm, long long t,
                            float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s);
 
+// weight of the KL latent loss of the full variant (vqa/model_vlmap_answer_full.py:33)
+#define VQA_LATENT_LOSS_WEIGHT 0.1f
+
 // RNG stream ids (which dropout site a Philox draw belongs to)
-enum { RNG_STREAM_ATT = 1, RNG_STREAM_JOINT = 2, RNG_STREAM_JOINT_L = 3 };
+enum { RNG_STREAM_ATT = 1, RNG_STREAM_JOINT = 2, RNG_STREAM_JOINT_L = 3, RNG_STREAM_NOISE = 4 };
 
 }  // namespace vqa

@@ -38,6 +38,8 @@ __device__ __forceinline__ float wmax(float v) {
 struct LossArgs {
   int A, num_train_answer, use_train_mask;
   const float* logit; const float* target;
+  const float* loss_b; int mask_b;   // optional second BCE term (vqa_all / vqa_all2)
+  const float* pred_logit;           // optional: argmax input when it is not `logit`
   const float* is_object; const float* is_attribute; const float* answer_exist;
   float grad_scale;
   int* pred; float* per_sample; int batch;
@@ -52,6 +54,8 @@ __global__ void __launch_bounds__(LOSS_THREADS) bce_metrics_kernel(LossArgs a) {
   const int b = blockIdx.x, A = a.A, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* x = a.logit + static_cast<long long>(b) * A;
   const float* z = a.target + static_cast<long long>(b) * A;
+  const float* xb = a.loss_b ? a.loss_b + static_cast<long long>(b) * A : nullptr;
+  const float* xp = a.pred_logit ? a.pred_logit + static_cast<long long>(b) * A : nullptr;
   float l_train = 0.f, l_all = 0.f;
   float best = -CUDART_INF_F;
   int best_i = 0x7fffffff;
@@ -70,6 +74,15 @@ __global__ void __launch_bounds__(LOSS_THREADS) bce_metrics_kernel(LossArgs a) {
     const float xs[4] = {xv.x, xv.y, xv.z, xv.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w};
     const float obs[4] = {ob.x, ob.y, ob.z, ob.w}, ats[4] = {at.x, at.y, at.z, at.w};
     const float exs[4] = {ex.x, ex.y, ex.z, ex.w};
+    float bs[4] = {0.f, 0.f, 0.f, 0.f}, ps[4] = {xv.x, xv.y, xv.z, xv.w};
+    if (xb) {
+      const float4 v = *reinterpret_cast<const float4*>(xb + c);
+      bs[0] = v.x; bs[1] = v.y; bs[2] = v.z; bs[3] = v.w;
+    }
+    if (xp) {
+      const float4 v = *reinterpret_cast<const float4*>(xp + c);
+      ps[0] = v.x; ps[1] = v.y; ps[2] = v.z; ps[3] = v.w;
+    }
     float dl[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -81,11 +94,16 @@ __global__ void __launch_bounds__(LOSS_THREADS) bce_metrics_kernel(LossArgs a) {
       l_all += l;
       const float lm = a.use_train_mask ? tm : 1.f;
       l_train += l * lm;
+      if (xb) {
+        const float lb = fmaxf(bs[j], 0.f) - bs[j] * zz + log1pf(expf(-fabsf(bs[j])));
+        l_all += lb;
+        l_train += lb * (a.mask_b ? tm : 1.f);
+      }
       // sigmoid(x) from the same exponential: x >= 0: 1/(1+e), x < 0: e/(1+e)
       const float sg = xx >= 0.f ? 1.f / (1.f + e) : e / (1.f + e);
       dl[j] = (sg - zz) * lm * a.grad_scale;
-      if (xx > best) {  // ascending i within a thread: strict > keeps the first maximal index
-        best = xx;
+      if (ps[j] > best) {  // ascending i within a thread: strict > keeps the first maximal index
+        best = ps[j];
         best_i = i;
       }
       mx[0] = fmaxf(mx[0], zz * tm);
@@ -230,6 +248,8 @@ __global__ void __launch_bounds__(256) report_finalize_kernel(const float* __res
       report[VQA_REPORT_MAX_EXIST_ACC] = m[S_MAX_EXIST];
       report[VQA_REPORT_TEST_MAX_ACC] = m[S_TEST_MAX];
       report[VQA_REPORT_TEST_MAX_EXIST_ACC] = m[S_TEST_MAX_EXIST];
+      report[VQA_REPORT_LATENT_LOSS] = 0.f;          // the 'full' variant overwrites these (latent_finalize_kernel)
+      report[VQA_REPORT_TRAIN_LATENT_LOSS] = 0.f;
     }
   }
 }
@@ -301,9 +321,32 @@ VqaStatus bce_metrics_launch(int batch, int A, int num_train_answer, int use_tra
   LossArgs a;
   a.A = A; a.num_train_answer = num_train_answer; a.use_train_mask = use_train_mask;
   a.logit = logit; a.target = target;
+  a.loss_b = nullptr; a.mask_b = 0; a.pred_logit = nullptr;
   a.is_object = masks.is_object; a.is_attribute = masks.is_attribute; a.answer_exist = masks.answer_exist;
   a.grad_scale = grad_scale; a.pred = pred; a.per_sample = per_sample; a.batch = batch;
   a.d_f32 = d_logit_f32; a.d_hi = d_hi; a.d_lo = d_lo; a.rows = scratch;
+  bce_metrics_kernel<<<batch, LOSS_THREADS, 0, s>>>(a);
+  VQA_LAUNCH_CHECK("bce_metrics");
+  report_finalize_kernel<<<1, 256, 0, s>>>(scratch, batch, loss, report);
+  VQA_LAUNCH_CHECK("report_finalize");
+  return VQA_OK;
+}
+
+VqaStatus bce_metrics2_launch(int batch, int A, int num_train_answer, int use_train_mask, const float* logit,
+                              const float* loss_b, int mask_b, const float* pred_logit, const float* target,
+                              const VqaAnswerMasks& masks, float* loss, float* report, int* pred, float* per_sample,
+                              float* scratch, cudaStream_t s) {
+  if (batch == 0) return VQA_OK;
+  if (!logit || !target || !masks.is_object || !masks.is_attribute || !masks.answer_exist || !scratch)
+    return set_error(VQA_ERR_BAD_ARG, "bce_metrics2: null argument");
+  if (A & 3) return set_error(VQA_ERR_BAD_SHAPE, "bce_metrics2: A must be a multiple of 4");
+  LossArgs a;
+  a.A = A; a.num_train_answer = num_train_answer; a.use_train_mask = use_train_mask;
+  a.logit = logit; a.target = target;
+  a.loss_b = loss_b; a.mask_b = mask_b; a.pred_logit = pred_logit;
+  a.is_object = masks.is_object; a.is_attribute = masks.is_attribute; a.answer_exist = masks.answer_exist;
+  a.grad_scale = 0.f; a.pred = pred; a.per_sample = per_sample; a.batch = batch;
+  a.d_f32 = nullptr; a.d_hi = nullptr; a.d_lo = nullptr; a.rows = scratch;
   bce_metrics_kernel<<<batch, LOSS_THREADS, 0, s>>>(a);
   VQA_LAUNCH_CHECK("bce_metrics");
   report_finalize_kernel<<<1, 256, 0, s>>>(scratch, batch, loss, report);

@@ -105,13 +105,16 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
       {p->gru_gates_w, &w.gru_gates_w, c.W + c.L, 2LL * c.L},
       {p->gru_cand_w, &w.gru_cand_w, c.W + c.L, c.L},
       {p->qv_w, &w.qv_w, c.L, c.D},
-      {p->pl_w, &w.pl_w, c.Dv, c.L},
+      {p->pl_w, &w.pl_w, c.variant == VQA_VARIANT_VLMAP_ANSWER_ADAPT ? c.D : c.Dv, c.L},   // adapt pools the D-wide v_adapt
       {p->ql_w, &w.ql_w, c.L, c.L},
       {p->joint_w, &w.joint_w, c.L, c.J},
       {p->ans_w, &w.ans_w, c.J, c.A},
       {p->qp_w, &w.qp_w, c.L, c.L},   // answer2 / no_noise only (NULL otherwise)
       {p->jl_w, &w.jl_w, c.L, c.J},   // noc only
       {p->al_w, &w.al_w, c.J, c.A},   // noc only
+      {p->qs_w, &w.qs_w, c.L, c.L},   // full only
+      {p->tw_w, &w.tw_w, c.J, c.A},   // vqa_all / vqa_all2 only
+      {p->va_w, &w.va_w, c.Dv, c.D},  // adapt only
   };
   // the refreshes are independent small memory-bound kernels: spread them over the auxiliary streams instead of
   // queueing them behind one another (they sit between the optimizer and the next step's first GEMM)
@@ -119,9 +122,13 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
   bool forked[VqaHandle_t::kAux] = {};
   cudaStream_t gru_stream = s;
   for (auto& it : items) {
-    const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE;
+    const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE ||
+                        c.variant == VQA_VARIANT_VLMAP_ANSWER_FULL;
     if (it.dst == &w.qp_w && !has_qp) continue;   // the base variants have no such layer
     if ((it.dst == &w.jl_w || it.dst == &w.al_w) && c.variant != VQA_VARIANT_VLMAP_ANSWER_NOC) continue;
+    if (it.dst == &w.qs_w && c.variant != VQA_VARIANT_VLMAP_ANSWER_FULL) continue;
+    if (it.dst == &w.tw_w && c.variant != VQA_VARIANT_VLMAP_ANSWER_VQA_ALL && c.variant != VQA_VARIANT_VLMAP_ANSWER_VQA_ALL2) continue;
+    if (it.dst == &w.va_w && c.variant != VQA_VARIANT_VLMAP_ANSWER_ADAPT) continue;
     if (!it.src) {
       if (!h->params_ready) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: the first call needs every weight");
       continue;  // unchanged since the last call
@@ -168,6 +175,10 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   const int K = c.K, Dv = c.Dv, D = c.D, L = c.L, J = c.J, A = c.A, W = c.W, Wp = h->Wpad;
   const bool fp32 = c.precision == VQA_PREC_FP32;
   const long long BL = static_cast<long long>(Bn) * L;
+  const bool v_full = c.variant == VQA_VARIANT_VLMAP_ANSWER_FULL;
+  const bool v_tuned = c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL || c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL2;
+  const bool v_adapt = c.variant == VQA_VARIANT_VLMAP_ANSWER_ADAPT;
+  const int Pd = v_adapt ? D : Dv;   // width of the pooled vector
 
   // branch 0 (auxiliary stream): embedding lookup + the hoisted x-parts of the GRU pre-activations; it is
   // epilogue/store-bound and overlaps the MMA-bound v-projection below      (:134-137, modules.py:124-140)
@@ -204,6 +215,20 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     else { Planes zp; zp.hi = static_cast<bf16*>(b.z); g.planes(zp, 0, D); }
     VQA_TRY(g.run(h, s));
   }
+  if (v_adapt) {
+    // v_adapt = relu(LN_{K,D}(V Wa + ba)): the tensor attention pools in this variant (model_vlmap_answer_adapt.py:132-142)
+    if (!p->va_w || !p->va_b || !p->va_gamma || !p->va_beta)
+      return set_error(VQA_ERR_BAD_ARG, "vqa_forward: the adapt variant needs va_*");
+    GemmB g(Bn * K, D, Dv);
+    g.a(b.v, 0, Dv, false).b(b.w.va_w, 0, D, true).bias(p->va_b);
+    if (fp32) g.f32(static_cast<float*>(b.za), D);
+    else { Planes zp; zp.hi = static_cast<bf16*>(b.za); g.planes(zp, 0, D); }
+    VQA_TRY(g.run(h, s));
+    SlabLnFwd f{};
+    f.batch = Bn; f.K = K; f.D = D; f.z = b.za; f.gamma = p->va_gamma; f.beta = p->va_beta;
+    f.out_hi = b.va.hi; f.out_lo = b.va.lo; f.mean = b.lnva_mean; f.rstd = b.lnva_rstd;
+    VQA_TRY(slab_ln_relu_fwd_launch(f, c.precision, s));
+  }
   PH_END(VQA_PH_VPROJ_FWD);
   VQA_TRY(join_stream(h, 0, s));
   PH_BEGIN(VQA_PH_GRU_FWD);
@@ -239,10 +264,19 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_BEGIN(VQA_PH_QHEADS_FWD);
   // a6 (question half) on the auxiliary stream: Hl = relu(LN(q Wl + b))   (:170-174); needed only by the joint head
   VQA_TRY(fork_stream(h, 0, s, &s1));
-  const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE;
+  const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE || v_full;
   if (has_qp) {
     if (!p->qp_w || !p->qp_b) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: this variant needs qp_w / qp_b");
-    if (c.variant == VQA_VARIANT_VLMAP_ANSWER2) {
+    if (v_full) {
+      // q_L_mean, q_L_log_sigma_sq (both linear), q_L_mean_noise = mean + N(0,1) * sqrt(exp(lss))   (_full.py:124-134)
+      if (!p->qs_w || !p->qs_b) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: the full variant needs qs_w / qs_b");
+      VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.qp_w, 0, L, true).bias(p->qp_b).f32(b.qp_f32, L).run(h, s1));
+      VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.qs_w, 0, L, true).bias(p->qs_b).f32(b.lss, L).run(h, s1));
+      ReparamFwd r{};
+      r.batch = Bn; r.L = L; r.mean = b.qp_f32; r.lss = b.lss; r.seed = seed; r.step = step;
+      r.out_hi = b.qp.hi; r.out_lo = b.qp.lo; r.kl_rows = b.kl_rows;
+      VQA_TRY(reparam_fwd_launch(r, s1));
+    } else if (c.variant == VQA_VARIANT_VLMAP_ANSWER2) {
       // q_L_ft2 = tanh(LN(q W2 + b2))           (vqa/model_vlmap_answer2.py:127-130)
       if (!p->qp_gamma || !p->qp_beta) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: answer2 needs qp_gamma / qp_beta");
       VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.qp_w, 0, L, true).bias(p->qp_b).f32(b.zqp, L).run(h, s1));
@@ -280,15 +314,16 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   {
     VqaAttnFwd a{};
     a.batch = Bn; a.z = b.z; a.gamma = p->v_gamma; a.beta = p->v_beta; a.hq = b.hq;
-    a.att_w = p->att_w; a.att_b = p->att_b; a.nbox = b.nbox; a.v_hi = b.v.hi; a.v_lo = b.v.lo;
+    a.att_w = p->att_w; a.att_b = p->att_b; a.nbox = b.nbox;
+    a.v_hi = v_adapt ? b.va.hi : b.v.hi; a.v_lo = v_adapt ? b.va.lo : b.v.lo;   // adapt pools v_adapt [K, D]
     a.seed = seed; a.step = step; a.att = b.att; a.pooled = b.pooled; a.pooled_hi = b.pooled_op.hi;
     a.pooled_lo = b.pooled_op.lo; a.ln_mean = b.lnv_mean; a.ln_rstd = b.lnv_rstd;
-    VQA_TRY(attn_fwd_launch(a, K, D, Dv, c.precision, c.keep_att, s));
+    VQA_TRY(attn_fwd_launch(a, K, D, Pd, c.precision, c.keep_att, s));
   }
   PH_END(VQA_PH_ATTN_FWD);
   PH_BEGIN(VQA_PH_HEAD_FWD);
   // a6: Hp = relu(LN(P Wp + b)); X = Hp (.) Hl; Jd = dropout(relu(LN(X Wj + b)), 0.5)   (:163-181)
-  VQA_TRY(GemmB(Bn, L, Dv).a(b.pooled_op, 0, Dv, false).b(b.w.pl_w, 0, L, true).bias(p->pl_b).f32(b.zp, L).run(h, s));
+  VQA_TRY(GemmB(Bn, L, Pd).a(b.pooled_op, 0, Pd, false).b(b.w.pl_w, 0, L, true).bias(p->pl_b).f32(b.zp, L).run(h, s));
   VQA_TRY(join_stream(h, 0, s));  // Hl
   {
     RowLnFwd r{};
@@ -320,23 +355,48 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(GemmB(Bn, A, J).a(b.jdl, 0, J, false).b(b.w.al_w, 0, A, true).bias(p->al_b).addend(b.logit, A)
                 .f32(b.logit, A).run(h, s));
   }
+  const float* out_logit = b.logit;
+  if (v_tuned) {
+    // TunedWordWeightAnswer reads `joint` itself (model_vlmap_answer_vqa_all.py:215-216), then the logits are combined
+    if (!p->tw_w || !p->tw_b) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: the vqa_all variants need tw_w / tw_b");
+    VQA_TRY(GemmB(Bn, A, J).a(b.jd, 0, J, false).b(b.w.tw_w, 0, A, true).bias(p->tw_b).f32(b.tuned, A).run(h, s));
+    TunedHeadFwd t{};
+    t.batch = Bn; t.A = A; t.num_train_answer = c.num_train_answer;
+    t.fill_min = c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL;
+    t.logit0 = b.logit; t.tuned = b.tuned; t.exist = masks->answer_exist; t.l1 = b.logit1; t.total = b.logit_total;
+    t.pred_logit = t.fill_min ? nullptr : b.pred_logit;
+    VQA_TRY(tuned_combine_launch(t, s));
+    out_logit = b.logit_total;
+  }
   PH_END(VQA_PH_HEAD_FWD);
   PH_BEGIN(VQA_PH_LOSS);
   // a8 + a9: loss, pred, report                                       (:192-288)
   const int use_tm = c.variant != VQA_VARIANT_STANDARD;  // every vlmap_answer* variant masks the loss to the train answers
-  VQA_TRY(bce_metrics_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target, *masks, 0.f,
-                             b.loss, b.report, b.pred, b.per_sample, nullptr, nullptr, nullptr, b.scratch, s));
+  if (c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL) {
+    // (BCE(fixed) + BCE(fixed + tuned)) * train_mask; pred from fixed + tuned              (_vqa_all.py:234-244)
+    VQA_TRY(bce_metrics2_launch(Bn, A, c.num_train_answer, 1, b.logit_total, b.logit1, 1, nullptr, batch->answer_target,
+                                *masks, b.loss, b.report, b.pred, b.per_sample, b.scratch, s));
+  } else if (c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL2) {
+    // BCE(fixed) * train_mask + BCE(tuned); pred from fixed * test_mask + tuned * train_mask (_vqa_all2.py:231-242)
+    VQA_TRY(bce_metrics2_launch(Bn, A, c.num_train_answer, 1, b.logit1, b.tuned, 0, b.pred_logit, batch->answer_target,
+                                *masks, b.loss, b.report, b.pred, b.per_sample, b.scratch, s));
+  } else {
+    VQA_TRY(bce_metrics_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target, *masks, 0.f,
+                               b.loss, b.report, b.pred, b.per_sample, nullptr, nullptr, nullptr, b.scratch, s));
+  }
+  if (v_full)   // loss += 0.1 * KL(q_L_mean, q_L_log_sigma_sq); report latent_loss / train_latent_loss  (_full.py:217-223)
+    VQA_TRY(latent_finalize_launch(b.kl_rows, Bn, VQA_LATENT_LOSS_WEIGHT, b.loss, b.report, s));
   PH_END(VQA_PH_LOSS);
   if (out) {
     VQA_TRY(copy_out(out->loss, b.loss, sizeof(float), s));
     VQA_TRY(copy_out(out->report, b.report, sizeof(float) * VQA_NUM_REPORT, s));
     VQA_TRY(copy_out(out->att_score, b.att, sizeof(float) * Bn * K, s));
-    VQA_TRY(copy_out(out->logit, b.logit, sizeof(float) * Bn * A, s));
+    VQA_TRY(copy_out(out->logit, out_logit, sizeof(float) * Bn * A, s));
     VQA_TRY(copy_out(out->pred, b.pred, sizeof(int) * Bn, s));
     VQA_TRY(copy_out(out->per_sample, b.per_sample, sizeof(float) * VQA_NUM_PER_SAMPLE * Bn, s));
     // heavy_output['condition']: q (base), q_L_ft2 (vqa/model_vlmap_answer2.py:131)
     VQA_TRY(copy_out(out->condition, c.variant == VQA_VARIANT_VLMAP_ANSWER2 ? b.qp_f32 : q, sizeof(float) * BL, s));
-    VQA_TRY(copy_out(out->pooled, b.pooled, sizeof(float) * Bn * Dv, s));
+    VQA_TRY(copy_out(out->pooled, b.pooled, sizeof(float) * Bn * Pd, s));
   }
   h->fwd_valid = true;
   h->last_batch = Bn;
@@ -363,16 +423,37 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   const uint64_t seed = h->last_seed, step = h->last_step;
   const int use_tm = c.variant != VQA_VARIANT_STANDARD;  // every vlmap_answer* variant masks the loss to the train answers
   const long long q_off = T * BL;
+  const bool v_full = c.variant == VQA_VARIANT_VLMAP_ANSWER_FULL;
+  const bool v_tuned = c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL || c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL2;
+  const bool v_adapt = c.variant == VQA_VARIANT_VLMAP_ANSWER_ADAPT;
+  const int Pd = v_adapt ? D : Dv;
 
   PH_BEGIN(VQA_PH_HEAD_BWD);
-  // d logit = (sigmoid(x) - z) * train_mask / B
-  VQA_TRY(bce_grad_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target,
-                          loss_scale / static_cast<float>(Bn), b.dlogit_f32, b.dlogit.hi, b.dlogit.lo, s));
+  if (v_tuned) {
+    // gradients of the two-term loss w.r.t. the word-weight logits (through the min fill in vqa_all) and the tuned ones
+    TunedHeadBwd t{};
+    t.batch = Bn; t.A = A; t.num_train_answer = c.num_train_answer;
+    t.fill_min = c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL;
+    t.logit0 = b.logit; t.l1 = b.logit1; t.total = b.logit_total; t.tuned = b.tuned;
+    t.target = batch->answer_target; t.exist = h->last_masks.answer_exist;
+    t.grad_scale = loss_scale / static_cast<float>(Bn);
+    t.d_logit0_f32 = b.dlogit_f32; t.d_logit0_hi = b.dlogit.hi; t.d_logit0_lo = b.dlogit.lo;
+    t.d_tuned_f32 = b.dtuned_f32; t.d_tuned_hi = b.dtuned.hi; t.d_tuned_lo = b.dtuned.lo;
+    VQA_TRY(tuned_grad_launch(t, s));
+    if (g->tw_w) VQA_TRY(GemmB(J, A, Bn).a(b.jd, 0, J, true).b(b.dtuned, 0, A, true).f32(g->tw_w, A).run(h, s));
+    if (g->tw_b) VQA_TRY(colsum_launch(b.dtuned_f32, Bn, A, A, g->tw_b, b.scratch, s));
+  } else {
+    // d logit = (sigmoid(x) - z) * train_mask / B
+    VQA_TRY(bce_grad_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target,
+                            loss_scale / static_cast<float>(Bn), b.dlogit_f32, b.dlogit.hi, b.dlogit.lo, s));
+  }
   if (g->ans_w)
     VQA_TRY(GemmB(J, A, Bn).a(b.jd, 0, J, true).b(b.dlogit, 0, A, true).f32(g->ans_w, A).run(h, s));
   if (g->ans_b) VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->ans_b, b.scratch, s));
   // dJd = dlogit Wa^T
   VQA_TRY(GemmB(Bn, J, A).a(b.dlogit, 0, A, false).b(b.w.ans_w, 0, A, false).f32(b.dJ, J).run(h, s));
+  if (v_tuned)   // both heads read the same joint: dJd += d tuned Wt^T
+    VQA_TRY(GemmB(Bn, J, A).a(b.dtuned, 0, A, false).b(b.w.tw_w, 0, A, false).addend(b.dJ, J).f32(b.dJ, J).run(h, s));
   // joint_fc: dropout, ReLU, LN backward
   {
     RowLnBwd r{};
@@ -428,9 +509,9 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->ql_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->ql_gamma, b.scratch, s));
     if (g->ql_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->ql_beta, b.scratch, s));
   }
-  if (g->pl_w) VQA_TRY(GemmB(Dv, L, Bn).a(b.pooled_op, 0, Dv, true).b(b.dzp, 0, L, true).f32(g->pl_w, L).run(h, s));
+  if (g->pl_w) VQA_TRY(GemmB(Pd, L, Bn).a(b.pooled_op, 0, Pd, true).b(b.dzp, 0, L, true).f32(g->pl_w, L).run(h, s));
   if (g->pl_b) VQA_TRY(colsum_launch(b.dzp_f32, Bn, L, L, g->pl_b, b.scratch, s));
-  const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE;
+  const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE || v_full;
   {
     const Planes& ql_in = has_qp ? b.qp : b.h;   // q_linear_l reads the extra layer's output in those variants
     if (g->ql_w)
@@ -438,7 +519,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   }
   if (g->ql_b) VQA_TRY(colsum_launch(b.dzl_f32, Bn, L, L, g->ql_b, b.scratch, s));
   // dP = dZp Wp^T ; dq = dZl Wl^T
-  VQA_TRY(GemmB(Bn, Dv, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Dv).run(h, s));
+  VQA_TRY(GemmB(Bn, Pd, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Pd).run(h, s));
   if (!has_qp) {
     VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, s));
   } else if (c.variant == VQA_VARIANT_VLMAP_ANSWER2) {
@@ -452,6 +533,15 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(row_ln_relu_bwd_launch(r, s));
     if (g->qp_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->qp_gamma, b.scratch, s));
     if (g->qp_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->qp_beta, b.scratch, s));
+  } else if (v_full) {
+    // d(q_L_mean_noise) -> d mean (+ KL), d log_sigma_sq (+ KL)                        (_full.py:132-134, 272-276)
+    VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dqp, L).run(h, s));
+    ReparamBwd r{};
+    r.batch = Bn; r.L = L; r.d_out = b.dqp; r.mean = b.qp_f32; r.lss = b.lss; r.seed = seed; r.step = step;
+    r.kl_scale = VQA_LATENT_LOSS_WEIGHT * loss_scale / static_cast<float>(Bn);
+    r.d_mean_f32 = b.dzqp_f32; r.d_mean_hi = b.dzqp.hi; r.d_mean_lo = b.dzqp.lo;
+    r.d_lss_f32 = b.dlss_f32; r.d_lss_hi = b.dlss.hi; r.d_lss_lo = b.dlss.lo;
+    VQA_TRY(reparam_bwd_launch(r, s));
   } else {
     // q_L_mean is linear: the gradient of its output IS the gradient of its pre-activation
     VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dzqp_f32, L).planes(b.dzqp, 0, L)
@@ -461,6 +551,11 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->qp_w) VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dzqp, 0, L, true).f32(g->qp_w, L).run(h, s));
     if (g->qp_b) VQA_TRY(colsum_launch(b.dzqp_f32, Bn, L, L, g->qp_b, b.scratch, s));
     VQA_TRY(GemmB(Bn, L, L).a(b.dzqp, 0, L, false).b(b.w.qp_w, 0, L, false).f32(b.dq, L).run(h, s));
+    if (v_full) {
+      if (g->qs_w) VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dlss, 0, L, true).f32(g->qs_w, L).run(h, s));
+      if (g->qs_b) VQA_TRY(colsum_launch(b.dlss_f32, Bn, L, L, g->qs_b, b.scratch, s));
+      VQA_TRY(GemmB(Bn, L, L).a(b.dlss, 0, L, false).b(b.w.qs_w, 0, L, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
+    }
   }
   PH_END(VQA_PH_HEAD_BWD);
   PH_BEGIN(VQA_PH_ATTN_BWD);
@@ -468,13 +563,26 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   {
     VqaAttnBwd a{};
     a.batch = Bn; a.z = b.z; a.gamma = p->v_gamma; a.beta = p->v_beta; a.hq = b.hq; a.att_w = p->att_w;
-    a.nbox = b.nbox; a.v_hi = b.v.hi; a.v_lo = b.v.lo; a.seed = seed; a.step = step; a.att = b.att;
+    a.nbox = b.nbox; a.v_hi = v_adapt ? b.va.hi : b.v.hi; a.v_lo = v_adapt ? b.va.lo : b.v.lo;
+    a.seed = seed; a.step = step; a.att = b.att;
     a.ln_mean = b.lnv_mean; a.ln_rstd = b.lnv_rstd; a.d_pooled = b.dP; a.dz_hi = b.dzv.hi;
     a.dz_lo = b.dzv.lo; a.d_hq = b.dhq; a.d_att_w = g->att_w; a.d_att_b = g->att_b;
     a.d_gamma = g->v_gamma; a.d_beta = g->v_beta; a.d_bias = g->v_b;
     const bool side = !(h->profile && !h->profile_overlapped);
-    VQA_TRY(attn_bwd_launch(a, K, D, Dv, c.precision, c.keep_att, b.attn_part, s, side ? h->aux[3] : nullptr,
+    VQA_TRY(attn_bwd_launch(a, K, D, Pd, c.precision, c.keep_att, b.attn_part, s, side ? h->aux[3] : nullptr,
                             side ? h->ev_fork[3] : nullptr));
+  }
+  if (v_adapt) {
+    // d v_adapt[k, :] = a_k dP -> ReLU / LayerNorm(K*D) backward -> dZa; parameter gradients of v_adapt
+    SlabLnBwd r{};
+    r.batch = Bn; r.K = K; r.D = D; r.z = b.za; r.gamma = p->va_gamma; r.beta = p->va_beta;
+    r.mean = b.lnva_mean; r.rstd = b.lnva_rstd; r.att = b.att; r.d_pooled = b.dP;
+    r.dz_hi = b.dza.hi; r.dz_lo = b.dza.lo; r.part = b.va_part;
+    VQA_TRY(slab_ln_relu_bwd_launch(r, c.precision, s));
+    if (g->va_gamma) VQA_TRY(colsum_launch(b.va_part, Bn, D, 3 * D, g->va_gamma, b.scratch, s));
+    if (g->va_beta) VQA_TRY(colsum_launch(b.va_part + D, Bn, D, 3 * D, g->va_beta, b.scratch, s));
+    if (g->va_b) VQA_TRY(colsum_launch(b.va_part + 2 * D, Bn, D, 3 * D, g->va_b, b.scratch, s));
+    if (g->va_w) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dza, 0, D, true).f32(g->va_w, D).run(h, s));
   }
   PH_END(VQA_PH_ATTN_BWD);
   // data-parallel runs take dWv here, ahead of the BPTT, so that its all-reduce can overlap the recurrent kernels
@@ -664,6 +772,13 @@ VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch
   }
 }
 
+VQA_API VqaStatus vqa_reparam_noise(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step, float* noise,
+                                    void* stream) {
+  if (!h || !noise) return set_error(VQA_ERR_BAD_ARG, "vqa_reparam_noise: null argument");
+  return reparam_noise_launch(noise, static_cast<long long>(batch) * h->cfg.L, seed, step,
+                              static_cast<cudaStream_t>(stream));
+}
+
 VQA_API VqaStatus vqa_set_early_gradients(VqaHandle h, int32_t enable) {
   if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_set_early_gradients: null handle");
   h->early_grads = enable != 0;
@@ -704,6 +819,7 @@ VQA_API VqaStatus vqa_peek_activation(VqaHandle h, int32_t which, const void** d
     case VQA_ACT_HP: *dev_ptr = b.hp; *bytes = Bn * c.L * 4; break;
     case VQA_ACT_JD: *dev_ptr = b.jd.hi; *bytes = Bn * c.J * 2; break;
     case VQA_ACT_JDL: *dev_ptr = b.jdl.hi; *bytes = Bn * c.J * 2; break;
+    case VQA_ACT_VA: *dev_ptr = b.va.hi; *bytes = Bn * c.K * c.D * 2; break;
     case VQA_ACT_Z: *dev_ptr = b.z; *bytes = Bn * c.K * c.D * (c.precision == VQA_PREC_FP32 ? 4 : 2); break;
     default: return set_error(VQA_ERR_BAD_ARG, "vqa_peek_activation: unknown activation %d", which);
   }

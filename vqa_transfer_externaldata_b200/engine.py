@@ -46,12 +46,21 @@ _NOC_NAMES = {   # vqa/model_vlmap_answer_noc.py:177-203
     "al_w": "WordWeightAnswerL/fc/weights", "al_b": "WordWeightAnswerL/fc/biases",
 }
 _NOC = ("vlmap_answer_noc", "vlmap_answer_nocarch")
+_QP_SCOPE["vlmap_answer_full"] = "q_L_mean"     # vqa/model_vlmap_answer_full.py:124-131
+_EXTRA_NAMES = {
+    "qs_w": "q_L_log_sigma_sq/fc/weights", "qs_b": "q_L_log_sigma_sq/fc/biases",
+    "tw_w": "TunedWordWeightAnswer/fc/weights", "tw_b": "TunedWordWeightAnswer/fc/biases",   # _vqa_all.py:215-219
+    "va_w": "v_adapt/fc/weights", "va_b": "v_adapt/fc/biases",                               # _adapt.py:132-135
+    "va_gamma": "v_adapt/LayerNorm/gamma", "va_beta": "v_adapt/LayerNorm/beta",
+}
 
 
 def tf_name(field, variant):
     """Checkpoint variable name of a parameter field for a model_type."""
     if variant in _NOC and field in _NOC_NAMES:
         return _NOC_NAMES[field]
+    if field in _EXTRA_NAMES:
+        return _EXTRA_NAMES[field]
     if field in _QP_LEAF:
         return _QP_SCOPE[variant] + "/" + _QP_LEAF[field]
     if variant == "standard":  # vqa/model_standard.py:251-275
@@ -190,19 +199,20 @@ class PendingScalars:
 
     def __init__(self, eng):
         slots = PendingScalars._pool.setdefault(id(eng), [])
-        self.buf = slots.pop() if slots else torch.zeros(1 + len(L.REPORT_KEYS)).pin_memory()
+        self.buf = slots.pop() if slots else torch.zeros(1 + L.NUM_REPORT).pin_memory()
         self._slots = slots
         self.buf[:1].copy_(eng.o_loss, non_blocking=True)
         self.buf[1:].copy_(eng.o_report, non_blocking=True)
         self.event = torch.cuda.Event()
         self.event.record(torch.cuda.current_stream(eng.device))
-        self.nbytes = 4 * (1 + len(L.REPORT_KEYS))
+        self.nbytes = 4 * (1 + L.NUM_REPORT)
+        self._keys = eng.report_keys
 
     def get(self):
         self.event.synchronize()
         vals = self.buf.tolist()
         self._slots.append(self.buf)
-        return vals[0], dict(zip(L.REPORT_KEYS, vals[1:]))
+        return vals[0], dict(zip(self._keys, vals[1:]))
 
 
 class BatchSet:
@@ -251,14 +261,17 @@ class Engine:
         self.copy_stream = torch.cuda.Stream(device=dev)
         # outputs
         self.o_loss = torch.zeros(1, device=dev)
-        self.o_report = torch.zeros(len(L.REPORT_KEYS), device=dev)
+        self.o_report = torch.zeros(L.NUM_REPORT, device=dev)
         self.o_att = torch.zeros(cfg.B, cfg.K, device=dev)
         self.o_logit = torch.zeros(cfg.B, cfg.A, device=dev)
         self.o_pred = torch.zeros(cfg.B, dtype=torch.int32, device=dev)
         self.o_per_sample = torch.zeros(len(L.PER_SAMPLE_KEYS) * cfg.B, device=dev)
         self.o_condition = torch.zeros(cfg.B, cfg.L, device=dev)
-        self.o_pooled = torch.zeros(cfg.B, cfg.Dv, device=dev)
-        self.h_scalars = torch.zeros(1 + len(L.REPORT_KEYS)).pin_memory()
+        # adapt pools the D-wide v_adapt (vqa/model_vlmap_answer_adapt.py:142)
+        self.o_pooled = torch.zeros(cfg.B, cfg.D if cfg.variant == "vlmap_answer_adapt" else cfg.Dv, device=dev)
+        self.h_scalars = torch.zeros(1 + L.NUM_REPORT).pin_memory()
+        # report keys this model_type fills: the 13 common ones (+ the latent losses of the full variant)
+        self.report_keys = L.REPORT_KEYS + (L.EXTRA_REPORT_KEYS if cfg.variant == "vlmap_answer_full" else [])
         self.grad_norm = torch.zeros(1, device=dev)
         self._outs = L.VqaOutputs(
             loss=self.o_loss.data_ptr(), report=self.o_report.data_ptr(), att_score=self.o_att.data_ptr(),
@@ -475,6 +488,13 @@ class Engine:
                                                self._stream()))
         return out
 
+    def reparam_noise(self, seed, step, batch=None):
+        """The N(0, 1) draw [batch, L] the full variant's forward uses for (seed, step) (vqa_reparam_noise)."""
+        Bn = self.batch_size if batch is None else batch
+        out = torch.empty(Bn, self.cfg.L, dtype=torch.float32, device=self.device)
+        L.check(self.lib.vqa_reparam_noise(self.h, Bn, C.c_uint64(seed), C.c_uint64(step), out.data_ptr(), self._stream()))
+        return out
+
     def peek_activation(self, which, dtype, shape):
         """Copy of an activation the last forward saved in the workspace (vqa_peek_activation)."""
         ptr, nbytes = C.c_void_p(), C.c_uint64()
@@ -488,7 +508,7 @@ class Engine:
         self.h_scalars[1:].copy_(self.o_report, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         vals = self.h_scalars.tolist()
-        return vals[0], dict(zip(L.REPORT_KEYS, vals[1:]))
+        return vals[0], dict(zip(self.report_keys, vals[1:]))
 
     def read_scalars_async(self):
         """Enqueue the D2H of loss + report into a fresh pinned slot and return a handle; handle.get() waits for

@@ -16,7 +16,8 @@ VQA_ERR_BAD_ARG, VQA_ERR_BAD_SHAPE, VQA_ERR_WORKSPACE = -1, -2, -3
 VQA_ERR_CUDA, VQA_ERR_NO_DEVICE, VQA_ERR_STATE = -4, -5, -6
 VARIANT_VLMAP_ANSWER, VARIANT_STANDARD, VARIANT_VLMAP_ANSWER2, VARIANT_VLMAP_ANSWER_NO_NOISE, VARIANT_VLMAP_ANSWER_NOC = range(5)
 VARIANTS = {"vlmap_answer": 0, "standard": 1, "vlmap_answer2": 2, "vlmap_answer_no_noise": 3,
-            "vlmap_answer_noc": 4, "vlmap_answer_nocarch": 4}   # nocarch is the same graph (model_vlmap_answer_nocarch.py)
+            "vlmap_answer_noc": 4, "vlmap_answer_nocarch": 4,   # nocarch is the same graph (model_vlmap_answer_nocarch.py)
+            "vlmap_answer_full": 5, "vlmap_answer_vqa_all": 6, "vlmap_answer_vqa_all2": 7, "vlmap_answer_adapt": 8}
 PREC_BF16, PREC_FP32 = 0, 1
 
 REPORT_KEYS = [
@@ -24,13 +25,16 @@ REPORT_KEYS = [
     "normal_test_acc", "normal_test_object_acc", "normal_test_attribute_acc", "normal_exist_acc",
     "normal_train_exist_acc", "max_exist_acc", "test_max_acc", "test_max_exist_acc",
 ]
+# report slots after the 13 common ones (vqa/model_vlmap_answer_full.py:221-223); 0 for the other variants
+EXTRA_REPORT_KEYS = ["latent_loss", "train_latent_loss"]
+NUM_REPORT = len(REPORT_KEYS) + len(EXTRA_REPORT_KEYS)   # VQA_NUM_REPORT
 PER_SAMPLE_KEYS = [
     "all_score", "max_train_score", "test_obj_score", "test_obj_max_score", "test_attr_score",
     "test_attr_max_score",
 ]
 
 NUM_PHASES = 14
-ACT_HQ, ACT_HL, ACT_HP, ACT_JD, ACT_Z, ACT_JDL = range(6)
+ACT_HQ, ACT_HL, ACT_HP, ACT_JD, ACT_Z, ACT_JDL, ACT_VA = range(7)
 SITE_ATT, SITE_JOINT, SITE_JOINT_L = 1, 2, 3   # dropout sites of vqa_dropout_mask_site
 
 PARAM_FIELDS = [
@@ -55,7 +59,8 @@ class VqaConfig(C.Structure):
 
 # the extra question layer of model_vlmap_answer2 (q_L_ft2: FC + LayerNorm + tanh) and model_vlmap_answer_no_noise
 # (q_L_mean: FC only); NULL in the struct for the other variants
-EXTRA_FIELDS = ["qp_w", "qp_b", "qp_gamma", "qp_beta", "jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b"]
+EXTRA_FIELDS = ["qp_w", "qp_b", "qp_gamma", "qp_beta", "jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b",
+                "qs_w", "qs_b", "tw_w", "tw_b", "va_w", "va_b", "va_gamma", "va_beta"]
 
 
 def param_fields(variant):
@@ -65,7 +70,13 @@ def param_fields(variant):
     if variant == "vlmap_answer_no_noise":
         return PARAM_FIELDS + EXTRA_FIELDS[:2]
     if variant in ("vlmap_answer_noc", "vlmap_answer_nocarch"):   # joint_l + WordWeightAnswerL
-        return PARAM_FIELDS + EXTRA_FIELDS[4:]
+        return PARAM_FIELDS + EXTRA_FIELDS[4:10]
+    if variant == "vlmap_answer_full":        # q_L_mean (qp_*) + q_L_log_sigma_sq (qs_*)
+        return PARAM_FIELDS + ["qp_w", "qp_b", "qs_w", "qs_b"]
+    if variant in ("vlmap_answer_vqa_all", "vlmap_answer_vqa_all2"):   # TunedWordWeightAnswer
+        return PARAM_FIELDS + ["tw_w", "tw_b"]
+    if variant == "vlmap_answer_adapt":       # v_adapt
+        return PARAM_FIELDS + ["va_w", "va_b", "va_gamma", "va_beta"]
     return list(PARAM_FIELDS)
 
 
@@ -144,6 +155,7 @@ SYMBOLS = {
     "vqa_gemm": (C.c_int32, [_P, C.POINTER(VqaGemmDesc), _P]),
     "vqa_split_bf16": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P]),
     "vqa_dropout_mask_site": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
+    "vqa_reparam_noise": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "vqa_multimem_all_reduce": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vqa_set_early_gradients": (C.c_int32, [_P, C.c_int32]),
     "vqa_stream_wait_early_gradients": (C.c_int32, [_P, _P]),

@@ -37,8 +37,23 @@ def get_dummy_data():
             "max_box_num": bs, "vfeat_dim": dim}
 
 
+# report keys of the older family members (vqa/model_vlmap_answer_no_noise.py:211-219, _full.py:221-235,
+# _adapt.py:212-220): nine scalars under longer names; the other four of the base model are not reported there
+OLD_REPORT_NAMES = {
+    "answer_train_loss": "answer_train_loss", "answer_report_loss": "answer_report_loss",
+    "answer_acc": "answer_accuracy", "exist_acc": "exist_answer_accuracy", "test_acc": "test_answer_accuracy",
+    "normal_test_acc": "normal_test_answer_accuracy", "max_exist_acc": "max_exist_answer_accuracy",
+    "test_max_acc": "test_max_answer_accuracy", "test_max_exist_acc": "test_max_exist_answer_accuracy",
+    "latent_loss": "latent_loss", "train_latent_loss": "train_latent_loss",
+}
+
+
 class Model(object):
     MODEL_TYPE = "vlmap_answer"
+    OLD_REPORT = False     # True: report under the names of OLD_REPORT_NAMES
+    # checkpoint variables the reference creates for this model_type that never reach the loss (kept so that
+    # state_dict() / load_state_dict() round-trip a reference checkpoint): name -> shape as a function of the config
+    DEAD_VARIABLES = {}
 
     def __init__(self, batch, config, is_train=True, image_features=None):
         self.batch = batch
@@ -85,7 +100,7 @@ class Model(object):
 
     # ---- reference API: which variables train / transfer (by top-level scope) ------------------
     def filter_train_vars(self, trainable_vars):
-        frozen_scopes = {TF_NAMES[f].split("/")[0] for f in frozen_fields(self.MODEL_TYPE)}
+        frozen_scopes = {tf_name(f, self.MODEL_TYPE).split("/")[0] for f in frozen_fields(self.MODEL_TYPE)}
         return [v for v in trainable_vars if _name(v).split("/")[0] not in frozen_scopes]
 
     def filter_transfer_vars(self, all_vars):
@@ -113,6 +128,15 @@ class Model(object):
         if params is None:
             params = self.initial_params(seed=int(getattr(cfgd, "seed", 123)))
         self.engine.load_params(params)
+        rng = np.random.default_rng(int(getattr(cfgd, "seed", 123)) + 99)
+        self.dead_variables = {}
+        for name, shape_fn in self.DEAD_VARIABLES.items():
+            shape = shape_fn(self.engine_config)
+            if name.endswith("weights"):
+                lim = np.sqrt(6.0 / (shape[0] + shape[1]))
+                self.dead_variables[name] = rng.uniform(-lim, lim, size=shape).astype(np.float32)
+            else:
+                self.dead_variables[name] = (np.ones if name.endswith("gamma") else np.zeros)(shape, np.float32)
         self.seed = int(getattr(cfgd, "seed", 123))
         self.global_step = 0
         self._dp = None
@@ -125,7 +149,8 @@ class Model(object):
              ("B", "K", "Dv", "D", "L", "J", "A", "T", "W", "Vq", "num_train_answer")}
         p, _ = init_params(c, seed=seed, variant="standard")  # Xavier head; replaced below for vlmap_answer
         extra, _ = init_params(c, seed=seed + 1, variant=self.MODEL_TYPE)
-        p.update({k: v for k, v in extra.items() if k.startswith(("qp_", "jl_", "al_"))})   # layers of the variants
+        p.update({k: v for k, v in extra.items()
+                  if k.startswith(("qp_", "jl_", "al_", "qs_", "tw_", "va_")) or (k == "pl_w" and self.MODEL_TYPE == "vlmap_answer_adapt")})   # layers of the variants
         glove = getattr(self.config, "glove_embed", None)
         if glove is not None:  # LearnGloVe (vlmap/modules.py:415-448): rows by vocabulary word
             p["embed"] = np.asarray(glove, np.float32)
@@ -143,7 +168,9 @@ class Model(object):
 
     # ---- checkpoint contract: tensors keyed by TF variable names ---------------------------------
     def state_dict(self):
-        return {k: v.detach().cpu().numpy().copy() for k, v in self.engine.params.by_tf_name().items()}
+        sd = {k: v.detach().cpu().numpy().copy() for k, v in self.engine.params.by_tf_name().items()}
+        sd.update({k: v.copy() for k, v in self.dead_variables.items()})
+        return sd
 
     def load_state_dict(self, state, strict=True):
         fields = {tf_name(f, self.MODEL_TYPE): f for f in L.param_fields(self.MODEL_TYPE)}
@@ -153,6 +180,9 @@ class Model(object):
         for name, f in fields.items():
             if name in state:
                 self.engine.params.views[f].copy_(torch.as_tensor(np.asarray(state[name], np.float32)))
+        for name in self.dead_variables:
+            if name in state:
+                self.dead_variables[name] = np.asarray(state[name], np.float32).copy()
         self.engine.prepare_params()
 
     # ---- running the path --------------------------------------------------------------------------
@@ -199,10 +229,8 @@ class Model(object):
             pending = self.engine.read_scalars_async()
             return pending, h2d, pending.nbytes
         loss, report = self.engine.read_scalars()
-        self.loss = loss
-        self.losses["answer"] = loss
-        self.report = report
-        return loss, h2d, 4 * (1 + len(L.REPORT_KEYS))
+        self._bind_report(loss, report)
+        return loss, h2d, 4 * (1 + L.NUM_REPORT)
 
     def _bind_outputs(self):
         e = self.engine
@@ -214,9 +242,21 @@ class Model(object):
 
     def fetch(self):
         """Synchronise and return (loss, report) of the last forward."""
-        self.loss, self.report = self.engine.read_scalars()
-        self.losses["answer"] = self.loss
+        self._bind_report(*self.engine.read_scalars())
         return self.loss, self.report
+
+    def _bind_report(self, loss, report):
+        """model.loss / model.losses / model.report under the key names this model_type uses in the reference."""
+        self.loss = loss
+        if "train_latent_loss" in report:   # vqa/model_vlmap_answer_full.py:220-221: two entries that sum to the loss
+            self.losses["answer"] = report["answer_train_loss"]
+            self.losses["latent"] = report["train_latent_loss"]
+            report = dict(report, latent_loss_weight=0.1)
+        else:
+            self.losses["answer"] = loss
+        if self.OLD_REPORT:
+            report = {OLD_REPORT_NAMES.get(k, k): v for k, v in report.items() if k in OLD_REPORT_NAMES or k == "latent_loss_weight"}
+        self.report = report
 
 
 class Answer2Model(Model):
@@ -227,6 +267,39 @@ class Answer2Model(Model):
 class NoNoiseModel(Model):
     """vqa/model_vlmap_answer_no_noise.py: q_L_mean = FC(q) (linear) feeds q_linear_l."""
     MODEL_TYPE = "vlmap_answer_no_noise"
+    OLD_REPORT = True
+
+
+class FullModel(Model):
+    """vqa/model_vlmap_answer_full.py: q_linear_l reads q_L_mean + N(0,1) * sqrt(exp(q_L_log_sigma_sq)); the KL latent
+    loss enters model.loss with weight 0.1 and is reported as latent_loss / train_latent_loss."""
+    MODEL_TYPE = "vlmap_answer_full"
+    OLD_REPORT = True
+
+
+class AdaptModel(Model):
+    """vqa/model_vlmap_answer_adapt.py: attention pools v_adapt = relu(LN(FC(V))) (trained, 1024-d) instead of the raw
+    features; pooled_linear_l/fc/weights is [V_DIM, L_DIM]."""
+    MODEL_TYPE = "vlmap_answer_adapt"
+    OLD_REPORT = True
+
+
+class VqaAllModel(Model):
+    """vqa/model_vlmap_answer_vqa_all.py: the frozen word-weight head (absent answers filled with the row minimum) plus
+    the trained TunedWordWeightAnswer on the same joint; tuned_q_linear_l / tuned_joint_fc exist as variables but
+    never reach the loss (:215-216 feeds `joint`)."""
+    MODEL_TYPE = "vlmap_answer_vqa_all"
+    DEAD_VARIABLES = {
+        "tuned_q_linear_l/fc/weights": lambda c: (c.L, c.L), "tuned_q_linear_l/fc/biases": lambda c: (c.L,),
+        "tuned_q_linear_l/LayerNorm/gamma": lambda c: (c.L,), "tuned_q_linear_l/LayerNorm/beta": lambda c: (c.L,),
+        "tuned_joint_fc/fc/weights": lambda c: (c.L, c.J), "tuned_joint_fc/fc/biases": lambda c: (c.J,),
+        "tuned_joint_fc/LayerNorm/gamma": lambda c: (c.J,), "tuned_joint_fc/LayerNorm/beta": lambda c: (c.J,),
+    }
+
+
+class VqaAll2Model(VqaAllModel):
+    """vqa/model_vlmap_answer_vqa_all2.py: no fill; BCE(tuned) unmasked; pred = argmax(fixed * test + tuned * train)."""
+    MODEL_TYPE = "vlmap_answer_vqa_all2"
 
 
 class NocModel(Model):

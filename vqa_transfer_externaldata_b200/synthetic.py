@@ -19,7 +19,8 @@ PARAM_SHAPES = {
     "qv_w": lambda c: (c["L"], c["D"]), "qv_b": lambda c: (c["D"],),
     "qv_gamma": lambda c: (c["D"],), "qv_beta": lambda c: (c["D"],),
     "att_w": lambda c: (c["D"], 1), "att_b": lambda c: (1,),
-    "pl_w": lambda c: (c["Dv"], c["L"]), "pl_b": lambda c: (c["L"],),
+    # adapt pools the 1024-d v_adapt instead of the raw features (model_vlmap_answer_adapt.py:142-150)
+    "pl_w": lambda c: (c["D"] if c.get("variant") == "vlmap_answer_adapt" else c["Dv"], c["L"]), "pl_b": lambda c: (c["L"],),
     "pl_gamma": lambda c: (c["L"],), "pl_beta": lambda c: (c["L"],),
     "ql_w": lambda c: (c["L"], c["L"]), "ql_b": lambda c: (c["L"],),
     "ql_gamma": lambda c: (c["L"],), "ql_beta": lambda c: (c["L"],),
@@ -33,10 +34,21 @@ PARAM_SHAPES = {
     "jl_w": lambda c: (c["L"], c["J"]), "jl_b": lambda c: (c["J"],),
     "jl_gamma": lambda c: (c["J"],), "jl_beta": lambda c: (c["J"],),
     "al_w": lambda c: (c["J"], c["A"]), "al_b": lambda c: (c["A"],),
+    # vlmap_answer_full: q_L_log_sigma_sq next to q_L_mean (= qp_*)
+    "qs_w": lambda c: (c["L"], c["L"]), "qs_b": lambda c: (c["L"],),
+    # vlmap_answer_vqa_all / vqa_all2: TunedWordWeightAnswer
+    "tw_w": lambda c: (c["J"], c["A"]), "tw_b": lambda c: (c["A"],),
+    # vlmap_answer_adapt: v_adapt
+    "va_w": lambda c: (c["Dv"], c["D"]), "va_b": lambda c: (c["D"],),
+    "va_gamma": lambda c: (c["D"],), "va_beta": lambda c: (c["D"],),
 }
 _NOC = ("jl_w", "jl_b", "jl_gamma", "jl_beta", "al_w", "al_b")
 EXTRA_FIELDS = {"vlmap_answer2": ("qp_w", "qp_b", "qp_gamma", "qp_beta"), "vlmap_answer_no_noise": ("qp_w", "qp_b"),
-                "vlmap_answer_noc": _NOC, "vlmap_answer_nocarch": _NOC}
+                "vlmap_answer_noc": _NOC, "vlmap_answer_nocarch": _NOC,
+                "vlmap_answer_full": ("qp_w", "qp_b", "qs_w", "qs_b"),
+                "vlmap_answer_vqa_all": ("tw_w", "tw_b"), "vlmap_answer_vqa_all2": ("tw_w", "tw_b"),
+                "vlmap_answer_adapt": ("va_w", "va_b", "va_gamma", "va_beta")}
+_EXTRA_PREFIXES = ("qp_", "jl_", "al_", "qs_", "tw_", "va_")
 
 
 def dims(B=512, K=36, Dv=2048, D=1024, L=1024, J=None, A=3000, T=14, W=300, Vq=8192,
@@ -57,9 +69,9 @@ def init_params(c, seed=4321, variant="vlmap_answer", perturb=0.0, present_frac=
     rng = np.random.default_rng(seed)
     p = {}
     for name, shp in PARAM_SHAPES.items():
-        if name.startswith(("qp_", "jl_", "al_")) and name not in EXTRA_FIELDS.get(variant, ()):
+        if name.startswith(_EXTRA_PREFIXES) and name not in EXTRA_FIELDS.get(variant, ()):
             continue
-        shape = shp(c)
+        shape = shp(dict(c, variant=variant))
         if name == "embed":
             p[name] = (rng.standard_normal(shape) * 0.4).astype(np.float32)  # GloVe-like scale
         elif name.endswith("_gamma"):
