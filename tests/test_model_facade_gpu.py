@@ -45,8 +45,10 @@ def test_train_step_through_the_plugin_interface(model_type):
     names = list(after)
     trained = {n.split("/")[0] for n in model.filter_train_vars(names)}
     frozen = {n.split("/")[0] for n in names} - trained
-    if model_type != "standard":
-        assert {"q_linear_l", "pooled_linear_l", "joint_fc"} <= frozen
+    if model_type in ("vlmap_answer_noc", "vlmap_answer_nocarch"):   # model_vlmap_answer_noc.py:78-88
+        assert {"q_linear_l", "pooled_linear_l", "joint_v", "joint_l", "WordWeightAnswerV", "WordWeightAnswerL"} <= frozen
+    elif model_type != "standard":
+        assert {"q_linear_l", "pooled_linear_l", "joint_fc", "WordWeightAnswer"} <= frozen
     changed = {n.split("/")[0] for n in names if not np.array_equal(before[n], after[n])}
     assert changed and changed <= trained, (changed - trained)
     if model_type in ("vlmap_answer_vqa_all", "vlmap_answer_vqa_all2"):

@@ -17,6 +17,7 @@
 #include <math_constants.h>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "philox.cuh"
 #include "ptx.cuh"
 
@@ -186,6 +187,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(FwdArgs a, int K,
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int CH = D >> 3;
   const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
+  pdl_sync();
   if (SLAB) {
     const int head = ((3 * D + K + 3 * ATT_WARPS + 2) * 4 + 15) & ~15;
     uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm) + head);
@@ -348,6 +350,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
   uint64_t* zbar = nullptr;
+  pdl_sync();
   if (SLAB) {
     // the slab copy is in flight while the feature rows are reduced against dP below
     const size_t head = ((static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * 4 +
@@ -662,7 +665,7 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
   const bool use_slab = smem_slab <= 110 * 1024 && (slab & 15) == 0 && !a.v_lo;
   auto launch = [&](auto kern, size_t smem) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    kern<<<a.batch, ATT_THREADS, smem, s>>>(f, K, D, Dv, keep, thr);
+    launch_pdl(kern, dim3(a.batch), dim3(ATT_THREADS), smem, s, f, K, D, Dv, keep, thr);
   };
   if (precision == VQA_PREC_FP32) {
     if (use_slab) launch(attn_fwd_kernel<float, true>, smem_slab);
@@ -688,11 +691,11 @@ static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv,
   if (use_slab) {
     e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
-    attn_bwd_kernel<ZT, NCOL, true><<<batch, ATT_THREADS, smem_slab, s>>>(g, K, D, Dv, keep, thr);
+    launch_pdl(attn_bwd_kernel<ZT, NCOL, true>, dim3(batch), dim3(ATT_THREADS), smem_slab, s, g, K, D, Dv, keep, thr);
   } else {
     e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
-    attn_bwd_kernel<ZT, NCOL, false><<<batch, ATT_THREADS, head, s>>>(g, K, D, Dv, keep, thr);
+    launch_pdl(attn_bwd_kernel<ZT, NCOL, false>, dim3(batch), dim3(ATT_THREADS), head, s, g, K, D, Dv, keep, thr);
   }
   return cudaGetLastError();
 }

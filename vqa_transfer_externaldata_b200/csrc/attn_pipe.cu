@@ -18,6 +18,7 @@
 #include <cstdlib>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "philox.cuh"
 #include "ptx.cuh"
 
@@ -108,6 +109,7 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_fwd_pipe_kernel(PipeFwdArg
     ptx::fence_barrier_init();
   }
   __syncthreads();
+  pdl_sync();   // barriers are set up under the previous kernel's tail; z / v / hq are read from here on
   const int first = blockIdx.x, stride = gridDim.x;
   const int n_my = first < a.batch ? (a.batch - first + stride - 1) / stride : 0;
 
@@ -355,7 +357,7 @@ VqaStatus attn_fwd_pipe_launch(const VqaAttnFwd& a, int K, int D, int Dv, float 
     smem_set = smem;
   }
   const int grid = a.batch < num_sms ? a.batch : num_sms;
-  attn_fwd_pipe_kernel<<<grid, AP_THREADS, smem, s>>>(f);
+  launch_pdl(attn_fwd_pipe_kernel, dim3(grid), dim3(AP_THREADS), smem, s, f);
   VQA_LAUNCH_CHECK("attn_fwd (pipelined)");
   return VQA_OK;
 }

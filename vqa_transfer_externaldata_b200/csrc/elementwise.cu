@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "internal.h"
+#include "launch.cuh"
 
 namespace vqa {
 
@@ -41,6 +42,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 __global__ void split_bf16_kernel(const float* __restrict__ src, long long rows, long long cols4,
                                   long long ld, bf16* __restrict__ hi, bf16* __restrict__ lo,
                                   long long ld_out) {
+  pdl_sync();
   const long long total = rows * cols4;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -56,6 +58,7 @@ __global__ void gather_features_kernel(const float* __restrict__ bank, const int
                                        long long per_image4, bf16* __restrict__ v_hi,
                                        bf16* __restrict__ v_lo, int* __restrict__ nbox) {
   const int b = blockIdx.y;
+  pdl_sync();
   const long long img = image_idx[b];
   if (blockIdx.x == 0 && threadIdx.x == 0) nbox[b] = num_boxes[img];
   const float4* src = reinterpret_cast<const float4*>(bank) + img * per_image4;
@@ -74,6 +77,7 @@ __global__ void embed_gather_kernel(const float* __restrict__ embed, const int* 
                                     bf16* __restrict__ e_hi, bf16* __restrict__ e_lo) {
   const int row = blockIdx.x;  // t * batch + b
   const int t = row / batch, b = row - t * batch;
+  pdl_sync();
   const int id = q_intseq[b * Tstride + t];
   const float* src = embed + static_cast<long long>(id) * W;
   for (int c = threadIdx.x; c < Wpad; c += blockDim.x) {
@@ -92,6 +96,7 @@ __global__ void embed_scatter_add_kernel(const float* __restrict__ dE, long long
                                          float* __restrict__ d_embed) {
   const int row = blockIdx.x;
   const int t = row / batch, b = row - t * batch;
+  pdl_sync();
   if (t >= q_len[b]) return;
   const int id = q_intseq[b * Tstride + t];
   float* dst = d_embed + static_cast<long long>(id) * W;
@@ -104,6 +109,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, long long row
                                       long long ld, float* __restrict__ part) {
   __shared__ float sm[32][33];
   const long long c = blockIdx.x * 32LL + threadIdx.x;
+  pdl_sync();
   float acc = 0.0f;
   if (c < cols)
     for (long long r = blockIdx.y * 32LL + threadIdx.y; r < rows; r += 32LL * gridDim.y)
@@ -120,6 +126,7 @@ __global__ void colsum_partial_kernel(const float* __restrict__ x, long long row
 __global__ void colsum_final_kernel(const float* __restrict__ part, int parts, long long cols,
                                     float* __restrict__ out) {
   const long long c = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  pdl_sync();
   if (c >= cols) return;
   float s = 0.0f;
   for (int p = 0; p < parts; ++p) s += part[p * cols + c];
@@ -258,8 +265,8 @@ VqaStatus split_bf16_launch(const float* src, long long rows, long long cols, lo
   if ((cols & 3) || (ld & 3) || (ld_out & 3))
     return set_error(VQA_ERR_BAD_SHAPE, "split_bf16: cols and pitches must be multiples of 4");
   if (rows * cols == 0) return VQA_OK;
-  split_bf16_kernel<<<grid_for(rows * cols / 4, 256), 256, 0, s>>>(src, rows, cols / 4, ld, hi, lo,
-                                                                  ld_out);
+  launch_pdl(split_bf16_kernel, dim3(grid_for(rows * cols / 4, 256)), dim3(256), 0, s, src, rows, cols / 4, ld, hi, lo,
+             ld_out);
   VQA_LAUNCH_CHECK("split_bf16");
   return VQA_OK;
 }
@@ -272,7 +279,7 @@ VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const 
   int gx = static_cast<int>((per_image4 + 255) / 256);
   if (gx > 8) gx = 8;
   dim3 grid(gx, batch);
-  gather_features_kernel<<<grid, 256, 0, s>>>(bank, num_boxes, image_idx, batch, per_image4, v_hi,
+  launch_pdl(gather_features_kernel, dim3(grid), dim3(256), 0, s, bank, num_boxes, image_idx, batch, per_image4, v_hi,
                                               v_lo, nbox);
   VQA_LAUNCH_CHECK("gather_features");
   return VQA_OK;
@@ -281,7 +288,7 @@ VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const 
 VqaStatus embed_gather_launch(const float* embed, const int* q_intseq, int batch, int T, int Tstride,
                               int W, int Wpad, int /*Bpad*/, bf16* e_hi, bf16* e_lo, cudaStream_t s) {
   if (batch * T == 0) return VQA_OK;
-  embed_gather_kernel<<<batch * T, 128, 0, s>>>(embed, q_intseq, batch, T, Tstride, W, Wpad, e_hi,
+  launch_pdl(embed_gather_kernel, dim3(batch * T), dim3(128), 0, s, embed, q_intseq, batch, T, Tstride, W, Wpad, e_hi,
                                                 e_lo);
   VQA_LAUNCH_CHECK("embed_gather");
   return VQA_OK;
@@ -291,7 +298,7 @@ VqaStatus embed_scatter_add_launch(const float* dE, long long ld_dE, const int* 
                                    const int* q_len, int batch, int T, int Tstride, int W, int /*Bpad*/,
                                    float* d_embed, cudaStream_t s) {
   if (batch * T == 0) return VQA_OK;
-  embed_scatter_add_kernel<<<batch * T, 128, 0, s>>>(dE, ld_dE, q_intseq, q_len, batch, T, Tstride, W,
+  launch_pdl(embed_scatter_add_kernel, dim3(batch * T), dim3(128), 0, s, dE, ld_dE, q_intseq, q_len, batch, T, Tstride, W,
                                                      d_embed);
   VQA_LAUNCH_CHECK("embed_scatter_add");
   return VQA_OK;
@@ -304,9 +311,9 @@ VqaStatus colsum_launch(const float* x, long long rows, long long cols, long lon
   if (rs > 32) rs = 32;
   if (rs < 1) rs = 1;
   dim3 grid(static_cast<unsigned>((cols + 31) / 32), rs);
-  colsum_partial_kernel<<<grid, dim3(32, 32), 0, s>>>(x, rows, cols, ld, scratch);
+  launch_pdl(colsum_partial_kernel, dim3(grid), dim3(32, 32), 0, s, x, rows, cols, ld, scratch);
   VQA_LAUNCH_CHECK("colsum_partial");
-  colsum_final_kernel<<<static_cast<unsigned>((cols + 255) / 256), 256, 0, s>>>(scratch, rs, cols, out);
+  launch_pdl(colsum_final_kernel, dim3(static_cast<unsigned>((cols + 255) / 256)), dim3(256), 0, s, scratch, rs, cols, out);
   VQA_LAUNCH_CHECK("colsum_final");
   return VQA_OK;
 }

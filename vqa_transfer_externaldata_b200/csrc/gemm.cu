@@ -23,6 +23,7 @@
 #include <unordered_map>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace vqa {
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // everything above overlapped the previous kernel's tail; operands / bias / addend are read below
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -477,8 +479,7 @@ cudaError_t launch_one(const CUtensorMap& ta_hi, const CUtensorMap& ta_lo, const
     attr_set = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, 1);
-  kern<<<grid, GEMM_THREADS, Cfg::SMEM_BYTES, stream>>>(ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K);
-  return cudaGetLastError();
+  return launch_pdl(kern, grid, dim3(GEMM_THREADS), Cfg::SMEM_BYTES, stream, ta_hi, ta_lo, tb_hi, tb_lo, ep, M, N, K);
 }
 
 template <int BN, int SPLIT, int KBS = 1>

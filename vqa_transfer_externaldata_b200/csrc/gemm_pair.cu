@@ -21,6 +21,7 @@
 #include <cstdlib>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "ptx.cuh"
 
 namespace vqa {
@@ -117,6 +118,7 @@ __global__ void __launch_bounds__(P_THREADS, 1) gemm_pair_kernel(const __grid_co
   ptx::cluster_sync_all();   // the peer's barriers exist before anything is signalled at them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_sync();   // prologue done under the previous kernel's tail; global memory (operands, semaphores) from here on
 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs) =====================
@@ -376,13 +378,15 @@ cudaError_t launch_pair(const CUtensorMap& ta, const CUtensorMap& tb, const CUte
   cfg.blockDim = dim3(P_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = 2;
   at[0].val.clusterDim.y = 1;
   at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   return cudaLaunchKernelEx(&cfg, kern, ta, tb, ta2, tb2, tof, tob, g);
 }
 

@@ -8,6 +8,7 @@
 #include <math_constants.h>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "philox.cuh"
 
 namespace vqa {
@@ -52,6 +53,7 @@ __global__ void __launch_bounds__(LOSS_THREADS) bce_metrics_kernel(LossArgs a) {
   __shared__ int red_idx[LOSS_THREADS / 32];
   __shared__ float red_val[LOSS_THREADS / 32];
   const int b = blockIdx.x, A = a.A, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  pdl_sync();
   const float* x = a.logit + static_cast<long long>(b) * A;
   const float* z = a.target + static_cast<long long>(b) * A;
   const float* xb = a.loss_b ? a.loss_b + static_cast<long long>(b) * A : nullptr;
@@ -213,6 +215,7 @@ __global__ void __launch_bounds__(256) report_finalize_kernel(const float* __res
                                                               float* __restrict__ loss,
                                                               float* __restrict__ report) {
   __shared__ float sm[8][S_COUNT];
+  pdl_sync();
   float acc[S_COUNT];
 #pragma unroll
   for (int i = 0; i < S_COUNT; ++i) acc[i] = 0.f;
@@ -259,6 +262,7 @@ __global__ void bce_grad_kernel(const float* __restrict__ logit, const float* __
                                 long long total4, int A4, int num_train_answer, int use_train_mask,
                                 float grad_scale, float* __restrict__ d_f32, bf16* __restrict__ d_hi,
                                 bf16* __restrict__ d_lo) {
+  pdl_sync();
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const int c = static_cast<int>(i % A4) * 4;
@@ -325,9 +329,9 @@ VqaStatus bce_metrics_launch(int batch, int A, int num_train_answer, int use_tra
   a.is_object = masks.is_object; a.is_attribute = masks.is_attribute; a.answer_exist = masks.answer_exist;
   a.grad_scale = grad_scale; a.pred = pred; a.per_sample = per_sample; a.batch = batch;
   a.d_f32 = d_logit_f32; a.d_hi = d_hi; a.d_lo = d_lo; a.rows = scratch;
-  bce_metrics_kernel<<<batch, LOSS_THREADS, 0, s>>>(a);
+  launch_pdl(bce_metrics_kernel, dim3(batch), dim3(LOSS_THREADS), 0, s, a);
   VQA_LAUNCH_CHECK("bce_metrics");
-  report_finalize_kernel<<<1, 256, 0, s>>>(scratch, batch, loss, report);
+  launch_pdl(report_finalize_kernel, dim3(1), dim3(256), 0, s, scratch, batch, loss, report);
   VQA_LAUNCH_CHECK("report_finalize");
   return VQA_OK;
 }
@@ -347,9 +351,9 @@ VqaStatus bce_metrics2_launch(int batch, int A, int num_train_answer, int use_tr
   a.is_object = masks.is_object; a.is_attribute = masks.is_attribute; a.answer_exist = masks.answer_exist;
   a.grad_scale = 0.f; a.pred = pred; a.per_sample = per_sample; a.batch = batch;
   a.d_f32 = nullptr; a.d_hi = nullptr; a.d_lo = nullptr; a.rows = scratch;
-  bce_metrics_kernel<<<batch, LOSS_THREADS, 0, s>>>(a);
+  launch_pdl(bce_metrics_kernel, dim3(batch), dim3(LOSS_THREADS), 0, s, a);
   VQA_LAUNCH_CHECK("bce_metrics");
-  report_finalize_kernel<<<1, 256, 0, s>>>(scratch, batch, loss, report);
+  launch_pdl(report_finalize_kernel, dim3(1), dim3(256), 0, s, scratch, batch, loss, report);
   VQA_LAUNCH_CHECK("report_finalize");
   return VQA_OK;
 }
@@ -362,8 +366,8 @@ VqaStatus bce_grad_launch(int batch, int A, int num_train_answer, int use_train_
   const long long total4 = static_cast<long long>(batch) * A / 4;
   long long g = (total4 + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
-  bce_grad_kernel<<<static_cast<int>(g), 256, 0, s>>>(logit, target, total4, A / 4, num_train_answer,
-                                                      use_train_mask, grad_scale, d_logit_f32, d_hi, d_lo);
+  launch_pdl(bce_grad_kernel, dim3(static_cast<int>(g)), dim3(256), 0, s, logit, target, total4, A / 4, num_train_answer,
+             use_train_mask, grad_scale, d_logit_f32, d_hi, d_lo);
   VQA_LAUNCH_CHECK("bce_grad");
   return VQA_OK;
 }

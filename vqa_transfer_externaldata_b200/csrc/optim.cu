@@ -9,6 +9,7 @@
 #include <cmath>
 
 #include "internal.h"
+#include "launch.cuh"
 
 namespace vqa {
 
@@ -19,6 +20,7 @@ constexpr int OPT_THREADS = 256;
 __global__ void __launch_bounds__(OPT_THREADS) sumsq_partial_kernel(const float* __restrict__ g,
                                                                     long long n, float* __restrict__ part) {
   __shared__ float red[OPT_THREADS / 32];
+  pdl_sync();
   float acc = 0.f;
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < n4;
@@ -43,6 +45,7 @@ __global__ void __launch_bounds__(OPT_THREADS) norm_final_kernel(const float* __
                                                                  float* __restrict__ norm_out,
                                                                  float* __restrict__ user_out) {
   __shared__ double red[OPT_THREADS / 32];
+  pdl_sync();
   double acc = 0.0;
   for (int i = threadIdx.x; i < parts; i += OPT_THREADS) acc += static_cast<double>(part[i]);
 #pragma unroll
@@ -63,6 +66,7 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* __restrict__ p
                                                            long long n, float lr_t, float b1, float b2,
                                                            float eps, float clip,
                                                            const float* __restrict__ norm) {
+  pdl_sync();
   const float nrm = norm[0];
   const float scale = clip > 0.f ? clip / fmaxf(nrm, clip) : 1.f;  // clip_by_global_norm
   const long long n4 = n >> 2;
@@ -109,14 +113,14 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
   const long long need = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   if (need < blocks) blocks = need < 1 ? 1 : static_cast<int>(need);
   if (blocks > 2048) blocks = 2048;
-  sumsq_partial_kernel<<<blocks, OPT_THREADS, 0, s>>>(grad, n, scratch + 8);
+  launch_pdl(sumsq_partial_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, grad, n, scratch + 8);
   VQA_LAUNCH_CHECK("sumsq_partial");
-  norm_final_kernel<<<1, OPT_THREADS, 0, s>>>(scratch + 8, blocks, scratch, grad_norm_out);
+  launch_pdl(norm_final_kernel, dim3(1), dim3(OPT_THREADS), 0, s, scratch + 8, blocks, scratch, grad_norm_out);
   VQA_LAUNCH_CHECK("norm_final");
   const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t)));
-  adam_kernel<<<blocks, OPT_THREADS, 0, s>>>(param, grad, m, v, n, static_cast<float>(lr_t), beta1, beta2, eps,
-                                             clip_norm, scratch);
+  launch_pdl(adam_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, param, grad, m, v, n, static_cast<float>(lr_t), beta1,
+             beta2, eps, clip_norm, scratch);
   VQA_LAUNCH_CHECK("adam");
   return VQA_OK;
 }

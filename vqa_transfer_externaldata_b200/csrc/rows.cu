@@ -6,6 +6,7 @@
 #include <cuda_runtime.h>
 
 #include "internal.h"
+#include "launch.cuh"
 #include "philox.cuh"
 
 namespace vqa {
@@ -55,6 +56,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_ln_relu_fwd_kernel(RowLnFwd a
   __shared__ float red[ROW_THREADS / 32];
   const int row = blockIdx.x, N = a.N, CH = N >> 3;
   const long long base = static_cast<long long>(row) * N;
+  pdl_sync();
   float x[MAX_CHUNKS][8];
   float s = 0.f;
 #pragma unroll
@@ -121,6 +123,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_ln_relu_bwd_kernel(RowLnBwd a
   __shared__ float red[ROW_THREADS / 32];
   const int row = blockIdx.x, N = a.N, CH = N >> 3;
   const long long base = static_cast<long long>(row) * N;
+  pdl_sync();
   const float mean = a.mean[row], rstd = a.rstd[row];
   const float inv_keep = 1.0f / a.keep;
   float xh[MAX_CHUNKS][8], dxh[MAX_CHUNKS][8];
@@ -194,7 +197,7 @@ VqaStatus row_ln_relu_fwd_launch(const RowLnFwd& a, cudaStream_t s) {
   if (a.rows == 0) return VQA_OK;
   if ((a.N & 7) || a.N > 8 * ROW_THREADS * MAX_CHUNKS)
     return set_error(VQA_ERR_BAD_SHAPE, "row_ln_relu: N must be a multiple of 8 and <= 4096");
-  row_ln_relu_fwd_kernel<<<a.rows, ROW_THREADS, 0, s>>>(a, keep_threshold(a.keep));
+  launch_pdl(row_ln_relu_fwd_kernel, dim3(a.rows), dim3(ROW_THREADS), 0, s, a, keep_threshold(a.keep));
   VQA_LAUNCH_CHECK("row_ln_relu_fwd");
   return VQA_OK;
 }
@@ -203,7 +206,7 @@ VqaStatus row_ln_relu_bwd_launch(const RowLnBwd& a, cudaStream_t s) {
   if (a.rows == 0) return VQA_OK;
   if ((a.N & 7) || a.N > 8 * ROW_THREADS * MAX_CHUNKS)
     return set_error(VQA_ERR_BAD_SHAPE, "row_ln_relu: N must be a multiple of 8 and <= 4096");
-  row_ln_relu_bwd_kernel<<<a.rows, ROW_THREADS, 0, s>>>(a, keep_threshold(a.keep));
+  launch_pdl(row_ln_relu_bwd_kernel, dim3(a.rows), dim3(ROW_THREADS), 0, s, a, keep_threshold(a.keep));
   VQA_LAUNCH_CHECK("row_ln_relu_bwd");
   return VQA_OK;
 }
