@@ -308,6 +308,14 @@ VQA_API VqaStatus vqa_adam_step(VqaHandle h, float* param, const float* grad, fl
                                 int64_t n, float lr, float beta1, float beta2, float eps,
                                 float clip_norm, int64_t t, float* grad_norm_out, void* stream);
 
+/* The same step with the parameter refresh folded in: `params` names the tensors of the model; every weight matrix of
+ * it that lies inside [param, param + n) has its GEMM-operand shadow rewritten by the Adam pass itself (and the GRU
+ * weights repacked), i.e. vqa_adam_step followed by vqa_prepare_params of the trainable matrices, in one pass over
+ * the parameters instead of two. */
+VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* params, float* param, const float* grad,
+                                         float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                                         float eps, float clip_norm, int64_t t, float* grad_norm_out, void* stream);
+
 /* ---- per-phase device timing (bench.py roofline): CUDA events recorded on the caller's stream around
  * the phases of vqa_forward / vqa_backward while enabled. Not for use under CUDA-graph capture. ------- */
 enum {

@@ -271,9 +271,17 @@ struct SlabLnBwd {
 VqaStatus slab_ln_relu_bwd_launch(const SlabLnBwd& a, int precision, cudaStream_t s);
 
 // ---- optim.cu ----
+// weight matrices inside the flat parameter buffer whose GEMM-operand shadows the Adam pass rewrites as it goes
+struct AdamShadows {
+  int n;
+  long long begin4[8], end4[8];   // float4 index range of the tensor inside the flat buffer
+  bf16* hi[8];
+  bf16* lo[8];
+};
 VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, long long n, float lr,
                            float beta1, float beta2, float eps, float clip_norm, long long t,
-                           float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s);
+                           float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s,
+                           const AdamShadows* shadows = nullptr);
 
 // weight of the KL latent loss of the full variant (vqa/model_vlmap_answer_full.py:33)
 #define VQA_LATENT_LOSS_WEIGHT 0.1f

@@ -9,6 +9,8 @@
 // vqa/model_vlmap_answer.py:81-89 -- so those layers run dgrad only).
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "handle.h"
 #include "internal.h"
 
@@ -832,6 +834,60 @@ VQA_API VqaStatus vqa_adam_step(VqaHandle h, float* param, const float* grad, fl
   VQA_TRY(check_ready(h, "vqa_adam_step"));
   return adam_step_launch(param, grad, m, v, n, lr, beta1, beta2, eps, clip_norm, t, grad_norm_out,
                           h->buf.scratch, h->num_sms, static_cast<cudaStream_t>(stream));
+}
+
+VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* p, float* param, const float* grad, float* m,
+                                         float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                         float clip_norm, int64_t t, float* grad_norm_out, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_adam_step_shadowed"));
+  if (!p || !param) return set_error(VQA_ERR_BAD_ARG, "vqa_adam_step_shadowed: null argument");
+  if (!h->params_ready) return set_error(VQA_ERR_STATE, "vqa_adam_step_shadowed: call vqa_prepare_params first");
+  const VqaConfig& c = h->cfg;
+  WeightShadows& w = h->buf.w;
+  const bool adapt = c.variant == VQA_VARIANT_VLMAP_ANSWER_ADAPT;
+  struct Item { const float* src; Planes* dst; long long elems; } items[] = {
+      {p->v_w, &w.v_w, 1LL * c.Dv * c.D},
+      {p->gru_gates_w, &w.gru_gates_w, 1LL * (c.W + c.L) * 2 * c.L},
+      {p->gru_cand_w, &w.gru_cand_w, 1LL * (c.W + c.L) * c.L},
+      {p->qv_w, &w.qv_w, 1LL * c.L * c.D},
+      {p->pl_w, &w.pl_w, 1LL * (adapt ? c.D : c.Dv) * c.L},
+      {p->ql_w, &w.ql_w, 1LL * c.L * c.L},
+      {p->joint_w, &w.joint_w, 1LL * c.L * c.J},
+      {p->ans_w, &w.ans_w, 1LL * c.J * c.A},
+      {p->qp_w, &w.qp_w, 1LL * c.L * c.L},
+      {p->jl_w, &w.jl_w, 1LL * c.L * c.J},
+      {p->al_w, &w.al_w, 1LL * c.J * c.A},
+      {p->qs_w, &w.qs_w, 1LL * c.L * c.L},
+      {p->tw_w, &w.tw_w, 1LL * c.J * c.A},
+      {p->va_w, &w.va_w, 1LL * c.Dv * c.D},
+  };
+  AdamShadows tab{};
+  std::vector<const Item*> rest;   // more than 8 trainable matrices (model_standard): the others are refreshed after
+  bool gru = false;
+  for (const Item& it : items) {
+    if (!it.src || it.src < param || it.src + it.elems > param + n) continue;   // frozen / absent: unchanged
+    const long long off = it.src - param;
+    if ((off & 3) || (it.elems & 3)) return set_error(VQA_ERR_BAD_ARG, "vqa_adam_step_shadowed: tensors must start on 16-byte boundaries");
+    if (it.src == p->gru_gates_w || it.src == p->gru_cand_w) gru = true;
+    if (tab.n < 8) {
+      tab.begin4[tab.n] = off >> 2;
+      tab.end4[tab.n] = (off + it.elems) >> 2;
+      tab.hi[tab.n] = it.dst->hi;
+      tab.lo[tab.n] = it.dst->lo;
+      ++tab.n;
+    } else {
+      rest.push_back(&it);
+    }
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VQA_TRY(adam_step_launch(param, grad, m, v, n, lr, beta1, beta2, eps, clip_norm, t, grad_norm_out, h->buf.scratch,
+                           h->num_sms, s, &tab));
+  for (const Item* it : rest)
+    VQA_TRY(split_bf16_launch(it->src, 1, it->elems, it->elems, it->dst->hi, it->dst->lo, it->elems, s));
+  if (gru && gru_persistent_supported(c.B, c.L, c.precision, h->num_sms))
+    VQA_TRY(gru_pack_weights_launch(w.gru_gates_w.hi + static_cast<long long>(c.W) * 2 * c.L,
+                                    w.gru_cand_w.hi + static_cast<long long>(c.W) * c.L, c.L, h->buf.gru_pack, s));
+  return VQA_OK;
 }
 
 VQA_API VqaStatus vqa_attn_fwd(VqaHandle h, const VqaAttnFwd* a, void* stream) {

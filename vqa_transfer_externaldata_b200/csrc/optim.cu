@@ -4,6 +4,7 @@
 // The trainable set is one flat fp32 buffer (the caller lays the variables out contiguously), so the
 // step is: (1) sum of squares, two-level deterministic reduction; (2) one fused, 128-bit vectorised
 // pass over param / grad / m / v. HBM-bound: 4 reads + 3 writes of 4 bytes per parameter.
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -16,6 +17,24 @@ namespace vqa {
 namespace {
 
 constexpr int OPT_THREADS = 256;
+
+// write 4 updated parameters as GEMM-operand planes (bf16 hi, optional lo residual)
+__device__ __forceinline__ void shadow_store4(bf16* hi, bf16* lo, long long o, const float4& x) {
+  const bf16 h0 = __float2bfloat16_rn(x.x), h1 = __float2bfloat16_rn(x.y), h2 = __float2bfloat16_rn(x.z),
+             h3 = __float2bfloat16_rn(x.w);
+  __nv_bfloat162 p0(h0, h1), p1(h2, h3);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&p0);
+  pk.y = *reinterpret_cast<uint32_t*>(&p1);
+  *reinterpret_cast<uint2*>(hi + o) = pk;
+  if (lo) {
+    __nv_bfloat162 q0(__float2bfloat16_rn(x.x - __bfloat162float(h0)), __float2bfloat16_rn(x.y - __bfloat162float(h1)));
+    __nv_bfloat162 q1(__float2bfloat16_rn(x.z - __bfloat162float(h2)), __float2bfloat16_rn(x.w - __bfloat162float(h3)));
+    pk.x = *reinterpret_cast<uint32_t*>(&q0);
+    pk.y = *reinterpret_cast<uint32_t*>(&q1);
+    *reinterpret_cast<uint2*>(lo + o) = pk;
+  }
+}
 
 __global__ void __launch_bounds__(OPT_THREADS) sumsq_partial_kernel(const float* __restrict__ g,
                                                                     long long n, float* __restrict__ part) {
@@ -65,7 +84,7 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* __restrict__ p
                                                            float* __restrict__ m, float* __restrict__ v,
                                                            long long n, float lr_t, float b1, float b2,
                                                            float eps, float clip,
-                                                           const float* __restrict__ norm) {
+                                                           const float* __restrict__ norm, AdamShadows tab) {
   pdl_sync();
   const float nrm = norm[0];
   const float scale = clip > 0.f ? clip / fmaxf(nrm, clip) : 1.f;  // clip_by_global_norm
@@ -86,6 +105,10 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* __restrict__ p
     VQA_ADAM1(x) VQA_ADAM1(y) VQA_ADAM1(z) VQA_ADAM1(w)
 #undef VQA_ADAM1
     reinterpret_cast<float4*>(p)[i] = pp;
+    // the weight matrices' bf16 operand shadows are refreshed in the same pass (tensor starts are 64-element aligned,
+    // so a float4 never straddles two tensors)
+    for (int k = 0; k < tab.n; ++k)
+      if (i >= tab.begin4[k] && i < tab.end4[k]) shadow_store4(tab.hi[k], tab.lo[k], (i - tab.begin4[k]) * 4, pp);
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
   }
@@ -102,7 +125,7 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* __restrict__ p
 
 VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, long long n, float lr,
                            float beta1, float beta2, float eps, float clip_norm, long long t,
-                           float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s) {
+                           float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s, const AdamShadows* shadows) {
   if (n <= 0) return VQA_OK;
   if (!param || !grad || !m || !v || !scratch) return set_error(VQA_ERR_BAD_ARG, "vqa_adam_step: null argument");
   if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
@@ -119,8 +142,10 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
   VQA_LAUNCH_CHECK("norm_final");
   const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t)));
+  AdamShadows tab{};
+  if (shadows) tab = *shadows;
   launch_pdl(adam_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, param, grad, m, v, n, static_cast<float>(lr_t), beta1,
-             beta2, eps, clip_norm, scratch);
+             beta2, eps, clip_norm, scratch, tab);
   VQA_LAUNCH_CHECK("adam");
   return VQA_OK;
 }

@@ -466,10 +466,11 @@ class Engine:
             ps.adam_m = torch.zeros_like(ps.grad)
             ps.adam_v = torch.zeros_like(ps.grad)
         self.adam_t += 1
-        L.check(self.lib.vqa_adam_step(self.h, ps.flat.data_ptr(), ps.grad.data_ptr(), ps.adam_m.data_ptr(),
-                                       ps.adam_v.data_ptr(), ps.n_train, lr, beta1, beta2, eps, clip_norm,
-                                       self.adam_t, self.grad_norm.data_ptr(), self._stream()))
-        self.prepare_params(trainable_only=True)
+        # one pass: clip + Adam + the bf16 operand shadows of the updated weight matrices (+ the GRU repack)
+        L.check(self.lib.vqa_adam_step_shadowed(self.h, C.byref(self._p), ps.flat.data_ptr(), ps.grad.data_ptr(),
+                                                ps.adam_m.data_ptr(), ps.adam_v.data_ptr(), ps.n_train, lr, beta1,
+                                                beta2, eps, clip_norm, self.adam_t, self.grad_norm.data_ptr(),
+                                                self._stream()))
 
     def dropout_masks(self, seed, step, batch=None):
         Bn = self.batch_size if batch is None else batch

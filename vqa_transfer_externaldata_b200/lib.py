@@ -149,6 +149,8 @@ SYMBOLS = {
     "vqa_peek_activation": (C.c_int32, [_P, C.c_int32, C.POINTER(_P), C.POINTER(C.c_uint64)]),
     "vqa_adam_step": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float,
                                   C.c_float, C.c_float, C.c_int64, _P, _P]),
+    "vqa_adam_step_shadowed": (C.c_int32, [_P, C.POINTER(VqaParams), _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float,
+                                           C.c_float, C.c_float, C.c_float, C.c_int64, _P, _P]),
     "vqa_profile_enable": (C.c_int32, [_P, C.c_int32]),
     "vqa_profile_read": (C.c_int32, [_P, C.POINTER(C.c_float)]),
     "vqa_phase_name": (C.c_char_p, [C.c_int32]),
