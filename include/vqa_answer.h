@@ -248,6 +248,13 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* params, const VqaFea
                               const VqaBatch* batch, const VqaAnswerMasks* masks, uint64_t seed,
                               uint64_t step, const VqaOutputs* out, void* stream);
 
+/* Software pipelining across steps: register the NEXT batch (`batch->image_idx`, `batch->batch_size`; `stream` = the
+ * stream its image_idx upload was enqueued on). The feature gather depends on no parameter, so the next vqa_backward
+ * launches it into a second set of operand planes next to its weight-gradient GEMMs (an HBM-bound copy beside
+ * tensor-bound kernels), and the following vqa_forward with the same image_idx pointer and batch size adopts the
+ * planes instead of gathering. Optional: without it (or without a backward pass in between) vqa_forward gathers. */
+VQA_API VqaStatus vqa_prefetch_features(VqaHandle h, const VqaFeatureBank* bank, const VqaBatch* batch, void* stream);
+
 /* Backward of the same graph (tf.gradients inside optimize_loss, vqa/trainer.py:106-114) w.r.t. every
  * non-NULL field of `grads`, for the batch of the preceding vqa_forward on this handle.
  * loss_scale multiplies d(loss) (1/world_size under data parallelism, so that summed grads = mean). */

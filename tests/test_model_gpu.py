@@ -279,3 +279,36 @@ def test_backward_requires_forward():
     with pytest.raises(L.VqaError) as e:
         eng.backward()
     assert e.value.status == L.VQA_ERR_STATE
+
+
+def test_feature_prefetch_across_steps_is_bit_identical():
+    """vqa_prefetch_features gathers the next batch's features under the current backward; the step that adopts them
+    must produce exactly what a step that gathers for itself produces."""
+    from vqa_transfer_externaldata_b200 import synthetic as S
+    case = build_case(SMALL, variant="vlmap_answer", precision="bf16", seed=41)
+    eng, c = case["eng"], case["c"]
+    b0, b1 = case["batch"], S.make_batch(c, 24, seed=4242)
+
+    def two_steps(prefetch):
+        eng.prefetch_features = prefetch
+        eng.stage_batch(b0)
+        eng.forward(seed=9, step=1)
+        if prefetch:
+            eng.prefetch_batch(b1)
+        eng.backward()
+        eng.stage_batch(b1)
+        eng.forward(seed=9, step=2)
+        eng.backward()
+        torch.cuda.synchronize()
+        return (eng.outputs()["logit"].clone(), eng.outputs()["att_score"].clone(),
+                {f: g.clone() for f, g in eng.params.grad_views.items()})
+
+    l0, a0, g0 = two_steps(False)
+    l1, a1, g1 = two_steps(True)
+    assert torch.equal(l0, l1) and torch.equal(a0, a1)
+    # gradients: the scatter-add into the embedding uses fp32 atomics (order-dependent), everything else is bit-exact
+    for f in g0:
+        if f == "embed":
+            assert (g0[f] - g1[f]).abs().max().item() <= 1e-5 * g0[f].abs().max().item()
+        else:
+            assert torch.equal(g0[f], g1[f]), f

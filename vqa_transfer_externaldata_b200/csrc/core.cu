@@ -83,6 +83,8 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
 
   planes(b.v, B * K * Dv);
   b.nbox = a.take<int>(B);
+  planes(b.v_alt, B * K * Dv);
+  b.nbox_alt = a.take<int>(B);
   planes(b.e, T * B * Wp);
   b.z = two ? static_cast<void*>(a.take<float>(B * K * D)) : static_cast<void*>(a.take<bf16>(B * K * D));
   b.z_planes = Planes();
@@ -265,7 +267,14 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   }
   h->aux_created = true;
   h->early_grads = false;
-  if (cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess) {
+  h->prefetched = false;
+  h->prefetched_idx = nullptr;
+  h->prefetched_batch = 0;
+  h->pf_pending = false;
+  h->pf_joined = true;
+  if (cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return set_error(VQA_ERR_CUDA, "vqa_create: could not create the early-gradient event");
   }
@@ -280,7 +289,11 @@ VQA_API VqaStatus vqa_destroy(VqaHandle h) {
       cudaEventDestroy(h->ev[i][0]);
       cudaEventDestroy(h->ev[i][1]);
     }
-  if (h && h->aux_created) cudaEventDestroy(h->ev_early);
+  if (h && h->aux_created) {
+    cudaEventDestroy(h->ev_early);
+    cudaEventDestroy(h->ev_prefetch);
+    cudaEventDestroy(h->ev_upload);
+  }
   if (h && h->aux_created)
     for (int i = 0; i < VqaHandle_t::kAux; ++i) {
       cudaStreamDestroy(h->aux[i]);
@@ -316,6 +329,8 @@ VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes) 
   h->gemm_ctx.next_region = 0;
   h->params_ready = false;
   h->fwd_valid = false;
+  h->prefetched = false;
+  h->pf_pending = false;
   return VQA_OK;
 }
 

@@ -57,16 +57,19 @@ __global__ void gather_features_kernel(const float* __restrict__ bank, const int
                                        const long long* __restrict__ image_idx, int batch,
                                        long long per_image4, bf16* __restrict__ v_hi,
                                        bf16* __restrict__ v_lo, int* __restrict__ nbox) {
-  const int b = blockIdx.y;
   pdl_sync();
-  const long long img = image_idx[b];
-  if (blockIdx.x == 0 && threadIdx.x == 0) nbox[b] = num_boxes[img];
-  const float4* src = reinterpret_cast<const float4*>(bank) + img * per_image4;
-  const long long dst0 = static_cast<long long>(b) * per_image4 * 4;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_image4;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const float4 x = __ldg(src + i);
-    store_planes4(v_hi, v_lo, dst0 + i * 4, x);
+  // gridDim.y == batch for the in-step gather; the background prefetch runs a small grid that walks the samples
+  for (int b = blockIdx.y; b < batch; b += gridDim.y) {
+    const long long img = image_idx[b];
+    if (blockIdx.x == 0 && threadIdx.x == 0) nbox[b] = num_boxes[img];
+    const float4* src = reinterpret_cast<const float4*>(bank) + img * per_image4;
+    const long long dst0 = static_cast<long long>(b) * per_image4 * 4;
+#pragma unroll 4
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_image4;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const float4 x = __ldg(src + i);
+      store_planes4(v_hi, v_lo, dst0 + i * 4, x);
+    }
   }
 }
 
@@ -273,12 +276,28 @@ VqaStatus split_bf16_launch(const float* src, long long rows, long long cols, lo
 
 VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const long long* image_idx,
                                  int batch, int K, int Dv, bf16* v_hi, bf16* v_lo, int* nbox,
-                                 cudaStream_t s) {
+                                 cudaStream_t s, int max_ctas) {
   if (batch == 0) return VQA_OK;
   const long long per_image4 = static_cast<long long>(K) * Dv / 4;
   int gx = static_cast<int>((per_image4 + 255) / 256);
   if (gx > 8) gx = 8;
-  dim3 grid(gx, batch);
+  int gy = batch;
+  if (max_ctas > 0) {
+    // background prefetch under the cooperative BPTT kernel: max_ctas CTAs of 1024 threads that each claim a whole
+    // SM's shared memory, so they land on the SMs the recurrent grid leaves free and never share one with it
+    static bool attr_set = false;
+    constexpr int kExclusiveSmem = 200 * 1024;
+    if (!attr_set) {
+      VQA_CUDA_CHECK(cudaFuncSetAttribute(gather_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExclusiveSmem));
+      attr_set = true;
+    }
+    gy = max_ctas < batch ? max_ctas : batch;
+    gather_features_kernel<<<dim3(1, gy), 1024, kExclusiveSmem, s>>>(bank, num_boxes, image_idx, batch, per_image4, v_hi,
+                                                                     v_lo, nbox);
+    VQA_LAUNCH_CHECK("gather_features (background)");
+    return VQA_OK;
+  }
+  dim3 grid(gx, gy);
   launch_pdl(gather_features_kernel, dim3(grid), dim3(256), 0, s, bank, num_boxes, image_idx, batch, per_image4, v_hi,
                                               v_lo, nbox);
   VQA_LAUNCH_CHECK("gather_features");

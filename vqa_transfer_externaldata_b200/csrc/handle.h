@@ -18,6 +18,8 @@ struct Buffers {
   // inputs in operand form
   Planes v;        // [B*K, Dv] gathered features
   int* nbox;       // [B]
+  Planes v_alt;    // second set: vqa_prefetch_features gathers the NEXT batch here while this step's backward runs
+  int* nbox_alt;
   Planes e;        // [T*B, Wpad] embedded question tokens, time-major
   // v-projection
   void* z;         // [B*K, D] pre-LN projection: bf16 (PREC_BF16) / fp32 (PREC_FP32)
@@ -112,10 +114,22 @@ struct VqaHandle_t {
   VqaAnswerMasks last_masks;
   // auxiliary streams: independent branches of the graph (x-projections vs v-projection, the weight-gradient
   // GEMMs) are forked off the caller's stream and joined back with events -- capturable in a CUDA graph
-  static constexpr int kAux = 4;
+  static constexpr int kAux = 5;
   cudaStream_t aux[kAux];
   cudaEvent_t ev_fork[kAux], ev_join[kAux];
   bool aux_created;
+  // vqa_prefetch_features: the alternate feature planes hold the gather of (image_idx pointer, batch size)
+  bool prefetched;
+  const void* prefetched_idx;
+  int prefetched_batch;
+  cudaEvent_t ev_prefetch;
+  // a registered request that the next vqa_backward launches next to its weight-gradient GEMMs
+  bool pf_pending;
+  bool pf_joined;          // auxiliary stream 4 has been joined back into the caller's stream
+  VqaFeatureBank pf_bank;
+  const void* pf_idx;
+  int pf_batch;
+  cudaEvent_t ev_upload;   // image_idx of the next batch is on the device
   bool early_grads;        // vqa_set_early_gradients
   cudaEvent_t ev_early;    // recorded by vqa_backward once the non-GRU gradients are complete
   // optional per-phase timing

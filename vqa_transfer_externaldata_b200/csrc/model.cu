@@ -9,6 +9,8 @@
 // vqa/model_vlmap_answer.py:81-89 -- so those layers run dgrad only).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+#include <utility>
 #include <vector>
 
 #include "handle.h"
@@ -89,6 +91,26 @@ VqaStatus join_stream(VqaHandle h, int i, cudaStream_t s) {
 VqaStatus copy_out(void* dst, const void* src, size_t bytes, cudaStream_t s) {
   if (!dst || bytes == 0) return VQA_OK;
   VQA_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, s));
+  return VQA_OK;
+}
+
+// launch the registered feature prefetch on auxiliary stream 4 (already forked from the main stream by the caller): an
+// HBM-bound copy on the SMs the cooperative BPTT grid (128 CTAs, one per SM) does not use. Joined by the
+// weight-gradient section.
+VqaStatus launch_pending_prefetch(VqaHandle h, cudaStream_t a4) {
+  h->pf_pending = false;
+  const VqaConfig& c = h->cfg;
+  Buffers& b = h->buf;
+  int free_sms = h->num_sms - 128;   // the CTA-pair recurrent kernels occupy 128 SMs (gru_pair.cu)
+  if (free_sms < 4) free_sms = 4;
+  VQA_CUDA_CHECK(cudaStreamWaitEvent(a4, h->ev_upload, 0));
+  VQA_TRY(gather_features_launch(h->pf_bank.features, h->pf_bank.num_boxes, static_cast<const long long*>(h->pf_idx),
+                                 h->pf_batch, c.K, c.Dv, b.v_alt.hi, b.v_alt.lo, b.nbox_alt, a4, free_sms));
+  VQA_CUDA_CHECK(cudaEventRecord(h->ev_prefetch, a4));
+  h->prefetched = true;
+  h->prefetched_idx = h->pf_idx;
+  h->prefetched_batch = h->pf_batch;
+  h->pf_joined = false;
   return VQA_OK;
 }
 
@@ -204,9 +226,19 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
 
   PH_BEGIN(VQA_PH_GATHER);
   // a0: V = features[image_idx], nbox = num_boxes[image_idx]      (model_vlmap_answer.py:110-123)
-  VQA_TRY(gather_features_launch(bank->features, bank->num_boxes,
-                                 reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi,
-                                 b.v.lo, b.nbox, s));
+  if (h->prefetched && h->prefetched_idx == batch->image_idx && h->prefetched_batch == Bn) {
+    // vqa_prefetch_features already gathered this batch into the alternate planes (under the previous step's
+    // backward): adopt them
+    std::swap(b.v, b.v_alt);
+    std::swap(b.nbox, b.nbox_alt);
+    VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_prefetch, 0));
+  } else {
+    VQA_TRY(gather_features_launch(bank->features, bank->num_boxes,
+                                   reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi,
+                                   b.v.lo, b.nbox, s));
+  }
+  h->prefetched = false;
+  h->pf_pending = false;   // a request no backward pass picked up (inference loops): this forward gathered itself
   PH_END(VQA_PH_GATHER);
   PH_BEGIN(VQA_PH_VPROJ_FWD);
   // a1: Z = V Wv + bv (LayerNorm over (K, D) + ReLU are applied inside the attention kernels)
@@ -651,7 +683,13 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       a.dG_bf = b.dG.hi; a.dC_bf = b.dC.hi; a.bias_part = b.gru_bias_part;
       a.wg_h = b.w.gru_gates_w.hi + static_cast<long long>(W) * 2 * L;
       a.wc_h = b.w.gru_cand_w.hi + static_cast<long long>(W) * L;
+      // the next batch's feature gather goes to the SMs the recurrent grid leaves idle: fork BEFORE the launch (so the
+      // gather is ordered after the same prefix of this step), enqueue it AFTER (so the cooperative grid is first in line)
+      const bool pf = h->pf_pending && !(h->profile && !h->profile_overlapped) && gru_pair_supported(Bn, L, h->num_sms);
+      cudaStream_t a4 = s;
+      if (pf) VQA_TRY(fork_stream(h, 4, s, &a4));
       VQA_TRY(gru_bwd_persistent_launch(a, h->num_sms, s));
+      if (pf) VQA_TRY(launch_pending_prefetch(h, a4));
       (void)pp;
     } else {
       for (int t = T - 1; t >= 0; --t) {
@@ -747,6 +785,10 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       VQA_TRY(join_stream(h, 1, s));
       VQA_TRY(join_stream(h, 2, s));
       VQA_TRY(join_stream(h, 3, s));
+      if (h->prefetched && !h->pf_joined) {   // the background gather forked before the BPTT
+        VQA_TRY(join_stream(h, 4, s));
+        h->pf_joined = true;
+      }
       PH_END(VQA_PH_GRU_WGRAD);
     }
   } else {
@@ -772,6 +814,24 @@ VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch
     default:
       return set_error(VQA_ERR_BAD_ARG, "vqa_dropout_mask_site: unknown site %d", site);
   }
+}
+
+VQA_API VqaStatus vqa_prefetch_features(VqaHandle h, const VqaFeatureBank* bank, const VqaBatch* batch, void* stream) {
+  VQA_TRY(check_ready(h, "vqa_prefetch_features"));
+  if (!bank || !batch || !bank->features || !bank->num_boxes || !batch->image_idx)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_prefetch_features: null argument");
+  const VqaConfig& c = h->cfg;
+  if (batch->batch_size < 0 || batch->batch_size > c.B)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_prefetch_features: batch_size %d (max %d)", batch->batch_size, c.B);
+  // only registered here: the next vqa_backward launches the gather beside its cooperative BPTT kernel, on the SMs that
+  // grid leaves idle. Launched right away it takes SMs from the latency-bound head kernels and delays the cooperative
+  // grid; launched beside the weight-gradient GEMMs it slows those by as much as it saves (both measured).
+  VQA_CUDA_CHECK(cudaEventRecord(h->ev_upload, static_cast<cudaStream_t>(stream)));
+  h->pf_bank = *bank;
+  h->pf_idx = batch->image_idx;
+  h->pf_batch = batch->batch_size;
+  h->pf_pending = true;
+  return VQA_OK;
 }
 
 VQA_API VqaStatus vqa_reparam_noise(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step, float* noise,

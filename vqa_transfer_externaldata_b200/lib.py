@@ -143,6 +143,7 @@ SYMBOLS = {
     "vqa_forward": (C.c_int32, [_P, C.POINTER(VqaParams), C.POINTER(VqaFeatureBank), C.POINTER(VqaBatch),
                                 C.POINTER(VqaAnswerMasks), C.c_uint64, C.c_uint64, C.POINTER(VqaOutputs),
                                 _P]),
+    "vqa_prefetch_features": (C.c_int32, [_P, C.POINTER(VqaFeatureBank), C.POINTER(VqaBatch), _P]),
     "vqa_backward": (C.c_int32, [_P, C.POINTER(VqaParams), C.POINTER(VqaBatch), C.POINTER(VqaParams),
                                  C.c_float, _P]),
     "vqa_dropout_masks": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P, _P]),
