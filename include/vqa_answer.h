@@ -64,6 +64,11 @@ enum {
   /* vqa/model_vlmap_answer_adapt.py:132-142: attention pools v_adapt = relu(LN(FC(V))) [K, D] (trained) instead of
    * the raw features, so the pooled vector is D-wide and pooled_linear_l/fc/weights is [D, L] */
   VQA_VARIANT_VLMAP_ANSWER_ADAPT = 8,
+  /* vqa/model_vlmap_answer_ent.py:14-16,193-213,284-294: the base model plus a maximum-entropy regulariser: the joint
+   * head is evaluated on num_marginal tiles per sample (pooled_linear_l rows of OTHER samples, stop_gradient, times
+   * this sample's q_linear_l; LayerNorm over the whole [num_marginal, J] slab; dropout 0.5), softmax over the train &
+   * existing answers, mean over the tiles = marginal; loss += 0.1 * mean_b sum_a marg log(marg + 1e-8) */
+  VQA_VARIANT_VLMAP_ANSWER_ENT = 9,
   VQA_NUM_VARIANTS
 };
 
@@ -89,6 +94,7 @@ typedef struct VqaConfig {
   int32_t precision;        /* VQA_PREC_*                                                     */
   float keep_att;           /* attention-feature dropout keep prob (0.8), vlmap/modules.py:82 */
   float keep_joint;         /* joint dropout keep prob (0.5), vqa/model_vlmap_answer.py:180   */
+  int32_t num_marginal;     /* NUM_MARGINAL of the ent variant (200, model_vlmap_answer_ent.py:16); 0 = 200 */
 } VqaConfig;
 
 /*
@@ -194,6 +200,9 @@ enum {
   /* vqa/model_vlmap_answer_full.py:221-223 (0 for every other variant) */
   VQA_REPORT_LATENT_LOSS,
   VQA_REPORT_TRAIN_LATENT_LOSS,
+  /* vqa/model_vlmap_answer_ent.py:292-294 (0 for every other variant) */
+  VQA_REPORT_ENTROPY,
+  VQA_REPORT_WEIGHTED_ENTROPY,
   VQA_NUM_REPORT
 };
 
@@ -264,7 +273,8 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* params, const VqaBa
 /* Materialise the dropout masks vqa_forward(seed, step) uses, as 0/1 bytes: att [batch, K, D],
  * joint [batch, J]. Test / parity helper (the kernels regenerate the same bits on the fly). */
 /* One dropout site's keep mask (0 / 1 bytes) for (seed, step): site 1 = attention features [batch, K, D],
- * 2 = joint (joint_v in noc) [batch, J], 3 = joint_l of the noc variants [batch, J]. */
+ * 2 = joint (joint_v in noc) [batch, J], 3 = joint_l of the noc variants [batch, J], 5 = the tiled joint of the ent
+ * variant [batch, num_marginal, J]. */
 VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch, uint64_t seed, uint64_t step,
                                         uint8_t* mask, void* stream);
 

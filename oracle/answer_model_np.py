@@ -24,6 +24,8 @@ Reference files followed (paths under /root/reference):
   vqa/model_vlmap_answer_vqa_all2.py:188-243  same without the fill; BCE(tuned) unmasked; pred from
                                       logit * test_mask + tuned * train_mask                       ('vlmap_answer_vqa_all2')
   vqa/model_vlmap_answer_adapt.py:132-142     v_adapt = relu(LN(FC(V))) is what attention pools     ('vlmap_answer_adapt')
+  vqa/model_vlmap_answer_ent.py:14-16,193-213,284-294  NUM_MARGINAL-way tiled joint head, marginal softmax over the
+                                      train & existing answers, loss += 0.1 * negative entropy          ('vlmap_answer_ent')
   vlmap/modules.py:630-650            fc_layer = fully_connected -> layer_norm -> activation
   vlmap/modules.py:67-97              hadamard_attention
   vlmap/modules.py:23-39              attention_pooling
@@ -78,6 +80,8 @@ EXTRA_TF_NAMES = {
     "va_gamma": "v_adapt/LayerNorm/gamma", "va_beta": "v_adapt/LayerNorm/beta",
 }
 LATENT_LOSS_WEIGHT = 0.1   # model_vlmap_answer_full.py:33
+W_ENTROPY = 0.1            # model_vlmap_answer_ent.py:14
+NUM_MARGINAL = 200         # model_vlmap_answer_ent.py:16
 
 
 def param_fields(variant):
@@ -312,7 +316,8 @@ GEMM_WEIGHTS = ("v_w", "gru_gates_w", "gru_cand_w", "qv_w", "pl_w", "ql_w", "joi
 
 
 def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0.8, keep_joint=0.5,
-            att_mask=None, joint_mask=None, operand_round=None, joint_l_mask=None, noise=None):
+            att_mask=None, joint_mask=None, operand_round=None, joint_l_mask=None, noise=None,
+            num_marginal=NUM_MARGINAL, ent_mask=None, ent_tile=None):
     """Model.build() forward. p: dict field -> fp64 array (TF layout [in,out]).
     features [N,K,Dv], num_boxes [N]; batch: image_idx [B], q_intseq [B,T], q_intseq_len [B],
     answer_target [B,A]; att_mask [B,K,D] / joint_mask [B,J] are the 0/1 keep masks tf.nn.dropout
@@ -420,6 +425,29 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
     else:
         train_loss, report, ps, pred = metrics(logit, target, m, use_train_mask=use_tm)
     total_loss = train_loss
+    ent_cache = None
+    if variant == "vlmap_answer_ent":           # model_vlmap_answer_ent.py:193-213, 284-294
+        M = int(num_marginal)
+        # tf.reshape(tf.tile(stop_gradient(Hp), [M, 1]), [-1, M, L]): entry [b, m] is row (b*M + m) mod B of Hp
+        tidx = (np.arange(B)[:, None] * M + np.arange(M)[None, :]) % B
+        # tf.stop_gradient: the tile is a constant of the gradient. ent_tile lets the finite-difference check hold it at
+        # its unperturbed value, which is what "no gradient through this path" means for a difference quotient.
+        TP = Hp[tidx] if ent_tile is None else f64(ent_tile)              # [B, M, L], no gradient
+        X2 = TP * Hl[:, None, :]
+        Jn2, j2_cache = fc_ln_relu_fwd(X2, p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"], q=q, qz=q)
+        jm2 = np.ones_like(Jn2) if ent_mask is None else f64(ent_mask)    # LN over (M, J): SURVEY Q1
+        Jd2 = q(Jn2 * jm2 / keep_joint)
+        logit2 = Jd2 @ p["ans_w"] + p["ans_b"]                            # [B, M, A]
+        sel = (m["exist"] * m["train"]) > 0.5                             # train_exist_answer_mask_bool
+        ml = logit2[:, :, sel]
+        e2 = np.exp(ml - ml.max(axis=-1, keepdims=True))
+        prob = e2 / e2.sum(axis=-1, keepdims=True)
+        marg = prob.mean(axis=1)                                          # [B, #selected]
+        neg_ent = (marg * np.log(marg + 1e-8)).sum(axis=-1).mean()
+        report["entropy"] = neg_ent
+        report["weighted_entropy"] = W_ENTROPY * neg_ent
+        total_loss = train_loss + W_ENTROPY * neg_ent
+        ent_cache = dict(TP=TP, j2_cache=j2_cache, jm2=jm2, Jd2=Jd2, sel=sel, prob=prob, marg=marg, M=M)
     if variant == "vlmap_answer_full":          # _full.py:217-223, 272-276
         _, mean, (lss, _, _) = qp_cache
         latent = -0.5 * (1.0 + lss - mean ** 2 - np.exp(lss)).sum(axis=1).mean()
@@ -433,7 +461,7 @@ def forward(p, features, num_boxes, batch, m, variant="vlmap_answer", keep_att=0
                  Hp=Hp, l_cache=l_cache, Hl=Hl, X=X, j_cache=j_cache, jm=jm, Jd=Jd, logit=logit,
                  keep_att=keep_att, keep_joint=keep_joint, use_tm=use_tm, m=m, W=W, p=p, variant=variant,
                  qp_cache=qp_cache, jl_cache=jl_cache, jlm=jlm, Jld=Jld, noc=noc, tuned_cache=tuned_cache,
-                 va_cache=va_cache, Vp=Vp)
+                 va_cache=va_cache, Vp=Vp, ent_cache=ent_cache)
     return out, cache
 
 
@@ -476,6 +504,26 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
         dJn, p["joint_w"], p["joint_gamma"], c["j_cache"], flip=gf.get("joint"), gate=go.get("joint"))
     if not c.get("noc"):
         dHp, dHl = dX * c["Hl"], dX * c["Hp"]
+        if c.get("ent_cache") is not None:
+            # d(0.1 * mean_b sum_a marg log(marg + 1e-8)) back through the marginal softmax, the tiled head and the
+            # broadcast Hl; the tiled Hp carries tf.stop_gradient
+            ec = c["ent_cache"]
+            marg, prob, M = ec["marg"], ec["prob"], ec["M"]
+            dmarg = W_ENTROPY * loss_scale / B * (np.log(marg + 1e-8) + marg / (marg + 1e-8))
+            dprob = np.broadcast_to(dmarg[:, None, :] / M, prob.shape)
+            dml = prob * (dprob - (prob * dprob).sum(axis=-1, keepdims=True))
+            dl2 = np.zeros(prob.shape[:2] + (A,))
+            dl2[:, :, ec["sel"]] = dml
+            g["ans_w"] = g["ans_w"] + ec["Jd2"].reshape(-1, ec["Jd2"].shape[-1]).T @ dl2.reshape(-1, A)
+            g["ans_b"] = g["ans_b"] + dl2.sum(axis=(0, 1))
+            dJn2 = (dl2 @ p["ans_w"].T) * ec["jm2"] / c["keep_joint"]
+            dX2, gw, gb, gg, gbt = fc_ln_relu_bwd(dJn2, p["joint_w"], p["joint_gamma"], ec["j2_cache"],
+                                                  flip=gf.get("joint2"), gate=go.get("joint2"))
+            g["joint_w"] = g["joint_w"] + gw
+            g["joint_b"] = g["joint_b"] + gb
+            g["joint_gamma"] = g["joint_gamma"] + gg
+            g["joint_beta"] = g["joint_beta"] + gbt
+            dHl = dHl + (dX2 * ec["TP"]).sum(axis=1)
     else:
         dHp = dX
         g["al_w"] = c["Jld"].T @ dx

@@ -44,7 +44,8 @@ def gru_encode(E, q_len, Wg, bg, Wc, bc):
 
 
 def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", keep_att=0.8,
-            keep_joint=0.5, att_mask=None, joint_mask=None, joint_l_mask=None, noise=None, exist=None):
+            keep_joint=0.5, att_mask=None, joint_mask=None, joint_l_mask=None, noise=None, exist=None,
+            num_marginal=200, ent_mask=None):
     """p: dict field -> torch tensor (requires_grad where wanted). Returns dict with loss, logit,
     att_score, pooled, condition, pred."""
     idx = batch["image_idx"].long()
@@ -116,6 +117,17 @@ def forward(p, features, num_boxes, batch, train_mask, variant="vlmap_answer", k
         bce = BCE(logit)
         bce_train = bce * train_mask if variant != "standard" else bce
     loss = bce_train.sum(-1).mean()
+    if variant == "vlmap_answer_ent":         # vqa/model_vlmap_answer_ent.py:193-213, 284-294
+        M = num_marginal
+        tile = Hp.detach().repeat(M, 1).reshape(-1, M, Hp.shape[1])       # tf.tile + tf.reshape, stop_gradient
+        tj = fc_layer(tile * Hl.unsqueeze(1), p["joint_w"], p["joint_b"], p["joint_gamma"], p["joint_beta"])
+        if ent_mask is not None:
+            tj = tj * ent_mask
+        tl = (tj / keep_joint) @ p["ans_w"] + p["ans_b"]
+        sel = (exist * train_mask) > 0.5
+        prob = torch.softmax(tl[:, :, sel], dim=-1)
+        marg = prob.mean(dim=1)
+        loss = loss + 0.1 * (marg * torch.log(marg + 1e-8)).sum(-1).mean()
     if variant == "vlmap_answer_full":        # latent_loss, weight 0.1 (:33, 217-223, 272-276)
         latent = -0.5 * (1 + q_lss - q_mean.pow(2) - torch.exp(q_lss)).sum(-1).mean()
         loss = loss + 0.1 * latent

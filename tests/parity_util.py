@@ -47,9 +47,10 @@ def relu_tie_budget(cache, inter, ref_g, fields, tau, loss_scale=1.0, max_ties=9
 
 
 def build_case(dims, variant="vlmap_answer", precision="fp32", seed=0, num_images=24, ragged=True,
-               batch=None, T=None, perturb=0.2, keep_att=0.8, keep_joint=0.5):
+               batch=None, T=None, perturb=0.2, keep_att=0.8, keep_joint=0.5, num_marginal=5):
     c = S.dims(**dims)
-    cfg = AnswerModelConfig(variant=variant, precision=precision, keep_att=keep_att, keep_joint=keep_joint, **c)
+    cfg = AnswerModelConfig(variant=variant, precision=precision, keep_att=keep_att, keep_joint=keep_joint,
+                            num_marginal=num_marginal, **c)
     params, exist = S.init_params(c, seed=seed, variant=variant, perturb=perturb)
     feats, nb = S.make_bank(c, num_images=num_images, seed=seed + 2, ragged_boxes=ragged)
     bt = S.make_batch(c, num_images, seed=seed + 3, batch=batch, T=T)
@@ -79,6 +80,10 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
         jl_kw = {"joint_l_mask": jl_mask.cpu().numpy()}
     if cfg.variant == "vlmap_answer_full":   # the reparameterisation noise the device drew for (seed, step)
         jl_kw = {"noise": eng.reparam_noise(seed, step).cpu().numpy()}
+    if cfg.variant == "vlmap_answer_ent":    # the tiled joint's own dropout mask
+        from vqa_transfer_externaldata_b200 import lib as L_
+        jl_kw = {"num_marginal": cfg.num_marginal,
+                 "ent_mask": eng.dropout_mask_site(L_.SITE_ENT, seed, step).cpu().numpy()}
     torch.cuda.synchronize()
     loss, report = eng.read_scalars()
     got = {"loss": loss, "report": report}

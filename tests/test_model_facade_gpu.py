@@ -25,6 +25,7 @@ OUTPUT_KEYS = {"att_score", "logit", "pred", "all_score", "max_train_score", "te
 @pytest.mark.parametrize("model_type", importer.get_model_types())
 def test_train_step_through_the_plugin_interface(model_type):
     config, feats, batch, _ = make_synthetic_config(SMALL, variant=model_type, precision="bf16", seed=5, num_images=16)
+    config.num_marginal = 6
     cls = importer.get_model_class(model_type)
     model = cls(batch, config, is_train=True, image_features=feats)
     before = {k: v.copy() for k, v in model.state_dict().items()}
@@ -35,6 +36,9 @@ def test_train_step_through_the_plugin_interface(model_type):
         want = want | {"latent_loss", "train_latent_loss", "latent_loss_weight"}
         assert abs(model.losses["answer"] + model.losses["latent"] - loss) < 1e-4 * max(1.0, abs(loss))
         assert abs(model.report["train_latent_loss"] - 0.1 * model.report["latent_loss"]) < 1e-6
+    if model_type == "vlmap_answer_ent":       # model_vlmap_answer_ent.py:290-294
+        want = want | {"entropy", "weighted_entropy"}
+        assert abs(model.losses["answer"] + model.losses["entropy"] - loss) < 1e-4 * max(1.0, abs(loss))
     assert set(model.report) == want
     assert OUTPUT_KEYS <= set(model.output)
     assert model.output["logit"].shape == (SMALL["B"], SMALL["A"])

@@ -155,7 +155,7 @@ def test_gru_pair_kernels_match_single_cta_kernels_at_full_size():
 
 # ---- family variants: one more layer between the GRU state and q_linear_l ----
 VARIANTS = ["vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc", "vlmap_answer_full", "vlmap_answer_vqa_all",
-            "vlmap_answer_vqa_all2", "vlmap_answer_adapt"]
+            "vlmap_answer_vqa_all2", "vlmap_answer_adapt", "vlmap_answer_ent"]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)

@@ -33,13 +33,17 @@ def _setup(variant="vlmap_answer", seed=0, perturb=0.3, dims=TINY):
 
 
 VARIANTS = ["vlmap_answer", "standard", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc",
-            "vlmap_answer_full", "vlmap_answer_vqa_all", "vlmap_answer_vqa_all2", "vlmap_answer_adapt"]
+            "vlmap_answer_full", "vlmap_answer_vqa_all", "vlmap_answer_vqa_all2", "vlmap_answer_adapt",
+            "vlmap_answer_ent"]
 
 
 def _extra_kw(variant, c, seed=3):
     """the N(0,1) draw of the 'full' variant's reparameterisation"""
     if variant == "vlmap_answer_full":
         return {"noise": np.random.default_rng(seed).standard_normal((c["B"], c["L"]))}
+    if variant == "vlmap_answer_ent":   # 4-way marginal (B = 3 is not a divisor of 4: exercises the tile/reshape wrap)
+        return {"num_marginal": 4,
+                "ent_mask": (np.random.default_rng(seed).uniform(size=(c["B"], 4, c["J"])) < 0.5).astype(np.float64)}
     return {}
 
 
@@ -49,6 +53,8 @@ def test_backward_matches_finite_differences(variant):
     kw = _extra_kw(variant, c)
     out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm, **kw)
     g = O.backward(cache)
+    if variant == "vlmap_answer_ent":   # tf.stop_gradient on the tiled pooled_linear_l: a constant for the quotient too
+        kw["ent_tile"] = cache["ent_cache"]["TP"]
     rng = np.random.default_rng(5)
     eps = 1e-6
     for name in O.param_fields(variant):
@@ -74,11 +80,13 @@ def test_numpy_oracle_matches_torch_twin(variant):
     kw = _extra_kw(variant, c)
     out, cache = O.forward(p, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm, **kw)
     g = O.backward(cache)
+    kw.pop("ent_tile", None)
     tp = {k: torch.tensor(v, dtype=torch.float64, requires_grad=True) for k, v in p.items()}
     tb = {k: torch.tensor(v) for k, v in batch.items()}
     tout = OT.forward(tp, torch.tensor(feats), torch.tensor(nb), tb, torch.tensor(m["train"]),
                       variant=variant, att_mask=torch.tensor(am), joint_mask=torch.tensor(jm),
-                      exist=torch.tensor(m["exist"]), **{k: torch.tensor(v) for k, v in kw.items()})
+                      exist=torch.tensor(m["exist"]),
+                      **{k: (torch.tensor(v) if isinstance(v, np.ndarray) else v) for k, v in kw.items()})
     tout["loss"].backward()
     assert abs(tout["loss"].item() - out["loss"]) < 1e-12
     np.testing.assert_allclose(tout["logit"].detach().numpy(), out["logit"], rtol=1e-10, atol=1e-12)

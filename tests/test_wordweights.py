@@ -46,7 +46,7 @@ def test_tf_names_and_frozen_sets():
 def test_importer_names():
     assert importer.get_model_types() == ["vlmap_answer", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc",
                                           "vlmap_answer_nocarch", "vlmap_answer_full", "vlmap_answer_vqa_all",
-                                          "vlmap_answer_vqa_all2", "vlmap_answer_adapt", "standard"]
+                                          "vlmap_answer_vqa_all2", "vlmap_answer_adapt", "vlmap_answer_ent", "standard"]
     assert importer.get_model_class("vlmap_answer_vqa_all2").MODEL_TYPE == "vlmap_answer_vqa_all2"
     assert importer.get_model_class("vlmap_answer_full").OLD_REPORT and importer.get_model_class("vlmap_answer_adapt").OLD_REPORT
     assert issubclass(importer.get_model_class("vlmap_answer_nocarch"), importer.get_model_class("vlmap_answer_noc"))
@@ -56,5 +56,6 @@ def test_importer_names():
     import pytest
     with pytest.raises(ValueError):
         importer.get_model_class("nope")
+    assert importer.get_model_class("vlmap_answer_ent").MODEL_TYPE == "vlmap_answer_ent"
     with pytest.raises(NotImplementedError):
-        importer.get_model_class("vlmap_answer_ent")
+        importer.get_model_class("vlmap_only")

@@ -130,6 +130,23 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   b.pred_logit = a.take<float>(v_tuned ? B * A : 0);
   b.dtuned_f32 = a.take<float>(v_tuned ? B * A : 0);
   planes(b.dtuned, v_tuned ? B * A : 0);
+  const bool v_ent = c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT;
+  const uint64_t BM = v_ent ? B * static_cast<uint64_t>(h->M) : 0;
+  planes(b.x2, BM * L);
+  b.z2 = two ? static_cast<void*>(a.take<float>(BM * J)) : static_cast<void*>(a.take<bf16>(BM * J));
+  b.ln2_mean = a.take<float>(v_ent ? B : 0);
+  b.ln2_rstd = a.take<float>(v_ent ? B : 0);
+  planes(b.jd2, BM * J);
+  b.logit2 = a.take<float>(BM * A);
+  b.row_max = a.take<float>(BM);
+  b.row_inv = a.take<float>(BM);
+  b.marg = a.take<float>(v_ent ? B * A : 0);
+  b.ent_rows = a.take<float>(v_ent ? B : 0);
+  planes(b.dl2, BM * A);
+  b.dJ2 = a.take<float>(BM * J);
+  planes(b.dz2, BM * J);
+  b.dX2 = a.take<float>(BM * L);
+  b.dhl_ent = a.take<float>(v_ent ? B * L : 0);
   const uint64_t nza = v_adapt ? B * K * D : 0;
   b.za = two ? static_cast<void*>(a.take<float>(nza)) : static_cast<void*>(a.take<bf16>(nza));
   planes(b.va, nza);
@@ -225,6 +242,10 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: unknown precision %d", c.precision);
   if (!(c.keep_att > 0.f && c.keep_att <= 1.f) || !(c.keep_joint > 0.f && c.keep_joint <= 1.f))
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: keep probabilities must be in (0, 1]");
+  if (c.num_marginal < 0 || c.num_marginal > 4096)
+    return set_error(VQA_ERR_BAD_ARG, "vqa_create: num_marginal out of range");
+  if (c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT && c.A > 4096)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_create: the ent variant supports A <= 4096");
   if (c.num_train_answer < 0 || c.num_train_answer > c.A)
     return set_error(VQA_ERR_BAD_ARG, "vqa_create: num_train_answer out of range");
 
@@ -248,6 +269,7 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   h->num_sms = prop.multiProcessorCount;
   h->Wpad = (c.W + 7) & ~7;
   h->planes = c.precision == VQA_PREC_FP32 ? 2 : 1;
+  h->M = c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT ? (c.num_marginal > 0 ? c.num_marginal : 200) : 0;
   h->ws = nullptr;
   h->ws_bytes = 0;
   h->params_ready = false;

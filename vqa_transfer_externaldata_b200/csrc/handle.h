@@ -51,6 +51,10 @@ struct Buffers {
   // adapt: pre-LN v_adapt projection (bf16 / fp32 like z), v_adapt as the pooling operand, LN stats, gradient planes,
   // per-sample partials [B, 3, D]
   void* za; Planes va; float* lnva_mean; float* lnva_rstd; Planes dza; float* va_part;
+  // ent (M = num_marginal): tiled joint input, its pre-LN projection (bf16 / fp32 like z), LN stats, dropped-out
+  // output, tile logits, softmax row statistics, marginal, per-sample negative entropies, and the backward tensors
+  Planes x2; void* z2; float* ln2_mean; float* ln2_rstd; Planes jd2; float* logit2; float* row_max; float* row_inv;
+  float* marg; float* ent_rows; Planes dl2; float* dJ2; Planes dz2; float* dX2; float* dhl_ent;
   float* att;      // [B, K]
   float* pooled;   // [B, Dv]  ([B, D] in the adapt variant)
   Planes pooled_op;
@@ -100,6 +104,7 @@ struct VqaHandle_t {
   int num_sms;
   int Wpad;             // W rounded up to 8 (TMA pitch must be a multiple of 16 bytes)
   int planes;           // 1 (bf16) or 2 (fp32 = hi + lo)
+  int M;                // num_marginal of the ent variant (0 otherwise)
   void* ws;
   uint64_t ws_bytes;
   uint64_t ws_needed;

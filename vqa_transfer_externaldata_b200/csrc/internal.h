@@ -238,8 +238,39 @@ struct ReparamFwd {
   float* kl_rows;                         // [batch] sum_l (1 + lss - mean^2 - exp(lss))
 };
 VqaStatus reparam_fwd_launch(const ReparamFwd& a, cudaStream_t s);
-VqaStatus latent_finalize_launch(const float* kl_rows, int batch, float weight, float* loss, float* report,
-                                 cudaStream_t s);
+// loss[0] += weight * (scale * mean_b rows); report[slot] = scale * mean_b rows, report[slot + 1] = weight * that
+VqaStatus latent_finalize_launch(const float* rows, int batch, float scale, float weight, int slot, float* loss,
+                                 float* report, cudaStream_t s);
+
+// ent variant (vqa/model_vlmap_answer_ent.py:193-213, 284-294)
+struct EntTile {
+  int batch, M, L;
+  const float* hp; const float* hl;   // [batch, L] pooled_linear_l (no gradient through the tile), q_linear_l
+  bf16* out_hi; bf16* out_lo;         // [batch * M, L]
+};
+VqaStatus ent_tile_launch(const EntTile& a, cudaStream_t s);
+struct EntMarginal {
+  int batch, M, A, num_train_answer;
+  const float* logit2;                // [batch * M, A]
+  const float* exist;                 // [A]
+  float* marg;                        // [batch, A] marginal probabilities (0 at unselected answers)
+  float* row_max; float* row_inv;     // [batch * M] softmax statistics kept for the backward
+  float* ent_rows;                    // [batch] sum_a marg log(marg + 1e-8)
+};
+VqaStatus ent_marginal_launch(const EntMarginal& a, cudaStream_t s);
+struct EntMarginalBwd {
+  int batch, M, A, num_train_answer;
+  const float* logit2; const float* exist; const float* marg; const float* row_max; const float* row_inv;
+  float scale;                        // W_ENTROPY * loss_scale / batch
+  bf16* d_hi; bf16* d_lo;             // [batch * M, A] d logit2 as GEMM operand planes
+};
+VqaStatus ent_marginal_bwd_launch(const EntMarginalBwd& a, cudaStream_t s);
+struct EntDhl {
+  int batch, M, L;
+  const float* dX; const float* dX2; const float* hp;
+  float* out;                         // [batch, L] gradient w.r.t. q_linear_l's output
+};
+VqaStatus ent_dhl_launch(const EntDhl& a, cudaStream_t s);
 struct ReparamBwd {
   int batch, L;
   const float* d_out; const float* mean; const float* lss;
@@ -258,6 +289,8 @@ struct SlabLnFwd {
   const float* gamma; const float* beta;  // [D]
   bf16* out_hi; bf16* out_lo;             // relu(LN_{K,D}(z)) as operand planes
   float* mean; float* rstd;               // [batch]
+  // optional dropout on the output (set thr = 65536 for none): the tiled joint of the ent variant
+  unsigned int thr; float inv_keep; unsigned long long seed, step; unsigned int site;
 };
 VqaStatus slab_ln_relu_fwd_launch(const SlabLnFwd& a, int precision, cudaStream_t s);
 struct SlabLnBwd {
@@ -266,7 +299,10 @@ struct SlabLnBwd {
   const float* att;                       // [batch, K]
   const float* d_pooled;                  // [batch, D]
   bf16* dz_hi; bf16* dz_lo;               // [batch, K, D]
-  float* part;                            // [batch, 3, D] per-sample partials: d gamma | d beta | d bias
+  float* part;                            // [batch, 3, D] per-sample partials: d gamma | d beta | d bias (NULL: none)
+  // ent: the upstream gradient is a tensor [batch, K, D] that passed through dropout (att / d_pooled unused then)
+  const float* dout;
+  unsigned int thr; float inv_keep; unsigned long long seed, step; unsigned int site;
 };
 VqaStatus slab_ln_relu_bwd_launch(const SlabLnBwd& a, int precision, cudaStream_t s);
 
@@ -287,6 +323,7 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
 #define VQA_LATENT_LOSS_WEIGHT 0.1f
 
 // RNG stream ids (which dropout site a Philox draw belongs to)
-enum { RNG_STREAM_ATT = 1, RNG_STREAM_JOINT = 2, RNG_STREAM_JOINT_L = 3, RNG_STREAM_NOISE = 4 };
+enum { RNG_STREAM_ATT = 1, RNG_STREAM_JOINT = 2, RNG_STREAM_JOINT_L = 3, RNG_STREAM_NOISE = 4, RNG_STREAM_ENT = 5 };
+#define VQA_W_ENTROPY 0.1f        /* vqa/model_vlmap_answer_ent.py:14 */
 
 }  // namespace vqa

@@ -253,6 +253,8 @@ __global__ void __launch_bounds__(256) report_finalize_kernel(const float* __res
       report[VQA_REPORT_TEST_MAX_EXIST_ACC] = m[S_TEST_MAX_EXIST];
       report[VQA_REPORT_LATENT_LOSS] = 0.f;          // the 'full' variant overwrites these (latent_finalize_kernel)
       report[VQA_REPORT_TRAIN_LATENT_LOSS] = 0.f;
+      report[VQA_REPORT_ENTROPY] = 0.f;              // the 'ent' variant overwrites these
+      report[VQA_REPORT_WEIGHTED_ENTROPY] = 0.f;
     }
   }
 }

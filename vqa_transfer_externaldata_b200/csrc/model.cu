@@ -15,6 +15,7 @@
 
 #include "handle.h"
 #include "internal.h"
+#include "philox.cuh"
 
 using namespace vqa;
 
@@ -261,6 +262,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     SlabLnFwd f{};
     f.batch = Bn; f.K = K; f.D = D; f.z = b.za; f.gamma = p->va_gamma; f.beta = p->va_beta;
     f.out_hi = b.va.hi; f.out_lo = b.va.lo; f.mean = b.lnva_mean; f.rstd = b.lnva_rstd;
+    f.thr = 65536u; f.inv_keep = 1.f;   // no dropout on v_adapt
     VQA_TRY(slab_ln_relu_fwd_launch(f, c.precision, s));
   }
   PH_END(VQA_PH_VPROJ_FWD);
@@ -402,6 +404,31 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(tuned_combine_launch(t, s));
     out_logit = b.logit_total;
   }
+  const bool v_ent = c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT;
+  if (v_ent) {
+    // maximum-entropy regulariser (model_vlmap_answer_ent.py:193-213): the joint head on M tiles per sample
+    const int M = h->M, BM = Bn * M;
+    EntTile t{};
+    t.batch = Bn; t.M = M; t.L = L; t.hp = b.hp; t.hl = b.hl; t.out_hi = b.x2.hi; t.out_lo = b.x2.lo;
+    VQA_TRY(ent_tile_launch(t, s));
+    {
+      GemmB g(BM, J, L);
+      g.a(b.x2, 0, L, false).b(b.w.joint_w, 0, J, true).bias(p->joint_b);
+      if (fp32) g.f32(static_cast<float*>(b.z2), J);
+      else { Planes zp; zp.hi = static_cast<bf16*>(b.z2); g.planes(zp, 0, J); }
+      VQA_TRY(g.run(h, s));
+    }
+    SlabLnFwd f{};   // LayerNorm over the whole [M, J] slab, ReLU, dropout 0.5
+    f.batch = Bn; f.K = M; f.D = J; f.z = b.z2; f.gamma = p->joint_gamma; f.beta = p->joint_beta;
+    f.out_hi = b.jd2.hi; f.out_lo = b.jd2.lo; f.mean = b.ln2_mean; f.rstd = b.ln2_rstd;
+    f.thr = keep_threshold(c.keep_joint); f.inv_keep = 1.f / c.keep_joint; f.seed = seed; f.step = step; f.site = RNG_STREAM_ENT;
+    VQA_TRY(slab_ln_relu_fwd_launch(f, c.precision, s));
+    VQA_TRY(GemmB(BM, A, J).a(b.jd2, 0, J, false).b(b.w.ans_w, 0, A, true).bias(p->ans_b).f32(b.logit2, A).run(h, s));
+    EntMarginal e{};
+    e.batch = Bn; e.M = M; e.A = A; e.num_train_answer = c.num_train_answer; e.logit2 = b.logit2;
+    e.exist = masks->answer_exist; e.marg = b.marg; e.row_max = b.row_max; e.row_inv = b.row_inv; e.ent_rows = b.ent_rows;
+    VQA_TRY(ent_marginal_launch(e, s));
+  }
   PH_END(VQA_PH_HEAD_FWD);
   PH_BEGIN(VQA_PH_LOSS);
   // a8 + a9: loss, pred, report                                       (:192-288)
@@ -419,7 +446,9 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
                                b.loss, b.report, b.pred, b.per_sample, nullptr, nullptr, nullptr, b.scratch, s));
   }
   if (v_full)   // loss += 0.1 * KL(q_L_mean, q_L_log_sigma_sq); report latent_loss / train_latent_loss  (_full.py:217-223)
-    VQA_TRY(latent_finalize_launch(b.kl_rows, Bn, VQA_LATENT_LOSS_WEIGHT, b.loss, b.report, s));
+    VQA_TRY(latent_finalize_launch(b.kl_rows, Bn, -0.5f, VQA_LATENT_LOSS_WEIGHT, VQA_REPORT_LATENT_LOSS, b.loss, b.report, s));
+  if (v_ent)    // loss += 0.1 * negative entropy of the marginal; report entropy / weighted_entropy     (_ent.py:284-294)
+    VQA_TRY(latent_finalize_launch(b.ent_rows, Bn, 1.0f, VQA_W_ENTROPY, VQA_REPORT_ENTROPY, b.loss, b.report, s));
   PH_END(VQA_PH_LOSS);
   if (out) {
     VQA_TRY(copy_out(out->loss, b.loss, sizeof(float), s));
@@ -533,9 +562,31 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->pl_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->pl_gamma, b.scratch, s));
     if (g->pl_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->pl_beta, b.scratch, s));
   }
+  const bool v_ent = c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT;
+  if (v_ent) {
+    // regulariser backward: d marginal -> d tile logits -> tiled joint head (frozen: data gradients only) -> dHl
+    const int M = h->M, BM = Bn * M;
+    EntMarginalBwd e{};
+    e.batch = Bn; e.M = M; e.A = A; e.num_train_answer = c.num_train_answer; e.logit2 = b.logit2;
+    e.exist = h->last_masks.answer_exist; e.marg = b.marg; e.row_max = b.row_max; e.row_inv = b.row_inv;
+    e.scale = VQA_W_ENTROPY * loss_scale / static_cast<float>(Bn); e.d_hi = b.dl2.hi; e.d_lo = b.dl2.lo;
+    VQA_TRY(ent_marginal_bwd_launch(e, s));
+    VQA_TRY(GemmB(BM, J, A).a(b.dl2, 0, A, false).b(b.w.ans_w, 0, A, false).f32(b.dJ2, J).run(h, s));
+    SlabLnBwd r{};
+    r.batch = Bn; r.K = M; r.D = J; r.z = b.z2; r.gamma = p->joint_gamma; r.beta = p->joint_beta;
+    r.mean = b.ln2_mean; r.rstd = b.ln2_rstd; r.dz_hi = b.dz2.hi; r.dz_lo = b.dz2.lo; r.part = nullptr;
+    r.dout = b.dJ2; r.thr = keep_threshold(c.keep_joint); r.inv_keep = 1.f / c.keep_joint; r.seed = seed; r.step = step;
+    r.site = RNG_STREAM_ENT;
+    VQA_TRY(slab_ln_relu_bwd_launch(r, c.precision, s));
+    VQA_TRY(GemmB(BM, L, J).a(b.dz2, 0, J, false).b(b.w.joint_w, 0, J, false).f32(b.dX2, L).run(h, s));
+    EntDhl d{};
+    d.batch = Bn; d.M = M; d.L = L; d.dX = b.dX; d.dX2 = b.dX2; d.hp = b.hp; d.out = b.dhl_ent;
+    VQA_TRY(ent_dhl_launch(d, s));
+    d_hl_src = b.dhl_ent;
+  }
   {
     RowLnBwd r{};
-    r.rows = Bn; r.N = L; r.dout = d_hl_src; r.mul = noc ? nullptr : b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
+    r.rows = Bn; r.N = L; r.dout = d_hl_src; r.mul = (noc || v_ent) ? nullptr : b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
     r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi;
     r.dz_lo = b.dzl.lo;
     if (g->ql_gamma || g->ql_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
@@ -612,6 +663,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.batch = Bn; r.K = K; r.D = D; r.z = b.za; r.gamma = p->va_gamma; r.beta = p->va_beta;
     r.mean = b.lnva_mean; r.rstd = b.lnva_rstd; r.att = b.att; r.d_pooled = b.dP;
     r.dz_hi = b.dza.hi; r.dz_lo = b.dza.lo; r.part = b.va_part;
+    r.dout = nullptr; r.thr = 65536u; r.inv_keep = 1.f;
     VQA_TRY(slab_ln_relu_bwd_launch(r, c.precision, s));
     if (g->va_gamma) VQA_TRY(colsum_launch(b.va_part, Bn, D, 3 * D, g->va_gamma, b.scratch, s));
     if (g->va_beta) VQA_TRY(colsum_launch(b.va_part + D, Bn, D, 3 * D, g->va_beta, b.scratch, s));
@@ -807,6 +859,8 @@ VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch
   switch (site) {
     case RNG_STREAM_ATT:
       return dropout_mask_launch(mask, static_cast<long long>(batch) * c.K * c.D, c.keep_att, seed, step, RNG_STREAM_ATT, s);
+    case RNG_STREAM_ENT:
+      return dropout_mask_launch(mask, static_cast<long long>(batch) * h->M * c.J, c.keep_joint, seed, step, RNG_STREAM_ENT, s);
     case RNG_STREAM_JOINT:
     case RNG_STREAM_JOINT_L:
       return dropout_mask_launch(mask, static_cast<long long>(batch) * c.J, c.keep_joint, seed, step,

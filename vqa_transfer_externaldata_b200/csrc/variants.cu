@@ -74,6 +74,40 @@ __device__ __forceinline__ void store_planes4(bf16* hi, bf16* lo, long long o, c
   }
 }
 
+// 8-element loads (fp32 or bf16 source) and operand-plane stores shared by the slab / tile kernels below
+template <typename ZT>
+__device__ __forceinline__ void ldz8(const ZT* p, float (&x)[8]);
+template <>
+__device__ __forceinline__ void ldz8<float>(const float* p, float (&x)[8]) {
+  const float4 a = *reinterpret_cast<const float4*>(p);
+  const float4 b = *reinterpret_cast<const float4*>(p + 4);
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ldz8<bf16>(const bf16* p, float (&x)[8]) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const float2 f = __bfloat1622float2(h[j]);
+    x[2 * j] = f.x;
+    x[2 * j + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void ldf8(const float* p, float (&x)[8]) { ldz8<float>(p, x); }
+__device__ __forceinline__ void st_planes8(bf16* hi, bf16* lo, long long off, const float (&x)[8]) {
+  __nv_bfloat162 h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const bf16 a = __float2bfloat16_rn(x[2 * j]), b = __float2bfloat16_rn(x[2 * j + 1]);
+    h[j] = __nv_bfloat162(a, b);
+    l[j] = __nv_bfloat162(__float2bfloat16_rn(x[2 * j] - __bfloat162float(a)),
+                          __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(b)));
+  }
+  *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<uint4*>(h);
+  if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<uint4*>(l);
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // vqa_all / vqa_all2: combine the two heads' logits
 // ------------------------------------------------------------------------------------------------------------------
@@ -230,19 +264,189 @@ __global__ void __launch_bounds__(VT) reparam_fwd_kernel(ReparamFwd a) {
 }
 
 // latent = -0.5 * mean_b kl_rows; loss += weight * latent; report slots (fixed summation order)
-__global__ void __launch_bounds__(VT) latent_finalize_kernel(const float* __restrict__ kl_rows, int batch, float weight,
-                                                             float* __restrict__ loss, float* __restrict__ report) {
+__global__ void __launch_bounds__(VT) latent_finalize_kernel(const float* __restrict__ kl_rows, int batch, float scale,
+                                                             float weight, int slot, float* __restrict__ loss,
+                                                             float* __restrict__ report) {
   __shared__ float red[VT / 32];
   float s = 0.f;
   for (int b = threadIdx.x; b < batch; b += VT) s += kl_rows[b];
   s = bsum(s, red);
   if (threadIdx.x == 0) {
-    const float latent = -0.5f * s / batch;
-    if (loss) loss[0] += weight * latent;
+    const float extra = scale * s / batch;   // full: -0.5 * mean_b KL sums; ent: mean_b negative entropies
+    if (loss) loss[0] += weight * extra;
     if (report) {
-      report[VQA_REPORT_LATENT_LOSS] = latent;
-      report[VQA_REPORT_TRAIN_LATENT_LOSS] = weight * latent;
+      report[slot] = extra;
+      report[slot + 1] = weight * extra;
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// ent: tiled joint input, marginal softmax + negative entropy, and their backward (model_vlmap_answer_ent.py:193-213)
+// ------------------------------------------------------------------------------------------------------------------
+// x2[b, m, :] = Hp[(b*M + m) mod B, :] * Hl[b, :]   (tf.reshape(tf.tile(stop_gradient(Hp), [M, 1]), [-1, M, L]) * Hl[:, None])
+__global__ void ent_tile_kernel(EntTile a, long long total8) {
+  const int CH = a.L >> 3;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long row = i / CH;            // b * M + m
+    const int c = static_cast<int>(i - row * CH);
+    const int b = static_cast<int>(row / a.M);
+    const int src = static_cast<int>(row % a.batch);
+    float hp[8], hl[8];
+    ldf8(a.hp + static_cast<long long>(src) * a.L + c * 8, hp);
+    ldf8(a.hl + static_cast<long long>(b) * a.L + c * 8, hl);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) hp[j] *= hl[j];
+    st_planes8(a.out_hi, a.out_lo, i * 8, hp);
+  }
+}
+
+// one CTA per sample: for every marginal row m, softmax over the selected (train & existing) answers; the mean over m is
+// the marginal; ent_rows[b] = sum_a marg log(marg + 1e-8). Row maxima and reciprocal sums are kept for the backward.
+__global__ void __launch_bounds__(VT) ent_marginal_kernel(EntMarginal a) {
+  __shared__ float red[VT / 32];
+  const int b = blockIdx.x, A = a.A, M = a.M;
+  constexpr int MAXC = 4;   // float4 column chunks per thread: A <= 4 * 4 * VT = 4096
+  float4 acc[MAXC], selm[MAXC];
+#pragma unroll
+  for (int t = 0; t < MAXC; ++t) {
+    acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int c = (threadIdx.x + t * VT) * 4;
+    selm[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < A) {
+      const float4 ex = *reinterpret_cast<const float4*>(a.exist + c);
+      selm[t].x = (ex.x > 0.5f && c + 0 < a.num_train_answer) ? 1.f : 0.f;
+      selm[t].y = (ex.y > 0.5f && c + 1 < a.num_train_answer) ? 1.f : 0.f;
+      selm[t].z = (ex.z > 0.5f && c + 2 < a.num_train_answer) ? 1.f : 0.f;
+      selm[t].w = (ex.w > 0.5f && c + 3 < a.num_train_answer) ? 1.f : 0.f;
+    }
+  }
+  const float inv_m = 1.0f / M;
+  for (int m = 0; m < M; ++m) {
+    const float* x = a.logit2 + (static_cast<long long>(b) * M + m) * A;
+    float4 xv[MAXC];
+    float mx = -CUDART_INF_F;
+#pragma unroll
+    for (int t = 0; t < MAXC; ++t) {
+      const int c = (threadIdx.x + t * VT) * 4;
+      xv[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < A) {
+        xv[t] = *reinterpret_cast<const float4*>(x + c);
+        if (selm[t].x > 0.f) mx = fmaxf(mx, xv[t].x);
+        if (selm[t].y > 0.f) mx = fmaxf(mx, xv[t].y);
+        if (selm[t].z > 0.f) mx = fmaxf(mx, xv[t].z);
+        if (selm[t].w > 0.f) mx = fmaxf(mx, xv[t].w);
+      }
+    }
+    mx = -bmin(-mx, red);
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXC; ++t) {
+      xv[t].x = selm[t].x > 0.f ? expf(xv[t].x - mx) : 0.f;
+      xv[t].y = selm[t].y > 0.f ? expf(xv[t].y - mx) : 0.f;
+      xv[t].z = selm[t].z > 0.f ? expf(xv[t].z - mx) : 0.f;
+      xv[t].w = selm[t].w > 0.f ? expf(xv[t].w - mx) : 0.f;
+      sum += xv[t].x + xv[t].y + xv[t].z + xv[t].w;
+    }
+    sum = bsum(sum, red);
+    const float inv = 1.0f / sum;
+#pragma unroll
+    for (int t = 0; t < MAXC; ++t) {
+      acc[t].x += xv[t].x * inv; acc[t].y += xv[t].y * inv; acc[t].z += xv[t].z * inv; acc[t].w += xv[t].w * inv;
+    }
+    if (threadIdx.x == 0) {
+      a.row_max[static_cast<long long>(b) * M + m] = mx;
+      a.row_inv[static_cast<long long>(b) * M + m] = inv;
+    }
+  }
+  float ent = 0.f;
+#pragma unroll
+  for (int t = 0; t < MAXC; ++t) {
+    const int c = (threadIdx.x + t * VT) * 4;
+    if (c < A) {
+      const float4 mg = make_float4(acc[t].x * inv_m, acc[t].y * inv_m, acc[t].z * inv_m, acc[t].w * inv_m);
+      *reinterpret_cast<float4*>(a.marg + static_cast<long long>(b) * A + c) = mg;
+      // unselected answers are not part of the boolean_mask'ed tensor: they contribute nothing
+      ent += selm[t].x * mg.x * logf(mg.x + 1e-8f) + selm[t].y * mg.y * logf(mg.y + 1e-8f) +
+             selm[t].z * mg.z * logf(mg.z + 1e-8f) + selm[t].w * mg.w * logf(mg.w + 1e-8f);
+    }
+  }
+  ent = bsum(ent, red);
+  if (threadIdx.x == 0) a.ent_rows[b] = ent;
+}
+
+// d logit2[b, m, a] = prob * (dprob - sum_a' prob dprob), dprob = c (log(marg + eps) + marg / (marg + eps)) / M
+__global__ void __launch_bounds__(VT) ent_marginal_bwd_kernel(EntMarginalBwd a) {
+  __shared__ float red[VT / 32];
+  const int b = blockIdx.x, A = a.A, M = a.M;
+  constexpr int MAXC = 4;
+  float4 dpr[MAXC];
+#pragma unroll
+  for (int t = 0; t < MAXC; ++t) {
+    const int c = (threadIdx.x + t * VT) * 4;
+    dpr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < A) {
+      const float4 ex = *reinterpret_cast<const float4*>(a.exist + c);
+      const float4 mg = *reinterpret_cast<const float4*>(a.marg + static_cast<long long>(b) * A + c);
+      const float k = a.scale / M;
+      if (ex.x > 0.5f && c + 0 < a.num_train_answer) dpr[t].x = k * (logf(mg.x + 1e-8f) + mg.x / (mg.x + 1e-8f));
+      if (ex.y > 0.5f && c + 1 < a.num_train_answer) dpr[t].y = k * (logf(mg.y + 1e-8f) + mg.y / (mg.y + 1e-8f));
+      if (ex.z > 0.5f && c + 2 < a.num_train_answer) dpr[t].z = k * (logf(mg.z + 1e-8f) + mg.z / (mg.z + 1e-8f));
+      if (ex.w > 0.5f && c + 3 < a.num_train_answer) dpr[t].w = k * (logf(mg.w + 1e-8f) + mg.w / (mg.w + 1e-8f));
+    }
+  }
+  for (int m = 0; m < M; ++m) {
+    const long long row = static_cast<long long>(b) * M + m;
+    const float* x = a.logit2 + row * A;
+    const float mx = a.row_max[row], inv = a.row_inv[row];
+    float4 pr[MAXC];
+    float dot = 0.f;
+#pragma unroll
+    for (int t = 0; t < MAXC; ++t) {
+      const int c = (threadIdx.x + t * VT) * 4;
+      pr[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c < A) {
+        const float4 xv = *reinterpret_cast<const float4*>(x + c);
+        const float4 ex = *reinterpret_cast<const float4*>(a.exist + c);
+        if (ex.x > 0.5f && c + 0 < a.num_train_answer) pr[t].x = expf(xv.x - mx) * inv;
+        if (ex.y > 0.5f && c + 1 < a.num_train_answer) pr[t].y = expf(xv.y - mx) * inv;
+        if (ex.z > 0.5f && c + 2 < a.num_train_answer) pr[t].z = expf(xv.z - mx) * inv;
+        if (ex.w > 0.5f && c + 3 < a.num_train_answer) pr[t].w = expf(xv.w - mx) * inv;
+        dot += pr[t].x * dpr[t].x + pr[t].y * dpr[t].y + pr[t].z * dpr[t].z + pr[t].w * dpr[t].w;
+      }
+    }
+    dot = bsum(dot, red);
+#pragma unroll
+    for (int t = 0; t < MAXC; ++t) {
+      const int c = (threadIdx.x + t * VT) * 4;
+      if (c < A) {
+        const float d[4] = {pr[t].x * (dpr[t].x - dot), pr[t].y * (dpr[t].y - dot), pr[t].z * (dpr[t].z - dot),
+                            pr[t].w * (dpr[t].w - dot)};
+        store_planes4(a.d_hi, a.d_lo, row * A + c, d);
+      }
+    }
+  }
+}
+
+// dHl[b, :] = dX[b, :] * Hp[b, :] + sum_m dX2[b, m, :] * Hp[(b*M + m) mod B, :]
+__global__ void ent_dhl_kernel(EntDhl a, long long total4) {
+  const int L4 = a.L >> 2;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int b = static_cast<int>(i / L4), c = static_cast<int>(i - static_cast<long long>(b) * L4) * 4;
+    const float4 dx = *reinterpret_cast<const float4*>(a.dX + static_cast<long long>(b) * a.L + c);
+    const float4 hp = *reinterpret_cast<const float4*>(a.hp + static_cast<long long>(b) * a.L + c);
+    float4 acc = make_float4(dx.x * hp.x, dx.y * hp.y, dx.z * hp.z, dx.w * hp.w);
+    for (int m = 0; m < a.M; ++m) {
+      const long long row = static_cast<long long>(b) * a.M + m;
+      const int src = static_cast<int>(row % a.batch);
+      const float4 d2 = *reinterpret_cast<const float4*>(a.dX2 + row * a.L + c);
+      const float4 h2 = *reinterpret_cast<const float4*>(a.hp + static_cast<long long>(src) * a.L + c);
+      acc.x = fmaf(d2.x, h2.x, acc.x); acc.y = fmaf(d2.y, h2.y, acc.y);
+      acc.z = fmaf(d2.z, h2.z, acc.z); acc.w = fmaf(d2.w, h2.w, acc.w);
+    }
+    *reinterpret_cast<float4*>(a.out + static_cast<long long>(b) * a.L + c) = acc;
   }
 }
 
@@ -271,39 +475,6 @@ __global__ void reparam_bwd_kernel(ReparamBwd a, long long total4) {
 // ------------------------------------------------------------------------------------------------------------------
 // adapt: LayerNorm over the whole [K, D] slab of a sample + ReLU, materialised; and its backward
 // ------------------------------------------------------------------------------------------------------------------
-template <typename ZT>
-__device__ __forceinline__ void ldz8(const ZT* p, float (&x)[8]);
-template <>
-__device__ __forceinline__ void ldz8<float>(const float* p, float (&x)[8]) {
-  const float4 a = *reinterpret_cast<const float4*>(p);
-  const float4 b = *reinterpret_cast<const float4*>(p + 4);
-  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-}
-template <>
-__device__ __forceinline__ void ldz8<bf16>(const bf16* p, float (&x)[8]) {
-  const uint4 v = *reinterpret_cast<const uint4*>(p);
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const float2 f = __bfloat1622float2(h[j]);
-    x[2 * j] = f.x;
-    x[2 * j + 1] = f.y;
-  }
-}
-__device__ __forceinline__ void ldf8(const float* p, float (&x)[8]) { ldz8<float>(p, x); }
-__device__ __forceinline__ void st_planes8(bf16* hi, bf16* lo, long long off, const float (&x)[8]) {
-  __nv_bfloat162 h[4], l[4];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const bf16 a = __float2bfloat16_rn(x[2 * j]), b = __float2bfloat16_rn(x[2 * j + 1]);
-    h[j] = __nv_bfloat162(a, b);
-    l[j] = __nv_bfloat162(__float2bfloat16_rn(x[2 * j] - __bfloat162float(a)),
-                          __float2bfloat16_rn(x[2 * j + 1] - __bfloat162float(b)));
-  }
-  *reinterpret_cast<uint4*>(hi + off) = *reinterpret_cast<uint4*>(h);
-  if (lo) *reinterpret_cast<uint4*>(lo + off) = *reinterpret_cast<uint4*>(l);
-}
-
 template <typename ZT>
 __global__ void __launch_bounds__(VT) slab_ln_relu_fwd_kernel(SlabLnFwd a) {
   __shared__ float red[VT / 32];
@@ -335,6 +506,12 @@ __global__ void __launch_bounds__(VT) slab_ln_relu_fwd_kernel(SlabLnFwd a) {
     ldf8(a.beta + c * 8, bt);
 #pragma unroll
     for (int j = 0; j < 8; ++j) y[j] = fmaxf(fmaf((x[j] - mean) * rstd, g[j], bt[j]), 0.f);
+    if (a.thr < 65536u) {   // tf.nn.dropout on the layer's output (the tiled joint of the ent variant)
+      const uint32_t bits = philox_keep_bits(
+          philox4x32_10(static_cast<unsigned long long>(base >> 3) + i, a.site, a.seed, a.step), a.thr);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = ((bits >> j) & 1u) ? y[j] * a.inv_keep : 0.f;
+    }
     st_planes8(a.out_hi, a.out_lo, base + static_cast<long long>(i) * 8, y);
   }
   if (threadIdx.x == 0) {
@@ -353,8 +530,27 @@ __global__ void __launch_bounds__(VT) slab_ln_relu_bwd_kernel(SlabLnBwd a) {
   const ZT* z = static_cast<const ZT*>(a.z) + base;
   const float N = static_cast<float>(a.K) * D;
   const float mean = a.mean[b], rstd = a.rstd[b];
-  const float* att = a.att + static_cast<long long>(b) * a.K;
-  const float* dP = a.d_pooled + static_cast<long long>(b) * D;
+  const float* att = a.dout ? nullptr : a.att + static_cast<long long>(b) * a.K;
+  const float* dP = a.dout ? nullptr : a.d_pooled + static_cast<long long>(b) * D;
+  const float* dout = a.dout ? a.dout + base : nullptr;
+  // upstream gradient of 8 outputs at flat chunk i (row k, column chunk c): a_k * dP (adapt) or the given tensor through
+  // the regenerated dropout mask (ent)
+  auto upstream = [&](int i, int k, int c, float (&up)[8]) {
+    if (dout) {
+      ldf8(dout + static_cast<long long>(i) * 8, up);
+      if (a.thr < 65536u) {
+        const uint32_t bits = philox_keep_bits(
+            philox4x32_10(static_cast<unsigned long long>(base >> 3) + i, a.site, a.seed, a.step), a.thr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) up[j] = ((bits >> j) & 1u) ? up[j] * a.inv_keep : 0.f;
+      }
+    } else {
+      ldf8(dP + c * 8, up);
+      const float ak = att[k];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) up[j] *= ak;
+    }
+  };
   float s1 = 0.f, s2 = 0.f;
   for (int i = threadIdx.x; i < n8; i += VT) {
     const int k = i / CH, c = i % CH;
@@ -362,12 +558,11 @@ __global__ void __launch_bounds__(VT) slab_ln_relu_bwd_kernel(SlabLnBwd a) {
     ldz8<ZT>(z + static_cast<long long>(i) * 8, x);
     ldf8(a.gamma + c * 8, g);
     ldf8(a.beta + c * 8, bt);
-    ldf8(dP + c * 8, dp);
-    const float ak = att[k];
+    upstream(i, k, c, dp);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float xh = (x[j] - mean) * rstd;
-      const float dy = fmaf(xh, g[j], bt[j]) > 0.f ? ak * dp[j] : 0.f;
+      const float dy = fmaf(xh, g[j], bt[j]) > 0.f ? dp[j] : 0.f;
       const float dxh = dy * g[j];
       s1 += dxh;
       s2 = fmaf(dxh, xh, s2);
@@ -377,21 +572,20 @@ __global__ void __launch_bounds__(VT) slab_ln_relu_bwd_kernel(SlabLnBwd a) {
   const float m2 = bsum(s2, red) / N;
   // second pass: a thread owns column chunks and walks the K rows, so the per-column partial sums stay in registers
   for (int c = threadIdx.x; c < CH; c += VT) {
-    float g[8], bt[8], dp[8], dg[8], db[8], dbias[8];
+    float g[8], bt[8], dg[8], db[8], dbias[8];
     ldf8(a.gamma + c * 8, g);
     ldf8(a.beta + c * 8, bt);
-    ldf8(dP + c * 8, dp);
 #pragma unroll
     for (int j = 0; j < 8; ++j) dg[j] = db[j] = dbias[j] = 0.f;
     for (int k = 0; k < a.K; ++k) {
-      float x[8], dz[8];
+      float x[8], dz[8], dp[8];
       const long long o = static_cast<long long>(k) * D + c * 8;
       ldz8<ZT>(z + o, x);
-      const float ak = att[k];
+      upstream(k * CH + c, k, c, dp);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float xh = (x[j] - mean) * rstd;
-        const float dy = fmaf(xh, g[j], bt[j]) > 0.f ? ak * dp[j] : 0.f;
+        const float dy = fmaf(xh, g[j], bt[j]) > 0.f ? dp[j] : 0.f;
         dg[j] = fmaf(dy, xh, dg[j]);
         db[j] += dy;
         dz[j] = rstd * (dy * g[j] - m1 - xh * m2);
@@ -399,6 +593,7 @@ __global__ void __launch_bounds__(VT) slab_ln_relu_bwd_kernel(SlabLnBwd a) {
       }
       st_planes8(a.dz_hi, a.dz_lo, base + o, dz);
     }
+    if (!a.part) continue;   // frozen layer: no parameter gradients wanted
     float* pg = a.part + (static_cast<long long>(b) * 3 + 0) * D + c * 8;
     float* pb = a.part + (static_cast<long long>(b) * 3 + 1) * D + c * 8;
     float* ps = a.part + (static_cast<long long>(b) * 3 + 2) * D + c * 8;
@@ -453,11 +648,45 @@ VqaStatus reparam_fwd_launch(const ReparamFwd& a, cudaStream_t s) {
   return VQA_OK;
 }
 
-VqaStatus latent_finalize_launch(const float* kl_rows, int batch, float weight, float* loss, float* report,
-                                 cudaStream_t s) {
+VqaStatus latent_finalize_launch(const float* rows, int batch, float scale, float weight, int slot, float* loss,
+                                 float* report, cudaStream_t s) {
   if (batch == 0) return VQA_OK;
-  latent_finalize_kernel<<<1, VT, 0, s>>>(kl_rows, batch, weight, loss, report);
+  latent_finalize_kernel<<<1, VT, 0, s>>>(rows, batch, scale, weight, slot, loss, report);
   VQA_LAUNCH_CHECK("latent_finalize");
+  return VQA_OK;
+}
+
+VqaStatus ent_tile_launch(const EntTile& a, cudaStream_t s) {
+  if (a.batch == 0) return VQA_OK;
+  if (a.L & 7) return set_error(VQA_ERR_BAD_SHAPE, "ent_tile: L must be a multiple of 8");
+  const long long total8 = static_cast<long long>(a.batch) * a.M * (a.L >> 3);
+  ent_tile_kernel<<<grid_for(total8, 256), 256, 0, s>>>(a, total8);
+  VQA_LAUNCH_CHECK("ent_tile");
+  return VQA_OK;
+}
+
+VqaStatus ent_marginal_launch(const EntMarginal& a, cudaStream_t s) {
+  if (a.batch == 0) return VQA_OK;
+  if ((a.A & 3) || a.A > 16 * VT) return set_error(VQA_ERR_BAD_SHAPE, "ent_marginal: A must be a multiple of 4 and <= 4096");
+  ent_marginal_kernel<<<a.batch, VT, 0, s>>>(a);
+  VQA_LAUNCH_CHECK("ent_marginal");
+  return VQA_OK;
+}
+
+VqaStatus ent_marginal_bwd_launch(const EntMarginalBwd& a, cudaStream_t s) {
+  if (a.batch == 0) return VQA_OK;
+  if ((a.A & 3) || a.A > 16 * VT) return set_error(VQA_ERR_BAD_SHAPE, "ent_marginal: A must be a multiple of 4 and <= 4096");
+  ent_marginal_bwd_kernel<<<a.batch, VT, 0, s>>>(a);
+  VQA_LAUNCH_CHECK("ent_marginal_bwd");
+  return VQA_OK;
+}
+
+VqaStatus ent_dhl_launch(const EntDhl& a, cudaStream_t s) {
+  if (a.batch == 0) return VQA_OK;
+  if (a.L & 3) return set_error(VQA_ERR_BAD_SHAPE, "ent_dhl: L must be a multiple of 4");
+  const long long total4 = static_cast<long long>(a.batch) * (a.L >> 2);
+  ent_dhl_kernel<<<grid_for(total4, 128), 128, 0, s>>>(a, total4);
+  VQA_LAUNCH_CHECK("ent_dhl");
   return VQA_OK;
 }
 

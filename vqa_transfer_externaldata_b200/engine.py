@@ -90,6 +90,7 @@ class AnswerModelConfig:
     precision: str = "bf16"         # 'bf16' | 'fp32'
     keep_att: float = 0.8
     keep_joint: float = 0.5
+    num_marginal: int = 200         # NUM_MARGINAL of the ent variant (vqa/model_vlmap_answer_ent.py:16)
 
     def shape(self, field):
         c = asdict(self)
@@ -102,7 +103,7 @@ class AnswerModelConfig:
             Vq=self.Vq, num_train_answer=self.num_train_answer,
             variant=L.VARIANTS[self.variant],
             precision={"bf16": L.PREC_BF16, "fp32": L.PREC_FP32}[self.precision],
-            keep_att=self.keep_att, keep_joint=self.keep_joint)
+            keep_att=self.keep_att, keep_joint=self.keep_joint, num_marginal=self.num_marginal)
 
 
 def frozen_fields(variant):
@@ -206,13 +207,14 @@ class PendingScalars:
         self.event = torch.cuda.Event()
         self.event.record(torch.cuda.current_stream(eng.device))
         self.nbytes = 4 * (1 + L.NUM_REPORT)
-        self._keys = eng.report_keys
+        self._keys, self._all = eng.report_keys, eng._all_report_keys
 
     def get(self):
         self.event.synchronize()
         vals = self.buf.tolist()
         self._slots.append(self.buf)
-        return vals[0], dict(zip(self._keys, vals[1:]))
+        full = dict(zip(self._all, vals[1:]))
+        return vals[0], {k: full[k] for k in self._keys}
 
 
 class BatchSet:
@@ -271,7 +273,8 @@ class Engine:
         self.o_pooled = torch.zeros(cfg.B, cfg.D if cfg.variant == "vlmap_answer_adapt" else cfg.Dv, device=dev)
         self.h_scalars = torch.zeros(1 + L.NUM_REPORT).pin_memory()
         # report keys this model_type fills: the 13 common ones (+ the latent losses of the full variant)
-        self.report_keys = L.REPORT_KEYS + (L.EXTRA_REPORT_KEYS if cfg.variant == "vlmap_answer_full" else [])
+        self._all_report_keys = L.REPORT_KEYS + L.EXTRA_REPORT_KEYS
+        self.report_keys = L.REPORT_KEYS + L.VARIANT_REPORT_KEYS.get(cfg.variant, [])
         self.grad_norm = torch.zeros(1, device=dev)
         self._outs = L.VqaOutputs(
             loss=self.o_loss.data_ptr(), report=self.o_report.data_ptr(), att_score=self.o_att.data_ptr(),
@@ -496,7 +499,8 @@ class Engine:
     def dropout_mask_site(self, site, seed, step, batch=None):
         """0 / 1 keep mask of one dropout site (L.SITE_*) for (seed, step)."""
         Bn = self.batch_size if batch is None else batch
-        shape = (Bn, self.cfg.K, self.cfg.D) if site == L.SITE_ATT else (Bn, self.cfg.J)
+        shape = ((Bn, self.cfg.K, self.cfg.D) if site == L.SITE_ATT else
+                 (Bn, self.cfg.num_marginal, self.cfg.J) if site == L.SITE_ENT else (Bn, self.cfg.J))
         out = torch.empty(*shape, dtype=torch.uint8, device=self.device)
         L.check(self.lib.vqa_dropout_mask_site(self.h, site, Bn, C.c_uint64(seed), C.c_uint64(step), out.data_ptr(),
                                                self._stream()))
@@ -522,7 +526,8 @@ class Engine:
         self.h_scalars[1:].copy_(self.o_report, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         vals = self.h_scalars.tolist()
-        return vals[0], dict(zip(self.report_keys, vals[1:]))
+        full = dict(zip(self._all_report_keys, vals[1:]))
+        return vals[0], {k: full[k] for k in self.report_keys}
 
     def read_scalars_async(self):
         """Enqueue the D2H of loss + report into a fresh pinned slot and return a handle; handle.get() waits for

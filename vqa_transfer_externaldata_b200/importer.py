@@ -4,9 +4,9 @@ Only the hot-path family is served; the other names of the reference raise NotIm
 scope decision instead of silently mapping to something else."""
 
 SUPPORTED = ("vlmap_answer", "vlmap_answer2", "vlmap_answer_no_noise", "vlmap_answer_noc", "vlmap_answer_nocarch",
-             "vlmap_answer_full", "vlmap_answer_vqa_all", "vlmap_answer_vqa_all2", "vlmap_answer_adapt", "standard")
-# the one family member not built: the 200-way tiled marginal-entropy regulariser (vqa/model_vlmap_answer_ent.py:193-213)
-PLANNED = ("vlmap_answer_ent",)
+             "vlmap_answer_full", "vlmap_answer_vqa_all", "vlmap_answer_vqa_all2", "vlmap_answer_adapt",
+             "vlmap_answer_ent", "standard")
+PLANNED = ()   # every vlmap_answer* member of vqa/importer.py:22-51 is served
 OUT_OF_SCOPE = ("vqa", "standard_testmask", "standard_word2vec", "vlmap_only", "vlmap_finetune")
 
 
@@ -15,10 +15,10 @@ def get_model_types():
 
 
 def get_model_class(model_type="vlmap_answer"):
-    from .model import (AdaptModel, Answer2Model, FullModel, Model, NocArchModel, NocModel, NoNoiseModel, StandardModel,
-                        VqaAll2Model, VqaAllModel)
+    from .model import (AdaptModel, Answer2Model, EntModel, FullModel, Model, NocArchModel, NocModel, NoNoiseModel,
+                        StandardModel, VqaAll2Model, VqaAllModel)
     extra = {"vlmap_answer_full": FullModel, "vlmap_answer_vqa_all": VqaAllModel,
-             "vlmap_answer_vqa_all2": VqaAll2Model, "vlmap_answer_adapt": AdaptModel}
+             "vlmap_answer_vqa_all2": VqaAll2Model, "vlmap_answer_adapt": AdaptModel, "vlmap_answer_ent": EntModel}
     if model_type in extra:
         return extra[model_type]
     if model_type == "vlmap_answer_noc":

@@ -17,7 +17,8 @@ VQA_ERR_CUDA, VQA_ERR_NO_DEVICE, VQA_ERR_STATE = -4, -5, -6
 VARIANT_VLMAP_ANSWER, VARIANT_STANDARD, VARIANT_VLMAP_ANSWER2, VARIANT_VLMAP_ANSWER_NO_NOISE, VARIANT_VLMAP_ANSWER_NOC = range(5)
 VARIANTS = {"vlmap_answer": 0, "standard": 1, "vlmap_answer2": 2, "vlmap_answer_no_noise": 3,
             "vlmap_answer_noc": 4, "vlmap_answer_nocarch": 4,   # nocarch is the same graph (model_vlmap_answer_nocarch.py)
-            "vlmap_answer_full": 5, "vlmap_answer_vqa_all": 6, "vlmap_answer_vqa_all2": 7, "vlmap_answer_adapt": 8}
+            "vlmap_answer_full": 5, "vlmap_answer_vqa_all": 6, "vlmap_answer_vqa_all2": 7, "vlmap_answer_adapt": 8,
+            "vlmap_answer_ent": 9}
 PREC_BF16, PREC_FP32 = 0, 1
 
 REPORT_KEYS = [
@@ -26,7 +27,10 @@ REPORT_KEYS = [
     "normal_train_exist_acc", "max_exist_acc", "test_max_acc", "test_max_exist_acc",
 ]
 # report slots after the 13 common ones (vqa/model_vlmap_answer_full.py:221-223); 0 for the other variants
-EXTRA_REPORT_KEYS = ["latent_loss", "train_latent_loss"]
+EXTRA_REPORT_KEYS = ["latent_loss", "train_latent_loss", "entropy", "weighted_entropy"]
+# which of them a model_type reports (model_vlmap_answer_full.py:221-223, model_vlmap_answer_ent.py:292-294)
+VARIANT_REPORT_KEYS = {"vlmap_answer_full": ["latent_loss", "train_latent_loss"],
+                       "vlmap_answer_ent": ["entropy", "weighted_entropy"]}
 NUM_REPORT = len(REPORT_KEYS) + len(EXTRA_REPORT_KEYS)   # VQA_NUM_REPORT
 PER_SAMPLE_KEYS = [
     "all_score", "max_train_score", "test_obj_score", "test_obj_max_score", "test_attr_score",
@@ -35,7 +39,7 @@ PER_SAMPLE_KEYS = [
 
 NUM_PHASES = 14
 ACT_HQ, ACT_HL, ACT_HP, ACT_JD, ACT_Z, ACT_JDL, ACT_VA = range(7)
-SITE_ATT, SITE_JOINT, SITE_JOINT_L = 1, 2, 3   # dropout sites of vqa_dropout_mask_site
+SITE_ATT, SITE_JOINT, SITE_JOINT_L, SITE_ENT = 1, 2, 3, 5   # dropout sites of vqa_dropout_mask_site
 
 PARAM_FIELDS = [
     "embed", "v_w", "v_b", "v_gamma", "v_beta", "gru_gates_w", "gru_gates_b", "gru_cand_w",
@@ -54,7 +58,7 @@ class VqaError(RuntimeError):
 class VqaConfig(C.Structure):
     _fields_ = [(n, C.c_int32) for n in
                 ("B", "K", "Dv", "D", "L", "J", "A", "T", "W", "Vq", "num_train_answer", "variant",
-                 "precision")] + [("keep_att", C.c_float), ("keep_joint", C.c_float)]
+                 "precision")] + [("keep_att", C.c_float), ("keep_joint", C.c_float), ("num_marginal", C.c_int32)]
 
 
 # the extra question layer of model_vlmap_answer2 (q_L_ft2: FC + LayerNorm + tanh) and model_vlmap_answer_no_noise

@@ -120,7 +120,7 @@ class Model(object):
             L=int(getattr(cfgd, "l_dim", L_DIM)), J=2 * int(getattr(cfgd, "l_dim", L_DIM)),
             A=self.num_answer, T=T, W=int(getattr(cfgd, "w_dim", W_DIM)), Vq=len(self.vocab["vocab"]),
             num_train_answer=self.num_train_answer, variant=self.MODEL_TYPE,
-            precision=getattr(cfgd, "precision", "bf16"))
+            precision=getattr(cfgd, "precision", "bf16"), num_marginal=int(getattr(cfgd, "num_marginal", 200)))
         self.engine = Engine(self.engine_config, device=getattr(cfgd, "device", None))
         self.engine.set_feature_bank(self.features, self.num_boxes)
         self.engine.set_answer_masks(self.obj_answer_mask[0], self.attr_answer_mask[0], self.answer_exist_mask[0])
@@ -252,6 +252,9 @@ class Model(object):
             self.losses["answer"] = report["answer_train_loss"]
             self.losses["latent"] = report["train_latent_loss"]
             report = dict(report, latent_loss_weight=0.1)
+        elif "weighted_entropy" in report:  # vqa/model_vlmap_answer_ent.py:290-291
+            self.losses["answer"] = report["answer_train_loss"]
+            self.losses["entropy"] = report["weighted_entropy"]
         else:
             self.losses["answer"] = loss
         if self.OLD_REPORT:
@@ -275,6 +278,12 @@ class FullModel(Model):
     loss enters model.loss with weight 0.1 and is reported as latent_loss / train_latent_loss."""
     MODEL_TYPE = "vlmap_answer_full"
     OLD_REPORT = True
+
+
+class EntModel(Model):
+    """vqa/model_vlmap_answer_ent.py: the base model plus the maximum-entropy regulariser (NUM_MARGINAL tiles of the
+    joint head per sample, marginal softmax over the train & existing answers, loss += 0.1 * negative entropy)."""
+    MODEL_TYPE = "vlmap_answer_ent"
 
 
 class AdaptModel(Model):
