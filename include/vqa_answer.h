@@ -240,6 +240,10 @@ VQA_API int32_t vqa_abi_version(void);
 /* number of kernels this library has enqueued so far in this process */
 VQA_API uint64_t vqa_launch_count(void);
 
+/* CRC-32C (Castagnoli) of a HOST buffer: the checksum of the TFRecord framing the reference's input pipeline reads
+ * (vqa/datasets/input_ops_vqa_tf_record_memft.py:17-22); used by the Python mirror's record reader. No GPU involved. */
+VQA_API uint32_t vqa_crc32c(const uint8_t* data_host, uint64_t n);
+
 /* bytes of device workspace this handle needs; attach a buffer of at least that size (256-B aligned) */
 VQA_API VqaStatus vqa_workspace_bytes(VqaHandle h, uint64_t* bytes);
 VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes);

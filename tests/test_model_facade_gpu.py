@@ -65,3 +65,27 @@ def test_train_step_through_the_plugin_interface(model_type):
         assert {"q_L_mean", "q_L_log_sigma_sq"} <= changed
     # a checkpoint round trip by variable name
     model.load_state_dict(after)
+
+
+def test_tfrecord_batches_feed_the_model(tmp_path):
+    """vqa/trainer.py: batch = input_ops.create(...); Model(batch, config, ...). A batch read back from TFRecord shards
+    (input_ops.create) drives the CUDA path exactly like the dict it was written from."""
+    from vqa_transfer_externaldata_b200 import input_ops as IO
+    config, feats, batch, _ = make_synthetic_config(SMALL, variant="vlmap_answer", precision="bf16", seed=7, num_images=16)
+    B, A = SMALL["B"], SMALL["A"]
+    samples = []
+    for i in range(B):
+        ids = np.nonzero(batch["answer_target"][i])[0]
+        samples.append({"qid": int(batch["id"][i]), "image_id": f"{i}".encode(), "image_idx": int(batch["image_idx"][i]),
+                        "q_intseq": batch["q_intseq"][i, :batch["q_intseq_len"][i]],
+                        "answer_ids": ids, "answer_scores": batch["answer_target"][i, ids]})
+    IO.write_shards(str(tmp_path), "val", samples, A, num_shards=1)
+    (rb,) = list(IO.create(B, str(tmp_path), "val", is_train=False))
+    assert np.array_equal(rb["answer_target"], batch["answer_target"])
+    assert np.array_equal(rb["q_intseq_len"], batch["q_intseq_len"])
+    model = importer.get_model_class("vlmap_answer")(batch, config, is_train=False, image_features=feats)
+    model.forward(batch)
+    ref = model.output["logit"].clone()
+    model.forward(rb)     # T of this batch = its longest question (padded_batch), not the configured maximum
+    assert torch.equal(model.output["logit"], ref)
+    assert torch.equal(model.output["pred"], model.output["pred"])

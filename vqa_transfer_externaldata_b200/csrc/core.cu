@@ -402,6 +402,34 @@ VQA_API const char* vqa_phase_name(int32_t phase) {
   return (phase >= 0 && phase < VQA_NUM_PHASES) ? names[phase] : "?";
 }
 
+/* CRC-32C (Castagnoli) of a host buffer: the checksum of TFRecord framing (input_ops.py reads the reference's shards) */
+VQA_API uint32_t vqa_crc32c(const uint8_t* data_host, uint64_t n) {
+  static uint32_t table[8][256];
+  static bool ready = false;
+  if (!ready) {   // slicing-by-8 tables of the reflected polynomial 0x82F63B78
+    for (uint32_t i = 0; i < 256; ++i) {
+      uint32_t c = i;
+      for (int k = 0; k < 8; ++k) c = (c & 1u) ? (c >> 1) ^ 0x82F63B78u : c >> 1;
+      table[0][i] = c;
+    }
+    for (uint32_t i = 0; i < 256; ++i)
+      for (int t = 1; t < 8; ++t) table[t][i] = (table[t - 1][i] >> 8) ^ table[0][table[t - 1][i] & 0xFFu];
+    ready = true;
+  }
+  uint32_t c = 0xFFFFFFFFu;
+  uint64_t i = 0;
+  for (; i + 8 <= n; i += 8) {
+    uint32_t lo, hi;
+    memcpy(&lo, data_host + i, 4);
+    memcpy(&hi, data_host + i + 4, 4);
+    lo ^= c;
+    c = table[7][lo & 0xFFu] ^ table[6][(lo >> 8) & 0xFFu] ^ table[5][(lo >> 16) & 0xFFu] ^ table[4][lo >> 24] ^
+        table[3][hi & 0xFFu] ^ table[2][(hi >> 8) & 0xFFu] ^ table[1][(hi >> 16) & 0xFFu] ^ table[0][hi >> 24];
+  }
+  for (; i < n; ++i) c = table[0][(c ^ data_host[i]) & 0xFFu] ^ (c >> 8);
+  return c ^ 0xFFFFFFFFu;
+}
+
 /* number of kernels this library has enqueued in this process (bench.py's gpu_launches) */
 VQA_API uint64_t vqa_launch_count(void) { return launch_count(); }
 

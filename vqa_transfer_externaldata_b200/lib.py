@@ -141,6 +141,7 @@ SYMBOLS = {
     "vqa_last_error": (C.c_char_p, []),
     "vqa_abi_version": (C.c_int32, []),
     "vqa_launch_count": (C.c_uint64, []),
+    "vqa_crc32c": (C.c_uint32, [C.c_char_p, C.c_uint64]),
     "vqa_workspace_bytes": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "vqa_set_workspace": (C.c_int32, [_P, _P, C.c_uint64]),
     "vqa_prepare_params": (C.c_int32, [_P, C.POINTER(VqaParams), _P]),
