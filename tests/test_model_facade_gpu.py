@@ -87,5 +87,4 @@ def test_tfrecord_batches_feed_the_model(tmp_path):
     model.forward(batch)
     ref = model.output["logit"].clone()
     model.forward(rb)     # T of this batch = its longest question (padded_batch), not the configured maximum
-    assert torch.equal(model.output["logit"], ref)
-    assert torch.equal(model.output["pred"], model.output["pred"])
+    assert torch.allclose(model.output["logit"], ref, rtol=1e-5, atol=1e-5)
