@@ -552,6 +552,21 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(GemmB(Bn, L, J).a(b.dzjl, 0, J, false).b(b.w.jl_w, 0, J, false).f32(b.dXl, L).run(h, s));
     d_hl_src = b.dXl;
   }
+  // The q_linear_l branch (LN / ReLU backward + dq = dZl Wl^T) is independent of the pooled_linear_l branch: when it is
+  // the plain frozen layer (no extra question layer, no parameter gradients, no regulariser) it runs on auxiliary
+  // stream 2 beside the pooled branch and the attention backward; the BPTT, which consumes dq, joins it.
+  const bool has_qp_early = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE || v_full;
+  const bool fork_ql = !has_qp_early && !noc && c.variant != VQA_VARIANT_VLMAP_ANSWER_ENT && !g->ql_w && !g->ql_b &&
+                       !g->ql_gamma && !g->ql_beta && !(h->profile && !h->profile_overlapped);
+  if (fork_ql) {
+    cudaStream_t sq;
+    VQA_TRY(fork_stream(h, 2, s, &sq));
+    RowLnBwd r{};
+    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
+    r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi; r.dz_lo = b.dzl.lo;
+    VQA_TRY(row_ln_relu_bwd_launch(r, sq));
+    VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, sq));
+  }
   {
     RowLnBwd r{};
     r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = noc ? nullptr : b.hl; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta;
@@ -584,7 +599,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(ent_dhl_launch(d, s));
     d_hl_src = b.dhl_ent;
   }
-  {
+  if (!fork_ql) {
     RowLnBwd r{};
     r.rows = Bn; r.N = L; r.dout = d_hl_src; r.mul = (noc || v_ent) ? nullptr : b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
     r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi;
@@ -605,7 +620,9 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   if (g->ql_b) VQA_TRY(colsum_launch(b.dzl_f32, Bn, L, L, g->ql_b, b.scratch, s));
   // dP = dZp Wp^T ; dq = dZl Wl^T
   VQA_TRY(GemmB(Bn, Pd, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Pd).run(h, s));
-  if (!has_qp) {
+  if (fork_ql) {
+    // dq is being produced on auxiliary stream 2
+  } else if (!has_qp) {
     VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, s));
   } else if (c.variant == VQA_VARIANT_VLMAP_ANSWER2) {
     // d(q_L_ft2) -> tanh / LayerNorm backward -> parameter gradients of q_L_ft2 -> dq
@@ -671,6 +688,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->va_w) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dza, 0, D, true).f32(g->va_w, D).run(h, s));
   }
   PH_END(VQA_PH_ATTN_BWD);
+  if (fork_ql) VQA_TRY(join_stream(h, 2, s));   // dq (q_linear_l branch) is needed by the BPTT below
   // data-parallel runs take dWv here, ahead of the BPTT, so that its all-reduce can overlap the recurrent kernels
   const bool early = h->early_grads && !(h->profile && !h->profile_overlapped);
   if (early && g->v_w)
