@@ -377,7 +377,36 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
   const long long vb = static_cast<long long>(b) * K * Dv;
   for (int k = warp; k < K; k += ATT_WARPS) {
     float acc = 0.f;
-    if (k < nb) {
+    if (k < nb && !a.v_lo) {
+      // single bf16 plane: keep the raw 16-byte words in registers (4 per chunk instead of 8 floats) so that EIGHT loads
+      // per lane are in flight -- the pass is bound by memory latency at 16 warps per SM (ncu: long scoreboard)
+      constexpr int UR = 8;
+      const bf16* vrow = a.v_hi + vb + static_cast<long long>(k) * Dv;
+      for (int c0 = lane; c0 < (Dv >> 3); c0 += 32 * UR) {
+        uint4 raw[UR];
+#pragma unroll
+        for (int i = 0; i < UR; ++i) {
+          const int c = c0 + 32 * i;
+          if (c < (Dv >> 3)) raw[i] = __ldg(reinterpret_cast<const uint4*>(vrow + c * 8));
+        }
+#pragma unroll
+        for (int i = 0; i < UR; ++i) {
+          const int c = c0 + 32 * i;
+          if (c < (Dv >> 3)) {
+            const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw[i]);
+            const float2 f0 = __bfloat1622float2(hh[0]), f1 = __bfloat1622float2(hh[1]);
+            const float2 f2 = __bfloat1622float2(hh[2]), f3 = __bfloat1622float2(hh[3]);
+            const float4 p0 = *reinterpret_cast<const float4*>(sdP + c * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(sdP + c * 8 + 4);
+            acc = fmaf(f0.x, p0.x, acc); acc = fmaf(f0.y, p0.y, acc);
+            acc = fmaf(f1.x, p0.z, acc); acc = fmaf(f1.y, p0.w, acc);
+            acc = fmaf(f2.x, p1.x, acc); acc = fmaf(f2.y, p1.y, acc);
+            acc = fmaf(f3.x, p1.z, acc); acc = fmaf(f3.y, p1.w, acc);
+          }
+        }
+      }
+      acc = warp_sum(acc);
+    } else if (k < nb) {
       constexpr int UB = 4;
       for (int c0 = lane; c0 < (Dv >> 3); c0 += 32 * UB) {
         float v[UB][8];

@@ -155,12 +155,36 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_fwd_pipe_kernel(PipeFwdArg
   const float inv_keep = 1.0f / a.keep;
   const float bias = a.att_b[0];
   unsigned int vc = 0;
+  // sample-independent coefficients stay in registers for the whole kernel (D <= 2 * AP_CONSUMERS: two columns per
+  // thread); the per-sample hq values are fetched at the top of each sample, ahead of the statistics pass that hides
+  // their latency (ncu: long-scoreboard stalls of the coefficient set-up)
+  const bool coef_regs = D <= 2 * AP_CONSUMERS;
+  float g_r[2] = {0.f, 0.f}, be_r[2] = {0.f, 0.f}, w_r[2] = {0.f, 0.f};
+  if (coef_regs) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int d = tid + q * AP_CONSUMERS;
+      if (d < D) {
+        g_r[q] = a.gamma[d];
+        be_r[q] = a.beta[d];
+        w_r[q] = a.att_w[d] * inv_keep;
+      }
+    }
+  }
   for (int i = 0; i < n_my; ++i) {
     const int b = first + i * stride;
     const int j = i & 1;
     const bf16* zs = reinterpret_cast<const bf16*>(zbuf + static_cast<size_t>(j) * zbytes);
     int nb = a.nbox[b];
     nb = nb < 0 ? 0 : (nb > K ? K : nb);
+    float hq_r[2] = {0.f, 0.f};
+    if (coef_regs) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int d = tid + q * AP_CONSUMERS;
+        if (d < D) hq_r[q] = a.hq[static_cast<long long>(b) * D + d];
+      }
+    }
     ptx::mbar_wait(&zfull[j], (i >> 1) & 1);
 
     // ---- statistics over the K*D slab (one pass, Chan merge) ----
@@ -198,11 +222,24 @@ __global__ void __launch_bounds__(AP_THREADS, 1) attn_fwd_pipe_kernel(PipeFwdArg
     }
     cons_bar();
     const float mu = red[60], rstd = red[61];
-    for (int d = tid; d < D; d += AP_CONSUMERS) {
-      const float g = a.gamma[d] * rstd;
-      cA[d] = g;
-      cB[d] = a.beta[d] - mu * g;
-      cC[d] = a.hq[static_cast<long long>(b) * D + d] * a.att_w[d] * inv_keep;
+    if (coef_regs) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int d = tid + q * AP_CONSUMERS;
+        if (d < D) {
+          const float g = g_r[q] * rstd;
+          cA[d] = g;
+          cB[d] = be_r[q] - mu * g;
+          cC[d] = hq_r[q] * w_r[q];
+        }
+      }
+    } else {
+      for (int d = tid; d < D; d += AP_CONSUMERS) {
+        const float g = a.gamma[d] * rstd;
+        cA[d] = g;
+        cB[d] = a.beta[d] - mu * g;
+        cC[d] = a.hq[static_cast<long long>(b) * D + d] * a.att_w[d] * inv_keep;
+      }
     }
     cons_bar();
 
