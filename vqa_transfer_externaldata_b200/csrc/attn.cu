@@ -44,6 +44,11 @@ __device__ __forceinline__ void load8(const float* p, float (&x)[8]) {
   x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
   x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
 }
+__device__ __forceinline__ void ld8f(const float* p, float (&x)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
+  x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+}
 // features are streamed once per pass: read-only path
 __device__ __forceinline__ void load8_planes(const bf16* hi, const bf16* lo, long long off,
                                              float (&x)[8]) {
@@ -469,11 +474,8 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
       const int c = tc + i * CW;
       if (c >= CH) break;
       float g[8], bt[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        g[j] = a.gamma[c * 8 + j];
-        bt[j] = a.beta[c * 8 + j];
-      }
+      ld8f(a.gamma + c * 8, g);   // two 128-bit loads per array instead of eight scalar ones
+      ld8f(a.beta + c * 8, bt);
       constexpr int UD = SLAB ? 2 : 3;
       for (int k0 = tr; k0 < nb; k0 += RP * UD) {
         float xb[UD][8];
@@ -535,6 +537,10 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
     for (int i = 0; i < NCOL; ++i) {
       const int c = tc + i * CW;
       if (c >= CH) break;
+      float w8[8], hq8[8], gm8[8];
+      ld8f(a.att_w + c * 8, w8);
+      ld8f(a.hq + static_cast<long long>(b) * D + c * 8, hq8);
+      ld8f(a.gamma + c * 8, gm8);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float T = 0.f, U = 0.f, Vv = 0.f;
@@ -545,7 +551,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
           Vv += colacc[(2 * ATT_THREADS + t2) * 8 * NCOL + i * 8 + j];
         }
         const int d = c * 8 + j;
-        const float w = a.att_w[d], hq = a.hq[static_cast<long long>(b) * D + d], gm = a.gamma[d];
+        const float w = w8[j], hq = hq8[j], gm = gm8[j];
         const float whk = w * hq * inv_keep;
         a.d_hq[static_cast<long long>(b) * D + d] = T * w * inv_keep;  // sum_k dF * hv
         part[d] = T * hq * inv_keep;                                   // dw partial
@@ -564,11 +570,12 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
     for (int i = 0; i < NCOL; ++i) {
       const int c = tc + i * CW;
       if (c >= CH) break;
+      float w8[8], hq8[8], gm8[8];
+      ld8f(a.att_w + c * 8, w8);
+      ld8f(a.hq + static_cast<long long>(b) * D + c * 8, hq8);
+      ld8f(a.gamma + c * 8, gm8);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int d = c * 8 + j;
-        G[i][j] = a.att_w[d] * a.hq[static_cast<long long>(b) * D + d] * inv_keep * a.gamma[d];
-      }
+      for (int j = 0; j < 8; ++j) G[i][j] = w8[j] * hq8[j] * inv_keep * gm8[j];
     }
   }
   s1 = warp_sum(s1);
