@@ -88,3 +88,27 @@ def test_tfrecord_batches_feed_the_model(tmp_path):
     ref = model.output["logit"].clone()
     model.forward(rb)     # T of this batch = its longest question (padded_batch), not the configured maximum
     assert torch.allclose(model.output["logit"], ref, rtol=1e-5, atol=1e-5)
+
+
+def test_checkpoint_bundle_round_trip(tmp_path):
+    """Model.save_checkpoint / load_checkpoint: TensorFlow's tensor-bundle files keyed by the reference's variable
+    names (vqa/trainer.py:141-147, 173-186); a model restored from the bundle computes the same logits."""
+    config, feats, batch, _ = make_synthetic_config(SMALL, variant="vlmap_answer_vqa_all", precision="bf16", seed=9, num_images=16)
+    cls = importer.get_model_class("vlmap_answer_vqa_all")
+    m1 = cls(batch, config, is_train=True, image_features=feats)
+    m1.train_step()
+    m1.train_step()
+    prefix = str(tmp_path / "model-2")
+    m1.save_checkpoint(prefix)
+    from vqa_transfer_externaldata_b200 import tf_bundle
+    names = set(tf_bundle.read_bundle(prefix))
+    assert {"global_step", "LearnGloVe/embed_map", "encode_L/rnn/gru_cell/gates/kernel", "WordWeightAnswer/fc/weights",
+            "TunedWordWeightAnswer/fc/biases", "tuned_joint_fc/LayerNorm/gamma"} <= names
+    config2, _, _, _ = make_synthetic_config(SMALL, variant="vlmap_answer_vqa_all", precision="bf16", seed=77, num_images=16)
+    m2 = cls(batch, config2, is_train=False, image_features=feats)     # different initial weights
+    m2.load_checkpoint(prefix)
+    assert m2.global_step == 2
+    m1.forward(batch)
+    m2.seed, m2.global_step = m1.seed, m1.global_step                   # same dropout draw
+    m2.forward(batch)
+    assert torch.equal(m1.output["logit"], m2.output["logit"])

@@ -185,6 +185,23 @@ class Model(object):
                 self.dead_variables[name] = np.asarray(state[name], np.float32).copy()
         self.engine.prepare_params()
 
+    def save_checkpoint(self, prefix):
+        """tf.train.Saver.save equivalent (vqa/trainer.py:141-147): `<prefix>.index` + `<prefix>.data-00000-of-00001`
+        in TensorFlow's tensor-bundle format, variables under their reference names plus `global_step`."""
+        from . import tf_bundle
+        sd = self.state_dict()
+        sd["global_step"] = np.asarray(self.global_step, np.int64)
+        tf_bundle.write_bundle(prefix, sd)
+
+    def load_checkpoint(self, prefix, strict=True):
+        """Restore from a TensorFlow checkpoint bundle by variable name (vqa/trainer.py:173-186); optimizer slots and
+        other variables the path does not own are ignored."""
+        from . import tf_bundle
+        state = tf_bundle.read_bundle(prefix)
+        if "global_step" in state:
+            self.global_step = int(state["global_step"])
+        self.load_state_dict(state, strict=strict)
+
     # ---- running the path --------------------------------------------------------------------------
     def attach_data_parallel(self, dp):
         self._dp = dp
