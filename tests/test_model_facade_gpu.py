@@ -105,6 +105,7 @@ def test_checkpoint_bundle_round_trip(tmp_path):
     assert {"global_step", "LearnGloVe/embed_map", "encode_L/rnn/gru_cell/gates/kernel", "WordWeightAnswer/fc/weights",
             "TunedWordWeightAnswer/fc/biases", "tuned_joint_fc/LayerNorm/gamma"} <= names
     config2, _, _, _ = make_synthetic_config(SMALL, variant="vlmap_answer_vqa_all", precision="bf16", seed=77, num_images=16)
+    config2.answer_exist_mask = config.answer_exist_mask              # same exported word-weight vocabulary
     m2 = cls(batch, config2, is_train=False, image_features=feats)     # different initial weights
     m2.load_checkpoint(prefix)
     assert m2.global_step == 2
