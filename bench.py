@@ -56,56 +56,93 @@ def ncu_traffic(dom):
     return None
 
 
+_SAMPLER_SRC = r"""
+import sys, time
+import pynvml as n
+n.nvmlInit()
+h = n.nvmlDeviceGetHandleByIndex(int(sys.argv[1]))
+mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+while True:
+    print(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, n.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons(h)), flush=True)
+    time.sleep(0.01)
+"""
+
+
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed regions."""
+    """SM clock / power / throttle reasons sampled DURING the timed regions, every 10 ms, by a helper PROCESS that
+    holds an NVML handle (nvidia_ml_py). Why not `nvidia-smi -lms`: it initialises NVML inside the timed region and
+    stretched the end-to-end loop by ~10 %; why not a thread of this process: it competes with the enqueue loop for
+    the GIL (scripts/gpu_e2e_probe.py: the same loop runs 1.04 ms/step unobserved). start() returns once the helper
+    has delivered its first sample, i.e. after its NVML initialisation. nvidia-smi stays the fallback."""
+
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
-        self.rows = []
+        self.rows = []          # (sm MHz, max MHz, watts, reasons bitmask)
         self.proc = None
+        self.source = None
+        self._first = threading.Event()
 
     def start(self):
-        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-             "clocks_event_reasons.sw_power_cap")
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
-                 str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except OSError:
-            self.proc = None
+            import pynvml  # noqa: F401 -- only to know the helper can import it
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.source = "nvml"
+        except Exception:  # noqa: BLE001
+            q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_power_cap")
+            try:
+                self.proc = subprocess.Popen(
+                    ["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i",
+                     str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                self.source = "nvidia-smi"
+            except OSError:
+                self.proc = None
+                return
+        self.thread = threading.Thread(target=self._read, daemon=True)
+        self.thread.start()
+        self._first.wait(timeout=10.0)
 
     def _read(self):
+        bits = [0x8, 0x40, 0x20, 0x4]
         for line in self.proc.stdout:
-            self.rows.append(line.strip())
+            try:
+                if self.source == "nvml":
+                    f = line.split()
+                    self.rows.append((float(f[0]), float(f[1]), float(f[2]), int(f[3])))
+                else:
+                    f = [x.strip() for x in line.strip().split(",")]
+                    mask = sum(bit for bit, v in zip(bits, f[3:7]) if v.lower().startswith("active"))
+                    self.rows.append((float(f[0]), float(f[1]), float(f[2]), mask))
+                self._first.set()
+            except (ValueError, IndexError):
+                continue
 
     def stop(self):
         if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no NVML / nvidia-smi"]}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
-        except Exception:
+        except Exception:  # noqa: BLE001
             self.proc.kill()
-        sm, mx, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = [r[0] for r in self.rows]
+        power = [r[2] for r in self.rows]
+        reasons = set()
         for r in self.rows:
-            f = [x.strip() for x in r.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
-            except ValueError:
-                continue
-            for n, v in zip(names, f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(n)
+            for bit, name in self.REASONS.items():
+                if r[3] & bit:
+                    reasons.add(name)
         # samples under load only: the SM clock idles low between regions
-        load = [s for s, p in zip(sm, power) if p > 300.0] or sm
-        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+        load = [s_ for s_, p_ in zip(sm, power) if p_ > 300.0] or sm
+        return {"sm_mhz": float(np.median(load)) if load else None,
+                "sm_max_mhz": max(r[1] for r in self.rows) if self.rows else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons),
+                "source": self.source}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -239,7 +276,6 @@ def run_ours(args):
     sampler = ClockSampler(dp.local_rank)
     if rank == 0:
         sampler.start()
-        time.sleep(0.3)
     ms_value, launches = timed(step_resident, args.steps)
 
     # end to end through the public API (Model.train_step): every step uploads ITS batch from pinned host
