@@ -163,6 +163,10 @@ typedef struct VqaFeatureBank {
   const float* features;    /* image_features [N, K, Dv] fp32                                 */
   const int32_t* num_boxes; /* num_boxes      [N]                                             */
   int64_t num_images;       /* N                                                              */
+  const void* features_bf16; /* optional one-off bf16 copy of image_features [N, K, Dv] (vqa_split_bf16): in bf16 mode
+                              * the per-step gather then copies bf16 rows (half the bytes read); the rounding is the
+                              * same fp32 -> bf16 conversion done once instead of every step, so results are identical.
+                              * NULL = gather from the fp32 bank. Ignored in fp32 mode.                            */
 } VqaFeatureBank;
 
 /* One batch, keys as in vqa/datasets/input_ops_vqa_tf_record_memft.py:47-59 */

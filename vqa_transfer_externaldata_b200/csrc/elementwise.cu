@@ -52,6 +52,23 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long long rows,
   }
 }
 
+// the same gather from the one-off bf16 copy of the bank: a 16-byte row copy
+__global__ void gather_features_bf16_kernel(const bf16* __restrict__ bank, const int* __restrict__ num_boxes,
+                                            const long long* __restrict__ image_idx, int batch, long long per_image8,
+                                            bf16* __restrict__ v_hi, int* __restrict__ nbox) {
+  pdl_sync();
+  for (int b = blockIdx.y; b < batch; b += gridDim.y) {
+    const long long img = image_idx[b];
+    if (blockIdx.x == 0 && threadIdx.x == 0) nbox[b] = num_boxes[img];
+    const uint4* src = reinterpret_cast<const uint4*>(bank) + img * per_image8;
+    uint4* dst = reinterpret_cast<uint4*>(v_hi) + static_cast<long long>(b) * per_image8;
+#pragma unroll 4
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < per_image8;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+      dst[i] = __ldg(src + i);
+  }
+}
+
 // V[b] = features[image_idx[b]] (vqa/model_vlmap_answer.py:110-123) written as GEMM operand planes
 __global__ void gather_features_kernel(const float* __restrict__ bank, const int* __restrict__ num_boxes,
                                        const long long* __restrict__ image_idx, int batch,
@@ -271,6 +288,18 @@ VqaStatus split_bf16_launch(const float* src, long long rows, long long cols, lo
   launch_pdl(split_bf16_kernel, dim3(grid_for(rows * cols / 4, 256)), dim3(256), 0, s, src, rows, cols / 4, ld, hi, lo,
              ld_out);
   VQA_LAUNCH_CHECK("split_bf16");
+  return VQA_OK;
+}
+
+VqaStatus gather_features_bf16_launch(const bf16* bank, const int* num_boxes, const long long* image_idx, int batch,
+                                      int K, int Dv, bf16* v_hi, int* nbox, cudaStream_t s) {
+  if (batch == 0) return VQA_OK;
+  const long long per_image8 = static_cast<long long>(K) * Dv / 8;
+  int gx = static_cast<int>((per_image8 + 255) / 256);
+  if (gx > 8) gx = 8;
+  launch_pdl(gather_features_bf16_kernel, dim3(gx, batch), dim3(256), 0, s, bank, num_boxes, image_idx, batch, per_image8,
+             v_hi, nbox);
+  VQA_LAUNCH_CHECK("gather_features (bf16 bank)");
   return VQA_OK;
 }
 

@@ -233,6 +233,9 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     std::swap(b.v, b.v_alt);
     std::swap(b.nbox, b.nbox_alt);
     VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_prefetch, 0));
+  } else if (bank->features_bf16 && !fp32) {
+    VQA_TRY(gather_features_bf16_launch(static_cast<const bf16*>(bank->features_bf16), bank->num_boxes,
+                                        reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi, b.nbox, s));
   } else {
     VQA_TRY(gather_features_launch(bank->features, bank->num_boxes,
                                    reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi,

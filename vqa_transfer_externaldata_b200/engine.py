@@ -4,6 +4,7 @@ PyTorch is plumbing here (device memory, streams, pinned staging buffers, torch.
 kernel on the path is in libvqa_answer_b200.so and is reached through ctypes with raw pointers.
 """
 import ctypes as C
+import os
 from dataclasses import dataclass, asdict
 
 import numpy as np
@@ -294,7 +295,6 @@ class Engine:
         self.masks = None
         self.adam_t = 0
         self.early_gradients = False
-        import os
         # cross-step feature prefetch (vqa_prefetch_features): bit-identical results, but measured no faster on B200
         # (1.100 ms/step on vs 1.078 off: the background gather and the step's own kernels share the same HBM and
         # SMs), so it is opt-in
@@ -320,9 +320,19 @@ class Engine:
             raise ValueError(f"feature bank shape {tuple(f.shape)} != [N, {self.cfg.K}, {self.cfg.Dv}]")
         self.bank_features = f.to(self.device, dtype=torch.float32).contiguous()
         self.bank_num_boxes = torch.as_tensor(np.asarray(num_boxes)).to(self.device, dtype=torch.int32).contiguous()
+        # bf16 mode: a one-off bf16 copy of the bank (the very conversion the per-step gather would do, done once), so
+        # the gather reads half the bytes. VQA_BANK_BF16=0 keeps the fp32-only layout.
+        self.bank_bf16 = None
+        if self.cfg.precision == "bf16" and os.environ.get("VQA_BANK_BF16", "1") != "0":
+            n = self.bank_features.numel()
+            self.bank_bf16 = torch.empty(self.bank_features.shape, dtype=torch.bfloat16, device=self.device)
+            cols = self.cfg.K * self.cfg.Dv
+            L.check(self.lib.vqa_split_bf16(self.h, self.bank_features.data_ptr(), n // cols, cols, cols,
+                                            self.bank_bf16.data_ptr(), None, cols, self._stream()))
         self.bank = L.VqaFeatureBank(features=self.bank_features.data_ptr(),
                                      num_boxes=self.bank_num_boxes.data_ptr(),
-                                     num_images=self.bank_features.shape[0])
+                                     num_images=self.bank_features.shape[0],
+                                     features_bf16=self.bank_bf16.data_ptr() if self.bank_bf16 is not None else None)
 
     def set_answer_masks(self, is_object, is_attribute, answer_exist):
         dev = self.device

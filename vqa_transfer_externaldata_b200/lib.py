@@ -89,7 +89,8 @@ class VqaParams(C.Structure):
 
 
 class VqaFeatureBank(C.Structure):
-    _fields_ = [("features", C.c_void_p), ("num_boxes", C.c_void_p), ("num_images", C.c_int64)]
+    _fields_ = [("features", C.c_void_p), ("num_boxes", C.c_void_p), ("num_images", C.c_int64),
+                ("features_bf16", C.c_void_p)]
 
 
 class VqaBatch(C.Structure):
