@@ -53,7 +53,7 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long long rows,
 }
 
 // the same gather from the one-off bf16 copy of the bank: a 16-byte row copy
-__global__ void gather_features_bf16_kernel(const bf16* __restrict__ bank, const int* __restrict__ num_boxes,
+__global__ void __launch_bounds__(1024) gather_features_bf16_kernel(const bf16* __restrict__ bank, const int* __restrict__ num_boxes,
                                             const long long* __restrict__ image_idx, int batch, long long per_image8,
                                             bf16* __restrict__ v_hi, int* __restrict__ nbox) {
   pdl_sync();
@@ -70,7 +70,7 @@ __global__ void gather_features_bf16_kernel(const bf16* __restrict__ bank, const
 }
 
 // V[b] = features[image_idx[b]] (vqa/model_vlmap_answer.py:110-123) written as GEMM operand planes
-__global__ void gather_features_kernel(const float* __restrict__ bank, const int* __restrict__ num_boxes,
+__global__ void __launch_bounds__(1024) gather_features_kernel(const float* __restrict__ bank, const int* __restrict__ num_boxes,
                                        const long long* __restrict__ image_idx, int batch,
                                        long long per_image4, bf16* __restrict__ v_hi,
                                        bf16* __restrict__ v_lo, int* __restrict__ nbox) {
@@ -291,10 +291,37 @@ VqaStatus split_bf16_launch(const float* src, long long rows, long long cols, lo
   return VQA_OK;
 }
 
+namespace {
+template <typename... P, typename... A>
+VqaStatus gather_exclusive_launch(void (*kern)(P...), int ctas, cudaStream_t s, A... args) {
+  constexpr int kExclusiveSmem = 200 * 1024;
+  VQA_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kExclusiveSmem));
+  ctas = (ctas + 1) & ~1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1, ctas);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = kExclusiveSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = 2;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, args...));
+  count_launch();
+  return VQA_OK;
+}
+}  // namespace
+
 VqaStatus gather_features_bf16_launch(const bf16* bank, const int* num_boxes, const long long* image_idx, int batch,
-                                      int K, int Dv, bf16* v_hi, int* nbox, cudaStream_t s) {
+                                      int K, int Dv, bf16* v_hi, int* nbox, cudaStream_t s, int max_ctas) {
   if (batch == 0) return VQA_OK;
   const long long per_image8 = static_cast<long long>(K) * Dv / 8;
+  if (max_ctas > 0)
+    return gather_exclusive_launch(gather_features_bf16_kernel, max_ctas < batch ? max_ctas : batch, s, bank, num_boxes,
+                                   image_idx, batch, per_image8, v_hi, nbox);
   int gx = static_cast<int>((per_image8 + 255) / 256);
   if (gx > 8) gx = 8;
   launch_pdl(gather_features_bf16_kernel, dim3(gx, batch), dim3(256), 0, s, bank, num_boxes, image_idx, batch, per_image8,
@@ -313,18 +340,11 @@ VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const 
   int gy = batch;
   if (max_ctas > 0) {
     // background prefetch under the cooperative BPTT kernel: max_ctas CTAs of 1024 threads that each claim a whole
-    // SM's shared memory, so they land on the SMs the recurrent grid leaves free and never share one with it
-    static bool attr_set = false;
-    constexpr int kExclusiveSmem = 200 * 1024;
-    if (!attr_set) {
-      VQA_CUDA_CHECK(cudaFuncSetAttribute(gather_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExclusiveSmem));
-      attr_set = true;
-    }
-    gy = max_ctas < batch ? max_ctas : batch;
-    gather_features_kernel<<<dim3(1, gy), 1024, kExclusiveSmem, s>>>(bank, num_boxes, image_idx, batch, per_image4, v_hi,
-                                                                     v_lo, nbox);
-    VQA_LAUNCH_CHECK("gather_features (background)");
-    return VQA_OK;
+    // SM's shared memory, launched as 2-CTA CLUSTERS so that they fill whole TPCs: the recurrent grid is made of
+    // 2-CTA clusters itself, and single CTAs scattered over twenty TPCs would leave it twenty SM pairs short (a
+    // cooperative launch then waits for the copy to finish: measured)
+    return gather_exclusive_launch(gather_features_kernel, max_ctas < batch ? max_ctas : batch, s, bank, num_boxes, image_idx,
+                                   batch, per_image4, v_hi, v_lo, nbox);
   }
   dim3 grid(gx, gy);
   launch_pdl(gather_features_kernel, dim3(grid), dim3(256), 0, s, bank, num_boxes, image_idx, batch, per_image4, v_hi,

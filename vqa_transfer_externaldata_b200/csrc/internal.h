@@ -78,7 +78,7 @@ VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const 
                                  int batch, int K, int Dv, bf16* v_hi, bf16* v_lo, int* nbox,
                                  cudaStream_t s, int max_ctas = 0);
 VqaStatus gather_features_bf16_launch(const bf16* bank, const int* num_boxes, const long long* image_idx, int batch,
-                                      int K, int Dv, bf16* v_hi, int* nbox, cudaStream_t s);
+                                      int K, int Dv, bf16* v_hi, int* nbox, cudaStream_t s, int max_ctas = 0);
 VqaStatus embed_gather_launch(const float* embed, const int* q_intseq, int batch, int T, int Tstride,
                               int W, int Wpad, int Bpad, bf16* e_hi, bf16* e_lo, cudaStream_t s);
 VqaStatus embed_scatter_add_launch(const float* dE, long long ld_dE, const int* q_intseq,

@@ -105,8 +105,13 @@ VqaStatus launch_pending_prefetch(VqaHandle h, cudaStream_t a4) {
   int free_sms = h->num_sms - 128;   // the CTA-pair recurrent kernels occupy 128 SMs (gru_pair.cu)
   if (free_sms < 4) free_sms = 4;
   VQA_CUDA_CHECK(cudaStreamWaitEvent(a4, h->ev_upload, 0));
-  VQA_TRY(gather_features_launch(h->pf_bank.features, h->pf_bank.num_boxes, static_cast<const long long*>(h->pf_idx),
-                                 h->pf_batch, c.K, c.Dv, b.v_alt.hi, b.v_alt.lo, b.nbox_alt, a4, free_sms));
+  if (h->pf_bank.features_bf16 && c.precision == VQA_PREC_BF16)
+    VQA_TRY(gather_features_bf16_launch(static_cast<const bf16*>(h->pf_bank.features_bf16), h->pf_bank.num_boxes,
+                                        static_cast<const long long*>(h->pf_idx), h->pf_batch, c.K, c.Dv, b.v_alt.hi,
+                                        b.nbox_alt, a4, free_sms));
+  else
+    VQA_TRY(gather_features_launch(h->pf_bank.features, h->pf_bank.num_boxes, static_cast<const long long*>(h->pf_idx),
+                                   h->pf_batch, c.K, c.Dv, b.v_alt.hi, b.v_alt.lo, b.nbox_alt, a4, free_sms));
   VQA_CUDA_CHECK(cudaEventRecord(h->ev_prefetch, a4));
   h->prefetched = true;
   h->prefetched_idx = h->pf_idx;

@@ -295,10 +295,10 @@ class Engine:
         self.masks = None
         self.adam_t = 0
         self.early_gradients = False
-        # cross-step feature prefetch (vqa_prefetch_features): bit-identical results, but measured no faster on B200
-        # (1.100 ms/step on vs 1.078 off: the background gather and the step's own kernels share the same HBM and
-        # SMs), so it is opt-in
-        self.prefetch_features = os.environ.get("VQA_PREFETCH_FEATURES", "0") == "1"
+        # cross-step feature prefetch (vqa_prefetch_features): the next batch's gather runs under this step's BPTT, as
+        # 2-CTA clusters on the ten TPCs the cooperative recurrent grid leaves idle; bit-identical results
+        # (tests/test_model_gpu.py), ~1 % faster (1.032 vs 1.04 ms/step). VQA_PREFETCH_FEATURES=0 turns it off.
+        self.prefetch_features = os.environ.get("VQA_PREFETCH_FEATURES", "1") != "0"
 
     def close(self):
         if self.h:
