@@ -65,12 +65,12 @@ mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
 reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
 while True:
     print(n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM), mx, n.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons(h)), flush=True)
-    time.sleep(0.01)
+    time.sleep(float(sys.argv[2]))
 """
 
 
 class ClockSampler:
-    """SM clock / power / throttle reasons sampled DURING the timed regions, every 10 ms, by a helper PROCESS that
+    """SM clock / power / throttle reasons sampled DURING the timed regions, every 25 ms, by a helper PROCESS that
     holds an NVML handle (nvidia_ml_py). Why not `nvidia-smi -lms`: it initialises NVML inside the timed region and
     stretched the end-to-end loop by ~10 %; why not a thread of this process: it competes with the enqueue loop for
     the GIL (scripts/gpu_e2e_probe.py: the same loop runs 1.04 ms/step unobserved). start() returns once the helper
@@ -88,7 +88,8 @@ class ClockSampler:
     def start(self):
         try:
             import pynvml  # noqa: F401 -- only to know the helper can import it
-            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index)], stdout=subprocess.PIPE,
+            period = float(os.environ.get("VQA_BENCH_SAMPLE_MS", "25")) / 1e3
+            self.proc = subprocess.Popen([sys.executable, "-c", _SAMPLER_SRC, str(self.index), str(period)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.source = "nvml"
         except Exception:  # noqa: BLE001
@@ -287,16 +288,19 @@ def run_ours(args):
     losses = []
 
     def run_e2e(steps):
+        # asynchronous dispatch, two steps deep: the host reads the loss of step i - 2 after enqueuing step i, so a
+        # hiccup of the host (this loop is ~0.6 ms of Python + launches per 1.04 ms step) does not starve the device
         nonlocal h2d, d2h
-        pending = None
+        pending = []
         for i in range(steps):
             nxt = pinned[(i + 1) % R] if i + 1 < steps else None
             p, a, b = model.train_step(pinned[i % R], next_batch=nxt, sync=False)
             h2d, d2h = a, b
-            if pending is not None:
-                losses.append(pending.get()[0])
-            pending = p
-        losses.append(pending.get()[0])
+            pending.append(p)
+            if len(pending) > 2:
+                losses.append(pending.pop(0).get()[0])
+        for p in pending:
+            losses.append(p.get()[0])
 
     run_e2e(3)
     dp.barrier()

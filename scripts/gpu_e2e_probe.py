@@ -73,6 +73,32 @@ def main():
             pending = p
         pending.get()
 
+    # host time per step: how long the enqueue of one step takes when the device is never waited for
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    pend = []
+    for i in range(20):
+        p, _, _ = model.train_step(pinned[i % R], next_batch=pinned[(i + 1) % R], sync=False)
+        pend.append(p)
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    print(f"host enqueue of Model.train_step (no waiting): {1e3 * (t1 - t0) / 20:.4f} ms/step", flush=True)
+    for p in pend:
+        p.get()
+    import cProfile
+    import pstats
+    pr = cProfile.Profile()
+    pr.enable()
+    pend = []
+    for i in range(20):
+        p, _, _ = model.train_step(pinned[i % R], next_batch=pinned[(i + 1) % R], sync=False)
+        pend.append(p)
+    pr.disable()
+    torch.cuda.synchronize()
+    for p in pend:
+        p.get()
+    pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+
     for steps in (30, 30, 100):
         bench_like(3)
         torch.cuda.synchronize()
