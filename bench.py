@@ -44,7 +44,7 @@ def load_peaks():
 
 def ncu_traffic(dom):
     """DRAM bytes of the dominant launch from the committed `ncu --set full` capture (None if absent)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary_v4.json")
+    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary_v5.json")
     want = "v_linear_v wgrad" if dom == "vproj_wgrad" else "v_linear_v forward"
     try:
         with open(p) as f:
@@ -353,7 +353,7 @@ def run_ours(args):
     kern = "gemm_pair_kernel" if args.precision == "bf16" else "gemm_bf16_tcgen05_kernel"
     roofline = {"bound": "tensor", "kernel": f"{kern} ({dom})", "achieved": ach, "peak": peak_tc,
                 "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": ncu_traffic(dom) if args.precision == "bf16" else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch, profiles/r01_ncu_full_summary_v4.json",
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch, profiles/r01_ncu_full_summary_v5.json",
                 "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)"}
     zb = 2 if args.precision == "bf16" else 4     # bytes / element of the stored pre-LN projection
     vb = 2 if args.precision == "bf16" else 4     # gathered features: bf16 plane (fp32 mode: hi + lo planes)
