@@ -249,7 +249,7 @@ def run_ours(args):
         # batch i+1's buffers + feature gather are issued right after this step's forward
         eng.stage_batch(dev_batches[i % R])
         rk = dp.rank if world > 1 else 0
-        eng.forward(seed=model.seed + 7919 * rk, step=model.global_step, full_outputs=False)
+        eng.forward(seed=model.seed + 7919 * rk, step=model.global_step, full_outputs=False, defer_outputs=True)
         eng.prefetch_batch(dev_batches[(i + 1) % R])
         model.backward()
         eng.adam_step(lr=1e-3, clip_norm=20.0)

@@ -286,6 +286,14 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* params, const VqaBa
 VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch, uint64_t seed, uint64_t step,
                                         uint8_t* mask, void* stream);
 
+/* Deferred outputs (training loops): nothing downstream of the logits needs the loss / metrics kernels -- the backward
+ * pass recomputes d(logits) from the logits -- so with this enabled vqa_forward enqueues them (and the copies into
+ * VqaOutputs) on an auxiliary stream, and the following vqa_backward joins that stream before it returns: loss, report,
+ * pred, ... are valid on `stream` AFTER vqa_backward instead of after vqa_forward. A forward that is not followed by a
+ * backward is joined by the next vqa_forward, or explicitly by vqa_sync_outputs(h, stream). Off by default. */
+VQA_API VqaStatus vqa_set_deferred_outputs(VqaHandle h, int32_t enable);
+VQA_API VqaStatus vqa_sync_outputs(VqaHandle h, void* stream);
+
 /* Data-parallel overlap (vqa/trainer.py has no distributed code; this is the B200 side of SURVEY 8e).
  * With early gradients enabled, vqa_backward produces the gradients of everything EXCEPT the embedding and the GRU
  * (v_linear_v, q_linear_v, the attention score layer, and the trainable heads of model_standard) BEFORE the GRU's

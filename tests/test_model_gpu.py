@@ -312,3 +312,27 @@ def test_feature_prefetch_across_steps_is_bit_identical():
             assert (g0[f] - g1[f]).abs().max().item() <= 1e-5 * g0[f].abs().max().item()
         else:
             assert torch.equal(g0[f], g1[f]), f
+
+
+def test_deferred_outputs_are_identical_after_backward():
+    """vqa_set_deferred_outputs: loss / report / pred of a training step are produced on an auxiliary stream and are
+    valid after vqa_backward; they equal what an undeferred forward produces, and so do the gradients."""
+    case = build_case(SMALL, variant="vlmap_answer_full", precision="bf16", seed=43)
+    eng = case["eng"]
+    eng.stage_batch(case["batch"])
+
+    def run(defer):
+        eng.forward(seed=11, step=4, full_outputs=True, defer_outputs=defer)
+        eng.backward()
+        loss, report = eng.read_scalars()
+        return (loss, report, eng.outputs()["pred"].clone(), eng.outputs()["logit"].clone(),
+                {f: g.clone() for f, g in eng.params.grad_views.items() if f != "embed"})
+
+    l0, r0, p0, x0, g0 = run(False)
+    l1, r1, p1, x1, g1 = run(True)
+    assert l0 == l1 and r0 == r1 and torch.equal(p0, p1) and torch.equal(x0, x1)
+    assert all(torch.equal(g0[f], g1[f]) for f in g0)
+    # a deferred forward that no backward follows is joined by the next entry point that needs the outputs
+    eng.forward(seed=11, step=4, full_outputs=True, defer_outputs=True)
+    l2, r2 = eng.read_scalars()
+    assert l2 == l0 and r2 == r0

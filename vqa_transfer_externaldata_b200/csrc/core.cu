@@ -294,9 +294,13 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   h->prefetched_batch = 0;
   h->pf_pending = false;
   h->pf_joined = true;
+  h->defer_outputs = false;
+  h->outputs_pending = false;
+  h->pack_pending = false;
   if (cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming) != cudaSuccess) {
+      cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming) != cudaSuccess) {
     delete h;
     return set_error(VQA_ERR_CUDA, "vqa_create: could not create the early-gradient event");
   }
@@ -315,6 +319,7 @@ VQA_API VqaStatus vqa_destroy(VqaHandle h) {
     cudaEventDestroy(h->ev_early);
     cudaEventDestroy(h->ev_prefetch);
     cudaEventDestroy(h->ev_upload);
+    cudaEventDestroy(h->ev_pack);
   }
   if (h && h->aux_created)
     for (int i = 0; i < VqaHandle_t::kAux; ++i) {

@@ -135,6 +135,13 @@ struct VqaHandle_t {
   const void* pf_idx;
   int pf_batch;
   cudaEvent_t ev_upload;   // image_idx of the next batch is on the device
+  // vqa_set_deferred_outputs: loss / metrics kernels and output copies of vqa_forward run on auxiliary stream 1 and are
+  // joined by the following vqa_backward (or the next entry point that needs them)
+  bool defer_outputs;
+  bool outputs_pending;
+  // the GRU weight repack after an optimizer step runs on auxiliary stream 2; the next forward's GRU waits for it
+  bool pack_pending;
+  cudaEvent_t ev_pack;
   bool early_grads;        // vqa_set_early_gradients
   cudaEvent_t ev_early;    // recorded by vqa_backward once the non-GRU gradients are complete
   // optional per-phase timing

@@ -201,6 +201,10 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   h->fwd_valid = false;
   if (Bn == 0) return VQA_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->outputs_pending) {   // deferred outputs of a forward that no backward pass followed
+    VQA_TRY(join_stream(h, 1, s));
+    h->outputs_pending = false;
+  }
   Buffers& b = h->buf;
   const int K = c.K, Dv = c.Dv, D = c.D, L = c.L, J = c.J, A = c.A, W = c.W, Wp = h->Wpad;
   const bool fp32 = c.precision == VQA_PREC_FP32;
@@ -276,6 +280,10 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_END(VQA_PH_VPROJ_FWD);
   VQA_TRY(join_stream(h, 0, s));
   PH_BEGIN(VQA_PH_GRU_FWD);
+  if (h->pack_pending) {   // the repack of the GRU weights after the last optimizer step ran on an auxiliary stream
+    VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_pack, 0));
+    h->pack_pending = false;
+  }
   if (serial) VQA_TRY(gru_inputs(s));  // serialised for per-phase timing
   // a2: the recurrent part of the GRU
   const bool persistent = gru_persistent_supported(Bn, L, c.precision, h->num_sms);
@@ -440,18 +448,28 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_END(VQA_PH_HEAD_FWD);
   PH_BEGIN(VQA_PH_LOSS);
   // a8 + a9: loss, pred, report                                       (:192-288)
+  // Nothing downstream of the logits needs the loss / metrics kernels (the backward pass recomputes d logits from the
+  // logits), so a training step may defer them to auxiliary stream 1 (vqa_set_deferred_outputs): they then run beside
+  // the first kernels of vqa_backward, which joins them.
+  const bool defer = h->defer_outputs && !(h->profile && !h->profile_overlapped);
+  cudaStream_t s_main = s;
+  float* loss_scratch = b.scratch;
+  if (defer) {
+    VQA_TRY(fork_stream(h, 1, s_main, &s));          // `s` is the loss / output stream until the end of this function
+    loss_scratch = b.scratch + b.scratch_floats;      // auxiliary stream 1's scratch region (as in the weight-gradient section)
+  }
   const int use_tm = c.variant != VQA_VARIANT_STANDARD;  // every vlmap_answer* variant masks the loss to the train answers
   if (c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL) {
     // (BCE(fixed) + BCE(fixed + tuned)) * train_mask; pred from fixed + tuned              (_vqa_all.py:234-244)
     VQA_TRY(bce_metrics2_launch(Bn, A, c.num_train_answer, 1, b.logit_total, b.logit1, 1, nullptr, batch->answer_target,
-                                *masks, b.loss, b.report, b.pred, b.per_sample, b.scratch, s));
+                                *masks, b.loss, b.report, b.pred, b.per_sample, loss_scratch, s));
   } else if (c.variant == VQA_VARIANT_VLMAP_ANSWER_VQA_ALL2) {
     // BCE(fixed) * train_mask + BCE(tuned); pred from fixed * test_mask + tuned * train_mask (_vqa_all2.py:231-242)
     VQA_TRY(bce_metrics2_launch(Bn, A, c.num_train_answer, 1, b.logit1, b.tuned, 0, b.pred_logit, batch->answer_target,
-                                *masks, b.loss, b.report, b.pred, b.per_sample, b.scratch, s));
+                                *masks, b.loss, b.report, b.pred, b.per_sample, loss_scratch, s));
   } else {
     VQA_TRY(bce_metrics_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target, *masks, 0.f,
-                               b.loss, b.report, b.pred, b.per_sample, nullptr, nullptr, nullptr, b.scratch, s));
+                               b.loss, b.report, b.pred, b.per_sample, nullptr, nullptr, nullptr, loss_scratch, s));
   }
   if (v_full)   // loss += 0.1 * KL(q_L_mean, q_L_log_sigma_sq); report latent_loss / train_latent_loss  (_full.py:217-223)
     VQA_TRY(latent_finalize_launch(b.kl_rows, Bn, -0.5f, VQA_LATENT_LOSS_WEIGHT, VQA_REPORT_LATENT_LOSS, b.loss, b.report, s));
@@ -469,6 +487,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(copy_out(out->condition, c.variant == VQA_VARIANT_VLMAP_ANSWER2 ? b.qp_f32 : q, sizeof(float) * BL, s));
     VQA_TRY(copy_out(out->pooled, b.pooled, sizeof(float) * Bn * Pd, s));
   }
+  if (defer) h->outputs_pending = true;   // joined by vqa_backward (or by the next vqa_forward / vqa_sync_outputs)
   h->fwd_valid = true;
   h->last_batch = Bn;
   h->last_T = T;
@@ -874,6 +893,10 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(vproj_wgrad(s));
     PH_END(VQA_PH_VPROJ_WGRAD);
   }
+  if (h->outputs_pending) {   // the forward's deferred loss / metrics / output copies (auxiliary stream 1)
+    VQA_TRY(join_stream(h, 1, s));
+    h->outputs_pending = false;
+  }
   return VQA_OK;
 }
 
@@ -1024,9 +1047,33 @@ VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* p, float*
                            h->num_sms, s, &tab));
   for (const Item* it : rest)
     VQA_TRY(split_bf16_launch(it->src, 1, it->elems, it->elems, it->dst->hi, it->dst->lo, it->elems, s));
-  if (gru && gru_persistent_supported(c.B, c.L, c.precision, h->num_sms))
+  if (gru && gru_persistent_supported(c.B, c.L, c.precision, h->num_sms)) {
+    // only the next forward's recurrent kernel reads the packed weights: repack on auxiliary stream 2, under the
+    // first kernels of that forward, which waits for ev_pack right before its GRU launch
+    cudaStream_t sp;
+    VQA_TRY(fork_stream(h, 2, s, &sp));
     VQA_TRY(gru_pack_weights_launch(w.gru_gates_w.hi + static_cast<long long>(c.W) * 2 * c.L,
-                                    w.gru_cand_w.hi + static_cast<long long>(c.W) * c.L, c.L, h->buf.gru_pack, s));
+                                    w.gru_cand_w.hi + static_cast<long long>(c.W) * c.L, c.L, h->buf.gru_pack, sp));
+    if (sp != s) {
+      VQA_CUDA_CHECK(cudaEventRecord(h->ev_pack, sp));
+      h->pack_pending = true;
+    }
+  }
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_set_deferred_outputs(VqaHandle h, int32_t enable) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_set_deferred_outputs: null handle");
+  h->defer_outputs = enable != 0;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_sync_outputs(VqaHandle h, void* stream) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_sync_outputs: null handle");
+  if (h->outputs_pending) {
+    VQA_TRY(join_stream(h, 1, static_cast<cudaStream_t>(stream)));
+    h->outputs_pending = false;
+  }
   return VQA_OK;
 }
 

@@ -205,6 +205,7 @@ class PendingScalars:
         self._slots = slots
         # ONE device->host copy of [loss | report], on the read-back stream: the compute stream only records an event
         # (a copy enqueued on the compute stream itself costs it ~10 us of copy-engine latency per step)
+        eng.sync_outputs()
         main = torch.cuda.current_stream(eng.device)
         eng.d2h_stream.wait_stream(main)
         with torch.cuda.stream(eng.d2h_stream):
@@ -294,6 +295,7 @@ class Engine:
         self.bank = None
         self.masks = None
         self.adam_t = 0
+        self._deferred = False
         self.early_gradients = False
         # cross-step feature prefetch (vqa_prefetch_features): the next batch's gather runs under this step's BPTT, as
         # 2-CTA clusters on the ten TPCs the cooperative recurrent grid leaves idle; bit-identical results
@@ -466,9 +468,14 @@ class Engine:
                           q_intseq_len=bs.d_qlen.data_ptr(), answer_target=bs.d_target.data_ptr())
 
     # ---- the path -------------------------------------------------------------------------------
-    def forward(self, seed=0, step=0, full_outputs=True):
+    def forward(self, seed=0, step=0, full_outputs=True, defer_outputs=False):
+        """defer_outputs: a training step (a backward pass follows): the loss / metrics kernels run on an auxiliary
+        stream beside the start of the backward pass, which joins them (vqa_set_deferred_outputs)."""
         if self.bank is None or self.masks is None:
             raise RuntimeError("set_feature_bank() and set_answer_masks() first")
+        if defer_outputs != self._deferred:
+            L.check(self.lib.vqa_set_deferred_outputs(self.h, int(defer_outputs)))
+            self._deferred = defer_outputs
         b = self._c_batch()
         outs = self._outs if full_outputs else self._outs_min
         if self._last_d2h is not None:   # an asynchronous read-back of the previous loss / report may still be in flight
@@ -541,8 +548,13 @@ class Engine:
         off = ptr.value - self.workspace.data_ptr()
         return self.workspace[off:off + nbytes.value].view(dtype).view(shape).clone()
 
+    def sync_outputs(self):
+        """Join deferred outputs of the last forward into the current stream (no-op otherwise)."""
+        L.check(self.lib.vqa_sync_outputs(self.h, self._stream()))
+
     def read_scalars(self):
         """D2H of loss + report (pinned, synchronises the current stream)."""
+        self.sync_outputs()
         self.h_scalars.copy_(self.o_scalars, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
         vals = self.h_scalars.tolist()

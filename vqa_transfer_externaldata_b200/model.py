@@ -213,12 +213,13 @@ class Model(object):
             dp.use_multicast_gradients(self.engine)   # in-switch all-reduce when NVSwitch multicast is available
         self.engine.set_early_gradients(dp is not None and dp.world_size > 1 and os.environ.get("VQA_DP_EARLY") == "1")
 
-    def forward(self, batch=None, full_outputs=True):
+    def forward(self, batch=None, full_outputs=True, defer_outputs=False):
         """session.run([loss, report, output]) of the reference (vqa/evaler.py:118-123). Returns h2d bytes."""
         b = self.batch if batch is None else batch
         nbytes = self.engine.stage_batch(b)
         rank = self._dp.rank if self._dp is not None else 0
-        self.engine.forward(seed=self.seed + 7919 * rank, step=self.global_step, full_outputs=full_outputs)
+        self.engine.forward(seed=self.seed + 7919 * rank, step=self.global_step, full_outputs=full_outputs,
+                            defer_outputs=defer_outputs)
         self._bind_outputs()
         return nbytes
 
@@ -235,7 +236,7 @@ class Model(object):
         step's kernels (the reference's tf.data pipeline prefetches the same way).
         sync=False: asynchronous dispatch -- `loss` is a handle whose .get() -> (loss, report) waits for this
         step only, so the host can enqueue step i+1 while the device runs step i."""
-        h2d = self.forward(batch, full_outputs=False)
+        h2d = self.forward(batch, full_outputs=False, defer_outputs=True)   # the backward below joins the loss kernels
         if next_batch is not None:
             self.engine.prefetch_batch(next_batch)
         self.backward()
