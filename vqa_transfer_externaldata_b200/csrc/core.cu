@@ -201,6 +201,11 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   if (J > maxn) maxn = J;
   b.ln_part_g = a.take<float>(B * maxn);
   b.ln_part_b = a.take<float>(B * maxn);
+  for (int i = 0; i < 5; ++i) {   // per-layer partials: their column sums run on an auxiliary stream while the next layer works
+    const uint64_t n = (i < 2 ? J : L) * B;
+    b.ln_parts[i][0] = a.take<float>(n);
+    b.ln_parts[i][1] = a.take<float>(n);
+  }
   uint64_t maxc = 3 * L;
   if (A > maxc) maxc = A;
   if (J > maxc) maxc = J;

@@ -86,7 +86,8 @@ struct Buffers {
   float* dC_f32; Planes dC;  // [T*B, L]
   float* dG_f32; Planes dG;  // [T*B, 2L]
   float* dE;       // [T*B, Wpad]
-  float* ln_part_g; float* ln_part_b;  // [B, max(D,L,J)] LayerNorm gamma/beta partials
+  float* ln_part_g; float* ln_part_b;  // [B, max(D,L,J)] LayerNorm gamma/beta partials (q_linear_v)
+  float* ln_parts[5][2];               // the same for joint_fc, joint_l, pooled_linear_l, q_linear_l, the extra question layer
   unsigned int* gemm_sem;     // split-K hand-over semaphores of the pair GEMM (kGemmSemRegions x kGemmSemElems)
   unsigned int* gru_counter;  // per-row-tile phase counters of the persistent GRU kernels
   bf16* gru_pack;             // [L/32][96][L] packed weight slices of the forward recurrent kernel

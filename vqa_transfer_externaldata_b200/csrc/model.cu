@@ -518,6 +518,21 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   const bool v_adapt = c.variant == VQA_VARIANT_VLMAP_ANSWER_ADAPT;
   const int Pd = v_adapt ? D : Dv;
 
+  // Parameter gradients of the head layers (weight-gradient GEMMs, bias / LayerNorm column sums) are needed by nobody
+  // before the optimizer: each is enqueued on auxiliary stream 3, ordered after the main stream at that point, and the
+  // weight-gradient section (or the end of this function) joins it. Each layer has its own LayerNorm partial buffers.
+  cudaStream_t pg = s;
+  float* pg_scr = b.scratch;
+  bool pg_used = false;
+  auto pg_fork = [&]() -> VqaStatus {
+    if (h->profile && !h->profile_overlapped) return VQA_OK;   // isolated phase timing: everything stays on s
+    VQA_CUDA_CHECK(cudaEventRecord(h->ev_fork[3], s));
+    VQA_CUDA_CHECK(cudaStreamWaitEvent(h->aux[3], h->ev_fork[3], 0));
+    pg = h->aux[3];
+    pg_scr = b.scratch + 4 * b.scratch_floats;
+    pg_used = true;
+    return VQA_OK;
+  };
   PH_BEGIN(VQA_PH_HEAD_BWD);
   if (v_tuned) {
     // gradients of the two-term loss w.r.t. the word-weight logits (through the min fill in vqa_all) and the tuned ones
@@ -530,16 +545,27 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     t.d_logit0_f32 = b.dlogit_f32; t.d_logit0_hi = b.dlogit.hi; t.d_logit0_lo = b.dlogit.lo;
     t.d_tuned_f32 = b.dtuned_f32; t.d_tuned_hi = b.dtuned.hi; t.d_tuned_lo = b.dtuned.lo;
     VQA_TRY(tuned_grad_launch(t, s));
-    if (g->tw_w) VQA_TRY(GemmB(J, A, Bn).a(b.jd, 0, J, true).b(b.dtuned, 0, A, true).f32(g->tw_w, A).run(h, s));
-    if (g->tw_b) VQA_TRY(colsum_launch(b.dtuned_f32, Bn, A, A, g->tw_b, b.scratch, s));
+    if (g->tw_w) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(GemmB(J, A, Bn).a(b.jd, 0, J, true).b(b.dtuned, 0, A, true).f32(g->tw_w, A).run(h, pg));
+    }
+    if (g->tw_b) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.dtuned_f32, Bn, A, A, g->tw_b, pg_scr, pg));
+    }
   } else {
     // d logit = (sigmoid(x) - z) * train_mask / B
     VQA_TRY(bce_grad_launch(Bn, A, c.num_train_answer, use_tm, b.logit, batch->answer_target,
                             loss_scale / static_cast<float>(Bn), b.dlogit_f32, b.dlogit.hi, b.dlogit.lo, s));
   }
-  if (g->ans_w)
-    VQA_TRY(GemmB(J, A, Bn).a(b.jd, 0, J, true).b(b.dlogit, 0, A, true).f32(g->ans_w, A).run(h, s));
-  if (g->ans_b) VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->ans_b, b.scratch, s));
+  if (g->ans_w) {
+    VQA_TRY(pg_fork());
+    VQA_TRY(GemmB(J, A, Bn).a(b.jd, 0, J, true).b(b.dlogit, 0, A, true).f32(g->ans_w, A).run(h, pg));
+  }
+  if (g->ans_b) {
+    VQA_TRY(pg_fork());
+    VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->ans_b, pg_scr, pg));
+  }
   // dJd = dlogit Wa^T
   VQA_TRY(GemmB(Bn, J, A).a(b.dlogit, 0, A, false).b(b.w.ans_w, 0, A, false).f32(b.dJ, J).run(h, s));
   if (v_tuned)   // both heads read the same joint: dJd += d tuned Wt^T
@@ -550,32 +576,62 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.rows = Bn; r.N = J; r.dout = b.dJ; r.z = b.zj; r.gamma = p->joint_gamma; r.beta = p->joint_beta;
     r.mean = b.lnj_mean; r.rstd = b.lnj_rstd; r.keep = c.keep_joint; r.seed = seed; r.step = step;
     r.stream_id = RNG_STREAM_JOINT; r.dz_f32 = b.dzj_f32; r.dz_hi = b.dzj.hi; r.dz_lo = b.dzj.lo;
-    if (g->joint_gamma || g->joint_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    if (g->joint_gamma || g->joint_beta) { r.dgamma_part = b.ln_parts[0][0]; r.dbeta_part = b.ln_parts[0][1]; }
     VQA_TRY(row_ln_relu_bwd_launch(r, s));
-    if (g->joint_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, J, J, g->joint_gamma, b.scratch, s));
-    if (g->joint_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, J, J, g->joint_beta, b.scratch, s));
+    if (g->joint_gamma) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[0][0], Bn, J, J, g->joint_gamma, pg_scr, pg));
+    }
+    if (g->joint_beta) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[0][1], Bn, J, J, g->joint_beta, pg_scr, pg));
+    }
   }
-  if (g->joint_w) VQA_TRY(GemmB(L, J, Bn).a(b.x, 0, L, true).b(b.dzj, 0, J, true).f32(g->joint_w, J).run(h, s));
-  if (g->joint_b) VQA_TRY(colsum_launch(b.dzj_f32, Bn, J, J, g->joint_b, b.scratch, s));
+  if (g->joint_w) {
+    VQA_TRY(pg_fork());
+    VQA_TRY(GemmB(L, J, Bn).a(b.x, 0, L, true).b(b.dzj, 0, J, true).f32(g->joint_w, J).run(h, pg));
+  }
+  if (g->joint_b) {
+    VQA_TRY(pg_fork());
+    VQA_TRY(colsum_launch(b.dzj_f32, Bn, J, J, g->joint_b, pg_scr, pg));
+  }
   // dX = dZj Wj^T ; dHp = dX (.) Hl ; dHl = dX (.) Hp   (noc: dHp = dX, dHl comes from the joint_l branch)
   const bool noc = c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC;
   VQA_TRY(GemmB(Bn, L, J).a(b.dzj, 0, J, false).b(b.w.joint_w, 0, J, false).f32(b.dX, L).run(h, s));
   const float* d_hl_src = b.dX;
   if (noc) {
     // joint_l branch: dJl = dlogit Wal^T -> dropout / ReLU / LN backward -> dHl = dZjl Wjl^T
-    if (g->al_w) VQA_TRY(GemmB(J, A, Bn).a(b.jdl, 0, J, true).b(b.dlogit, 0, A, true).f32(g->al_w, A).run(h, s));
-    if (g->al_b) VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->al_b, b.scratch, s));
+    if (g->al_w) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(GemmB(J, A, Bn).a(b.jdl, 0, J, true).b(b.dlogit, 0, A, true).f32(g->al_w, A).run(h, pg));
+    }
+    if (g->al_b) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->al_b, pg_scr, pg));
+    }
     VQA_TRY(GemmB(Bn, J, A).a(b.dlogit, 0, A, false).b(b.w.al_w, 0, A, false).f32(b.dJl, J).run(h, s));
     RowLnBwd r{};
     r.rows = Bn; r.N = J; r.dout = b.dJl; r.z = b.zjl; r.gamma = p->jl_gamma; r.beta = p->jl_beta;
     r.mean = b.lnjl_mean; r.rstd = b.lnjl_rstd; r.keep = c.keep_joint; r.seed = seed; r.step = step;
     r.stream_id = RNG_STREAM_JOINT_L; r.dz_f32 = b.dzjl_f32; r.dz_hi = b.dzjl.hi; r.dz_lo = b.dzjl.lo;
-    if (g->jl_gamma || g->jl_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    if (g->jl_gamma || g->jl_beta) { r.dgamma_part = b.ln_parts[1][0]; r.dbeta_part = b.ln_parts[1][1]; }
     VQA_TRY(row_ln_relu_bwd_launch(r, s));
-    if (g->jl_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, J, J, g->jl_gamma, b.scratch, s));
-    if (g->jl_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, J, J, g->jl_beta, b.scratch, s));
-    if (g->jl_w) VQA_TRY(GemmB(L, J, Bn).a(b.hl_op, 0, L, true).b(b.dzjl, 0, J, true).f32(g->jl_w, J).run(h, s));
-    if (g->jl_b) VQA_TRY(colsum_launch(b.dzjl_f32, Bn, J, J, g->jl_b, b.scratch, s));
+    if (g->jl_gamma) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[1][0], Bn, J, J, g->jl_gamma, pg_scr, pg));
+    }
+    if (g->jl_beta) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[1][1], Bn, J, J, g->jl_beta, pg_scr, pg));
+    }
+    if (g->jl_w) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(GemmB(L, J, Bn).a(b.hl_op, 0, L, true).b(b.dzjl, 0, J, true).f32(g->jl_w, J).run(h, pg));
+    }
+    if (g->jl_b) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.dzjl_f32, Bn, J, J, g->jl_b, pg_scr, pg));
+    }
     VQA_TRY(GemmB(Bn, L, J).a(b.dzjl, 0, J, false).b(b.w.jl_w, 0, J, false).f32(b.dXl, L).run(h, s));
     d_hl_src = b.dXl;
   }
@@ -599,10 +655,16 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = noc ? nullptr : b.hl; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta;
     r.mean = b.lnp_mean; r.rstd = b.lnp_rstd; r.keep = 1.f; r.dz_f32 = b.dzp_f32; r.dz_hi = b.dzp.hi;
     r.dz_lo = b.dzp.lo;
-    if (g->pl_gamma || g->pl_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    if (g->pl_gamma || g->pl_beta) { r.dgamma_part = b.ln_parts[2][0]; r.dbeta_part = b.ln_parts[2][1]; }
     VQA_TRY(row_ln_relu_bwd_launch(r, s));
-    if (g->pl_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->pl_gamma, b.scratch, s));
-    if (g->pl_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->pl_beta, b.scratch, s));
+    if (g->pl_gamma) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[2][0], Bn, L, L, g->pl_gamma, pg_scr, pg));
+    }
+    if (g->pl_beta) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[2][1], Bn, L, L, g->pl_beta, pg_scr, pg));
+    }
   }
   const bool v_ent = c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT;
   if (v_ent) {
@@ -631,20 +693,37 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.rows = Bn; r.N = L; r.dout = d_hl_src; r.mul = (noc || v_ent) ? nullptr : b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
     r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi;
     r.dz_lo = b.dzl.lo;
-    if (g->ql_gamma || g->ql_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    if (g->ql_gamma || g->ql_beta) { r.dgamma_part = b.ln_parts[3][0]; r.dbeta_part = b.ln_parts[3][1]; }
     VQA_TRY(row_ln_relu_bwd_launch(r, s));
-    if (g->ql_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->ql_gamma, b.scratch, s));
-    if (g->ql_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->ql_beta, b.scratch, s));
+    if (g->ql_gamma) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[3][0], Bn, L, L, g->ql_gamma, pg_scr, pg));
+    }
+    if (g->ql_beta) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[3][1], Bn, L, L, g->ql_beta, pg_scr, pg));
+    }
   }
-  if (g->pl_w) VQA_TRY(GemmB(Pd, L, Bn).a(b.pooled_op, 0, Pd, true).b(b.dzp, 0, L, true).f32(g->pl_w, L).run(h, s));
-  if (g->pl_b) VQA_TRY(colsum_launch(b.dzp_f32, Bn, L, L, g->pl_b, b.scratch, s));
+  if (g->pl_w) {
+    VQA_TRY(pg_fork());
+    VQA_TRY(GemmB(Pd, L, Bn).a(b.pooled_op, 0, Pd, true).b(b.dzp, 0, L, true).f32(g->pl_w, L).run(h, pg));
+  }
+  if (g->pl_b) {
+    VQA_TRY(pg_fork());
+    VQA_TRY(colsum_launch(b.dzp_f32, Bn, L, L, g->pl_b, pg_scr, pg));
+  }
   const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE || v_full;
   {
     const Planes& ql_in = has_qp ? b.qp : b.h;   // q_linear_l reads the extra layer's output in those variants
-    if (g->ql_w)
-      VQA_TRY(GemmB(L, L, Bn).a(ql_in, has_qp ? 0 : q_off, L, true).b(b.dzl, 0, L, true).f32(g->ql_w, L).run(h, s));
+    if (g->ql_w) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(GemmB(L, L, Bn).a(ql_in, has_qp ? 0 : q_off, L, true).b(b.dzl, 0, L, true).f32(g->ql_w, L).run(h, pg));
+    }
   }
-  if (g->ql_b) VQA_TRY(colsum_launch(b.dzl_f32, Bn, L, L, g->ql_b, b.scratch, s));
+  if (g->ql_b) {
+    VQA_TRY(pg_fork());
+    VQA_TRY(colsum_launch(b.dzl_f32, Bn, L, L, g->ql_b, pg_scr, pg));
+  }
   // dP = dZp Wp^T ; dq = dZl Wl^T
   VQA_TRY(GemmB(Bn, Pd, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Pd).run(h, s));
   if (fork_ql) {
@@ -658,10 +737,16 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.rows = Bn; r.N = L; r.dout = b.dqp; r.z = b.zqp; r.gamma = p->qp_gamma; r.beta = p->qp_beta;
     r.mean = b.lnqp_mean; r.rstd = b.lnqp_rstd; r.keep = 1.f; r.act = 1; r.dz_f32 = b.dzqp_f32;
     r.dz_hi = b.dzqp.hi; r.dz_lo = b.dzqp.lo;
-    if (g->qp_gamma || g->qp_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
+    if (g->qp_gamma || g->qp_beta) { r.dgamma_part = b.ln_parts[4][0]; r.dbeta_part = b.ln_parts[4][1]; }
     VQA_TRY(row_ln_relu_bwd_launch(r, s));
-    if (g->qp_gamma) VQA_TRY(colsum_launch(b.ln_part_g, Bn, L, L, g->qp_gamma, b.scratch, s));
-    if (g->qp_beta) VQA_TRY(colsum_launch(b.ln_part_b, Bn, L, L, g->qp_beta, b.scratch, s));
+    if (g->qp_gamma) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[4][0], Bn, L, L, g->qp_gamma, pg_scr, pg));
+    }
+    if (g->qp_beta) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[4][1], Bn, L, L, g->qp_beta, pg_scr, pg));
+    }
   } else if (v_full) {
     // d(q_L_mean_noise) -> d mean (+ KL), d log_sigma_sq (+ KL)                        (_full.py:132-134, 272-276)
     VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dqp, L).run(h, s));
@@ -677,12 +762,24 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
                 .run(h, s));
   }
   if (has_qp) {
-    if (g->qp_w) VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dzqp, 0, L, true).f32(g->qp_w, L).run(h, s));
-    if (g->qp_b) VQA_TRY(colsum_launch(b.dzqp_f32, Bn, L, L, g->qp_b, b.scratch, s));
+    if (g->qp_w) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dzqp, 0, L, true).f32(g->qp_w, L).run(h, pg));
+    }
+    if (g->qp_b) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.dzqp_f32, Bn, L, L, g->qp_b, pg_scr, pg));
+    }
     VQA_TRY(GemmB(Bn, L, L).a(b.dzqp, 0, L, false).b(b.w.qp_w, 0, L, false).f32(b.dq, L).run(h, s));
     if (v_full) {
-      if (g->qs_w) VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dlss, 0, L, true).f32(g->qs_w, L).run(h, s));
-      if (g->qs_b) VQA_TRY(colsum_launch(b.dlss_f32, Bn, L, L, g->qs_b, b.scratch, s));
+      if (g->qs_w) {
+        VQA_TRY(pg_fork());
+        VQA_TRY(GemmB(L, L, Bn).a(b.h, q_off, L, true).b(b.dlss, 0, L, true).f32(g->qs_w, L).run(h, pg));
+      }
+      if (g->qs_b) {
+        VQA_TRY(pg_fork());
+        VQA_TRY(colsum_launch(b.dlss_f32, Bn, L, L, g->qs_b, pg_scr, pg));
+      }
       VQA_TRY(GemmB(Bn, L, L).a(b.dlss, 0, L, false).b(b.w.qs_w, 0, L, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
     }
   }
@@ -893,6 +990,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(vproj_wgrad(s));
     PH_END(VQA_PH_VPROJ_WGRAD);
   }
+  if (pg_used && !need_gru) VQA_TRY(join_stream(h, 3, s));   // (the weight-gradient section joins auxiliary stream 3 otherwise)
   if (h->outputs_pending) {   // the forward's deferred loss / metrics / output copies (auxiliary stream 1)
     VQA_TRY(join_stream(h, 1, s));
     h->outputs_pending = false;
