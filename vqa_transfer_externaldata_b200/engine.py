@@ -212,7 +212,8 @@ class PendingScalars:
             self.buf.copy_(eng.o_scalars, non_blocking=True)
             self.event = torch.cuda.Event()
             self.event.record(eng.d2h_stream)
-        eng._last_d2h = self.event   # the next forward overwrites o_scalars: it waits for this copy first
+        # the scalars are double-buffered: only the forward after next rewrites this buffer, and it waits for this copy
+        eng._last_d2h[eng._oi] = self.event
         self.nbytes = 4 * (1 + L.NUM_REPORT)
         self._keys, self._all = eng.report_keys, eng._all_report_keys
 
@@ -269,11 +270,12 @@ class Engine:
         self._cur = 0
         self.copy_stream = torch.cuda.Stream(device=dev)
         # outputs
-        self.o_scalars = torch.zeros(1 + L.NUM_REPORT, device=dev)   # [loss | report]: read back with one copy
-        self.o_loss = self.o_scalars[:1]
-        self.o_report = self.o_scalars[1:]
+        # [loss | report], read back with one copy; two buffers used alternately, so that a step never waits for the
+        # read-back of the step before it (that copy only starts when the previous step has finished)
+        self._o_scalars = [torch.zeros(1 + L.NUM_REPORT, device=dev) for _ in range(2)]
+        self._oi = 0
         self.d2h_stream = torch.cuda.Stream(device=dev)
-        self._last_d2h = None
+        self._last_d2h = [None, None]
         self.o_att = torch.zeros(cfg.B, cfg.K, device=dev)
         self.o_logit = torch.zeros(cfg.B, cfg.A, device=dev)
         self.o_pred = torch.zeros(cfg.B, dtype=torch.int32, device=dev)
@@ -286,12 +288,12 @@ class Engine:
         self._all_report_keys = L.REPORT_KEYS + L.EXTRA_REPORT_KEYS
         self.report_keys = L.REPORT_KEYS + L.VARIANT_REPORT_KEYS.get(cfg.variant, [])
         self.grad_norm = torch.zeros(1, device=dev)
-        self._outs = L.VqaOutputs(
-            loss=self.o_loss.data_ptr(), report=self.o_report.data_ptr(), att_score=self.o_att.data_ptr(),
+        self._outs_all = [L.VqaOutputs(
+            loss=sc[:1].data_ptr(), report=sc[1:].data_ptr(), att_score=self.o_att.data_ptr(),
             logit=self.o_logit.data_ptr(), pred=self.o_pred.data_ptr(),
             per_sample=self.o_per_sample.data_ptr(), condition=self.o_condition.data_ptr(),
-            pooled=self.o_pooled.data_ptr())
-        self._outs_min = L.VqaOutputs(loss=self.o_loss.data_ptr(), report=self.o_report.data_ptr())
+            pooled=self.o_pooled.data_ptr()) for sc in self._o_scalars]
+        self._outs_min_all = [L.VqaOutputs(loss=sc[:1].data_ptr(), report=sc[1:].data_ptr()) for sc in self._o_scalars]
         self.bank = None
         self.masks = None
         self.adam_t = 0
@@ -366,6 +368,10 @@ class Engine:
     @property
     def cur(self):
         return self._sets[self._cur]
+
+    o_scalars = property(lambda self: self._o_scalars[self._oi])   # of the most recent forward
+    o_loss = property(lambda self: self._o_scalars[self._oi][:1])
+    o_report = property(lambda self: self._o_scalars[self._oi][1:])
 
     # the active set's buffers under their historical names
     d_image_idx = property(lambda self: self.cur.d_image_idx)
@@ -477,10 +483,11 @@ class Engine:
             L.check(self.lib.vqa_set_deferred_outputs(self.h, int(defer_outputs)))
             self._deferred = defer_outputs
         b = self._c_batch()
-        outs = self._outs if full_outputs else self._outs_min
-        if self._last_d2h is not None:   # an asynchronous read-back of the previous loss / report may still be in flight
-            torch.cuda.current_stream(self.device).wait_event(self._last_d2h)
-            self._last_d2h = None
+        self._oi ^= 1                    # this step's loss / report go to the other scalar buffer
+        outs = (self._outs_all if full_outputs else self._outs_min_all)[self._oi]
+        if self._last_d2h[self._oi] is not None:   # the read-back that used this buffer two steps ago
+            torch.cuda.current_stream(self.device).wait_event(self._last_d2h[self._oi])
+            self._last_d2h[self._oi] = None
         L.check(self.lib.vqa_forward(self.h, C.byref(self._p), C.byref(self.bank), C.byref(b),
                                      C.byref(self.masks), C.c_uint64(seed), C.c_uint64(step), C.byref(outs),
                                      self._stream()))
