@@ -300,7 +300,7 @@ def run_ours(args):
         nonlocal h2d, d2h
         pending = []
         for i in range(steps):
-            nxt = pinned[(i + 1) % R] if i + 1 < steps else None
+            nxt = pinned[(i + 1) % R]   # steady-state pipeline: every step uploads the batch of the step after it
             p, a, b = model.train_step(pinned[i % R], next_batch=nxt, sync=False)
             h2d, d2h = a, b
             pending.append(p)
@@ -309,7 +309,7 @@ def run_ours(args):
         for p in pending:
             losses.append(p.get()[0])
 
-    run_e2e(3)
+    run_e2e(R)   # R warm-up steps: the last one prefetches pinned[0], the first batch of the timed run
     dp.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
