@@ -349,6 +349,16 @@ VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* params, f
                                          float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                                          float eps, float clip_norm, int64_t t, float* grad_norm_out, void* stream);
 
+/* How the reference's clip_by_global_norm(20.0) sees the embedding gradient: tf.nn.embedding_lookup on a variable yields
+ * an IndexedSlices (one row per token occurrence), and clip_ops.global_norm takes its `.values` as they are, so
+ * LearnGloVe/embed_map contributes sum_{b,t} |dE[b,t]|^2 -- not the norm of the scattered dense gradient (they differ
+ * whenever a token occurs more than once in the batch). With a slot set (one device float, e.g. just past the flat
+ * gradient buffer so that a data-parallel all-reduce sums it with the gradients), vqa_backward writes that sum into it
+ * and vqa_adam_step_shadowed uses it in place of the dense tensor's share of the norm. The Adam update itself is the
+ * dense one in both (the reference sums duplicate indices before applying and decays m, v of every row). NULL = off:
+ * plain dense norm. */
+VQA_API VqaStatus vqa_set_embedding_slice_norm(VqaHandle h, float* slot);
+
 /* ---- per-phase device timing (bench.py roofline): CUDA events recorded on the caller's stream around
  * the phases of vqa_forward / vqa_backward while enabled. Not for use under CUDA-graph capture. ------- */
 enum {

@@ -583,6 +583,8 @@ def backward(cache, loss_scale=1.0, intermediates=None, gate_flips=None, gate_ov
     demb = np.zeros_like(p["embed"])
     np.add.at(demb, c["q_ids"], dE)                          # gradient of embedding_lookup
     g["embed"] = demb
+    if intermediates is not None:
+        intermediates["dE"] = dE                             # the IndexedSlices values TF's global norm sees
     return g
 
 
@@ -613,9 +615,19 @@ def v_layer_tie_delta(cache, dHv, idx):
 # ------------------------------------------------------------------------------------------------
 # optimizer (vqa/trainer.py:106-114): clip_by_global_norm(20) over train vars, then Adam
 # ------------------------------------------------------------------------------------------------
-def clip_adam_step(params, grads, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=20.0):
-    """params/grads/m/v: dict field -> array over the trainable set; t = 1-based step. In place."""
-    gnorm = np.sqrt(sum(float((g ** 2).sum()) for g in grads.values()))
+def clip_adam_step(params, grads, m, v, t, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip=20.0, slice_sumsq=None):
+    """params/grads/m/v: dict field -> array over the trainable set; t = 1-based step. In place.
+    slice_sumsq: dict field -> sum of squares of that variable's gradient AS TF HOLDS IT. The gradient of
+    tf.nn.embedding_lookup on a variable is an IndexedSlices (values [B*T, W], one row per token occurrence), and
+    clip_ops.global_norm takes `t.values` of an IndexedSlices as they are -- duplicates NOT summed -- so optimize_loss'
+    clip_by_global_norm(20.0) sees sum_{b,t} |dE[b,t]|^2 for LearnGloVe/embed_map, not the norm of the scattered dense
+    gradient (vqa/trainer.py:106-114 -> tf.contrib.layers.optimize_loss -> clip_ops.clip_by_global_norm). The Adam update
+    itself sums duplicate indices first (Optimizer._apply_sparse_duplicate_indices) and decays m, v of every row, i.e.
+    it equals the dense update below."""
+    ss = {k: float((g ** 2).sum()) for k, g in grads.items()}
+    if slice_sumsq:
+        ss.update({k: float(x) for k, x in slice_sumsq.items()})
+    gnorm = np.sqrt(sum(ss.values()))
     scale = clip / max(gnorm, clip)
     lr_t = lr * np.sqrt(1.0 - beta2 ** t) / (1.0 - beta1 ** t)
     for k in grads:

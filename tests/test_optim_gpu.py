@@ -27,10 +27,23 @@ def test_two_optimizer_steps_match_the_oracle(variant, clip):
         eng.forward(seed=5, step=t)
         eng.backward()
         g = {f: eng.params.grad_views[f].detach().cpu().numpy().astype(np.float64) for f in fields}
+        # the embedding gradient as TF holds it (IndexedSlices rows): the oracle's own dE for the current parameters
+        att_mask, joint_mask = eng.dropout_masks(5, t)
+        torch.cuda.synchronize()
+        _, cache = O.forward(p, case["feats"], case["nb"], case["batch"], case["m"], variant=variant,
+                             att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy())
+        inter = {}
+        O.backward(cache, intermediates=inter)
+        slice_ss = float((inter["dE"] ** 2).sum())
+        dense_ss = float((g["embed"] ** 2).sum())
+        assert slice_ss > dense_ss * 1.0001 or slice_ss < dense_ss * 0.9999   # repeated tokens: the two norms differ
+        dev_slot = float(eng.params.grad_buf[eng.params.n_train].item())
+        assert abs(dev_slot - slice_ss) <= 2e-3 * slice_ss               # fp32-mode gradients, 1e-4-class agreement
         eng.adam_step(lr=1e-3, clip_norm=clip)
         torch.cuda.synchronize()
         pt = {k: p[k] for k in fields}
-        gnorm = O.clip_adam_step(pt, g, m, v, t, clip=clip)
+        # the device's own slot value keeps the comparison of the update itself at round-off level
+        gnorm = O.clip_adam_step(pt, g, m, v, t, clip=clip, slice_sumsq={"embed": dev_slot})
         p.update(pt)
         assert abs(eng.grad_norm.item() - gnorm) <= 1e-5 * gnorm
         if clip < 1.0:

@@ -164,6 +164,19 @@ def test_frozen_set_matches_reference_filter():
     assert set(O.trainable_fields("standard")) == set(O.PARAM_FIELDS)
 
 
+def test_clip_norm_of_an_indexed_slices_gradient():
+    """A token that occurs twice: TF's global norm takes both slice rows as they are, the dense norm sums them first."""
+    p = {"embed": np.zeros((4, 2)), "w": np.zeros(3)}
+    dE = np.array([[3.0, 0.0], [4.0, 0.0]])          # two occurrences of token 1
+    dense = np.zeros((4, 2))
+    np.add.at(dense, [1, 1], dE)
+    g = {"embed": dense, "w": np.array([0.0, 0.0, 12.0])}
+    m = {k: np.zeros_like(v) for k, v in p.items()}
+    v = {k: np.zeros_like(x) for k, x in p.items()}
+    assert abs(O.clip_adam_step(dict(p), g, dict(m), dict(v), 1) - np.sqrt(49 + 144)) < 1e-12            # dense: |3 + 4|
+    assert abs(O.clip_adam_step(dict(p), g, dict(m), dict(v), 1, slice_sumsq={"embed": (dE ** 2).sum()}) - 13.0) < 1e-12
+
+
 def test_clip_adam_step():
     rng = np.random.default_rng(3)
     p = {"a": rng.standard_normal(5), "b": rng.standard_normal((2, 3))}

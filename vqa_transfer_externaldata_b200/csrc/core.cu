@@ -299,6 +299,7 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   h->prefetched_batch = 0;
   h->pf_pending = false;
   h->pf_joined = true;
+  h->slice_slot = nullptr;
   h->defer_outputs = false;
   h->outputs_pending = false;
   h->pack_pending = false;

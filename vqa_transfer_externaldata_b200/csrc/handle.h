@@ -143,6 +143,7 @@ struct VqaHandle_t {
   // the GRU weight repack after an optimizer step runs on auxiliary stream 2; the next forward's GRU waits for it
   bool pack_pending;
   cudaEvent_t ev_pack;
+  float* slice_slot;       // vqa_set_embedding_slice_norm: where vqa_backward leaves sum |dE rows|^2 (NULL = off)
   bool early_grads;        // vqa_set_early_gradients
   cudaEvent_t ev_early;    // recorded by vqa_backward once the non-GRU gradients are complete
   // optional per-phase timing

@@ -319,7 +319,11 @@ struct AdamShadows {
 VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, long long n, float lr,
                            float beta1, float beta2, float eps, float clip_norm, long long t,
                            float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s,
-                           const AdamShadows* shadows = nullptr);
+                           const AdamShadows* shadows = nullptr, const float* slice_grad = nullptr, long long slice_n = 0,
+                           const float* slice_sumsq = nullptr);
+// out[0] = sum of squares of x[rows, cols] (pitch ld); scratch: >= 148 floats
+VqaStatus rows_sumsq_launch(const float* x, long long rows, int cols, long long ld, float* out, float* scratch,
+                            cudaStream_t s);
 
 // weight of the KL latent loss of the full variant (vqa/model_vlmap_answer_full.py:33)
 #define VQA_LATENT_LOSS_WEIGHT 0.1f

@@ -944,6 +944,9 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
                     .f32(b.dE, Wp).run(h, st));
         VQA_TRY(GemmB(TB, W, L).a(b.dC, 0, L, false).b(b.w.gru_cand_w, 0, L, false).addend(b.dE, Wp)
                     .f32(b.dE, Wp).run(h, st));
+        // what clip_ops.global_norm sees for an IndexedSlices gradient: its rows as they are (vqa_set_embedding_slice_norm)
+        if (h->slice_slot)
+          VQA_TRY(rows_sumsq_launch(b.dE, TB, W, Wp, h->slice_slot, b.scratch + 5 * b.scratch_floats, st));   // auxiliary stream 4's scratch region: its gather uses none
         VQA_TRY(fill_zero_launch(g->embed, sizeof(float) * c.Vq * W, st));
         VQA_TRY(embed_scatter_add_launch(b.dE, Wp, batch->q_intseq, batch->q_intseq_len, Bn, T, T, W, Bn,
                                          g->embed, st));
@@ -1141,8 +1144,16 @@ VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* p, float*
     }
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // the embedding's gradient is an IndexedSlices in the reference: its share of the clip norm is the sum of squares of
+  // the slice rows (left by vqa_backward in the slot), not that of the scattered dense gradient
+  const float* slice_grad = nullptr;
+  long long slice_n = 0;
+  if (h->slice_slot && p->embed && p->embed >= param && p->embed + static_cast<long long>(c.Vq) * c.W <= param + n) {
+    slice_grad = grad + (p->embed - param);
+    slice_n = static_cast<long long>(c.Vq) * c.W;
+  }
   VQA_TRY(adam_step_launch(param, grad, m, v, n, lr, beta1, beta2, eps, clip_norm, t, grad_norm_out, h->buf.scratch,
-                           h->num_sms, s, &tab));
+                           h->num_sms, s, &tab, slice_grad, slice_n, slice_grad ? h->slice_slot : nullptr));
   for (const Item* it : rest)
     VQA_TRY(split_bf16_launch(it->src, 1, it->elems, it->elems, it->dst->hi, it->dst->lo, it->elems, s));
   if (gru && gru_persistent_supported(c.B, c.L, c.precision, h->num_sms)) {
@@ -1157,6 +1168,12 @@ VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* p, float*
       h->pack_pending = true;
     }
   }
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_set_embedding_slice_norm(VqaHandle h, float* slot) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_set_embedding_slice_norm: null handle");
+  h->slice_slot = slot;
   return VQA_OK;
 }
 

@@ -60,13 +60,19 @@ __global__ void __launch_bounds__(OPT_THREADS) sumsq_partial_kernel(const float*
   }
 }
 
+// norm = sqrt(sum(part) - sum(minus) + *plus): `minus` / `plus` swap the dense embedding gradient's contribution for the
+// sum of squares of its IndexedSlices rows (what clip_ops.global_norm sees in the reference)
 __global__ void __launch_bounds__(OPT_THREADS) norm_final_kernel(const float* __restrict__ part, int parts,
+                                                                 const float* __restrict__ minus, int minus_parts,
+                                                                 const float* __restrict__ plus,
                                                                  float* __restrict__ norm_out,
                                                                  float* __restrict__ user_out) {
   __shared__ double red[OPT_THREADS / 32];
   pdl_sync();
   double acc = 0.0;
   for (int i = threadIdx.x; i < parts; i += OPT_THREADS) acc += static_cast<double>(part[i]);
+  for (int i = threadIdx.x; i < minus_parts; i += OPT_THREADS) acc -= static_cast<double>(minus[i]);
+  if (threadIdx.x == 0 && plus) acc += static_cast<double>(plus[0]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -74,7 +80,7 @@ __global__ void __launch_bounds__(OPT_THREADS) norm_final_kernel(const float* __
   if (threadIdx.x == 0) {
     double s = 0.0;
     for (int w = 0; w < OPT_THREADS / 32; ++w) s += red[w];
-    const float nrm = static_cast<float>(sqrt(s));
+    const float nrm = static_cast<float>(sqrt(s > 0.0 ? s : 0.0));
     norm_out[0] = nrm;
     if (user_out) user_out[0] = nrm;
   }
@@ -121,11 +127,62 @@ __global__ void __launch_bounds__(OPT_THREADS) adam_kernel(float* __restrict__ p
     }
 }
 
+// sum of squares of a [rows, cols] matrix with pitch ld (the pad columns are not part of it): per-block partials
+__global__ void __launch_bounds__(OPT_THREADS) rows_sumsq_partial_kernel(const float* __restrict__ x, long long rows, int cols,
+                                                                         long long ld, float* __restrict__ part) {
+  __shared__ float red[OPT_THREADS / 32];
+  pdl_sync();
+  float acc = 0.f;
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * OPT_THREADS) {
+    const long long r = i / cols;
+    const float v = x[r * ld + (i - r * cols)];
+    acc = fmaf(v, v, acc);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int w = 0; w < OPT_THREADS / 32; ++w) t += red[w];
+    part[blockIdx.x] = t;
+  }
+}
+__global__ void __launch_bounds__(OPT_THREADS) sum_parts_kernel(const float* __restrict__ part, int parts, float* __restrict__ out) {
+  __shared__ double red[OPT_THREADS / 32];
+  pdl_sync();
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < parts; i += OPT_THREADS) acc += static_cast<double>(part[i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < OPT_THREADS / 32; ++w) t += red[w];
+    out[0] = static_cast<float>(t);
+  }
+}
+
 }  // namespace
+
+VqaStatus rows_sumsq_launch(const float* x, long long rows, int cols, long long ld, float* out, float* scratch,
+                            cudaStream_t s) {
+  if (!out) return VQA_OK;
+  const int blocks = 148;
+  launch_pdl(rows_sumsq_partial_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, x, rows, cols, ld, scratch);
+  VQA_LAUNCH_CHECK("rows_sumsq_partial");
+  launch_pdl(sum_parts_kernel, dim3(1), dim3(OPT_THREADS), 0, s, static_cast<const float*>(scratch), blocks, out);
+  VQA_LAUNCH_CHECK("sum_parts");
+  return VQA_OK;
+}
 
 VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, long long n, float lr,
                            float beta1, float beta2, float eps, float clip_norm, long long t,
-                           float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s, const AdamShadows* shadows) {
+                           float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s, const AdamShadows* shadows,
+                           const float* slice_grad, long long slice_n, const float* slice_sumsq) {
   if (n <= 0) return VQA_OK;
   if (!param || !grad || !m || !v || !scratch) return set_error(VQA_ERR_BAD_ARG, "vqa_adam_step: null argument");
   if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
@@ -138,7 +195,18 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
   if (blocks > 2048) blocks = 2048;
   launch_pdl(sumsq_partial_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, grad, n, scratch + 8);
   VQA_LAUNCH_CHECK("sumsq_partial");
-  launch_pdl(norm_final_kernel, dim3(1), dim3(OPT_THREADS), 0, s, scratch + 8, blocks, scratch, grad_norm_out);
+  int minus_blocks = 0;
+  float* minus_part = scratch + 8 + 2048;
+  if (slice_grad && slice_sumsq && slice_n > 0) {   // the dense gradient of the IndexedSlices variable: taken out of the norm
+    minus_blocks = static_cast<int>((slice_n / 4 + OPT_THREADS - 1) / OPT_THREADS);
+    if (minus_blocks > 1024) minus_blocks = 1024;
+    if (minus_blocks < 1) minus_blocks = 1;
+    launch_pdl(sumsq_partial_kernel, dim3(minus_blocks), dim3(OPT_THREADS), 0, s, slice_grad, slice_n, minus_part);
+    VQA_LAUNCH_CHECK("sumsq_partial (slices)");
+  }
+  launch_pdl(norm_final_kernel, dim3(1), dim3(OPT_THREADS), 0, s, static_cast<const float*>(scratch + 8), blocks,
+             static_cast<const float*>(minus_part), minus_blocks, minus_blocks ? slice_sumsq : static_cast<const float*>(nullptr),
+             scratch, grad_norm_out);
   VQA_LAUNCH_CHECK("norm_final");
   const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t)));

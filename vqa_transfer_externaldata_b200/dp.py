@@ -48,7 +48,7 @@ class DataParallel:
             return False
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            n = (engine.params.n_train + 1023) // 1024 * 1024
+            n = (engine.params.n_train + engine.params.TAIL + 1023) // 1024 * 1024
             buf = symm_mem.empty(n, dtype=torch.float32, device=engine.device)
             hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
             if not hdl.has_multicast_support or not hdl.multicast_ptr:
@@ -58,7 +58,7 @@ class DataParallel:
                 print(f"[dp] multicast gradients unavailable ({e!r}); using NCCL all-reduce", flush=True)
             return False
         engine.rebind_gradients(buf)
-        self._mc = (hdl, buf, engine.params.n_train)
+        self._mc = (hdl, buf, engine.params.n_train + engine.params.TAIL)   # the tail slots are summed with the gradients
         return True
 
     def all_reduce_gradients(self, engine):
@@ -66,7 +66,7 @@ class DataParallel:
         is complete before the GRU's back-propagation through time (everything but the embedding and the GRU) is
         reduced on a side stream as soon as the device reaches that point -- under the recurrent kernels -- and only
         the rest waits for the end of the backward pass."""
-        g = engine.params.grad
+        g = engine.params.grad_buf   # gradients + tail slots (the embedding slice norm adds up over ranks like a gradient)
         if self.world_size == 1:
             return
         if self._mc is not None:

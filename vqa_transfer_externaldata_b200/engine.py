@@ -131,6 +131,7 @@ LATE_GRAD_FIELDS = ("embed", "gru_gates_w", "gru_gates_b", "gru_cand_w", "gru_ca
 class ParamStore:
     """fp32 master parameters in TF layout inside ONE flat device buffer: trainable tensors first (so the
     gradient all-reduce and the fused clip+Adam step run over one contiguous slice), frozen after."""
+    TAIL = 64
 
     def __init__(self, cfg, device):
         self.cfg = cfg
@@ -157,7 +158,10 @@ class ParamStore:
             off += _align(n)
         self.n_total = off
         self.flat = torch.zeros(self.n_total, dtype=torch.float32, device=device)
-        self.grad = torch.zeros(self.n_train, dtype=torch.float32, device=device)
+        # TAIL floats past the gradients travel with them through the data-parallel all-reduce: slot 0 holds the sum of
+        # squares of the embedding gradient's IndexedSlices rows (vqa_set_embedding_slice_norm)
+        self.grad_buf = torch.zeros(self.n_train + self.TAIL, dtype=torch.float32, device=device)
+        self.grad = self.grad_buf[:self.n_train]
         self.adam_m = None
         self.adam_v = None
         self.views = {f: self.flat[o:o + n].view(cfg.shape(f)) for f, (o, n) in self.offsets.items()}
@@ -166,8 +170,9 @@ class ParamStore:
 
     def rebind_grad(self, new_grad):
         """Move the flat gradient buffer (e.g. into symmetric memory for the multicast all-reduce)."""
-        assert new_grad.numel() >= self.n_train and new_grad.dtype == torch.float32
-        new_grad[:self.n_train].zero_()
+        assert new_grad.numel() >= self.n_train + self.TAIL and new_grad.dtype == torch.float32
+        new_grad[:self.n_train + self.TAIL].zero_()
+        self.grad_buf = new_grad[:self.n_train + self.TAIL]
         self.grad = new_grad[:self.n_train]
         self.grad_views = {f: self.grad[self.offsets[f][0]:self.offsets[f][0] + self.offsets[f][1]]
                            .view(self.cfg.shape(f)) for f in self.trainable}
@@ -263,6 +268,9 @@ class Engine:
         self.params = ParamStore(cfg, self.device)
         self._p = self.params.c_params()
         self._g = self.params.c_grads()
+        # clip norm with the embedding gradient as TF holds it (IndexedSlices rows); VQA_DENSE_CLIP_NORM=1 = dense norm
+        self.slice_norm = "embed" in self.params.trainable and os.environ.get("VQA_DENSE_CLIP_NORM", "0") != "1"
+        self._bind_slice_slot()
         dev = self.device
         # two sets of static batch buffers (addresses stay fixed -> capturable): while a step computes on one
         # set, the next batch is uploaded into the other on a copy stream (prefetch_batch)
@@ -497,10 +505,15 @@ class Engine:
         L.check(self.lib.vqa_backward(self.h, C.byref(self._p), C.byref(b), C.byref(self._g),
                                       C.c_float(loss_scale), self._stream()))
 
+    def _bind_slice_slot(self):
+        slot = self.params.grad_buf[self.params.n_train:].data_ptr() if self.slice_norm else None
+        L.check(self.lib.vqa_set_embedding_slice_norm(self.h, slot))
+
     def rebind_gradients(self, new_grad):
         """Use `new_grad` (>= n_train fp32 elements) as the flat gradient buffer from now on."""
         self.params.rebind_grad(new_grad)
         self._g = self.params.c_grads()
+        self._bind_slice_slot()
 
     def set_early_gradients(self, enable=True):
         """Data-parallel overlap: produce the non-GRU gradients before the BPTT (vqa_set_early_gradients)."""

@@ -166,6 +166,7 @@ SYMBOLS = {
     "vqa_dropout_mask_site": (C.c_int32, [_P, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "vqa_reparam_noise": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "vqa_multimem_all_reduce": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
+    "vqa_set_embedding_slice_norm": (C.c_int32, [_P, _P]),
     "vqa_set_deferred_outputs": (C.c_int32, [_P, C.c_int32]),
     "vqa_sync_outputs": (C.c_int32, [_P, _P]),
     "vqa_set_early_gradients": (C.c_int32, [_P, C.c_int32]),
