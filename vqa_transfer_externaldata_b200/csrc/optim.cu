@@ -36,14 +36,17 @@ __device__ __forceinline__ void shadow_store4(bf16* hi, bf16* lo, long long o, c
   }
 }
 
-__global__ void __launch_bounds__(OPT_THREADS) sumsq_partial_kernel(const float* __restrict__ g,
-                                                                    long long n, float* __restrict__ part) {
+// float4 chunks [skip_begin4, skip_end4) are left out (the dense gradient of the IndexedSlices variable, see norm_final)
+__global__ void __launch_bounds__(OPT_THREADS) sumsq_partial_kernel(const float* __restrict__ g, long long n,
+                                                                    long long skip_begin4, long long skip_end4,
+                                                                    float* __restrict__ part) {
   __shared__ float red[OPT_THREADS / 32];
   pdl_sync();
   float acc = 0.f;
   const long long n4 = n >> 2;
   for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < n4;
        i += static_cast<long long>(gridDim.x) * OPT_THREADS) {
+    if (i >= skip_begin4 && i < skip_end4) continue;
     const float4 v = reinterpret_cast<const float4*>(g)[i];
     acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
   }
@@ -60,10 +63,9 @@ __global__ void __launch_bounds__(OPT_THREADS) sumsq_partial_kernel(const float*
   }
 }
 
-// norm = sqrt(sum(part) - sum(minus) + *plus): `minus` / `plus` swap the dense embedding gradient's contribution for the
-// sum of squares of its IndexedSlices rows (what clip_ops.global_norm sees in the reference)
+// norm = sqrt(sum(part) + *plus): `plus` is the sum of squares of the embedding gradient's IndexedSlices rows (what
+// clip_ops.global_norm sees in the reference); the partials then leave the dense embedding gradient out
 __global__ void __launch_bounds__(OPT_THREADS) norm_final_kernel(const float* __restrict__ part, int parts,
-                                                                 const float* __restrict__ minus, int minus_parts,
                                                                  const float* __restrict__ plus,
                                                                  float* __restrict__ norm_out,
                                                                  float* __restrict__ user_out) {
@@ -71,7 +73,6 @@ __global__ void __launch_bounds__(OPT_THREADS) norm_final_kernel(const float* __
   pdl_sync();
   double acc = 0.0;
   for (int i = threadIdx.x; i < parts; i += OPT_THREADS) acc += static_cast<double>(part[i]);
-  for (int i = threadIdx.x; i < minus_parts; i += OPT_THREADS) acc -= static_cast<double>(minus[i]);
   if (threadIdx.x == 0 && plus) acc += static_cast<double>(plus[0]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -193,20 +194,17 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
   const long long need = (n / 4 + OPT_THREADS - 1) / OPT_THREADS;
   if (need < blocks) blocks = need < 1 ? 1 : static_cast<int>(need);
   if (blocks > 2048) blocks = 2048;
-  launch_pdl(sumsq_partial_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, grad, n, scratch + 8);
-  VQA_LAUNCH_CHECK("sumsq_partial");
-  int minus_blocks = 0;
-  float* minus_part = scratch + 8 + 2048;
-  if (slice_grad && slice_sumsq && slice_n > 0) {   // the dense gradient of the IndexedSlices variable: taken out of the norm
-    minus_blocks = static_cast<int>((slice_n / 4 + OPT_THREADS - 1) / OPT_THREADS);
-    if (minus_blocks > 1024) minus_blocks = 1024;
-    if (minus_blocks < 1) minus_blocks = 1;
-    launch_pdl(sumsq_partial_kernel, dim3(minus_blocks), dim3(OPT_THREADS), 0, s, slice_grad, slice_n, minus_part);
-    VQA_LAUNCH_CHECK("sumsq_partial (slices)");
+  // the dense gradient of the IndexedSlices variable is left out of the partial sums; its slice rows' sum comes in as `plus`
+  long long skip_b = 0, skip_e = 0;
+  const bool slices = slice_grad && slice_sumsq && slice_n > 0 && ((slice_grad - grad) & 3) == 0 && (slice_n & 3) == 0;
+  if (slices) {
+    skip_b = (slice_grad - grad) >> 2;
+    skip_e = skip_b + (slice_n >> 2);
   }
+  launch_pdl(sumsq_partial_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, grad, n, skip_b, skip_e, scratch + 8);
+  VQA_LAUNCH_CHECK("sumsq_partial");
   launch_pdl(norm_final_kernel, dim3(1), dim3(OPT_THREADS), 0, s, static_cast<const float*>(scratch + 8), blocks,
-             static_cast<const float*>(minus_part), minus_blocks, minus_blocks ? slice_sumsq : static_cast<const float*>(nullptr),
-             scratch, grad_norm_out);
+             slices ? slice_sumsq : static_cast<const float*>(nullptr), scratch, grad_norm_out);
   VQA_LAUNCH_CHECK("norm_final");
   const double lr_t = static_cast<double>(lr) * std::sqrt(1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(t))) /
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t)));
