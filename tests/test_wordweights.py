@@ -59,3 +59,16 @@ def test_importer_names():
     assert importer.get_model_class("vlmap_answer_ent").MODEL_TYPE == "vlmap_answer_ent"
     with pytest.raises(NotImplementedError):
         importer.get_model_class("vlmap_only")
+
+
+def test_learning_rate_schedule():
+    """vqa/trainer.py:87-96: constant 0.001, or halved every 10 000 steps (staircase) with --lr_weight_decay."""
+    from types import SimpleNamespace
+    from vqa_transfer_externaldata_b200.model import Model
+    m = Model.__new__(Model)
+    m.config, m.global_step = SimpleNamespace(), 25000
+    assert m.learning_rate() == 1e-3
+    m.config = SimpleNamespace(learning_rate=2e-3, lr_weight_decay=True)
+    assert m.learning_rate() == 2e-3 * 0.25
+    m.global_step = 9999
+    assert m.learning_rate() == 2e-3

@@ -229,7 +229,16 @@ class Model(object):
         if self._dp is not None:
             self._dp.all_reduce_gradients(self.engine)
 
-    def train_step(self, batch=None, lr=1e-3, clip_norm=20.0, apply_optimizer=True, next_batch=None, sync=True):
+    def learning_rate(self):
+        """The trainer's schedule (vqa/trainer.py:87-96): config.learning_rate (0.001), halved every 10 000 steps when
+        config.lr_weight_decay is set (tf.train.exponential_decay, staircase=True, on the global step BEFORE this
+        step's increment)."""
+        lr = float(getattr(self.config, "learning_rate", 1e-3))
+        if getattr(self.config, "lr_weight_decay", False):
+            lr *= 0.5 ** (self.global_step // 10000)
+        return lr
+
+    def train_step(self, batch=None, lr=None, clip_norm=20.0, apply_optimizer=True, next_batch=None, sync=True):
         """run_train_step of vqa/trainer.py:275-287: forward + backward (+ all-reduce) + clip + Adam.
         Returns (loss, h2d_bytes, d2h_bytes); the loss read is the step's device->host copy.
         next_batch: host batch of the FOLLOWING step; its upload starts now on a copy stream and overlaps this
@@ -241,7 +250,7 @@ class Model(object):
             self.engine.prefetch_batch(next_batch)
         self.backward()
         if apply_optimizer:
-            self.engine.adam_step(lr=lr, clip_norm=clip_norm)
+            self.engine.adam_step(lr=self.learning_rate() if lr is None else lr, clip_norm=clip_norm)
         self.global_step += 1
         if not sync:
             pending = self.engine.read_scalars_async()
