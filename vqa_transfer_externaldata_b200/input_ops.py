@@ -301,7 +301,9 @@ def read_num_answers(tf_record_dir):
             with h5py.File(p, "r") as f:
                 return int(np.asarray(f["data_info"]["num_answers"]))
         except ImportError:
-            pass
+            from . import hdf5_min
+            with hdf5_min.File(p) as f:
+                return int(f["data_info/num_answers"])
     p = os.path.join(tf_record_dir, "data_info.npz")
     if os.path.exists(p):
         return int(np.load(p)["num_answers"])

@@ -7,8 +7,9 @@ Reference behaviour mirrored (paths under /root/reference):
                                             vocab.pkl, answer_dict.pkl
   vqa/model_vlmap_answer.py:57-70           feature bank HDF5 {image_features, spatial_features,
                                             normal_boxes, num_boxes, data_info/{max_box_num, vfeat_dim}}
-HDF5 is read through h5py when it is importable; this image has neither h5py nor libhdf5, so a `.npz`
-mirror with the same dataset names (weights.npz / *.npz next to the .hdf5 path) is accepted too.
+HDF5 is read through h5py when it is importable, else through hdf5_min (a pure-Python reader of the subset of the
+format these files use); a `.npz` mirror with the same dataset names (weights.npz / *.npz next to the .hdf5 path) is
+accepted too and takes precedence.
 """
 import os
 import pickle
@@ -31,10 +32,18 @@ def _read_datasets(path, names):
             return {n: np.asarray(z[n]) for n in names if n in z}
     try:
         import h5py
-    except ImportError as e:
-        raise ImportError(f"{path}: h5py is not installed and no {npz} mirror exists") from e
-    with h5py.File(path, "r") as f:
-        return {n: np.array(f.get(n)) for n in names if n in f}
+        opener = lambda p: h5py.File(p, "r")  # noqa: E731
+    except ImportError:
+        from . import hdf5_min                 # pure-Python reader of the subset these files use
+        opener = hdf5_min.File
+    out = {}
+    with opener(path) as f:
+        for n in names:
+            for key in (n, "data_info/" + n):  # scalars such as max_box_num / vfeat_dim live in the data_info group
+                if key in f:
+                    out[n] = np.array(f[key])
+                    break
+    return out
 
 
 def word_weight_answer(input_dim, answer_dict, word_weight_dir, weight_name="class_weights",
