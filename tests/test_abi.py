@@ -80,3 +80,18 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+
+
+def test_enums_match_header():
+    """model_type -> VQA_VARIANT_* values, the report array length and the dropout sites follow the header."""
+    from vqa_transfer_externaldata_b200 import importer, lib as L
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    variants = dict((n.lower(), int(v)) for n, v in re.findall(r"VQA_VARIANT_(\w+)\s*=\s*(\d+)", src))
+    for model_type, value in L.VARIANTS.items():
+        key = "vlmap_answer_noc" if model_type == "vlmap_answer_nocarch" else model_type   # nocarch is the same graph
+        assert variants[key] == value, model_type
+    assert set(importer.get_model_types()) == set(L.VARIANTS)
+    report = re.search(r"VQA_REPORT_ANSWER_TRAIN_LOSS = 0,(.*?)VQA_NUM_REPORT", src, flags=re.S).group(1)
+    assert 1 + len(re.findall(r"VQA_REPORT_\w+", report)) == L.NUM_REPORT == len(L.REPORT_KEYS) + len(L.EXTRA_REPORT_KEYS)
+    acts = re.search(r"VQA_ACT_HQ = 0,(.*?)VQA_NUM_ACT", src, flags=re.S).group(1)
+    assert 1 + len(re.findall(r"VQA_ACT_\w+", acts)) == 7 == L.ACT_VA + 1
