@@ -72,3 +72,31 @@ def test_learning_rate_schedule():
     assert m.learning_rate() == 2e-3 * 0.25
     m.global_step = 9999
     assert m.learning_rate() == 2e-3
+
+
+def test_param_store_layout_on_cpu():
+    """ParamStore: trainable tensors first (one contiguous all-reduce / Adam slice), 256-byte aligned starts, frozen after,
+    TAIL slots past the gradients, views keyed by the reference's variable names."""
+    import torch
+    from vqa_transfer_externaldata_b200 import lib as L
+    from vqa_transfer_externaldata_b200.engine import AnswerModelConfig, ParamStore, frozen_fields, tf_name
+    for variant in ("vlmap_answer", "standard", "vlmap_answer_vqa_all", "vlmap_answer_adapt", "vlmap_answer_full"):
+        cfg = AnswerModelConfig(B=8, K=4, Dv=64, D=32, L=32, J=64, A=24, T=5, W=12, Vq=30, num_train_answer=18, variant=variant)
+        ps = ParamStore(cfg, torch.device("cpu"))
+        assert set(ps.fields) == set(L.param_fields(variant))
+        assert set(ps.frozen) == frozen_fields(variant) & set(ps.fields)
+        end_train = max(ps.offsets[f][0] + ps.offsets[f][1] for f in ps.trainable)
+        assert end_train <= ps.n_train and all(ps.offsets[f][0] >= ps.n_train for f in ps.frozen)
+        assert all(ps.offsets[f][0] % 64 == 0 for f in ps.fields)                      # 64 floats = 256 bytes
+        assert ps.grad_buf.numel() == ps.n_train + ps.TAIL and ps.grad.data_ptr() == ps.grad_buf.data_ptr()
+        spans = sorted(ps.offsets.values())
+        assert all(a[0] + a[1] <= b[0] for a, b in zip(spans, spans[1:]))              # no overlap
+        names = ps.by_tf_name()
+        assert len(names) == len(ps.fields) and tf_name("v_w", variant) in names
+        if variant == "vlmap_answer_adapt":
+            assert tuple(ps.views["pl_w"].shape) == (cfg.D, cfg.L) and "v_adapt/fc/weights" in names
+        if variant == "vlmap_answer_vqa_all":
+            assert "TunedWordWeightAnswer/fc/weights" in names and "tw_w" in ps.trainable
+        # gradients of the late group (embedding + GRU) sit at the end of the trainable slice
+        late = [f for f in ps.trainable if f in ("embed", "gru_gates_w", "gru_gates_b", "gru_cand_w", "gru_cand_b")]
+        assert ps.trainable[-len(late):] == late
