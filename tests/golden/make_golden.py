@@ -35,12 +35,43 @@ def inputs(variant, seed):
     return c, params, exist, feats, nb, batch, (is_obj, is_attr), m, am, jm
 
 
+# the other members of the family (tests/golden/answer_model_variants.npz): data seed per model_type
+VARIANT_CASES = {"vlmap_answer2": 21, "vlmap_answer_no_noise": 22, "vlmap_answer_noc": 23, "vlmap_answer_full": 24,
+                 "vlmap_answer_vqa_all": 25, "vlmap_answer_vqa_all2": 26, "vlmap_answer_adapt": 27, "vlmap_answer_ent": 28}
+NUM_MARGINAL = 5        # of the ent case (the reference's 200 would make the fixture's oracle run needlessly large)
+
+
+def extras(variant, c):
+    """Variant-specific random draws, from the same Philox restatement the device uses (sites 3 / 4 / 5)."""
+    if variant in ("vlmap_answer_noc", "vlmap_answer_nocarch"):
+        return {"joint_l_mask": PH.keep_mask(c["B"] * c["J"], 0.5, SEED, STEP, 3).reshape(c["B"], c["J"])}
+    if variant == "vlmap_answer_full":
+        return {"noise": PH.normal_draw(c["B"] * c["L"], SEED, STEP).reshape(c["B"], c["L"])}
+    if variant == "vlmap_answer_ent":
+        return {"num_marginal": NUM_MARGINAL,
+                "ent_mask": PH.keep_mask(c["B"] * NUM_MARGINAL * c["J"], 0.5, SEED, STEP, 5).reshape(c["B"], NUM_MARGINAL, c["J"])}
+    return {}
+
+
 def run(variant, seed, operand_round=None):
     c, params, exist, feats, nb, batch, flags, m, am, jm = inputs(variant, seed)
     out, cache = O.forward(params, feats, nb, batch, m, variant=variant, att_mask=am, joint_mask=jm,
-                           operand_round=operand_round)
+                           operand_round=operand_round, **extras(variant, c))
     g = O.backward(cache)
     return out, {f: g[f] for f in O.trainable_fields(variant)}
+
+
+def summarise(out, g):
+    """Compact fixture of one case: forward tensors in full (they are small), gradients as their l2 norm plus their
+    first 48 entries."""
+    blob = {"loss": np.float64(out["loss"]), "logit": out["logit"].astype(np.float32), "att_score": out["att_score"],
+            "pred": out["pred"], "condition": out["condition"].astype(np.float32),
+            "report_keys": np.array(sorted(out["report"])),
+            "report": np.array([out["report"][k] for k in sorted(out["report"])])}
+    for f, v in g.items():
+        blob[f"grad_norm/{f}"] = np.float64(np.linalg.norm(v))
+        blob[f"grad_head/{f}"] = np.asarray(v, np.float64).reshape(-1)[:48]
+    return blob
 
 
 def main():
@@ -57,7 +88,15 @@ def main():
             blob[f"{variant}/grad/{f}"] = v.astype(np.float32) if v.size > 4096 else v
         blob[f"{variant}/att_mask_sum"] = np.int64(inputs(variant, seed)[8].sum())
     path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "answer_model_small.npz")
-    np.savez_compressed(path, **blob)
+    if "--variants-only" not in sys.argv:
+        np.savez_compressed(path, **blob)
+        print(path, os.path.getsize(path), "bytes")
+    vblob = {}
+    for variant, seed in VARIANT_CASES.items():
+        out, g = run(variant, seed)
+        vblob.update({f"{variant}/{k}": v for k, v in summarise(out, g).items()})
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "answer_model_variants.npz")
+    np.savez_compressed(path, **vblob)
     print(path, os.path.getsize(path), "bytes")
 
 
