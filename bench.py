@@ -3,6 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
   python bench.py --impl reference --gpus N --steps K ...   # CPU arm (see below)
+  python bench.py --mode infer --gpus N                      # BASELINE config 5: batched inference sweep, batch sharded
 
 A "step" is one train step of vqa/trainer.py:275-287 on one synthetic batch: forward + backward of the
 vlmap_answer model at B 512 x K 36 x Dv 2048 (T 14, A 3000) + gradient all-reduce (N > 1) + global-norm
@@ -43,16 +44,20 @@ def load_peaks():
 
 
 def ncu_traffic(dom):
-    """DRAM bytes of the dominant launch from the committed `ncu --set full` capture (None if absent)."""
-    p = os.path.join(ROOT, "profiles", "r01_ncu_full_summary_v5.json")
-    want = "v_linear_v wgrad" if dom == "vproj_wgrad" else "v_linear_v forward"
-    try:
-        with open(p) as f:
-            for k in json.load(f)["kernels"]:
-                if k["role"].startswith(want):
-                    return k["dram_traffic_bytes"]
-    except (OSError, KeyError, ValueError):
-        pass
+    """DRAM bytes of the dominant section's kernel from the committed `ncu --set full` captures (None if absent: the
+    cooperative + cluster recurrent kernels cannot be replayed by ncu)."""
+    want = {"vproj_wgrad": "v_linear_v wgrad", "vproj_fwd": "v_linear_v forward", "attn_fwd": "attention forward",
+            "attn_bwd": "attention backward"}.get(dom)
+    if want is None:
+        return None
+    for name in ("r02_ncu_full_summary.json", "r01_ncu_full_summary_v5.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                for k in json.load(f)["kernels"]:
+                    if k["role"].startswith(want):
+                        return k["dram_traffic_bytes"]
+        except (OSError, KeyError, ValueError):
+            continue
     return None
 
 
@@ -193,13 +198,14 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    sample_b = 128
+    sample_b = CFG1["B"]   # the SAME batch as our arm (512): ~0.3 s per step on 16 threads
     rate, threads, busy = cpu_port_rate(sample_b, max(1, args.steps), max(1, min(args.warmup, 2)))
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "samples/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample_b / rate,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU arm; each step = a 128-sample slice of the 512 batch"},
+        "config": {"workload": WORKLOAD, "per_gpu_batch": sample_b, "global_batch": sample_b,
+                   "note": "CPU arm: the oracle's torch-CPU port of the same graph at the same batch (B 512), all host threads"},
         "cpu_baseline": {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
                          "sample": f"fwd+bwd of oracle/answer_model_torch.py at cfg1 layer sizes, batch {sample_b}, "
                                    f"{args.steps} timed steps ({busy:.1f} s CPU wall)"},
@@ -210,9 +216,189 @@ def run_reference(args):
     return 0
 
 
+
+def phase_work(c, precision):
+    """Algorithmic work of every section of the step's critical path:
+    name -> (bound, FLOPs or bytes per step, kernel that dominates the section)."""
+    B, K, Dv, D, L, J, A, T, W = (c[k] for k in ("B", "K", "Dv", "D", "L", "J", "A", "T", "W"))
+    zb = vb = 2 if precision == "bf16" else 4
+    att_fwd = B * (K * D * zb + K * Dv * vb + D * 4 + Dv * 4 + Dv * vb + K * 4)
+    att_bwd = B * (K * Dv * vb + K * D * zb + Dv * 4 + D * 4 + K * 4 + K * D * vb + D * 4 + (4 * D + 8) * 4)
+    pair = "gemm_pair_kernel" if precision == "bf16" else "gemm_bf16_tcgen05_kernel (hi/lo planes)"
+    small = "gemm_bf16_tcgen05_kernel (M = 512 head GEMMs) + row_ln_relu kernels"
+    return {
+        "gather": ("hbm", 2.0 * B * K * Dv * vb, "gather_features_bf16_kernel"),
+        "vproj_fwd": ("tensor", 2.0 * B * K * Dv * D, pair),
+        "gru_fwd": ("tensor", 2.0 * B * L * 3 * L * T, "gru_pair_kernel<0> (recurrence, h-part: 2 B L 3L T)"),
+        "qheads_fwd": ("tensor", 2.0 * B * (L * L + L * D), small),
+        "attn_fwd": ("hbm", float(att_fwd), "attn_fwd_pipe_kernel"),
+        "head_fwd": ("tensor", 2.0 * B * (Dv * L + L * J + J * A), small),
+        "loss": ("hbm", 2.0 * B * A * 4, "bce_metrics_kernel"),
+        "head_bwd": ("tensor", 2.0 * B * (A * J + J * L + L * Dv + L * L), small),
+        "attn_bwd": ("hbm", float(att_bwd), "attn_bwd_kernel"),
+        "qv_bwd": ("tensor", 2.0 * B * D * L, small),
+        "vproj_wgrad": ("tensor", 2.0 * B * K * Dv * D, pair),
+        "gru_bwd": ("tensor", 2.0 * B * L * 3 * L * T, "gru_pair_kernel<1> (BPTT, 2 B L 3L T)"),
+        "gru_wgrad": ("tensor", 2.0 * T * B * 3 * L * (W + L) + 2.0 * T * B * W * 3 * L + 2.0 * B * K * Dv * D,
+                      pair + " x 7 on forked streams (4 GRU weight gradients + dE + dWv)"),
+        "embed_bwd": ("hbm", 0.0, "embed_scatter_add"),
+    }, att_fwd, att_bwd
+
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+def measure_fp32_mode(bank, c, n_img, dev, peaks, steps=10, warmup=3):
+    """The same train step in the reference-precision mode (north_star: fp32 mode within 1e-4), >= 10 timed steps."""
+    import torch
+    from vqa_transfer_externaldata_b200 import synthetic as S
+    from vqa_transfer_externaldata_b200.model import Model, make_synthetic_config
+    config, _, _, _ = make_synthetic_config(CFG1, variant="vlmap_answer", precision="fp32", seed=4321, num_images=2)
+    config.device = dev
+    feats = {"features": bank, "num_boxes": np.full(n_img, c["K"], np.int32), "max_box_num": c["K"], "vfeat_dim": c["Dv"]}
+    hb = [S.make_batch(c, n_img, seed=4242 + r) for r in range(2)]
+    m = Model(hb[0], config, is_train=True, image_features=feats)
+    e = m.engine
+    db = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("image_idx", "q_intseq", "q_intseq_len", "answer_target")}
+          for b in hb]
+
+    def step(i):
+        e.stage_batch(db[i % 2])
+        e.forward(seed=m.seed, step=m.global_step, full_outputs=False, defer_outputs=True)
+        m.backward()
+        e.adam_step(lr=1e-3, clip_norm=20.0)
+        m.global_step += 1
+
+    for i in range(warmup):
+        step(i)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    loss, _ = e.read_scalars()
+    t_roof = (3 * 356.1e9 / (peaks["bf16_tflops_sustained"] * 1e12) + (543.4e6 + 18.4e6) / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    out = {"ms_per_step": ms, "samples_per_s": c["B"] / (ms * 1e-3), "steps": steps, "warmup": warmup,
+           "step_roofline_frac": t_roof / ms, "t_roof_ms": t_roof, "loss_finite": bool(np.isfinite(loss)),
+           "model": "3 x 356.1 GF / bf16 sustained (x = hi + lo bf16 planes, 3 tcgen05 MMAs per k-step, fp32 TMEM accumulation) "
+                    "+ 561.8 MB / HBM"}
+    e.close()
+    del m, e
+    torch.cuda.empty_cache()
+    return out
+
+
+INFER_DIMS = dict(K=100, Dv=2048, D=1024, L=1024, A=3000, T=14, W=300, Vq=8192)
+
+
+def run_infer(args):
+    """BASELINE config 5 (vqa/evaler.py:118-123): forward-only sweep over GLOBAL batch sizes, K = 100 padded boxes with
+    10..100 valid per image, the batch sharded over the N ranks with NO collective on the path; one JSON line."""
+    import torch
+    from vqa_transfer_externaldata_b200 import synthetic as S
+    from vqa_transfer_externaldata_b200.dp import DataParallel
+    from vqa_transfer_externaldata_b200.engine import AnswerModelConfig, Engine
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this repo has no CPU path")
+    dp = DataParallel()
+    rank, world = dp.rank, dp.world_size
+    torch.cuda.set_device(dp.local_rank)
+    dev = torch.device(f"cuda:{dp.local_rank}")
+    peaks = load_peaks()
+    sizes = [int(x) for x in args.infer_batches.split(",")]
+    n_img = 2048
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    K = INFER_DIMS["K"]
+    bank = torch.randn(n_img, K, INFER_DIMS["Dv"], device=dev, generator=g).abs_().mul_(0.5)
+    rng = np.random.default_rng(5 + rank)
+    nb = rng.integers(10, K + 1, size=n_img).astype(np.int32)
+    bank *= (torch.arange(K, device=dev)[None, :] < torch.from_numpy(nb).to(dev)[:, None])[:, :, None]
+    sweep = []
+    sampler = ClockSampler(dp.local_rank)
+    if rank == 0:
+        sampler.start()
+    launches = 0
+    for Bg in sizes:
+        s0, s1 = dp.shard(Bg)
+        Bl = s1 - s0
+        c = S.dims(B=max(Bl, 1), **INFER_DIMS)
+        eng = Engine(AnswerModelConfig(variant="vlmap_answer", precision=args.precision, **c), device=dev)
+        eng.set_feature_bank(bank, nb)
+        params, exist = S.init_params(c, seed=4321, variant="vlmap_answer")
+        is_obj, is_attr = S.make_answer_flags(c)
+        eng.set_answer_masks(is_obj, is_attr, exist)
+        eng.load_params(params)
+        hb = [S.make_batch(c, n_img, seed=1234 + 17 * r + 1000 * rank) for r in range(3)]
+        db = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("image_idx", "q_intseq", "q_intseq_len", "answer_target")}
+              for b in hb]
+        pinned = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in ("image_idx", "q_intseq", "q_intseq_len", "answer_target")}
+                  for b in hb]
+        host_out = torch.zeros(c["B"], dtype=torch.int32).pin_memory()
+
+        def step_dev(i):
+            eng.stage_batch(db[i % 3])
+            eng.forward(seed=777 + 7919 * rank, step=i, full_outputs=True)
+
+        def step_e2e(i):   # host batch in, predictions + loss/report back on the host
+            nbytes = eng.stage_batch(pinned[i % 3])
+            eng.forward(seed=777 + 7919 * rank, step=i, full_outputs=True)
+            host_out[:Bl].copy_(eng.o_pred[:Bl], non_blocking=True)
+            return nbytes
+
+        def timed(fn, steps):
+            dp.barrier()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = eng.launch_count()
+            e0.record()
+            for i in range(steps):
+                fn(i)
+            e1.record()
+            torch.cuda.synchronize()
+            dp.barrier()
+            return dp.max_over_ranks(e0.elapsed_time(e1)) / steps, eng.launch_count() - n0
+
+        W = max(3, args.warmup)
+        for i in range(W):
+            step_dev(i)
+        ms, n_l = timed(step_dev, args.steps)
+        launches += n_l
+        for i in range(2):
+            step_e2e(i)
+        ms_e2e, _ = timed(step_e2e, args.steps)
+        h2d = Bl * 8 + Bl * c["T"] * 4 + Bl * 4 + Bl * c["A"] * 4
+        ok = bool(torch.isfinite(eng.outputs()["att_score"]).all().item())
+        sweep.append({"global_batch": Bg, "per_gpu_batch": Bl, "ms_per_step": ms, "samples_per_s": Bg / (ms * 1e-3),
+                      "e2e_ms_per_step": ms_e2e, "e2e_samples_per_s": Bg / (ms_e2e * 1e-3),
+                      "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": 4 * Bl * world,
+                      "roofline_frac": 0.59e-3 * Bl / ms, "outputs_finite": ok,
+                      "gru_kernels": {1: "pair", 2: "single-CTA"}.get(int(eng.lib.vqa_gru_kernel_path()) & 3, "?")})
+        eng.close()
+        del eng
+        torch.cuda.empty_cache()
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        best = max(sweep, key=lambda r: r["samples_per_s"])
+        line = {"metric": "inference samples/sec fwd, K100 masked, batch sharded over GPUs (BASELINE config 5)",
+                "value": best["samples_per_s"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": best["ms_per_step"], "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32",
+                "data": "synthetic",
+                "config": {"workload": "cfg5 vlmap_answer forward (logits, attention, pred, report), K 100 padded boxes with "
+                                       "10..100 valid, T14, A3000; global batch sharded over the ranks, no collective",
+                           "global_batch": best["global_batch"], "parallelism": f"shard{world}", "precision": args.precision,
+                           "l2_policy": "inputs larger than L2: 2048-image x 100-box feature bank (1.68 GB fp32 + 0.84 GB bf16 copy) "
+                                        "indexed at random", "roofline_per_sample_us": 0.59},
+                "e2e": {"value": best["e2e_samples_per_s"], "unit": "samples/s", "ms_per_step": best["e2e_ms_per_step"],
+                        "h2d_bytes_per_step": best["h2d_bytes_per_step"], "d2h_bytes_per_step": best["d2h_bytes_per_step"]},
+                "gpu_launches": int(launches), "clocks": clocks, "sweep": sweep}
+        _emit(line)
+    dp.close()
+    return 0
+
+
 def run_ours(args):
     import torch
     from vqa_transfer_externaldata_b200 import lib as L
@@ -275,6 +461,16 @@ def run_ours(args):
         dp.barrier()
         ms = dp.max_over_ranks(e0.elapsed_time(e1))
         return ms, eng.launch_count() - n0
+
+    if world > 1:
+        # data-parallel step == single-rank step on the concatenated batch, on THIS job's ranks and collective, before
+        # anything is timed (raises on mismatch)
+        dp_check = dp.self_check(device=dev)
+    else:
+        dp_check = None
+    collective = ("none (1 GPU)" if world == 1 else
+                  "multimem.ld_reduce/st in-switch all-reduce (csrc/collective.cu), NCCL for rendezvous + broadcast only"
+                  if dp._mc is not None else "NCCL all-reduce")
 
     W = max(3, args.warmup)
     for i in range(W):
@@ -346,26 +542,59 @@ def run_ours(args):
     L.check(lib.vqa_profile_enable(eng.h, 0))
     critical_ms = {lib.vqa_phase_name(i).decode(): float(acc2[i] / PROF_STEPS) for i in range(L.NUM_PHASES)}
 
+    # optimizer and all-reduce sections of the same step (events on the launching stream)
+    evs = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    opt_ms = ar_ms = 0.0
+    for i in range(PROF_STEPS):
+        eng.stage_batch(dev_batches[i % R])
+        rk = dp.rank if world > 1 else 0
+        eng.forward(seed=model.seed + 7919 * rk, step=model.global_step, full_outputs=False, defer_outputs=True)
+        eng.prefetch_batch(dev_batches[(i + 1) % R])
+        eng.backward(loss_scale=1.0 / world)
+        evs[0].record()
+        if world > 1:
+            dp.all_reduce_gradients(eng)
+        evs[1].record()
+        eng.adam_step(lr=1e-3, clip_norm=20.0)
+        evs[2].record()
+        model.global_step += 1
+        torch.cuda.synchronize()
+        ar_ms += evs[0].elapsed_time(evs[1]) / PROF_STEPS
+        opt_ms += evs[1].elapsed_time(evs[2]) / PROF_STEPS
+    phase_ms["allreduce"] = critical_ms["allreduce"] = dp.max_over_ranks(ar_ms) if world > 1 else 0.0
+    phase_ms["optimizer"] = critical_ms["optimizer"] = opt_ms
+
     samples = world * B * args.steps
     value = samples / (ms_value * 1e-3)
     e2e_value = samples / (ms_e2e * 1e-3)
 
-    # rooflines. Dominant kernel = the v-projection GEMM pair (fwd: [B*K,Dv]x[Dv,D], wgrad: [Dv,B*K]x[B*K,D]),
-    # each ONE launch of gemm_pair_kernel (bf16 mode); algorithmic FLOPs = 2*M*N*K (77.31 GF each).
-    K_, Dv, D = c["K"], c["Dv"], c["D"]
-    gemm_flops = 2.0 * B * K_ * Dv * D * (3 if args.precision == "fp32" else 1)
-    dom = "vproj_wgrad" if phase_ms["vproj_wgrad"] >= phase_ms["vproj_fwd"] else "vproj_fwd"
-    ach = gemm_flops / (phase_ms[dom] * 1e-3) / 1e12
-    peak_tc = peaks["bf16_tflops_sustained"]
-    kern = "gemm_pair_kernel" if args.precision == "bf16" else "gemm_bf16_tcgen05_kernel"
-    roofline = {"bound": "tensor", "kernel": f"{kern} ({dom})", "achieved": ach, "peak": peak_tc,
-                "unit": "TFLOP/s", "frac": ach / peak_tc, "traffic": ncu_traffic(dom) if args.precision == "bf16" else None,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch, profiles/r01_ncu_full_summary_v5.json",
-                "peak_source": f"{peaks['source']} bf16 sustained (kernel timed inside a long step)"}
-    zb = 2 if args.precision == "bf16" else 4     # bytes / element of the stored pre-LN projection
-    vb = 2 if args.precision == "bf16" else 4     # gathered features: bf16 plane (fp32 mode: hi + lo planes)
-    att_fwd_bytes = B * (K_ * D * zb + K_ * Dv * vb + D * 4 + Dv * 4 + Dv * vb + K_ * 4)
-    att_bwd_bytes = B * (K_ * Dv * vb + K_ * D * zb + Dv * 4 + D * 4 + K_ * 4 + K_ * D * vb + D * 4 + (4 * D + 8) * 4)
+    # rooflines. `roofline` names the section with the LARGEST share of the step's critical path; its work is the
+    # algorithmic FLOPs / bytes of SURVEY 8d (phase_work), its time the section's device time inside the real step.
+    work, att_fwd_bytes, att_bwd_bytes = phase_work(c, args.precision)
+    peak_tc = peaks["bf16_tflops_sustained"] / (3.0 if args.precision == "fp32" else 1.0)
+    sections = {}
+    for name, (bound, amount, kern) in work.items():
+        ms = critical_ms.get(name, 0.0)
+        if ms <= 0.0 or amount <= 0.0:
+            continue
+        if bound == "tensor":
+            ach, peak, unit = amount / (ms * 1e-3) / 1e12, peak_tc, "TFLOP/s"
+        else:
+            ach, peak, unit = amount / (ms * 1e-3) / 1e9, peaks["hbm_gbs"], "GB/s"
+        sections[name] = {"bound": bound, "kernel": kern, "ms": ms, "share_of_step": ms / (ms_value / args.steps),
+                          "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak}
+    dom = max(sections, key=lambda k: sections[k]["ms"])
+    d = sections[dom]
+    roofline = {"bound": d["bound"], "kernel": d["kernel"], "section": dom, "achieved": d["achieved"], "peak": d["peak"],
+                "unit": d["unit"], "frac": d["frac"], "share_of_step": d["share_of_step"], "ms": d["ms"],
+                "traffic": ncu_traffic(dom) if args.precision == "bf16" else None,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of that launch from the committed ncu --set full "
+                                  "capture under profiles/ (null for the cooperative + cluster recurrent kernels, which ncu "
+                                  "cannot replay: their evidence is the in-kernel globaltimer phase trace under profiles/)",
+                "peak_source": f"{peaks['source']}: bf16 sustained (kernel timed inside a long step)"
+                               + (" / 3 (hi + lo planes: 3 MMAs per k-step)" if args.precision == "fp32" else "")
+                               if d["bound"] == "tensor" else f"{peaks['source']} HBM copy bandwidth",
+                "how_chosen": "largest critical_path_ms section of the step"}
     attn = {
         "fwd": {"ms": phase_ms["attn_fwd"], "bytes": att_fwd_bytes,
                 "GBps": att_fwd_bytes / (phase_ms["attn_fwd"] * 1e-3) / 1e9},
@@ -376,15 +605,20 @@ def run_ours(args):
     attn["fwd"]["frac"] = attn["fwd"]["GBps"] / peaks["hbm_gbs"]
     attn["bwd"]["frac"] = attn["bwd"]["GBps"] / peaks["hbm_gbs"]
     # whole-step roofline of BASELINE.md section 3 (cfg1: 356.1 GF + 543.4 MB + 18.4 MB -> 340 us on 1 GPU)
-    t_roof_ms = (356.1e9 / (peaks["bf16_tflops_sustained"] * 1e12) + (543.4e6 + 18.4e6) / (peaks["hbm_gbs"] * 1e9)) * 1e3
+    t_roof_ms = (356.1e9 / (peak_tc * 1e12) + (543.4e6 + 18.4e6) / (peaks["hbm_gbs"] * 1e9)) * 1e3
     step_frac = t_roof_ms / (ms_value / args.steps)
+
+    # the reference-precision mode (fp32 I/O, hi + lo operand planes: 3 MMAs per k-step) in the same job
+    fp32_mode = None
+    if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_fp32:
+        fp32_mode = measure_fp32_mode(bank, c, n_img, dev, peaks)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, threads, busy = cpu_port_rate(128, 0, 1, budget_s=12.0)
+        rate, threads, busy = cpu_port_rate(B, 0, 1, budget_s=10.0)
         cpu_baseline = {"value": rate, "unit": "samples/s", "cores": threads, "kind": "port",
-                        "sample": f"fwd+bwd of the oracle's torch-CPU port at cfg1 layer sizes, 128-sample slices of the "
-                                  f"512 batch, {busy:.1f} s of timed CPU work (median step); the reference's TF-1.6 CPU "
+                        "sample": f"fwd+bwd of the oracle's torch-CPU port at cfg1 layer sizes and cfg1's batch ({B}), "
+                                  f"{busy:.1f} s of timed CPU work (median step); the reference's TF-1.6 CPU "
                                   f"path cannot run in this image"}
 
     if rank == 0:
@@ -393,7 +627,10 @@ def run_ours(args):
             "warmup": W, "ms_per_step": ms_value / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
-                       "precision": args.precision, "parallelism": f"dp{world}",
+                       "precision": args.precision, "parallelism": f"dp{world}", "gradient_collective": collective,
+                       "dp_step_check": dp_check,
+                       "gru_kernels": {1: "CTA-pair (gru_pair.cu)", 2: "single-CTA (gru.cu)"}.get(int(lib.vqa_gru_kernel_path()) & 3, "?")
+                                      + (" [pair launch REFUSED earlier]" if int(lib.vqa_gru_kernel_path()) & 256 else ""),
                        "l2_policy": f"inputs larger than L2: {n_img}-image feature bank ({bank.numel() * 4 / 1e9:.2f} GB fp32"
                                     + (f" + its one-off {bank.numel() * 2 / 1e9:.2f} GB bf16 copy, which the gather reads"
                                        if eng.bank_bf16 is not None else "")
@@ -406,6 +643,8 @@ def run_ours(args):
             "step_roofline": {"t_roof_ms": t_roof_ms, "frac": step_frac,
                               "model": "356.1 GF / bf16 sustained + 561.8 MB / HBM (BASELINE.md section 3)"},
             "attn_hbm": attn,
+            "sections": sections,
+            "fp32_mode": fp32_mode,
             "phase_ms": phase_ms,
             "critical_path_ms": critical_ms,
             "cpu_baseline": cpu_baseline,
@@ -434,9 +673,14 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--bank-images", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement (N = 1 only)")
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--infer-batches", default="64,512,4096,8192")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "infer":
+        return run_infer(args)
     return run_ours(args)
 
 

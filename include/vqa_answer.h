@@ -241,6 +241,12 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out);
 VQA_API VqaStatus vqa_destroy(VqaHandle h);
 VQA_API const char* vqa_last_error(void);
 VQA_API int32_t vqa_abi_version(void);
+/* which recurrent (GRU) kernels the most recent forward used: bit 0 = the CTA-pair kernels (csrc/gru_pair.cu), bit 1 =
+ * the single-CTA kernels (csrc/gru.cu: ~2x slower per phase; taken when the batch needs more row tiles than one wave of
+ * CTA pairs or when the cluster + cooperative launch was refused), bit 8 = such a refusal happened in this process
+ * (also reported once on stderr and in vqa_last_error()). Replaces nothing in the reference (tf.nn.dynamic_rnn,
+ * vlmap/modules.py:131-135, has no kernel choice); it exists so that a silent 2x slowdown cannot hide. */
+VQA_API int32_t vqa_gru_kernel_path(void);
 /* number of kernels this library has enqueued so far in this process */
 VQA_API uint64_t vqa_launch_count(void);
 
@@ -293,6 +299,15 @@ VQA_API VqaStatus vqa_dropout_mask_site(VqaHandle h, int32_t site, int32_t batch
  * backward is joined by the next vqa_forward, or explicitly by vqa_sync_outputs(h, stream). Off by default. */
 VQA_API VqaStatus vqa_set_deferred_outputs(VqaHandle h, int32_t enable);
 VQA_API VqaStatus vqa_sync_outputs(VqaHandle h, void* stream);
+
+/* Index inputs out of range. The reference fails loudly: tf.nn.embedding_lookup raises on a token id outside [0, Vq)
+ * (vqa/model_vlmap_answer.py:134) and np.take raises on an image_idx outside [-N, N) while WRAPPING negative ones
+ * (parse_fn's default for a missing feature is -1 = the last image; vqa/model_vlmap_answer.py:110-117,
+ * vqa/datasets/input_ops_vqa_tf_record_memft.py:28-46). Kernels cannot raise: the gathers wrap a negative image_idx
+ * like np.take, replace anything still out of range by index 0 (no out-of-bounds read, no out-of-bounds atomicAdd in
+ * the embedding scatter-add) and count it in a sticky per-process device counter. This call copies the counter to the
+ * host (it SYNCHRONISES with the device) and optionally clears it; the Python host raises when it is non-zero. */
+VQA_API VqaStatus vqa_input_error_count(uint32_t* count, int32_t reset);
 
 /* Data-parallel overlap (vqa/trainer.py has no distributed code; this is the B200 side of SURVEY 8e).
  * With early gradients enabled, vqa_backward produces the gradients of everything EXCEPT the embedding and the GRU

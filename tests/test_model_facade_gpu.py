@@ -84,9 +84,9 @@ def test_tfrecord_batches_feed_the_model(tmp_path):
     assert np.array_equal(rb["answer_target"], batch["answer_target"])
     assert np.array_equal(rb["q_intseq_len"], batch["q_intseq_len"])
     model = importer.get_model_class("vlmap_answer")(batch, config, is_train=False, image_features=feats)
-    model.forward(batch)
+    model.forward(batch, dropout_step=0)
     ref = model.output["logit"].clone()
-    model.forward(rb)     # T of this batch = its longest question (padded_batch), not the configured maximum
+    model.forward(rb, dropout_step=0)     # T of this batch = its longest question (padded_batch), not the configured maximum
     assert torch.allclose(model.output["logit"], ref, rtol=1e-5, atol=1e-5)
 
 
@@ -109,7 +109,16 @@ def test_checkpoint_bundle_round_trip(tmp_path):
     m2 = cls(batch, config2, is_train=False, image_features=feats)     # different initial weights
     m2.load_checkpoint(prefix)
     assert m2.global_step == 2
-    m1.forward(batch)
-    m2.seed, m2.global_step = m1.seed, m1.global_step                   # same dropout draw
-    m2.forward(batch)
+    m1.forward(batch, dropout_step=5)
+    m2.seed = m1.seed
+    m2.forward(batch, dropout_step=5)                                   # same dropout draw
     assert torch.equal(m1.output["logit"], m2.output["logit"])
+    # the optimizer slots travel with the checkpoint under the reference's names (tf.train.Saver of vqa/trainer.py:141-147)
+    assert {"optimizer/TunedWordWeightAnswer/fc/weights/Adam", "optimizer/beta1_power",
+            "optimizer/encode_L/rnn/gru_cell/gates/kernel/Adam_1"} <= names
+    assert m2.engine.adam_t == 2 and torch.equal(m2.engine.params.adam_m, m1.engine.params.adam_m)
+    # evaluation draws a fresh dropout mask per call (tf.nn.dropout has no train switch, one draw per session.run)
+    m1.forward(batch)
+    a = m1.output["logit"].clone()
+    m1.forward(batch)
+    assert not torch.equal(a, m1.output["logit"])

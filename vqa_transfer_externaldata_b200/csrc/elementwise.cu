@@ -52,13 +52,35 @@ __global__ void split_bf16_kernel(const float* __restrict__ src, long long rows,
   }
 }
 
+// Range checks of the two index inputs (the reference: np.take wraps negative image_idx -- parse_fn's default for a
+// missing feature is -1 -> the LAST image, vqa/model_vlmap_answer.py:110-117 --, raises on the rest; tf.nn.embedding_lookup
+// raises on an id outside [0, Vq)). A kernel cannot raise: it counts the offence in a sticky device counter that the
+// host reads with vqa_input_error_count (Engine.read_scalars raises) and uses index 0, so nothing is read or, in the
+// scatter-add, WRITTEN out of bounds.
+__device__ unsigned int g_input_errors = 0;
+__device__ __forceinline__ long long checked_image(long long img, long long num_images, bool count) {
+  if (img < 0) img += num_images;
+  if (img < 0 || img >= num_images) {
+    if (count) atomicAdd(&g_input_errors, 1u);
+    img = 0;
+  }
+  return img;
+}
+__device__ __forceinline__ int checked_token(int id, int vocab, bool count) {
+  if (id < 0 || id >= vocab) {
+    if (count) atomicAdd(&g_input_errors, 1u);
+    id = 0;
+  }
+  return id;
+}
+
 // the same gather from the one-off bf16 copy of the bank: a 16-byte row copy
 __global__ void __launch_bounds__(1024) gather_features_bf16_kernel(const bf16* __restrict__ bank, const int* __restrict__ num_boxes,
                                             const long long* __restrict__ image_idx, int batch, long long per_image8,
-                                            bf16* __restrict__ v_hi, int* __restrict__ nbox) {
+                                            bf16* __restrict__ v_hi, int* __restrict__ nbox, long long num_images) {
   pdl_sync();
   for (int b = blockIdx.y; b < batch; b += gridDim.y) {
-    const long long img = image_idx[b];
+    const long long img = checked_image(image_idx[b], num_images, blockIdx.x == 0 && threadIdx.x == 0);
     if (blockIdx.x == 0 && threadIdx.x == 0) nbox[b] = num_boxes[img];
     const uint4* src = reinterpret_cast<const uint4*>(bank) + img * per_image8;
     uint4* dst = reinterpret_cast<uint4*>(v_hi) + static_cast<long long>(b) * per_image8;
@@ -73,11 +95,11 @@ __global__ void __launch_bounds__(1024) gather_features_bf16_kernel(const bf16* 
 __global__ void __launch_bounds__(1024) gather_features_kernel(const float* __restrict__ bank, const int* __restrict__ num_boxes,
                                        const long long* __restrict__ image_idx, int batch,
                                        long long per_image4, bf16* __restrict__ v_hi,
-                                       bf16* __restrict__ v_lo, int* __restrict__ nbox) {
+                                       bf16* __restrict__ v_lo, int* __restrict__ nbox, long long num_images) {
   pdl_sync();
   // gridDim.y == batch for the in-step gather; the background prefetch runs a small grid that walks the samples
   for (int b = blockIdx.y; b < batch; b += gridDim.y) {
-    const long long img = image_idx[b];
+    const long long img = checked_image(image_idx[b], num_images, blockIdx.x == 0 && threadIdx.x == 0);
     if (blockIdx.x == 0 && threadIdx.x == 0) nbox[b] = num_boxes[img];
     const float4* src = reinterpret_cast<const float4*>(bank) + img * per_image4;
     const long long dst0 = static_cast<long long>(b) * per_image4 * 4;
@@ -94,11 +116,11 @@ __global__ void __launch_bounds__(1024) gather_features_kernel(const float* __re
 // time-major so that each GRU step reads a contiguous [batch, W] slab. Columns [W, Wpad) are zero.
 __global__ void embed_gather_kernel(const float* __restrict__ embed, const int* __restrict__ q_intseq,
                                     int batch, int T, int Tstride, int W, int Wpad,
-                                    bf16* __restrict__ e_hi, bf16* __restrict__ e_lo) {
+                                    bf16* __restrict__ e_hi, bf16* __restrict__ e_lo, int vocab) {
   const int row = blockIdx.x;  // t * batch + b
   const int t = row / batch, b = row - t * batch;
   pdl_sync();
-  const int id = q_intseq[b * Tstride + t];
+  const int id = checked_token(q_intseq[b * Tstride + t], vocab, threadIdx.x == 0);
   const float* src = embed + static_cast<long long>(id) * W;
   for (int c = threadIdx.x; c < Wpad; c += blockDim.x) {
     const float x = c < W ? src[c] : 0.0f;
@@ -113,12 +135,12 @@ __global__ void embed_gather_kernel(const float* __restrict__ embed, const int* 
 __global__ void embed_scatter_add_kernel(const float* __restrict__ dE, long long ld,
                                          const int* __restrict__ q_intseq, const int* __restrict__ q_len,
                                          int batch, int T, int Tstride, int W,
-                                         float* __restrict__ d_embed) {
+                                         float* __restrict__ d_embed, int vocab) {
   const int row = blockIdx.x;
   const int t = row / batch, b = row - t * batch;
   pdl_sync();
   if (t >= q_len[b]) return;
-  const int id = q_intseq[b * Tstride + t];
+  const int id = checked_token(q_intseq[b * Tstride + t], vocab, false);   // (the forward gather counted it)
   float* dst = d_embed + static_cast<long long>(id) * W;
   const float* src = dE + static_cast<long long>(row) * ld;
   for (int c = threadIdx.x; c < W; c += blockDim.x) atomicAdd(dst + c, src[c]);
@@ -316,22 +338,23 @@ VqaStatus gather_exclusive_launch(void (*kern)(P...), int ctas, cudaStream_t s, 
 }  // namespace
 
 VqaStatus gather_features_bf16_launch(const bf16* bank, const int* num_boxes, const long long* image_idx, int batch,
-                                      int K, int Dv, bf16* v_hi, int* nbox, cudaStream_t s, int max_ctas) {
+                                      int K, int Dv, bf16* v_hi, int* nbox, long long num_images, cudaStream_t s,
+                                      int max_ctas) {
   if (batch == 0) return VQA_OK;
   const long long per_image8 = static_cast<long long>(K) * Dv / 8;
   if (max_ctas > 0)
     return gather_exclusive_launch(gather_features_bf16_kernel, max_ctas < batch ? max_ctas : batch, s, bank, num_boxes,
-                                   image_idx, batch, per_image8, v_hi, nbox);
+                                   image_idx, batch, per_image8, v_hi, nbox, num_images);
   int gx = static_cast<int>((per_image8 + 255) / 256);
   if (gx > 8) gx = 8;
   launch_pdl(gather_features_bf16_kernel, dim3(gx, batch), dim3(256), 0, s, bank, num_boxes, image_idx, batch, per_image8,
-             v_hi, nbox);
+             v_hi, nbox, num_images);
   VQA_LAUNCH_CHECK("gather_features (bf16 bank)");
   return VQA_OK;
 }
 
 VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const long long* image_idx,
-                                 int batch, int K, int Dv, bf16* v_hi, bf16* v_lo, int* nbox,
+                                 int batch, int K, int Dv, bf16* v_hi, bf16* v_lo, int* nbox, long long num_images,
                                  cudaStream_t s, int max_ctas) {
   if (batch == 0) return VQA_OK;
   const long long per_image4 = static_cast<long long>(K) * Dv / 4;
@@ -344,31 +367,42 @@ VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const 
     // 2-CTA clusters itself, and single CTAs scattered over twenty TPCs would leave it twenty SM pairs short (a
     // cooperative launch then waits for the copy to finish: measured)
     return gather_exclusive_launch(gather_features_kernel, max_ctas < batch ? max_ctas : batch, s, bank, num_boxes, image_idx,
-                                   batch, per_image4, v_hi, v_lo, nbox);
+                                   batch, per_image4, v_hi, v_lo, nbox, num_images);
   }
   dim3 grid(gx, gy);
   launch_pdl(gather_features_kernel, dim3(grid), dim3(256), 0, s, bank, num_boxes, image_idx, batch, per_image4, v_hi,
-                                              v_lo, nbox);
+                                              v_lo, nbox, num_images);
   VQA_LAUNCH_CHECK("gather_features");
   return VQA_OK;
 }
 
 VqaStatus embed_gather_launch(const float* embed, const int* q_intseq, int batch, int T, int Tstride,
-                              int W, int Wpad, int /*Bpad*/, bf16* e_hi, bf16* e_lo, cudaStream_t s) {
+                              int W, int Wpad, int vocab, bf16* e_hi, bf16* e_lo, cudaStream_t s) {
   if (batch * T == 0) return VQA_OK;
   launch_pdl(embed_gather_kernel, dim3(batch * T), dim3(128), 0, s, embed, q_intseq, batch, T, Tstride, W, Wpad, e_hi,
-                                                e_lo);
+                                                e_lo, vocab);
   VQA_LAUNCH_CHECK("embed_gather");
   return VQA_OK;
 }
 
 VqaStatus embed_scatter_add_launch(const float* dE, long long ld_dE, const int* q_intseq,
-                                   const int* q_len, int batch, int T, int Tstride, int W, int /*Bpad*/,
+                                   const int* q_len, int batch, int T, int Tstride, int W, int vocab,
                                    float* d_embed, cudaStream_t s) {
   if (batch * T == 0) return VQA_OK;
   launch_pdl(embed_scatter_add_kernel, dim3(batch * T), dim3(128), 0, s, dE, ld_dE, q_intseq, q_len, batch, T, Tstride, W,
-                                                     d_embed);
+                                                     d_embed, vocab);
   VQA_LAUNCH_CHECK("embed_scatter_add");
+  return VQA_OK;
+}
+
+VqaStatus input_error_count(unsigned int* out, bool reset) {
+  unsigned int v = 0;
+  VQA_CUDA_CHECK(cudaMemcpyFromSymbol(&v, g_input_errors, sizeof(v)));   // synchronises with the device
+  if (reset && v) {
+    const unsigned int zero = 0;
+    VQA_CUDA_CHECK(cudaMemcpyToSymbol(g_input_errors, &zero, sizeof(zero)));
+  }
+  *out = v;
   return VQA_OK;
 }
 

@@ -722,6 +722,12 @@ extern "C" __attribute__((visibility("default"))) void vqa_internal_set_gru_trac
   g_gru_trace = static_cast<unsigned long long*>(dev_ptr);
 }
 
+// which recurrent kernels ran last: bit 0 = CTA-pair kernels, bit 1 = single-CTA kernels, bit 8 = a pair launch was
+// refused earlier in this process (sticky)
+extern "C" __attribute__((visibility("default"))) int32_t vqa_gru_kernel_path(void) {
+  return (g_fwd_was_pair ? 1 : 2) | (g_pair_refused ? 256 : 0);
+}
+
 bool gru_persistent_supported(int B, int L, int precision, int num_sms) {
   (void)B;
   if (precision != VQA_PREC_BF16) return false;
@@ -748,7 +754,11 @@ static bool try_pair(cudaError_t e, const char* what) {
     return true;
   }
   cudaGetLastError();
-  if (getenv("VQA_VERBOSE")) fprintf(stderr, "[vqa] %s: pair launch refused (%s): single-CTA kernels from now on\n", what, cudaGetErrorString(e));
+  // LOUD: the single-CTA kernels are ~2x slower per phase (profiles/r01_launch_summary_v3.md); a process that lost
+  // the pair kernels says so on stderr, in vqa_last_error() and in vqa_gru_kernel_path() (bench.py prints it)
+  fprintf(stderr, "[vqa] WARNING %s: CTA-pair recurrent kernel launch refused (%s): falling back to the slower single-CTA "
+          "kernels for the rest of this process\n", what, cudaGetErrorString(e));
+  set_error(VQA_OK, "%s: CTA-pair recurrent kernel launch refused (%s); single-CTA fallback in use", what, cudaGetErrorString(e));
   g_pair_refused = true;
   return false;
 }

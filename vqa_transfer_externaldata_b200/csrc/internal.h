@@ -75,15 +75,17 @@ bool cached_tmap_kind(CUtensorMap_st* out, const void* base, int kind, uint64_t 
 VqaStatus split_bf16_launch(const float* src, long long rows, long long cols, long long ld, bf16* hi,
                             bf16* lo, long long ld_out, cudaStream_t s);
 VqaStatus gather_features_launch(const float* bank, const int* num_boxes, const long long* image_idx,
-                                 int batch, int K, int Dv, bf16* v_hi, bf16* v_lo, int* nbox,
+                                 int batch, int K, int Dv, bf16* v_hi, bf16* v_lo, int* nbox, long long num_images,
                                  cudaStream_t s, int max_ctas = 0);
 VqaStatus gather_features_bf16_launch(const bf16* bank, const int* num_boxes, const long long* image_idx, int batch,
-                                      int K, int Dv, bf16* v_hi, int* nbox, cudaStream_t s, int max_ctas = 0);
+                                      int K, int Dv, bf16* v_hi, int* nbox, long long num_images, cudaStream_t s,
+                                      int max_ctas = 0);
 VqaStatus embed_gather_launch(const float* embed, const int* q_intseq, int batch, int T, int Tstride,
-                              int W, int Wpad, int Bpad, bf16* e_hi, bf16* e_lo, cudaStream_t s);
+                              int W, int Wpad, int vocab, bf16* e_hi, bf16* e_lo, cudaStream_t s);
 VqaStatus embed_scatter_add_launch(const float* dE, long long ld_dE, const int* q_intseq,
-                                   const int* q_len, int batch, int T, int Tstride, int W, int Bpad,
+                                   const int* q_len, int batch, int T, int Tstride, int W, int vocab,
                                    float* d_embed, cudaStream_t s);
+VqaStatus input_error_count(unsigned int* out, bool reset);   // sticky count of out-of-range image_idx / token ids
 VqaStatus colsum_launch(const float* x, long long rows, long long cols, long long ld, float* out,
                         float* scratch, cudaStream_t s);
 VqaStatus fill_zero_launch(void* p, size_t bytes, cudaStream_t s);

@@ -108,10 +108,10 @@ VqaStatus launch_pending_prefetch(VqaHandle h, cudaStream_t a4) {
   if (h->pf_bank.features_bf16 && c.precision == VQA_PREC_BF16)
     VQA_TRY(gather_features_bf16_launch(static_cast<const bf16*>(h->pf_bank.features_bf16), h->pf_bank.num_boxes,
                                         static_cast<const long long*>(h->pf_idx), h->pf_batch, c.K, c.Dv, b.v_alt.hi,
-                                        b.nbox_alt, a4, free_sms));
+                                        b.nbox_alt, h->pf_bank.num_images, a4, free_sms));
   else
     VQA_TRY(gather_features_launch(h->pf_bank.features, h->pf_bank.num_boxes, static_cast<const long long*>(h->pf_idx),
-                                   h->pf_batch, c.K, c.Dv, b.v_alt.hi, b.v_alt.lo, b.nbox_alt, a4, free_sms));
+                                   h->pf_batch, c.K, c.Dv, b.v_alt.hi, b.v_alt.lo, b.nbox_alt, h->pf_bank.num_images, a4, free_sms));
   VQA_CUDA_CHECK(cudaEventRecord(h->ev_prefetch, a4));
   h->prefetched = true;
   h->prefetched_idx = h->pf_idx;
@@ -198,6 +198,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   if (!bank->features || !bank->num_boxes || !batch->image_idx || !batch->q_intseq ||
       !batch->q_intseq_len || !batch->answer_target)
     return set_error(VQA_ERR_BAD_ARG, "vqa_forward: null batch / bank pointer");
+  if (bank->num_images <= 0) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: feature bank with num_images %lld", static_cast<long long>(bank->num_images));
   h->fwd_valid = false;
   if (Bn == 0) return VQA_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -218,7 +219,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   // epilogue/store-bound and overlaps the MMA-bound v-projection below      (:134-137, modules.py:124-140)
   cudaStream_t s1 = s;
   auto gru_inputs = [&](cudaStream_t st) -> VqaStatus {
-    VQA_TRY(embed_gather_launch(p->embed, batch->q_intseq, Bn, T, T, W, Wp, Bn, b.e.hi, b.e.lo, st));
+    VQA_TRY(embed_gather_launch(p->embed, batch->q_intseq, Bn, T, T, W, Wp, c.Vq, b.e.hi, b.e.lo, st));
     VQA_TRY(GemmB(T * Bn, 2 * L, W).a(b.e, 0, Wp, false).b(b.w.gru_gates_w, 0, 2 * L, true)
                 .bias(p->gru_gates_b).f32(b.xg, 2 * L).run(h, st));
     VQA_TRY(GemmB(T * Bn, L, W).a(b.e, 0, Wp, false).b(b.w.gru_cand_w, 0, L, true)
@@ -244,11 +245,12 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_prefetch, 0));
   } else if (bank->features_bf16 && !fp32) {
     VQA_TRY(gather_features_bf16_launch(static_cast<const bf16*>(bank->features_bf16), bank->num_boxes,
-                                        reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi, b.nbox, s));
+                                        reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi, b.nbox,
+                                        bank->num_images, s));
   } else {
     VQA_TRY(gather_features_launch(bank->features, bank->num_boxes,
                                    reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi,
-                                   b.v.lo, b.nbox, s));
+                                   b.v.lo, b.nbox, bank->num_images, s));
   }
   h->prefetched = false;
   h->pf_pending = false;   // a request no backward pass picked up (inference loops): this forward gathered itself
@@ -948,7 +950,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
         if (h->slice_slot)
           VQA_TRY(rows_sumsq_launch(b.dE, TB, W, Wp, h->slice_slot, b.scratch + 5 * b.scratch_floats, st));   // auxiliary stream 4's scratch region: its gather uses none
         VQA_TRY(fill_zero_launch(g->embed, sizeof(float) * c.Vq * W, st));
-        VQA_TRY(embed_scatter_add_launch(b.dE, Wp, batch->q_intseq, batch->q_intseq_len, Bn, T, T, W, Bn,
+        VQA_TRY(embed_scatter_add_launch(b.dE, Wp, batch->q_intseq, batch->q_intseq_len, Bn, T, T, W, c.Vq,
                                          g->embed, st));
       }
       return VQA_OK;
@@ -1043,6 +1045,14 @@ VQA_API VqaStatus vqa_reparam_noise(VqaHandle h, int32_t batch, uint64_t seed, u
   if (!h || !noise) return set_error(VQA_ERR_BAD_ARG, "vqa_reparam_noise: null argument");
   return reparam_noise_launch(noise, static_cast<long long>(batch) * h->cfg.L, seed, step,
                               static_cast<cudaStream_t>(stream));
+}
+
+VQA_API VqaStatus vqa_input_error_count(uint32_t* count, int32_t reset) {
+  if (!count) return set_error(VQA_ERR_BAD_ARG, "vqa_input_error_count: null argument");
+  unsigned int v = 0;
+  VQA_TRY(input_error_count(&v, reset != 0));
+  *count = v;
+  return VQA_OK;
 }
 
 VQA_API VqaStatus vqa_set_early_gradients(VqaHandle h, int32_t enable) {

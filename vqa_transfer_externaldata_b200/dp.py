@@ -93,6 +93,76 @@ class DataParallel:
         if w2 is not None:
             w2.wait()
 
+    def self_check(self, device=None, per_rank=32, tol=None):
+        """Hardware check of the data-parallel step on THIS job's ranks and collective: every rank runs forward +
+        backward(loss_scale = 1 / world) on its shard of one global batch and the gradients are all-reduced exactly as
+        in training (the in-switch multimem kernel when available, NCCL otherwise); rank 0 also runs the SAME global
+        batch as one single-rank step. The two gradient sets must agree per tensor to `tol` (max-norm relative; default
+        1e-5 in fp32 mode, 5e-5 in bf16 mode: the sums over the batch are formed in a different order) and be
+        bit-identical across ranks. Dropout is off (keep = 1): a rank's mask is keyed by its local element index.
+        Returns {precision: worst relative error}; raises AssertionError on a mismatch."""
+        import numpy as np
+        from . import synthetic as S
+        from .engine import AnswerModelConfig, Engine
+        if self.world_size == 1:
+            return {}
+        world, rank = self.world_size, self.rank
+        device = device if device is not None else torch.device(f"cuda:{self.local_rank}")
+        Bg = per_rank * world
+        dims = dict(K=12, Dv=256, D=128, L=128, A=200, T=6, W=20, Vq=50)
+        out = {}
+        keep_mc = self._mc
+        for precision in ("fp32", "bf16"):
+            limit = tol if tol is not None else (1e-5 if precision == "fp32" else 5e-5)
+            cg = S.dims(B=Bg, **dims)
+            params, exist = S.init_params(cg, seed=11, perturb=0.2)
+            feats, nb = S.make_bank(cg, num_images=40, seed=12, ragged_boxes=True)
+            batch = S.make_batch(cg, 40, seed=13)
+            is_obj, is_attr = S.make_answer_flags(cg)
+
+            def run(B, sub, scale, reduce):
+                c = S.dims(B=B, **dims)
+                eng = Engine(AnswerModelConfig(variant="vlmap_answer", precision=precision, keep_att=1.0, keep_joint=1.0, **c),
+                             device=device)
+                eng.set_feature_bank(feats, nb)
+                eng.set_answer_masks(is_obj, is_attr, exist)
+                eng.load_params(params)
+                if reduce:
+                    self._mc = None
+                    self.use_multicast_gradients(eng)
+                eng.stage_batch(sub)
+                eng.forward(seed=1, step=1)
+                eng.backward(loss_scale=scale)
+                if reduce:
+                    self.all_reduce_gradients(eng)
+                torch.cuda.synchronize(device)
+                g = {f: v.detach().clone() for f, v in eng.params.grad_views.items()}
+                used_mc = self._mc is not None
+                eng.close()
+                return g, used_mc
+
+            s0, s1 = self.shard(Bg)
+            g_dp, used_mc = run(s1 - s0, {k: v[s0:s1] for k, v in batch.items()}, 1.0 / world, True)
+            flat = torch.cat([g_dp[f].reshape(-1) for f in sorted(g_dp)])
+            ref0 = flat.clone()
+            dist.broadcast(ref0, src=0)
+            same = bool(torch.equal(ref0, flat))
+            worst = 0.0
+            if rank == 0:
+                g_one, _ = run(Bg, batch, 1.0, False)
+                for f in sorted(g_dp):
+                    a, b = g_dp[f].double(), g_one[f].double()
+                    err = float((a - b).abs().max() / max(float(b.abs().max()), 1e-30))
+                    worst = max(worst, err)
+            worst = self.max_over_ranks(worst)
+            n_diff = self.max_over_ranks(0.0 if same else 1.0)
+            assert n_diff == 0.0, f"data-parallel gradients differ between ranks ({precision})"
+            assert worst <= limit, f"data-parallel step != single-rank step on the concatenated batch ({precision}): {worst:.3e} > {limit:.1e}"
+            out[precision] = worst
+            out["collective"] = "multimem" if used_mc else "nccl"
+        self._mc = keep_mc
+        return out
+
     def barrier(self):
         if self.world_size > 1:
             dist.barrier()

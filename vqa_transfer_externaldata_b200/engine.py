@@ -244,6 +244,7 @@ class BatchSet:
         self.h_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32).pin_memory()
         self.batch_size, self.q_len_max = 0, cfg.T
         self.ready = torch.cuda.Event()
+        self.staged = None   # event after the last H2D copies out of the pinned staging buffers of this set
         self.source = None   # the host batch object this set was filled from (prefetch bookkeeping)
 
 
@@ -423,17 +424,61 @@ class Engine:
                  ("q_intseq_len", bs.h_qlen, bs.d_qlen, torch.int32, np.int32, Bn),
                  ("answer_target", bs.h_target, bs.d_target, torch.float32, np.float32, Bn * cfg.A))
         nbytes = 0
+        used_staging = False
         for key, hbuf, dbuf, tdt, ndt, n in items:
             v = batch[key]
-            if isinstance(v, torch.Tensor) and v.dtype == tdt and v.is_contiguous() and (v.is_pinned() or v.is_cuda):
+            direct = isinstance(v, torch.Tensor) and v.dtype == tdt and v.is_contiguous() and (v.is_pinned() or v.is_cuda)
+            if not (direct and v.is_cuda):
+                self._validate(key, v, Bn, T)   # host inputs are range-checked here; device-resident ones by the kernels
+            if direct:
                 src = v.view(-1)   # pinned host memory, or already on the device (device-resident input pipelines)
             else:
+                if not used_staging and bs.staged is not None:
+                    # the previous upload out of this set's pinned staging buffers may still be queued behind kernels
+                    # (train_step(sync=False) lets the host run ahead): rewriting them now would change THAT step's data
+                    bs.staged.synchronize()
+                used_staging = True
                 hbuf[:n].copy_(torch.from_numpy(np.ascontiguousarray(np.asarray(v, dtype=ndt)).reshape(-1)))
                 src = hbuf[:n]
             dbuf[:n].copy_(src, non_blocking=True)
             nbytes += n * dbuf.element_size()
+        if used_staging:
+            if bs.staged is None:
+                bs.staged = torch.cuda.Event()
+            bs.staged.record(torch.cuda.current_stream(self.device))
         bs.batch_size, bs.q_len_max = Bn, T
         return nbytes
+
+    def _validate(self, key, v, Bn, T):
+        """Range checks of a HOST batch field, with the reference's error behaviour: tf.nn.embedding_lookup raises on
+        ids outside [0, Vq), np.take on an image_idx outside [-N, N) (negative ones wrap: parse_fn's default for a
+        missing feature is -1, vqa/datasets/input_ops_vqa_tf_record_memft.py:28-46), dynamic_rnn needs
+        0 <= len <= T. Device-resident inputs are checked by the kernels instead (vqa_input_error_count)."""
+        if key == "answer_target":
+            return
+        a = v.numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+        if a.size == 0:
+            return
+        lo, hi = int(a.min()), int(a.max())
+        if key == "image_idx":
+            n = int(self.bank.num_images) if self.bank is not None else None
+            if n is not None and (lo < -n or hi >= n):
+                raise IndexError(f"image_idx out of range: [{lo}, {hi}] for a feature bank of {n} images")
+        elif key == "q_intseq":
+            if lo < 0 or hi >= self.cfg.Vq:
+                raise IndexError(f"q_intseq token id out of range: [{lo}, {hi}] for a vocabulary of {self.cfg.Vq}")
+        elif key == "q_intseq_len":
+            if lo < 0 or hi > T:
+                raise ValueError(f"q_intseq_len out of range: [{lo}, {hi}] for padded length {T}")
+
+    def check_input_errors(self):
+        """Raise if a gather kernel met an out-of-range image_idx / token id since the last check (device-resident
+        inputs; host inputs never get that far). Synchronises with the device."""
+        n = C.c_uint32()
+        L.check(self.lib.vqa_input_error_count(C.byref(n), 1))
+        if n.value:
+            raise IndexError(f"{n.value} out-of-range image_idx / q_intseq entries reached the device gathers "
+                             "(replaced by index 0; results of those samples are meaningless)")
 
     def stage_batch(self, batch):
         """Upload `batch` into the active set on the current stream (or adopt it if prefetch_batch already
@@ -577,6 +622,7 @@ class Engine:
         self.sync_outputs()
         self.h_scalars.copy_(self.o_scalars, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self.check_input_errors()
         vals = self.h_scalars.tolist()
         full = dict(zip(self._all_report_keys, vals[1:]))
         return vals[0], {k: full[k] for k in self.report_keys}

@@ -142,6 +142,7 @@ SYMBOLS = {
     "vqa_last_error": (C.c_char_p, []),
     "vqa_abi_version": (C.c_int32, []),
     "vqa_launch_count": (C.c_uint64, []),
+    "vqa_gru_kernel_path": (C.c_int32, []),
     "vqa_crc32c": (C.c_uint32, [C.c_char_p, C.c_uint64]),
     "vqa_workspace_bytes": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "vqa_set_workspace": (C.c_int32, [_P, _P, C.c_uint64]),
@@ -169,6 +170,7 @@ SYMBOLS = {
     "vqa_set_embedding_slice_norm": (C.c_int32, [_P, _P]),
     "vqa_set_deferred_outputs": (C.c_int32, [_P, C.c_int32]),
     "vqa_sync_outputs": (C.c_int32, [_P, _P]),
+    "vqa_input_error_count": (C.c_int32, [C.POINTER(C.c_uint32), C.c_int32]),
     "vqa_set_early_gradients": (C.c_int32, [_P, C.c_int32]),
     "vqa_stream_wait_early_gradients": (C.c_int32, [_P, _P]),
     "vqa_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaAttnFwd), _P]),

@@ -103,11 +103,10 @@ class Model(object):
         frozen_scopes = {tf_name(f, self.MODEL_TYPE).split("/")[0] for f in frozen_fields(self.MODEL_TYPE)}
         return [v for v in trainable_vars if _name(v).split("/")[0] not in frozen_scopes]
 
+    TRANSFER_SCOPES = ("q_linear_l", "pooled_linear_l", "joint_fc")   # vqa/model_vlmap_answer.py:91-100 (and siblings)
+
     def filter_transfer_vars(self, all_vars):
-        if self.MODEL_TYPE == "standard":  # vqa/model_standard.py:86-93
-            scopes = ("encode_L", "GloVe")
-        else:  # vqa/model_vlmap_answer.py:91-100
-            scopes = ("q_linear_l", "pooled_linear_l", "joint_fc")
+        scopes = self.TRANSFER_SCOPES
         return [v for v in all_vars if _name(v).split("/")[0] in scopes]
 
     # ---- graph construction == engine construction ---------------------------------------------
@@ -139,6 +138,7 @@ class Model(object):
                 self.dead_variables[name] = (np.ones if name.endswith("gamma") else np.zeros)(shape, np.float32)
         self.seed = int(getattr(cfgd, "seed", 123))
         self.global_step = 0
+        self.eval_draws = 0    # forward() calls so far outside train_step: each draws fresh dropout masks (see forward)
         self._dp = None
         return self.loss
 
@@ -154,6 +154,10 @@ class Model(object):
         glove = getattr(self.config, "glove_embed", None)
         if glove is not None:  # LearnGloVe (vlmap/modules.py:415-448): rows by vocabulary word
             p["embed"] = np.asarray(glove, np.float32)
+        elif getattr(self.config, "vocab_path", None):   # a real vocabulary without its GloVe table: say so
+            import warnings
+            warnings.warn("config.glove_embed is not set: LearnGloVe/embed_map starts from a random table instead of the "
+                          "GloVe rows the reference loads (vlmap/modules.py:415-448); restore a checkpoint or pass glove_embed")
         if self.MODEL_TYPE != "standard":
             if self.MODEL_TYPE in ("vlmap_answer_noc", "vlmap_answer_nocarch"):
                 # vqa/model_vlmap_answer_noc.py:189-201: v_class_* / l_class_* of export_noc_word_weights.py:74-82
@@ -191,16 +195,63 @@ class Model(object):
         from . import tf_bundle
         sd = self.state_dict()
         sd["global_step"] = np.asarray(self.global_step, np.int64)
+        sd.update(self.optimizer_state_dict())
         tf_bundle.write_bundle(prefix, sd)
 
+    # optimize_loss(..., optimizer=AdamOptimizer, name='optimizer') (vqa/trainer.py:106-114) applies the gradients inside
+    # variable_scope('optimizer'): tf.train.Saver stores the slots of every trained variable as `optimizer/<var>/Adam` (m)
+    # and `optimizer/<var>/Adam_1` (v), plus `optimizer/beta1_power` and `optimizer/beta2_power`
+    ADAM_SCOPE = "optimizer"
+
+    def optimizer_state_dict(self):
+        """Adam slots under the reference's checkpoint names (empty before the first optimizer step)."""
+        e = self.engine
+        ps = e.params
+        if ps.adam_m is None:
+            return {}
+        out = {}
+        for f in ps.trainable:
+            o, n = ps.offsets[f]
+            name = tf_name(f, self.MODEL_TYPE)
+            shape = self.engine_config.shape(f)
+            out[f"{self.ADAM_SCOPE}/{name}/Adam"] = ps.adam_m[o:o + n].view(shape).cpu().numpy().copy()
+            out[f"{self.ADAM_SCOPE}/{name}/Adam_1"] = ps.adam_v[o:o + n].view(shape).cpu().numpy().copy()
+        out[f"{self.ADAM_SCOPE}/beta1_power"] = np.asarray(0.9 ** e.adam_t, np.float32)
+        out[f"{self.ADAM_SCOPE}/beta2_power"] = np.asarray(0.999 ** e.adam_t, np.float32)
+        return out
+
+    def load_optimizer_state_dict(self, state):
+        """Restore m, v and the step count t (from beta1_power = 0.9^t) when the bundle carries them; returns whether it did."""
+        e = self.engine
+        ps = e.params
+        key = f"{self.ADAM_SCOPE}/beta1_power"
+        if key not in state:
+            return False
+        m = torch.zeros_like(ps.grad)
+        v = torch.zeros_like(ps.grad)
+        for f in ps.trainable:
+            o, n = ps.offsets[f]
+            name = tf_name(f, self.MODEL_TYPE)
+            km, kv = f"{self.ADAM_SCOPE}/{name}/Adam", f"{self.ADAM_SCOPE}/{name}/Adam_1"
+            if km not in state or kv not in state:
+                return False
+            m[o:o + n].copy_(torch.as_tensor(np.asarray(state[km], np.float32)).reshape(-1))
+            v[o:o + n].copy_(torch.as_tensor(np.asarray(state[kv], np.float32)).reshape(-1))
+        ps.adam_m, ps.adam_v = m, v
+        b1p = float(np.asarray(state[key]))
+        e.adam_t = int(round(np.log(b1p) / np.log(0.9))) if 0.0 < b1p < 1.0 else 0
+        return True
+
     def load_checkpoint(self, prefix, strict=True):
-        """Restore from a TensorFlow checkpoint bundle by variable name (vqa/trainer.py:173-186); optimizer slots and
-        other variables the path does not own are ignored."""
+        """Restore from a TensorFlow checkpoint bundle by variable name (vqa/trainer.py:173-186), Adam slots and beta
+        powers included when present (a resumed run continues the bias correction instead of restarting it at t = 1);
+        variables the path does not own are ignored."""
         from . import tf_bundle
         state = tf_bundle.read_bundle(prefix)
         if "global_step" in state:
             self.global_step = int(state["global_step"])
         self.load_state_dict(state, strict=strict)
+        self.load_optimizer_state_dict(state)
 
     # ---- running the path --------------------------------------------------------------------------
     def attach_data_parallel(self, dp):
@@ -213,12 +264,19 @@ class Model(object):
             dp.use_multicast_gradients(self.engine)   # in-switch all-reduce when NVSwitch multicast is available
         self.engine.set_early_gradients(dp is not None and dp.world_size > 1 and os.environ.get("VQA_DP_EARLY") == "1")
 
-    def forward(self, batch=None, full_outputs=True, defer_outputs=False):
-        """session.run([loss, report, output]) of the reference (vqa/evaler.py:118-123). Returns h2d bytes."""
+    def forward(self, batch=None, full_outputs=True, defer_outputs=False, dropout_step=None):
+        """session.run([loss, report, output]) of the reference (vqa/evaler.py:118-123). Returns h2d bytes.
+        tf.nn.dropout has no train switch: it fires in evaluation too, with a FRESH mask per session.run.
+        So every call draws its masks from its own Philox step: the global step inside train_step, and outside it a
+        counter of forward() calls placed above any reachable global step. dropout_step pins the draw (parity tests,
+        reproducing a given evaluation)."""
         b = self.batch if batch is None else batch
         nbytes = self.engine.stage_batch(b)
         rank = self._dp.rank if self._dp is not None else 0
-        self.engine.forward(seed=self.seed + 7919 * rank, step=self.global_step, full_outputs=full_outputs,
+        if dropout_step is None:
+            dropout_step = (1 << 40) + self.eval_draws
+            self.eval_draws += 1
+        self.engine.forward(seed=self.seed + 7919 * rank, step=int(dropout_step), full_outputs=full_outputs,
                             defer_outputs=defer_outputs)
         self._bind_outputs()
         return nbytes
@@ -245,7 +303,8 @@ class Model(object):
         step's kernels (the reference's tf.data pipeline prefetches the same way).
         sync=False: asynchronous dispatch -- `loss` is a handle whose .get() -> (loss, report) waits for this
         step only, so the host can enqueue step i+1 while the device runs step i."""
-        h2d = self.forward(batch, full_outputs=False, defer_outputs=True)   # the backward below joins the loss kernels
+        h2d = self.forward(batch, full_outputs=False, defer_outputs=True,   # the backward below joins the loss kernels
+                           dropout_step=self.global_step)
         if next_batch is not None:
             self.engine.prefetch_batch(next_batch)
         self.backward()
@@ -343,6 +402,7 @@ class NocModel(Model):
     branch (pooled_linear_l -> joint_v -> WordWeightAnswerV) and a language branch (q_linear_l -> joint_l ->
     WordWeightAnswerL), logits added; heads initialised from v_/l_class_weights of export_noc_word_weights.py."""
     MODEL_TYPE = "vlmap_answer_noc"
+    TRANSFER_SCOPES = ("q_linear_l", "pooled_linear_l", "joint_v", "joint_l")   # vqa/model_vlmap_answer_noc.py:90-101
 
 
 class NocArchModel(NocModel):
@@ -352,6 +412,7 @@ class NocArchModel(NocModel):
 class StandardModel(Model):
     """vqa/model_standard.py: same trunk, learned reasoning/classifier head, everything trainable."""
     MODEL_TYPE = "standard"
+    TRANSFER_SCOPES = ("encode_L", "GloVe")   # vqa/model_standard.py:86-93
 
 
 def _name(v):
