@@ -63,9 +63,12 @@ def build_case(dims, variant="vlmap_answer", precision="fp32", seed=0, num_image
     return dict(c=c, cfg=cfg, params=params, feats=feats, nb=nb, batch=bt, eng=eng, m=m)
 
 
-def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
+def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None, device_gates=None, gate_tie=None):
     """emulate: None = restate the device's operand rounding when the case runs in bf16 mode (the oracle then
-    makes the same ReLU gate decisions), False = always the reference's plain arithmetic."""
+    makes the same ReLU gate decisions), False = always the reference's plain arithmetic.
+    device_gates: take the ReLU gates of the 2-D heads from the device (every gate that differs from the oracle's own
+    decision must be a near-tie: |pre-activation| < gate_tie). Default: with `emulate`. At B 512 even the fp32 mode
+    meets a few dozen undecidable gates among 2.6 M, each of which would cost one more oracle backward to bound."""
     import torch
     eng, cfg = case["eng"], case["cfg"]
     eng.stage_batch(case["batch"])
@@ -103,7 +106,11 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
                                          att_mask=att_mask.cpu().numpy(), joint_mask=joint_mask.cpu().numpy(), **jl_kw)
     inter = {}
     gates = None
-    if emulate:
+    if device_gates is None:
+        device_gates = emulate
+    if gate_tie is None:
+        gate_tie = 2e-2 if emulate else 1e-4
+    if device_gates:
         # bf16 mode: the backward pass is linear in the ReLU gates, and a gate whose pre-activation is zero to
         # bf16 working precision is decided by rounding noise. Take the four 2-D heads' gates from the DEVICE
         # (its saved post-ReLU activations), account for every gate that differs from the oracle's own
@@ -133,7 +140,7 @@ def run_both(case, seed=777, step=3, loss_scale=1.0, emulate=None):
             n_diff += int(diff.sum())
             n_all += diff.size
             # a gate the device decided differently must be a near-tie of the oracle (|y| small vs O(1) LN output)
-            assert not diff.any() or np.abs(y[diff]).max() < 2e-2, (layer, np.abs(y[diff]).max())
+            assert not diff.any() or np.abs(y[diff]).max() < gate_tie, (layer, np.abs(y[diff]).max())
         assert n_diff <= max(2, 2e-3 * n_all), (n_diff, n_all)
         case["gate_diffs"] = (n_diff, n_all)
     ref_g = O.backward(cache, loss_scale=loss_scale, intermediates=inter, gate_override=gates)

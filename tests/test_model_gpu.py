@@ -91,7 +91,7 @@ def _check(case, got, ref, ref_g, tol, exact_pred=True, grad_metric="max", grad_
         budget, n_ties = relu_tie_budget(case["oracle_cache"], case["oracle_inter"], ref_g, list(bad),
                                          FP32_TIE_TAU, loss_scale=case["loss_scale"],
                                          layers=("v",) if go else None, gate_override=go,
-                                         max_ties=512 if go else 96)
+                                         max_ties=8192 if go else 96)
         for f in list(bad):
             diff = np.abs(got["grads"][f].astype(np.float64) - ref_g[f])
             if np.all(diff <= tol * np.abs(ref_g[f]).max() + 1.01 * budget[f]):

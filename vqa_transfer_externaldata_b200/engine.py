@@ -312,6 +312,7 @@ class Engine:
         # 2-CTA clusters on the ten TPCs the cooperative recurrent grid leaves idle; bit-identical results
         # (tests/test_model_gpu.py), ~1 % faster (1.032 vs 1.04 ms/step). VQA_PREFETCH_FEATURES=0 turns it off.
         self.prefetch_features = os.environ.get("VQA_PREFETCH_FEATURES", "1") != "0"
+        self.validate_inputs = os.environ.get("VQA_VALIDATE_INPUTS", "1") != "0"   # host-side range checks in _fill
 
     def close(self):
         if self.h:
@@ -428,7 +429,7 @@ class Engine:
         for key, hbuf, dbuf, tdt, ndt, n in items:
             v = batch[key]
             direct = isinstance(v, torch.Tensor) and v.dtype == tdt and v.is_contiguous() and (v.is_pinned() or v.is_cuda)
-            if not (direct and v.is_cuda):
+            if self.validate_inputs and not (direct and v.is_cuda):
                 self._validate(key, v, Bn, T)   # host inputs are range-checked here; device-resident ones by the kernels
             if direct:
                 src = v.view(-1)   # pinned host memory, or already on the device (device-resident input pipelines)

@@ -72,14 +72,20 @@ def answer_exist_mask(answer_dict, word_weight_dir=None):
     return np.array([1.0 if a in wdict["dict"] else 0.0 for a in answer_dict["vocab"]], dtype=np.float32)
 
 
-def export_word_weights(out_dir, class_weights, class_biases, answer_vocab, extra=None):
-    """Writer of the exporter's contract (vlmap_memft/export_word_weights.py:60-83) as the .npz mirror +
-    the two pickles, so that a round trip through word_weight_answer() can be tested without HDF5."""
+def export_word_weights(out_dir, class_weights, class_biases, answer_vocab, extra=None, npz_mirror=False):
+    """The exporter's contract (vlmap_memft/export_word_weights.py:60-83): `weights.hdf5` with the datasets
+    class_weights [J, A'], class_biases [A'] (+ v_word, l_word, l_answer_word, or the v_/l_class_* sets of
+    export_noc_word_weights.py:74-82, passed in `extra`) and the two pickles vocab.pkl / answer_dict.pkl. The HDF5 file
+    is written by hdf5_min (contiguous datasets, the layout h5py's create_dataset(data=...) produces); npz_mirror also
+    drops the .npz copy that _read_datasets prefers when present."""
+    from . import hdf5_min
     os.makedirs(out_dir, exist_ok=True)
     arrays = {"class_weights": np.asarray(class_weights, np.float32),
               "class_biases": np.asarray(class_biases, np.float32)}
-    arrays.update(extra or {})
-    np.savez(os.path.join(out_dir, "weights.npz"), **arrays)
+    arrays.update({k: np.asarray(v) for k, v in (extra or {}).items()})
+    hdf5_min.write(os.path.join(out_dir, "weights.hdf5"), arrays)
+    if npz_mirror:
+        np.savez(os.path.join(out_dir, "weights.npz"), **arrays)
     adict = {"vocab": list(answer_vocab), "dict": {a: i for i, a in enumerate(answer_vocab)}}
     for name in ("answer_dict.pkl", "vocab.pkl"):
         with open(os.path.join(out_dir, name), "wb") as f:
