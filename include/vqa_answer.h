@@ -426,6 +426,13 @@ VQA_API VqaStatus vqa_gemm(VqaHandle h, const VqaGemmDesc* d, void* stream);
 VQA_API VqaStatus vqa_split_bf16(VqaHandle h, const float* src, int64_t rows, int64_t cols, int64_t ld,
                                  void* hi, void* lo, int64_t ld_out, void* stream);
 
+/* The attention-feature dropout (tf.nn.dropout(feature, 0.8), vlmap/modules.py:82) of (seed, step) as a bit plane: one
+ * byte per group of 8 consecutive elements of the [batch, K, D] tensor, bit j = keep flag of element j -- the very bits
+ * vqa_dropout_masks materialises one byte per element. vqa_forward fills the workspace's plane once per step on an
+ * auxiliary stream (under the v-projection GEMM) and both attention kernels read it: 1 byte per 8 elements instead of
+ * ten Philox rounds per 8 elements in the forward AND in the backward kernel. n = batch*K*D must be a multiple of 8. */
+VQA_API VqaStatus vqa_keep_bits(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step, uint8_t* bits, void* stream);
+
 /* attention block forward: per-sample LayerNorm(K*D)+ReLU of z, Hadamard with hq, dropout, score,
  * masked softmax, attended pooling of the features (vlmap/modules.py:67-97, 23-39) */
 typedef struct VqaAttnFwd {
@@ -441,6 +448,8 @@ typedef struct VqaAttnFwd {
   float* pooled;            /* [batch, Dv]                                                    */
   void* pooled_hi; void* pooled_lo; /* bf16 planes of pooled for the next GEMM (may be NULL)   */
   float* ln_mean; float* ln_rstd;   /* [batch] saved statistics                               */
+  const uint8_t* keep_bits; /* [batch*K*D/8] dropout keep bits of (seed, step), one byte per 8 consecutive elements (bit j =
+                             * element j; vqa_keep_bits fills it), or NULL: the kernel then draws the same bits itself */
 } VqaAttnFwd;
 VQA_API VqaStatus vqa_attn_fwd(VqaHandle h, const VqaAttnFwd* a, void* stream);
 
@@ -454,6 +463,7 @@ typedef struct VqaAttnBwd {
   void* dz_hi; void* dz_lo; /* [batch*K, D] bf16 planes of d(pre-LN projection)               */
   float* d_hq;              /* [batch, D]                                                     */
   float* d_att_w; float* d_att_b; float* d_gamma; float* d_beta; float* d_bias; /* [D],[1],[D],[D],[D] */
+  const uint8_t* keep_bits; /* as in VqaAttnFwd (the SAME plane: the backward pass regenerates nothing)  */
 } VqaAttnBwd;
 VQA_API VqaStatus vqa_attn_bwd(VqaHandle h, const VqaAttnBwd* a, void* stream);
 

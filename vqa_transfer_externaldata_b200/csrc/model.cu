@@ -54,6 +54,15 @@ struct GemmB {  // builder with the conventions of VqaGemmDesc
   VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s, &h->gemm_ctx, narrow_); }
 };
 
+// The attention-dropout keep bits as a precomputed plane (vqa_keep_bits) instead of Philox inside the two attention
+// kernels. Measured on B200 (profiles/r02_attn_keep_bits.md): the kernels are latency-bound with idle ALUs, so the ten
+// Philox rounds were free and a byte fetched from global memory per 8 elements is NOT: forward 68 -> 77 us, backward
+// 102 -> 108 us. Off unless VQA_ATTN_KEEP_BITS=1; the entry point and the kernels' plane path stay (tests cover them).
+bool use_keep_bits(const VqaConfig& c, int K, int D) {
+  static const bool on = getenv("VQA_ATTN_KEEP_BITS") == nullptr || atoi(getenv("VQA_ATTN_KEEP_BITS")) != 0;
+  return on && c.keep_att < 1.0f && (static_cast<long long>(K) * D) % 8 == 0;
+}
+
 VqaStatus check_ready(VqaHandle h, const char* who) {
   if (!h) return set_error(VQA_ERR_BAD_ARG, "%s: null handle", who);
   if (!h->ws) return set_error(VQA_ERR_WORKSPACE, "%s: no workspace attached (vqa_set_workspace)", who);
@@ -227,6 +236,9 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(fill_zero_launch(b.h_f32, sizeof(float) * BL, st));
     VQA_TRY(fill_zero_launch(b.h.hi, sizeof(bf16) * BL, st));
     if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, st));
+    // the step's attention-dropout keep bits, once, for both attention kernels (hidden under the v-projection GEMM)
+    if (use_keep_bits(c, K, D))
+      VQA_TRY(keep_bits_launch(b.att_bits, static_cast<long long>(Bn) * K * D, c.keep_att, seed, step, RNG_STREAM_ATT, st));
     return VQA_OK;
   };
   const bool serial = h->profile && !h->profile_overlapped;
@@ -372,6 +384,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     a.v_hi = v_adapt ? b.va.hi : b.v.hi; a.v_lo = v_adapt ? b.va.lo : b.v.lo;   // adapt pools v_adapt [K, D]
     a.seed = seed; a.step = step; a.att = b.att; a.pooled = b.pooled; a.pooled_hi = b.pooled_op.hi;
     a.pooled_lo = b.pooled_op.lo; a.ln_mean = b.lnv_mean; a.ln_rstd = b.lnv_rstd;
+    a.keep_bits = use_keep_bits(c, K, D) ? b.att_bits : nullptr;
     VQA_TRY(attn_fwd_launch(a, K, D, Pd, c.precision, c.keep_att, s));
   }
   PH_END(VQA_PH_ATTN_FWD);
@@ -796,6 +809,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     a.ln_mean = b.lnv_mean; a.ln_rstd = b.lnv_rstd; a.d_pooled = b.dP; a.dz_hi = b.dzv.hi;
     a.dz_lo = b.dzv.lo; a.d_hq = b.dhq; a.d_att_w = g->att_w; a.d_att_b = g->att_b;
     a.d_gamma = g->v_gamma; a.d_beta = g->v_beta; a.d_bias = g->v_b;
+    a.keep_bits = use_keep_bits(c, K, D) ? b.att_bits : nullptr;
     const bool side = !(h->profile && !h->profile_overlapped);
     VQA_TRY(attn_bwd_launch(a, K, D, Pd, c.precision, c.keep_att, b.attn_part, s, side ? h->aux[3] : nullptr,
                             side ? h->ev_fork[3] : nullptr));
@@ -1080,6 +1094,13 @@ VQA_API VqaStatus vqa_dropout_masks(VqaHandle h, int32_t batch, uint64_t seed, u
     VQA_TRY(dropout_mask_launch(joint_mask, static_cast<long long>(batch) * c.J, c.keep_joint, seed, step,
                                 RNG_STREAM_JOINT, s));
   return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_keep_bits(VqaHandle h, int32_t batch, uint64_t seed, uint64_t step, uint8_t* bits, void* stream) {
+  if (!h || !bits) return set_error(VQA_ERR_BAD_ARG, "vqa_keep_bits: null argument");
+  const VqaConfig& c = h->cfg;
+  return keep_bits_launch(bits, static_cast<long long>(batch) * c.K * c.D, c.keep_att, seed, step, RNG_STREAM_ATT,
+                          static_cast<cudaStream_t>(stream));
 }
 
 VQA_API VqaStatus vqa_peek_activation(VqaHandle h, int32_t which, const void** dev_ptr, uint64_t* bytes) {

@@ -121,7 +121,7 @@ class VqaAttnFwd(C.Structure):
                 ("hq", C.c_void_p), ("att_w", C.c_void_p), ("att_b", C.c_void_p), ("nbox", C.c_void_p),
                 ("v_hi", C.c_void_p), ("v_lo", C.c_void_p), ("seed", C.c_uint64), ("step", C.c_uint64),
                 ("att", C.c_void_p), ("pooled", C.c_void_p), ("pooled_hi", C.c_void_p),
-                ("pooled_lo", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p)]
+                ("pooled_lo", C.c_void_p), ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("keep_bits", C.c_void_p)]
 
 
 class VqaAttnBwd(C.Structure):
@@ -131,7 +131,7 @@ class VqaAttnBwd(C.Structure):
                 ("ln_mean", C.c_void_p), ("ln_rstd", C.c_void_p), ("d_pooled", C.c_void_p),
                 ("dz_hi", C.c_void_p), ("dz_lo", C.c_void_p), ("d_hq", C.c_void_p),
                 ("d_att_w", C.c_void_p), ("d_att_b", C.c_void_p), ("d_gamma", C.c_void_p),
-                ("d_beta", C.c_void_p), ("d_bias", C.c_void_p)]
+                ("d_beta", C.c_void_p), ("d_bias", C.c_void_p), ("keep_bits", C.c_void_p)]
 
 
 # every symbol include/vqa_answer.h declares: name -> (restype, argtypes)
@@ -173,6 +173,7 @@ SYMBOLS = {
     "vqa_input_error_count": (C.c_int32, [C.POINTER(C.c_uint32), C.c_int32]),
     "vqa_set_early_gradients": (C.c_int32, [_P, C.c_int32]),
     "vqa_stream_wait_early_gradients": (C.c_int32, [_P, _P]),
+    "vqa_keep_bits": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "vqa_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaAttnFwd), _P]),
     "vqa_attn_bwd": (C.c_int32, [_P, C.POINTER(VqaAttnBwd), _P]),
     "vqa_bce_metrics": (C.c_int32, [_P, C.c_int32, _P, _P, C.POINTER(VqaAnswerMasks), C.c_float, _P, _P,
