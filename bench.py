@@ -293,21 +293,13 @@ def measure_fp32_mode(bank, c, n_img, dev, peaks, steps=10, warmup=3):
 INFER_DIMS = dict(K=100, Dv=2048, D=1024, L=1024, A=3000, T=14, W=300, Vq=8192)
 
 
-def run_infer(args):
+def infer_sweep(dp, dev, precision, sizes, steps, warmup):
     """BASELINE config 5 (vqa/evaler.py:118-123): forward-only sweep over GLOBAL batch sizes, K = 100 padded boxes with
-    10..100 valid per image, the batch sharded over the N ranks with NO collective on the path; one JSON line."""
+    10..100 valid per image, the batch sharded over the ranks with NO collective on the path. Returns (rows, launches)."""
     import torch
     from vqa_transfer_externaldata_b200 import synthetic as S
-    from vqa_transfer_externaldata_b200.dp import DataParallel
     from vqa_transfer_externaldata_b200.engine import AnswerModelConfig, Engine
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- this repo has no CPU path")
-    dp = DataParallel()
     rank, world = dp.rank, dp.world_size
-    torch.cuda.set_device(dp.local_rank)
-    dev = torch.device(f"cuda:{dp.local_rank}")
-    peaks = load_peaks()
-    sizes = [int(x) for x in args.infer_batches.split(",")]
     n_img = 2048
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     K = INFER_DIMS["K"]
@@ -316,58 +308,52 @@ def run_infer(args):
     nb = rng.integers(10, K + 1, size=n_img).astype(np.int32)
     bank *= (torch.arange(K, device=dev)[None, :] < torch.from_numpy(nb).to(dev)[:, None])[:, :, None]
     sweep = []
-    sampler = ClockSampler(dp.local_rank)
-    if rank == 0:
-        sampler.start()
     launches = 0
+    keys = ("image_idx", "q_intseq", "q_intseq_len", "answer_target")
     for Bg in sizes:
         s0, s1 = dp.shard(Bg)
         Bl = s1 - s0
         c = S.dims(B=max(Bl, 1), **INFER_DIMS)
-        eng = Engine(AnswerModelConfig(variant="vlmap_answer", precision=args.precision, **c), device=dev)
+        eng = Engine(AnswerModelConfig(variant="vlmap_answer", precision=precision, **c), device=dev)
         eng.set_feature_bank(bank, nb)
         params, exist = S.init_params(c, seed=4321, variant="vlmap_answer")
         is_obj, is_attr = S.make_answer_flags(c)
         eng.set_answer_masks(is_obj, is_attr, exist)
         eng.load_params(params)
         hb = [S.make_batch(c, n_img, seed=1234 + 17 * r + 1000 * rank) for r in range(3)]
-        db = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in ("image_idx", "q_intseq", "q_intseq_len", "answer_target")}
-              for b in hb]
-        pinned = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in ("image_idx", "q_intseq", "q_intseq_len", "answer_target")}
-                  for b in hb]
+        db = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).to(dev) for k in keys} for b in hb]
+        pinned = [{k: torch.from_numpy(np.ascontiguousarray(b[k])).pin_memory() for k in keys} for b in hb]
         host_out = torch.zeros(c["B"], dtype=torch.int32).pin_memory()
 
         def step_dev(i):
             eng.stage_batch(db[i % 3])
             eng.forward(seed=777 + 7919 * rank, step=i, full_outputs=True)
 
-        def step_e2e(i):   # host batch in, predictions + loss/report back on the host
-            nbytes = eng.stage_batch(pinned[i % 3])
+        def step_e2e(i):   # host batch in, predictions back on the host
+            eng.stage_batch(pinned[i % 3])
             eng.forward(seed=777 + 7919 * rank, step=i, full_outputs=True)
             host_out[:Bl].copy_(eng.o_pred[:Bl], non_blocking=True)
-            return nbytes
 
-        def timed(fn, steps):
+        def timed(fn, n):
             dp.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n0 = eng.launch_count()
             e0.record()
-            for i in range(steps):
+            for i in range(n):
                 fn(i)
             e1.record()
             torch.cuda.synchronize()
             dp.barrier()
-            return dp.max_over_ranks(e0.elapsed_time(e1)) / steps, eng.launch_count() - n0
+            return dp.max_over_ranks(e0.elapsed_time(e1)) / n, eng.launch_count() - n0
 
-        W = max(3, args.warmup)
-        for i in range(W):
+        for i in range(max(3, warmup)):
             step_dev(i)
-        ms, n_l = timed(step_dev, args.steps)
+        ms, n_l = timed(step_dev, steps)
         launches += n_l
         for i in range(2):
             step_e2e(i)
-        ms_e2e, _ = timed(step_e2e, args.steps)
+        ms_e2e, _ = timed(step_e2e, steps)
         h2d = Bl * 8 + Bl * c["T"] * 4 + Bl * 4 + Bl * c["A"] * 4
         ok = bool(torch.isfinite(eng.outputs()["att_score"]).all().item())
         sweep.append({"global_batch": Bg, "per_gpu_batch": Bl, "ms_per_step": ms, "samples_per_s": Bg / (ms * 1e-3),
@@ -378,6 +364,24 @@ def run_infer(args):
         eng.close()
         del eng
         torch.cuda.empty_cache()
+    return sweep, launches
+
+
+def run_infer(args):
+    """`--mode infer`: the BASELINE config 5 sweep as its own JSON line."""
+    import torch
+    from vqa_transfer_externaldata_b200.dp import DataParallel
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this repo has no CPU path")
+    dp = DataParallel()
+    rank, world = dp.rank, dp.world_size
+    torch.cuda.set_device(dp.local_rank)
+    dev = torch.device(f"cuda:{dp.local_rank}")
+    sizes = [int(x) for x in args.infer_batches.split(",")]
+    sampler = ClockSampler(dp.local_rank)
+    if rank == 0:
+        sampler.start()
+    sweep, launches = infer_sweep(dp, dev, args.precision, sizes, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
         best = max(sweep, key=lambda r: r["samples_per_s"])
@@ -469,7 +473,9 @@ def run_ours(args):
     else:
         dp_check = None
     collective = ("none (1 GPU)" if world == 1 else
-                  "multimem.ld_reduce/st in-switch all-reduce (csrc/collective.cu), NCCL for rendezvous + broadcast only"
+                  ("multimem.ld_reduce/st in-switch all-reduce (csrc/collective.cu) launched INSIDE vqa_backward: early slice under the "
+                   "BPTT, in-kernel barriers; NCCL for rendezvous + broadcast only" if dp._in_library else
+                   "multimem.ld_reduce/st in-switch all-reduce (csrc/collective.cu), NCCL for rendezvous + broadcast only")
                   if dp._mc is not None else "NCCL all-reduce")
 
     W = max(3, args.warmup)
@@ -613,6 +619,23 @@ def run_ours(args):
     if rank == 0 and world == 1 and args.precision == "bf16" and not args.no_fp32:
         fp32_mode = measure_fp32_mode(bank, c, n_img, dev, peaks)
 
+    # BASELINE config 5 on the same ranks (forward only, batch sharded, no collective): a short sweep so that the
+    # inference row is on the same record as the training line at every N the driver runs
+    l2_policy = (f"inputs larger than L2: {n_img}-image feature bank ({bank.numel() * 4 / 1e9:.2f} GB fp32"
+                 + (f" + its one-off {bank.numel() * 2 / 1e9:.2f} GB bf16 copy, which the gather reads" if eng.bank_bf16 is not None else "")
+                 + ") indexed at random, ~0.6 GB touched per step")
+    gru_path = int(lib.vqa_gru_kernel_path())
+    gru_label = ({1: "CTA-pair (gru_pair.cu)", 2: "single-CTA (gru.cu)"}.get(gru_path & 3, "?")
+                 + (" [pair launch REFUSED earlier]" if gru_path & 256 else ""))
+    inference = None
+    if not args.no_infer:
+        model.engine.close()
+        del bank
+        torch.cuda.empty_cache()
+        sweep, _ = infer_sweep(dp, dev, args.precision, [512, 4096, 8192], 5, 3)
+        inference = {"config": "cfg5: forward, K 100 padded boxes (10..100 valid), global batch sharded over the ranks, no collective; "
+                               "roofline 0.59 us / sample / GPU", "sweep": sweep}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, threads, busy = cpu_port_rate(B, 0, 1, budget_s=10.0)
@@ -629,12 +652,7 @@ def run_ours(args):
             "config": {"workload": WORKLOAD, "per_gpu_batch": B, "global_batch": B * world,
                        "precision": args.precision, "parallelism": f"dp{world}", "gradient_collective": collective,
                        "dp_step_check": dp_check,
-                       "gru_kernels": {1: "CTA-pair (gru_pair.cu)", 2: "single-CTA (gru.cu)"}.get(int(lib.vqa_gru_kernel_path()) & 3, "?")
-                                      + (" [pair launch REFUSED earlier]" if int(lib.vqa_gru_kernel_path()) & 256 else ""),
-                       "l2_policy": f"inputs larger than L2: {n_img}-image feature bank ({bank.numel() * 4 / 1e9:.2f} GB fp32"
-                                    + (f" + its one-off {bank.numel() * 2 / 1e9:.2f} GB bf16 copy, which the gather reads"
-                                       if eng.bank_bf16 is not None else "")
-                                    + ") indexed at random, ~0.6 GB touched per step"},
+                       "gru_kernels": gru_label, "l2_policy": l2_policy},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
             "gpu_launches": int(launches),
@@ -645,6 +663,7 @@ def run_ours(args):
             "attn_hbm": attn,
             "sections": sections,
             "fp32_mode": fp32_mode,
+            "inference": inference,
             "phase_ms": phase_ms,
             "critical_path_ms": critical_ms,
             "cpu_baseline": cpu_baseline,
@@ -674,6 +693,7 @@ def main():
     ap.add_argument("--bank-images", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement (N = 1 only)")
+    ap.add_argument("--no-infer", action="store_true", help="skip the BASELINE config 5 inference sweep")
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--infer-batches", default="64,512,4096,8192")
     args = ap.parse_args()

@@ -315,6 +315,20 @@ VQA_API VqaStatus vqa_input_error_count(uint32_t* count, int32_t reset);
  * back-propagation through time and records an event there; vqa_stream_wait_early_gradients makes `stream` wait for
  * that event of the most recent vqa_backward, so an all-reduce of that slice can run under the BPTT kernels. */
 VQA_API VqaStatus vqa_set_early_gradients(VqaHandle h, int32_t enable);
+/* The gradient exchange of the data-parallel step INSIDE vqa_backward. The caller puts the flat gradient buffer (the one
+ * the VqaParams gradient struct points into) in symmetric memory that is also mapped as one NVSwitch multicast object
+ * (torch.distributed._symmetric_memory does rendezvous and mapping), with 64 spare bytes at float offset `flags_offset`
+ * (>= n_total) zeroed on every rank, and registers both addresses here. vqa_backward then
+ *   - takes dWv before the BPTT (as with vqa_set_early_gradients) and all-reduces [0, n_early) -- everything but the
+ *     GRU and the embedding -- on an auxiliary stream UNDER the cooperative recurrent kernel, as ten 2-CTA clusters on
+ *     the TPCs that grid leaves idle (csrc/collective.cu: multimem.ld_reduce / multimem.st, sums formed in the switch);
+ *   - all-reduces [n_early, n_total) after the weight-gradient section, on `stream`.
+ * Both launches carry their own cross-rank entry / exit barriers (multimem.red on two counters at flags_offset), so the
+ * host issues nothing between vqa_backward and the optimizer step, and the sums are valid on `stream` when vqa_backward's
+ * work completes. Sizes in floats, multiples of 4. multicast_base = NULL unregisters. (The reference has no distributed
+ * code at all: one process per GPU via CUDA_VISIBLE_DEVICES, run.py:25-46.) */
+VQA_API VqaStatus vqa_set_gradient_allreduce(VqaHandle h, void* multicast_base, void* local_base, int64_t n_early,
+                                             int64_t n_total, int64_t flags_offset, int32_t rank, int32_t world);
 VQA_API VqaStatus vqa_stream_wait_early_gradients(VqaHandle h, void* stream);
 
 /* In-switch all-reduce(sum) of n floats that every rank holds at the same offset of a symmetric allocation mapped

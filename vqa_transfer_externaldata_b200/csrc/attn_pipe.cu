@@ -35,7 +35,7 @@ constexpr int AP_CONSUMER_WARPS = 16;
 constexpr int AP_CONSUMERS = 32 * AP_CONSUMER_WARPS;
 constexpr int AP_THREADS = AP_CONSUMERS + 32;
 constexpr int AP_VSLOTS = 4;
-constexpr int AP_DEFAULT_VAR = 8;
+constexpr int AP_DEFAULT_VAR = 10;   // measured best of the sixteen on one box (profiles/r02_attn_phase_trace.md)
 
 __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(AP_CONSUMERS) : "memory"); }
 __device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
@@ -557,13 +557,13 @@ VqaStatus attn_fwd_pipe_launch(const VqaAttnFwd& a, int K, int D, int Dv, float 
   f.keep_bits = f.thr < 65536u ? a.keep_bits : nullptr;
   f.trace = g_gru_trace ? g_gru_trace + 65536 : nullptr;   // (shared debugging buffer: vqa_internal_set_gru_trace)
   static const int var_env = getenv("VQA_ATTN_VAR") ? atoi(getenv("VQA_ATTN_VAR")) : AP_DEFAULT_VAR;
-  int var = var_env & 15;
+  // bits 0 (batched statistics loads) and 2 (four pooling rows in flight) measured slower or equal in every combination
+  // (38.7 us for VAR 10 against 41.0 / 41.0 / 42.0 / 42.0 for VAR 0 / 1 / 4 / 15): only bits 1 and 3 are instantiated
+  int var = var_env & 10;
   if (!f.keep_bits) var &= 7;   // the Philox path is needed
   using Kern = void (*)(PipeFwdArgs);
-  static const Kern kerns[16] = {attn_fwd_pipe_kernel<0>, attn_fwd_pipe_kernel<1>, attn_fwd_pipe_kernel<2>, attn_fwd_pipe_kernel<3>,
-                                 attn_fwd_pipe_kernel<4>, attn_fwd_pipe_kernel<5>, attn_fwd_pipe_kernel<6>, attn_fwd_pipe_kernel<7>,
-                                 attn_fwd_pipe_kernel<8>, attn_fwd_pipe_kernel<9>, attn_fwd_pipe_kernel<10>, attn_fwd_pipe_kernel<11>,
-                                 attn_fwd_pipe_kernel<12>, attn_fwd_pipe_kernel<13>, attn_fwd_pipe_kernel<14>, attn_fwd_pipe_kernel<15>};
+  static const Kern kerns[16] = {attn_fwd_pipe_kernel<0>, nullptr, attn_fwd_pipe_kernel<2>, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                 attn_fwd_pipe_kernel<8>, nullptr, attn_fwd_pipe_kernel<10>, nullptr, nullptr, nullptr, nullptr, nullptr};
   static size_t smem_set[16] = {};
   if (smem_set[var] < smem) {
     VQA_CUDA_CHECK(cudaFuncSetAttribute(kerns[var], cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

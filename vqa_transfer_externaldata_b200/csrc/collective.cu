@@ -47,7 +47,103 @@ __global__ void __launch_bounds__(MC_THREADS) multimem_allreduce_kernel(float* m
   for (; i < end4; i += stride) mc_st(mc + 4 * i, mc_ld_reduce(mc + 4 * i));
 }
 
+// ---- the same exchange with the two cross-rank barriers INSIDE the kernel -------------------------------------------
+// flags[0] / flags[1] live in the symmetric buffer behind the gradients (each rank has its own copy; the multicast
+// address reaches all of them). Every call adds `world` to both: the host passes the totals after this call.
+//   entry : "the gradients of every rank are complete" -- block 0 of every rank adds 1 to flags[0] of ALL ranks
+//           (multimem.red, release: ordered after this rank's earlier kernels, whose writes a kernel boundary has
+//           already made visible), every block waits until its rank's copy has reached the total;
+//   exit  : "every slice has been broadcast" -- blocks count themselves on a local counter after their last
+//           multimem.st (+ fence); the last one adds 1 to flags[1] everywhere and waits for the total, so the kernel
+//           (and with it the stream) does not complete before every rank's slice has landed here.
+// A spin that sees no progress for ~2 s traps (a lost rank becomes a launch failure, not a hung GPU).
+__device__ __forceinline__ void mc_red_add_release(unsigned int* p, unsigned int v) {
+  asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
+  unsigned int v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target) {
+  const long long t0 = clock64();
+  while (static_cast<int>(ld_acquire_sys(p) - target) < 0) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+
+__global__ void __launch_bounds__(1024) multimem_allreduce_sync_kernel(float* mc, long long begin4, long long end4,
+                                                                       unsigned int* mc_flags, const unsigned int* my_flags,
+                                                                       unsigned int* grid_ctr, unsigned int flag_total,
+                                                                       unsigned int grid_total) {
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) mc_red_add_release(mc_flags, 1u);
+    spin_until(my_flags, flag_total);
+  }
+  __syncthreads();
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  long long i = begin4 + static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  for (; i + (MC_UNROLL - 1) * stride < end4; i += MC_UNROLL * stride) {
+    float4 v[MC_UNROLL];
+#pragma unroll
+    for (int u = 0; u < MC_UNROLL; ++u) v[u] = mc_ld_reduce(mc + 4 * (i + u * stride));
+#pragma unroll
+    for (int u = 0; u < MC_UNROLL; ++u) mc_st(mc + 4 * (i + u * stride), v[u]);
+  }
+  for (; i < end4; i += stride) mc_st(mc + 4 * i, mc_ld_reduce(mc + 4 * i));
+  __threadfence_system();   // this thread's broadcasts are performed before the block counts itself
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int prev = atomicAdd(grid_ctr, 1u);
+    if (prev + 1u == grid_total) {   // the last block of this launch
+      mc_red_add_release(mc_flags + 1, 1u);
+      spin_until(my_flags + 1, flag_total);
+    }
+  }
+}
+
 }  // namespace
+
+// cluster of two CTAs per launch unit, each claiming a whole SM (the shape the cooperative recurrent grid tolerates
+// beside it: csrc/elementwise.cu gather_exclusive_launch) when `exclusive`; a plain wide grid otherwise
+VqaStatus multimem_allreduce_sync_launch(float* mc, long long n, int rank, int world, unsigned int* mc_flags,
+                                         const unsigned int* my_flags, unsigned int* grid_ctr, unsigned int flag_total,
+                                         unsigned int* grid_total_io, bool exclusive, int ctas, cudaStream_t s) {
+  const long long n4 = n >> 2;
+  const long long per = (n4 + world - 1) / world;
+  long long begin = per * rank;
+  long long end = begin + per < n4 ? begin + per : n4;
+  if (begin > end) begin = end;   // a rank without elements still takes part in the two barriers
+  const int threads = exclusive ? 1024 : MC_THREADS;
+  if (ctas <= 0) ctas = exclusive ? 20 : 96;
+  long long need = (end - begin + threads - 1) / threads;
+  if (need < 1) need = 1;
+  if (need < ctas) ctas = static_cast<int>(need);
+  if (exclusive) ctas = (ctas + 1) & ~1;
+  *grid_total_io += static_cast<unsigned int>(ctas);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(ctas);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  int nat = 0;
+  if (exclusive) {
+    constexpr int kExclusiveSmem = 200 * 1024;
+    VQA_CUDA_CHECK(cudaFuncSetAttribute(multimem_allreduce_sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExclusiveSmem));
+    cfg.dynamicSmemBytes = kExclusiveSmem;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    nat = 1;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = nat;
+  VQA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, multimem_allreduce_sync_kernel, mc, begin, end, mc_flags, my_flags, grid_ctr,
+                                    flag_total, *grid_total_io));
+  count_launch();
+  return VQA_OK;
+}
 
 }  // namespace vqa
 

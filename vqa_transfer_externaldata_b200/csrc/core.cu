@@ -212,6 +212,7 @@ uint64_t plan_workspace(VqaHandle_t* h, uint8_t* base) {
   if (J > maxc) maxc = J;
   if (Dv > maxc) maxc = Dv;
   b.gemm_sem = a.take<unsigned int>(VqaHandle_t::kGemmSemRegions * VqaHandle_t::kGemmSemElems);
+  b.ar_grid_ctr = a.take<unsigned int>(4);
   b.gru_counter = a.take<unsigned int>(64);
   b.gru_pack = a.take<bf16>(gru_pack_elems(static_cast<int>(L)));
   b.gru_bias_part = a.take<float>(gru_bias_part_floats(static_cast<int>(B), static_cast<int>(L)));
@@ -295,6 +296,7 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   }
   h->aux_created = true;
   h->early_grads = false;
+  h->ar = {};
   h->prefetched = false;
   h->prefetched_idx = nullptr;
   h->prefetched_batch = 0;

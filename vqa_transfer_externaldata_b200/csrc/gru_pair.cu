@@ -38,11 +38,19 @@ namespace {
 constexpr int Q_ROWS = 64;                      // batch rows per CTA
 constexpr int Q_UNITS = 32;                     // hidden units whose weights this CTA holds (64 per pair)
 constexpr int Q_BK = 64;
-constexpr int Q_STAGES = 2;
 constexpr int Q_KBS = 4;                        // k-blocks per stage = per TMA operation (fewer when L / 64 is not a multiple)
 constexpr int Q_A_TILE = Q_ROWS * Q_BK * 2;     // 8 KB activation tile of one k-block
 constexpr int Q_W_TILE = Q_UNITS * Q_BK * 2;    // 4 KB streamed weight tile (32 rows) of one k-block
-constexpr int Q_STAGE = Q_KBS * (Q_A_TILE + Q_W_TILE);    // 48 KB: [kbs activation tiles | kbs weight tiles]
+// The 96 KB ring has two geometries (every phase starts at stage 0 with all stages free):
+//   phases whose weights STREAM : 2 stages of 48 KB = [kbs activation tiles (32 KB) | kbs weight tiles (16 KB)]
+//   phases whose weights are RESIDENT: 3 stages of 32 KB, activation tiles only. With two stages only 64 KB of the
+//     128 KB (256 KB in the BPTT's K = 2L phase) operand were in flight per ~0.9 us TMA round trip: the phase's loads
+//     took two (four) dependent round trips, 2.1 (4.1) us of every phase (profiles/r02_gru_phase_trace.txt).
+constexpr int Q_STAGES = 3;
+constexpr int Q_STAGE_S = Q_KBS * (Q_A_TILE + Q_W_TILE);   // 48 KB streamed-phase stage
+constexpr int Q_STAGE_R = Q_KBS * Q_A_TILE;                // 32 KB resident-phase stage
+constexpr int Q_RING = 2 * Q_STAGE_S;                      // = 3 * Q_STAGE_R = 96 KB
+static_assert(Q_RING == 3 * Q_STAGE_R, "ring geometries");
 constexpr int Q_EPI_WARPS = 16;
 constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS;
 constexpr int Q_TMEM_COLS = 128;                // forward: gates at column 0 (64 wide), candidate at 64 (32 wide)
@@ -50,7 +58,7 @@ constexpr int NU = 8;                           // units per epilogue thread
 
 // resident weights: forward = this CTA's gate rows (64 x L), BPTT = its Wg_h rows (32 x 2L): 128 L bytes
 __host__ __device__ constexpr int q_wres_bytes(int L) { return 2 * Q_UNITS * L * 2; }
-__host__ __device__ constexpr int q_smem_bytes(int L) { return q_wres_bytes(L) + Q_STAGES * Q_STAGE + 256 + 1024; }
+__host__ __device__ constexpr int q_smem_bytes(int L) { return q_wres_bytes(L) + Q_RING + 256 + 1024; }
 
 struct PairGruArgs {
   int B, row_end, L, T;
@@ -169,7 +177,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
   // 2 KB tiles of 4 KB). The other matrix (32 rows) streams through the ring next to the activation tiles.
   uint8_t* wres = smem;
   uint8_t* ring = smem + q_wres_bytes(L);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + Q_STAGES * Q_STAGE);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + Q_RING);
   uint64_t* empty_bar = full_bar + Q_STAGES;
   uint64_t* tmem_full_bar = empty_bar + Q_STAGES;
   uint64_t* w_bar = tmem_full_bar + 1;
@@ -239,8 +247,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       }
     }
     __syncwarp();
-    int stage = 0;
-    uint32_t phase_bit = 0;
+    uint32_t uses[Q_STAGES] = {0u, 0u, 0u};   // how often each stage has been filled so far (barrier phase parity)
     for (int p = 0; p < num_phases; ++p) {
       bool mm; int kind, t;
       phase_info(p, mm, kind, t);
@@ -253,16 +260,27 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       const int arow = t * B + m0;
       const int kbs = g.kbs;
       const uint32_t a_bytes = kbs * Q_A_TILE, w_bytes = kbs * Q_W_TILE;
+      const int nstages = streamed ? 2 : 3;
+      const uint32_t pitch = streamed ? Q_STAGE_S : Q_STAGE_R;
+      // the two geometries overlap: before anything of this phase is written (the early weight load below included),
+      // every stage the previous phase filled must have been consumed by its MMAs
+#pragma unroll
+      for (int q = 0; q < Q_STAGES; ++q)
+        if (uses[q]) ptx::mbar_wait(&empty_bar[q], (uses[q] - 1u) & 1u);
+      int stage = 0;
       for (int kb = 0; kb < nkb; kb += kbs) {
-        ptx::mbar_wait(&empty_bar[stage], phase_bit ^ 1);
+        uint32_t use = 0;
+#pragma unroll
+        for (int q = 0; q < Q_STAGES; ++q) if (q == stage) { use = uses[q]; uses[q] = use + 1; }
+        ptx::mbar_wait(&empty_bar[stage], (use & 1u) ^ 1u);
         const uint32_t lf = ptx::mapa_u32(ptx::smem_u32(&full_bar[stage]), 0);
-        uint8_t* st = ring + stage * Q_STAGE;
+        uint8_t* st = ring + stage * pitch;
         const bool first = kb == 0;
         // the streamed weights do not depend on the other CTAs: for the first stage they go out BEFORE the counter
         // wait (stage 0 doubles as the epilogue's TMA-store staging, but only its activation area)
         if (ptx::elect_one() && g.dbg != 2) {
           if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * (a_bytes + (streamed ? w_bytes : 0)));
-          if (streamed) ptx::tma_load_3d_pair(st + a_bytes, tw, lf, 0, wrow, kb);
+          if (streamed) ptx::tma_load_3d_pair(st + Q_KBS * Q_A_TILE, tw, lf, 0, wrow, kb);
         }
         __syncwarp();
         if (first) {
@@ -280,10 +298,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
           }
         }
         __syncwarp();
-        if (++stage == Q_STAGES) {
-          stage = 0;
-          phase_bit ^= 1;
-        }
+        if (++stage == nstages) stage = 0;
       }
     }
   } else if (warp == 1) {
@@ -292,8 +307,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       constexpr uint32_t idesc128 = ptx::make_idesc_bf16(128, 128, false, false);   // forward gates: r|u of 64 units
       constexpr uint32_t idesc64 = ptx::make_idesc_bf16(128, 64, false, false);
       ptx::mbar_wait(w_bar, 0);
-      int stage = 0;
-      uint32_t phase_bit = 0;
+      uint32_t uses[Q_STAGES] = {0u, 0u, 0u};
       for (int p = 0; p < num_phases; ++p) {
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
@@ -305,12 +319,18 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
         const uint32_t wtile = wide ? 8192 : 4096;
         const uint32_t d_tmem = tmem_base + ((MODE == 0 && kind == 1) ? 64 : 0);
         const int kbs = g.kbs;
+        const int nstages = streamed ? 2 : 3;
+        const uint32_t pitch = streamed ? Q_STAGE_S : Q_STAGE_R;
+        int stage = 0;
         for (int kb = 0; kb < nkb; kb += kbs) {
-          ptx::mbar_wait(&full_bar[stage], phase_bit);
+          uint32_t use = 0;
+#pragma unroll
+          for (int q = 0; q < Q_STAGES; ++q) if (q == stage) { use = uses[q]; uses[q] = use + 1; }
+          ptx::mbar_wait(&full_bar[stage], use & 1u);
           ptx::tc_fence_after();
           if (kb == 0 && lane == 0) GRU_TRACE(p, 1);
-          const uint32_t sa0 = ptx::smem_u32(ring + stage * Q_STAGE);
-          const uint32_t sw0 = sa0 + kbs * Q_A_TILE;
+          const uint32_t sa0 = ptx::smem_u32(ring + stage * pitch);
+          const uint32_t sw0 = sa0 + Q_KBS * Q_A_TILE;
           if (ptx::elect_one()) {
             if (g.dbg != 1)
             for (int i = 0; i < kbs; ++i) {
@@ -326,10 +346,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
             ptx::umma_commit_pair(&empty_bar[stage], 3);
           }
           __syncwarp();
-          if (++stage == Q_STAGES) {
-            stage = 0;
-            phase_bit ^= 1;
-          }
+          if (++stage == nstages) stage = 0;
         }
         if (ptx::elect_one()) ptx::umma_commit_pair(tmem_full_bar, 3);
         __syncwarp();
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     uint32_t tfull_phase = 0;
     // TMA-store staging: the A areas of ring stages 0 and 1 (idle between the last MMA of a phase and the next
     // phase's first load, which waits for this CTA's own arrival below)
-    const uint32_t stg0 = ptx::smem_u32(ring), stg1 = ptx::smem_u32(ring + Q_STAGE);
+    const uint32_t stg0 = ptx::smem_u32(ring), stg1 = ptx::smem_u32(ring + Q_A_TILE);   // both inside stage 0's activation area
     const int srow = (q & 1) * 32 + lane;         // row inside the CTA's 64-row tile
     const int schunk = uhalf * 4 + sub;           // 16-byte chunk inside the 128-byte row of 64 units
     const int ucol = (slice32 >> 1) * 64;         // first unit of the pair

@@ -90,6 +90,7 @@ struct Buffers {
   float* ln_part_g; float* ln_part_b;  // [B, max(D,L,J)] LayerNorm gamma/beta partials (q_linear_v)
   float* ln_parts[5][2];               // the same for joint_fc, joint_l, pooled_linear_l, q_linear_l, the extra question layer
   unsigned int* gemm_sem;     // split-K hand-over semaphores of the pair GEMM (kGemmSemRegions x kGemmSemElems)
+  unsigned int* ar_grid_ctr;  // block counter of the in-kernel exit barrier of the gradient all-reduce
   unsigned int* gru_counter;  // per-row-tile phase counters of the persistent GRU kernels
   bf16* gru_pack;             // [L/32][96][L] packed weight slices of the forward recurrent kernel
   float* gru_bias_part;       // [ceil(B/128)+1, 3L] partial bias gradients of the BPTT kernel
@@ -121,7 +122,7 @@ struct VqaHandle_t {
   VqaAnswerMasks last_masks;
   // auxiliary streams: independent branches of the graph (x-projections vs v-projection, the weight-gradient
   // GEMMs) are forked off the caller's stream and joined back with events -- capturable in a CUDA graph
-  static constexpr int kAux = 5;
+  static constexpr int kAux = 6;
   cudaStream_t aux[kAux];
   cudaEvent_t ev_fork[kAux], ev_join[kAux];
   bool aux_created;
@@ -145,6 +146,17 @@ struct VqaHandle_t {
   bool pack_pending;
   cudaEvent_t ev_pack;
   float* slice_slot;       // vqa_set_embedding_slice_norm: where vqa_backward leaves sum |dE rows|^2 (NULL = off)
+  // vqa_set_gradient_allreduce: the data-parallel gradient exchange runs INSIDE vqa_backward (csrc/collective.cu)
+  struct {
+    float* mc;                  // multicast address of the symmetric gradient buffer (NULL = not registered)
+    float* local;               // this rank's own mapping of it (= where the VqaParams gradient struct points)
+    long long n_early, n_total; // floats: [0, n_early) is complete before the BPTT, [n_early, n_total) after the weight-gradient section
+    unsigned int* mc_flags;     // two barrier counters behind the gradients (multicast / own mapping)
+    unsigned int* my_flags;
+    unsigned int* grid_ctr;     // local block counter of the exit barrier
+    unsigned int flag_total, grid_total;
+    int rank, world;
+  } ar;
   bool early_grads;        // vqa_set_early_gradients
   cudaEvent_t ev_early;    // recorded by vqa_backward once the non-GRU gradients are complete
   // optional per-phase timing

@@ -85,7 +85,11 @@ VqaStatus embed_gather_launch(const float* embed, const int* q_intseq, int batch
 VqaStatus embed_scatter_add_launch(const float* dE, long long ld_dE, const int* q_intseq,
                                    const int* q_len, int batch, int T, int Tstride, int W, int vocab,
                                    float* d_embed, cudaStream_t s);
-VqaStatus input_error_count(unsigned int* out, bool reset);   // sticky count of out-of-range image_idx / token ids
+VqaStatus input_error_count(unsigned int* out, bool reset);
+// ---- collective.cu ----
+VqaStatus multimem_allreduce_sync_launch(float* mc, long long n, int rank, int world, unsigned int* mc_flags,
+                                         const unsigned int* my_flags, unsigned int* grid_ctr, unsigned int flag_total,
+                                         unsigned int* grid_total_io, bool exclusive, int ctas, cudaStream_t s);   // sticky count of out-of-range image_idx / token ids
 VqaStatus colsum_launch(const float* x, long long rows, long long cols, long long ld, float* out,
                         float* scratch, cudaStream_t s);
 VqaStatus fill_zero_launch(void* p, size_t bytes, cudaStream_t s);

@@ -830,7 +830,10 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   PH_END(VQA_PH_ATTN_BWD);
   if (fork_ql) VQA_TRY(join_stream(h, 2, s));   // dq (q_linear_l branch) is needed by the BPTT below
   // data-parallel runs take dWv here, ahead of the BPTT, so that its all-reduce can overlap the recurrent kernels
-  const bool early = h->early_grads && !(h->profile && !h->profile_overlapped);
+  // in-library gradient exchange (vqa_set_gradient_allreduce): the slice that is final before the BPTT is reduced under it
+  const bool ar_on = h->ar.mc != nullptr && h->ar.world > 1 && g->v_w != nullptr &&
+                     g->v_w >= h->ar.local && g->v_w < h->ar.local + h->ar.n_total;
+  const bool early = (h->early_grads || ar_on) && !(h->profile && !h->profile_overlapped);
   if (early && g->v_w)
     VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, s));
   PH_BEGIN(VQA_PH_QV_BWD);
@@ -878,6 +881,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->v_w && !early) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, st));
     return VQA_OK;
   };
+  bool ar_early_done = false;
   // GRU: back-propagation through time from dq
   const bool need_gru = g->gru_gates_w || g->gru_gates_b || g->gru_cand_w || g->gru_cand_b || g->embed;
   if (need_gru) {
@@ -896,9 +900,19 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       // the next batch's feature gather goes to the SMs the recurrent grid leaves idle: fork BEFORE the launch (so the
       // gather is ordered after the same prefix of this step), enqueue it AFTER (so the cooperative grid is first in line)
       const bool pf = h->pf_pending && !(h->profile && !h->profile_overlapped) && gru_pair_supported(Bn, L, h->num_sms);
-      cudaStream_t a4 = s;
+      cudaStream_t a4 = s, a5 = s;
       if (pf) VQA_TRY(fork_stream(h, 4, s, &a4));
+      const bool ar_early = ar_on && early && h->ar.n_early > 0;
+      if (ar_early) VQA_TRY(fork_stream(h, 5, s, &a5));   // forked BEFORE the cooperative launch, enqueued AFTER it
       VQA_TRY(gru_bwd_persistent_launch(a, h->num_sms, s));
+      if (ar_early) {
+        // ten 2-CTA clusters that each take a whole SM: the TPCs the 64 CTA pairs of the recurrent grid leave free
+        h->ar.flag_total += static_cast<unsigned int>(h->ar.world);
+        VQA_TRY(multimem_allreduce_sync_launch(h->ar.mc, h->ar.n_early, h->ar.rank, h->ar.world, h->ar.mc_flags, h->ar.my_flags,
+                                               h->ar.grid_ctr, h->ar.flag_total, &h->ar.grid_total,
+                                               gru_pair_supported(Bn, L, h->num_sms), 0, a5));
+        ar_early_done = true;
+      }
       if (pf) VQA_TRY(launch_pending_prefetch(h, a4));
       (void)pp;
     } else {
@@ -1014,6 +1028,45 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(join_stream(h, 1, s));
     h->outputs_pending = false;
   }
+  if (ar_on) {
+    // the rest of the gradients (GRU, embedding, the tail slots -- or everything when nothing went out early): one wide
+    // launch whose own entry / exit barriers make the sums valid on `s` when it completes
+    long long off = 0;
+    if (ar_early_done) {
+      VQA_TRY(join_stream(h, 5, s));
+      off = h->ar.n_early;
+    }
+    h->ar.flag_total += static_cast<unsigned int>(h->ar.world);
+    VQA_TRY(multimem_allreduce_sync_launch(h->ar.mc + off, h->ar.n_total - off, h->ar.rank, h->ar.world, h->ar.mc_flags,
+                                           h->ar.my_flags, h->ar.grid_ctr, h->ar.flag_total, &h->ar.grid_total, false, 0, s));
+  }
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_set_gradient_allreduce(VqaHandle h, void* multicast_base, void* local_base, int64_t n_early,
+                                             int64_t n_total, int64_t flags_offset, int32_t rank, int32_t world) {
+  VQA_TRY(check_ready(h, "vqa_set_gradient_allreduce"));
+  if (!multicast_base) {   // unregister
+    h->ar = {};
+    return VQA_OK;
+  }
+  if (!local_base || world <= 0 || rank < 0 || rank >= world || n_total <= 0 || n_early < 0 || n_early > n_total ||
+      (n_early & 3) || (n_total & 3) || flags_offset < n_total || (flags_offset & 3) ||
+      (reinterpret_cast<uintptr_t>(multicast_base) & 15) || (reinterpret_cast<uintptr_t>(local_base) & 15))
+    return set_error(VQA_ERR_BAD_ARG, "vqa_set_gradient_allreduce: bad argument (sizes are floats, multiples of 4; 16-byte aligned buffers)");
+  h->ar.mc = static_cast<float*>(multicast_base);
+  h->ar.local = static_cast<float*>(local_base);
+  h->ar.n_early = n_early;
+  h->ar.n_total = n_total;
+  h->ar.mc_flags = reinterpret_cast<unsigned int*>(h->ar.mc + flags_offset);
+  h->ar.my_flags = reinterpret_cast<unsigned int*>(h->ar.local + flags_offset);
+  h->ar.grid_ctr = h->buf.ar_grid_ctr;
+  h->ar.flag_total = 0;
+  h->ar.grid_total = 0;
+  h->ar.rank = rank;
+  h->ar.world = world;
+  // (the caller zeroes the flag words on every rank and synchronises the ranks before the first vqa_backward)
+  VQA_CUDA_CHECK(cudaMemset(h->buf.ar_grid_ctr, 0, 4 * sizeof(unsigned int)));
   return VQA_OK;
 }
 

@@ -17,6 +17,7 @@ class DataParallel:
         self.owns_group = False
         self._side = None
         self._mc = None
+        self._in_library = False
         if self.world_size > 1 and not dist.is_initialized():
             backend = backend or ("nccl" if torch.cuda.is_available() else "gloo")
             if backend == "nccl":
@@ -48,7 +49,9 @@ class DataParallel:
             return False
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            n = (engine.params.n_train + engine.params.TAIL + 1023) // 1024 * 1024
+            n_grad = engine.params.n_train + engine.params.TAIL
+            flags_off = (n_grad + 1023) // 1024 * 1024          # barrier counters of the in-library exchange live here
+            n = flags_off + 1024
             buf = symm_mem.empty(n, dtype=torch.float32, device=engine.device)
             hdl = symm_mem.rendezvous(buf, dist.group.WORLD)
             if not hdl.has_multicast_support or not hdl.multicast_ptr:
@@ -57,8 +60,19 @@ class DataParallel:
             if self.rank == 0:
                 print(f"[dp] multicast gradients unavailable ({e!r}); using NCCL all-reduce", flush=True)
             return False
+        buf.zero_()
         engine.rebind_gradients(buf)
-        self._mc = (hdl, buf, engine.params.n_train + engine.params.TAIL)   # the tail slots are summed with the gradients
+        self._mc = (hdl, buf, n_grad)   # the tail slots are summed with the gradients
+        self._in_library = False
+        if os.environ.get("VQA_DP_IN_LIBRARY", "1") != "0":
+            # the exchange runs inside vqa_backward (early slice under the BPTT, in-kernel barriers): nothing to do per step
+            from . import lib as L
+            torch.cuda.synchronize(engine.device)
+            hdl.barrier(channel=0)          # every rank's flag words are zero before anybody's first backward
+            torch.cuda.synchronize(engine.device)
+            L.check(engine.lib.vqa_set_gradient_allreduce(engine.h, hdl.multicast_ptr, buf.data_ptr(), engine.params.n_early,
+                                                          n_grad, flags_off, self.rank, self.world_size))
+            self._in_library = True
         return True
 
     def all_reduce_gradients(self, engine):
@@ -69,6 +83,8 @@ class DataParallel:
         g = engine.params.grad_buf   # gradients + tail slots (the embedding slice norm adds up over ranks like a gradient)
         if self.world_size == 1:
             return
+        if self._mc is not None and getattr(self, "_in_library", False):
+            return   # vqa_backward has already reduced them (vqa_set_gradient_allreduce)
         if self._mc is not None:
             hdl, buf, n = self._mc
             from . import lib as L
@@ -111,7 +127,7 @@ class DataParallel:
         Bg = per_rank * world
         dims = dict(K=12, Dv=256, D=128, L=128, A=200, T=6, W=20, Vq=50)
         out = {}
-        keep_mc = self._mc
+        keep_mc, keep_lib = self._mc, getattr(self, "_in_library", False)
         for precision in ("fp32", "bf16"):
             limit = tol if tol is not None else (1e-5 if precision == "fp32" else 5e-5)
             cg = S.dims(B=Bg, **dims)
@@ -160,7 +176,7 @@ class DataParallel:
             assert worst <= limit, f"data-parallel step != single-rank step on the concatenated batch ({precision}): {worst:.3e} > {limit:.1e}"
             out[precision] = worst
             out["collective"] = "multimem" if used_mc else "nccl"
-        self._mc = keep_mc
+        self._mc, self._in_library = keep_mc, keep_lib
         return out
 
     def barrier(self):

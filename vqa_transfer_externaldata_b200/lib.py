@@ -173,6 +173,7 @@ SYMBOLS = {
     "vqa_input_error_count": (C.c_int32, [C.POINTER(C.c_uint32), C.c_int32]),
     "vqa_set_early_gradients": (C.c_int32, [_P, C.c_int32]),
     "vqa_stream_wait_early_gradients": (C.c_int32, [_P, _P]),
+    "vqa_set_gradient_allreduce": (C.c_int32, [_P, _P, _P, C.c_int64, C.c_int64, C.c_int64, C.c_int32, C.c_int32]),
     "vqa_keep_bits": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "vqa_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaAttnFwd), _P]),
     "vqa_attn_bwd": (C.c_int32, [_P, C.POINTER(VqaAttnBwd), _P]),
