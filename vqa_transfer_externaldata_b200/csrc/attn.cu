@@ -344,7 +344,10 @@ struct BwdArgs {
   float* part;  // [batch, 4*D + 8]: T*hq/keep (dw) | dgamma | dbeta | dbias | db
   const unsigned char* keep_bits;   // [batch*K*D/8] the forward's keep bits (NULL: regenerated here with Philox)
   unsigned long long* trace;        // optional [batch][8] globaltimer stamps
+  int vring_rows;                   // > 0: the <V, dP> pass streams the feature rows through a 3-slot ring of this many rows
+                                    // laid over the (not yet loaded) slab buffer (bulk copies) instead of global loads
 };
+constexpr int AB_VSLOTS = 3;
 __device__ __forceinline__ unsigned long long gtimer_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -369,23 +372,50 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
   uint64_t* zbar = nullptr;
+  uint64_t* vfull = nullptr;
+  uint64_t* vempty = nullptr;
+  ZT* zs_mem = nullptr;
+  const ZT* zb_global = zb;
   pdl_sync();
   if (SLAB) {
     // the slab copy is in flight while the feature rows are reduced against dP below
     const size_t head = ((static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * 4 +
                          static_cast<size_t>(K) * CH + 15) & ~static_cast<size_t>(15);
     zbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm) + head);
-    ZT* zs = reinterpret_cast<ZT*>(zbar + 2);
+    ZT* zs = reinterpret_cast<ZT*>(zbar + 8);
+    vfull = zbar + 1;
+    vempty = zbar + 1 + AB_VSLOTS;
+    zs_mem = zs;
     if (tid == 0) {
       ptx::mbar_init(zbar, a.keep_bits ? 2 : 1);
+      for (int i = 0; i < AB_VSLOTS; ++i) {
+        ptx::mbar_init(&vfull[i], 1);
+        ptx::mbar_init(&vempty[i], ATT_WARPS);
+      }
       ptx::fence_barrier_init();
-      slab_to_smem(zs, zb, static_cast<uint32_t>(K) * D * sizeof(ZT), zbar);
-      if (a.keep_bits) {
-        // the forward's keep bits of this slab land in `flags`; the column pass below turns them into gate flags in place
-        ptx::mbar_arrive_expect_tx(zbar, static_cast<uint32_t>(K) * CH);
-        bulk_load(flags, a.keep_bits + static_cast<size_t>(b) * K * CH, static_cast<uint32_t>(K) * CH, zbar);
+      if (a.vring_rows > 0) {
+        // the slab buffer first serves as a ring for the feature rows of the <V, dP> pass; the slab itself is fetched
+        // when that pass is over (it is needed from the column pass on)
+        int nb0 = a.nbox[b];
+        nb0 = nb0 < 0 ? 0 : (nb0 > K ? K : nb0);
+        const uint32_t vrow = static_cast<uint32_t>(Dv) * 2;
+        const uint8_t* vsrc = reinterpret_cast<const uint8_t*>(a.v_hi) + static_cast<size_t>(b) * K * vrow;
+        for (int ch = 0; ch < AB_VSLOTS && ch * a.vring_rows < nb0; ++ch) {
+          const int rows = nb0 - ch * a.vring_rows < a.vring_rows ? nb0 - ch * a.vring_rows : a.vring_rows;
+          ptx::mbar_arrive_expect_tx(&vfull[ch], rows * vrow);
+          bulk_load(reinterpret_cast<uint8_t*>(zs) + static_cast<size_t>(ch) * a.vring_rows * vrow,
+                    vsrc + static_cast<size_t>(ch) * a.vring_rows * vrow, rows * vrow, &vfull[ch]);
+        }
+      } else {
+        slab_to_smem(zs, zb, static_cast<uint32_t>(K) * D * sizeof(ZT), zbar);
+        if (a.keep_bits) {
+          // the forward's keep bits of this slab land in `flags`; the column pass below turns them into gate flags in place
+          ptx::mbar_arrive_expect_tx(zbar, static_cast<uint32_t>(K) * CH);
+          bulk_load(flags, a.keep_bits + static_cast<size_t>(b) * K * CH, static_cast<uint32_t>(K) * CH, zbar);
+        }
       }
     }
+    zb_global = zb;
     zb = zs;
   }
   AB_TRACE(0);
@@ -401,6 +431,60 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
 
   // da_k = <V_k, dP>: one warp per box row
   const long long vb = static_cast<long long>(b) * K * Dv;
+  const bool vring = SLAB && a.vring_rows > 0;
+  if (vring) {
+    const int RV = a.vring_rows;
+    const uint32_t vrow = static_cast<uint32_t>(Dv) * 2;
+    const uint8_t* vsrc = reinterpret_cast<const uint8_t*>(a.v_hi) + static_cast<size_t>(b) * K * vrow;
+    uint8_t* ringb = reinterpret_cast<uint8_t*>(zs_mem);
+    const int nch = (nb + RV - 1) / RV;
+    for (int k = nb + tid; k < K; k += ATT_THREADS) ds[k] = 0.f;
+    for (int ch = 0; ch < nch; ++ch) {
+      const int slot = ch % AB_VSLOTS;
+      const int rows = nb - ch * RV < RV ? nb - ch * RV : RV;
+      ptx::mbar_wait(&vfull[slot], (ch / AB_VSLOTS) & 1);
+      const uint8_t* vs = ringb + static_cast<size_t>(slot) * RV * vrow;
+      for (int r = warp; r < rows; r += ATT_WARPS) {
+        float acc = 0.f;
+        for (int c = lane; c < (Dv >> 3); c += 32) {
+          uint4 raw;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                       : "r"(ptx::smem_u32(vs + static_cast<size_t>(r) * vrow + c * 16)));
+          const __nv_bfloat162* hh = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          const float2 f0 = __bfloat1622float2(hh[0]), f1 = __bfloat1622float2(hh[1]);
+          const float2 f2 = __bfloat1622float2(hh[2]), f3 = __bfloat1622float2(hh[3]);
+          const float4 p0 = *reinterpret_cast<const float4*>(sdP + c * 8);
+          const float4 p1 = *reinterpret_cast<const float4*>(sdP + c * 8 + 4);
+          acc = fmaf(f0.x, p0.x, acc); acc = fmaf(f0.y, p0.y, acc);
+          acc = fmaf(f1.x, p0.z, acc); acc = fmaf(f1.y, p0.w, acc);
+          acc = fmaf(f2.x, p1.x, acc); acc = fmaf(f2.y, p1.y, acc);
+          acc = fmaf(f3.x, p1.z, acc); acc = fmaf(f3.y, p1.w, acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) ds[ch * RV + r] = acc;
+      }
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&vempty[slot]);
+      // refill: the thread that issues waits until all eight warps have left this slot (completion ch / AB_VSLOTS + 1)
+      if (tid == ATT_THREADS - 1 && (ch + AB_VSLOTS) * RV < nb) {
+        ptx::mbar_wait(&vempty[slot], (ch / AB_VSLOTS) & 1);
+        const int nxt = ch + AB_VSLOTS;
+        const int nrows = nb - nxt * RV < RV ? nb - nxt * RV : RV;
+        ptx::fence_proxy_async();   // the generic-proxy reads of this slot precede the async-proxy refill
+        ptx::mbar_arrive_expect_tx(&vfull[slot], nrows * vrow);
+        bulk_load(ringb + static_cast<size_t>(slot) * RV * vrow, vsrc + static_cast<size_t>(nxt) * RV * vrow, nrows * vrow, &vfull[slot]);
+      }
+    }
+    __syncthreads();   // every warp is done with the ring: the slab (and its keep bits) may land on it
+    if (tid == 0) {
+      ptx::fence_proxy_async();
+      slab_to_smem(zs_mem, zb_global, static_cast<uint32_t>(K) * D * sizeof(ZT), zbar);
+      if (a.keep_bits) {
+        ptx::mbar_arrive_expect_tx(zbar, static_cast<uint32_t>(K) * CH);
+        bulk_load(flags, a.keep_bits + static_cast<size_t>(b) * K * CH, static_cast<uint32_t>(K) * CH, zbar);
+      }
+    }
+  } else
   for (int k = warp; k < K; k += ATT_WARPS) {
     float acc = 0.f;
     if (k < nb && !a.v_lo) {
@@ -769,10 +853,18 @@ static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv,
   const size_t head = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float) +
                       static_cast<size_t>(K) * (D >> 3);
   const size_t slab = static_cast<size_t>(K) * D * sizeof(ZT);
-  const size_t smem_slab = ((head + 15) & ~static_cast<size_t>(15)) + 16 + slab;
-  const bool use_slab = smem_slab <= 112 * 1024 && (slab & 15) == 0;
+  const size_t smem_slab = ((head + 15) & ~static_cast<size_t>(15)) + 64 + slab;
+  const bool use_slab = smem_slab <= 113 * 1024 && (slab & 15) == 0;
   if (head > 220 * 1024) return cudaErrorInvalidValue;
   BwdArgs g2 = g;
+  // feature rows of the <V, dP> pass through a ring laid over the slab buffer: single bf16 plane, whole rows per slot
+  g2.vring_rows = 0;
+  static const bool vring_off = getenv("VQA_ATTN_BWD_VRING") != nullptr && atoi(getenv("VQA_ATTN_BWD_VRING")) == 0;
+  if (use_slab && !g.v_lo && !vring_off) {
+    const size_t vrow = static_cast<size_t>(Dv) * 2;
+    const int rows = static_cast<int>((slab / AB_VSLOTS) / vrow);
+    if (rows >= 1 && (reinterpret_cast<uintptr_t>(g.v_hi) & 15) == 0) g2.vring_rows = rows;
+  }
   // the bit plane travels by bulk copy into `flags` (slab mode, 16-byte granularity); otherwise the kernel redraws the bits
   const size_t flags_off = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float);
   if (!use_slab || (static_cast<size_t>(K) * (D >> 3)) % 16 != 0 || (flags_off & 15) != 0 ||

@@ -217,7 +217,7 @@ VqaStatus dropout_mask_launch(unsigned char* out, long long n, float keep, unsig
                               unsigned long long step, unsigned int stream_id, cudaStream_t s);
 // one byte per group of 8 elements (bit j = keep of element j): the plane the attention kernels read
 VqaStatus keep_bits_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
-                           unsigned long long step, unsigned int stream_id, cudaStream_t s);
+                           unsigned long long step, unsigned int stream_id, cudaStream_t s, int max_ctas = 0);
 
 // ---- variants.cu: kernels of the later family members (vqa_all / vqa_all2, full, adapt) ----
 struct TunedHeadFwd {

@@ -339,12 +339,13 @@ __global__ void keep_bits_kernel(unsigned char* __restrict__ out, long long grou
 }  // namespace
 
 VqaStatus keep_bits_launch(unsigned char* out, long long n, float keep, unsigned long long seed,
-                           unsigned long long step, unsigned int stream_id, cudaStream_t s) {
+                           unsigned long long step, unsigned int stream_id, cudaStream_t s, int max_ctas) {
   if (n == 0) return VQA_OK;
   if (n & 7) return set_error(VQA_ERR_BAD_SHAPE, "keep_bits: n must be a multiple of 8");
   const long long groups = n / 8, quads = (groups + 3) / 4;
   long long g = (quads + 255) / 256;
   if (g > 148 * 8) g = 148 * 8;
+  if (max_ctas > 0 && g > max_ctas) g = max_ctas;
   launch_pdl(keep_bits_kernel, dim3(static_cast<int>(g)), dim3(256), 0, s, out, groups, keep_threshold(keep), seed, step,
              stream_id);
   VQA_LAUNCH_CHECK("keep_bits");

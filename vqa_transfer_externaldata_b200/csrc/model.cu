@@ -236,9 +236,6 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(fill_zero_launch(b.h_f32, sizeof(float) * BL, st));
     VQA_TRY(fill_zero_launch(b.h.hi, sizeof(bf16) * BL, st));
     if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, st));
-    // the step's attention-dropout keep bits, once, for both attention kernels (hidden under the v-projection GEMM)
-    if (use_keep_bits(c, K, D))
-      VQA_TRY(keep_bits_launch(b.att_bits, static_cast<long long>(Bn) * K * D, c.keep_att, seed, step, RNG_STREAM_ATT, st));
     return VQA_OK;
   };
   const bool serial = h->profile && !h->profile_overlapped;
@@ -301,14 +298,28 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   if (serial) VQA_TRY(gru_inputs(s));  // serialised for per-phase timing
   // a2: the recurrent part of the GRU
   const bool persistent = gru_persistent_supported(Bn, L, c.precision, h->num_sms);
+  const bool want_bits = use_keep_bits(c, K, D);
+  bool kb_forked = false;
   if (persistent) {
     GruFwdPersistent a{};
     a.B = Bn; a.L = L; a.T = T; a.q_len = batch->q_intseq_len; a.counter = b.gru_counter;
     a.xg = b.xg; a.xc = b.xc; a.h_f32 = b.h_f32; a.h_bf = b.h.hi; a.rh_bf = b.rh.hi;
     a.r = b.r; a.u = b.u; a.c = b.c;
     a.w_pack = b.gru_pack;
+    // The step's attention-dropout keep bits, once, for both attention kernels: an ALU-only kernel (ten Philox rounds
+    // per 8 elements) on the SMs the cooperative recurrent grid leaves idle -- forked BEFORE that launch, enqueued AFTER
+    // it (the cooperative grid must be first in line), joined before the attention kernel. Beside the v-projection GEMM
+    // it cost that GEMM 10 us (measured).
+    cudaStream_t a5 = s;
+    kb_forked = want_bits && !serial;
+    if (kb_forked) VQA_TRY(fork_stream(h, 5, s, &a5));
     VQA_TRY(gru_fwd_persistent_launch(a, h->num_sms, s));
+    if (want_bits)
+      VQA_TRY(keep_bits_launch(b.att_bits, static_cast<long long>(Bn) * K * D, c.keep_att, seed, step, RNG_STREAM_ATT, a5,
+                               kb_forked ? 8 * (h->num_sms > 128 ? h->num_sms - 128 : 8) : 0));
   } else {
+    if (want_bits)
+      VQA_TRY(keep_bits_launch(b.att_bits, static_cast<long long>(Bn) * K * D, c.keep_att, seed, step, RNG_STREAM_ATT, s));
     for (int t = 0; t < T; ++t) {
       VQA_TRY(GemmB(Bn, 2 * L, L).a(b.h, t * BL, L, false)
                   .b(b.w.gru_gates_w, static_cast<long long>(W) * 2 * L, 2 * L, true)
@@ -375,6 +386,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(row_ln_relu_fwd_launch(r, s));
   }
   PH_END(VQA_PH_QHEADS_FWD);
+  if (kb_forked) VQA_TRY(join_stream(h, 5, s));   // the keep bits
   PH_BEGIN(VQA_PH_ATTN_FWD);
   // a4 + a5: attention + pooling                                     (:151-156)
   {
@@ -833,7 +845,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   // in-library gradient exchange (vqa_set_gradient_allreduce): the slice that is final before the BPTT is reduced under it
   const bool ar_on = h->ar.mc != nullptr && h->ar.world > 1 && g->v_w != nullptr &&
                      g->v_w >= h->ar.local && g->v_w < h->ar.local + h->ar.n_total;
-  const bool early = (h->early_grads || ar_on) && !(h->profile && !h->profile_overlapped);
+  const bool early = h->early_grads && !(h->profile && !h->profile_overlapped);
   if (early && g->v_w)
     VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, s));
   PH_BEGIN(VQA_PH_QV_BWD);
@@ -881,7 +893,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->v_w && !early) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, st));
     return VQA_OK;
   };
-  bool ar_early_done = false;
+  bool ar_early_done = false, ar_late_done = false;
   // GRU: back-propagation through time from dq
   const bool need_gru = g->gru_gates_w || g->gru_gates_b || g->gru_cand_w || g->gru_cand_b || g->embed;
   if (need_gru) {
@@ -999,19 +1011,48 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       // five independent branches (profile mode 2 times the whole section as GRU_WGRAD on the main stream)
       PH_BEGIN(VQA_PH_GRU_WGRAD);
       cudaStream_t a0, a1, a2, a3;
-      VQA_TRY(fork_stream(h, 0, s, &a0));
-      VQA_TRY(fork_stream(h, 1, s, &a1));
-      VQA_TRY(fork_stream(h, 2, s, &a2));
-      VQA_TRY(fork_stream(h, 3, s, &a3));
-      VQA_TRY(gates_h_wgrad(a1, scratch1));
-      VQA_TRY(cand_h_wgrad(a2, scratch2));
-      VQA_TRY(x_wgrad(a3));
-      VQA_TRY(vproj_wgrad(a0));
-      VQA_TRY(embed_bwd(s));
-      VQA_TRY(join_stream(h, 0, s));
-      VQA_TRY(join_stream(h, 1, s));
-      VQA_TRY(join_stream(h, 2, s));
-      VQA_TRY(join_stream(h, 3, s));
+      static const int order_env = getenv("VQA_WGRAD_ORDER") ? atoi(getenv("VQA_WGRAD_ORDER")) : -1;
+      // data-parallel runs (in-library exchange, dWv not taken early): the GRU / embedding gradients FIRST, side by side;
+      // their all-reduce then runs under the v-projection weight gradient, the largest GEMM of the section, which
+      // leaves only the non-GRU slice for the exposed tail. (Single-GPU order: all five side by side.)
+      const bool staged = order_env >= 0 ? order_env != 0 : (ar_on && !early);
+      if (staged) {
+        VQA_TRY(fork_stream(h, 1, s, &a1));
+        VQA_TRY(fork_stream(h, 2, s, &a2));
+        VQA_TRY(fork_stream(h, 3, s, &a3));
+        VQA_TRY(gates_h_wgrad(a1, scratch1));
+        VQA_TRY(cand_h_wgrad(a2, scratch2));
+        VQA_TRY(x_wgrad(a3));
+        VQA_TRY(embed_bwd(s));
+        VQA_TRY(join_stream(h, 1, s));
+        VQA_TRY(join_stream(h, 2, s));
+        VQA_TRY(join_stream(h, 3, s));   // (also: every head / attention parameter gradient of auxiliary stream 3)
+        if (ar_on && !early) {
+          cudaStream_t a5;
+          VQA_TRY(fork_stream(h, 5, s, &a5));
+          h->ar.flag_total += static_cast<unsigned int>(h->ar.world);
+          VQA_TRY(multimem_allreduce_sync_launch(h->ar.mc + h->ar.n_early, h->ar.n_total - h->ar.n_early, h->ar.rank,
+                                                 h->ar.world, h->ar.mc_flags, h->ar.my_flags, h->ar.grid_ctr,
+                                                 h->ar.flag_total, &h->ar.grid_total, false, 32, a5));
+          ar_late_done = true;
+        }
+        VQA_TRY(vproj_wgrad(s));
+        if (ar_late_done) VQA_TRY(join_stream(h, 5, s));
+      } else {
+        VQA_TRY(fork_stream(h, 0, s, &a0));
+        VQA_TRY(fork_stream(h, 1, s, &a1));
+        VQA_TRY(fork_stream(h, 2, s, &a2));
+        VQA_TRY(fork_stream(h, 3, s, &a3));
+        VQA_TRY(gates_h_wgrad(a1, scratch1));
+        VQA_TRY(cand_h_wgrad(a2, scratch2));
+        VQA_TRY(x_wgrad(a3));
+        VQA_TRY(vproj_wgrad(a0));
+        VQA_TRY(embed_bwd(s));
+        VQA_TRY(join_stream(h, 0, s));
+        VQA_TRY(join_stream(h, 1, s));
+        VQA_TRY(join_stream(h, 2, s));
+        VQA_TRY(join_stream(h, 3, s));
+      }
       if (h->prefetched && !h->pf_joined) {   // the background gather forked before the BPTT
         VQA_TRY(join_stream(h, 4, s));
         h->pf_joined = true;
@@ -1029,16 +1070,22 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     h->outputs_pending = false;
   }
   if (ar_on) {
-    // the rest of the gradients (GRU, embedding, the tail slots -- or everything when nothing went out early): one wide
-    // launch whose own entry / exit barriers make the sums valid on `s` when it completes
-    long long off = 0;
+    // what has not been exchanged yet, one wide launch on `s` whose own entry / exit barriers make the sums valid when it
+    // completes: the non-GRU slice [0, n_early) when the GRU / embedding slice went out under the dWv GEMM (default),
+    // the GRU / embedding slice when the early slice went out under the BPTT (vqa_set_early_gradients), else everything
+    long long off = 0, cnt = h->ar.n_total;
     if (ar_early_done) {
       VQA_TRY(join_stream(h, 5, s));
       off = h->ar.n_early;
+      cnt = h->ar.n_total - off;
+    } else if (ar_late_done) {
+      cnt = h->ar.n_early;
     }
-    h->ar.flag_total += static_cast<unsigned int>(h->ar.world);
-    VQA_TRY(multimem_allreduce_sync_launch(h->ar.mc + off, h->ar.n_total - off, h->ar.rank, h->ar.world, h->ar.mc_flags,
-                                           h->ar.my_flags, h->ar.grid_ctr, h->ar.flag_total, &h->ar.grid_total, false, 0, s));
+    if (cnt > 0) {
+      h->ar.flag_total += static_cast<unsigned int>(h->ar.world);
+      VQA_TRY(multimem_allreduce_sync_launch(h->ar.mc + off, cnt, h->ar.rank, h->ar.world, h->ar.mc_flags, h->ar.my_flags,
+                                             h->ar.grid_ctr, h->ar.flag_total, &h->ar.grid_total, false, 0, s));
+    }
   }
   return VQA_OK;
 }

@@ -153,7 +153,8 @@ class DataParallel:
                     self.all_reduce_gradients(eng)
                 torch.cuda.synchronize(device)
                 g = {f: v.detach().clone() for f, v in eng.params.grad_views.items()}
-                used_mc = self._mc is not None
+                used_mc = ("multimem, inside vqa_backward" if self._mc is not None and self._in_library else
+                           "multimem" if self._mc is not None else "nccl")
                 eng.close()
                 return g, used_mc
 
