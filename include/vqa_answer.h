@@ -254,6 +254,29 @@ VQA_API uint64_t vqa_launch_count(void);
  * (vqa/datasets/input_ops_vqa_tf_record_memft.py:17-22); used by the Python mirror's record reader. No GPU involved. */
 VQA_API uint32_t vqa_crc32c(const uint8_t* data_host, uint64_t n);
 
+/* ---- input side in native code (vqa/datasets/input_ops_vqa_tf_record_memft.py:17-82; csrc/input_host.cu) -----------------
+ * vqa_tfrecord_index_host: payload offsets / lengths of every record of one TFRecord file held in HOST memory (framing
+ *   u64 length | u32 masked crc32c | payload | u32 masked crc32c), both checksums verified when verify_crc; *count is
+ *   the number of records found (fill at most `capacity`; call again with larger arrays if *count > capacity).
+ * vqa_parse_examples_host: parse_fn + padded_batch for n serialized tf.train.Example records in HOST memory: qid ->
+ *   id (default -1), image_idx (default -1), q_intseq/list -> row i of q_intseq [n, t_cap] padded with 0, q_intseq/len
+ *   (required), *t_longest = longest question of the batch; the soft-score target is emitted SPARSE: triples
+ *   (ans_row, ans_id, ans_score), *ans_count of them (a repeated id keeps its last score, as target[ids] = scores
+ *   does); image_id is returned as offset / length into each record (optional). Errors (malformed message, missing
+ *   q_intseq/len, ids / scores of different length, answer id outside [0, num_answers), a question longer than
+ *   t_cap) return VQA_ERR_BAD_SHAPE with the record number in vqa_last_error().
+ * vqa_densify_targets: tf.sparse_to_dense on the DEVICE: target[batch, num_answers] = 0, then target[row, id] = score
+ *   for the n triples (device pointers), on `stream`. A step then uploads the triples (KBs), not 6 MB of zeros. */
+VQA_API VqaStatus vqa_tfrecord_index_host(const uint8_t* file_host, uint64_t size, int32_t verify_crc, uint64_t* offsets,
+                                          uint64_t* lengths, int64_t capacity, int64_t* count);
+VQA_API VqaStatus vqa_parse_examples_host(const uint8_t* const* records, const uint64_t* lengths, int32_t n,
+                                          int32_t num_answers, int32_t t_cap, int64_t* id, int64_t* image_idx,
+                                          int32_t* q_intseq, int32_t* q_intseq_len, int32_t* t_longest,
+                                          int32_t* ans_row, int32_t* ans_id, float* ans_score, int32_t ans_cap,
+                                          int32_t* ans_count, uint32_t* image_id_off, uint32_t* image_id_len);
+VQA_API VqaStatus vqa_densify_targets(const int32_t* rows, const int32_t* ids, const float* scores, int32_t n, int32_t batch,
+                                      int32_t num_answers, float* target, void* stream);
+
 /* bytes of device workspace this handle needs; attach a buffer of at least that size (256-B aligned) */
 VQA_API VqaStatus vqa_workspace_bytes(VqaHandle h, uint64_t* bytes);
 VQA_API VqaStatus vqa_set_workspace(VqaHandle h, void* dev_ptr, uint64_t bytes);

@@ -88,6 +88,17 @@ def test_tfrecord_batches_feed_the_model(tmp_path):
     ref = model.output["logit"].clone()
     model.forward(rb, dropout_step=0)     # T of this batch = its longest question (padded_batch), not the configured maximum
     assert torch.allclose(model.output["logit"], ref, rtol=1e-5, atol=1e-5)
+    loss_ref = float(model.fetch()[0])
+    # the native reader (csrc/input_host.cu): same batch, the soft-score target as (row, id, score) triples that
+    # vqa_densify_targets scatters on the device
+    from vqa_transfer_externaldata_b200 import input_native as IN
+    (nb,) = list(IN.create(B, str(tmp_path), "val", is_train=False))
+    assert "answer_target" not in nb and np.array_equal(IN.densify(nb), batch["answer_target"])
+    model.forward(nb, dropout_step=0)
+    assert torch.allclose(model.output["logit"], ref, rtol=1e-5, atol=1e-5)
+    assert abs(float(model.fetch()[0]) - loss_ref) <= 1e-6 * max(1.0, abs(loss_ref))
+    got_target = model.engine.cur.d_target[:B * A].cpu().numpy().reshape(B, A)
+    assert np.array_equal(got_target, batch["answer_target"])
 
 
 def test_checkpoint_bundle_round_trip(tmp_path):

@@ -242,6 +242,10 @@ class BatchSet:
         self.h_q = torch.zeros(cfg.B * cfg.T, dtype=torch.int32).pin_memory()
         self.h_qlen = torch.zeros(cfg.B, dtype=torch.int32).pin_memory()
         self.h_target = torch.zeros(cfg.B * cfg.A, dtype=torch.float32).pin_memory()
+        # sparse soft-score targets (input_native batches): (row, answer id, score) triples, densified on the device
+        self.ans_cap = 16 * cfg.B
+        self.d_ans = torch.zeros(3 * self.ans_cap, dtype=torch.int32, device=dev)
+        self.h_ans = torch.zeros(3 * self.ans_cap, dtype=torch.int32).pin_memory()
         self.batch_size, self.q_len_max = 0, cfg.T
         self.ready = torch.cuda.Event()
         self.staged = None   # event after the last H2D copies out of the pinned staging buffers of this set
@@ -418,14 +422,40 @@ class Engine:
         Bn, T = int(q.shape[0]), int(q.shape[1])
         if Bn > cfg.B or T > cfg.T:
             raise ValueError(f"batch [{Bn}, T={T}] exceeds config (B={cfg.B}, T={cfg.T})")
-        if tuple(batch["answer_target"].shape) != (Bn, cfg.A):
+        sparse = "answer_target" not in batch and "answer_sparse" in batch
+        if not sparse and tuple(batch["answer_target"].shape) != (Bn, cfg.A):
             raise ValueError(f"answer_target shape {tuple(batch['answer_target'].shape)} != ({Bn}, {cfg.A})")
-        items = (("image_idx", bs.h_image_idx, bs.d_image_idx, torch.int64, np.int64, Bn),
+        items = [("image_idx", bs.h_image_idx, bs.d_image_idx, torch.int64, np.int64, Bn),
                  ("q_intseq", bs.h_q, bs.d_q, torch.int32, np.int32, Bn * T),
-                 ("q_intseq_len", bs.h_qlen, bs.d_qlen, torch.int32, np.int32, Bn),
-                 ("answer_target", bs.h_target, bs.d_target, torch.float32, np.float32, Bn * cfg.A))
+                 ("q_intseq_len", bs.h_qlen, bs.d_qlen, torch.int32, np.int32, Bn)]
+        if not sparse:
+            items.append(("answer_target", bs.h_target, bs.d_target, torch.float32, np.float32, Bn * cfg.A))
         nbytes = 0
         used_staging = False
+        if sparse:
+            # tf.sparse_to_dense on the device (vqa_densify_targets): the step uploads the triples, not [B, A] floats
+            rows, ids, scores = (np.asarray(x) for x in batch["answer_sparse"])
+            n = int(rows.shape[0])
+            if n > bs.ans_cap:
+                raise ValueError(f"{n} answer triples exceed the staging capacity {bs.ans_cap}")
+            if n and (int(rows.min()) < 0 or int(rows.max()) >= Bn or int(ids.min()) < 0 or int(ids.max()) >= cfg.A):
+                raise IndexError("answer_sparse: row / answer id out of range")
+            if bs.staged is not None:
+                bs.staged.synchronize()
+            used_staging = True
+            cap = bs.ans_cap
+            h = bs.h_ans.numpy()
+            h[:n] = rows.astype(np.int32, copy=False)
+            h[cap:cap + n] = ids.astype(np.int32, copy=False)
+            h[2 * cap:2 * cap + n] = scores.astype(np.float32, copy=False).view(np.int32)
+            for k in range(3):
+                bs.d_ans[k * cap:k * cap + n].copy_(bs.h_ans[k * cap:k * cap + n], non_blocking=True)
+            d0 = bs.d_ans.data_ptr()
+            L.check(self.lib.vqa_densify_targets(C.c_void_p(d0), C.c_void_p(d0 + 4 * cap), C.c_void_p(d0 + 8 * cap),
+                                                 C.c_int32(n), C.c_int32(Bn), C.c_int32(cfg.A),
+                                                 C.c_void_p(bs.d_target.data_ptr()),
+                                                 C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
+            nbytes += 12 * n
         for key, hbuf, dbuf, tdt, ndt, n in items:
             v = batch[key]
             direct = isinstance(v, torch.Tensor) and v.dtype == tdt and v.is_contiguous() and (v.is_pinned() or v.is_cuda)

@@ -359,9 +359,9 @@ def create(batch_size, tf_record_dir, split, is_train=True, scope="vqa_tf_record
                 cache["items"].append(s)
             buf.append(s)
             if len(buf) >= size:
-                yield buf.pop(int(rng.integers(len(buf))) if size > 1 else 0)
+                yield buf.pop(int(rng.random() * len(buf)) if size > 1 else 0)
         while buf:
-            yield buf.pop(int(rng.integers(len(buf))) if size > 1 else 0)
+            yield buf.pop(int(rng.random() * len(buf)) if size > 1 else 0)
         cache["done"] = is_train
 
     def batches():

@@ -144,6 +144,10 @@ SYMBOLS = {
     "vqa_launch_count": (C.c_uint64, []),
     "vqa_gru_kernel_path": (C.c_int32, []),
     "vqa_crc32c": (C.c_uint32, [C.c_char_p, C.c_uint64]),
+    "vqa_tfrecord_index_host": (C.c_int32, [_P, C.c_uint64, C.c_int32, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "vqa_parse_examples_host": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, C.POINTER(C.c_int32),
+                                            _P, _P, _P, C.c_int32, C.POINTER(C.c_int32), _P, _P]),
+    "vqa_densify_targets": (C.c_int32, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "vqa_workspace_bytes": (C.c_int32, [_P, C.POINTER(C.c_uint64)]),
     "vqa_set_workspace": (C.c_int32, [_P, _P, C.c_uint64]),
     "vqa_prepare_params": (C.c_int32, [_P, C.POINTER(VqaParams), _P]),
