@@ -95,3 +95,26 @@ def test_enums_match_header():
     assert 1 + len(re.findall(r"VQA_REPORT_\w+", report)) == L.NUM_REPORT == len(L.REPORT_KEYS) + len(L.EXTRA_REPORT_KEYS)
     acts = re.search(r"VQA_ACT_HQ = 0,(.*?)VQA_NUM_ACT", src, flags=re.S).group(1)
     assert 1 + len(re.findall(r"VQA_ACT_\w+", acts)) == 7 == L.ACT_VA + 1
+
+
+MEMFT_HEADER = os.path.join(ROOT, "include", "vqa_memft.h")
+
+
+def test_memft_header_binding_and_layouts(lib):
+    """include/vqa_memft.h (the pre-training path's operators): every declared symbol is exported and bound, the binding
+    binds nothing else, and the ctypes structs list the fields in the header's order."""
+    from vqa_transfer_externaldata_b200 import lib as L
+    src = re.sub(r"/\*.*?\*/", "", open(MEMFT_HEADER).read(), flags=re.S)
+    names = sorted(set(re.findall(r"VQA_API\s+[\w\s\*]+?\b(vqa_\w+)\s*\(", src)))
+    assert len(names) >= 15 and sorted(L.MEMFT_SYMBOLS) == names
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/vqa_memft.h but not exported"
+    for cname, cls in (("VqaSlabLn", L.VqaSlabLn), ("VqaSpatAttn", L.VqaSpatAttn), ("VqaSoftmaxCe", L.VqaSoftmaxCe),
+                       ("VqaGruSeq", L.VqaGruSeq)):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
+        fields = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                fields.extend(re.findall(r"(\w+)\s*(?:\[\d+\])?\s*$", part.strip())[0] for part in decl.split(","))
+        assert fields == [f[0] for f in cls._fields_], cname

@@ -128,11 +128,14 @@ def test_bf16_full_row_tiles():
     _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
 
 
-def test_gru_pair_kernels_match_single_cta_kernels_at_full_size():
+@pytest.mark.parametrize("B", [512, 1216])
+def test_gru_pair_kernels_match_single_cta_kernels_at_full_size(B):
     """cfg1 layer sizes and batch (B 512, L 1024, T 14): the CTA-pair GRU kernels (TMA-store publication, k-block
     boxes) against the single-CTA kernels on the same inputs. Both round operands to bf16 at the same points and
-    accumulate every dot product in the same k order, so states and gradients must agree to fp32 rounding."""
-    dims = dict(B=512, K=8, Dv=256, D=1024, L=1024, A=200, T=14, W=300, Vq=512)
+    accumulate every dot product in the same k order, so states and gradients must agree to fp32 rounding.
+    B 1216 = 512 + 512 + 192 rows: three consecutive cooperative launches, the last with a half-empty second row tile
+    (the pre-training graph's 5120 sequences and BASELINE config 5's large inference batches run this way)."""
+    dims = dict(B=B, K=8, Dv=256, D=1024, L=1024, A=200, T=14, W=300, Vq=512)
     case = build_case(dims, precision="bf16", seed=9, num_images=32)
     eng = case["eng"]
     eng.stage_batch(case["batch"])

@@ -766,7 +766,7 @@ static bool try_pair(cudaError_t e, const char* what) {
 VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
   g_fwd_was_pair = false;
-  if (!g_pair_refused && gru_pair_supported(B, L, num_sms) && try_pair(gru_pair_fwd(a, s), "gru forward")) {
+  if (!g_pair_refused && gru_pair_supported(B, L, num_sms) && try_pair(gru_pair_fwd(a, num_sms, s), "gru forward")) {
     g_fwd_was_pair = true;
     return VQA_OK;
   }
@@ -786,7 +786,7 @@ VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cuda
   const int B = a.B, L = a.L, T = a.T;
   if (g_fwd_was_pair) {
     // the saved state is in the pair kernels' layout: only the pair BPTT kernel can read it
-    cudaError_t e = gru_pair_bwd(a, s);
+    cudaError_t e = gru_pair_bwd(a, num_sms, s);
     if (e != cudaSuccess) return set_cuda_error(e, "gru BPTT (pair) launch");
     count_launch();
     return VQA_OK;

@@ -62,6 +62,7 @@ __host__ __device__ constexpr int q_smem_bytes(int L) { return q_wres_bytes(L) +
 
 struct PairGruArgs {
   int B, row_end, L, T;
+  int row0;                // first batch row of this launch (batches beyond one co-resident wave run as consecutive launches)
   const int* q_len;
   unsigned int* counter;   // [2 * row tiles]
   const float* xg; const float* xc;
@@ -188,7 +189,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
   const int slice32 = blockIdx.x;               // 32-unit slice whose weights this CTA holds (= 2 * pair + rank)
   const int mi = blockIdx.y;
   const int j0 = slice32 * Q_UNITS;
-  const int m0 = mi * 128 + static_cast<int>(rank) * Q_ROWS;   // first batch row of this CTA
+  const int m0 = g.row0 + mi * 128 + static_cast<int>(rank) * Q_ROWS;   // first batch row of this CTA
   const unsigned int nprod = gridDim.x >> 1;    // CTAs producing this CTA's activation rows (same row tile and rank)
   unsigned int* counter = g.counter + 2 * mi + rank;
   const int num_phases = 2 * T;
@@ -612,7 +613,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       if ((q & 1) == 0 && lane < 3 * NU) {
         const int k = lane / NU, j = lane % NU;
         const float s = red[((warp - 2) * 3 + k) * NU + j] + red[((warp - 2 + 1) * 3 + k) * NU + j];
-        float* out = g.bias_part + static_cast<long long>(2 * mi + rank) * 3 * L;
+        float* out = g.bias_part + static_cast<long long>(2 * (g.row0 / 128 + mi) + rank) * 3 * L;
         out[k * L + unit + j] = s;
       }
     }
@@ -673,12 +674,32 @@ bool gru_pair_supported(int B, int L, int num_sms) {
   if (g_pair_off) return false;
   if (L % 64 != 0 || L < 64) return false;
   if (q_smem_bytes(L) > 227 * 1024) return false;
-  const int row_tiles = (B + 127) / 128;
-  return (L / Q_UNITS) * row_tiles <= num_sms && 2 * row_tiles <= 64;   // one wave, counters fit
+  (void)B;   // any batch: row tiles beyond one co-resident wave run as consecutive launches (launch_chunks)
+  return L / Q_UNITS <= num_sms;
+}
+
+// one cooperative launch per wave of co-resident row tiles (num_sms / (L / 32) tiles of 128 rows: 4 at L = 1024)
+template <int MODE>
+cudaError_t launch_chunks(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
+                          const CUtensorMap& o0, const CUtensorMap& o1, PairGruArgs& g, int num_sms, cudaStream_t s) {
+  const int slices = g.L / Q_UNITS;
+  int per = num_sms / slices;
+  if (per > 32) per = 32;   // counters: [2 * tiles] of a 64-entry array
+  for (int row0 = 0; row0 < g.B; row0 += per * 128) {
+    const int rows = g.B - row0 < per * 128 ? g.B - row0 : per * 128;
+    const int tiles = (rows + 127) / 128;
+    cudaError_t e = cudaMemsetAsync(g.counter, 0, sizeof(unsigned int) * 2 * tiles, s);
+    if (e != cudaSuccess) return e;
+    g.row0 = row0;
+    e = launch_pair_gru<MODE>(a0, a1, w0, w1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L), s);
+    if (e != cudaSuccess) return e;
+    if (row0 > 0) count_launch();   // (the caller counts the first)
+  }
+  return cudaSuccess;
 }
 
 // returns cudaSuccess, or the launch error (the caller falls back to the single-CTA kernels)
-cudaError_t gru_pair_fwd(const GruFwdPersistent& a, cudaStream_t s) {
+cudaError_t gru_pair_fwd(const GruFwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
   CUtensorMap tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h;
   const uint64_t prow = static_cast<uint64_t>(L / 32) * 96;
@@ -696,13 +717,10 @@ cudaError_t gru_pair_fwd(const GruFwdPersistent& a, cudaStream_t s) {
   g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
   g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;
   g.kbs = kbs;
-  const int row_tiles = (B + 127) / 128;
-  cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * 2 * row_tiles, s);
-  if (e != cudaSuccess) return e;
-  return launch_pair_gru<0>(tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h, g, dim3(L / Q_UNITS, row_tiles), q_smem_bytes(L), s);
+  return launch_chunks<0>(tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h, g, num_sms, s);
 }
 
-cudaError_t gru_pair_bwd(const GruBwdPersistent& a, cudaStream_t s) {
+cudaError_t gru_pair_bwd(const GruBwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
   CUtensorMap tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc;
   const int kbs = pick_kbs(L);
@@ -720,10 +738,7 @@ cudaError_t gru_pair_bwd(const GruBwdPersistent& a, cudaStream_t s) {
   g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
   g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;
   g.kbs = kbs;
-  const int row_tiles = (B + 127) / 128;
-  cudaError_t e = cudaMemsetAsync(a.counter, 0, sizeof(unsigned int) * 2 * row_tiles, s);
-  if (e != cudaSuccess) return e;
-  return launch_pair_gru<1>(tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc, g, dim3(L / Q_UNITS, row_tiles), q_smem_bytes(L), s);
+  return launch_chunks<1>(tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc, g, num_sms, s);
 }
 
 }  // namespace vqa

@@ -137,8 +137,8 @@ size_t gru_bias_part_floats(int B, int L);
 int gru_bias_part_rows(int B);   // partial rows of [3L] the BPTT kernels write (two per 128-row tile)
 extern unsigned long long* g_gru_trace;
 bool gru_pair_supported(int B, int L, int num_sms);
-cudaError_t gru_pair_fwd(const GruFwdPersistent& a, cudaStream_t s);
-cudaError_t gru_pair_bwd(const GruBwdPersistent& a, cudaStream_t s);
+cudaError_t gru_pair_fwd(const GruFwdPersistent& a, int num_sms, cudaStream_t s);
+cudaError_t gru_pair_bwd(const GruBwdPersistent& a, int num_sms, cudaStream_t s);
 VqaStatus gru_pack_weights_launch(const bf16* wg_h, const bf16* wc_h, int L, bf16* out, cudaStream_t s);
 VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cudaStream_t s);
 VqaStatus gru_bwd_persistent_launch(const GruBwdPersistent& a, int num_sms, cudaStream_t s);

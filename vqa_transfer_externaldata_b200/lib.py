@@ -185,6 +185,65 @@ SYMBOLS = {
                                     _P, _P, _P, _P]),
 }
 
+
+# ---- include/vqa_memft.h: operators of the vlmap pre-training path ----
+class VqaSlabLn(C.Structure):
+    _fields_ = [("slabs", C.c_int32), ("n", C.c_int32), ("N", C.c_int32), ("act", C.c_int32), ("z", C.c_void_p),
+                ("gamma", C.c_void_p), ("beta", C.c_void_p), ("mul", C.c_void_p), ("mul_rows", C.c_int64),
+                ("keep", C.c_float), ("seed", C.c_uint64), ("step", C.c_uint64), ("site0", C.c_uint32),
+                ("rows_per_site", C.c_int64), ("mean", C.c_void_p), ("rstd", C.c_void_p), ("y", C.c_void_p),
+                ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("out_lo", C.c_void_p), ("dout", C.c_void_p),
+                ("dout2", C.c_void_p), ("dz_f32", C.c_void_p), ("dz_hi", C.c_void_p), ("dz_lo", C.c_void_p),
+                ("dmul", C.c_void_p), ("part", C.c_void_p)]
+
+
+class VqaSpatAttn(C.Structure):
+    _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("n", C.c_int32), ("D", C.c_int32), ("Dv", C.c_int32),
+                ("kinds", C.c_int32), ("hv_hi", C.c_void_p), ("hv_lo", C.c_void_p), ("hq", C.c_void_p),
+                ("att_w", C.c_void_p), ("att_b", C.c_void_p), ("num_boxes", C.c_void_p), ("v", C.c_void_p),
+                ("keep", C.c_float), ("seed", C.c_uint64), ("step", C.c_uint64), ("site0", C.c_uint32),
+                ("att", C.c_void_p), ("pooled", C.c_void_p), ("pooled_hi", C.c_void_p), ("pooled_lo", C.c_void_p),
+                ("d_pooled", C.c_void_p), ("d_hv", C.c_void_p), ("d_hq", C.c_void_p), ("part", C.c_void_p)]
+
+
+class VqaSoftmaxCe(C.Structure):
+    _fields_ = [("heads", C.c_int32), ("B", C.c_int32), ("n", C.c_int32), ("A", C.c_int32), ("top_k", C.c_int32),
+                ("logit", C.c_void_p), ("fills", C.c_void_p), ("num", C.c_void_p * 8), ("loss_scale", C.c_float),
+                ("stats", C.c_void_p), ("report", C.c_void_p), ("d_logit", C.c_void_p), ("d_hi", C.c_void_p),
+                ("d_lo", C.c_void_p)]
+
+
+class VqaGruSeq(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("L", C.c_int32), ("W", C.c_int32), ("Vq", C.c_int32),
+                ("precision", C.c_int32), ("embed", C.c_void_p), ("gates_w", C.c_void_p), ("gates_b", C.c_void_p),
+                ("cand_w", C.c_void_p), ("cand_b", C.c_void_p), ("tokens", C.c_void_p), ("len", C.c_void_p),
+                ("ws", C.c_void_p), ("ws_bytes", C.c_uint64), ("q", C.c_void_p), ("q_hi", C.c_void_p),
+                ("q_lo", C.c_void_p), ("dq", C.c_void_p), ("d_embed", C.c_void_p), ("d_gates_w", C.c_void_p),
+                ("d_gates_b", C.c_void_p), ("d_cand_w", C.c_void_p), ("d_cand_b", C.c_void_p)]
+
+
+MEMFT_SYMBOLS = {
+    "vqa_ops_create": (C.c_int32, [C.POINTER(_P)]),
+    "vqa_ops_destroy": (C.c_int32, [_P]),
+    "vqa_ops_gemm": (C.c_int32, [_P, C.POINTER(VqaGemmDesc), C.c_int32, _P]),
+    "vqa_ops_colsum": (C.c_int32, [_P, _P, C.c_int64, C.c_int64, C.c_int64, _P, _P]),
+    "vqa_ops_adam": (C.c_int32, [_P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
+                                 C.c_int64, _P, _P]),
+    "vqa_ops_split_bf16": (C.c_int32, [_P, C.c_int64, C.c_int64, C.c_int64, _P, _P, C.c_int64, _P]),
+    "vqa_ops_dropout_mask": (C.c_int32, [_P, C.c_int64, C.c_float, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
+    "vqa_ops_slab_ln_fwd": (C.c_int32, [_P, C.POINTER(VqaSlabLn), _P]),
+    "vqa_ops_slab_ln_bwd": (C.c_int32, [_P, C.POINTER(VqaSlabLn), _P]),
+    "vqa_ops_pad_planes": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P]),
+    "vqa_memft_spat_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaSpatAttn), _P]),
+    "vqa_memft_spat_attn_bwd": (C.c_int32, [_P, C.POINTER(VqaSpatAttn), _P]),
+    "vqa_memft_softmax_ce": (C.c_int32, [_P, C.POINTER(VqaSoftmaxCe), _P]),
+    "vqa_memft_wordset_fwd": (C.c_int32, [_P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P, _P, C.c_int32, _P]),
+    "vqa_memft_wordset_bwd": (C.c_int32, [_P, _P, _P, C.c_int64, C.c_int32, C.c_int32, _P, _P]),
+    "vqa_ops_gru_workspace_bytes": (C.c_int32, [C.POINTER(VqaGruSeq), C.POINTER(C.c_uint64)]),
+    "vqa_ops_gru_fwd": (C.c_int32, [_P, C.POINTER(VqaGruSeq), _P]),
+    "vqa_ops_gru_bwd": (C.c_int32, [_P, C.POINTER(VqaGruSeq), _P]),
+}
+
 _lib = None
 
 
@@ -199,7 +258,7 @@ def load(path=None):
             f"{p} not found: build it with `python -m vqa_transfer_externaldata_b200.build` "
             "(or __graft_entry__.build()). This package has no CPU fallback.")
     lib = C.CDLL(p)
-    for name, (res, args) in SYMBOLS.items():
+    for name, (res, args) in list(SYMBOLS.items()) + list(MEMFT_SYMBOLS.items()):
         fn = getattr(lib, name)  # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
