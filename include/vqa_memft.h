@@ -103,6 +103,9 @@ typedef struct VqaSoftmaxCe {
   const int32_t* fills;          /* [heads * B * n] target class per row */
   const int32_t* num[8];         /* per head: [B] */
   float loss_scale;
+  float count[8];                /* > 0: the head's valid-entry count to normalise d_logit by instead of this batch's own
+                                  * (batch-sharded data parallelism: the count of the GLOBAL batch, so that the sum of the
+                                  * ranks' gradients is the gradient of the global loss) */
   float* stats; float* report;
   float* d_logit; void* d_hi; void* d_lo;
 } VqaSoftmaxCe;

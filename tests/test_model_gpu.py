@@ -128,18 +128,21 @@ def test_bf16_full_row_tiles():
     _check(case, got, ref, ref_g, BF16_TOL, exact_pred=False)
 
 
-@pytest.mark.parametrize("B", [512, 1216])
-def test_gru_pair_kernels_match_single_cta_kernels_at_full_size(B):
+@pytest.mark.parametrize("B,waves", [(512, 0), (1216, 0), (512, 2), (1216, 1), (832, 2)])
+def test_gru_pair_kernels_match_single_cta_kernels_at_full_size(B, waves):
     """cfg1 layer sizes and batch (B 512, L 1024, T 14): the CTA-pair GRU kernels (TMA-store publication, k-block
     boxes) against the single-CTA kernels on the same inputs. Both round operands to bf16 at the same points and
     accumulate every dot product in the same k order, so states and gradients must agree to fp32 rounding.
-    B 1216 = 512 + 512 + 192 rows: three consecutive cooperative launches, the last with a half-empty second row tile
-    (the pre-training graph's 5120 sequences and BASELINE config 5's large inference batches run this way)."""
+    B 1216 = 1024 + 192 rows: one launch in which every CTA pair alternates between two 512-row waves, then a
+    single-wave launch with a half-empty second row tile (the pre-training graph's 5120 sequences and BASELINE config 5's
+    large inference batches run this way). waves = 1: single waves only (512 + 512 + 192); waves = 2: also a batch of one
+    wave is split into two half-waves on half of the SMs."""
     dims = dict(B=B, K=8, Dv=256, D=1024, L=1024, A=200, T=14, W=300, Vq=512)
     case = build_case(dims, precision="bf16", seed=9, num_images=32)
     eng = case["eng"]
     eng.stage_batch(case["batch"])
     res = {}
+    eng.lib.vqa_internal_set_gru_waves(C.c_int(waves))
     for on in (1, 0):
         eng.lib.vqa_internal_set_gru_pair(C.c_int(on))
         eng.forward(seed=3, step=1)
@@ -147,6 +150,7 @@ def test_gru_pair_kernels_match_single_cta_kernels_at_full_size(B):
         torch.cuda.synchronize()
         res[on] = (eng.o_condition.clone(), {k: v.clone() for k, v in eng.params.grad_views.items()})
     eng.lib.vqa_internal_set_gru_pair(C.c_int(1))
+    eng.lib.vqa_internal_set_gru_waves(C.c_int(0))
     q1, g1 = res[1]
     q0, g0 = res[0]
     assert torch.isfinite(q1).all()

@@ -426,7 +426,10 @@ bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int n
   int splits = 1;
   if (!narrow && !d.out_hi && d.out_f32 && ctx && ctx->sem && tiles < pairs && tiles <= ctx->region_elems) {
     splits = static_cast<int>(pairs / tiles);
-    if (splits > 4) splits = 4;
+    // (a very long K over a handful of tiles -- the x-row weight gradients of 5120 GRU sequences, K = 51200 -- is worth
+    // eight hand-overs per tile; the heads' K <= 18432 keeps four)
+    const int cap = num_kb >= 512 ? 8 : 4;
+    if (splits > cap) splits = cap;
     while (splits > 1 && num_kb / splits < 8) --splits;   // keep >= 8 k-blocks per item
   }
   // M = 512 heads with a short K: the 128 x 64 single-CTA tiles start sooner than 2 x 256-row pair tiles fill

@@ -52,7 +52,7 @@ constexpr int Q_STAGE_R = Q_KBS * Q_A_TILE;                // 32 KB resident-pha
 constexpr int Q_RING = 2 * Q_STAGE_S;                      // = 3 * Q_STAGE_R = 96 KB
 static_assert(Q_RING == 3 * Q_STAGE_R, "ring geometries");
 constexpr int Q_EPI_WARPS = 16;
-constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS;
+constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS + 32;   // producer, MMA issuer, 16 epilogue warps, publisher (WAVES = 2)
 constexpr int Q_TMEM_COLS = 128;                // forward: gates at column 0 (64 wide), candidate at 64 (32 wide)
 constexpr int NU = 8;                           // units per epilogue thread
 
@@ -63,6 +63,8 @@ __host__ __device__ constexpr int q_smem_bytes(int L) { return q_wres_bytes(L) +
 struct PairGruArgs {
   int B, row_end, L, T;
   int row0;                // first batch row of this launch (batches beyond one co-resident wave run as consecutive launches)
+  int wave_rows;           // WAVES = 2: rows between the two row groups a CTA pair alternates between (tiles per wave * 128)
+  int priv_layout;         // B % 64 == 0: saved state in the lane-contiguous private layout
   const int* q_len;
   unsigned int* counter;   // [2 * row tiles]
   const float* xg; const float* xc;
@@ -163,7 +165,14 @@ __device__ __forceinline__ void stage8bf(uint32_t tile, int r, int chunk, const 
 // tm_o0 / tm_o1: the tensors phase kind 0 / 1 PRODUCES (= the operand of the other kind), 64 x 64 boxes for TMA stores;
 // tm_w0 / tm_w1: this CTA's weight rows of kind 0 / 1 (forward: packed slices, box 64 x 64 and 64 x 32;
 //                BPTT: Wc_h rows and Wg_h rows in TF layout, box 64 x 32 both).
-template <int MODE>
+// WAVES = 2: every CTA pair serves TWO independent row groups ("waves") with the same resident weights and alternates
+// between them phase by phase: while the epilogue warps turn wave A's accumulator into the next operand tile and the
+// other CTAs' arrivals trickle in, the producer and MMA warps already run wave B's phase. One wave leaves the tensor
+// pipe and the load path idle for ~60 % of a phase (profiles/r02_gru_phase_trace.txt: 2.6 us of loads + MMAs in a 5.9 us
+// phase); two waves fill that gap. Each wave has its own accumulator columns, accumulator barrier and counters; the ring
+// is shared (a phase starts once the previous phase's stages are consumed), so the operand tiles leave through plain
+// 16-byte stores + a gpu-scope fence instead of the TMA-store staging inside the ring.
+template <int MODE, int WAVES>
 __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
     const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
@@ -180,19 +189,27 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
   uint8_t* ring = smem + q_wres_bytes(L);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + Q_RING);
   uint64_t* empty_bar = full_bar + Q_STAGES;
-  uint64_t* tmem_full_bar = empty_bar + Q_STAGES;
-  uint64_t* w_bar = tmem_full_bar + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + Q_STAGES;   // [2]: one per wave
+  uint64_t* w_bar = tmem_full_bar + 2;
+  uint64_t* pub_bar = w_bar + 1;                     // [2]: "every epilogue thread has stored its share of the operand tile"
+  uint64_t* sig_bar = pub_bar + 2;                   // [2]: "the publisher has signalled this wave's phase"
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sig_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
   const int slice32 = blockIdx.x;               // 32-unit slice whose weights this CTA holds (= 2 * pair + rank)
   const int mi = blockIdx.y;
   const int j0 = slice32 * Q_UNITS;
-  const int m0 = g.row0 + mi * 128 + static_cast<int>(rank) * Q_ROWS;   // first batch row of this CTA
+  int m0w[WAVES];                                // first batch row of this CTA in each wave
+  unsigned int* counterw[WAVES];
+#pragma unroll
+  for (int w = 0; w < WAVES; ++w) {
+    m0w[w] = g.row0 + w * g.wave_rows + mi * 128 + static_cast<int>(rank) * Q_ROWS;
+    counterw[w] = g.counter + 2 * (w * static_cast<int>(gridDim.y) + mi) + rank;
+  }
   const unsigned int nprod = gridDim.x >> 1;    // CTAs producing this CTA's activation rows (same row tile and rank)
-  unsigned int* counter = g.counter + 2 * mi + rank;
   const int num_phases = 2 * T;
+  constexpr int TM_WAVE = 128;                  // accumulator columns per wave
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tensormap(&tm_a0);
@@ -203,12 +220,17 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       ptx::mbar_init(&full_bar[s], 1);
       ptx::mbar_init(&empty_bar[s], 1);
     }
-    ptx::mbar_init(tmem_full_bar, 1);
+    ptx::mbar_init(&tmem_full_bar[0], 1);
+    ptx::mbar_init(&tmem_full_bar[1], 1);
     ptx::mbar_init(w_bar, 1);
+    ptx::mbar_init(&pub_bar[0], 32 * Q_EPI_WARPS);
+    ptx::mbar_init(&pub_bar[1], 32 * Q_EPI_WARPS);
+    ptx::mbar_init(&sig_bar[0], 1);
+    ptx::mbar_init(&sig_bar[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc_pair(tmem_slot, Q_TMEM_COLS);
+    ptx::tmem_alloc_pair(tmem_slot, Q_TMEM_COLS * WAVES);
     ptx::tmem_relinquish_pair();
   }
   ptx::tc_fence_before();
@@ -249,7 +271,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     }
     __syncwarp();
     uint32_t uses[Q_STAGES] = {0u, 0u, 0u};   // how often each stage has been filled so far (barrier phase parity)
-    for (int p = 0; p < num_phases; ++p) {
+    for (int pw = 0; pw < num_phases * WAVES; ++pw) {
+      const int p = pw / WAVES, w = pw - p * WAVES;
       bool mm; int kind, t;
       phase_info(p, mm, kind, t);
       if (!mm) continue;
@@ -258,7 +281,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       const CUtensorMap* tw = (MODE == 0) ? &tm_w1 : &tm_w0;
       const int wrow = (MODE == 0) ? slice32 * 96 + 64 : j0;
       const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
-      const int arow = t * B + m0;
+      const int arow = t * B + (w == 0 ? m0w[0] : m0w[WAVES - 1]);
+      unsigned int* counter = w == 0 ? counterw[0] : counterw[WAVES - 1];
       const int kbs = g.kbs;
       const uint32_t a_bytes = kbs * Q_A_TILE, w_bytes = kbs * Q_W_TILE;
       const int nstages = streamed ? 2 : 3;
@@ -288,7 +312,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
           // this phase's operand rows were written by the epilogues of phase p - 1 of the CTAs sharing our rows
           wait_counter(counter, static_cast<unsigned int>(p) * nprod);
           ptx::fence_proxy_async_full();
-          if (lane == 0) GRU_TRACE(p, 0);
+          if (lane == 0 && w == 0) GRU_TRACE(p, 0);
           __syncwarp();
         }
         if (ptx::elect_one()) {
@@ -309,7 +333,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       constexpr uint32_t idesc64 = ptx::make_idesc_bf16(128, 64, false, false);
       ptx::mbar_wait(w_bar, 0);
       uint32_t uses[Q_STAGES] = {0u, 0u, 0u};
-      for (int p = 0; p < num_phases; ++p) {
+      for (int pw = 0; pw < num_phases * WAVES; ++pw) {
+        const int p = pw / WAVES, w = pw - p * WAVES;
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
         if (!mm) continue;
@@ -318,7 +343,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
         const uint32_t idesc = wide ? idesc128 : idesc64;
         const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
         const uint32_t wtile = wide ? 8192 : 4096;
-        const uint32_t d_tmem = tmem_base + ((MODE == 0 && kind == 1) ? 64 : 0);
+        const uint32_t d_tmem = tmem_base + w * TM_WAVE + ((MODE == 0 && kind == 1) ? 64 : 0);
         const int kbs = g.kbs;
         const int nstages = streamed ? 2 : 3;
         const uint32_t pitch = streamed ? Q_STAGE_S : Q_STAGE_R;
@@ -329,7 +354,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
           for (int q = 0; q < Q_STAGES; ++q) if (q == stage) { use = uses[q]; uses[q] = use + 1; }
           ptx::mbar_wait(&full_bar[stage], use & 1u);
           ptx::tc_fence_after();
-          if (kb == 0 && lane == 0) GRU_TRACE(p, 1);
+          if (kb == 0 && lane == 0 && w == 0) GRU_TRACE(p, 1);
           const uint32_t sa0 = ptx::smem_u32(ring + stage * pitch);
           const uint32_t sw0 = sa0 + Q_KBS * Q_A_TILE;
           if (ptx::elect_one()) {
@@ -349,49 +374,95 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
           __syncwarp();
           if (++stage == nstages) stage = 0;
         }
-        if (ptx::elect_one()) ptx::umma_commit_pair(tmem_full_bar, 3);
+        if (ptx::elect_one()) ptx::umma_commit_pair(&tmem_full_bar[w], 3);
         __syncwarp();
         // the accumulators are overwritten only after both CTAs' next counter waits, which their own epilogues
         // reach after draining TMEM: no tmem_empty barrier needed
       }
     }
+  } else if (warp >= 2 + Q_EPI_WARPS) {
+    // ===================== publisher warp (WAVES = 2) =====================
+    // The epilogue threads arrive on pub_bar[w] after storing their share of the operand tile and go straight on to the
+    // other wave; this warp turns the arrivals into the cross-CTA signal (gpu-scope fence + counter), so the fence's
+    // latency is off the epilogue warps' path. Phases without a matmul (the first one or two) publish in line instead:
+    // nothing there keeps the epilogue from running a whole phase ahead of this warp.
+    if (WAVES == 2) {
+      uint32_t par[2] = {0u, 0u};
+      for (int pw = 0; pw < num_phases * WAVES; ++pw) {
+        const int p = pw / WAVES, w = pw - p * WAVES;
+        bool mm; int kind, t;
+        phase_info(p, mm, kind, t);
+        if (!mm) continue;
+        ptx::mbar_wait(&pub_bar[w], par[w]);
+        par[w] ^= 1u;
+        if (lane == 0) {
+          if (w == 0) GRU_TRACE(p, 6);
+          // release only (no L1 invalidation): the consumers acquire on their side. The saved state (r, u, c, h) is
+          // stored AFTER this signal -- the epilogue threads wait for sig_bar -- so the membar has only the 8 - 16 KB
+          // operand tile to wait for, not 32 - 64 KB of scattered fp32 stores nobody on the critical path needs
+          asm volatile("fence.release.gpu;" ::: "memory");
+          ptx::fence_proxy_async_full();
+          if (w == 0) GRU_TRACE(p, 7);
+          red_relaxed_add(w == 0 ? counterw[0] : counterw[WAVES - 1], 1u);
+          if (w == 0) GRU_TRACE(p, 3);
+          ptx::mbar_arrive(&sig_bar[w]);
+        }
+        __syncwarp();
+      }
+    }
   } else {
-    // ===================== epilogue warps: thread = (batch row, 8 units) =====================
+    // ===================== epilogue warps: thread = (batch row, 8 units), for each wave =====================
     const int q = warp & 3;                          // TMEM lane quarter this warp may read
     const int sub = (warp - 2) >> 2;                 // which 8 of the 32 units of the half
     const int uhalf = q >> 1;                        // lanes 0..63: first 32 units of the pair, 64..127: the others
-    const int row = m0 + (q & 1) * 32 + lane;
-    const bool row_ok = row < g.row_end;
     const int unit = (slice32 & ~1) * Q_UNITS + uhalf * 32 + sub * NU;   // first of this thread's 8 units
-    const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + sub * NU;
-    const int my_len = row_ok ? g.q_len[row] : 0;
     const bool leader = threadIdx.x == 64;
-    uint32_t tfull_phase = 0;
-    // TMA-store staging: the A areas of ring stages 0 and 1 (idle between the last MMA of a phase and the next
-    // phase's first load, which waits for this CTA's own arrival below)
-    const uint32_t stg0 = ptx::smem_u32(ring), stg1 = ptx::smem_u32(ring + Q_A_TILE);   // both inside stage 0's activation area
     const int srow = (q & 1) * 32 + lane;         // row inside the CTA's 64-row tile
     const int schunk = uhalf * 4 + sub;           // 16-byte chunk inside the 128-byte row of 64 units
     const int ucol = (slice32 >> 1) * 64;         // first unit of the pair
-    const bool tma_out = g.tma_out != 0;
+    // operand tiles leave by TMA store only when one wave owns the ring between its phases
+    const bool tma_out = WAVES == 1 && g.tma_out != 0;
+    const bool priv_layout = g.priv_layout != 0;
+    // TMA-store staging: the A areas of ring stages 0 and 1 (idle between the last MMA of a phase and the next
+    // phase's first load, which waits for this CTA's own arrival below)
+    const uint32_t stg0 = ptx::smem_u32(ring), stg1 = ptx::smem_u32(ring + Q_A_TILE);   // both inside stage 0's activation area
+    int roww[WAVES], lenw[WAVES];
+    bool okw[WAVES];
+    uint32_t tlanew[WAVES], tfullw[WAVES], sigparw[WAVES];
+#pragma unroll
+    for (int w = 0; w < WAVES; ++w) {
+      roww[w] = m0w[w] + (q & 1) * 32 + lane;
+      okw[w] = roww[w] < g.row_end;
+      lenw[w] = okw[w] ? g.q_len[roww[w]] : 0;
+      tlanew[w] = tmem_base + w * TM_WAVE + (static_cast<uint32_t>(q * 32) << 16) + sub * NU;
+      tfullw[w] = 0;
+      sigparw[w] = 0;
+    }
     // fp32 state kept for BPTT (r, u, c, h_t): with full 64-row tiles it lives in a layout private to these two
     // kernels, [t][64-row tile][unit / 8][row % 64][unit % 8], in which the 32 bytes of the lanes of a warp are
     // consecutive (1 KB per warp access instead of 32 sectors 4 KB apart). The final state h_T stays row-major:
     // it is the model's `condition` output.
     const int nt64 = (B + Q_ROWS - 1) / Q_ROWS;
-    auto priv = [&](int tblock) -> long long {
-      if (tma_out)
+    auto priv = [&](int tblock, int m0, int row) -> long long {
+      if (priv_layout)
         return ((static_cast<long long>(tblock) * nt64 + (m0 >> 6)) * (L >> 3) + (unit >> 3)) * (Q_ROWS * NU) + srow * NU;
       return (static_cast<long long>(tblock) * B + row) * L + unit;
     };
     // publish: CTA barrier, then ONE thread hands the staged tile(s) to the TMA, waits for the writes to be
     // performed, fences and releases the counter
-    auto publish = [&](int p, const CUtensorMap* tm, int ntiles, int col1, long long grow) {
+    auto publish = [&](int p, int w, bool mm, const CUtensorMap* tm, int ntiles, int col1, long long grow, int m0, unsigned int* counter) {
+      if (WAVES == 2 && mm) {   // the publisher warp signals
+        if (leader && w == 0) GRU_TRACE(p, 5);
+        ptx::mbar_arrive(&pub_bar[w]);
+        ptx::mbar_wait(&sig_bar[w], sigparw[w]);
+        sigparw[w] ^= 1u;
+        return;
+      }
       if (tma_out) ptx::fence_proxy_async();
-      if (leader) GRU_TRACE(p, 5);
+      if (leader && w == 0) GRU_TRACE(p, 5);
       epi_bar_all();
       if (leader) {
-        GRU_TRACE(p, 6);
+        if (w == 0) GRU_TRACE(p, 6);
         if (tma_out) {
           // The tile(s) leave through the async proxy and bulk_wait<0> returns once the writes are PERFORMED (at
           // L2, where the consumers' TMA loads read them), so the relaxed arrival below is ordered after them by
@@ -403,193 +474,213 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
             ptx::bulk_commit();
             ptx::bulk_wait<0>();
           }
-          GRU_TRACE(p, 4);
+          if (w == 0) GRU_TRACE(p, 4);
         } else {
-          GRU_TRACE(p, 4);
+          if (w == 0) GRU_TRACE(p, 4);
           asm volatile("fence.acq_rel.gpu;" ::: "memory");
           ptx::fence_proxy_async_full();
         }
-        GRU_TRACE(p, 7);
+        if (w == 0) GRU_TRACE(p, 7);
         red_relaxed_add(counter, 1u);
-        GRU_TRACE(p, 3);
+        if (w == 0) GRU_TRACE(p, 3);
       }
     };
 
     if (MODE == 0) {
-      float h[NU], u[NU];
+      float hw[WAVES][NU], uw[WAVES][NU];
 #pragma unroll
-      for (int j = 0; j < NU; ++j) h[j] = 0.f, u[j] = 0.f;
+      for (int w = 0; w < WAVES; ++w)
+#pragma unroll
+        for (int j = 0; j < NU; ++j) hw[w][j] = 0.f, uw[w][j] = 0.f;
       for (int p = 0; p < num_phases; ++p) {
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
         const long long tb = static_cast<long long>(t) * B;
-        float sv[NU];   // r (kind 0) or c (kind 1)
-        if (kind == 0) {
-          float xr[NU], xu[NU], ar[NU], au[NU];
 #pragma unroll
-          for (int j = 0; j < NU; ++j) xr[j] = xu[j] = ar[j] = au[j] = 0.f;
-          if (row_ok) {
-            const float* x = g.xg + (tb + row) * 2 * L + unit;
-            load8f(x, xr);
-            load8f(x + L, xu);
-          }
-          if (mm) {
-            ptx::mbar_wait(tmem_full_bar, tfull_phase);
-            tfull_phase ^= 1;
-            ptx::tc_fence_after();
-            if (leader) GRU_TRACE(p, 2);
-            tmem_ld8(t_lane, ar);
-            tmem_ld8(t_lane + 32, au);
-            ptx::tc_fence_before();
-          }
-          float rh[NU];
-#pragma unroll
-          for (int j = 0; j < NU; ++j) {
-            sv[j] = sigm(ar[j] + xr[j]);
-            u[j] = sigm(au[j] + xu[j]);
-            rh[j] = sv[j] * h[j];
-          }
-          // the operand the other CTAs wait for goes out first; r / u (kept for BPTT) after the arrival
-          if (tma_out) stage8bf(stg0, srow, schunk, rh);
-          else if (row_ok) store8bf(g.rh_bf + (tb + row) * L + unit, rh);
-        } else {
-          float xc[NU], ac[NU];
-#pragma unroll
-          for (int j = 0; j < NU; ++j) xc[j] = ac[j] = 0.f;
-          if (row_ok) load8f(g.xc + (tb + row) * L + unit, xc);
-          if (mm) {
-            ptx::mbar_wait(tmem_full_bar, tfull_phase);
-            tfull_phase ^= 1;
-            ptx::tc_fence_after();
-            if (leader) GRU_TRACE(p, 2);
-            tmem_ld8(t_lane + 64, ac);
-            ptx::tc_fence_before();
-          }
-          const bool valid = t < my_len;
-#pragma unroll
-          for (int j = 0; j < NU; ++j) {
-            sv[j] = tanh_fast(ac[j] + xc[j]);
-            h[j] = valid ? u[j] * h[j] + (1.0f - u[j]) * sv[j] : h[j];
-          }
-          if (tma_out) stage8bf(stg0, srow, schunk, h);
-          else if (row_ok) store8bf(g.h_bf + (tb + B + row) * L + unit, h);
-        }
-        // r.h is the operand of the candidate phase (tm_a1), h_{t+1} the operand of the next gate phase (tm_a0)
-        publish(p, kind == 0 ? &tm_o0 : &tm_o1, 1, 0, kind == 0 ? tb + m0 : tb + B + m0);
-        // what only BPTT reads goes out off the critical path
-        if (row_ok) {
-          const long long o = priv(t);
+        for (int w = 0; w < WAVES; ++w) {
+          const int row = roww[w], m0 = m0w[w];
+          const bool row_ok = okw[w];
+          float (&h)[NU] = hw[w];
+          float (&u)[NU] = uw[w];
+          float sv[NU];   // r (kind 0) or c (kind 1)
           if (kind == 0) {
-            store8f(g.r + o, sv);
-            store8f(g.u + o, u);
+            float xr[NU], xu[NU], ar[NU], au[NU];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) xr[j] = xu[j] = ar[j] = au[j] = 0.f;
+            if (row_ok) {
+              const float* x = g.xg + (tb + row) * 2 * L + unit;
+              load8f(x, xr);
+              load8f(x + L, xu);
+            }
+            if (mm) {
+              ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
+              tfullw[w] ^= 1;
+              ptx::tc_fence_after();
+              if (leader && w == 0) GRU_TRACE(p, 2);
+              tmem_ld8(tlanew[w], ar);
+              tmem_ld8(tlanew[w] + 32, au);
+              ptx::tc_fence_before();
+            }
+            float rh[NU];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+              sv[j] = sigm(ar[j] + xr[j]);
+              u[j] = sigm(au[j] + xu[j]);
+              rh[j] = sv[j] * h[j];
+            }
+            // the operand the other CTAs wait for goes out first; r / u (kept for BPTT) after the arrival
+            if (tma_out) stage8bf(stg0, srow, schunk, rh);
+            else if (row_ok) store8bf(g.rh_bf + (tb + row) * L + unit, rh);
           } else {
-            store8f(g.c + o, sv);
-            if (t + 1 == T) store8f(g.h_f32 + (tb + B + row) * L + unit, h);
-            else store8f(g.h_f32 + priv(t + 1), h);
+            float xc[NU], ac[NU];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) xc[j] = ac[j] = 0.f;
+            if (row_ok) load8f(g.xc + (tb + row) * L + unit, xc);
+            if (mm) {
+              ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
+              tfullw[w] ^= 1;
+              ptx::tc_fence_after();
+              if (leader && w == 0) GRU_TRACE(p, 2);
+              tmem_ld8(tlanew[w] + 64, ac);
+              ptx::tc_fence_before();
+            }
+            const bool valid = t < lenw[w];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+              sv[j] = tanh_fast(ac[j] + xc[j]);
+              h[j] = valid ? u[j] * h[j] + (1.0f - u[j]) * sv[j] : h[j];
+            }
+            if (tma_out) stage8bf(stg0, srow, schunk, h);
+            else if (row_ok) store8bf(g.h_bf + (tb + B + row) * L + unit, h);
+          }
+          // r.h is the operand of the candidate phase (tm_a1), h_{t+1} the operand of the next gate phase (tm_a0)
+          publish(p, w, mm, kind == 0 ? &tm_o0 : &tm_o1, 1, 0, kind == 0 ? tb + m0 : tb + B + m0, m0, counterw[w]);
+          // what only BPTT reads goes out off the critical path
+          if (row_ok) {
+            const long long o = priv(t, m0, row);
+            if (kind == 0) {
+              store8f(g.r + o, sv);
+              store8f(g.u + o, u);
+            } else {
+              store8f(g.c + o, sv);
+              if (t + 1 == T) store8f(g.h_f32 + (tb + B + row) * L + unit, h);
+              else store8f(g.h_f32 + priv(t + 1, m0, row), h);
+            }
           }
         }
       }
     } else {
-      float dhp[NU], du[NU];
-      float db_r[NU], db_u[NU], db_c[NU];
+      float dhpw[WAVES][NU], duw[WAVES][NU];
+      float db_r[NU], db_u[NU], db_c[NU];   // bias gradients: both waves' rows add into the same partial row
 #pragma unroll
-      for (int j = 0; j < NU; ++j) dhp[j] = du[j] = db_r[j] = db_u[j] = db_c[j] = 0.f;
+      for (int j = 0; j < NU; ++j) db_r[j] = db_u[j] = db_c[j] = 0.f;
+#pragma unroll
+      for (int w = 0; w < WAVES; ++w)
+#pragma unroll
+        for (int j = 0; j < NU; ++j) dhpw[w][j] = duw[w][j] = 0.f;
       for (int p = 0; p < num_phases; ++p) {
         bool mm; int kind, t;
         phase_info(p, mm, kind, t);
-        if (kind == 0) {
-          // dRH = acc ;  dG_r = dRH h r (1-r) ; dG_u = du u (1-u) ; dh_part += dRH r
-          const long long tb = static_cast<long long>(t) * B;
-          float hh[NU], rv[NU], uv[NU], acc[NU];
 #pragma unroll
-          for (int j = 0; j < NU; ++j) hh[j] = rv[j] = uv[j] = acc[j] = 0.f;
-          if (row_ok) {
-            const long long o = priv(t);
-            if (t > 0) load8f(g.h_f32 + o, hh);   // h_0 = 0 (block 0 is never written in the private layout)
-            load8f(g.r + o, rv);
-            load8f(g.u + o, uv);
-          }
-          ptx::mbar_wait(tmem_full_bar, tfull_phase);
-          tfull_phase ^= 1;
-          ptx::tc_fence_after();
-          if (leader) GRU_TRACE(p, 2);
-          tmem_ld8(t_lane, acc);
-          ptx::tc_fence_before();
-          float dgr[NU], dgu[NU];
+        for (int w = 0; w < WAVES; ++w) {
+          const int row = roww[w], m0 = m0w[w];
+          const bool row_ok = okw[w];
+          float (&dhp)[NU] = dhpw[w];
+          float (&du)[NU] = duw[w];
+          if (kind == 0) {
+            // dRH = acc ;  dG_r = dRH h r (1-r) ; dG_u = du u (1-u) ; dh_part += dRH r
+            const long long tb = static_cast<long long>(t) * B;
+            float hh[NU], rv[NU], uv[NU], acc[NU];
 #pragma unroll
-          for (int j = 0; j < NU; ++j) {
-            const float drh = acc[j];   // zero for steps beyond the question length (dC is zero there)
-            dgr[j] = drh * hh[j] * rv[j] * (1.0f - rv[j]);
-            dgu[j] = du[j] * uv[j] * (1.0f - uv[j]);
-            dhp[j] = fmaf(drh, rv[j], dhp[j]);
-          }
-          if (row_ok) {
+            for (int j = 0; j < NU; ++j) hh[j] = rv[j] = uv[j] = acc[j] = 0.f;
+            if (row_ok) {
+              const long long o = priv(t, m0, row);
+              if (t > 0) load8f(g.h_f32 + o, hh);   // h_0 = 0 (block 0 is never written in the private layout)
+              load8f(g.r + o, rv);
+              load8f(g.u + o, uv);
+            }
+            ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
+            tfullw[w] ^= 1;
+            ptx::tc_fence_after();
+            if (leader && w == 0) GRU_TRACE(p, 2);
+            tmem_ld8(tlanew[w], acc);
+            ptx::tc_fence_before();
+            float dgr[NU], dgu[NU];
 #pragma unroll
             for (int j = 0; j < NU; ++j) {
-              db_r[j] += dgr[j];
-              db_u[j] += dgu[j];
+              const float drh = acc[j];   // zero for steps beyond the question length (dC is zero there)
+              dgr[j] = drh * hh[j] * rv[j] * (1.0f - rv[j]);
+              dgu[j] = du[j] * uv[j] * (1.0f - uv[j]);
+              dhp[j] = fmaf(drh, rv[j], dhp[j]);
             }
-            if (!tma_out) {
-              const long long o = (tb + row) * 2 * L + unit;
-              store8bf(g.dG_bf + o, dgr);
-              store8bf(g.dG_bf + o + L, dgu);
-            }
-          }
-          if (tma_out) {
-            stage8bf(stg0, srow, schunk, dgr);
-            stage8bf(stg1, srow, schunk, dgu);
-          }
-          publish(p, &tm_o0, 2, L + ucol, tb + m0);   // dG_t = [dG_r | dG_u]: operand of the next phase
-        } else {
-          // dh = acc + dh_part (or dq) ; element-wise head of step tp = t - 1
-          const int tp = t - 1;
-          const long long tb = static_cast<long long>(tp) * B;
-          float hh[NU], uv[NU], cv[NU], acc[NU];
+            if (row_ok) {
 #pragma unroll
-          for (int j = 0; j < NU; ++j) hh[j] = uv[j] = cv[j] = acc[j] = 0.f;
-          if (row_ok) {
-            const long long o = priv(tp);
-            if (tp > 0) load8f(g.h_f32 + o, hh);
-            load8f(g.u + o, uv);
-            load8f(g.c + o, cv);
-            if (!mm) {
-              load8f(g.dq + static_cast<long long>(row) * L + unit, dhp);
-              if (g.dq2) {
-                float d2[NU];
-                load8f(g.dq2 + static_cast<long long>(row) * L + unit, d2);
-#pragma unroll
-                for (int j = 0; j < NU; ++j) dhp[j] += d2[j];
+              for (int j = 0; j < NU; ++j) {
+                db_r[j] += dgr[j];
+                db_u[j] += dgu[j];
+              }
+              if (!tma_out) {
+                const long long o = (tb + row) * 2 * L + unit;
+                store8bf(g.dG_bf + o, dgr);
+                store8bf(g.dG_bf + o + L, dgu);
               }
             }
-          }
-          if (mm) {
-            ptx::mbar_wait(tmem_full_bar, tfull_phase);
-            tfull_phase ^= 1;
-            ptx::tc_fence_after();
-            if (leader) GRU_TRACE(p, 2);
-            tmem_ld8(t_lane, acc);
-            ptx::tc_fence_before();
-          }
-          const bool pvalid = tp < my_len;
-          float dcv[NU];
+            if (tma_out) {
+              stage8bf(stg0, srow, schunk, dgr);
+              stage8bf(stg1, srow, schunk, dgu);
+            }
+            publish(p, w, mm, &tm_o0, 2, L + ucol, tb + m0, m0, counterw[w]);   // dG_t = [dG_r | dG_u]: operand of the next phase
+          } else {
+            // dh = acc + dh_part (or dq) ; element-wise head of step tp = t - 1
+            const int tp = t - 1;
+            const long long tb = static_cast<long long>(tp) * B;
+            float hh[NU], uv[NU], cv[NU], acc[NU];
 #pragma unroll
-          for (int j = 0; j < NU; ++j) {
-            const float dh = acc[j] + dhp[j];
-            dcv[j] = pvalid ? dh * (1.0f - uv[j]) * (1.0f - cv[j] * cv[j]) : 0.f;
-            du[j] = pvalid ? dh * (hh[j] - cv[j]) : 0.f;
-            dhp[j] = pvalid ? dh * uv[j] : dh;
-          }
-          if (row_ok) {
+            for (int j = 0; j < NU; ++j) hh[j] = uv[j] = cv[j] = acc[j] = 0.f;
+            if (row_ok) {
+              const long long o = priv(tp, m0, row);
+              if (tp > 0) load8f(g.h_f32 + o, hh);
+              load8f(g.u + o, uv);
+              load8f(g.c + o, cv);
+              if (!mm) {
+                load8f(g.dq + static_cast<long long>(row) * L + unit, dhp);
+                if (g.dq2) {
+                  float d2[NU];
+                  load8f(g.dq2 + static_cast<long long>(row) * L + unit, d2);
 #pragma unroll
-            for (int j = 0; j < NU; ++j) db_c[j] += dcv[j];
-            if (!tma_out) store8bf(g.dC_bf + (tb + row) * L + unit, dcv);
+                  for (int j = 0; j < NU; ++j) dhp[j] += d2[j];
+                }
+              }
+            }
+            if (mm) {
+              ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
+              tfullw[w] ^= 1;
+              ptx::tc_fence_after();
+              if (leader && w == 0) GRU_TRACE(p, 2);
+              tmem_ld8(tlanew[w], acc);
+              ptx::tc_fence_before();
+            }
+            const bool pvalid = tp < lenw[w];
+            float dcv[NU];
+#pragma unroll
+            for (int j = 0; j < NU; ++j) {
+              const float dh = acc[j] + dhp[j];
+              dcv[j] = pvalid ? dh * (1.0f - uv[j]) * (1.0f - cv[j] * cv[j]) : 0.f;
+              du[j] = pvalid ? dh * (hh[j] - cv[j]) : 0.f;
+              dhp[j] = pvalid ? dh * uv[j] : dh;
+            }
+            if (row_ok) {
+#pragma unroll
+              for (int j = 0; j < NU; ++j) db_c[j] += dcv[j];
+              if (!tma_out) store8bf(g.dC_bf + (tb + row) * L + unit, dcv);
+            }
+            if (tma_out) stage8bf(stg0, srow, schunk, dcv);
+            publish(p, w, mm, &tm_o1, 1, 0, tb + m0, m0, counterw[w]);          // dC_{t-1}: operand of the next phase
           }
-          if (tma_out) stage8bf(stg0, srow, schunk, dcv);
-          publish(p, &tm_o1, 1, 0, tb + m0);          // dC_{t-1}: operand of the next phase
         }
       }
       // bias gradients: sum over the 32 rows of the warp (fixed butterfly order), then over the two row-warps
-      // that share these units; one partial row of [3L] per CTA
+      // that share these units; one partial row of [3L] per CTA (the second wave's row is written as zeros)
 #pragma unroll
       for (int j = 0; j < NU; ++j) {
 #pragma unroll
@@ -613,8 +704,14 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       if ((q & 1) == 0 && lane < 3 * NU) {
         const int k = lane / NU, j = lane % NU;
         const float s = red[((warp - 2) * 3 + k) * NU + j] + red[((warp - 2 + 1) * 3 + k) * NU + j];
-        float* out = g.bias_part + static_cast<long long>(2 * (g.row0 / 128 + mi) + rank) * 3 * L;
-        out[k * L + unit + j] = s;
+#pragma unroll
+        for (int w = 0; w < WAVES; ++w) {
+          const int tile = (g.row0 + w * g.wave_rows) / 128 + mi;
+          if (tile * 128 < ((g.B + 127) / 128) * 128) {
+            float* out = g.bias_part + static_cast<long long>(2 * tile + rank) * 3 * L;
+            out[k * L + unit + j] = w == 0 ? s : 0.f;
+          }
+        }
       }
     }
   }
@@ -624,15 +721,15 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
   ptx::cluster_sync_all();
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc_pair(tmem_base, Q_TMEM_COLS);
+    ptx::tmem_dealloc_pair(tmem_base, Q_TMEM_COLS * WAVES);
   }
 }
 
-template <int MODE>
+template <int MODE, int WAVES>
 cudaError_t launch_pair_gru(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
                             const CUtensorMap& o0, const CUtensorMap& o1, PairGruArgs& a, dim3 grid, int smem,
                             cudaStream_t s) {
-  auto kern = gru_pair_kernel<MODE>;
+  auto kern = gru_pair_kernel<MODE, WAVES>;
   static int smem_set = 0;
   if (smem_set < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -678,22 +775,45 @@ bool gru_pair_supported(int B, int L, int num_sms) {
   return L / Q_UNITS <= num_sms;
 }
 
-// one cooperative launch per wave of co-resident row tiles (num_sms / (L / 32) tiles of 128 rows: 4 at L = 1024)
+// Launch plan. tiles_max = num_sms / (L / 32) co-resident row tiles of 128 rows (4 at L = 1024).
+//   waves2 (default for batches beyond one wave: the 5120 blank sequences of the pre-training graph, BASELINE config 5's
+//   large inference batches): every launch serves 2 x tiles_max row tiles, each CTA pair alternating between two row
+//   groups (gru_pair_kernel<MODE, 2>); a remainder of at most tiles_max tiles runs as one wave.
+//   VQA_GRU_WAVES = 1 forces single waves, = 2 also splits a batch of ONE wave into two half-waves on half of the SMs
+//   (the recurrent kernels then leave the other half of the machine to concurrent kernels).
+int g_waves_mode = getenv("VQA_GRU_WAVES") ? atoi(getenv("VQA_GRU_WAVES")) : 0;
+// testing aid (not part of the ABI header): the VQA_GRU_WAVES policy at run time
+extern "C" __attribute__((visibility("default"))) void vqa_internal_set_gru_waves(int mode) { g_waves_mode = mode; }
+
 template <int MODE>
 cudaError_t launch_chunks(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
                           const CUtensorMap& o0, const CUtensorMap& o1, PairGruArgs& g, int num_sms, cudaStream_t s) {
   const int slices = g.L / Q_UNITS;
-  int per = num_sms / slices;
-  if (per > 32) per = 32;   // counters: [2 * tiles] of a 64-entry array
-  for (int row0 = 0; row0 < g.B; row0 += per * 128) {
-    const int rows = g.B - row0 < per * 128 ? g.B - row0 : per * 128;
-    const int tiles = (rows + 127) / 128;
-    cudaError_t e = cudaMemsetAsync(g.counter, 0, sizeof(unsigned int) * 2 * tiles, s);
+  int tiles_max = num_sms / slices;
+  if (tiles_max > 16) tiles_max = 16;   // counters: [2 waves][tiles][2 ranks] of a 64-entry array
+  g.priv_layout = g.tma_out;
+  bool first = true;
+  for (int row0 = 0; row0 < g.B;) {
+    const int left = g.B - row0;
+    const int tiles_left = (left + 127) / 128;
+    int waves = 1, tiles = tiles_left < tiles_max ? tiles_left : tiles_max;
+    if (g_waves_mode != 1 && tiles_left > tiles_max) {
+      waves = 2;
+      tiles = (tiles_left + 1) / 2 < tiles_max ? (tiles_left + 1) / 2 : tiles_max;
+    } else if (g_waves_mode == 2 && tiles_left >= 2) {
+      waves = 2;
+      tiles = (tiles_left + 1) / 2;
+    }
+    cudaError_t e = cudaMemsetAsync(g.counter, 0, sizeof(unsigned int) * 2 * waves * tiles, s);
     if (e != cudaSuccess) return e;
     g.row0 = row0;
-    e = launch_pair_gru<MODE>(a0, a1, w0, w1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L), s);
+    g.wave_rows = tiles * 128;
+    e = waves == 2 ? launch_pair_gru<MODE, 2>(a0, a1, w0, w1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L), s)
+                   : launch_pair_gru<MODE, 1>(a0, a1, w0, w1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L), s);
     if (e != cudaSuccess) return e;
-    if (row0 > 0) count_launch();   // (the caller counts the first)
+    if (!first) count_launch();   // (the caller counts the first)
+    first = false;
+    row0 += waves * tiles * 128;
   }
   return cudaSuccess;
 }

@@ -544,7 +544,8 @@ __global__ void __launch_bounds__(256) softmax_ce_kernel(const VqaSoftmaxCe a) {
     st[3] = valid ? 1.f : 0.f;
   }
   if (a.d_logit || a.d_hi) {
-    const float scale = (valid && cnt > 0.f) ? a.loss_scale / cnt : 0.f;
+    const float norm = a.count[head] > 0.f ? a.count[head] : cnt;
+    const float scale = (valid && norm > 0.f) ? a.loss_scale / norm : 0.f;
     const float inv = 1.0f / z;
     bf16* hi = static_cast<bf16*>(a.d_hi);
     bf16* lo = static_cast<bf16*>(a.d_lo);

@@ -208,7 +208,7 @@ class VqaSpatAttn(C.Structure):
 
 class VqaSoftmaxCe(C.Structure):
     _fields_ = [("heads", C.c_int32), ("B", C.c_int32), ("n", C.c_int32), ("A", C.c_int32), ("top_k", C.c_int32),
-                ("logit", C.c_void_p), ("fills", C.c_void_p), ("num", C.c_void_p * 8), ("loss_scale", C.c_float),
+                ("logit", C.c_void_p), ("fills", C.c_void_p), ("num", C.c_void_p * 8), ("loss_scale", C.c_float), ("count", C.c_float * 8),
                 ("stats", C.c_void_p), ("report", C.c_void_p), ("d_logit", C.c_void_p), ("d_hi", C.c_void_p),
                 ("d_lo", C.c_void_p)]
 

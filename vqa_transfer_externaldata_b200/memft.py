@@ -89,7 +89,15 @@ class Model:
         L.check(self.lib.vqa_ops_create(C.byref(h)))
         self.ops = h
         self.fp32 = c.precision == "fp32"
-        self.seed = int(seed)
+        # batch-sharded data parallelism (BASELINE config 4: 8 x B200): one process per GPU, every row of the graph is per
+        # image, so the ranks only meet in one all-reduce of the flat gradient buffer (NCCL) and in the two valid-entry
+        # counts that normalise the loss. Per-rank dropout streams as in the answer model: seed + 7919 * rank.
+        import torch.distributed as dist
+        self._dist = dist if (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1) else None
+        self.rank = self._dist.get_rank() if self._dist else 0
+        self.world = self._dist.get_world_size() if self._dist else 1
+        self.seed = int(seed) + 7919 * self.rank
+        self.global_counts = None
         self.global_step = 0
         self.losses, self.report, self.mid_result = {}, {}, {}
         self.loss = None
@@ -245,6 +253,11 @@ class Model:
             d.num[i].copy_(t(batch[pre + "num"], np.int32), non_blocking=True)
             fills.append(f_)
         d.fills4.copy_(torch.from_numpy(np.concatenate(fills + fills)), non_blocking=True)
+        if self._dist:
+            cnt = torch.tensor([float(np.minimum(np.maximum(np.asarray(batch[f"{k}_blank_fill/num"]), 0), n).sum()) for k in KINDS],
+                               dtype=torch.float32, device=self.dev)
+            self._dist.all_reduce(cnt)
+            self.global_counts = cnt.cpu().tolist()
         torch.cuda.current_stream(self.dev).synchronize()   # the staging arrays above are temporaries
         self.batch = batch
 
@@ -362,6 +375,8 @@ class Model:
                             loss_scale=1.0, stats=b.stats.data_ptr(), report=b.rep.data_ptr())
         for h in range(4):
             ce.num[h] = d.num[h % 2].data_ptr()
+            if self.global_counts is not None:
+                ce.count[h] = self.global_counts[h % 2]
         if train:
             ce.d_logit = b.dlogit.data_ptr()
             ce.d_hi, ce.d_lo = b.dlogit_p.ptr()
@@ -440,6 +455,8 @@ class Model:
         """run_single_step of vlmap_memft/trainer.py: forward + backward + clip + Adam; returns the loss."""
         self.forward(batch, with_grad_seed=True)
         self.backward()
+        if self._dist:
+            self._dist.all_reduce(self.flat_grad)
         if apply_optimizer:
             self.adam_step(lr=lr, clip_norm=clip_norm)
         self.global_step += 1
