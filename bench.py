@@ -403,6 +403,125 @@ def run_infer(args):
     return 0
 
 
+def memft_cpu_rate(n_images=32, steps=2, budget_s=25.0):
+    """CPU baseline of BASELINE config 4: the oracle's torch-autograd twin of the pre-training graph
+    (oracle/memft_torch.py, fp32, all host threads) forward + backward on a bounded sample (n_images images of the cfg4
+    shapes). The reference's TF-1.6 graph cannot run in this image."""
+    import torch
+    from oracle import memft_np as M
+    from oracle import memft_torch as MT
+    from vqa_transfer_externaldata_b200 import memft as F
+    dims = dict(F.CFG4, B=n_images)
+    cfg = F.make_config(dims)
+    p = {k: torch.tensor(v, dtype=torch.float32, requires_grad=True) for k, v in F.xavier_params(cfg).items()}
+    hb = F.synthetic_batch(dims, seed=7)
+    tb = {k: torch.tensor(v, dtype=torch.float32 if np.asarray(v).dtype.kind == "f" else torch.int64) for k, v in hb.items()}
+    tm = {k: torch.tensor(v, dtype=torch.float32) for k, v in M.make_masks(dims, seed=3).items()}
+    times = []
+    t_start = time.perf_counter()
+    for i in range(steps + 1):
+        t0 = time.perf_counter()
+        loss, _ = MT.forward(p, tb, tm)
+        loss.backward()
+        for v in p.values():
+            v.grad = None
+        if i:
+            times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_start > budget_s and times:
+            break
+    return n_images / float(np.median(times)), torch.get_num_threads(), float(np.sum(times))
+
+
+def run_memft(args):
+    """`--mode memft`: BASELINE config 4 -- one train step of the vlmap pre-training graph (bs 512 per GPU, 5 + 5 entries
+    per image, K 36, A 4000, blanks <= 10 tokens), batch-sharded data parallel over N GPUs (NCCL all-reduce of the flat
+    gradient)."""
+    import torch
+    from vqa_transfer_externaldata_b200 import lib as L
+    from vqa_transfer_externaldata_b200 import memft as F
+    from vqa_transfer_externaldata_b200.dp import DataParallel
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this repo has no CPU path")
+    dp = DataParallel()
+    rank, world = dp.rank, dp.world_size
+    torch.cuda.set_device(dp.local_rank)
+    dev = torch.device(f"cuda:{dp.local_rank}")
+    peaks = load_peaks()
+    cfg = F.make_config(F.CFG4, precision=args.precision)
+    R = 2
+    host = [F.synthetic_batch(F.CFG4, seed=100 + 17 * r + 1000 * rank) for r in range(R)]
+    model = F.Model(host[0], cfg, is_train=True, params=F.xavier_params(cfg), seed=777)
+    lib = L.load()
+    # `value`: the batch resident in HBM; `e2e`: features resident (as the answer model's bank is), everything else --
+    # boxes, blanks, lengths, fills, counts, wordset ids -- uploaded from host memory every step, loss read back
+    feats = [{k: torch.from_numpy(hb[k]).to(dev) for k in ("image_ft", "spatial_ft")} for hb in host]
+    e2e_batches = [dict(hb, **f) for hb, f in zip(host, feats)]
+    h2d = sum(int(np.asarray(v).nbytes) for k, v in host[0].items() if k not in ("image_ft", "spatial_ft"))
+    W = max(3, args.warmup)
+
+    def timed(fn, steps):
+        dp.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = lib.vqa_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        dp.barrier()
+        return dp.max_over_ranks(e0.elapsed_time(e1)), lib.vqa_launch_count() - n0
+
+    def step_resident(i):
+        model.train_step(sync=False)
+
+    def step_e2e(i):
+        model.set_batch(e2e_batches[i % R])
+        model.train_step(sync=True)
+
+    timed(step_resident, W)
+    sampler = ClockSampler(dp.local_rank)
+    if rank == 0:
+        sampler.start()
+    ms, launches = timed(step_resident, args.steps)
+    timed(step_e2e, 2)
+    ms_e2e, _ = timed(step_e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    loss, report = model.fetch()
+    ms /= args.steps
+    ms_e2e /= args.steps
+    flops = F.gemm_flops_per_step(cfg)
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        v, cores, secs = memft_cpu_rate()
+        cpu = {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+               "sample": f"fwd+bwd of the oracle's torch twin of the pre-training graph at cfg4 layer sizes, 32 images per step, {secs:.1f} s of timed CPU work"}
+    if rank == 0:
+        B = F.CFG4["B"]
+        t_roof = flops / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3
+        line = {"metric": "vlmap_memft pretrain images/sec fwd+bwd bs512 (5 obj + 5 attr entries, K36, A4000, blanks<=10) (BASELINE config 4)",
+                "value": B * world / ms * 1e3, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": W,
+                "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": "cfg4 vlmap_memft bf_or_wordset_withatt_sp train step fwd+bwd+clip+adam, B512 x (5+5) entries, "
+                                       "K36 x Dv2048, 5120 blank sequences T10, A4000", "per_gpu_batch": B, "global_batch": B * world,
+                           "precision": args.precision, "parallelism": f"dp{world}",
+                           "gradient_collective": "NCCL all-reduce of the flat gradient buffer" if world > 1 else "none (1 GPU)",
+                           "l2_policy": "inputs larger than L2: 151 MB of image features + 164 MB of logits per step"},
+                "e2e": {"value": B * world / ms_e2e * 1e3, "unit": "images/s", "ms_per_step": ms_e2e,
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 52,
+                        "note": "image / box features resident in HBM; ids, boxes, blanks, counts uploaded and validated on the host every step"},
+                "gpu_launches": int(launches), "clocks": clocks, "loss": loss, "loss_finite": bool(np.isfinite(loss)),
+                "roofline": {"bound": "tensor", "kernel": "whole step (dense contractions of the graph)", "achieved": flops / 1e9 / ms,
+                             "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": t_roof / ms, "traffic": None,
+                             "model": f"{flops / 1e12:.2f} TFLOP per step / bf16 sustained"},
+                "cpu_baseline": cpu}
+        _emit(line)
+    model.close()
+    dp.close()
+    return 0
+
+
 def run_ours(args):
     import torch
     from vqa_transfer_externaldata_b200 import lib as L
@@ -694,13 +813,15 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement (N = 1 only)")
     ap.add_argument("--no-infer", action="store_true", help="skip the BASELINE config 5 inference sweep")
-    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer", "memft"])
     ap.add_argument("--infer-batches", default="64,512,4096,8192")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
     if args.mode == "infer":
         return run_infer(args)
+    if args.mode == "memft":
+        return run_memft(args)
     return run_ours(args)
 
 

@@ -85,9 +85,9 @@ typedef struct VqaSpatAttn {
   float* pooled; void* pooled_hi; void* pooled_lo;   /* [kinds * B * n, Dv] */
   /* backward */
   const float* d_pooled;                   /* [kinds * B * n, Dv] */
-  float* d_hv;                             /* [B, K, D] (summed over kinds and entries) */
+  float* d_hv;                             /* [kinds, B, K, D]: one plane per kind (summed over the kind's entries) */
   float* d_hq;                             /* [kinds * B * n, D] */
-  float* part;                             /* [B, D + 8] per-image partials: d att_w [D] | d att_b (slot D) */
+  float* part;                             /* [kinds * B, D + 8] partials per image and kind: d att_w [D] | d att_b (slot D) */
 } VqaSpatAttn;
 VQA_API VqaStatus vqa_memft_spat_attn_fwd(VqaOps ops, const VqaSpatAttn* a, void* stream);
 VQA_API VqaStatus vqa_memft_spat_attn_bwd(VqaOps ops, const VqaSpatAttn* a, void* stream);

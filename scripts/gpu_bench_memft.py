@@ -12,45 +12,9 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vqa_transfer_externaldata_b200 import memft as F  # noqa: E402
 
-CFG4 = dict(B=512, K=36, n=5, Dv=2048, D=1024, L=1024, W=300, A=4000, T=10, Vq=8192, Nws=2000)
-
-
-def synthetic(dims, seed=0):
-    rng = np.random.default_rng(seed)
-    B, K, n, T = dims["B"], dims["K"], dims["n"], dims["T"]
-    batch = {"image_ft": (np.abs(rng.standard_normal((B, K, dims["Dv"]), dtype=np.float32)) * 0.5),
-             "spatial_ft": rng.uniform(size=(B, K, 6)).astype(np.float32),
-             "num_boxes": rng.integers(10, K + 1, size=B).astype(np.int32)}
-    for kind in ("obj", "attr"):
-        x0, y0 = rng.uniform(0, 0.5, size=(B, n)), rng.uniform(0, 0.5, size=(B, n))
-        boxes = np.stack([x0, y0, x0 + rng.uniform(0.1, 0.5, size=(B, n)), y0 + rng.uniform(0.1, 0.5, size=(B, n))], axis=-1)
-        ln = rng.integers(1, T + 1, size=(B, n)).astype(np.int32)
-        blanks = rng.integers(1, dims["Vq"], size=(B, n, T)).astype(np.int32)
-        blanks[np.arange(T)[None, None, :] >= ln[:, :, None]] = 0
-        batch.update({f"{kind}_blank_fill/normal_boxes": boxes.astype(np.float32), f"{kind}_blank_fill/blanks": blanks,
-                      f"{kind}_blank_fill/blanks_len": ln, f"{kind}_blank_fill/fills": rng.integers(0, dims["A"], size=(B, n)).astype(np.int32),
-                      f"{kind}_blank_fill/num": rng.integers(1, n + 1, size=B).astype(np.int32),
-                      f"{kind}_blank_fill/wordsets": rng.integers(0, dims["Nws"], size=(B, n)).astype(np.int32)})
-    return batch
-
-
-def init_params(cfg, seed=1):
-    rng = np.random.default_rng(seed)
-    p = {}
-    for k, (shp, _) in F.FIELDS.items():
-        s = shp(cfg)
-        if k in ("wordset_map", "l_glove"):
-            p[k] = rng.standard_normal(s, dtype=np.float32) * 0.4
-        elif k.endswith("_gamma"):
-            p[k] = np.ones(s, np.float32)
-        elif k == "gru_gates_b":
-            p[k] = np.ones(s, np.float32)
-        elif len(s) == 2:
-            lim = np.sqrt(6.0 / (s[0] + s[1]))
-            p[k] = rng.uniform(-lim, lim, size=s).astype(np.float32)
-        else:
-            p[k] = np.zeros(s, np.float32)
-    return p
+CFG4 = F.CFG4
+synthetic = F.synthetic_batch
+init_params = F.xavier_params
 
 
 def main():

@@ -254,10 +254,243 @@ __global__ void __launch_bounds__(SL_THREADS) slab_ln_bwd_kernel(const VqaSlabLn
   }
 }
 
+// Register-resident variants (the default): thread (rg, cg) owns the 8 columns of column group cg in the rows
+// rg, rg + RG, ... of its slab -- at most RPT rows -- so the slab never touches shared memory, every global access is a
+// coalesced 32-byte piece per thread, and the per-column sums of the backward pass need no pass of their own (a thread
+// already holds whole column segments; RG > 1 adds one fixed-order combine through shared memory).
+// blockDim = (N / 8) * RG. ncu of the shared-memory kernels above at cfg4 shapes (profiles/r02_memft_ncu.md): 1 CTA of
+// 16 warps per SM for the [36, 1024] slab, 25 % occupancy, 1 TB/s.
+template <int RPT>
+__global__ void __launch_bounds__(RPT <= 5 ? 256 : 512) slab_ln_fwd_reg_kernel(const VqaSlabLn a, int RG) {
+  __shared__ float red[33];
+  const int N = a.N, CG = N >> 3, tid = threadIdx.x;
+  const int rg = tid / CG, c = (tid - rg * CG) << 3;
+  const long long row_base = static_cast<long long>(blockIdx.x) * a.n;
+  const float S = static_cast<float>(a.n) * static_cast<float>(N);
+  float x[RPT][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int r = rg + i * RG;
+    if (r < a.n) {
+      const float* z = a.z + (row_base + r) * N + c;
+      const float4 u = *reinterpret_cast<const float4*>(z), v = *reinterpret_cast<const float4*>(z + 4);
+      x[i][0] = u.x; x[i][1] = u.y; x[i][2] = u.z; x[i][3] = u.w; x[i][4] = v.x; x[i][5] = v.y; x[i][6] = v.z; x[i][7] = v.w;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += x[i][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[i][j] = 0.f;
+    }
+  }
+  const float mean = block_sum(s, red) / S;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    if (rg + i * RG < a.n) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = x[i][j] - mean;
+        q = fmaf(d, d, q);
+      }
+    }
+  }
+  const float var = block_sum(q, red) / S;
+  const float rstd = 1.0f / sqrtf(var + 1e-12f);
+  if (tid == 0) {
+    a.mean[blockIdx.x] = mean;
+    a.rstd[blockIdx.x] = rstd;
+  }
+  float gam[8], bet[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gam[j] = a.gamma[c + j];
+    bet[j] = a.beta[c + j];
+  }
+  const uint32_t thr = keep_threshold(a.keep);
+  const float inv_keep = 1.0f / a.keep;
+  bf16* ohi = static_cast<bf16*>(a.out_hi);
+  bf16* olo = static_cast<bf16*>(a.out_lo);
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int r = rg + i * RG;
+    if (r < a.n) {
+      const long long row = row_base + r;
+      const long long o = row * N + c;
+      float y[8], out[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        y[j] = act_fwd(fmaf(gam[j], (x[i][j] - mean) * rstd, bet[j]), a.act);
+        out[j] = y[j];
+      }
+      if (a.mul) {
+        const float* m = a.mul + (row % a.mul_rows) * N + c;
+        const float4 u = *reinterpret_cast<const float4*>(m), v = *reinterpret_cast<const float4*>(m + 4);
+        out[0] *= u.x; out[1] *= u.y; out[2] *= u.z; out[3] *= u.w; out[4] *= v.x; out[5] *= v.y; out[6] *= v.z; out[7] *= v.w;
+      }
+      if (thr < 65536u) {
+        const uint32_t bits = slab_keep_bits(a, row, c, thr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) out[j] = ((bits >> j) & 1u) ? out[j] * inv_keep : 0.f;
+      }
+      if (a.y) {
+        *reinterpret_cast<float4*>(a.y + o) = make_float4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<float4*>(a.y + o + 4) = make_float4(y[4], y[5], y[6], y[7]);
+      }
+      if (a.out_f32) {
+        *reinterpret_cast<float4*>(a.out_f32 + o) = make_float4(out[0], out[1], out[2], out[3]);
+        *reinterpret_cast<float4*>(a.out_f32 + o + 4) = make_float4(out[4], out[5], out[6], out[7]);
+      }
+      if (ohi) st8_planes(ohi, olo, o, out);
+    }
+  }
+}
+
+template <int RPT>
+__global__ void __launch_bounds__(512) slab_ln_bwd_reg_kernel(const VqaSlabLn a, int RG) {
+  extern __shared__ float comb[];   // RG > 1: [RG][3][N] per-row-group column sums
+  __shared__ float red[33];
+  const int N = a.N, CG = N >> 3, tid = threadIdx.x;
+  const int rg = tid / CG, c = (tid - rg * CG) << 3;
+  const long long row_base = static_cast<long long>(blockIdx.x) * a.n;
+  const float S = static_cast<float>(a.n) * static_cast<float>(N);
+  const float mean = a.mean[blockIdx.x], rstd = a.rstd[blockIdx.x];
+  const uint32_t thr = keep_threshold(a.keep);
+  const float inv_keep = 1.0f / a.keep;
+  float gam[8], bet[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gam[j] = a.gamma[c + j];
+    bet[j] = a.beta[c + j];
+  }
+  float dp[RPT][8];   // d loss / d pre-activation
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int r = rg + i * RG;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) dp[i][j] = 0.f;
+    if (r < a.n) {
+      const long long row = row_base + r;
+      const long long o = row * N + c;
+      const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
+      const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+      const float4 u0 = *reinterpret_cast<const float4*>(a.dout + o), u1 = *reinterpret_cast<const float4*>(a.dout + o + 4);
+      float up[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      if (a.dout2) {
+        const float4 v0 = *reinterpret_cast<const float4*>(a.dout2 + o), v1 = *reinterpret_cast<const float4*>(a.dout2 + o + 4);
+        up[0] += v0.x; up[1] += v0.y; up[2] += v0.z; up[3] += v0.w; up[4] += v1.x; up[5] += v1.y; up[6] += v1.z; up[7] += v1.w;
+      }
+      if (thr < 65536u) {
+        const uint32_t bits = slab_keep_bits(a, row, c, thr);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) up[j] = ((bits >> j) & 1u) ? up[j] * inv_keep : 0.f;
+      }
+      float mu[8];
+      if (a.mul) {
+        const float* m = a.mul + (row % a.mul_rows) * N + c;
+        const float4 m0 = *reinterpret_cast<const float4*>(m), m1 = *reinterpret_cast<const float4*>(m + 4);
+        mu[0] = m0.x; mu[1] = m0.y; mu[2] = m0.z; mu[3] = m0.w; mu[4] = m1.x; mu[5] = m1.y; mu[6] = m1.z; mu[7] = m1.w;
+      }
+      float dm[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (zz[j] - mean) * rstd;
+        const float pre = fmaf(gam[j], xh, bet[j]);
+        const float y = act_fwd(pre, a.act);
+        dm[j] = up[j] * y;
+        const float dy = a.mul ? up[j] * mu[j] : up[j];
+        const float dpre = a.act == 0 ? (pre > 0.f ? dy : 0.f) : (a.act == 1 ? dy * (1.0f - y * y) : dy);
+        dp[i][j] = dpre;
+        const float gg = dpre * gam[j];
+        s1 += gg;
+        s2 = fmaf(gg, xh, s2);
+      }
+      if (a.dmul) {
+        *reinterpret_cast<float4*>(a.dmul + o) = make_float4(dm[0], dm[1], dm[2], dm[3]);
+        *reinterpret_cast<float4*>(a.dmul + o + 4) = make_float4(dm[4], dm[5], dm[6], dm[7]);
+      }
+    }
+  }
+  const float m1 = block_sum(s1, red) / S;
+  const float m2 = block_sum(s2, red) / S;
+  bf16* dhi = static_cast<bf16*>(a.dz_hi);
+  bf16* dlo = static_cast<bf16*>(a.dz_lo);
+  float sg[8], sb[8], sz[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) sg[j] = sb[j] = sz[j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < RPT; ++i) {
+    const int r = rg + i * RG;
+    if (r < a.n) {
+      const long long o = (row_base + r) * N + c;
+      const float4 z0 = *reinterpret_cast<const float4*>(a.z + o), z1 = *reinterpret_cast<const float4*>(a.z + o + 4);
+      const float zz[8] = {z0.x, z0.y, z0.z, z0.w, z1.x, z1.y, z1.z, z1.w};
+      float dz[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xh = (zz[j] - mean) * rstd;
+        dz[j] = rstd * (dp[i][j] * gam[j] - m1 - xh * m2);
+        sg[j] = fmaf(dp[i][j], xh, sg[j]);
+        sb[j] += dp[i][j];
+        sz[j] += dz[j];
+      }
+      if (a.dz_f32) {
+        *reinterpret_cast<float4*>(a.dz_f32 + o) = make_float4(dz[0], dz[1], dz[2], dz[3]);
+        *reinterpret_cast<float4*>(a.dz_f32 + o + 4) = make_float4(dz[4], dz[5], dz[6], dz[7]);
+      }
+      if (dhi) st8_planes(dhi, dlo, o, dz);
+    }
+  }
+  if (a.part) {
+    float* p = a.part + static_cast<long long>(blockIdx.x) * 3 * N;
+    if (RG > 1) {
+      float* mine = comb + static_cast<long long>(rg) * 3 * N;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        mine[c + j] = sg[j];
+        mine[N + c + j] = sb[j];
+        mine[2 * N + c + j] = sz[j];
+      }
+      __syncthreads();
+      if (rg == 0) {
+        for (int g2 = 1; g2 < RG; ++g2) {   // fixed order
+          const float* o2 = comb + static_cast<long long>(g2) * 3 * N;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            sg[j] += o2[c + j];
+            sb[j] += o2[N + c + j];
+            sz[j] += o2[2 * N + c + j];
+          }
+        }
+      }
+    }
+    if (rg == 0) {
+      *reinterpret_cast<float4*>(p + c) = make_float4(sg[0], sg[1], sg[2], sg[3]);
+      *reinterpret_cast<float4*>(p + c + 4) = make_float4(sg[4], sg[5], sg[6], sg[7]);
+      *reinterpret_cast<float4*>(p + N + c) = make_float4(sb[0], sb[1], sb[2], sb[3]);
+      *reinterpret_cast<float4*>(p + N + c + 4) = make_float4(sb[4], sb[5], sb[6], sb[7]);
+      *reinterpret_cast<float4*>(p + 2 * N + c) = make_float4(sz[0], sz[1], sz[2], sz[3]);
+      *reinterpret_cast<float4*>(p + 2 * N + c + 4) = make_float4(sz[4], sz[5], sz[6], sz[7]);
+    }
+  }
+}
+
+// launch plan of the register-resident kernels: rows per thread and row groups, or 0 = use the shared-memory kernels
+inline int slab_reg_plan(int n, int N, int max_threads, int* rg_out) {
+  const int CG = N >> 3;
+  if (getenv("VQA_SLAB_SMEM")) return 0;
+  if (n <= 5 && CG <= 256) { *rg_out = 1; return 5; }
+  const int RG = (n + 8) / 9;
+  if (CG * RG <= max_threads) { *rg_out = RG; return 9; }
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // spatial attention + attended pooling: one CTA per image, the kinds one after the other
 // ---------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) spat_attn_fwd_kernel(const VqaSpatAttn a) {
+template <int NE>   // NE >= n entries: the unrolled per-entry accumulators (5 in the reference, datasets/dataset_vlmap.py:11-14)
+__global__ void __launch_bounds__(256, 3) spat_attn_fwd_kernel(const VqaSpatAttn a) {
   extern __shared__ float sm[];
   const int D = a.D, K = a.K, n = a.n, Dv = a.Dv, B = a.B;
   float* hq_s = sm;             // [n][D]
@@ -274,15 +507,15 @@ __global__ void __launch_bounds__(256) spat_attn_fwd_kernel(const VqaSpatAttn a)
   bf16* p_lo = static_cast<bf16*>(a.pooled_lo);
   for (int i = tid; i < D; i += 256) w_s[i] = a.att_w[i];
   const float bias = a.att_b[0];
-  for (int kind = 0; kind < a.kinds; ++kind) {
+  {
+    const int kind = blockIdx.y;   // one CTA per (image, kind)
     const long long row0 = (static_cast<long long>(kind) * B + b) * n;
-    __syncthreads();
     for (int i = tid; i < n * D; i += 256) hq_s[i] = a.hq[row0 * D + i];
     __syncthreads();
     for (int k = warp; k < K; k += 8) {
-      float acc[NMAX];
+      float acc[NE];
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e) acc[e] = 0.f;
+      for (int e = 0; e < NE; ++e) acc[e] = 0.f;
       const long long hv_base = (static_cast<long long>(b) * K + k) * D;
       for (int d8 = lane; d8 < D / 8; d8 += 32) {
         float hw[8];
@@ -290,7 +523,7 @@ __global__ void __launch_bounds__(256) spat_attn_fwd_kernel(const VqaSpatAttn a)
 #pragma unroll
         for (int j = 0; j < 8; ++j) hw[j] *= w_s[d8 * 8 + j];
 #pragma unroll
-        for (int e = 0; e < NMAX; ++e) {
+        for (int e = 0; e < NE; ++e) {
           if (e < n) {
             uint32_t bits = 0xFFu;
             if (thr < 65536u) {
@@ -307,7 +540,7 @@ __global__ void __launch_bounds__(256) spat_attn_fwd_kernel(const VqaSpatAttn a)
         }
       }
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e) {
+      for (int e = 0; e < NE; ++e) {
         if (e < n) {
           const float t = warp_sum(acc[e]);
           if (lane == 0) sc[e * K + k] = fmaf(t, inv_keep, bias);
@@ -332,13 +565,13 @@ __global__ void __launch_bounds__(256) spat_attn_fwd_kernel(const VqaSpatAttn a)
     }
     __syncthreads();
     for (int c = tid * 4; c < Dv; c += 1024) {
-      float4 acc[NMAX];
+      float4 acc[NE];
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int e = 0; e < NE; ++e) acc[e] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int k = 0; k < nb; ++k) {
         const float4 v = *reinterpret_cast<const float4*>(a.v + (static_cast<long long>(b) * K + k) * Dv + c);
 #pragma unroll
-        for (int e = 0; e < NMAX; ++e) {
+        for (int e = 0; e < NE; ++e) {
           if (e < n) {
             const float p = sc[e * K + k];
             acc[e].x = fmaf(p, v.x, acc[e].x);
@@ -349,7 +582,7 @@ __global__ void __launch_bounds__(256) spat_attn_fwd_kernel(const VqaSpatAttn a)
         }
       }
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e) {
+      for (int e = 0; e < NE; ++e) {
         if (e < n) {
           const long long o = (row0 + e) * Dv + c;
           if (a.pooled) *reinterpret_cast<float4*>(a.pooled + o) = acc[e];
@@ -365,7 +598,8 @@ __global__ void __launch_bounds__(256) spat_attn_fwd_kernel(const VqaSpatAttn a)
   }
 }
 
-__global__ void __launch_bounds__(256) spat_attn_bwd_kernel(const VqaSpatAttn a) {
+template <int NE>
+__global__ void __launch_bounds__(256, 2) spat_attn_bwd_kernel(const VqaSpatAttn a) {
   extern __shared__ float sm[];
   const int D = a.D, K = a.K, n = a.n, Dv = a.Dv, B = a.B;
   float* hq_s = sm;               // [n][D]
@@ -387,23 +621,24 @@ __global__ void __launch_bounds__(256) spat_attn_bwd_kernel(const VqaSpatAttn a)
     dw_s[i] = 0.f;
   }
   float dbias = 0.f;
-  for (int kind = 0; kind < a.kinds; ++kind) {
+  const int kind = blockIdx.y;   // one CTA per (image, kind): d Hv of each kind goes to its own plane [kinds, B, K, D]
+  float* d_hv = a.d_hv + static_cast<long long>(kind) * B * K * D;
+  {
     const long long row0 = (static_cast<long long>(kind) * B + b) * n;
-    __syncthreads();
     for (int i = tid; i < n * D; i += 256) hq_s[i] = a.hq[row0 * D + i];
     for (int i = tid; i < n * K; i += 256) at[i] = a.att[row0 * K + i];
     for (int i = tid; i < n * Dv; i += 256) dpool[i] = a.d_pooled[row0 * Dv + i];
     __syncthreads();
     // d a[e, k] = <d pooled[e], V[b, k]>
     for (int k = warp; k < K; k += 8) {
-      float acc[NMAX];
+      float acc[NE];
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e) acc[e] = 0.f;
+      for (int e = 0; e < NE; ++e) acc[e] = 0.f;
       if (k < nb) {
         for (int c = lane * 4; c < Dv; c += 128) {
           const float4 v = *reinterpret_cast<const float4*>(a.v + (static_cast<long long>(b) * K + k) * Dv + c);
 #pragma unroll
-          for (int e = 0; e < NMAX; ++e) {
+          for (int e = 0; e < NE; ++e) {
             if (e < n) {
               const float4 g = *reinterpret_cast<const float4*>(dpool + e * Dv + c);
               acc[e] = fmaf(g.x, v.x, fmaf(g.y, v.y, fmaf(g.z, v.z, fmaf(g.w, v.w, acc[e]))));
@@ -412,7 +647,7 @@ __global__ void __launch_bounds__(256) spat_attn_bwd_kernel(const VqaSpatAttn a)
         }
       }
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e) {
+      for (int e = 0; e < NE; ++e) {
         if (e < n) {
           const float t = warp_sum(acc[e]);
           if (lane == 0) ds[e * K + k] = t;
@@ -438,10 +673,10 @@ __global__ void __launch_bounds__(256) spat_attn_bwd_kernel(const VqaSpatAttn a)
       for (int e = 0; e < n; ++e) dbias += red[e];
     // thread = 4 consecutive feature columns, all boxes: no reduction across threads for d Hq / d Hv / d w
     for (int d0 = tid * 4; d0 < D; d0 += 1024) {
-      float dq[NMAX][4];
+      float dq[NE][4];
       float dwa[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e)
+      for (int e = 0; e < NE; ++e)
 #pragma unroll
         for (int j = 0; j < 4; ++j) dq[e][j] = 0.f;
       const float w4[4] = {w_s[d0], w_s[d0 + 1], w_s[d0 + 2], w_s[d0 + 3]};
@@ -453,7 +688,7 @@ __global__ void __launch_bounds__(256) spat_attn_bwd_kernel(const VqaSpatAttn a)
 #pragma unroll
           for (int j = 0; j < 4; ++j) hv[j] = ld_planes(hv_hi, hv_lo, o + j);
 #pragma unroll
-          for (int e = 0; e < NMAX; ++e) {
+          for (int e = 0; e < NE; ++e) {
             if (e < n) {
               uint32_t bits = 0xFu;
               if (thr < 65536u) {
@@ -474,16 +709,10 @@ __global__ void __launch_bounds__(256) spat_attn_bwd_kernel(const VqaSpatAttn a)
             }
           }
         }
-        float4* out = reinterpret_cast<float4*>(a.d_hv + o);
-        if (kind == 0) {
-          *out = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
-        } else {
-          const float4 old = *out;
-          *out = make_float4(old.x + dhv[0], old.y + dhv[1], old.z + dhv[2], old.w + dhv[3]);
-        }
+        *reinterpret_cast<float4*>(d_hv + o) = make_float4(dhv[0], dhv[1], dhv[2], dhv[3]);
       }
 #pragma unroll
-      for (int e = 0; e < NMAX; ++e)
+      for (int e = 0; e < NE; ++e)
         if (e < n)
           *reinterpret_cast<float4*>(a.d_hq + (row0 + e) * D + d0) = make_float4(dq[e][0], dq[e][1], dq[e][2], dq[e][3]);
 #pragma unroll
@@ -491,7 +720,7 @@ __global__ void __launch_bounds__(256) spat_attn_bwd_kernel(const VqaSpatAttn a)
     }
   }
   __syncthreads();
-  float* p = a.part + static_cast<long long>(b) * (D + 8);
+  float* p = a.part + (static_cast<long long>(kind) * B + b) * (D + 8);
   for (int i = tid; i < D; i += 256) p[i] = dw_s[i];
   if (tid == 0) p[D] = dbias;
 }
@@ -823,9 +1052,17 @@ VQA_API VqaStatus vqa_ops_slab_ln_fwd(VqaOps ops, const VqaSlabLn* a, void* stre
   if (!ops) return set_error(VQA_ERR_BAD_ARG, "vqa_ops_slab_ln_fwd: null context");
   VQA_TRY(check_slab(a, "vqa_ops_slab_ln_fwd"));
   if (a->slabs == 0) return VQA_OK;
-  const size_t smem = sizeof(float) * a->n * a->N;
-  VQA_TRY(ensure_smem(slab_ln_fwd_kernel, smem, "vqa_ops_slab_ln_fwd"));
-  slab_ln_fwd_kernel<<<a->slabs, SL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  int RG = 1;
+  const int rpt = slab_reg_plan(a->n, a->N, 512, &RG);
+  if (rpt == 5) {
+    slab_ln_fwd_reg_kernel<5><<<a->slabs, (a->N >> 3) * RG, 0, static_cast<cudaStream_t>(stream)>>>(*a, RG);
+  } else if (rpt == 9) {
+    slab_ln_fwd_reg_kernel<9><<<a->slabs, (a->N >> 3) * RG, 0, static_cast<cudaStream_t>(stream)>>>(*a, RG);
+  } else {
+    const size_t smem = sizeof(float) * a->n * a->N;
+    VQA_TRY(ensure_smem(slab_ln_fwd_kernel, smem, "vqa_ops_slab_ln_fwd"));
+    slab_ln_fwd_kernel<<<a->slabs, SL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  }
   VQA_LAUNCH_CHECK("slab_ln_fwd");
   return VQA_OK;
 }
@@ -835,9 +1072,20 @@ VQA_API VqaStatus vqa_ops_slab_ln_bwd(VqaOps ops, const VqaSlabLn* a, void* stre
   VQA_TRY(check_slab(a, "vqa_ops_slab_ln_bwd"));
   if (!a->dout) return set_error(VQA_ERR_BAD_ARG, "vqa_ops_slab_ln_bwd: dout is NULL");
   if (a->slabs == 0) return VQA_OK;
-  const size_t smem = sizeof(float) * a->n * a->N;
-  VQA_TRY(ensure_smem(slab_ln_bwd_kernel, smem, "vqa_ops_slab_ln_bwd"));
-  slab_ln_bwd_kernel<<<a->slabs, SL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  int RG = 1;
+  const int rpt = slab_reg_plan(a->n, a->N, 512, &RG);
+  const size_t comb = RG > 1 ? sizeof(float) * RG * 3 * a->N : 0;
+  if (rpt == 5) {
+    slab_ln_bwd_reg_kernel<5><<<a->slabs, (a->N >> 3) * RG, comb, static_cast<cudaStream_t>(stream)>>>(*a, RG);
+  } else if (rpt == 9 && comb <= 96 * 1024) {
+    if (comb > 32 * 1024)   // (+ the kernel's static shared memory: past the 48 KB default)
+      VQA_CUDA_CHECK(cudaFuncSetAttribute(slab_ln_bwd_reg_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    slab_ln_bwd_reg_kernel<9><<<a->slabs, (a->N >> 3) * RG, comb, static_cast<cudaStream_t>(stream)>>>(*a, RG);
+  } else {
+    const size_t smem = sizeof(float) * a->n * a->N;
+    VQA_TRY(ensure_smem(slab_ln_bwd_kernel, smem, "vqa_ops_slab_ln_bwd"));
+    slab_ln_bwd_kernel<<<a->slabs, SL_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  }
   VQA_LAUNCH_CHECK("slab_ln_bwd");
   return VQA_OK;
 }
@@ -870,8 +1118,14 @@ VQA_API VqaStatus vqa_memft_spat_attn_fwd(VqaOps ops, const VqaSpatAttn* a, void
   if (!a->pooled && !a->pooled_hi) return set_error(VQA_ERR_BAD_ARG, "vqa_memft_spat_attn_fwd: no pooled output");
   if (a->B == 0) return VQA_OK;
   const size_t smem = sizeof(float) * (static_cast<size_t>(a->n) * a->D + a->D + static_cast<size_t>(a->n) * a->K);
-  VQA_TRY(ensure_smem(spat_attn_fwd_kernel, smem, "vqa_memft_spat_attn_fwd"));
-  spat_attn_fwd_kernel<<<a->B, 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  const dim3 grid(a->B, a->kinds);
+  if (a->n <= 5) {
+    VQA_TRY(ensure_smem(spat_attn_fwd_kernel<5>, smem, "vqa_memft_spat_attn_fwd"));
+    spat_attn_fwd_kernel<5><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  } else {
+    VQA_TRY(ensure_smem(spat_attn_fwd_kernel<NMAX>, smem, "vqa_memft_spat_attn_fwd"));
+    spat_attn_fwd_kernel<NMAX><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  }
   VQA_LAUNCH_CHECK("spat_attn_fwd");
   return VQA_OK;
 }
@@ -883,8 +1137,14 @@ VQA_API VqaStatus vqa_memft_spat_attn_bwd(VqaOps ops, const VqaSpatAttn* a, void
   if (a->B == 0) return VQA_OK;
   const size_t smem = sizeof(float) * (static_cast<size_t>(a->n) * a->D + 2 * static_cast<size_t>(a->D) +
                                        2 * static_cast<size_t>(a->n) * a->K + static_cast<size_t>(a->n) * a->Dv);
-  VQA_TRY(ensure_smem(spat_attn_bwd_kernel, smem, "vqa_memft_spat_attn_bwd"));
-  spat_attn_bwd_kernel<<<a->B, 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  const dim3 grid(a->B, a->kinds);
+  if (a->n <= 5) {
+    VQA_TRY(ensure_smem(spat_attn_bwd_kernel<5>, smem, "vqa_memft_spat_attn_bwd"));
+    spat_attn_bwd_kernel<5><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  } else {
+    VQA_TRY(ensure_smem(spat_attn_bwd_kernel<NMAX>, smem, "vqa_memft_spat_attn_bwd"));
+    spat_attn_bwd_kernel<NMAX><<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(*a);
+  }
   VQA_LAUNCH_CHECK("spat_attn_bwd");
   return VQA_OK;
 }

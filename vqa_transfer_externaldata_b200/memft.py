@@ -160,7 +160,7 @@ class Model:
         b.dlang = f(R, L_)
         b.dzws, b.part_ws, b.dws_y = P(E, L_), f(2 * B, 3 * L_), f(E, W)
         b.dzp, b.part_p, b.dpooled = P(E, L_), f(2 * B, 3 * L_), f(E, Dv)
-        b.d_hv, b.d_hq, b.part_att = f(B * K, D), f(E, D), f(B, D + 8)
+        b.d_hv, b.d_hq, b.part_att = f(2 * B * K, D), f(E, D), f(2 * B, D + 8)
         b.dzq, b.part_q = P(E, D), f(2 * B, 3 * D)
         b.dzv, b.part_v = P(B * K, D), f(B, 3 * D)
         b.sum3 = f(3 * max(2 * L_, D) + 64)
@@ -179,6 +179,7 @@ class Model:
         d.num_boxes = i32(B)
         d.boxes, d.blanks, d.blanks_len = f(2, B, n, 4), i32(E, c.T), i32(E)
         d.fills4, d.num, d.wordsets = i32(R), i32(2, B), i32(E)
+        self._own = {"image_ft": d.image_ft, "spatial_ft": d.spatial_ft}
 
     def close(self):
         if getattr(self, "ops", None):
@@ -224,10 +225,18 @@ class Model:
         c, d = self.config, self.dbatch
         t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(np.asarray(a, dt)))   # noqa: E731
         B, n, T = c.B, c.n, c.T
-        if np.asarray(batch["image_ft"]).shape != (B, c.K, c.Dv):
-            raise ValueError(f"image_ft shape {np.asarray(batch['image_ft']).shape} != {(B, c.K, c.Dv)}")
-        d.image_ft.copy_(t(batch["image_ft"], np.float32), non_blocking=True)
-        d.spatial_ft.copy_(t(batch["spatial_ft"], np.float32), non_blocking=True)
+        if tuple(batch["image_ft"].shape) != (B, c.K, c.Dv):
+            raise ValueError(f"image_ft shape {tuple(batch['image_ft'].shape)} != {(B, c.K, c.Dv)}")
+        for key in ("image_ft", "spatial_ft"):
+            v = batch[key]
+            if isinstance(v, torch.Tensor) and v.is_cuda:   # device-resident features (a bank gathered on the device): adopted, no copy
+                if v.dtype != torch.float32 or not v.is_contiguous():
+                    raise ValueError(f"{key}: device tensors must be contiguous float32")
+                setattr(d, key, v)
+            else:
+                if getattr(d, key).data_ptr() != self._own[key].data_ptr():
+                    setattr(d, key, self._own[key])
+                getattr(d, key).copy_(t(v, np.float32), non_blocking=True)
         d.num_boxes.copy_(t(batch["num_boxes"], np.int32), non_blocking=True)
         fills = []
         for i, kind in enumerate(KINDS):
@@ -433,14 +442,15 @@ class Model:
         sa = self._spat(step)
         L.check(self.lib.vqa_memft_spat_attn_bwd(self.ops, C.byref(sa), s))
         sums = b.sum3[:D + 8]
-        self._colsum(b.part_att, B, D + 8, D + 8, sums)
+        self._colsum(b.part_att, 2 * B, D + 8, D + 8, sums)
         g["att_w"].view(-1).copy_(sums[:D])
         g["att_b"].copy_(sums[D:D + 1])
         self._slab(2 * B, n, D, b.zq, p["sq_gamma"], p["sq_beta"], b.mean_q, b.rstd_q, dout=b.d_hq, dz=b.dzq, part=b.part_q, bwd=True)
         self._ln_param_grads(b.part_q, 2 * B, D, g["sq_gamma"], g["sq_beta"], g["sq_b"])
         self._gemm(64, D, E, b.key_p, True, b.dzq, True, out=b.tmp64)
         g["sq_w"].copy_(b.tmp64[:6])
-        self._slab(B, K, D, b.zv, p["sv_gamma"], p["sv_beta"], b.mean_v, b.rstd_v, dout=b.d_hv, dz=b.dzv, part=b.part_v, bwd=True)
+        self._slab(B, K, D, b.zv, p["sv_gamma"], p["sv_beta"], b.mean_v, b.rstd_v, dout=b.d_hv[:B * K], dout2=b.d_hv[B * K:],
+                   dz=b.dzv, part=b.part_v, bwd=True)
         self._ln_param_grads(b.part_v, B, D, g["sv_gamma"], g["sv_beta"], g["sv_b"])
         self._gemm(64, D, B * K, b.spat_p, True, b.dzv, True, out=b.tmp64)
         g["sv_w"].copy_(b.tmp64[:6])
@@ -495,3 +505,55 @@ class Model:
     def gradients(self):
         torch.cuda.synchronize(self.dev)
         return {k: v.detach().cpu().numpy().copy() for k, v in self.g.items()}
+
+
+# ---- synthetic workload (BASELINE config 4 shapes; bench.py --mode memft, scripts/gpu_bench_memft.py) ----------------------
+CFG4 = dict(B=512, K=36, n=5, Dv=2048, D=1024, L=1024, W=300, A=4000, T=10, Vq=8192, Nws=2000)
+
+
+def synthetic_batch(dims, seed=0):
+    """A batch with the keys / dtypes of vlmap_memft/datasets/dataset_vlmap.py:128-266: non-negative features (post-ReLU
+    bottom-up features), 10..K valid proposals, 1..n valid entries per kind, blanks of 1..T tokens."""
+    rng = np.random.default_rng(seed)
+    B, K, n, T = dims["B"], dims["K"], dims["n"], dims["T"]
+    batch = {"image_ft": np.abs(rng.standard_normal((B, K, dims["Dv"]), dtype=np.float32)) * 0.5,
+             "spatial_ft": rng.uniform(size=(B, K, 6)).astype(np.float32),
+             "num_boxes": rng.integers(min(10, K), K + 1, size=B).astype(np.int32)}
+    for kind in KINDS:
+        x0, y0 = rng.uniform(0, 0.5, size=(B, n)), rng.uniform(0, 0.5, size=(B, n))
+        boxes = np.stack([x0, y0, x0 + rng.uniform(0.1, 0.5, size=(B, n)), y0 + rng.uniform(0.1, 0.5, size=(B, n))], axis=-1)
+        ln = rng.integers(1, T + 1, size=(B, n)).astype(np.int32)
+        blanks = rng.integers(1, dims["Vq"], size=(B, n, T)).astype(np.int32)
+        blanks[np.arange(T)[None, None, :] >= ln[:, :, None]] = 0
+        batch.update({f"{kind}_blank_fill/normal_boxes": boxes.astype(np.float32), f"{kind}_blank_fill/blanks": blanks,
+                      f"{kind}_blank_fill/blanks_len": ln,
+                      f"{kind}_blank_fill/fills": rng.integers(0, dims["A"], size=(B, n)).astype(np.int32),
+                      f"{kind}_blank_fill/num": rng.integers(1, n + 1, size=B).astype(np.int32),
+                      f"{kind}_blank_fill/wordsets": rng.integers(0, dims["Nws"], size=(B, n)).astype(np.int32)})
+    return batch
+
+
+def xavier_params(cfg, seed=1):
+    """Random initial variables as TF creates them (Xavier-uniform matrices, LayerNorm gamma 1 / beta 0, GRU gate bias 1)."""
+    rng = np.random.default_rng(seed)
+    p = {}
+    for k, (shp, _) in FIELDS.items():
+        s = shp(cfg)
+        if k in ("wordset_map", "l_glove"):
+            p[k] = rng.standard_normal(s, dtype=np.float32) * 0.4
+        elif k.endswith("_gamma") or k == "gru_gates_b":
+            p[k] = np.ones(s, np.float32)
+        elif len(s) == 2:
+            lim = np.sqrt(6.0 / (s[0] + s[1]))
+            p[k] = rng.uniform(-lim, lim, size=s).astype(np.float32)
+        else:
+            p[k] = np.zeros(s, np.float32)
+    return p
+
+
+def gemm_flops_per_step(c):
+    """Dense contractions of one train step (forward x 3: data + weight gradients), SURVEY 8d."""
+    E, R = 2 * c.B * c.n, 4 * c.B * c.n
+    fwd = 2.0 * (E * c.Dv * c.L + E * c.W * c.L + R * c.L * c.L + R * c.L * 2 * c.L + R * 2 * c.L * c.A +
+                 E * c.T * (c.W + c.L) * 3 * c.L)
+    return 3.0 * fwd
