@@ -23,3 +23,14 @@ def test_dp_step_equals_single_rank_step_two_ranks():
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     assert out.stdout.count("dp step == single-rank step: True") == 2
+
+
+def test_memft_dp_step_equals_single_rank_step_two_ranks():
+    """The same for the pre-training model (BASELINE config 4 is quoted on 8 x B200 DP)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29539", os.path.join(ROOT, "scripts", "gpu_memft_dp_check.py")]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("memft dp step == single-rank step: True") == 2

@@ -154,7 +154,10 @@ struct VqaHandle_t {
     unsigned int* mc_flags;     // two barrier counters behind the gradients (multicast / own mapping)
     unsigned int* my_flags;
     unsigned int* grid_ctr;     // local block counter of the exit barrier
-    unsigned int flag_total, grid_total;
+    unsigned int flag_total, grid_total;   // channel 0
+    // channels 1..3: exchanges that may be in flight at the same time (one per branch of the weight-gradient section)
+    // each own a pair of flag words (flags[2 ch], flags[2 ch + 1]), a block counter and their running totals
+    unsigned int ch_flag_total[4], ch_grid_total[4];
     int rank, world;
   } ar;
   bool early_grads;        // vqa_set_early_gradients

@@ -846,6 +846,24 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   const bool ar_on = h->ar.mc != nullptr && h->ar.world > 1 && g->v_w != nullptr &&
                      g->v_w >= h->ar.local && g->v_w < h->ar.local + h->ar.n_total;
   const bool early = h->early_grads && !(h->profile && !h->profile_overlapped);
+  // one exchange of gradient floats [off, off + cnt) on barrier channel ch (0 = the sequential channel)
+  auto ar_range = [&](long long off, long long cnt, int ch, bool exclusive, int ctas, cudaStream_t st) -> VqaStatus {
+    if (cnt <= 0) return VQA_OK;
+    unsigned int* ft = ch == 0 ? &h->ar.flag_total : &h->ar.ch_flag_total[ch];
+    unsigned int* gt = ch == 0 ? &h->ar.grid_total : &h->ar.ch_grid_total[ch];
+    *ft += static_cast<unsigned int>(h->ar.world);
+    return multimem_allreduce_sync_launch(h->ar.mc + off, cnt, h->ar.rank, h->ar.world, h->ar.mc_flags + 2 * ch,
+                                          h->ar.my_flags + 2 * ch, h->ar.grid_ctr + ch, *ft, gt, exclusive, ctas, st);
+  };
+  // Branch-wise exchange (default for the in-library collective): the small non-GRU slice goes out under the BPTT on the
+  // TPCs the recurrent grid leaves idle; in the weight-gradient section every branch's gradients are exchanged as soon as
+  // that branch is done, on its own barrier channel, beside the GEMMs still running -- only the exchange of the branch
+  // that finishes last is exposed. Needs dWv at the head of the buffer (ParamStore puts it there).
+  static const bool ar_branch_env = getenv("VQA_DP_BRANCH") == nullptr || atoi(getenv("VQA_DP_BRANCH")) != 0;
+  const long long vw_floats = ((static_cast<long long>(Dv) * D + 63) / 64) * 64;
+  const bool ar_branch = ar_on && !early && ar_branch_env && g->v_w == h->ar.local && g->embed && g->gru_gates_w &&
+                         g->embed == h->ar.local + h->ar.n_early && vw_floats <= h->ar.n_early &&
+                         !(h->profile && !h->profile_overlapped);
   if (early && g->v_w)
     VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, s));
   PH_BEGIN(VQA_PH_QV_BWD);
@@ -893,7 +911,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->v_w && !early) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, st));
     return VQA_OK;
   };
-  bool ar_early_done = false, ar_late_done = false;
+  bool ar_early_done = false, ar_late_done = false, ar_all_done = false;
   // GRU: back-propagation through time from dq
   const bool need_gru = g->gru_gates_w || g->gru_gates_b || g->gru_cand_w || g->gru_cand_b || g->embed;
   if (need_gru) {
@@ -915,8 +933,16 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       cudaStream_t a4 = s, a5 = s;
       if (pf) VQA_TRY(fork_stream(h, 4, s, &a4));
       const bool ar_early = ar_on && early && h->ar.n_early > 0;
-      if (ar_early) VQA_TRY(fork_stream(h, 5, s, &a5));   // forked BEFORE the cooperative launch, enqueued AFTER it
+      const bool ar_small = ar_branch && h->ar.n_early > vw_floats;
+      if (ar_early || ar_small) VQA_TRY(fork_stream(h, 5, s, &a5));   // forked BEFORE the cooperative launch, enqueued AFTER it
       VQA_TRY(gru_bwd_persistent_launch(a, h->num_sms, s));
+      if (ar_small) {   // everything final before the BPTT except dWv (which is taken in the weight-gradient section)
+        // (those parameter gradients were enqueued on auxiliary stream 3: the exchange waits for it, the BPTT does not)
+        VQA_CUDA_CHECK(cudaEventRecord(h->ev_join[3], h->aux[3]));
+        VQA_CUDA_CHECK(cudaStreamWaitEvent(a5, h->ev_join[3], 0));
+      }
+      if (ar_small)
+        VQA_TRY(ar_range(vw_floats, h->ar.n_early - vw_floats, 0, gru_pair_supported(Bn, L, h->num_sms), 0, a5));
       if (ar_early) {
         // ten 2-CTA clusters that each take a whole SM: the TPCs the 64 CTA pairs of the recurrent grid leave free
         h->ar.flag_total += static_cast<unsigned int>(h->ar.world);
@@ -928,6 +954,13 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       if (pf) VQA_TRY(launch_pending_prefetch(h, a4));
       (void)pp;
     } else {
+      if (ar_branch && h->ar.n_early > vw_floats) {   // the small slice, beside the per-step kernels
+        cudaStream_t a5;
+        VQA_TRY(fork_stream(h, 5, s, &a5));
+        VQA_CUDA_CHECK(cudaEventRecord(h->ev_join[3], h->aux[3]));
+        VQA_CUDA_CHECK(cudaStreamWaitEvent(a5, h->ev_join[3], 0));
+        VQA_TRY(ar_range(vw_floats, h->ar.n_early - vw_floats, 0, false, 16, a5));
+      }
       for (int t = T - 1; t >= 0; --t) {
         VQA_TRY(gru_bwd_update_launch(dh_cur, b.h_f32 + t * BL, b.u + t * BL, b.c + t * BL,
                                       batch->q_intseq_len, t, Bn, L, b.du, b.dh_part, b.dC_f32 + t * BL,
@@ -1015,7 +1048,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       // data-parallel runs (in-library exchange, dWv not taken early): the GRU / embedding gradients FIRST, side by side;
       // their all-reduce then runs under the v-projection weight gradient, the largest GEMM of the section, which
       // leaves only the non-GRU slice for the exposed tail. (Single-GPU order: all five side by side.)
-      const bool staged = order_env >= 0 ? order_env != 0 : (ar_on && !early);
+      const bool staged = order_env >= 0 ? order_env != 0 : (ar_on && !early && !ar_branch);
       if (staged) {
         VQA_TRY(fork_stream(h, 1, s, &a1));
         VQA_TRY(fork_stream(h, 2, s, &a2));
@@ -1039,6 +1072,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
         VQA_TRY(vproj_wgrad(s));
         if (ar_late_done) VQA_TRY(join_stream(h, 5, s));
       } else {
+        if (ar_branch) VQA_TRY(join_stream(h, 5, s));   // the small slice's exchange under the BPTT (its stream is reused below)
         VQA_TRY(fork_stream(h, 0, s, &a0));
         VQA_TRY(fork_stream(h, 1, s, &a1));
         VQA_TRY(fork_stream(h, 2, s, &a2));
@@ -1047,11 +1081,27 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
         VQA_TRY(cand_h_wgrad(a2, scratch2));
         VQA_TRY(x_wgrad(a3));
         VQA_TRY(vproj_wgrad(a0));
+        if (ar_branch) VQA_TRY(ar_range(0, vw_floats, 1, false, 24, a0));            // dWv, as soon as its GEMM is done
         VQA_TRY(embed_bwd(s));
+        if (ar_branch) {
+          const long long emb_floats = (g->gru_gates_w - g->embed);
+          cudaStream_t a5;
+          VQA_TRY(fork_stream(h, 5, s, &a5));
+          VQA_TRY(ar_range(h->ar.n_early, emb_floats, 2, false, 24, a5));             // the embedding gradient
+          VQA_TRY(join_stream(h, 1, s));
+          VQA_TRY(join_stream(h, 2, s));
+          VQA_TRY(join_stream(h, 3, s));
+          // the GRU kernels / biases + the tail slot (the embedding slice norm, written by embed_bwd on this stream)
+          VQA_TRY(ar_range(h->ar.n_early + emb_floats, h->ar.n_total - h->ar.n_early - emb_floats, 3, false, 48, s));
+          VQA_TRY(join_stream(h, 5, s));
+          VQA_TRY(join_stream(h, 0, s));
+          ar_all_done = true;
+        } else {
         VQA_TRY(join_stream(h, 0, s));
         VQA_TRY(join_stream(h, 1, s));
         VQA_TRY(join_stream(h, 2, s));
         VQA_TRY(join_stream(h, 3, s));
+        }
       }
       if (h->prefetched && !h->pf_joined) {   // the background gather forked before the BPTT
         VQA_TRY(join_stream(h, 4, s));
@@ -1069,7 +1119,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(join_stream(h, 1, s));
     h->outputs_pending = false;
   }
-  if (ar_on) {
+  if (ar_on && !ar_all_done) {
     // what has not been exchanged yet, one wide launch on `s` whose own entry / exit barriers make the sums valid when it
     // completes: the non-GRU slice [0, n_early) when the GRU / embedding slice went out under the dWv GEMM (default),
     // the GRU / embedding slice when the early slice went out under the BPTT (vqa_set_early_gradients), else everything
@@ -1110,6 +1160,7 @@ VQA_API VqaStatus vqa_set_gradient_allreduce(VqaHandle h, void* multicast_base, 
   h->ar.grid_ctr = h->buf.ar_grid_ctr;
   h->ar.flag_total = 0;
   h->ar.grid_total = 0;
+  for (int i = 0; i < 4; ++i) h->ar.ch_flag_total[i] = h->ar.ch_grid_total[i] = 0;
   h->ar.rank = rank;
   h->ar.world = world;
   // (the caller zeroes the flag words on every rank and synchronises the ranks before the first vqa_backward)
