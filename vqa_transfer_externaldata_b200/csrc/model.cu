@@ -859,7 +859,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   // TPCs the recurrent grid leaves idle; in the weight-gradient section every branch's gradients are exchanged as soon as
   // that branch is done, on its own barrier channel, beside the GEMMs still running -- only the exchange of the branch
   // that finishes last is exposed. Needs dWv at the head of the buffer (ParamStore puts it there).
-  static const bool ar_branch_env = getenv("VQA_DP_BRANCH") == nullptr || atoi(getenv("VQA_DP_BRANCH")) != 0;
+  static const bool ar_branch_env = getenv("VQA_DP_BRANCH") != nullptr && atoi(getenv("VQA_DP_BRANCH")) != 0;   // (opt-in until measured on >= 2 GPUs)
   const long long vw_floats = ((static_cast<long long>(Dv) * D + 63) / 64) * 64;
   const bool ar_branch = ar_on && !early && ar_branch_env && g->v_w == h->ar.local && g->embed && g->gru_gates_w &&
                          g->embed == h->ar.local + h->ar.n_early && vw_floats <= h->ar.n_early &&
