@@ -432,6 +432,39 @@ def memft_cpu_rate(n_images=32, steps=2, budget_s=25.0):
     return n_images / float(np.median(times)), torch.get_num_threads(), float(np.sum(times))
 
 
+def measure_memft(dp, dev, precision, peaks, steps=5, warmup=3):
+    """A short data-parallel run of the cfg4 train step on the ranks of this job (needs the engine of the headline run
+    closed: the two workspaces do not fit side by side with the 4096-image bank). Returns a dict on every rank."""
+    import torch
+    from vqa_transfer_externaldata_b200 import memft as F
+    torch.cuda.empty_cache()
+    cfg = F.make_config(F.CFG4, precision=precision)
+    model = F.Model(F.synthetic_batch(F.CFG4, seed=100 + 1000 * dp.rank), cfg, is_train=True, params=F.xavier_params(cfg), seed=777)
+    for _ in range(warmup):
+        model.train_step(sync=False)
+    dp.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        model.train_step(sync=False)
+    e1.record()
+    torch.cuda.synchronize()
+    dp.barrier()
+    ms = dp.max_over_ranks(e0.elapsed_time(e1)) / steps
+    loss, _ = model.fetch()
+    flops = F.gemm_flops_per_step(cfg)
+    model.close()
+    del model
+    torch.cuda.empty_cache()
+    B = F.CFG4["B"]
+    return {"config": "cfg4 vlmap_memft bf_or_wordset_withatt_sp train step fwd+bwd+clip+adam, B512 per GPU x (5+5) entries, K36 x Dv2048, "
+                      "5120 blank sequences T10, A4000; batch-sharded DP, NCCL all-reduce of the flat gradient",
+            "ms_per_step": ms, "images_per_s": B * dp.world_size / ms * 1e3, "steps": steps, "warmup": warmup,
+            "tflops_per_gpu": flops / 1e9 / ms, "roofline_frac": flops / (peaks["bf16_tflops_sustained"] * 1e12) * 1e3 / ms,
+            "loss_finite": bool(np.isfinite(loss))}
+
+
 def run_memft(args):
     """`--mode memft`: BASELINE config 4 -- one train step of the vlmap pre-training graph (bs 512 per GPU, 5 + 5 entries
     per image, K 36, A 4000, blanks <= 10 tokens), batch-sharded data parallel over N GPUs (NCCL all-reduce of the flat
@@ -755,6 +788,12 @@ def run_ours(args):
         inference = {"config": "cfg5: forward, K 100 padded boxes (10..100 valid), global batch sharded over the ranks, no collective; "
                                "roofline 0.59 us / sample / GPU", "sweep": sweep}
 
+    # BASELINE config 4 (the vlmap pre-training graph) on the same ranks: a short run of the data-parallel train step so
+    # that its row is on the same record as the headline at every N (`--mode memft` prints its own full line)
+    pretrain = None
+    if not args.no_memft:
+        pretrain = measure_memft(dp, dev, args.precision, peaks, steps=5, warmup=3)
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, threads, busy = cpu_port_rate(B, 0, 1, budget_s=10.0)
@@ -783,6 +822,7 @@ def run_ours(args):
             "sections": sections,
             "fp32_mode": fp32_mode,
             "inference": inference,
+            "pretrain_cfg4": pretrain,
             "phase_ms": phase_ms,
             "critical_path_ms": critical_ms,
             "cpu_baseline": cpu_baseline,
@@ -813,6 +853,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement (N = 1 only)")
     ap.add_argument("--no-infer", action="store_true", help="skip the BASELINE config 5 inference sweep")
+    ap.add_argument("--no-memft", action="store_true", help="skip the short BASELINE config 4 (pre-training graph) run")
     ap.add_argument("--mode", default="train", choices=["train", "infer", "memft"])
     ap.add_argument("--infer-batches", default="64,512,4096,8192")
     args = ap.parse_args()

@@ -1077,10 +1077,12 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
         VQA_TRY(fork_stream(h, 1, s, &a1));
         VQA_TRY(fork_stream(h, 2, s, &a2));
         VQA_TRY(fork_stream(h, 3, s, &a3));
+        static const int dwv_first = getenv("VQA_WGRAD_DWV_FIRST") ? atoi(getenv("VQA_WGRAD_DWV_FIRST")) : 0;
+        if (dwv_first) VQA_TRY(vproj_wgrad(a0));
         VQA_TRY(gates_h_wgrad(a1, scratch1));
         VQA_TRY(cand_h_wgrad(a2, scratch2));
         VQA_TRY(x_wgrad(a3));
-        VQA_TRY(vproj_wgrad(a0));
+        if (!dwv_first) VQA_TRY(vproj_wgrad(a0));
         if (ar_branch) VQA_TRY(ar_range(0, vw_floats, 1, false, 24, a0));            // dWv, as soon as its GEMM is done
         VQA_TRY(embed_bwd(s));
         if (ar_branch) {
