@@ -23,20 +23,24 @@ eng.lib.vqa_internal_set_gru_trace(C.c_void_p(trace.data_ptr()))
 model.train_step(batch)
 torch.cuda.synchronize()
 eng.lib.vqa_internal_set_gru_trace(C.c_void_p(0))
-T, ncta = CFG1["T"], 128
+T = CFG1["T"]
+WAVES = 2 if os.environ.get("VQA_GRU_WAVES") == "2" else 1
+ncta = 128 // WAVES
 for mode, name in ((0, "forward"), (1, "BPTT")):
-    tr = trace[mode << 17:(mode << 17) + ncta * 2 * T * 8].cpu().numpy().reshape(ncta, 2 * T, 8).astype(np.float64)
-    t0 = tr[tr > 0].min()
-    print(f"== {name}: total {(tr.max() - t0) / 1e3:.1f} us")
-    print("phase  start(us)  wait->tile0  tile0->acc  acc->arrive  (medians over CTAs, us)   spread of arrive")
-    for p in range(2 * T):
-        a = tr[:, p, :]
-        if a[:, 3].max() == 0:
-            continue
-        st = np.median(a[:, 0][a[:, 0] > 0]) if (a[:, 0] > 0).any() else np.nan
-        f = lambda x, y: np.median((a[:, y] - a[:, x])[(a[:, x] > 0) & (a[:, y] > 0)]) / 1e3 if ((a[:, x] > 0) & (a[:, y] > 0)).any() else float("nan")
-        if mode == 0 and p % 2 == 0 and p > 0:
-            print(f"      fwd kind0 detail: acc->staged {f(2, 5):.2f}  ->bar_all {f(5, 6):.2f}  ->stored {f(6, 4):.2f}  "
-                  f"->fenced {f(4, 7):.2f}  ->red {f(7, 3):.2f}")
-        print(f"{p:4d}  {(st - t0) / 1e3:9.2f}  {f(0, 1):10.2f}  {f(1, 2):10.2f}  {f(2, 3):10.2f}      "
-              f"{(a[:, 3].max() - a[:, 3].min()) / 1e3:6.2f}   arrive@{(np.median(a[:, 3]) - t0) / 1e3:8.2f}")
+    full = trace[mode << 17:(mode << 17) + ncta * WAVES * 2 * T * 8].cpu().numpy().reshape(ncta, WAVES, 2 * T, 8).astype(np.float64)
+    t0 = full[full > 0].min()
+    for wv in range(WAVES):
+        tr = full[:, wv]
+        print(f"== {name} wave {wv}: total {(full.max() - t0) / 1e3:.1f} us")
+        print("phase  start(us)  wait->tile0  tile0->acc  acc->arrive  (medians over CTAs, us)   spread of arrive")
+        for p in range(2 * T):
+            a = tr[:, p, :]
+            if a[:, 3].max() == 0:
+                continue
+            st = np.median(a[:, 0][a[:, 0] > 0]) if (a[:, 0] > 0).any() else np.nan
+
+            def f(x, y):
+                m = (a[:, x] > 0) & (a[:, y] > 0)
+                return np.median((a[:, y] - a[:, x])[m]) / 1e3 if m.any() else float("nan")
+            print(f"{p:4d}  {(st - t0) / 1e3:9.2f}  {f(0, 1):10.2f}  {f(1, 2):10.2f}  {f(2, 3):10.2f}      "
+                  f"{(a[:, 3].max() - a[:, 3].min()) / 1e3:6.2f}   arrive@{(np.median(a[:, 3]) - t0) / 1e3:8.2f}")

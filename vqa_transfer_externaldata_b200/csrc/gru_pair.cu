@@ -46,19 +46,29 @@ constexpr int Q_W_TILE = Q_UNITS * Q_BK * 2;    // 4 KB streamed weight tile (32
 //   phases whose weights are RESIDENT: 3 stages of 32 KB, activation tiles only. With two stages only 64 KB of the
 //     128 KB (256 KB in the BPTT's K = 2L phase) operand were in flight per ~0.9 us TMA round trip: the phase's loads
 //     took two (four) dependent round trips, 2.1 (4.1) us of every phase (profiles/r02_gru_phase_trace.txt).
-constexpr int Q_STAGES = 3;
+//
+// SWAP (the two-wave variant): the SMALLER matrix is resident instead (forward: candidate rows, BPTT: Wc_h rows; 64 KB),
+// which frees 64 KB: the ring grows to 128 KB (resident phases: 4 stages of 32 KB, the whole 128 KB operand in flight;
+// streamed phases: 2 stages of 64 KB = [32 KB activation | up to 32 KB weight tiles]) and each wave gets a DEDICATED
+// 16 KB staging buffer for its TMA stores. The number of TMA operations per time step is unchanged in the forward kernel
+// (8 + 4 instead of 4 + 8) and grows from 16 to 20 in the BPTT.
+constexpr int Q_STAGES = 4;                                // barrier slots (the geometries below use 2, 3 or 4 of them)
 constexpr int Q_STAGE_S = Q_KBS * (Q_A_TILE + Q_W_TILE);   // 48 KB streamed-phase stage
 constexpr int Q_STAGE_R = Q_KBS * Q_A_TILE;                // 32 KB resident-phase stage
 constexpr int Q_RING = 2 * Q_STAGE_S;                      // = 3 * Q_STAGE_R = 96 KB
 static_assert(Q_RING == 3 * Q_STAGE_R, "ring geometries");
+constexpr int Q_STG_BYTES = 2 * Q_A_TILE;                  // 16 KB: the (up to) two staged operand tiles of a phase
 constexpr int Q_EPI_WARPS = 16;
-constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS + 32;   // producer, MMA issuer, 16 epilogue warps, publisher (WAVES = 2)
+constexpr int Q_THREADS = 64 + 32 * Q_EPI_WARPS;   // producer, MMA issuer, 16 epilogue warps
 constexpr int Q_TMEM_COLS = 128;                // forward: gates at column 0 (64 wide), candidate at 64 (32 wide)
 constexpr int NU = 8;                           // units per epilogue thread
 
 // resident weights: forward = this CTA's gate rows (64 x L), BPTT = its Wg_h rows (32 x 2L): 128 L bytes
-__host__ __device__ constexpr int q_wres_bytes(int L) { return 2 * Q_UNITS * L * 2; }
-__host__ __device__ constexpr int q_smem_bytes(int L) { return q_wres_bytes(L) + Q_RING + 256 + 1024; }
+__host__ __device__ constexpr int q_wres_bytes(int L, bool swap = false) { return (swap ? 1 : 2) * Q_UNITS * L * 2; }
+__host__ __device__ constexpr int q_ring_bytes(bool swap) { return swap ? 4 * Q_STAGE_R : Q_RING; }
+__host__ __device__ constexpr int q_smem_bytes(int L, bool swap = false, int waves = 1) {
+  return q_wres_bytes(L, swap) + q_ring_bytes(swap) + (swap ? waves * Q_STG_BYTES : 0) + 256 + 1024;
+}
 
 struct PairGruArgs {
   int B, row_end, L, T;
@@ -84,11 +94,11 @@ __device__ __forceinline__ unsigned long long gtimer() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define GRU_TRACE(p, k)                                                                                   \
-  do {                                                                                                    \
-    if (g.trace)                                                                                          \
-      g.trace[((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * num_phases + (p)) * 8 + (k)] = \
-          gtimer();                                                                                       \
+#define GRU_TRACEW(w, p, k)                                                                                    \
+  do {                                                                                                          \
+    if (g.trace)                                                                                                \
+      g.trace[(((static_cast<size_t>(blockIdx.y) * gridDim.x + blockIdx.x) * WAVES + (w)) * num_phases + (p)) * 8 + (k)] = \
+          gtimer();                                                                                             \
   } while (0)
 
 
@@ -169,10 +179,11 @@ __device__ __forceinline__ void stage8bf(uint32_t tile, int r, int chunk, const 
 // between them phase by phase: while the epilogue warps turn wave A's accumulator into the next operand tile and the
 // other CTAs' arrivals trickle in, the producer and MMA warps already run wave B's phase. One wave leaves the tensor
 // pipe and the load path idle for ~60 % of a phase (profiles/r02_gru_phase_trace.txt: 2.6 us of loads + MMAs in a 5.9 us
-// phase); two waves fill that gap. Each wave has its own accumulator columns, accumulator barrier and counters; the ring
-// is shared (a phase starts once the previous phase's stages are consumed), so the operand tiles leave through plain
-// 16-byte stores + a gpu-scope fence instead of the TMA-store staging inside the ring.
-template <int MODE, int WAVES>
+// phase); two waves fill that gap. Each wave has its own accumulator columns, accumulator barrier, counters and
+// TMA-store staging buffer; the ring is shared (a phase starts once the previous phase's stages are consumed).
+// A first version published the operand tiles with plain stores + a gpu-scope fence (no room for staging next to
+// 128 KB of weights): MEMBAR.ALL.GPU cost 1.5 - 3.3 us per phase and stalled the other wave's loads -- hence SWAP.
+template <int MODE, int WAVES, bool SWAP>
 __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_a1,
     const __grid_constant__ CUtensorMap tm_w0, const __grid_constant__ CUtensorMap tm_w1,
@@ -182,18 +193,21 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
                                              ~static_cast<uintptr_t>(1023));
   const int L = g.L, T = g.T, B = g.B;
   const int KB = L / Q_BK;
-  constexpr int RES_KIND = (MODE == 0) ? 0 : 1;   // the phase kind whose weights are resident
-  // resident weights: forward kind 0 = gate rows (64 x L: KB tiles of 8 KB); BPTT kind 1 = Wg_h rows (32 x 2L:
-  // 2 KB tiles of 4 KB). The other matrix (32 rows) streams through the ring next to the activation tiles.
+  // the phase kind whose weights are resident: the larger matrix (forward kind 0 = gate rows, 64 x L: KB tiles of 8 KB;
+  // BPTT kind 1 = Wg_h rows, 32 x 2L: 2 KB tiles of 4 KB), or with SWAP the smaller one (forward kind 1 = candidate rows,
+  // BPTT kind 0 = Wc_h rows: 32 x L). The other matrix streams through the ring next to the activation tiles.
+  constexpr int RES_KIND = SWAP ? ((MODE == 0) ? 1 : 0) : ((MODE == 0) ? 0 : 1);
+  constexpr int NST_RES = SWAP ? 4 : 3;                               // ring stages of a resident-weight phase
+  constexpr uint32_t PITCH_S = SWAP ? 2 * Q_STAGE_R : Q_STAGE_S;      // stage pitch of a streamed-weight phase
+  auto wtile = [](int kind) -> uint32_t { return (MODE == 0 && kind == 0) ? 8192u : 4096u; };   // weight bytes per k-block
   uint8_t* wres = smem;
-  uint8_t* ring = smem + q_wres_bytes(L);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(ring + Q_RING);
+  uint8_t* ring = smem + q_wres_bytes(L, SWAP);
+  uint8_t* stg = ring + q_ring_bytes(SWAP);           // SWAP: [WAVES][16 KB] TMA-store staging
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + (SWAP ? WAVES * Q_STG_BYTES : 0));
   uint64_t* empty_bar = full_bar + Q_STAGES;
   uint64_t* tmem_full_bar = empty_bar + Q_STAGES;   // [2]: one per wave
   uint64_t* w_bar = tmem_full_bar + 2;
-  uint64_t* pub_bar = w_bar + 1;                     // [2]: "every epilogue thread has stored its share of the operand tile"
-  uint64_t* sig_bar = pub_bar + 2;                   // [2]: "the publisher has signalled this wave's phase"
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sig_bar + 2);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = ptx::cluster_ctarank();
@@ -223,10 +237,6 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     ptx::mbar_init(&tmem_full_bar[0], 1);
     ptx::mbar_init(&tmem_full_bar[1], 1);
     ptx::mbar_init(w_bar, 1);
-    ptx::mbar_init(&pub_bar[0], 32 * Q_EPI_WARPS);
-    ptx::mbar_init(&pub_bar[1], 32 * Q_EPI_WARPS);
-    ptx::mbar_init(&sig_bar[0], 1);
-    ptx::mbar_init(&sig_bar[1], 1);
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -258,19 +268,19 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     const uint32_t lw = ptx::mapa_u32(ptx::smem_u32(w_bar), 0);
     if (lane == 0) {
       // resident weights of BOTH CTAs complete on the leader's barrier (it issues the MMAs that read them)
-      if (rank == 0) ptx::mbar_arrive_expect_tx(w_bar, 2u * static_cast<uint32_t>(q_wres_bytes(L)));
-      // (the weight maps have 32-row boxes of g.kbs k-blocks: tiles of one k-block stay kbs * 4 KB apart per op)
-      if (MODE == 0) {
-        // gate rows: r (32 rows) and u (32 rows) of this slice, k-block tile = [r rows | u rows] = 8 KB
-        for (int kb = 0; kb < KB; ++kb) {
-          ptx::tma_load_2d_pair(wres + kb * 8192, &tm_w0, lw, kb * Q_BK, slice32 * 96);
-        }
-      } else {
-        for (int kb = 0; kb < 2 * KB; ++kb) ptx::tma_load_2d_pair(wres + kb * 4096, &tm_w1, lw, kb * Q_BK, j0);
-      }
+      if (rank == 0) ptx::mbar_arrive_expect_tx(w_bar, 2u * static_cast<uint32_t>(q_wres_bytes(L, SWAP)));
+      // tm_w0 / tm_w1 are the weights of phase kind 0 / 1: the resident one as 2-D boxes of one k-block, the streamed one
+      // as boxes of g.kbs k-blocks. Forward rows of a slice in the packed matrix: [r rows 32 | u rows 32 | c rows 32]
+      // (gate tile of a k-block = [r | u] = 8 KB, candidate tile 4 KB); BPTT: rows j0.. of Wc_h (kind 0) / Wg_h (kind 1).
+      const CUtensorMap* tres = RES_KIND == 0 ? &tm_w0 : &tm_w1;
+      const int res_row = (MODE == 0) ? slice32 * 96 + (RES_KIND == 0 ? 0 : 64) : j0;
+      const int res_nkb = (MODE == 1 && RES_KIND == 1) ? 2 * KB : KB;
+      for (int kb = 0; kb < res_nkb; ++kb)
+        ptx::tma_load_2d_pair(wres + kb * wtile(RES_KIND), tres, lw, kb * Q_BK, res_row);
     }
     __syncwarp();
-    uint32_t uses[Q_STAGES] = {0u, 0u, 0u};   // how often each stage has been filled so far (barrier phase parity)
+    uint32_t uses[Q_STAGES] = {0u, 0u, 0u, 0u};   // how often each stage has been filled so far (barrier phase parity)
+    uint32_t gslot = 0;                            // SWAP: boxes issued so far (slot = gslot % 4)
     for (int pw = 0; pw < num_phases * WAVES; ++pw) {
       const int p = pw / WAVES, w = pw - p * WAVES;
       bool mm; int kind, t;
@@ -278,15 +288,43 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       if (!mm) continue;
       const bool streamed = kind != RES_KIND;
       const CUtensorMap* ta = kind ? &tm_a1 : &tm_a0;
-      const CUtensorMap* tw = (MODE == 0) ? &tm_w1 : &tm_w0;
-      const int wrow = (MODE == 0) ? slice32 * 96 + 64 : j0;
+      const CUtensorMap* tw = kind ? &tm_w1 : &tm_w0;
+      const int wrow = (MODE == 0) ? slice32 * 96 + (kind == 0 ? 0 : 64) : j0;
       const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
       const int arow = t * B + (w == 0 ? m0w[0] : m0w[WAVES - 1]);
       unsigned int* counter = w == 0 ? counterw[0] : counterw[WAVES - 1];
       const int kbs = g.kbs;
-      const uint32_t a_bytes = kbs * Q_A_TILE, w_bytes = kbs * Q_W_TILE;
-      const int nstages = streamed ? 2 : 3;
-      const uint32_t pitch = streamed ? Q_STAGE_S : Q_STAGE_R;
+      const uint32_t a_bytes = kbs * Q_A_TILE, w_bytes = kbs * wtile(kind);
+      if constexpr (SWAP) {
+        // ONE continuous ring of four 32 KB slots across phases and waves: every box (activation or weight tiles of
+        // g.kbs k-blocks) takes the next slot, so the loads of the next phase / wave start as soon as slots free up and
+        // its counter allows -- nothing drains between phases. A streamed phase issues weight box, activation box,
+        // weight box, ... (the first weight box goes out before the counter wait).
+        auto issue = [&](const CUtensorMap* map, int row, int kb, uint32_t bytes) {
+          const uint32_t slot = gslot & 3u, use = gslot >> 2;
+          ++gslot;
+          ptx::mbar_wait(&empty_bar[slot], (use & 1u) ^ 1u);
+          const uint32_t lf = ptx::mapa_u32(ptx::smem_u32(&full_bar[slot]), 0);
+          if (ptx::elect_one()) {
+            if (rank == 0) ptx::mbar_arrive_expect_tx(&full_bar[slot], 2 * bytes);
+            ptx::tma_load_3d_pair(ring + slot * Q_STAGE_R, map, lf, 0, row, kb);
+          }
+          __syncwarp();
+        };
+        for (int kb = 0; kb < nkb; kb += kbs) {
+          if (streamed) issue(tw, wrow, kb, w_bytes);
+          if (kb == 0) {
+            wait_counter(counter, static_cast<unsigned int>(p) * nprod);
+            ptx::fence_proxy_async_full();
+            if (lane == 0) GRU_TRACEW(w, p, 0);
+            __syncwarp();
+          }
+          issue(ta, arow, kb, a_bytes);
+        }
+        continue;
+      }
+      const int nstages = streamed ? 2 : NST_RES;
+      const uint32_t pitch = streamed ? PITCH_S : Q_STAGE_R;
       // the two geometries overlap: before anything of this phase is written (the early weight load below included),
       // every stage the previous phase filled must have been consumed by its MMAs
 #pragma unroll
@@ -312,7 +350,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
           // this phase's operand rows were written by the epilogues of phase p - 1 of the CTAs sharing our rows
           wait_counter(counter, static_cast<unsigned int>(p) * nprod);
           ptx::fence_proxy_async_full();
-          if (lane == 0 && w == 0) GRU_TRACE(p, 0);
+          if (lane == 0) GRU_TRACEW(w, p, 0);
           __syncwarp();
         }
         if (ptx::elect_one()) {
@@ -332,7 +370,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       constexpr uint32_t idesc128 = ptx::make_idesc_bf16(128, 128, false, false);   // forward gates: r|u of 64 units
       constexpr uint32_t idesc64 = ptx::make_idesc_bf16(128, 64, false, false);
       ptx::mbar_wait(w_bar, 0);
-      uint32_t uses[Q_STAGES] = {0u, 0u, 0u};
+      uint32_t uses[Q_STAGES] = {0u, 0u, 0u, 0u};
+      uint32_t gslot = 0;
       for (int pw = 0; pw < num_phases * WAVES; ++pw) {
         const int p = pw / WAVES, w = pw - p * WAVES;
         bool mm; int kind, t;
@@ -342,11 +381,46 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
         const bool wide = (MODE == 0 && kind == 0);
         const uint32_t idesc = wide ? idesc128 : idesc64;
         const int nkb = (MODE == 1 && kind == 1) ? 2 * KB : KB;
-        const uint32_t wtile = wide ? 8192 : 4096;
+        const uint32_t wt = wtile(kind);
         const uint32_t d_tmem = tmem_base + w * TM_WAVE + ((MODE == 0 && kind == 1) ? 64 : 0);
         const int kbs = g.kbs;
-        const int nstages = streamed ? 2 : 3;
-        const uint32_t pitch = streamed ? Q_STAGE_S : Q_STAGE_R;
+        if constexpr (SWAP) {
+          for (int kb = 0; kb < nkb; kb += kbs) {
+            uint32_t wslot = 0;
+            if (streamed) {
+              wslot = gslot & 3u;
+              ptx::mbar_wait(&full_bar[wslot], (gslot >> 2) & 1u);
+              ++gslot;
+            }
+            const uint32_t aslot = gslot & 3u;
+            ptx::mbar_wait(&full_bar[aslot], (gslot >> 2) & 1u);
+            ++gslot;
+            ptx::tc_fence_after();
+            if (kb == 0 && lane == 0) GRU_TRACEW(w, p, 1);
+            const uint32_t sa0 = ptx::smem_u32(ring + aslot * Q_STAGE_R);
+            const uint32_t sw0 = ptx::smem_u32(ring + wslot * Q_STAGE_R);
+            if (ptx::elect_one()) {
+              for (int i = 0; i < kbs; ++i) {
+                const uint32_t sa = sa0 + i * Q_A_TILE;
+                const uint32_t sb = streamed ? sw0 + i * wt : ptx::smem_u32(wres) + (kb + i) * wt;
+#pragma unroll
+                for (int kk = 0; kk < Q_BK / 16; ++kk) {
+                  const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, 1024);
+                  const uint64_t db = ptx::make_smem_desc_sw128(sb + kk * 32, 16, 1024);
+                  ptx::umma_f16_pair(d_tmem, da, db, idesc, (kb | i | kk) != 0);
+                }
+              }
+              ptx::umma_commit_pair(&empty_bar[aslot], 3);
+              if (streamed) ptx::umma_commit_pair(&empty_bar[wslot], 3);
+            }
+            __syncwarp();
+          }
+          if (ptx::elect_one()) ptx::umma_commit_pair(&tmem_full_bar[w], 3);
+          __syncwarp();
+          continue;
+        }
+        const int nstages = streamed ? 2 : NST_RES;
+        const uint32_t pitch = streamed ? PITCH_S : Q_STAGE_R;
         int stage = 0;
         for (int kb = 0; kb < nkb; kb += kbs) {
           uint32_t use = 0;
@@ -354,14 +428,14 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
           for (int q = 0; q < Q_STAGES; ++q) if (q == stage) { use = uses[q]; uses[q] = use + 1; }
           ptx::mbar_wait(&full_bar[stage], use & 1u);
           ptx::tc_fence_after();
-          if (kb == 0 && lane == 0 && w == 0) GRU_TRACE(p, 1);
+          if (kb == 0 && lane == 0) GRU_TRACEW(w, p, 1);
           const uint32_t sa0 = ptx::smem_u32(ring + stage * pitch);
           const uint32_t sw0 = sa0 + Q_KBS * Q_A_TILE;
           if (ptx::elect_one()) {
             if (g.dbg != 1)
             for (int i = 0; i < kbs; ++i) {
               const uint32_t sa = sa0 + i * Q_A_TILE;
-              const uint32_t sb = streamed ? sw0 + i * Q_W_TILE : ptx::smem_u32(wres) + (kb + i) * wtile;
+              const uint32_t sb = streamed ? sw0 + i * wt : ptx::smem_u32(wres) + (kb + i) * wt;
 #pragma unroll
               for (int kk = 0; kk < Q_BK / 16; ++kk) {
                 const uint64_t da = ptx::make_smem_desc_sw128(sa + kk * 32, 16, 1024);
@@ -380,36 +454,6 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
         // reach after draining TMEM: no tmem_empty barrier needed
       }
     }
-  } else if (warp >= 2 + Q_EPI_WARPS) {
-    // ===================== publisher warp (WAVES = 2) =====================
-    // The epilogue threads arrive on pub_bar[w] after storing their share of the operand tile and go straight on to the
-    // other wave; this warp turns the arrivals into the cross-CTA signal (gpu-scope fence + counter), so the fence's
-    // latency is off the epilogue warps' path. Phases without a matmul (the first one or two) publish in line instead:
-    // nothing there keeps the epilogue from running a whole phase ahead of this warp.
-    if (WAVES == 2) {
-      uint32_t par[2] = {0u, 0u};
-      for (int pw = 0; pw < num_phases * WAVES; ++pw) {
-        const int p = pw / WAVES, w = pw - p * WAVES;
-        bool mm; int kind, t;
-        phase_info(p, mm, kind, t);
-        if (!mm) continue;
-        ptx::mbar_wait(&pub_bar[w], par[w]);
-        par[w] ^= 1u;
-        if (lane == 0) {
-          if (w == 0) GRU_TRACE(p, 6);
-          // release only (no L1 invalidation): the consumers acquire on their side. The saved state (r, u, c, h) is
-          // stored AFTER this signal -- the epilogue threads wait for sig_bar -- so the membar has only the 8 - 16 KB
-          // operand tile to wait for, not 32 - 64 KB of scattered fp32 stores nobody on the critical path needs
-          asm volatile("fence.release.gpu;" ::: "memory");
-          ptx::fence_proxy_async_full();
-          if (w == 0) GRU_TRACE(p, 7);
-          red_relaxed_add(w == 0 ? counterw[0] : counterw[WAVES - 1], 1u);
-          if (w == 0) GRU_TRACE(p, 3);
-          ptx::mbar_arrive(&sig_bar[w]);
-        }
-        __syncwarp();
-      }
-    }
   } else {
     // ===================== epilogue warps: thread = (batch row, 8 units), for each wave =====================
     const int q = warp & 3;                          // TMEM lane quarter this warp may read
@@ -420,15 +464,16 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     const int srow = (q & 1) * 32 + lane;         // row inside the CTA's 64-row tile
     const int schunk = uhalf * 4 + sub;           // 16-byte chunk inside the 128-byte row of 64 units
     const int ucol = (slice32 >> 1) * 64;         // first unit of the pair
-    // operand tiles leave by TMA store only when one wave owns the ring between its phases
-    const bool tma_out = WAVES == 1 && g.tma_out != 0;
+    // operand tiles leave by TMA store when the staging buffer is free between a wave's phases: one wave owning the
+    // ring (staging inside it), or the dedicated per-wave buffers of SWAP
+    static_assert(WAVES == 1 || SWAP, "two waves need the dedicated staging buffers");
+    const bool tma_out = g.tma_out != 0;
     const bool priv_layout = g.priv_layout != 0;
-    // TMA-store staging: the A areas of ring stages 0 and 1 (idle between the last MMA of a phase and the next
-    // phase's first load, which waits for this CTA's own arrival below)
-    const uint32_t stg0 = ptx::smem_u32(ring), stg1 = ptx::smem_u32(ring + Q_A_TILE);   // both inside stage 0's activation area
+    // !SWAP: the A areas of ring stage 0 (idle between the last MMA of a phase and the next phase's first load, which
+    // waits for this CTA's own arrival below)
     int roww[WAVES], lenw[WAVES];
     bool okw[WAVES];
-    uint32_t tlanew[WAVES], tfullw[WAVES], sigparw[WAVES];
+    uint32_t tlanew[WAVES], tfullw[WAVES], stg0w[WAVES], stg1w[WAVES];
 #pragma unroll
     for (int w = 0; w < WAVES; ++w) {
       roww[w] = m0w[w] + (q & 1) * 32 + lane;
@@ -436,7 +481,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
       lenw[w] = okw[w] ? g.q_len[roww[w]] : 0;
       tlanew[w] = tmem_base + w * TM_WAVE + (static_cast<uint32_t>(q * 32) << 16) + sub * NU;
       tfullw[w] = 0;
-      sigparw[w] = 0;
+      stg0w[w] = SWAP ? ptx::smem_u32(stg + w * Q_STG_BYTES) : ptx::smem_u32(ring);
+      stg1w[w] = stg0w[w] + Q_A_TILE;
     }
     // fp32 state kept for BPTT (r, u, c, h_t): with full 64-row tiles it lives in a layout private to these two
     // kernels, [t][64-row tile][unit / 8][row % 64][unit % 8], in which the 32 bytes of the lanes of a warp are
@@ -451,18 +497,12 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
     // publish: CTA barrier, then ONE thread hands the staged tile(s) to the TMA, waits for the writes to be
     // performed, fences and releases the counter
     auto publish = [&](int p, int w, bool mm, const CUtensorMap* tm, int ntiles, int col1, long long grow, int m0, unsigned int* counter) {
-      if (WAVES == 2 && mm) {   // the publisher warp signals
-        if (leader && w == 0) GRU_TRACE(p, 5);
-        ptx::mbar_arrive(&pub_bar[w]);
-        ptx::mbar_wait(&sig_bar[w], sigparw[w]);
-        sigparw[w] ^= 1u;
-        return;
-      }
+      const uint32_t stg0 = stg0w[w], stg1 = stg1w[w];
       if (tma_out) ptx::fence_proxy_async();
-      if (leader && w == 0) GRU_TRACE(p, 5);
+      if (leader) GRU_TRACEW(w, p, 5);
       epi_bar_all();
       if (leader) {
-        if (w == 0) GRU_TRACE(p, 6);
+        GRU_TRACEW(w, p, 6);
         if (tma_out) {
           // The tile(s) leave through the async proxy and bulk_wait<0> returns once the writes are PERFORMED (at
           // L2, where the consumers' TMA loads read them), so the relaxed arrival below is ordered after them by
@@ -474,16 +514,19 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
             ptx::bulk_commit();
             ptx::bulk_wait<0>();
           }
-          if (w == 0) GRU_TRACE(p, 4);
+          GRU_TRACEW(w, p, 4);
         } else {
-          if (w == 0) GRU_TRACE(p, 4);
+          GRU_TRACEW(w, p, 4);
           asm volatile("fence.acq_rel.gpu;" ::: "memory");
           ptx::fence_proxy_async_full();
         }
-        if (w == 0) GRU_TRACE(p, 7);
+        GRU_TRACEW(w, p, 7);
         red_relaxed_add(counter, 1u);
-        if (w == 0) GRU_TRACE(p, 3);
+        GRU_TRACEW(w, p, 3);
       }
+      // phases without a matmul wait for nothing before their staging writes: hold everybody until the leader's store
+      // has left the staging buffer (only the first one or two phases of a launch)
+      if (!mm && tma_out) epi_bar_all();
     };
 
     if (MODE == 0) {
@@ -516,7 +559,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
               ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
               tfullw[w] ^= 1;
               ptx::tc_fence_after();
-              if (leader && w == 0) GRU_TRACE(p, 2);
+              if (leader) GRU_TRACEW(w, p, 2);
               tmem_ld8(tlanew[w], ar);
               tmem_ld8(tlanew[w] + 32, au);
               ptx::tc_fence_before();
@@ -529,7 +572,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
               rh[j] = sv[j] * h[j];
             }
             // the operand the other CTAs wait for goes out first; r / u (kept for BPTT) after the arrival
-            if (tma_out) stage8bf(stg0, srow, schunk, rh);
+            if (tma_out) stage8bf(stg0w[w], srow, schunk, rh);
             else if (row_ok) store8bf(g.rh_bf + (tb + row) * L + unit, rh);
           } else {
             float xc[NU], ac[NU];
@@ -540,7 +583,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
               ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
               tfullw[w] ^= 1;
               ptx::tc_fence_after();
-              if (leader && w == 0) GRU_TRACE(p, 2);
+              if (leader) GRU_TRACEW(w, p, 2);
               tmem_ld8(tlanew[w] + 64, ac);
               ptx::tc_fence_before();
             }
@@ -550,7 +593,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
               sv[j] = tanh_fast(ac[j] + xc[j]);
               h[j] = valid ? u[j] * h[j] + (1.0f - u[j]) * sv[j] : h[j];
             }
-            if (tma_out) stage8bf(stg0, srow, schunk, h);
+            if (tma_out) stage8bf(stg0w[w], srow, schunk, h);
             else if (row_ok) store8bf(g.h_bf + (tb + B + row) * L + unit, h);
           }
           // r.h is the operand of the candidate phase (tm_a1), h_{t+1} the operand of the next gate phase (tm_a0)
@@ -602,7 +645,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
             ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
             tfullw[w] ^= 1;
             ptx::tc_fence_after();
-            if (leader && w == 0) GRU_TRACE(p, 2);
+            if (leader) GRU_TRACEW(w, p, 2);
             tmem_ld8(tlanew[w], acc);
             ptx::tc_fence_before();
             float dgr[NU], dgu[NU];
@@ -626,8 +669,8 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
               }
             }
             if (tma_out) {
-              stage8bf(stg0, srow, schunk, dgr);
-              stage8bf(stg1, srow, schunk, dgu);
+              stage8bf(stg0w[w], srow, schunk, dgr);
+              stage8bf(stg1w[w], srow, schunk, dgu);
             }
             publish(p, w, mm, &tm_o0, 2, L + ucol, tb + m0, m0, counterw[w]);   // dG_t = [dG_r | dG_u]: operand of the next phase
           } else {
@@ -656,7 +699,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
               ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
               tfullw[w] ^= 1;
               ptx::tc_fence_after();
-              if (leader && w == 0) GRU_TRACE(p, 2);
+              if (leader) GRU_TRACEW(w, p, 2);
               tmem_ld8(tlanew[w], acc);
               ptx::tc_fence_before();
             }
@@ -674,7 +717,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
               for (int j = 0; j < NU; ++j) db_c[j] += dcv[j];
               if (!tma_out) store8bf(g.dC_bf + (tb + row) * L + unit, dcv);
             }
-            if (tma_out) stage8bf(stg0, srow, schunk, dcv);
+            if (tma_out) stage8bf(stg0w[w], srow, schunk, dcv);
             publish(p, w, mm, &tm_o1, 1, 0, tb + m0, m0, counterw[w]);          // dC_{t-1}: operand of the next phase
           }
         }
@@ -725,11 +768,11 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
   }
 }
 
-template <int MODE, int WAVES>
+template <int MODE, int WAVES, bool SWAP>
 cudaError_t launch_pair_gru(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
                             const CUtensorMap& o0, const CUtensorMap& o1, PairGruArgs& a, dim3 grid, int smem,
                             cudaStream_t s) {
-  auto kern = gru_pair_kernel<MODE, WAVES>;
+  auto kern = gru_pair_kernel<MODE, WAVES, SWAP>;
   static int smem_set = 0;
   if (smem_set < smem) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
@@ -770,7 +813,7 @@ extern "C" __attribute__((visibility("default"))) void vqa_internal_set_gru_pair
 bool gru_pair_supported(int B, int L, int num_sms) {
   if (g_pair_off) return false;
   if (L % 64 != 0 || L < 64) return false;
-  if (q_smem_bytes(L) > 227 * 1024) return false;
+  if (q_smem_bytes(L) > 227 * 1024 || q_smem_bytes(L, true, 2) > 227 * 1024) return false;
   (void)B;   // any batch: row tiles beyond one co-resident wave run as consecutive launches (launch_chunks)
   return L / Q_UNITS <= num_sms;
 }
@@ -785,9 +828,12 @@ int g_waves_mode = getenv("VQA_GRU_WAVES") ? atoi(getenv("VQA_GRU_WAVES")) : 0;
 // testing aid (not part of the ABI header): the VQA_GRU_WAVES policy at run time
 extern "C" __attribute__((visibility("default"))) void vqa_internal_set_gru_waves(int mode) { g_waves_mode = mode; }
 
+// w0 / w1: weight maps of the single-wave kernels (larger matrix resident); sw0 / sw1: those of the two-wave kernels
+// (smaller matrix resident, the larger one streamed in k-block boxes)
 template <int MODE>
 cudaError_t launch_chunks(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w0, const CUtensorMap& w1,
-                          const CUtensorMap& o0, const CUtensorMap& o1, PairGruArgs& g, int num_sms, cudaStream_t s) {
+                          const CUtensorMap& sw0, const CUtensorMap& sw1, const CUtensorMap& o0, const CUtensorMap& o1,
+                          PairGruArgs& g, int num_sms, cudaStream_t s) {
   const int slices = g.L / Q_UNITS;
   int tiles_max = num_sms / slices;
   if (tiles_max > 16) tiles_max = 16;   // counters: [2 waves][tiles][2 ranks] of a 64-entry array
@@ -808,8 +854,10 @@ cudaError_t launch_chunks(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     if (e != cudaSuccess) return e;
     g.row0 = row0;
     g.wave_rows = tiles * 128;
-    e = waves == 2 ? launch_pair_gru<MODE, 2>(a0, a1, w0, w1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L), s)
-                   : launch_pair_gru<MODE, 1>(a0, a1, w0, w1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L), s);
+    static const bool swap1 = getenv("VQA_GRU_SWAP1") != nullptr && atoi(getenv("VQA_GRU_SWAP1")) != 0;   // experiment
+    e = waves == 2 ? launch_pair_gru<MODE, 2, true>(a0, a1, sw0, sw1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L, true, 2), s)
+        : swap1    ? launch_pair_gru<MODE, 1, true>(a0, a1, sw0, sw1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L, true, 1), s)
+                   : launch_pair_gru<MODE, 1, false>(a0, a1, w0, w1, o0, o1, g, dim3(slices, tiles), q_smem_bytes(g.L), s);
     if (e != cudaSuccess) return e;
     if (!first) count_launch();   // (the caller counts the first)
     first = false;
@@ -821,12 +869,13 @@ cudaError_t launch_chunks(const CUtensorMap& a0, const CUtensorMap& a1, const CU
 // returns cudaSuccess, or the launch error (the caller falls back to the single-CTA kernels)
 cudaError_t gru_pair_fwd(const GruFwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
-  CUtensorMap tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h;
+  CUtensorMap tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h, sw_wg, sw_wc;
   const uint64_t prow = static_cast<uint64_t>(L / 32) * 96;
   const int kbs = pick_kbs(L);
   if (!cached_tmap_kblocks(&tm_h, a.h_bf, L, static_cast<uint64_t>(T + 1) * B, L, Q_ROWS, kbs) ||
       !cached_tmap_kblocks(&tm_rh, a.rh_bf, L, static_cast<uint64_t>(T) * B, L, Q_ROWS, kbs) ||
       !cached_tmap(&tm_wg, a.w_pack, L, prow, L, 64, 64) || !cached_tmap_kblocks(&tm_wc, a.w_pack, L, prow, L, 32, kbs) ||
+      !cached_tmap_kblocks(&sw_wg, a.w_pack, L, prow, L, 64, kbs) || !cached_tmap(&sw_wc, a.w_pack, L, prow, L, 64, 32) ||
       !cached_tmap(&to_rh, a.rh_bf, L, static_cast<uint64_t>(T) * B, L, 64, Q_ROWS) ||
       !cached_tmap(&to_h, a.h_bf, L, static_cast<uint64_t>(T + 1) * B, L, 64, Q_ROWS))
     return cudaErrorInvalidValue;
@@ -837,16 +886,17 @@ cudaError_t gru_pair_fwd(const GruFwdPersistent& a, int num_sms, cudaStream_t s)
   g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
   g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;
   g.kbs = kbs;
-  return launch_chunks<0>(tm_h, tm_rh, tm_wg, tm_wc, to_rh, to_h, g, num_sms, s);
+  return launch_chunks<0>(tm_h, tm_rh, tm_wg, tm_wc, sw_wg, sw_wc, to_rh, to_h, g, num_sms, s);
 }
 
 cudaError_t gru_pair_bwd(const GruBwdPersistent& a, int num_sms, cudaStream_t s) {
   const int B = a.B, L = a.L, T = a.T;
-  CUtensorMap tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc;
+  CUtensorMap tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc, sw_wc, sw_wg;
   const int kbs = pick_kbs(L);
   if (!cached_tmap_kblocks(&tm_dc, a.dC_bf, L, static_cast<uint64_t>(T) * B, L, Q_ROWS, kbs) ||
       !cached_tmap_kblocks(&tm_dg, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B, 2 * L, Q_ROWS, kbs) ||
       !cached_tmap_kblocks(&tm_wc, a.wc_h, L, L, L, 32, kbs) || !cached_tmap(&tm_wg, a.wg_h, 2 * L, L, 2 * L, 64, 32) ||
+      !cached_tmap(&sw_wc, a.wc_h, L, L, L, 64, 32) || !cached_tmap_kblocks(&sw_wg, a.wg_h, 2 * L, L, 2 * L, 32, kbs) ||
       !cached_tmap(&to_dg, a.dG_bf, 2 * L, static_cast<uint64_t>(T) * B, 2 * L, 64, Q_ROWS) ||
       !cached_tmap(&to_dc, a.dC_bf, L, static_cast<uint64_t>(T) * B, L, 64, Q_ROWS))
     return cudaErrorInvalidValue;
@@ -858,7 +908,7 @@ cudaError_t gru_pair_bwd(const GruBwdPersistent& a, int num_sms, cudaStream_t s)
   g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
   g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;
   g.kbs = kbs;
-  return launch_chunks<1>(tm_dc, tm_dg, tm_wc, tm_wg, to_dg, to_dc, g, num_sms, s);
+  return launch_chunks<1>(tm_dc, tm_dg, tm_wc, tm_wg, sw_wc, sw_wg, to_dg, to_dc, g, num_sms, s);
 }
 
 }  // namespace vqa
