@@ -59,3 +59,57 @@ w2 = time.perf_counter()
 print(f"host enqueue {1e3 * (w1 - w0) / N:.3f} ms/step; device {e0.elapsed_time(e1) / N:.3f} ms/step; "
       f"wall incl. drain {1e3 * (w2 - w0) / N:.3f} ms/step; launches/step {eng.launch_count() // 110}")
 print("host per call (ms):", {k: round(1e3 * v / N, 3) for k, v in T.items()})
+
+# ---- the end-to-end loop of bench.py (pinned host batches, next-batch prefetch, loss read back two steps later) ----
+pinned = [{k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in b.items()
+           if k in ("image_idx", "q_intseq", "q_intseq_len", "answer_target")} for b in hb]
+pending = []
+for i in range(8):
+    p, _, _ = model.train_step(pinned[i % 4], next_batch=pinned[(i + 1) % 4], sync=False)
+    pending.append(p)
+for p in pending:
+    p.get()
+torch.cuda.synchronize()
+pending = []
+t_step = t_get = 0.0
+e0.record()
+w0 = time.perf_counter()
+for i in range(N):
+    a = time.perf_counter()
+    p, _, _ = model.train_step(pinned[i % 4], next_batch=pinned[(i + 1) % 4], sync=False)
+    b = time.perf_counter()
+    pending.append(p)
+    if len(pending) > 2:
+        pending.pop(0).get()
+    c2 = time.perf_counter()
+    t_step += b - a
+    t_get += c2 - b
+e1.record()
+w1 = time.perf_counter()
+torch.cuda.synchronize()
+print(f"e2e loop: host {1e3 * (w1 - w0) / N:.3f} ms/step (train_step call {1e3 * t_step / N:.3f}, loss get {1e3 * t_get / N:.3f}); "
+      f"device {e0.elapsed_time(e1) / N:.3f} ms/step")
+
+
+def loop(name, batches, nxt=True, get=True, sync_each=False):
+    pend = []
+    for i in range(6):
+        p, _, _ = model.train_step(batches[i % 4], next_batch=batches[(i + 1) % 4] if nxt else None, sync=False)
+    torch.cuda.synchronize()
+    e0.record()
+    for i in range(N):
+        p, _, _ = model.train_step(batches[i % 4], next_batch=batches[(i + 1) % 4] if nxt else None, sync=False)
+        pend.append(p)
+        if get and len(pend) > 2:
+            pend.pop(0).get()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"{name}: device {e0.elapsed_time(e1) / N:.3f} ms/step")
+
+
+loop("pinned + prefetch + get", pinned)
+loop("pinned + prefetch, no get", pinned, get=False)
+loop("pinned, no prefetch, no get", pinned, nxt=False, get=False)
+loop("device batches + prefetch + get", db)
+loop("device batches + prefetch, no get", db, get=False)
+loop("device batches, no prefetch, no get", db, nxt=False, get=False)

@@ -91,7 +91,7 @@ LAYOUTS = [(False, False), (False, True), (True, False), (True, True)]
 
 @pytest.mark.parametrize("a_mn,b_mn", LAYOUTS)
 @pytest.mark.parametrize("shape", [(128, 128, 64), (256, 256, 256), (512, 1024, 1024), (300, 200, 300),
-                                   (130, 3000, 520)])
+                                   (130, 3000, 520), (512, 2048, 3000), (200, 320, 456)])   # K = 3000 / 456: partial last k-block
 def test_gemm_bf16_layouts(handle, shape, a_mn, b_mn):
     lib, h = handle
     M, N, K = shape

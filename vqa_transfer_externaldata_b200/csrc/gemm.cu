@@ -123,14 +123,23 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         const int k0 = kb * BK;
         if (ptx::elect_one()) {
-        ptx::mbar_arrive_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+        // K-major operands whose K is not a multiple of 64 (the answer dimension, 3000): the k-block boxes cannot clip
+        // inside a k-block, so the group that holds the partial k-block arrives as per-k-block 2-D boxes (whose inner
+        // extent is K: the tail is zero-filled); k-blocks beyond the last are neither loaded nor multiplied
+        const bool tail = KBS > 1 && (K % BK) != 0 && kb + KBS > K / BK;
+        const int nblk = num_kb - kb < KBS ? num_kb - kb : KBS;
+        const uint32_t bytes_a = (!A_MN && tail) ? nblk * Cfg::A_TILE : KBS * Cfg::A_TILE;
+        const uint32_t bytes_b = (!B_MN && tail) ? nblk * Cfg::B_TILE : KBS * Cfg::B_TILE;
+        ptx::mbar_arrive_expect_tx(&full_bar[stage], KBS > 1 ? bytes_a + bytes_b : Cfg::STAGE_BYTES);
         if (KBS > 1) {
           uint8_t* sa = st;
           uint8_t* sb = st + KBS * Cfg::A_TILE;
           if (A_MN) ptx::tma_load_4d(sa, &tm_a_lo, &full_bar[stage], 0, 0, m0 >> 6, kb);
-          else ptx::tma_load_3d(sa, &tm_a_lo, &full_bar[stage], 0, m0, kb);
+          else if (!tail) ptx::tma_load_3d(sa, &tm_a_lo, &full_bar[stage], 0, m0, kb);
+          else for (int i = 0; i < nblk; ++i) ptx::tma_load_2d(sa + i * Cfg::A_TILE, &tm_a_hi, &full_bar[stage], k0 + i * BK, m0);
           if (B_MN) ptx::tma_load_4d(sb, &tm_b_lo, &full_bar[stage], 0, 0, n0 >> 6, kb);
-          else ptx::tma_load_3d(sb, &tm_b_lo, &full_bar[stage], 0, n0, kb);
+          else if (!tail) ptx::tma_load_3d(sb, &tm_b_lo, &full_bar[stage], 0, n0, kb);
+          else for (int i = 0; i < nblk; ++i) ptx::tma_load_2d(sb + i * Cfg::B_TILE, &tm_b_hi, &full_bar[stage], k0 + i * BK, n0);
         } else
 #pragma unroll
         for (int p = 0; p < Cfg::PLANES; ++p) {
@@ -180,6 +189,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
         if (ptx::elect_one()) {
 #pragma unroll
         for (int i = 0; i < KBS; ++i) {
+        if (KBS > 1 && kb + i >= num_kb) break;   // (a partial last group: nothing was loaded beyond the last k-block)
         const uint32_t sa_hi = st + i * Cfg::A_TILE, sa_lo = st + Cfg::A_TILE;
         const uint32_t sb_hi = st + KBS * Cfg::PLANES * Cfg::A_TILE + i * Cfg::B_TILE, sb_lo = sb_hi + Cfg::B_TILE;
 #pragma unroll
@@ -516,6 +526,13 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, Ge
   const bool split = (d.a_lo != nullptr) || (d.b_lo != nullptr);
   if (split && (!d.a_lo || !d.b_lo))
     return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: split precision needs both lo planes");
+  static const int m512_bn = getenv("VQA_M512_BN") ? atoi(getenv("VQA_M512_BN")) : 0;   // experiment: head GEMMs on the pair kernel
+  if (m512_bn < 0 && d.block_n == 0 && !split && d.M >= 256 && d.M <= 512 && d.out_f32 && !d.out_hi && d.K >= 1024 && d.N >= 512) {
+    VqaGemmDesc f = d;
+    f.block_n = m512_bn;
+    int pbn = 0, psplits = 1;
+    if (gemm_pair_plan(f, num_sms, ctx, narrow, &pbn, &psplits)) return gemm_pair_launch(f, num_sms, pbn, psplits, ctx, stream);
+  }
   if (d.block_n <= 0) {
     int pbn = 0, psplits = 1;
     if (gemm_pair_plan(d, num_sms, ctx, narrow, &pbn, &psplits)) return gemm_pair_launch(d, num_sms, pbn, psplits, ctx, stream);
@@ -527,7 +544,7 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, Ge
   // 128 x 64 tiles, 2 with 128 x 128 tiles when 64-wide tiles would need a second wave
   static const bool big_off = getenv("VQA_GEMM_SMALL_BOXES") != nullptr;
   int kbs = 1;
-  if (!split && !d.block_n && !big_off && (d.K % 64) == 0 && d.K >= 256) {
+  if (!split && !d.block_n && !big_off && d.K >= 256 && ((d.K % 64) == 0 || (!d.a_mn_major && !d.b_mn_major))) {
     const long long tm = (d.M + BM - 1) / BM;
     const long long t64 = tm * ((d.N + 63) / 64), t128 = tm * ((d.N + 127) / 128);
     if (t64 <= num_sms) { bn = 64; kbs = 4; }

@@ -51,6 +51,7 @@ struct GemmB {  // builder with the conventions of VqaGemmDesc
   }
   int narrow_ = 0;
   GemmB& narrow() { narrow_ = 1; return *this; }
+  GemmB& bn(int block_n) { d.block_n = block_n; return *this; }   // VqaGemmDesc.block_n: 0 auto, 64 / 128 / 256, -128 / -256 pair
   VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s, &h->gemm_ctx, narrow_); }
 };
 
@@ -1015,10 +1016,11 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     auto embed_bwd = [&](cudaStream_t st) -> VqaStatus {
       if (g->embed) {
         // dE = dG Wg[:W]^T + dC Wc[:W]^T ; d embed = scatter_add(q_intseq, dE)
+        static const int de_bn = getenv("VQA_DE_BN") ? atoi(getenv("VQA_DE_BN")) : 0;
         VQA_TRY(GemmB(TB, W, 2 * L).a(b.dG, 0, 2 * L, false).b(b.w.gru_gates_w, 0, 2 * L, false)
-                    .f32(b.dE, Wp).run(h, st));
+                    .f32(b.dE, Wp).bn(de_bn).run(h, st));
         VQA_TRY(GemmB(TB, W, L).a(b.dC, 0, L, false).b(b.w.gru_cand_w, 0, L, false).addend(b.dE, Wp)
-                    .f32(b.dE, Wp).run(h, st));
+                    .f32(b.dE, Wp).bn(de_bn).run(h, st));
         // what clip_ops.global_norm sees for an IndexedSlices gradient: its rows as they are (vqa_set_embedding_slice_norm)
         if (h->slice_slot)
           VQA_TRY(rows_sumsq_launch(b.dE, TB, W, Wp, h->slice_slot, b.scratch + 5 * b.scratch_floats, st));   // auxiliary stream 4's scratch region: its gather uses none

@@ -134,12 +134,21 @@ __global__ void __launch_bounds__(OPT_THREADS) rows_sumsq_partial_kernel(const f
   __shared__ float red[OPT_THREADS / 32];
   pdl_sync();
   float acc = 0.f;
-  const long long total = rows * cols;
-  for (long long i = blockIdx.x * static_cast<long long>(OPT_THREADS) + threadIdx.x; i < total;
-       i += static_cast<long long>(gridDim.x) * OPT_THREADS) {
-    const long long r = i / cols;
-    const float v = x[r * ld + (i - r * cols)];
-    acc = fmaf(v, v, acc);
+  // a warp per row, lanes across the columns (no per-element division: the first version spent 35 us on 2 M elements)
+  const int lane = threadIdx.x & 31;
+  const long long warp0 = blockIdx.x * static_cast<long long>(OPT_THREADS / 32) + (threadIdx.x >> 5);
+  const long long nwarps = static_cast<long long>(gridDim.x) * (OPT_THREADS / 32);
+  const bool vec = (cols & 3) == 0 && (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+  for (long long r = warp0; r < rows; r += nwarps) {
+    const float* row = x + r * ld;
+    if (vec) {
+      for (int c = lane * 4; c < cols; c += 128) {
+        const float4 v = *reinterpret_cast<const float4*>(row + c);
+        acc = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, acc))));
+      }
+    } else {
+      for (int c = lane; c < cols; c += 32) acc = fmaf(row[c], row[c], acc);
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
