@@ -69,6 +69,13 @@ VQA_API VqaStatus vqa_ops_slab_ln_bwd(VqaOps ops, const VqaSlabLn* a, void* stre
 VQA_API VqaStatus vqa_ops_pad_planes(const float* src, int64_t rows, int32_t cols, int32_t boxes, void* hi, void* lo,
                                      int32_t ld_out, void* stream);
 
+/* Weight gradient of a layer with F <= 8 input features (spat_v_linear_v / spat_q_linear_v: the 6-d box features):
+ * out[f, c] = sum over rows of feat[r, f] * dz[r, c]; dz as operand planes [rows, N]. boxes != 0: feat is [rows, 4] normalised
+ * boxes and the six features are derived as in vqa_ops_pad_planes. part: scratch [max_parts, F, N] (per-CTA partial sums,
+ * reduced in fixed order). F * N <= 8192. */
+VQA_API VqaStatus vqa_ops_feat_wgrad(VqaOps ops, const float* feat, int32_t F, int32_t boxes, const void* dz_hi, const void* dz_lo,
+                                     int64_t rows, int32_t N, float* part, int32_t max_parts, float* out, void* stream);
+
 /* Spatial Hadamard attention + attended pooling for the n entries of each image and kind (:323-365, :413-455;
  * vlmap/modules.py:67-97, 23-39): score[e, k] = sum_d Hv[b, k, d] Hq[e, d] w[d] keep[e, k, d] / keep_att + bias, -inf
  * beyond num_boxes[b], softmax over k, pooled[e] = sum_k att[e, k] V[b, k, :]. V is read once per image and kind, not

@@ -857,6 +857,44 @@ __global__ void wordset_bwd_kernel(const float* __restrict__ dy, const float* __
   }
 }
 
+// Weight gradient of a layer whose input has F <= 8 features (the 6-d box features): out[f, c] = sum_r feat[r, f] dz[r, c].
+// As a tensor-core GEMM this is one 64-row tile with K = rows (18432): 16 CTAs walking 288 k-blocks, 70 us. Here every
+// CTA takes a slice of rows, a thread four columns; per-CTA partials [ctas, F, N] are summed in fixed order afterwards.
+constexpr int FW_THREADS = 256;
+__global__ void __launch_bounds__(FW_THREADS) feat_wgrad_kernel(const float* __restrict__ feat, int F, int boxes,
+                                                                const bf16* __restrict__ dz_hi, const bf16* __restrict__ dz_lo,
+                                                                long long rows, int N, float* __restrict__ part) {
+  const long long per = (rows + gridDim.x - 1) / gridDim.x;
+  const long long r0 = blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+  for (int c = threadIdx.x * 4; c < N; c += FW_THREADS * 4) {
+    float acc[8][4];
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[f][j] = 0.f;
+    for (long long r = r0; r < r1; ++r) {
+      float x[8];
+      if (boxes) {   // (x0, y0, x1, y1, x1 - x0, y1 - y0) of a normalised box
+        const float4 b = *reinterpret_cast<const float4*>(feat + r * 4);
+        x[0] = b.x; x[1] = b.y; x[2] = b.z; x[3] = b.w; x[4] = b.z - b.x; x[5] = b.w - b.y; x[6] = x[7] = 0.f;
+      } else {
+#pragma unroll
+        for (int f = 0; f < 8; ++f) x[f] = f < F ? feat[r * F + f] : 0.f;
+      }
+      float d[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) d[j] = ld_planes(dz_hi, dz_lo, r * N + c + j);
+#pragma unroll
+      for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[f][j] = fmaf(x[f], d[j], acc[f][j]);
+    }
+    for (int f = 0; f < F; ++f)
+      *reinterpret_cast<float4*>(part + (static_cast<long long>(blockIdx.x) * F + f) * N + c) =
+          make_float4(acc[f][0], acc[f][1], acc[f][2], acc[f][3]);
+  }
+}
+
 template <typename Kern>
 VqaStatus ensure_smem(Kern kern, size_t bytes, const char* what) {
   if (bytes > 48 * 1024) {
@@ -1100,6 +1138,21 @@ VQA_API VqaStatus vqa_ops_pad_planes(const float* src, int64_t rows, int32_t col
       src, rows, cols, boxes, static_cast<bf16*>(hi), static_cast<bf16*>(lo), ld_out);
   VQA_LAUNCH_CHECK("pad_planes");
   return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_ops_feat_wgrad(VqaOps ops, const float* feat, int32_t F, int32_t boxes, const void* dz_hi, const void* dz_lo,
+                                     int64_t rows, int32_t N, float* part, int32_t max_parts, float* out, void* stream) {
+  if (!ops || !feat || !dz_hi || !part || !out || rows < 0 || N <= 0 || (N & 3) || F <= 0 || F > 8 || max_parts <= 0 ||
+      static_cast<long long>(F) * N > 8192 || (boxes && F != 6))
+    return set_error(VQA_ERR_BAD_ARG, "vqa_ops_feat_wgrad: bad argument (F <= 8, N a multiple of 4, F * N <= 8192)");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int ctas = ops->num_sms * 2;
+  if (ctas > max_parts) ctas = max_parts;
+  if (ctas > rows) ctas = rows > 0 ? static_cast<int>(rows) : 1;
+  feat_wgrad_kernel<<<ctas, FW_THREADS, 0, s>>>(feat, F, boxes, static_cast<const bf16*>(dz_hi), static_cast<const bf16*>(dz_lo),
+                                                 rows, N, part);
+  VQA_LAUNCH_CHECK("feat_wgrad");
+  return colsum_launch(part, ctas, static_cast<long long>(F) * N, static_cast<long long>(F) * N, out, ops->scratch, s);
 }
 
 static VqaStatus check_spat(const VqaSpatAttn* a, const char* who) {

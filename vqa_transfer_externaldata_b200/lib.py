@@ -234,6 +234,7 @@ MEMFT_SYMBOLS = {
     "vqa_ops_slab_ln_fwd": (C.c_int32, [_P, C.POINTER(VqaSlabLn), _P]),
     "vqa_ops_slab_ln_bwd": (C.c_int32, [_P, C.POINTER(VqaSlabLn), _P]),
     "vqa_ops_pad_planes": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P]),
+    "vqa_ops_feat_wgrad": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]),
     "vqa_memft_spat_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaSpatAttn), _P]),
     "vqa_memft_spat_attn_bwd": (C.c_int32, [_P, C.POINTER(VqaSpatAttn), _P]),
     "vqa_memft_softmax_ce": (C.c_int32, [_P, C.POINTER(VqaSoftmaxCe), _P]),

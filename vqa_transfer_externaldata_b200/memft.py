@@ -164,7 +164,7 @@ class Model:
         b.dzq, b.part_q = P(E, D), f(2 * B, 3 * D)
         b.dzv, b.part_v = P(B * K, D), f(B, 3 * D)
         b.sum3 = f(3 * max(2 * L_, D) + 64)
-        b.tmp64 = f(64, D)
+        b.fw_part = f(296, 6 * D)
         # GRU sequence operator
         self._gru = L.VqaGruSeq(B=E, T=c.T, L=L_, W=W, Vq=c.Vq, precision=L.PREC_FP32 if fp32 else L.PREC_BF16)
         nbytes = C.c_uint64()
@@ -447,13 +447,15 @@ class Model:
         g["att_b"].copy_(sums[D:D + 1])
         self._slab(2 * B, n, D, b.zq, p["sq_gamma"], p["sq_beta"], b.mean_q, b.rstd_q, dout=b.d_hq, dz=b.dzq, part=b.part_q, bwd=True)
         self._ln_param_grads(b.part_q, 2 * B, D, g["sq_gamma"], g["sq_beta"], g["sq_b"])
-        self._gemm(64, D, E, b.key_p, True, b.dzq, True, out=b.tmp64)
-        g["sq_w"].copy_(b.tmp64[:6])
+        hi, lo = b.dzq.ptr()
+        L.check(self.lib.vqa_ops_feat_wgrad(self.ops, _p(d.boxes), 6, 1, C.c_void_p(hi), C.c_void_p(lo), E, D, _p(b.fw_part),
+                                            b.fw_part.shape[0], _p(g["sq_w"]), s))
         self._slab(B, K, D, b.zv, p["sv_gamma"], p["sv_beta"], b.mean_v, b.rstd_v, dout=b.d_hv[:B * K], dout2=b.d_hv[B * K:],
                    dz=b.dzv, part=b.part_v, bwd=True)
         self._ln_param_grads(b.part_v, B, D, g["sv_gamma"], g["sv_beta"], g["sv_b"])
-        self._gemm(64, D, B * K, b.spat_p, True, b.dzv, True, out=b.tmp64)
-        g["sv_w"].copy_(b.tmp64[:6])
+        hi, lo = b.dzv.ptr()
+        L.check(self.lib.vqa_ops_feat_wgrad(self.ops, _p(d.spatial_ft), 6, 0, C.c_void_p(hi), C.c_void_p(lo), B * K, D, _p(b.fw_part),
+                                            b.fw_part.shape[0], _p(g["sv_w"]), s))
 
     def adam_step(self, lr=None, clip_norm=20.0, beta1=0.9, beta2=0.999, eps=1e-8):
         lr = self.config.learning_rate if lr is None else lr
