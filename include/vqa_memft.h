@@ -95,6 +95,8 @@ typedef struct VqaSpatAttn {
   float* d_hv;                             /* [kinds, B, K, D]: one plane per kind (summed over the kind's entries) */
   float* d_hq;                             /* [kinds * B * n, D] */
   float* part;                             /* [kinds * B, D + 8] partials per image and kind: d att_w [D] | d att_b (slot D) */
+  uint8_t* keep_bits;                      /* optional [kinds * B * n * K * D / 8]: the forward pass leaves the keep bits of
+                                            * every group of 8 feature columns here, the backward pass reads them back */
 } VqaSpatAttn;
 VQA_API VqaStatus vqa_memft_spat_attn_fwd(VqaOps ops, const VqaSpatAttn* a, void* stream);
 VQA_API VqaStatus vqa_memft_spat_attn_bwd(VqaOps ops, const VqaSpatAttn* a, void* stream);

@@ -530,6 +530,8 @@ __global__ void __launch_bounds__(256, 3) spat_attn_fwd_kernel(const VqaSpatAttn
               const unsigned long long group =
                   ((static_cast<unsigned long long>(b) * n + e) * K + k) * (D / 8) + d8;
               bits = philox_keep_bits(philox4x32_10(group, a.site0 + kind, a.seed, a.step), thr);
+              // the backward pass reads the byte back instead of drawing again (a draw is ~150 integer instructions)
+              if (a.keep_bits) a.keep_bits[static_cast<unsigned long long>(kind) * B * n * K * (D / 8) + group] = static_cast<uint8_t>(bits);
             }
             const float* hq = hq_s + e * D + d8 * 8;
             float t = 0.f;
@@ -694,7 +696,9 @@ __global__ void __launch_bounds__(256, 2) spat_attn_bwd_kernel(const VqaSpatAttn
               if (thr < 65536u) {
                 const unsigned long long group =
                     ((static_cast<unsigned long long>(b) * n + e) * K + k) * (D / 8) + (d0 >> 3);
-                bits = (philox_keep_bits(philox4x32_10(group, a.site0 + kind, a.seed, a.step), thr) >> (d0 & 4)) & 0xFu;
+                const uint32_t all = a.keep_bits ? a.keep_bits[static_cast<unsigned long long>(kind) * B * n * K * (D / 8) + group]
+                                                 : philox_keep_bits(philox4x32_10(group, a.site0 + kind, a.seed, a.step), thr);
+                bits = (all >> (d0 & 4)) & 0xFu;
               }
               const float dsv = ds[e * K + k] * inv_keep;
               const float* hq = hq_s + e * D + d0;

@@ -203,7 +203,8 @@ class VqaSpatAttn(C.Structure):
                 ("att_w", C.c_void_p), ("att_b", C.c_void_p), ("num_boxes", C.c_void_p), ("v", C.c_void_p),
                 ("keep", C.c_float), ("seed", C.c_uint64), ("step", C.c_uint64), ("site0", C.c_uint32),
                 ("att", C.c_void_p), ("pooled", C.c_void_p), ("pooled_hi", C.c_void_p), ("pooled_lo", C.c_void_p),
-                ("d_pooled", C.c_void_p), ("d_hv", C.c_void_p), ("d_hq", C.c_void_p), ("part", C.c_void_p)]
+                ("d_pooled", C.c_void_p), ("d_hv", C.c_void_p), ("d_hq", C.c_void_p), ("part", C.c_void_p),
+                ("keep_bits", C.c_void_p)]
 
 
 class VqaSoftmaxCe(C.Structure):

@@ -13,6 +13,7 @@ share every variable (tf.AUTO_REUSE), so each layer is ONE GEMM over all its row
 per kind and shared by the blank-fill and wordset heads (the reference evaluates it twice on the same input).
 """
 import ctypes as C
+import os
 from types import SimpleNamespace
 
 import numpy as np
@@ -161,6 +162,11 @@ class Model:
         b.dzws, b.part_ws, b.dws_y = P(E, L_), f(2 * B, 3 * L_), f(E, W)
         b.dzp, b.part_p, b.dpooled = P(E, L_), f(2 * B, 3 * L_), f(E, Dv)
         b.d_hv, b.d_hq, b.part_att = f(2 * B * K, D), f(E, D), f(2 * B, D + 8)
+        # keep bits of the attention dropout stored by the forward pass for the backward pass: measured SLOWER than drawing
+        # them again (backward 2.92 -> 3.06 ms at cfg4: the kernels are latency-bound with idle ALUs, a dependent byte load
+        # per 8 elements is not free), so off unless VQA_MEMFT_KEEP_BITS=1
+        self.store_keep_bits = os.environ.get("VQA_MEMFT_KEEP_BITS") == "1" and c.keep_att < 1.0
+        b.att_bits = torch.zeros(E * K * (D // 8) if self.store_keep_bits else 8, dtype=torch.uint8, device=dev)
         b.dzq, b.part_q = P(E, D), f(2 * B, 3 * D)
         b.dzv, b.part_v = P(B * K, D), f(B, 3 * D)
         b.sum3 = f(3 * max(2 * L_, D) + 64)
@@ -333,7 +339,7 @@ class Model:
                              num_boxes=d.num_boxes.data_ptr(), v=d.image_ft.data_ptr(), keep=c.keep_att, seed=self.seed,
                              step=step, site0=SITE_ATT0, att=b.att.data_ptr(), pooled=b.pooled.data_ptr(), pooled_hi=p_hi,
                              pooled_lo=p_lo, d_pooled=b.dpooled.data_ptr(), d_hv=b.d_hv.data_ptr(), d_hq=b.d_hq.data_ptr(),
-                             part=b.part_att.data_ptr())
+                             part=b.part_att.data_ptr(), keep_bits=b.att_bits.data_ptr() if self.store_keep_bits else None)
 
     # ---- the graph ---------------------------------------------------------------------------------------------------
     def forward(self, batch=None, dropout_step=None, with_grad_seed=None):
