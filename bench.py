@@ -601,7 +601,7 @@ def run_ours(args):
         eng.forward(seed=model.seed + 7919 * rk, step=model.global_step, full_outputs=False, defer_outputs=True)
         eng.prefetch_batch(dev_batches[(i + 1) % R])
         model.backward()
-        eng.adam_step(lr=1e-3, clip_norm=20.0)
+        eng.adam_step(lr=1e-3, clip_norm=20.0, pipelined_tail=True)   # as Model.train_step does
         model.global_step += 1
 
     def timed(fn, steps):

@@ -401,6 +401,15 @@ VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* params, f
                                          float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                                          float eps, float clip_norm, int64_t t, float* grad_norm_out, void* stream);
 
+/* Pipelined optimizer tail: with tail_begin > 0, vqa_adam_step_shadowed updates parameters [tail_begin, n) of the flat
+ * buffer (the embedding and the GRU: ParamStore lays them out last) on an auxiliary stream, so the next vqa_forward's
+ * first kernels -- which read only the head of the buffer -- start while the tail is still being updated; that forward's
+ * embedding / x-projection branch and its recurrent kernel wait for the tail. 0 switches it off (default). Any OTHER
+ * reader of the parameters between the optimizer step and the next vqa_forward must first call vqa_sync_params(h, stream),
+ * which makes `stream` wait for the tail (vqa/trainer.py:106-114 applies the update inside the same session.run). */
+VQA_API VqaStatus vqa_set_optimizer_tail(VqaHandle h, int64_t tail_begin);
+VQA_API VqaStatus vqa_sync_params(VqaHandle h, void* stream);
+
 /* How the reference's clip_by_global_norm(20.0) sees the embedding gradient: tf.nn.embedding_lookup on a variable yields
  * an IndexedSlices (one row per token occurrence), and clip_ops.global_norm takes its `.values` as they are, so
  * LearnGloVe/embed_map contributes sum_{b,t} |dE[b,t]|^2 -- not the norm of the scattered dense gradient (they differ

@@ -133,3 +133,25 @@ def test_checkpoint_bundle_round_trip(tmp_path):
     a = m1.output["logit"].clone()
     m1.forward(batch)
     assert not torch.equal(a, m1.output["logit"])
+
+
+def test_pipelined_optimizer_tail_is_bit_identical(monkeypatch):
+    """Model.train_step updates the embedding / GRU slice of the parameters on an auxiliary stream, under the first
+    kernels of the next forward (vqa_set_optimizer_tail). Three steps with and without it must leave identical
+    parameters, Adam moments and losses (bit for bit, except the moments of the atomically scattered embedding gradient)."""
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("VQA_ADAM_TAIL", mode)
+        config, feats, batch, _ = make_synthetic_config(SMALL, variant="vlmap_answer", precision="bf16", seed=9, num_images=16)
+        model = importer.get_model_class("vlmap_answer")(batch, config, is_train=True, image_features=feats)
+        losses = [model.train_step()[0] for _ in range(3)]
+        res[mode] = (losses, model.state_dict(), model.optimizer_state_dict())
+    assert res["1"][0] == res["0"][0]
+    for k, v in res["0"][1].items():
+        assert np.array_equal(res["1"][1][k], v), k
+    for k, v in res["0"][2].items():
+        a, b = np.asarray(res["1"][2][k]), np.asarray(v)
+        if "embed_map" in k:   # the embedding gradient is a scatter-add of fp32 atomics: rounding depends on the order
+            assert np.allclose(a, b, rtol=1e-4, atol=1e-10), k
+        else:
+            assert np.array_equal(a, b), k

@@ -306,7 +306,10 @@ VQA_API VqaStatus vqa_create(const VqaConfig* config, VqaHandle* out) {
   h->defer_outputs = false;
   h->outputs_pending = false;
   h->pack_pending = false;
-  if (cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess ||
+  h->adam_tail_begin = 0;
+  h->tail_pending = false;
+  if (cudaEventCreateWithFlags(&h->ev_tail, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&h->ev_early, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_prefetch, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_upload, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&h->ev_pack, cudaEventDisableTiming) != cudaSuccess) {
@@ -325,6 +328,7 @@ VQA_API VqaStatus vqa_destroy(VqaHandle h) {
       cudaEventDestroy(h->ev[i][1]);
     }
   if (h && h->aux_created) {
+    cudaEventDestroy(h->ev_tail);
     cudaEventDestroy(h->ev_early);
     cudaEventDestroy(h->ev_prefetch);
     cudaEventDestroy(h->ev_upload);

@@ -160,6 +160,11 @@ struct VqaHandle_t {
     unsigned int ch_flag_total[4], ch_grid_total[4];
     int rank, world;
   } ar;
+  // vqa_set_optimizer_tail: parameters [tail_begin, n) are updated on an auxiliary stream; the next forward's embedding /
+  // x-projection branch and recurrent kernel wait for ev_tail, everything else starts right after the head is updated
+  long long adam_tail_begin;
+  bool tail_pending;
+  cudaEvent_t ev_tail;
   bool early_grads;        // vqa_set_early_gradients
   cudaEvent_t ev_early;    // recorded by vqa_backward once the non-GRU gradients are complete
   // optional per-phase timing

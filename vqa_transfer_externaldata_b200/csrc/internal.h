@@ -329,7 +329,8 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
                            float beta1, float beta2, float eps, float clip_norm, long long t,
                            float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s,
                            const AdamShadows* shadows = nullptr, const float* slice_grad = nullptr, long long slice_n = 0,
-                           const float* slice_sumsq = nullptr);
+                           const float* slice_sumsq = nullptr, long long tail_begin = 0, cudaStream_t tail_stream = nullptr,
+                           cudaEvent_t fork_ev = nullptr);
 // out[0] = sum of squares of x[rows, cols] (pitch ld); scratch: >= 148 floats
 VqaStatus rows_sumsq_launch(const float* x, long long rows, int cols, long long ld, float* out, float* scratch,
                             cudaStream_t s);

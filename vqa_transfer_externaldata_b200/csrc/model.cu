@@ -138,6 +138,7 @@ VQA_API VqaStatus vqa_prepare_params(VqaHandle h, const VqaParams* p, void* stre
   VQA_TRY(check_ready(h, "vqa_prepare_params"));
   if (!p) return set_error(VQA_ERR_BAD_ARG, "vqa_prepare_params: null params");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (h->tail_pending) VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_tail, 0));   // (a split optimizer step may still be updating the tail)
   const VqaConfig& c = h->cfg;
   WeightShadows& w = h->buf.w;
   struct Item { const float* src; Planes* dst; long long rows, cols; } items[] = {
@@ -229,6 +230,10 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   // epilogue/store-bound and overlaps the MMA-bound v-projection below      (:134-137, modules.py:124-140)
   cudaStream_t s1 = s;
   auto gru_inputs = [&](cudaStream_t st) -> VqaStatus {
+    if (h->tail_pending) {   // the embedding / GRU parameters of the last optimizer step (vqa_set_optimizer_tail)
+      VQA_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_tail, 0));
+      h->tail_pending = false;
+    }
     VQA_TRY(embed_gather_launch(p->embed, batch->q_intseq, Bn, T, T, W, Wp, c.Vq, b.e.hi, b.e.lo, st));
     VQA_TRY(GemmB(T * Bn, 2 * L, W).a(b.e, 0, Wp, false).b(b.w.gru_gates_w, 0, 2 * L, true)
                 .bias(p->gru_gates_b).f32(b.xg, 2 * L).run(h, st));
@@ -1338,8 +1343,16 @@ VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* p, float*
     slice_grad = grad + (p->embed - param);
     slice_n = static_cast<long long>(c.Vq) * c.W;
   }
+  const bool tail = h->adam_tail_begin > 0 && h->adam_tail_begin < n && rest.empty() && h->aux_created &&
+                    !(h->profile && !h->profile_overlapped);
+  if (h->tail_pending) VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_tail, 0));   // (two optimizer steps without a forward between them)
   VQA_TRY(adam_step_launch(param, grad, m, v, n, lr, beta1, beta2, eps, clip_norm, t, grad_norm_out, h->buf.scratch,
-                           h->num_sms, s, &tab, slice_grad, slice_n, slice_grad ? h->slice_slot : nullptr));
+                           h->num_sms, s, &tab, slice_grad, slice_n, slice_grad ? h->slice_slot : nullptr,
+                           tail ? h->adam_tail_begin : 0, tail ? h->aux[2] : nullptr, tail ? h->ev_fork[2] : nullptr));
+  if (tail) {
+    VQA_CUDA_CHECK(cudaEventRecord(h->ev_tail, h->aux[2]));
+    h->tail_pending = true;
+  }
   for (const Item* it : rest)
     VQA_TRY(split_bf16_launch(it->src, 1, it->elems, it->elems, it->dst->hi, it->dst->lo, it->elems, s));
   if (gru && gru_persistent_supported(c.B, c.L, c.precision, h->num_sms)) {
@@ -1354,6 +1367,19 @@ VQA_API VqaStatus vqa_adam_step_shadowed(VqaHandle h, const VqaParams* p, float*
       h->pack_pending = true;
     }
   }
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_set_optimizer_tail(VqaHandle h, int64_t tail_begin) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_set_optimizer_tail: null handle");
+  if (tail_begin < 0 || (tail_begin & 3)) return set_error(VQA_ERR_BAD_ARG, "vqa_set_optimizer_tail: a non-negative multiple of 4 floats");
+  h->adam_tail_begin = tail_begin;
+  return VQA_OK;
+}
+
+VQA_API VqaStatus vqa_sync_params(VqaHandle h, void* stream) {
+  if (!h) return set_error(VQA_ERR_BAD_ARG, "vqa_sync_params: null handle");
+  if (h->tail_pending) VQA_CUDA_CHECK(cudaStreamWaitEvent(static_cast<cudaStream_t>(stream), h->ev_tail, 0));
   return VQA_OK;
 }
 

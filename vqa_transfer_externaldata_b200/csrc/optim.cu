@@ -192,7 +192,8 @@ VqaStatus rows_sumsq_launch(const float* x, long long rows, int cols, long long 
 VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, long long n, float lr,
                            float beta1, float beta2, float eps, float clip_norm, long long t,
                            float* grad_norm_out, float* scratch, int num_sms, cudaStream_t s, const AdamShadows* shadows,
-                           const float* slice_grad, long long slice_n, const float* slice_sumsq) {
+                           const float* slice_grad, long long slice_n, const float* slice_sumsq, long long tail_begin,
+                           cudaStream_t tail_stream, cudaEvent_t fork_ev) {
   if (n <= 0) return VQA_OK;
   if (!param || !grad || !m || !v || !scratch) return set_error(VQA_ERR_BAD_ARG, "vqa_adam_step: null argument");
   if ((reinterpret_cast<uintptr_t>(param) | reinterpret_cast<uintptr_t>(grad) |
@@ -219,6 +220,36 @@ VqaStatus adam_step_launch(float* param, const float* grad, float* m, float* v, 
                       (1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(t)));
   AdamShadows tab{};
   if (shadows) tab = *shadows;
+  if (tail_begin > 0 && tail_begin < n && (tail_begin & 3) == 0 && tail_stream && fork_ev) {
+    // two launches: [0, tail_begin) on `s`, the tail on `tail_stream` (ordered after the norm) -- the caller lets the next
+    // step's first kernels, which read only the head of the buffer, start while the tail is still being updated
+    auto sub = [&](long long b, long long e, cudaStream_t st) -> VqaStatus {
+      AdamShadows t2{};
+      for (int k = 0; k < tab.n; ++k) {
+        const long long lo4 = tab.begin4[k] > (b >> 2) ? tab.begin4[k] : (b >> 2);
+        const long long hi4 = tab.end4[k] < (e >> 2) ? tab.end4[k] : (e >> 2);
+        if (lo4 >= hi4) continue;
+        if (lo4 != tab.begin4[k] || hi4 != tab.end4[k]) return set_error(VQA_ERR_BAD_ARG, "vqa_adam_step: the tail boundary splits a weight matrix");
+        t2.begin4[t2.n] = lo4 - (b >> 2);
+        t2.end4[t2.n] = hi4 - (b >> 2);
+        t2.hi[t2.n] = tab.hi[k];
+        t2.lo[t2.n] = tab.lo[k];
+        ++t2.n;
+      }
+      int bl = blocks;
+      const long long need2 = ((e - b) / 4 + OPT_THREADS - 1) / OPT_THREADS;
+      if (need2 < bl) bl = need2 < 1 ? 1 : static_cast<int>(need2);
+      launch_pdl(adam_kernel, dim3(bl), dim3(OPT_THREADS), 0, st, param + b, grad + b, m + b, v + b, e - b,
+                 static_cast<float>(lr_t), beta1, beta2, eps, clip_norm, scratch, t2);
+      VQA_LAUNCH_CHECK("adam");
+      return VQA_OK;
+    };
+    VQA_CUDA_CHECK(cudaEventRecord(fork_ev, s));
+    VQA_CUDA_CHECK(cudaStreamWaitEvent(tail_stream, fork_ev, 0));
+    VQA_TRY(sub(0, tail_begin, s));
+    VQA_TRY(sub(tail_begin, n, tail_stream));
+    return VQA_OK;
+  }
   launch_pdl(adam_kernel, dim3(blocks), dim3(OPT_THREADS), 0, s, param, grad, m, v, n, static_cast<float>(lr_t), beta1,
              beta2, eps, clip_norm, scratch, tab);
   VQA_LAUNCH_CHECK("adam");

@@ -310,6 +310,7 @@ class Engine:
         self.bank = None
         self.masks = None
         self.adam_t = 0
+        self._adam_tail = 0
         self._deferred = False
         self.early_gradients = False
         # cross-step feature prefetch (vqa_prefetch_features): the next batch's gather runs under this step's BPTT, as
@@ -599,18 +600,28 @@ class Engine:
     def stream_wait_early_gradients(self, stream):
         L.check(self.lib.vqa_stream_wait_early_gradients(self.h, C.c_void_p(stream.cuda_stream)))
 
-    def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip_norm=20.0):
-        """optimize_loss(Adam, clip_gradients=20.0) over the trainable slice (vqa/trainer.py:106-114)."""
+    def adam_step(self, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, clip_norm=20.0, pipelined_tail=False):
+        """optimize_loss(Adam, clip_gradients=20.0) over the trainable slice (vqa/trainer.py:106-114).
+        pipelined_tail (training loops): the embedding / GRU slice of the buffer is updated on an auxiliary stream, under
+        the first kernels of the next forward (vqa_set_optimizer_tail); read parameters through sync_params() then."""
         ps = self.params
         if ps.adam_m is None:
             ps.adam_m = torch.zeros_like(ps.grad)
             ps.adam_v = torch.zeros_like(ps.grad)
         self.adam_t += 1
+        tail = ps.n_early if (pipelined_tail and 0 < ps.n_early < ps.n_train and os.environ.get("VQA_ADAM_TAIL", "1") != "0") else 0
+        if tail != self._adam_tail:
+            L.check(self.lib.vqa_set_optimizer_tail(self.h, tail))
+            self._adam_tail = tail
         # one pass: clip + Adam + the bf16 operand shadows of the updated weight matrices (+ the GRU repack)
         L.check(self.lib.vqa_adam_step_shadowed(self.h, C.byref(self._p), ps.flat.data_ptr(), ps.grad.data_ptr(),
                                                 ps.adam_m.data_ptr(), ps.adam_v.data_ptr(), ps.n_train, lr, beta1,
                                                 beta2, eps, clip_norm, self.adam_t, self.grad_norm.data_ptr(),
                                                 self._stream()))
+
+    def sync_params(self):
+        """Order the current stream after a pipelined optimizer tail (no-op otherwise): call before reading parameters."""
+        L.check(self.lib.vqa_sync_params(self.h, self._stream()))
 
     def dropout_masks(self, seed, step, batch=None):
         Bn = self.batch_size if batch is None else batch

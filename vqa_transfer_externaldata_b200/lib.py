@@ -172,6 +172,8 @@ SYMBOLS = {
     "vqa_reparam_noise": (C.c_int32, [_P, C.c_int32, C.c_uint64, C.c_uint64, _P, _P]),
     "vqa_multimem_all_reduce": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P]),
     "vqa_set_embedding_slice_norm": (C.c_int32, [_P, _P]),
+    "vqa_set_optimizer_tail": (C.c_int32, [_P, C.c_int64]),
+    "vqa_sync_params": (C.c_int32, [_P, _P]),
     "vqa_set_deferred_outputs": (C.c_int32, [_P, C.c_int32]),
     "vqa_sync_outputs": (C.c_int32, [_P, _P]),
     "vqa_input_error_count": (C.c_int32, [C.POINTER(C.c_uint32), C.c_int32]),

@@ -172,11 +172,13 @@ class Model(object):
 
     # ---- checkpoint contract: tensors keyed by TF variable names ---------------------------------
     def state_dict(self):
+        self.engine.sync_params()   # (a pipelined optimizer tail of the last train_step)
         sd = {k: v.detach().cpu().numpy().copy() for k, v in self.engine.params.by_tf_name().items()}
         sd.update({k: v.copy() for k, v in self.dead_variables.items()})
         return sd
 
     def load_state_dict(self, state, strict=True):
+        self.engine.sync_params()
         fields = {tf_name(f, self.MODEL_TYPE): f for f in L.param_fields(self.MODEL_TYPE)}
         missing = [n for n in fields if n not in state]
         if strict and missing:
@@ -205,6 +207,7 @@ class Model(object):
 
     def optimizer_state_dict(self):
         """Adam slots under the reference's checkpoint names (empty before the first optimizer step)."""
+        self.engine.sync_params()
         e = self.engine
         ps = e.params
         if ps.adam_m is None:
@@ -309,7 +312,7 @@ class Model(object):
             self.engine.prefetch_batch(next_batch)
         self.backward()
         if apply_optimizer:
-            self.engine.adam_step(lr=self.learning_rate() if lr is None else lr, clip_norm=clip_norm)
+            self.engine.adam_step(lr=self.learning_rate() if lr is None else lr, clip_norm=clip_norm, pipelined_tail=True)
         self.global_step += 1
         if not sync:
             pending = self.engine.read_scalars_async()
