@@ -78,3 +78,22 @@ def test_known_answers():
     # the entries beyond `num` do not count
     l2, _, _ = M.n_way_classification_loss(np.where(np.arange(3)[None, :, None] >= 2, 50.0 * np.eye(9)[0], 0.0), fills, np.array([2, 2]))
     assert abs(l2 - np.log(9)) < 1e-12
+
+
+def test_product_model_mirrors_the_oracle_parameter_set():
+    """vqa_transfer_externaldata_b200.memft (the CUDA path's host side) declares the same variables with the same shapes
+    as the oracle, under the reference's checkpoint names, and refuses to run without a GPU (no CPU fallback)."""
+    from types import SimpleNamespace
+    from vqa_transfer_externaldata_b200 import memft as F
+    c = SimpleNamespace(**DIMS)
+    assert list(F.FIELDS) == list(M.PARAM_SHAPES)
+    for k, (shape, name) in F.FIELDS.items():
+        assert tuple(shape(c)) == tuple(M.PARAM_SHAPES[k](DIMS)), k
+        assert "/" in name
+    assert F.TF_NAMES["cls_w"] == "classifier/fc/weights" and F.TF_NAMES["gru_gates_w"].startswith("encode_L_blank/")
+    assert len(set(F.TF_NAMES.values())) == len(F.TF_NAMES)
+    b = F.synthetic_batch(dict(DIMS, B=4), seed=3)
+    assert set(b) == set(M.make_batch(dict(DIMS, B=4), seed=3))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            F.Model(None, F.make_config(dict(B=2, K=4, n=2, Dv=16, D=8, L=8, W=8, A=8, T=3, Vq=9, Nws=5)))
