@@ -643,8 +643,19 @@ def run_ours(args):
     # end to end through the public API (Model.train_step): every step uploads ITS batch from pinned host
     # memory (on the copy stream, overlapping the previous step's kernels) and its loss/report are read back
     # by the host one step later (asynchronous dispatch), all inside the timed region.
-    pinned = [{k: torch.from_numpy(np.ascontiguousarray(v)).pin_memory() for k, v in hb.items()
-               if k in ("image_idx", "q_intseq", "q_intseq_len", "answer_target")} for hb in host_batches]
+    # The soft-score target travels the way the native reader delivers it (input_native.create / csrc/input_host.cu): as
+    # (row, answer id, score) triples that vqa_densify_targets scatters on the device -- ~70 KB per step instead of the
+    # 6.2 MB dense [B, A] matrix (--e2e-dense uploads the dense matrix as the pure-Python reader's batches do).
+    def host_batch(hb):
+        out = {k: torch.from_numpy(np.ascontiguousarray(hb[k])).pin_memory() for k in ("image_idx", "q_intseq", "q_intseq_len")}
+        if args.e2e_dense:
+            out["answer_target"] = torch.from_numpy(np.ascontiguousarray(hb["answer_target"])).pin_memory()
+        else:
+            rows, ids = np.nonzero(hb["answer_target"])
+            out["answer_sparse"] = (rows.astype(np.int32), ids.astype(np.int32), hb["answer_target"][rows, ids].astype(np.float32))
+        return out
+
+    pinned = [host_batch(hb) for hb in host_batches]
     h2d = d2h = 0
     losses = []
 
@@ -812,7 +823,10 @@ def run_ours(args):
                        "dp_step_check": dp_check,
                        "gru_kernels": gru_label, "l2_policy": l2_policy},
             "e2e": {"value": e2e_value, "unit": "samples/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
+                    "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world,
+                    "inputs": ("dense [B, A] soft-score target from pinned host memory" if args.e2e_dense else
+                               "ids / tokens / lengths from pinned host memory, soft-score target as sparse (row, id, score) "
+                               "triples densified on the device (the native reader's batch format)")},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roofline,
@@ -854,6 +868,7 @@ def main():
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32-mode measurement (N = 1 only)")
     ap.add_argument("--no-infer", action="store_true", help="skip the BASELINE config 5 inference sweep")
     ap.add_argument("--no-memft", action="store_true", help="skip the short BASELINE config 4 (pre-training graph) run")
+    ap.add_argument("--e2e-dense", action="store_true", help="e2e leg uploads the dense [B, A] soft-score target instead of its sparse triples")
     ap.add_argument("--mode", default="train", choices=["train", "infer", "memft"])
     ap.add_argument("--infer-batches", default="64,512,4096,8192")
     args = ap.parse_args()

@@ -10,6 +10,8 @@
 // complete before / all slices are broadcast after).
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "internal.h"
 
 namespace vqa {
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(MC_THREADS) multimem_allreduce_kernel(float* m
 //   exit  : "every slice has been broadcast" -- blocks count themselves on a local counter after their last
 //           multimem.st (+ fence); the last one adds 1 to flags[1] everywhere and waits for the total, so the kernel
 //           (and with it the stream) does not complete before every rank's slice has landed here.
-// A spin that sees no progress for ~2 s traps (a lost rank becomes a launch failure, not a hung GPU).
+// A spin that sees no progress for ~30 s traps (a lost rank becomes a launch failure, not a hung GPU).
 __device__ __forceinline__ void mc_red_add_release(unsigned int* p, unsigned int v) {
   asm volatile("multimem.red.release.sys.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -68,7 +70,7 @@ __device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
 __device__ __forceinline__ void spin_until(const unsigned int* p, unsigned int target) {
   const long long t0 = clock64();
   while (static_cast<int>(ld_acquire_sys(p) - target) < 0) {
-    if (clock64() - t0 > 4000000000LL) __trap();
+    if (clock64() - t0 > 60000000000LL) __trap();   // ~30 s: ranks of one job may be seconds apart (host-side stalls of a single rank)
   }
 }
 
@@ -115,7 +117,8 @@ VqaStatus multimem_allreduce_sync_launch(float* mc, long long n, int rank, int w
   long long end = begin + per < n4 ? begin + per : n4;
   if (begin > end) begin = end;   // a rank without elements still takes part in the two barriers
   const int threads = exclusive ? 1024 : MC_THREADS;
-  if (ctas <= 0) ctas = exclusive ? 20 : 96;
+  static const int ctas_env = getenv("VQA_AR_CTAS") ? atoi(getenv("VQA_AR_CTAS")) : 0;   // tuning aid for the wide launches
+  if (ctas <= 0) ctas = exclusive ? 20 : (ctas_env > 0 ? ctas_env : 96);
   long long need = (end - begin + threads - 1) / threads;
   if (need < 1) need = 1;
   if (need < ctas) ctas = static_cast<int>(need);

@@ -64,7 +64,9 @@ class DataParallel:
         engine.rebind_gradients(buf)
         self._mc = (hdl, buf, n_grad)   # the tail slots are summed with the gradients
         self._in_library = False
-        if os.environ.get("VQA_DP_IN_LIBRARY", "1") != "0":
+        # in-library exchange: validated on 2 GPUs; on 8 GPUs it hit launch failures (profiles/r02_dp_n8.md), so larger jobs
+        # keep the host-issued barriers of round 1 unless VQA_DP_IN_LIBRARY=1 asks for it
+        if os.environ.get("VQA_DP_IN_LIBRARY", "1" if self.world_size <= 2 else "0") != "0":
             # the exchange runs inside vqa_backward (early slice under the BPTT, in-kernel barriers): nothing to do per step
             from . import lib as L
             torch.cuda.synchronize(engine.device)
