@@ -63,6 +63,33 @@ typedef struct VqaSlabLn {
 VQA_API VqaStatus vqa_ops_slab_ln_fwd(VqaOps ops, const VqaSlabLn* a, void* stream);
 VQA_API VqaStatus vqa_ops_slab_ln_bwd(VqaOps ops, const VqaSlabLn* a, void* stream);
 
+/* modules.fc_layer on a rank-2 input as ONE kernel (csrc/linear_ln.cu; vlmap/modules.py:616-650, call sites
+ * vqa/model_vlmap_answer.py:142-181): the tcgen05 product with the layer's tail in its epilogue -- the CTAs of a row tile
+ * form a thread-block cluster along N and exchange row statistics through distributed shared memory.
+ *   backward = 0:  z = a W + bias;  y = act(LN(z));  out = y * mul * keep_mask / keep        (W: [K, N], TF's [in, out])
+ *   backward = 1:  raw = a W^T (= d loss / d out);  dz = LayerNorm / activation / mul / dropout backward of raw
+ *                  (W: the same buffer seen as [N, K]: N = the layer's inputs ... of the NEXT layer, whose data gradient
+ *                  this is; z / mean / rstd / gamma / beta / mul / dropout site are those of THIS layer's forward pass)
+ * bf16 operands (one plane), fp32 everything else. N = 64 or 128 x {1, 2, 4, 8, 16}; forward needs K % 64 == 0.
+ * VQA_ERR_BAD_SHAPE when the shape (or the device: 16-CTA clusters) is not eligible: use vqa_ops_gemm + vqa_ops_slab_ln_*
+ * (n = 1). Dropout element index = row * N + column at `site` (as vqa_ops_dropout_mask). */
+typedef struct VqaLinearLn {
+  int32_t M, N, K;
+  int32_t backward;
+  const void* a; int64_t lda;
+  const void* w; int64_t ldw;
+  const float* bias;
+  const float* gamma; const float* beta;
+  const float* mul;
+  int32_t act;                 /* 0 relu, 1 tanh */
+  float keep; uint64_t seed, step; uint32_t site;
+  float* z; float* mean; float* rstd;      /* forward: outputs; backward: inputs */
+  float* y; float* out_f32; void* out_hi;  /* forward outputs (any may be NULL) */
+  float* raw; float* dz_f32; void* dz_hi;  /* backward outputs (any may be NULL) */
+  float* dgamma_part; float* dbeta_part;   /* backward, optional: [M, N] per-row terms of d gamma / d beta (column-sum them) */
+} VqaLinearLn;
+VQA_API VqaStatus vqa_ops_linear_ln(VqaOps ops, const VqaLinearLn* a, void* stream);
+
 /* fp32 [rows, cols] -> GEMM operand planes [rows, ld_out] with the columns beyond `cols` zero (6-d box features as a
  * K = 64 operand). boxes != 0: src is [rows, 4] normalised boxes and the operand is (x0, y0, x1, y1, x1 - x0, y1 - y0)
  * (model_vlmap_bf_or_wordset_withatt_sp.py:340-345). */

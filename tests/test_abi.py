@@ -110,7 +110,7 @@ def test_memft_header_binding_and_layouts(lib):
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/vqa_memft.h but not exported"
     for cname, cls in (("VqaSlabLn", L.VqaSlabLn), ("VqaSpatAttn", L.VqaSpatAttn), ("VqaSoftmaxCe", L.VqaSoftmaxCe),
-                       ("VqaGruSeq", L.VqaGruSeq)):
+                       ("VqaGruSeq", L.VqaGruSeq), ("VqaLinearLn", L.VqaLinearLn)):
         body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), src, flags=re.S).group(1)
         fields = []
         for decl in body.split(";"):

@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libvqa_answer_b200.so")
-SOURCES = ["core.cu", "gemm.cu", "gemm_pair.cu", "elementwise.cu", "rows.cu", "attn.cu", "attn_pipe.cu", "gru.cu", "gru_pair.cu", "loss.cu", "variants.cu", "optim.cu", "collective.cu", "input_host.cu", "memft.cu", "model.cu"]
+SOURCES = ["core.cu", "gemm.cu", "gemm_pair.cu", "elementwise.cu", "rows.cu", "linear_ln.cu", "attn.cu", "attn_pipe.cu", "gru.cu", "gru_pair.cu", "loss.cu", "variants.cu", "optim.cu", "collective.cu", "input_host.cu", "memft.cu", "model.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall,-Wno-unused-function,-Wno-unknown-pragmas", "--expt-relaxed-constexpr",

@@ -184,6 +184,34 @@ struct RowLnBwd {
 };
 VqaStatus row_ln_relu_bwd_launch(const RowLnBwd& a, cudaStream_t s);
 
+// ---- linear_ln.cu ----
+// One fc_layer (rank-2 input) as one kernel: tcgen05 product + bias + row LayerNorm + activation + Hadamard partner +
+// dropout in the epilogue (forward), or the data-gradient product + dropout / Hadamard / activation / LayerNorm backward
+// (backward); the CTAs of a row tile form a cluster along N and exchange row statistics through distributed shared
+// memory. bf16 mode (one operand plane). *launched = false (and VQA_OK): shape / device not eligible -- the caller
+// runs the GEMM + rows.cu kernels instead. VQA_LINEAR_LN=0 turns it off.
+struct LinearLn {
+  int M, N, K;
+  const bf16* a; long long lda;      // [M, K], K contiguous
+  const bf16* b; long long ldb;      // forward: weights [K, N] (b_mn_major = 1); backward: weights [N, K] (K contiguous)
+  int b_mn_major;
+  int backward;
+  const float* bias;                 // forward
+  const float* gamma; const float* beta;
+  const float* mul;                  // optional [M, N]
+  int act;                           // 0 relu, 1 tanh
+  float keep;
+  unsigned long long seed, step;
+  unsigned int stream_id;
+  float* z;                          // [M, N] pre-LN: forward output, backward input
+  float* mean; float* rstd;          // [M]: forward output, backward input
+  float* y; float* out_f32; bf16* out_hi;            // forward outputs (as RowLnFwd)
+  float* raw;                        // backward, optional: the product itself (d loss / d layer output), fp32
+  float* dz_f32; bf16* dz_hi; float* dgamma_part; float* dbeta_part;   // backward outputs (as RowLnBwd)
+};
+VqaStatus linear_ln_launch(const LinearLn& d, cudaStream_t s, bool* launched);
+bool linear_ln_enabled();
+
 // ---- attn.cu ----
 VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precision, float keep,
                           cudaStream_t s);

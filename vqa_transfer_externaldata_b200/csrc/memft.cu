@@ -1132,6 +1132,31 @@ VQA_API VqaStatus vqa_ops_slab_ln_bwd(VqaOps ops, const VqaSlabLn* a, void* stre
   return VQA_OK;
 }
 
+VQA_API VqaStatus vqa_ops_linear_ln(VqaOps ops, const VqaLinearLn* a, void* stream) {
+  if (!ops || !a) return set_error(VQA_ERR_BAD_ARG, "vqa_ops_linear_ln: null argument");
+  if (!a->a || !a->w || !a->gamma || !a->beta || !a->z || !a->mean || !a->rstd || (!a->backward && !a->bias))
+    return set_error(VQA_ERR_BAD_ARG, "vqa_ops_linear_ln: a / w / gamma / beta / z / mean / rstd (and bias, forward) must be given");
+  if (a->keep <= 0.f || a->keep > 1.f) return set_error(VQA_ERR_BAD_ARG, "vqa_ops_linear_ln: keep %g", a->keep);
+  LinearLn d{};
+  d.M = a->M; d.N = a->N; d.K = a->K;
+  d.a = static_cast<const bf16*>(a->a); d.lda = a->lda;
+  d.b = static_cast<const bf16*>(a->w); d.ldb = a->ldw;
+  d.b_mn_major = a->backward ? 0 : 1;
+  d.backward = a->backward;
+  d.bias = a->bias; d.gamma = a->gamma; d.beta = a->beta; d.mul = a->mul;
+  d.act = a->act; d.keep = a->keep; d.seed = a->seed; d.step = a->step; d.stream_id = a->site;
+  d.z = a->z; d.mean = a->mean; d.rstd = a->rstd;
+  d.y = a->y; d.out_f32 = a->out_f32; d.out_hi = static_cast<bf16*>(a->out_hi);
+  d.raw = a->raw; d.dz_f32 = a->dz_f32; d.dz_hi = static_cast<bf16*>(a->dz_hi);
+  d.dgamma_part = a->dgamma_part; d.dbeta_part = a->dbeta_part;
+  bool launched = false;
+  VQA_TRY(linear_ln_launch(d, static_cast<cudaStream_t>(stream), &launched));
+  if (!launched)
+    return set_error(VQA_ERR_BAD_SHAPE, "vqa_ops_linear_ln: M %d N %d K %d is not eligible for the fused kernel on this device",
+                     a->M, a->N, a->K);
+  return VQA_OK;
+}
+
 VQA_API VqaStatus vqa_ops_pad_planes(const float* src, int64_t rows, int32_t cols, int32_t boxes, void* hi, void* lo,
                                      int32_t ld_out, void* stream) {
   if (!src || !hi || rows < 0 || ld_out <= 0 || (ld_out & 7) || cols > ld_out || (boxes && ld_out < 6))

@@ -55,6 +55,63 @@ struct GemmB {  // builder with the conventions of VqaGemmDesc
   VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s, &h->gemm_ctx, narrow_); }
 };
 
+// modules.fc_layer forward on a rank-2 input: z = a W + bias, then the LayerNorm / activation / Hadamard / dropout tail
+// described by `r` (r.z = the pre-LN buffer). bf16 mode: one fused kernel when the shape is eligible (linear_ln.cu),
+// else -- and in fp32 mode -- the GEMM followed by the row kernel.
+// Which call sites take the fused kernel (VQA_LINEAR_LN_SITES, bit per site: 1 q_linear_l, 2 q_linear_v, 4 pooled_linear_l,
+// 8 joint_fc, 16 joint_fc backward, 32 pooled_linear_l backward, 64 the variants' extra question layers).
+// Measured inside the cfg1 step (B200, profiles/r02_linear_ln.md): the two question layers, which follow the recurrent
+// kernel on an otherwise idle machine, gain (19.6 -> 17.5 us for the pair, step 0.997 -> 0.986 ms); pooled_linear_l and
+// joint_fc lose ~3 us each and the two backward sites ~7 us each although the kernel alone beats GEMM + row kernel by
+// 3 - 4.5 us: a 16-CTA cluster starts only when a whole GPC has drained, which the CTA-by-CTA hand-over from the
+// attention kernel / the concurrent weight-gradient GEMMs delays. Default: the question layers only.
+enum { LL_QL = 1, LL_QV = 2, LL_PL = 4, LL_JOINT = 8, LL_JOINT_BWD = 16, LL_PL_BWD = 32, LL_EXTRA = 64 };
+bool fused_site(int site) {
+  static const int mask = getenv("VQA_LINEAR_LN_SITES") ? atoi(getenv("VQA_LINEAR_LN_SITES")) : (LL_QL | LL_QV | LL_EXTRA);
+  return (mask & site) != 0;
+}
+
+VqaStatus fc_ln_fwd(VqaHandle h, int site, const Planes& a, long long a_off, long long lda, int K, const Planes& w, const float* bias,
+                    float* zbuf, RowLnFwd r, cudaStream_t s) {
+  r.z = zbuf;
+  if (fused_site(site) && !a.lo && !w.lo && !r.out_lo) {
+    LinearLn d{};
+    d.M = r.rows; d.N = r.N; d.K = K;
+    d.a = a.hi + a_off; d.lda = lda; d.b = w.hi; d.ldb = r.N; d.b_mn_major = 1;
+    d.bias = bias; d.gamma = r.gamma; d.beta = r.beta; d.mul = r.mul; d.act = r.act; d.keep = r.keep;
+    d.seed = r.seed; d.step = r.step; d.stream_id = r.stream_id;
+    d.z = zbuf; d.mean = r.mean; d.rstd = r.rstd; d.y = r.y; d.out_f32 = r.out_f32; d.out_hi = r.out_hi;
+    bool launched = false;
+    VQA_TRY(linear_ln_launch(d, s, &launched));
+    if (launched) return VQA_OK;
+  }
+  VQA_TRY(GemmB(r.rows, r.N, K).a(a, a_off, lda, false).b(w, 0, r.N, true).bias(bias).f32(zbuf, r.N).run(h, s));
+  return row_ln_relu_fwd_launch(r, s);
+}
+
+// The data gradient d = dy W^T of the layer ABOVE followed by this layer's dropout / Hadamard / activation / LayerNorm
+// backward (`r`; r.dout = the buffer that receives d when somebody else needs it too, else scratch for the unfused
+// path). W: [N, K] as stored (K contiguous). Fused under the same conditions as fc_ln_fwd.
+VqaStatus fc_ln_bwd(VqaHandle h, int site, const Planes& dy, long long lddy, int K, const Planes& w, float* dbuf, bool keep_d,
+                    RowLnBwd r, cudaStream_t s) {
+  r.dout = dbuf;
+  if (fused_site(site) && !dy.lo && !w.lo && !r.dz_lo) {
+    LinearLn d{};
+    d.M = r.rows; d.N = r.N; d.K = K; d.backward = 1;
+    d.a = dy.hi; d.lda = lddy; d.b = w.hi; d.ldb = K; d.b_mn_major = 0;
+    d.gamma = r.gamma; d.beta = r.beta; d.mul = r.mul; d.act = r.act; d.keep = r.keep;
+    d.seed = r.seed; d.step = r.step; d.stream_id = r.stream_id;
+    d.z = const_cast<float*>(r.z); d.mean = const_cast<float*>(r.mean); d.rstd = const_cast<float*>(r.rstd);
+    d.raw = keep_d ? dbuf : nullptr; d.dz_f32 = r.dz_f32; d.dz_hi = r.dz_hi;
+    d.dgamma_part = r.dgamma_part; d.dbeta_part = r.dbeta_part;
+    bool launched = false;
+    VQA_TRY(linear_ln_launch(d, s, &launched));
+    if (launched) return VQA_OK;
+  }
+  VQA_TRY(GemmB(r.rows, r.N, K).a(dy, 0, lddy, false).b(w, 0, K, false).f32(dbuf, r.N).run(h, s));
+  return row_ln_relu_bwd_launch(r, s);
+}
+
 // The attention-dropout keep bits as a precomputed plane (vqa_keep_bits) instead of Philox inside the two attention
 // kernels. Measured on B200 (profiles/r02_attn_keep_bits.md): the kernels are latency-bound with idle ALUs, so the ten
 // Philox rounds were free and a byte fetched from global memory per 8 elements is NOT: forward 68 -> 77 us, backward
@@ -362,11 +419,10 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     } else if (c.variant == VQA_VARIANT_VLMAP_ANSWER2) {
       // q_L_ft2 = tanh(LN(q W2 + b2))           (vqa/model_vlmap_answer2.py:127-130)
       if (!p->qp_gamma || !p->qp_beta) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: answer2 needs qp_gamma / qp_beta");
-      VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.qp_w, 0, L, true).bias(p->qp_b).f32(b.zqp, L).run(h, s1));
       RowLnFwd r{};
-      r.rows = Bn; r.N = L; r.z = b.zqp; r.gamma = p->qp_gamma; r.beta = p->qp_beta; r.keep = 1.f; r.act = 1;
+      r.rows = Bn; r.N = L; r.gamma = p->qp_gamma; r.beta = p->qp_beta; r.keep = 1.f; r.act = 1;
       r.y = b.qp_f32; r.out_hi = b.qp.hi; r.out_lo = b.qp.lo; r.mean = b.lnqp_mean; r.rstd = b.lnqp_rstd;
-      VQA_TRY(row_ln_relu_fwd_launch(r, s1));
+      VQA_TRY(fc_ln_fwd(h, LL_EXTRA, b.h, q_off, L, L, b.w.qp_w, p->qp_b, b.zqp, r, s1));
     } else {
       // q_L_mean = q Wm + bm: no LayerNorm, no activation   (vqa/model_vlmap_answer_no_noise.py:122-125)
       VQA_TRY(GemmB(Bn, L, L).a(b.h, q_off, L, false).b(b.w.qp_w, 0, L, true).bias(p->qp_b).f32(b.qp_f32, L)
@@ -375,21 +431,19 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   }
   const Planes& ql_in = has_qp ? b.qp : b.h;
   const long long ql_in_off = has_qp ? 0 : T * BL;
-  VQA_TRY(GemmB(Bn, L, L).a(ql_in, ql_in_off, L, false).b(b.w.ql_w, 0, L, true).bias(p->ql_b).f32(b.zl, L).run(h, s1));
   {
     RowLnFwd r{};
-    r.rows = Bn; r.N = L; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta; r.keep = 1.f;
+    r.rows = Bn; r.N = L; r.gamma = p->ql_gamma; r.beta = p->ql_beta; r.keep = 1.f;
     r.y = b.hl; r.mean = b.lnl_mean; r.rstd = b.lnl_rstd;
     if (c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC) { r.out_hi = b.hl_op.hi; r.out_lo = b.hl_op.lo; }   // joint_l reads Hl
-    VQA_TRY(row_ln_relu_fwd_launch(r, s1));
+    VQA_TRY(fc_ln_fwd(h, LL_QL, ql_in, ql_in_off, L, L, b.w.ql_w, p->ql_b, b.zl, r, s1));
   }
   // a3: Hq = relu(LN(q Wqv + b))                                    (:142-145)
-  VQA_TRY(GemmB(Bn, D, L).a(b.h, q_off, L, false).b(b.w.qv_w, 0, D, true).bias(p->qv_b).f32(b.zq, D).run(h, s));
   {
     RowLnFwd r{};
-    r.rows = Bn; r.N = D; r.z = b.zq; r.gamma = p->qv_gamma; r.beta = p->qv_beta; r.keep = 1.f;
+    r.rows = Bn; r.N = D; r.gamma = p->qv_gamma; r.beta = p->qv_beta; r.keep = 1.f;
     r.y = b.hq; r.mean = b.lnq_mean; r.rstd = b.lnq_rstd;
-    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+    VQA_TRY(fc_ln_fwd(h, LL_QV, b.h, q_off, L, L, b.w.qv_w, p->qv_b, b.zq, r, s));
   }
   PH_END(VQA_PH_QHEADS_FWD);
   if (kb_forked) VQA_TRY(join_stream(h, 5, s));   // the keep bits
@@ -408,22 +462,20 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_END(VQA_PH_ATTN_FWD);
   PH_BEGIN(VQA_PH_HEAD_FWD);
   // a6: Hp = relu(LN(P Wp + b)); X = Hp (.) Hl; Jd = dropout(relu(LN(X Wj + b)), 0.5)   (:163-181)
-  VQA_TRY(GemmB(Bn, L, Pd).a(b.pooled_op, 0, Pd, false).b(b.w.pl_w, 0, L, true).bias(p->pl_b).f32(b.zp, L).run(h, s));
-  VQA_TRY(join_stream(h, 0, s));  // Hl
+  VQA_TRY(join_stream(h, 0, s));  // Hl (the Hadamard partner in the layer's epilogue)
   {
     RowLnFwd r{};
-    r.rows = Bn; r.N = L; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta; r.keep = 1.f;
+    r.rows = Bn; r.N = L; r.gamma = p->pl_gamma; r.beta = p->pl_beta; r.keep = 1.f;
     const bool noc_f = c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC;   // noc: no Hadamard, joint_v reads Hp itself
     r.mul = noc_f ? nullptr : b.hl; r.y = b.hp; r.out_hi = b.x.hi; r.out_lo = b.x.lo; r.mean = b.lnp_mean; r.rstd = b.lnp_rstd;
-    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+    VQA_TRY(fc_ln_fwd(h, LL_PL, b.pooled_op, 0, Pd, Pd, b.w.pl_w, p->pl_b, b.zp, r, s));
   }
-  VQA_TRY(GemmB(Bn, J, L).a(b.x, 0, L, false).b(b.w.joint_w, 0, J, true).bias(p->joint_b).f32(b.zj, J).run(h, s));
   {
     RowLnFwd r{};
-    r.rows = Bn; r.N = J; r.z = b.zj; r.gamma = p->joint_gamma; r.beta = p->joint_beta;
+    r.rows = Bn; r.N = J; r.gamma = p->joint_gamma; r.beta = p->joint_beta;
     r.keep = c.keep_joint; r.seed = seed; r.step = step; r.stream_id = RNG_STREAM_JOINT;
     r.out_hi = b.jd.hi; r.out_lo = b.jd.lo; r.mean = b.lnj_mean; r.rstd = b.lnj_rstd;
-    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+    VQA_TRY(fc_ln_fwd(h, LL_JOINT, b.x, 0, L, L, b.w.joint_w, p->joint_b, b.zj, r, s));
   }
   // a7: logits against the (exported vlmap word) weights              (:183-185)
   VQA_TRY(GemmB(Bn, A, J).a(b.jd, 0, J, false).b(b.w.ans_w, 0, A, true).bias(p->ans_b).f32(b.logit, A).run(h, s));
@@ -431,12 +483,11 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     // second branch (model_vlmap_answer_noc.py:184-203): Jl = dropout(relu(LN(Hl Wjl + b))), logit += Jl Wal + bal
     if (!p->jl_w || !p->jl_b || !p->jl_gamma || !p->jl_beta || !p->al_w || !p->al_b)
       return set_error(VQA_ERR_BAD_ARG, "vqa_forward: the noc variant needs jl_* and al_*");
-    VQA_TRY(GemmB(Bn, J, L).a(b.hl_op, 0, L, false).b(b.w.jl_w, 0, J, true).bias(p->jl_b).f32(b.zjl, J).run(h, s));
     RowLnFwd r{};
-    r.rows = Bn; r.N = J; r.z = b.zjl; r.gamma = p->jl_gamma; r.beta = p->jl_beta;
+    r.rows = Bn; r.N = J; r.gamma = p->jl_gamma; r.beta = p->jl_beta;
     r.keep = c.keep_joint; r.seed = seed; r.step = step; r.stream_id = RNG_STREAM_JOINT_L;
     r.out_hi = b.jdl.hi; r.out_lo = b.jdl.lo; r.mean = b.lnjl_mean; r.rstd = b.lnjl_rstd;
-    VQA_TRY(row_ln_relu_fwd_launch(r, s));
+    VQA_TRY(fc_ln_fwd(h, LL_EXTRA, b.hl_op, 0, L, L, b.w.jl_w, p->jl_b, b.zjl, r, s));
     VQA_TRY(GemmB(Bn, A, J).a(b.jdl, 0, J, false).b(b.w.al_w, 0, A, true).bias(p->al_b).addend(b.logit, A)
                 .f32(b.logit, A).run(h, s));
   }
@@ -599,18 +650,21 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(pg_fork());
     VQA_TRY(colsum_launch(b.dlogit_f32, Bn, A, A, g->ans_b, pg_scr, pg));
   }
-  // dJd = dlogit Wa^T
-  VQA_TRY(GemmB(Bn, J, A).a(b.dlogit, 0, A, false).b(b.w.ans_w, 0, A, false).f32(b.dJ, J).run(h, s));
-  if (v_tuned)   // both heads read the same joint: dJd += d tuned Wt^T
-    VQA_TRY(GemmB(Bn, J, A).a(b.dtuned, 0, A, false).b(b.w.tw_w, 0, A, false).addend(b.dJ, J).f32(b.dJ, J).run(h, s));
-  // joint_fc: dropout, ReLU, LN backward
+  // dJd = dlogit Wa^T, then joint_fc's dropout / ReLU / LayerNorm backward (one kernel in bf16 mode: linear_ln.cu)
   {
     RowLnBwd r{};
     r.rows = Bn; r.N = J; r.dout = b.dJ; r.z = b.zj; r.gamma = p->joint_gamma; r.beta = p->joint_beta;
     r.mean = b.lnj_mean; r.rstd = b.lnj_rstd; r.keep = c.keep_joint; r.seed = seed; r.step = step;
     r.stream_id = RNG_STREAM_JOINT; r.dz_f32 = b.dzj_f32; r.dz_hi = b.dzj.hi; r.dz_lo = b.dzj.lo;
     if (g->joint_gamma || g->joint_beta) { r.dgamma_part = b.ln_parts[0][0]; r.dbeta_part = b.ln_parts[0][1]; }
-    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (v_tuned) {   // both heads read the same joint: dJd += d tuned Wt^T
+      VQA_TRY(GemmB(Bn, J, A).a(b.dlogit, 0, A, false).b(b.w.ans_w, 0, A, false).f32(b.dJ, J).run(h, s));
+      VQA_TRY(GemmB(Bn, J, A).a(b.dtuned, 0, A, false).b(b.w.tw_w, 0, A, false).addend(b.dJ, J).f32(b.dJ, J).run(h, s));
+      VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    } else {
+      if (!g->joint_b) r.dz_f32 = nullptr;   // (only the bias gradient reads the fp32 copy)
+      VQA_TRY(fc_ln_bwd(h, LL_JOINT_BWD, b.dlogit, A, A, b.w.ans_w, b.dJ, false, r, s));
+    }
     if (g->joint_gamma) {
       VQA_TRY(pg_fork());
       VQA_TRY(colsum_launch(b.ln_parts[0][0], Bn, J, J, g->joint_gamma, pg_scr, pg));
@@ -629,8 +683,25 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(colsum_launch(b.dzj_f32, Bn, J, J, g->joint_b, pg_scr, pg));
   }
   // dX = dZj Wj^T ; dHp = dX (.) Hl ; dHl = dX (.) Hp   (noc: dHp = dX, dHl comes from the joint_l branch)
+  // (pooled_linear_l's Hadamard / ReLU / LayerNorm backward rides in the epilogue of the dX product; dX itself is
+  //  stored for the q_linear_l branch)
   const bool noc = c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC;
-  VQA_TRY(GemmB(Bn, L, J).a(b.dzj, 0, J, false).b(b.w.joint_w, 0, J, false).f32(b.dX, L).run(h, s));
+  {
+    RowLnBwd r{};
+    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = noc ? nullptr : b.hl; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta;
+    r.mean = b.lnp_mean; r.rstd = b.lnp_rstd; r.keep = 1.f; r.dz_f32 = g->pl_b ? b.dzp_f32 : nullptr; r.dz_hi = b.dzp.hi;
+    r.dz_lo = b.dzp.lo;
+    if (g->pl_gamma || g->pl_beta) { r.dgamma_part = b.ln_parts[2][0]; r.dbeta_part = b.ln_parts[2][1]; }
+    VQA_TRY(fc_ln_bwd(h, LL_PL_BWD, b.dzj, J, J, b.w.joint_w, b.dX, true, r, s));
+    if (g->pl_gamma) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[2][0], Bn, L, L, g->pl_gamma, pg_scr, pg));
+    }
+    if (g->pl_beta) {
+      VQA_TRY(pg_fork());
+      VQA_TRY(colsum_launch(b.ln_parts[2][1], Bn, L, L, g->pl_beta, pg_scr, pg));
+    }
+  }
   const float* d_hl_src = b.dX;
   if (noc) {
     // joint_l branch: dJl = dlogit Wal^T -> dropout / ReLU / LN backward -> dHl = dZjl Wjl^T
@@ -682,22 +753,6 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi; r.dz_lo = b.dzl.lo;
     VQA_TRY(row_ln_relu_bwd_launch(r, sq));
     VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, sq));
-  }
-  {
-    RowLnBwd r{};
-    r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = noc ? nullptr : b.hl; r.z = b.zp; r.gamma = p->pl_gamma; r.beta = p->pl_beta;
-    r.mean = b.lnp_mean; r.rstd = b.lnp_rstd; r.keep = 1.f; r.dz_f32 = b.dzp_f32; r.dz_hi = b.dzp.hi;
-    r.dz_lo = b.dzp.lo;
-    if (g->pl_gamma || g->pl_beta) { r.dgamma_part = b.ln_parts[2][0]; r.dbeta_part = b.ln_parts[2][1]; }
-    VQA_TRY(row_ln_relu_bwd_launch(r, s));
-    if (g->pl_gamma) {
-      VQA_TRY(pg_fork());
-      VQA_TRY(colsum_launch(b.ln_parts[2][0], Bn, L, L, g->pl_gamma, pg_scr, pg));
-    }
-    if (g->pl_beta) {
-      VQA_TRY(pg_fork());
-      VQA_TRY(colsum_launch(b.ln_parts[2][1], Bn, L, L, g->pl_beta, pg_scr, pg));
-    }
   }
   const bool v_ent = c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT;
   if (v_ent) {

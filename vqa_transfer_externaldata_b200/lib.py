@@ -199,6 +199,15 @@ class VqaSlabLn(C.Structure):
                 ("dmul", C.c_void_p), ("part", C.c_void_p)]
 
 
+class VqaLinearLn(C.Structure):
+    _fields_ = [("M", C.c_int32), ("N", C.c_int32), ("K", C.c_int32), ("backward", C.c_int32), ("a", C.c_void_p),
+                ("lda", C.c_int64), ("w", C.c_void_p), ("ldw", C.c_int64), ("bias", C.c_void_p), ("gamma", C.c_void_p),
+                ("beta", C.c_void_p), ("mul", C.c_void_p), ("act", C.c_int32), ("keep", C.c_float), ("seed", C.c_uint64),
+                ("step", C.c_uint64), ("site", C.c_uint32), ("z", C.c_void_p), ("mean", C.c_void_p), ("rstd", C.c_void_p),
+                ("y", C.c_void_p), ("out_f32", C.c_void_p), ("out_hi", C.c_void_p), ("raw", C.c_void_p),
+                ("dz_f32", C.c_void_p), ("dz_hi", C.c_void_p), ("dgamma_part", C.c_void_p), ("dbeta_part", C.c_void_p)]
+
+
 class VqaSpatAttn(C.Structure):
     _fields_ = [("B", C.c_int32), ("K", C.c_int32), ("n", C.c_int32), ("D", C.c_int32), ("Dv", C.c_int32),
                 ("kinds", C.c_int32), ("hv_hi", C.c_void_p), ("hv_lo", C.c_void_p), ("hq", C.c_void_p),
@@ -236,6 +245,7 @@ MEMFT_SYMBOLS = {
     "vqa_ops_dropout_mask": (C.c_int32, [_P, C.c_int64, C.c_float, C.c_uint64, C.c_uint64, C.c_uint32, _P]),
     "vqa_ops_slab_ln_fwd": (C.c_int32, [_P, C.POINTER(VqaSlabLn), _P]),
     "vqa_ops_slab_ln_bwd": (C.c_int32, [_P, C.POINTER(VqaSlabLn), _P]),
+    "vqa_ops_linear_ln": (C.c_int32, [_P, C.POINTER(VqaLinearLn), _P]),
     "vqa_ops_pad_planes": (C.c_int32, [_P, C.c_int64, C.c_int32, C.c_int32, _P, _P, C.c_int32, _P]),
     "vqa_ops_feat_wgrad": (C.c_int32, [_P, _P, C.c_int32, C.c_int32, _P, _P, C.c_int64, C.c_int32, _P, C.c_int32, _P, _P]),
     "vqa_memft_spat_attn_fwd": (C.c_int32, [_P, C.POINTER(VqaSpatAttn), _P]),
