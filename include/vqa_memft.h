@@ -67,9 +67,10 @@ VQA_API VqaStatus vqa_ops_slab_ln_bwd(VqaOps ops, const VqaSlabLn* a, void* stre
  * vqa/model_vlmap_answer.py:142-181): the tcgen05 product with the layer's tail in its epilogue -- the CTAs of a row tile
  * form a thread-block cluster along N and exchange row statistics through distributed shared memory.
  *   backward = 0:  z = a W + bias;  y = act(LN(z));  out = y * mul * keep_mask / keep        (W: [K, N], TF's [in, out])
- *   backward = 1:  raw = a W^T (= d loss / d out);  dz = LayerNorm / activation / mul / dropout backward of raw
- *                  (W: the same buffer seen as [N, K]: N = the layer's inputs ... of the NEXT layer, whose data gradient
- *                  this is; z / mean / rstd / gamma / beta / mul / dropout site are those of THIS layer's forward pass)
+ *   backward = 1:  raw = a W'^T (the data gradient through the layer ABOVE: a = d loss / d pre-activation of that layer,
+ *                  W' = its weights, the same TF buffer seen as [N, K] with K contiguous);
+ *                  dz = this layer's dropout / mul / activation / LayerNorm backward applied to raw
+ *                  (z / mean / rstd / gamma / beta / mul / dropout site are those of THIS layer's forward pass)
  * bf16 operands (one plane), fp32 everything else. N = 64 or 128 x {1, 2, 4, 8, 16}; forward needs K % 64 == 0.
  * VQA_ERR_BAD_SHAPE when the shape (or the device: 16-CTA clusters) is not eligible: use vqa_ops_gemm + vqa_ops_slab_ln_*
  * (n = 1). Dropout element index = row * N + column at `site` (as vqa_ops_dropout_mask). */
