@@ -51,8 +51,10 @@ struct GemmB {  // builder with the conventions of VqaGemmDesc
   }
   int narrow_ = 0;
   GemmB& narrow() { narrow_ = 1; return *this; }
+  int sms_ = 0;
+  GemmB& sms(int n) { sms_ = n; return *this; }   // plan (and size the persistent grid) for n SMs instead of the whole device
   GemmB& bn(int block_n) { d.block_n = block_n; return *this; }   // VqaGemmDesc.block_n: 0 auto, 64 / 128 / 256, -128 / -256 pair
-  VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, h->num_sms, s, &h->gemm_ctx, narrow_); }
+  VqaStatus run(VqaHandle h, cudaStream_t s) { return gemm_launch(d, sms_ > 0 ? sms_ : h->num_sms, s, &h->gemm_ctx, narrow_); }
 };
 
 // modules.fc_layer forward on a rank-2 input: z = a W + bias, then the LayerNorm / activation / Hadamard / dropout tail
@@ -110,6 +112,38 @@ VqaStatus fc_ln_bwd(VqaHandle h, int site, const Planes& dy, long long lddy, int
   }
   VQA_TRY(GemmB(r.rows, r.N, K).a(dy, 0, lddy, false).b(w, 0, K, false).f32(dbuf, r.N).run(h, s));
   return row_ln_relu_bwd_launch(r, s);
+}
+
+// How many leading rows of the v-projection run under the recurrent forward kernel (0: none), and on how many SMs.
+// The persistent recurrent grid takes (L / 32) x ceil(B / 128) CTAs (gru_pair.cu); what is left holds idle CTA pairs for
+// the whole ~T x 12 us of the chain, and the question heads that follow it (~10 us) do not need Z either. As many
+// 256-row tiles move there as finish inside that window (a 256 x 256 tile: ~18 us per 2048 of K on one pair, measured:
+// 88 tiles on 10 pairs fit under cfg1's 176 us, 112 do not). Measured on cfg1 (profiles/r02_vproj_split.md): main launch
+// 73 -> 57 us, step -7 us. VQA_VPROJ_SPLIT=0 turns it off, =n forces n row tiles.
+int vproj_split_plan(VqaHandle h, int Bn, int K, int D, int Dv, int L, int T, bool fp32, bool off, bool keep_bits, long long* rows) {
+  static const int env = (getenv("VQA_VPROJ_SPLIT") && *getenv("VQA_VPROJ_SPLIT")) ? atoi(getenv("VQA_VPROJ_SPLIT")) : -1;
+  *rows = 0;
+  if (off || fp32 || env == 0 || D % 256 != 0) return 0;
+  if (!gru_persistent_supported(Bn, L, VQA_PREC_BF16, h->num_sms) || !gru_pair_supported(Bn, L, h->num_sms)) return 0;
+  const int gru_ctas = (L / 32) * ((Bn + 127) / 128);
+  const int idle = (h->num_sms - gru_ctas) & ~1;
+  if (gru_ctas > h->num_sms || idle < 8) return 0;
+  const long long M = static_cast<long long>(Bn) * K;
+  const int rt = static_cast<int>((M + 255) / 256), ct = D / 256, pairs = h->num_sms / 2, ipairs = idle / 2;
+  // the attention-dropout keep bits (ten Philox rounds per 8 elements, ALU only) run on the same idle SMs FIRST, on the same
+  // stream: side by side they starve the GEMM's issuer warp (inference at K = 100: the moved rows took 270 us instead of 160)
+  const double kb_us = keep_bits ? (static_cast<double>(M) * D / 8.0) * 64.0 / (idle * 4.0 * 32.0 * 1900.0) : 0.0;
+  const double tile_us = 18.0 * Dv / 2048.0, window_us = 12.0 * T + 10.0 - kb_us;
+  const int rounds = static_cast<int>(window_us / tile_us);
+  int rta = rounds * ipairs / ct;
+  if (rta > rt - (pairs + ct - 1) / ct) rta = rt - (pairs + ct - 1) / ct;   // leave the main launch a full wave
+  // tiles are dealt round-robin over the CTA pairs: the main launch only gets shorter by whole waves. Without one saved
+  // the moved rows can only lose (inference at K = 100, B = 512: 800 -> 752 tiles are 11 waves either way; 0.717 -> 0.757 ms)
+  if (rta > 0 && ((rt - rta) * ct + pairs - 1) / pairs >= (rt * ct + pairs - 1) / pairs) rta = 0;
+  if (env > 0) rta = env;
+  if (rta <= 0 || rta >= rt) return 0;
+  *rows = static_cast<long long>(rta) * 256;
+  return idle;
 }
 
 // The attention-dropout keep bits as a precomputed plane (vqa_keep_bits) instead of Philox inside the two attention
@@ -329,11 +363,16 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_END(VQA_PH_GATHER);
   PH_BEGIN(VQA_PH_VPROJ_FWD);
   // a1: Z = V Wv + bv (LayerNorm over (K, D) + ReLU are applied inside the attention kernels)
+  // The recurrent kernel below is a latency chain on 128 of the 148 SMs; the v-projection is 288 tiles of 256 x 256 on 74
+  // CTA pairs. Its first rows therefore run UNDER the recurrent kernel, as a persistent launch on the CTA pairs that grid
+  // leaves idle, and only the rest runs here (rows of the product are independent).
+  long long vsplit_rows = 0;
+  const int v_idle_sms = vproj_split_plan(h, Bn, K, D, Dv, L, T, fp32, serial || v_adapt, use_keep_bits(c, K, D), &vsplit_rows);
   {
-    GemmB g(Bn * K, D, Dv);
-    g.a(b.v, 0, Dv, false).b(b.w.v_w, 0, D, true).bias(p->v_b);
-    if (fp32) g.f32(static_cast<float*>(b.z), D);
-    else { Planes zp; zp.hi = static_cast<bf16*>(b.z); g.planes(zp, 0, D); }
+    GemmB g(static_cast<int>(Bn * K - vsplit_rows), D, Dv);
+    g.a(b.v, vsplit_rows * Dv, Dv, false).b(b.w.v_w, 0, D, true).bias(p->v_b);
+    if (fp32) g.f32(static_cast<float*>(b.z) + vsplit_rows * D, D);
+    else { Planes zp; zp.hi = static_cast<bf16*>(b.z); g.planes(zp, vsplit_rows * D, D); }
     VQA_TRY(g.run(h, s));
   }
   if (v_adapt) {
@@ -373,13 +412,19 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     // per 8 elements) on the SMs the cooperative recurrent grid leaves idle -- forked BEFORE that launch, enqueued AFTER
     // it (the cooperative grid must be first in line), joined before the attention kernel. Beside the v-projection GEMM
     // it cost that GEMM 10 us (measured).
-    cudaStream_t a5 = s;
+    cudaStream_t a5 = s, a2 = s;
     kb_forked = want_bits && !serial;
     if (kb_forked) VQA_TRY(fork_stream(h, 5, s, &a5));
+    if (vsplit_rows > 0 && !kb_forked) VQA_TRY(fork_stream(h, 2, s, &a2));   // (forked BEFORE the cooperative launch, enqueued AFTER it)
     VQA_TRY(gru_fwd_persistent_launch(a, h->num_sms, s));
     if (want_bits)
       VQA_TRY(keep_bits_launch(b.att_bits, static_cast<long long>(Bn) * K * D, c.keep_att, seed, step, RNG_STREAM_ATT, a5,
                                kb_forked ? 8 * (h->num_sms > 128 ? h->num_sms - 128 : 8) : 0));
+    if (vsplit_rows > 0) {   // rows [0, vsplit_rows) of the v-projection on the idle CTA pairs (after the keep bits, same stream)
+      Planes zp; zp.hi = static_cast<bf16*>(b.z);
+      VQA_TRY(GemmB(static_cast<int>(vsplit_rows), D, Dv).a(b.v, 0, Dv, false).b(b.w.v_w, 0, D, true).bias(p->v_b).planes(zp, 0, D)
+                  .sms(v_idle_sms).run(h, kb_forked ? a5 : a2));
+    }
   } else {
     if (want_bits)
       VQA_TRY(keep_bits_launch(b.att_bits, static_cast<long long>(Bn) * K * D, c.keep_att, seed, step, RNG_STREAM_ATT, s));
@@ -447,6 +492,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   }
   PH_END(VQA_PH_QHEADS_FWD);
   if (kb_forked) VQA_TRY(join_stream(h, 5, s));   // the keep bits
+  if (vsplit_rows > 0 && !kb_forked) VQA_TRY(join_stream(h, 2, s));   // the first rows of Z (else: on the keep bits' stream, joined above)
   PH_BEGIN(VQA_PH_ATTN_FWD);
   // a4 + a5: attention + pooling                                     (:151-156)
   {
