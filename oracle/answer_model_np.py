@@ -180,7 +180,8 @@ def fc_ln_relu_bwd(dh, w, gamma, cache, need_dx=True, flip=None, gate=None):
 # ------------------------------------------------------------------------------------------------
 def gru_fwd(E, q_len, Wg, bg, Wc, bc, q=_ident):
     """q rounds the matmul operands h and r*h (E, Wg, Wc arrive already rounded); the element-wise gate math
-    always uses the unrounded state."""
+    always uses the unrounded state. In the CUDA path's bf16 mode the x-parts of the two pre-activations (x Wx + b,
+    hoisted out of the recurrence as one product over all steps) are STORED as bf16: q rounds them too."""
     B, T, W = E.shape
     L = Wc.shape[1]
     h = np.zeros((B, L))
@@ -188,10 +189,16 @@ def gru_fwd(E, q_len, Wg, bg, Wc, bc, q=_ident):
     for t in range(T):
         x = E[:, t, :]
         h_op = q(h)
-        g = np.concatenate([x, h_op], axis=1) @ Wg + bg
+        if q is _ident:
+            g = np.concatenate([x, h_op], axis=1) @ Wg + bg
+        else:
+            g = q(x @ Wg[:W] + bg) + h_op @ Wg[W:]
         r, u = sigmoid(g[:, :L]), sigmoid(g[:, L:])
         rh_op = q(r * h)
-        c = np.tanh(np.concatenate([x, rh_op], axis=1) @ Wc + bc)
+        if q is _ident:
+            c = np.tanh(np.concatenate([x, rh_op], axis=1) @ Wc + bc)
+        else:
+            c = np.tanh(q(x @ Wc[:W] + bc) + rh_op @ Wc[W:])
         hn = u * h + (1.0 - u) * c
         valid = (t < q_len)[:, None]
         steps.append((x, h, r, u, rh_op, c, valid, h_op))

@@ -56,6 +56,7 @@ struct GruArgs {
   // forward
   const float* xg;   // [T*B, 2L] x-part of the gate pre-activations (+bias)
   const float* xc;   // [T*B, L]
+  int x_bf;          // xg / xc hold bf16 values (same element indexing)
   float* h_f32;      // [(T+1)*B, L]
   bf16* h_bf;        // [(T+1)*B, L]
   bf16* rh_bf;       // [T*B, L]
@@ -68,6 +69,12 @@ struct GruArgs {
   float* bias_part;  // [ceil(B/128), 3L] per-row-tile partial sums of (d gates_bias | d candidate_bias)
   unsigned long long* trace;  // optional [num_ctas, num_phases, 4] globaltimer stamps (scripts/gpu_gru_trace.py)
 };
+
+// one hoisted x-projection value: fp32 array, or the same array holding bf16 values
+__device__ __forceinline__ float ldx(const float* base, long long idx, int is_bf) {
+  if (!is_bf) return __ldg(base + idx);
+  return __bfloat162float(__ldg(reinterpret_cast<const bf16*>(base) + idx));
+}
 
 __device__ __forceinline__ unsigned long long gtimer() {
   unsigned long long t;
@@ -361,9 +368,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
             const int row = rbase + rr;
             xr[rr] = xu[rr] = ar[rr] = au[rr] = 0.f;
             if (row < g.row_end) {
-              const float* x = g.xg + (tb + row) * 2 * L + unit;
-              xr[rr] = __ldg(x);
-              xu[rr] = __ldg(x + L);
+              const long long xo = (tb + row) * 2 * L + unit;
+              xr[rr] = ldx(g.xg, xo, g.x_bf);
+              xu[rr] = ldx(g.xg, xo + L, g.x_bf);
             }
           }
           if (mm) {
@@ -399,7 +406,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) gru_persistent_kernel(
           for (int rr = 0; rr < NR; ++rr) {
             const int row = rbase + rr;
             ac[rr] = 0.f;
-            xc[rr] = (row < g.row_end) ? __ldg(g.xc + (tb + row) * L + unit) : 0.f;
+            xc[rr] = (row < g.row_end) ? ldx(g.xc, (tb + row) * L + unit, g.x_bf) : 0.f;
           }
           if (mm) {
             ptx::mbar_wait(tmem_full_bar, tfull_phase);
@@ -777,7 +784,7 @@ VqaStatus gru_fwd_persistent_launch(const GruFwdPersistent& a, int num_sms, cuda
   if (!ok) return set_error(VQA_ERR_CUDA, "gru_fwd_persistent: cuTensorMapEncodeTiled failed");
   GruArgs g{};
   g.B = B; g.row0 = 0; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
-  g.xg = a.xg; g.xc = a.xc; g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
+  g.xg = a.xg; g.xc = a.xc; g.x_bf = a.x_bf16; g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
   return launch_persistent<0>(a.h_bf, L, static_cast<uint64_t>(T + 1) * B, a.rh_bf, L, static_cast<uint64_t>(T) * B,
                               tm_wg, tm_wc, g, num_sms, s);
 }

@@ -78,6 +78,7 @@ struct PairGruArgs {
   const int* q_len;
   unsigned int* counter;   // [2 * row tiles]
   const float* xg; const float* xc;
+  int x_bf;                // xg / xc are bf16 arrays (same element indexing)
   float* h_f32; bf16* h_bf; bf16* rh_bf;
   float* r; float* u; float* c;
   const float* dq; const float* dq2;
@@ -139,6 +140,20 @@ __device__ __forceinline__ void load8f(const float* p, float (&v)[NU]) {
   const float4 a = __ldg(reinterpret_cast<const float4*>(p));
   const float4 b = __ldg(reinterpret_cast<const float4*>(p + 4));
   v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+// 8 consecutive x-projection values starting at element `idx`: fp32 array, or the same array holding bf16 values
+__device__ __forceinline__ void load8x(const float* base, long long idx, int is_bf, float (&v)[NU]) {
+  if (!is_bf) {
+    load8f(base + idx, v);
+    return;
+  }
+  const uint4 q = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(base) + idx));
+  const uint32_t w[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[2 * j] = __uint_as_float(w[j] << 16);
+    v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+  }
 }
 __device__ __forceinline__ void store8f(float* p, const float (&v)[NU]) {
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
@@ -551,9 +566,9 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
 #pragma unroll
             for (int j = 0; j < NU; ++j) xr[j] = xu[j] = ar[j] = au[j] = 0.f;
             if (row_ok) {
-              const float* x = g.xg + (tb + row) * 2 * L + unit;
-              load8f(x, xr);
-              load8f(x + L, xu);
+              const long long xo = (tb + row) * 2 * L + unit;
+              load8x(g.xg, xo, g.x_bf, xr);
+              load8x(g.xg, xo + L, g.x_bf, xu);
             }
             if (mm) {
               ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
@@ -578,7 +593,7 @@ __global__ void __launch_bounds__(Q_THREADS, 1) gru_pair_kernel(
             float xc[NU], ac[NU];
 #pragma unroll
             for (int j = 0; j < NU; ++j) xc[j] = ac[j] = 0.f;
-            if (row_ok) load8f(g.xc + (tb + row) * L + unit, xc);
+            if (row_ok) load8x(g.xc, (tb + row) * L + unit, g.x_bf, xc);
             if (mm) {
               ptx::mbar_wait(&tmem_full_bar[w], tfullw[w]);
               tfullw[w] ^= 1;
@@ -881,7 +896,7 @@ cudaError_t gru_pair_fwd(const GruFwdPersistent& a, int num_sms, cudaStream_t s)
     return cudaErrorInvalidValue;
   PairGruArgs g{};
   g.B = B; g.row_end = B; g.L = L; g.T = T; g.q_len = a.q_len; g.counter = a.counter;
-  g.xg = a.xg; g.xc = a.xc; g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
+  g.xg = a.xg; g.xc = a.xc; g.x_bf = a.x_bf16; g.h_f32 = a.h_f32; g.h_bf = a.h_bf; g.rh_bf = a.rh_bf; g.r = a.r; g.u = a.u; g.c = a.c;
   g.trace = g_gru_trace;
   g.dbg = getenv("VQA_GRU_DBG") ? atoi(getenv("VQA_GRU_DBG")) : 0;
   g.tma_out = (B % Q_ROWS == 0) ? 1 : 0;

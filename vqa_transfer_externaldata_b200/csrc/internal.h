@@ -114,6 +114,7 @@ struct GruFwdPersistent {
   const int* q_len;
   unsigned int* counter;
   const float* xg; const float* xc;      // hoisted x-parts (+bias): [T*B, 2L], [T*B, L]
+  int x_bf16;                            // != 0: xg / xc hold bf16 values (the x-projection GEMMs stored bf16: half the bytes)
   float* h_f32; bf16* h_bf;              // [(T+1)*B, L], block 0 = zero initial state
   bf16* rh_bf;                           // [T*B, L]
   float* r; float* u; float* c;          // [T*B, L]

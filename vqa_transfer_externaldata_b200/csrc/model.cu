@@ -320,16 +320,28 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   // branch 0 (auxiliary stream): embedding lookup + the hoisted x-parts of the GRU pre-activations; it is
   // epilogue/store-bound and overlaps the MMA-bound v-projection below      (:134-137, modules.py:124-140)
   cudaStream_t s1 = s;
+  static const bool x_bf16_env = getenv("VQA_GRU_X_BF16") == nullptr || atoi(getenv("VQA_GRU_X_BF16")) != 0;
+  const bool x_bf16 = x_bf16_env && !fp32 && gru_persistent_supported(Bn, L, c.precision, h->num_sms);
   auto gru_inputs = [&](cudaStream_t st) -> VqaStatus {
     if (h->tail_pending) {   // the embedding / GRU parameters of the last optimizer step (vqa_set_optimizer_tail)
       VQA_CUDA_CHECK(cudaStreamWaitEvent(st, h->ev_tail, 0));
       h->tail_pending = false;
     }
     VQA_TRY(embed_gather_launch(p->embed, batch->q_intseq, Bn, T, T, W, Wp, c.Vq, b.e.hi, b.e.lo, st));
-    VQA_TRY(GemmB(T * Bn, 2 * L, W).a(b.e, 0, Wp, false).b(b.w.gru_gates_w, 0, 2 * L, true)
-                .bias(p->gru_gates_b).f32(b.xg, 2 * L).run(h, st));
-    VQA_TRY(GemmB(T * Bn, L, W).a(b.e, 0, Wp, false).b(b.w.gru_cand_w, 0, L, true)
-                .bias(p->gru_cand_b).f32(b.xc, L).run(h, st));
+    // bf16 mode with the persistent recurrent kernels: the hoisted x-parts are stored as bf16 (in the same buffers) --
+    // these two products are store-bound (K = 300: 88 MB of fp32 per step at cfg1), and the recurrent kernel reads them back
+    GemmB gx(T * Bn, 2 * L, W), cx(T * Bn, L, W);
+    gx.a(b.e, 0, Wp, false).b(b.w.gru_gates_w, 0, 2 * L, true).bias(p->gru_gates_b);
+    cx.a(b.e, 0, Wp, false).b(b.w.gru_cand_w, 0, L, true).bias(p->gru_cand_b);
+    if (x_bf16) {
+      Planes pg, pc;
+      pg.hi = reinterpret_cast<bf16*>(b.xg); pc.hi = reinterpret_cast<bf16*>(b.xc);
+      gx.planes(pg, 0, 2 * L); cx.planes(pc, 0, L);
+    } else {
+      gx.f32(b.xg, 2 * L); cx.f32(b.xc, L);
+    }
+    VQA_TRY(gx.run(h, st));
+    VQA_TRY(cx.run(h, st));
     VQA_TRY(fill_zero_launch(b.h_f32, sizeof(float) * BL, st));
     VQA_TRY(fill_zero_launch(b.h.hi, sizeof(bf16) * BL, st));
     if (b.h.lo) VQA_TRY(fill_zero_launch(b.h.lo, sizeof(bf16) * BL, st));
@@ -405,7 +417,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   if (persistent) {
     GruFwdPersistent a{};
     a.B = Bn; a.L = L; a.T = T; a.q_len = batch->q_intseq_len; a.counter = b.gru_counter;
-    a.xg = b.xg; a.xc = b.xc; a.h_f32 = b.h_f32; a.h_bf = b.h.hi; a.rh_bf = b.rh.hi;
+    a.xg = b.xg; a.xc = b.xc; a.x_bf16 = x_bf16 ? 1 : 0; a.h_f32 = b.h_f32; a.h_bf = b.h.hi; a.rh_bf = b.rh.hi;
     a.r = b.r; a.u = b.u; a.c = b.c;
     a.w_pack = b.gru_pack;
     // The step's attention-dropout keep bits, once, for both attention kernels: an ALU-only kernel (ten Philox rounds
