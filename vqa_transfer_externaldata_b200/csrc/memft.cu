@@ -1004,6 +1004,7 @@ struct G {   // GEMM builder over Planes (conventions of VqaGemmDesc)
   G& bias(const float* p) { d.bias = p; return *this; }
   G& addend(const float* p, long long ld) { d.addend = p; d.ld_addend = ld; return *this; }
   G& f32(float* p, long long ld) { d.out_f32 = p; d.ld_f32 = ld; return *this; }
+  G& bf(bf16* p, long long ld) { d.out_hi = p; d.ld_bf = ld; return *this; }   // one bf16 output plane
   VqaStatus run(VqaOps ops, cudaStream_t s) { return gemm_launch(d, ops->num_sms, s, &ops->gemm_ctx, 0); }
 };
 
@@ -1294,15 +1295,24 @@ VQA_API VqaStatus vqa_ops_gru_fwd(VqaOps ops, const VqaGruSeq* ap, void* stream)
   if (persistent)
     VQA_TRY(gru_pack_weights_launch(w.wg.hi + static_cast<long long>(W) * 2 * L, w.wc.hi + static_cast<long long>(W) * L, L, w.pack, s));
   VQA_TRY(embed_gather_launch(a.embed, a.tokens, B, T, T, W, Wp, a.Vq, w.e.hi, w.e.lo, s));
-  VQA_TRY(G(static_cast<long long>(T) * B, 2 * L, W).a(w.e, 0, Wp, false).b(w.wg, 0, 2 * L, true).bias(a.gates_b).f32(w.xg, 2 * L).run(ops, s));
-  VQA_TRY(G(static_cast<long long>(T) * B, L, W).a(w.e, 0, Wp, false).b(w.wc, 0, L, true).bias(a.cand_b).f32(w.xc, L).run(ops, s));
+  // bf16 mode on the persistent kernels: the hoisted x-parts are stored as bf16 in the same buffers (these products are
+  // store-bound: 630 MB of fp32 per step for the 5120 blank sequences of BASELINE config 4); VQA_GRU_X_BF16=0: fp32
+  static const bool x_bf16_env = getenv("VQA_GRU_X_BF16") == nullptr || atoi(getenv("VQA_GRU_X_BF16")) != 0;
+  const bool x_bf16 = x_bf16_env && persistent && a.precision == VQA_PREC_BF16;
+  G gx(static_cast<long long>(T) * B, 2 * L, W), cx(static_cast<long long>(T) * B, L, W);
+  gx.a(w.e, 0, Wp, false).b(w.wg, 0, 2 * L, true).bias(a.gates_b);
+  cx.a(w.e, 0, Wp, false).b(w.wc, 0, L, true).bias(a.cand_b);
+  if (x_bf16) { gx.bf(reinterpret_cast<bf16*>(w.xg), 2 * L); cx.bf(reinterpret_cast<bf16*>(w.xc), L); }
+  else { gx.f32(w.xg, 2 * L); cx.f32(w.xc, L); }
+  VQA_TRY(gx.run(ops, s));
+  VQA_TRY(cx.run(ops, s));
   VQA_TRY(fill_zero_launch(w.h_f32, sizeof(float) * BL, s));
   VQA_TRY(fill_zero_launch(w.h.hi, sizeof(bf16) * BL, s));
   if (w.h.lo) VQA_TRY(fill_zero_launch(w.h.lo, sizeof(bf16) * BL, s));
   if (persistent) {
     GruFwdPersistent g{};
     g.B = B; g.L = L; g.T = T; g.q_len = a.len; g.counter = w.counter;
-    g.xg = w.xg; g.xc = w.xc; g.h_f32 = w.h_f32; g.h_bf = w.h.hi; g.rh_bf = w.rh.hi;
+    g.xg = w.xg; g.xc = w.xc; g.x_bf16 = x_bf16 ? 1 : 0; g.h_f32 = w.h_f32; g.h_bf = w.h.hi; g.rh_bf = w.rh.hi;
     g.r = w.r; g.u = w.u; g.c = w.c; g.w_pack = w.pack;
     VQA_TRY(gru_fwd_persistent_launch(g, ops->num_sms, s));
   } else {
