@@ -346,6 +346,10 @@ struct BwdArgs {
   unsigned long long* trace;        // optional [batch][8] globaltimer stamps
   int vring_rows;                   // > 0: the <V, dP> pass streams the feature rows through a 3-slot ring of this many rows
                                     // laid over the (not yet loaded) slab buffer (bulk copies) instead of global loads
+  // optional tail (qv_z != NULL): q_linear_v's ReLU / LayerNorm backward on this sample's d_hq row -- the CTA holds the
+  // whole row, so the row kernel between this kernel and the q-projection data gradient disappears from the path
+  const float* qv_z; const float* qv_gamma; const float* qv_mean; const float* qv_rstd;
+  bf16* qv_dz_hi; bf16* qv_dz_lo; float* qv_dz_f32; float* qv_dgamma_part; float* qv_dbeta_part;
 };
 constexpr int AB_VSLOTS = 3;
 __device__ __forceinline__ unsigned long long gtimer_ns() {
@@ -366,8 +370,8 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
   const int CH = D >> 3;
   float* sdP = sm;                  // [Dv]
   float* ds = sdP + Dv;             // [K] (first da, then ds)
-  float* red = ds + K;              // [40]
-  float* colacc = red + 40;         // [3][ATT_THREADS][8*NCOL] per-thread column accumulators
+  float* red = ds + K;              // [64]
+  float* colacc = red + 64;         // [3][ATT_THREADS][8*NCOL] per-thread column accumulators
   unsigned char* flags = reinterpret_cast<unsigned char*>(colacc + 3 * ATT_THREADS * 8 * NCOL);  // [K*CH]
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const ZT* zb = static_cast<const ZT*>(a.z) + static_cast<long long>(b) * K * D;
@@ -379,7 +383,7 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
   pdl_sync();
   if (SLAB) {
     // the slab copy is in flight while the feature rows are reduced against dP below
-    const size_t head = ((static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * 4 +
+    const size_t head = ((static_cast<size_t>(Dv) + K + 64 + 3 * ATT_THREADS * 8 * NCOL) * 4 +
                          static_cast<size_t>(K) * CH + 15) & ~static_cast<size_t>(15);
     zbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sm) + head);
     ZT* zs = reinterpret_cast<ZT*>(zbar + 8);
@@ -692,27 +696,100 @@ __global__ void __launch_bounds__(ATT_THREADS, SLAB ? 2 : 1) attn_bwd_kernel(Bwd
       for (int j = 0; j < 8; ++j) G[i][j] = w8[j] * hq8[j] * inv_keep * gm8[j];
     }
   }
+  // q_linear_v backward, part 1 (optional): d x_hat of this sample's question row and its two row sums. The values go to
+  // the colacc entries only this thread has read (row group 0 of its own column), which nobody touches before the end.
+  float q1 = 0.f, q2 = 0.f;
+  float qmean = 0.f, qrstd = 0.f;
+  if (a.qv_z) {
+    qmean = a.qv_mean[b];
+    qrstd = a.qv_rstd[b];
+    if (active && tr == 0) {
+#pragma unroll
+      for (int i = 0; i < NCOL; ++i) {
+        const int c = tc + i * CW;
+        if (c >= CH) break;
+        const long long o = static_cast<long long>(b) * D + c * 8;
+        float dq8[8], hq8[8], zq8[8], gq8[8], dg8[8], db8[8];
+        {   // written above by this thread: plain (coherent) loads, not the read-only path
+          const float4 d0 = *reinterpret_cast<const float4*>(a.d_hq + o);
+          const float4 d1 = *reinterpret_cast<const float4*>(a.d_hq + o + 4);
+          dq8[0] = d0.x; dq8[1] = d0.y; dq8[2] = d0.z; dq8[3] = d0.w; dq8[4] = d1.x; dq8[5] = d1.y; dq8[6] = d1.z; dq8[7] = d1.w;
+        }
+        ld8f(a.hq + o, hq8);
+        ld8f(a.qv_z + o, zq8);
+        ld8f(a.qv_gamma + c * 8, gq8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float xh = (zq8[j] - qmean) * qrstd;
+          const float dy = hq8[j] > 0.f ? dq8[j] : 0.f;   // hq = relu(pre): hq > 0 <=> pre > 0
+          const float dxh = dy * gq8[j];
+          dg8[j] = dy * xh;
+          db8[j] = dy;
+          colacc[(0 * ATT_THREADS + tc) * 8 * NCOL + i * 8 + j] = dxh;
+          colacc[(1 * ATT_THREADS + tc) * 8 * NCOL + i * 8 + j] = xh;
+          q1 += dxh;
+          q2 = fmaf(dxh, xh, q2);
+        }
+        if (a.qv_dgamma_part) {
+          *reinterpret_cast<float4*>(a.qv_dgamma_part + o) = make_float4(dg8[0], dg8[1], dg8[2], dg8[3]);
+          *reinterpret_cast<float4*>(a.qv_dgamma_part + o + 4) = make_float4(dg8[4], dg8[5], dg8[6], dg8[7]);
+          *reinterpret_cast<float4*>(a.qv_dbeta_part + o) = make_float4(db8[0], db8[1], db8[2], db8[3]);
+          *reinterpret_cast<float4*>(a.qv_dbeta_part + o + 4) = make_float4(db8[4], db8[5], db8[6], db8[7]);
+        }
+      }
+    }
+    q1 = warp_sum(q1);
+    q2 = warp_sum(q2);
+  }
   s1 = warp_sum(s1);
   s2 = warp_sum(s2);
   if (lane == 0) {
     red[warp] = s1;
     red[8 + warp] = s2;
+    red[40 + warp] = q1;
+    red[48 + warp] = q2;
   }
   __syncthreads();
   if (tid == 0) {
-    float t1 = 0.f, t2 = 0.f;
+    float t1 = 0.f, t2 = 0.f, u1 = 0.f, u2 = 0.f;
     for (int w = 0; w < ATT_WARPS; ++w) {
       t1 += red[w];
       t2 += red[8 + w];
+      u1 += red[40 + w];
+      u2 += red[48 + w];
     }
     const float inv_n = 1.0f / (static_cast<float>(K) * static_cast<float>(D));
     red[16] = t1 * inv_n;
     red[17] = t2 * inv_n;
+    red[56] = u1 / static_cast<float>(D);
+    red[57] = u2 / static_cast<float>(D);
     part[4 * D] = red[32];  // d att_b partial
   }
   __syncthreads();
   const float m1 = red[16], m2 = red[17];
   AB_TRACE(6);
+  // q_linear_v backward, part 2: dz = rstd (d x_hat - mean(d x_hat) - x_hat mean(d x_hat x_hat)) over the row of D
+  if (a.qv_z && active && tr == 0) {
+    const float mq1 = red[56], mq2 = red[57];
+#pragma unroll
+    for (int i = 0; i < NCOL; ++i) {
+      const int c = tc + i * CW;
+      if (c >= CH) break;
+      const long long o = static_cast<long long>(b) * D + c * 8;
+      float dzq[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dxh = colacc[(0 * ATT_THREADS + tc) * 8 * NCOL + i * 8 + j];
+        const float xh = colacc[(1 * ATT_THREADS + tc) * 8 * NCOL + i * 8 + j];
+        dzq[j] = qrstd * (dxh - mq1 - xh * mq2);
+      }
+      if (a.qv_dz_f32) {
+        *reinterpret_cast<float4*>(a.qv_dz_f32 + o) = make_float4(dzq[0], dzq[1], dzq[2], dzq[3]);
+        *reinterpret_cast<float4*>(a.qv_dz_f32 + o + 4) = make_float4(dzq[4], dzq[5], dzq[6], dzq[7]);
+      }
+      if (a.qv_dz_hi) store8_planes(a.qv_dz_hi, a.qv_dz_lo, o, dzq);
+    }
+  }
 
   // dz = rstd * (dxhat - mean(dxhat) - xhat * mean(dxhat * xhat)) for ALL K rows (padded rows are part
   // of the LayerNorm slab and receive gradient through the statistics)
@@ -850,7 +927,7 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
 template <typename ZT, int NCOL>
 static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv, float keep,
                               uint32_t thr, cudaStream_t s) {
-  const size_t head = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float) +
+  const size_t head = (static_cast<size_t>(Dv) + K + 64 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float) +
                       static_cast<size_t>(K) * (D >> 3);
   const size_t slab = static_cast<size_t>(K) * D * sizeof(ZT);
   const size_t smem_slab = ((head + 15) & ~static_cast<size_t>(15)) + 64 + slab;
@@ -866,7 +943,7 @@ static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv,
     if (rows >= 1 && (reinterpret_cast<uintptr_t>(g.v_hi) & 15) == 0) g2.vring_rows = rows;
   }
   // the bit plane travels by bulk copy into `flags` (slab mode, 16-byte granularity); otherwise the kernel redraws the bits
-  const size_t flags_off = (static_cast<size_t>(Dv) + K + 40 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float);
+  const size_t flags_off = (static_cast<size_t>(Dv) + K + 64 + 3 * ATT_THREADS * 8 * NCOL) * sizeof(float);
   if (!use_slab || (static_cast<size_t>(K) * (D >> 3)) % 16 != 0 || (flags_off & 15) != 0 ||
       (reinterpret_cast<uintptr_t>(g.keep_bits) & 15) != 0 || thr >= 65536u)
     g2.keep_bits = nullptr;
@@ -884,7 +961,8 @@ static cudaError_t launch_bwd(const BwdArgs& g, int batch, int K, int D, int Dv,
 }
 
 VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precision, float keep,
-                          float* partials, cudaStream_t s, cudaStream_t reduce_stream, cudaEvent_t kernel_done) {
+                          float* partials, cudaStream_t s, cudaStream_t reduce_stream, cudaEvent_t kernel_done,
+                          const AttnQvBwd* qv) {
   if (a.batch == 0) return VQA_OK;
   if (!a.z || !a.gamma || !a.beta || !a.hq || !a.att_w || !a.nbox || !a.v_hi || !a.att || !a.ln_mean ||
       !a.ln_rstd || !a.d_pooled || !a.dz_hi || !a.d_hq || !partials)
@@ -897,6 +975,13 @@ VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precisi
   g.seed = a.seed; g.step = a.step; g.att = a.att; g.ln_mean = a.ln_mean; g.ln_rstd = a.ln_rstd;
   g.d_pooled = a.d_pooled; g.dz_hi = static_cast<bf16*>(a.dz_hi); g.dz_lo = static_cast<bf16*>(a.dz_lo);
   g.d_hq = a.d_hq; g.part = partials; g.keep_bits = a.keep_bits;
+  g.qv_z = nullptr; g.qv_gamma = g.qv_mean = g.qv_rstd = nullptr;
+  g.qv_dz_hi = g.qv_dz_lo = nullptr; g.qv_dz_f32 = g.qv_dgamma_part = g.qv_dbeta_part = nullptr;
+  if (qv && qv->z && qv->gamma && qv->mean && qv->rstd && (qv->dz_hi || qv->dz_f32)) {
+    g.qv_z = qv->z; g.qv_gamma = qv->gamma; g.qv_mean = qv->mean; g.qv_rstd = qv->rstd;
+    g.qv_dz_hi = qv->dz_hi; g.qv_dz_lo = qv->dz_lo; g.qv_dz_f32 = qv->dz_f32;
+    if (qv->dgamma_part && qv->dbeta_part) { g.qv_dgamma_part = qv->dgamma_part; g.qv_dbeta_part = qv->dbeta_part; }
+  }
   g.trace = g_gru_trace ? g_gru_trace + 98304 : nullptr;
   const uint32_t thr = keep_threshold(keep);
   cudaError_t e;

@@ -218,9 +218,16 @@ VqaStatus attn_fwd_launch(const VqaAttnFwd& a, int K, int D, int Dv, int precisi
                           cudaStream_t s);
 // reduce_stream: where the reduction of the per-sample partials (d att_w / gamma / beta / bias / att_b) runs; the
 // caller has made it wait for nothing -- attn_bwd_launch orders it after the kernel itself (nullptr = s)
+// qv (optional): the attention kernel also applies q_linear_v's ReLU / LayerNorm backward to each sample's d_hq row
+// (what row_ln_relu_bwd would do next): z / gamma / mean / rstd of that layer's forward pass in, dz (+ the per-row
+// d gamma / d beta terms) out
+struct AttnQvBwd {
+  const float* z; const float* gamma; const float* mean; const float* rstd;
+  bf16* dz_hi; bf16* dz_lo; float* dz_f32; float* dgamma_part; float* dbeta_part;
+};
 VqaStatus attn_bwd_launch(const VqaAttnBwd& a, int K, int D, int Dv, int precision, float keep,
                           float* partials, cudaStream_t s, cudaStream_t reduce_stream = nullptr,
-                          cudaEvent_t kernel_done = nullptr);
+                          cudaEvent_t kernel_done = nullptr, const AttnQvBwd* qv = nullptr);
 size_t attn_bwd_partial_floats(int batch, int D);
 // attn_pipe.cu: persistent, software-pipelined forward (bf16 mode, buffers must fit one SM)
 bool attn_fwd_pipe_supported(int K, int D, int Dv, int precision, bool has_v_lo, bool mask, size_t* smem_out, int* rv_out);

@@ -932,6 +932,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   PH_END(VQA_PH_HEAD_BWD);
   PH_BEGIN(VQA_PH_ATTN_BWD);
   // attention block backward
+  static const bool qv_in_attn = getenv("VQA_QV_BWD_IN_ATTN") == nullptr || atoi(getenv("VQA_QV_BWD_IN_ATTN")) != 0;
   {
     VqaAttnBwd a{};
     a.batch = Bn; a.z = b.z; a.gamma = p->v_gamma; a.beta = p->v_beta; a.hq = b.hq; a.att_w = p->att_w;
@@ -942,8 +943,15 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     a.d_gamma = g->v_gamma; a.d_beta = g->v_beta; a.d_bias = g->v_b;
     a.keep_bits = use_keep_bits(c, K, D) ? b.att_bits : nullptr;
     const bool side = !(h->profile && !h->profile_overlapped);
+    // q_linear_v's ReLU / LayerNorm backward rides in the same kernel (one CTA holds the whole d_hq row of its sample)
+    AttnQvBwd qv{};
+    if (qv_in_attn) {
+      qv.z = b.zq; qv.gamma = p->qv_gamma; qv.mean = b.lnq_mean; qv.rstd = b.lnq_rstd;
+      qv.dz_hi = b.dzq.hi; qv.dz_lo = b.dzq.lo; qv.dz_f32 = b.dzq_f32;
+      if (g->qv_gamma || g->qv_beta) { qv.dgamma_part = b.ln_part_g; qv.dbeta_part = b.ln_part_b; }
+    }
     VQA_TRY(attn_bwd_launch(a, K, D, Pd, c.precision, c.keep_att, b.attn_part, s, side ? h->aux[3] : nullptr,
-                            side ? h->ev_fork[3] : nullptr));
+                            side ? h->ev_fork[3] : nullptr, qv_in_attn ? &qv : nullptr));
   }
   if (v_adapt) {
     // d v_adapt[k, :] = a_k dP -> ReLU / LayerNorm(K*D) backward -> dZa; parameter gradients of v_adapt
@@ -994,7 +1002,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.mean = b.lnq_mean; r.rstd = b.lnq_rstd; r.keep = 1.f; r.dz_f32 = b.dzq_f32; r.dz_hi = b.dzq.hi;
     r.dz_lo = b.dzq.lo;
     if (g->qv_gamma || g->qv_beta) { r.dgamma_part = b.ln_part_g; r.dbeta_part = b.ln_part_b; }
-    VQA_TRY(row_ln_relu_bwd_launch(r, s));
+    if (!qv_in_attn) VQA_TRY(row_ln_relu_bwd_launch(r, s));
   }
   {
     cudaStream_t sp = s;
