@@ -199,12 +199,13 @@ VqaStatus copy_out(void* dst, const void* src, size_t bytes, cudaStream_t s) {
 // launch the registered feature prefetch on auxiliary stream 4 (already forked from the main stream by the caller): an
 // HBM-bound copy on the SMs the cooperative BPTT grid (128 CTAs, one per SM) does not use. Joined by the
 // weight-gradient section.
-VqaStatus launch_pending_prefetch(VqaHandle h, cudaStream_t a4) {
+VqaStatus launch_pending_prefetch(VqaHandle h, cudaStream_t a4, int ctas = 0) {
   h->pf_pending = false;
   const VqaConfig& c = h->cfg;
   Buffers& b = h->buf;
-  int free_sms = h->num_sms - 128;   // the CTA-pair recurrent kernels occupy 128 SMs (gru_pair.cu)
-  if (free_sms < 4) free_sms = 4;
+  int free_sms = ctas != 0 ? ctas : h->num_sms - 128;   // default: the CTA-pair recurrent kernels occupy 128 SMs (gru_pair.cu)
+  if (free_sms >= 0 && free_sms < 4) free_sms = 4;
+  if (free_sms < 0) free_sms = 0;   // (the plain full-width kernel)
   VQA_CUDA_CHECK(cudaStreamWaitEvent(a4, h->ev_upload, 0));
   if (h->pf_bank.features_bf16 && c.precision == VQA_PREC_BF16)
     VQA_TRY(gather_features_bf16_launch(static_cast<const bf16*>(h->pf_bank.features_bf16), h->pf_bank.num_boxes,
@@ -675,6 +676,17 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     pg_used = true;
     return VQA_OK;
   };
+  // The next batch's feature gather (vqa_prefetch_features) goes out FIRST, beside the M = 512 head kernels below, which
+  // leave most SMs idle (CTAs that claim an SM each), instead of beside the BPTT on the 20 SMs its grid leaves free
+  // (116 us there, and its 0.15 GB of traffic slows the recurrence: BPTT 188 -> 183 us without it).
+  // VQA_PREFETCH_EARLY=0: beside the BPTT as before; =n: n CTAs; =-1: the plain full-width gather kernel.
+  static const int pf_early = (getenv("VQA_PREFETCH_EARLY") && *getenv("VQA_PREFETCH_EARLY")) ? atoi(getenv("VQA_PREFETCH_EARLY")) : 64;
+  if (pf_early != 0 && h->pf_pending && !(h->profile && !h->profile_overlapped) && gru_pair_supported(Bn, L, h->num_sms) &&
+      gru_persistent_supported(Bn, L, c.precision, h->num_sms)) {
+    cudaStream_t a4;
+    VQA_TRY(fork_stream(h, 4, s, &a4));
+    VQA_TRY(launch_pending_prefetch(h, a4, pf_early == 1 ? 64 : pf_early));
+  }
   PH_BEGIN(VQA_PH_HEAD_BWD);
   if (v_tuned) {
     // gradients of the two-term loss w.r.t. the word-weight logits (through the min fill in vqa_all) and the tuned ones
@@ -1034,6 +1046,9 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
   // dWv = V^T dZv (the largest weight gradient: [Dv, D] over B*K rows). Independent of everything below: it
   // runs on an auxiliary stream next to the GRU weight-gradient GEMMs (after BPTT, whose cooperative grid
   // needs the SMs to itself)
+  // (Tried: the first 512 rows of dWv beside the BPTT on the CTA pairs its grid leaves idle, once the gather had moved out
+  //  from there -- 8 tiles with K = 18432 each. They outlast the BPTT under its L2 traffic and the weight-gradient section
+  //  waits for them: step +20 us. Removed.)
   auto vproj_wgrad = [&](cudaStream_t st) -> VqaStatus {
     if (g->v_w && !early) VQA_TRY(GemmB(Dv, D, Bn * K).a(b.v, 0, Dv, true).b(b.dzv, 0, D, true).f32(g->v_w, D).run(h, st));
     return VQA_OK;
@@ -1233,7 +1248,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
         VQA_TRY(join_stream(h, 3, s));
         }
       }
-      if (h->prefetched && !h->pf_joined) {   // the background gather forked before the BPTT
+      if (h->prefetched && !h->pf_joined) {   // the background gather
         VQA_TRY(join_stream(h, 4, s));
         h->pf_joined = true;
       }
