@@ -462,6 +462,17 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
   PH_BEGIN(VQA_PH_QHEADS_FWD);
   // a6 (question half) on the auxiliary stream: Hl = relu(LN(q Wl + b))   (:170-174); needed only by the joint head
   VQA_TRY(fork_stream(h, 0, s, &s1));
+  // q_linear_v is enqueued FIRST: the attention block waits for it, and the device co-schedules 7 of the 8 sixteen-CTA
+  // clusters the two question layers ask for -- the one left waiting must be q_linear_l's, which nobody needs before the head
+  // a3: Hq = relu(LN(q Wqv + b))                                    (:142-145)
+  auto run_qv = [&]() -> VqaStatus {
+    RowLnFwd r{};
+    r.rows = Bn; r.N = D; r.gamma = p->qv_gamma; r.beta = p->qv_beta; r.keep = 1.f;
+    r.y = b.hq; r.mean = b.lnq_mean; r.rstd = b.lnq_rstd;
+    return fc_ln_fwd(h, LL_QV, b.h, q_off, L, L, b.w.qv_w, p->qv_b, b.zq, r, s);
+  };
+  static const bool qv_first = getenv("VQA_QV_FIRST") == nullptr || atoi(getenv("VQA_QV_FIRST")) != 0;
+  if (qv_first) VQA_TRY(run_qv());
   const bool has_qp = c.variant == VQA_VARIANT_VLMAP_ANSWER2 || c.variant == VQA_VARIANT_VLMAP_ANSWER_NO_NOISE || v_full;
   if (has_qp) {
     if (!p->qp_w || !p->qp_b) return set_error(VQA_ERR_BAD_ARG, "vqa_forward: this variant needs qp_w / qp_b");
@@ -496,13 +507,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     if (c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC) { r.out_hi = b.hl_op.hi; r.out_lo = b.hl_op.lo; }   // joint_l reads Hl
     VQA_TRY(fc_ln_fwd(h, LL_QL, ql_in, ql_in_off, L, L, b.w.ql_w, p->ql_b, b.zl, r, s1));
   }
-  // a3: Hq = relu(LN(q Wqv + b))                                    (:142-145)
-  {
-    RowLnFwd r{};
-    r.rows = Bn; r.N = D; r.gamma = p->qv_gamma; r.beta = p->qv_beta; r.keep = 1.f;
-    r.y = b.hq; r.mean = b.lnq_mean; r.rstd = b.lnq_rstd;
-    VQA_TRY(fc_ln_fwd(h, LL_QV, b.h, q_off, L, L, b.w.qv_w, p->qv_b, b.zq, r, s));
-  }
+  if (!qv_first) VQA_TRY(run_qv());
   PH_END(VQA_PH_QHEADS_FWD);
   if (kb_forked) VQA_TRY(join_stream(h, 5, s));   // the keep bits
   if (vsplit_rows > 0 && !kb_forked) VQA_TRY(join_stream(h, 2, s));   // the first rows of Z (else: on the keep bits' stream, joined above)
