@@ -44,6 +44,8 @@ struct EpilogueArgs {
   __nv_bfloat16* out_hi;
   __nv_bfloat16* out_lo;
   long long ld_bf;
+  int b_early;   // the B operand (weights) is not written by the in-stream predecessor: its first stages may be fetched
+                 // before the programmatic dependency resolves (multi-k-block stages only)
 };
 
 // KBS > 1 (bf16 mode only): a stage holds KBS k-blocks of each operand, [A kb0..kb(KBS-1) | B kb0..], and each
@@ -111,7 +113,22 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_sync();   // everything above overlapped the previous kernel's tail; operands / bias / addend are read below
+  // everything above overlapped the previous kernel's tail; operands / bias / addend are read after the dependency wait --
+  // except the first stages of a B operand the caller declared stable (weights), which the producer requests before it
+  int pre = 0;
+  if (KBS > 1 && warp == 0 && ep.b_early) {
+    for (int kb = 0; kb < num_kb && pre < Cfg::STAGES; kb += KBS, ++pre) {
+      if ((K % BK) != 0 && kb + KBS > K / BK) break;   // (the group with the partial k-block takes the ordinary path)
+      if (ptx::elect_one()) {
+        uint8_t* sb = smem + pre * Cfg::STAGE_BYTES + KBS * Cfg::A_TILE;
+        ptx::mbar_arrive_expect_tx(&full_bar[pre], Cfg::STAGE_BYTES);
+        if (B_MN) ptx::tma_load_4d(sb, &tm_b_lo, &full_bar[pre], 0, 0, n0 >> 6, kb);
+        else ptx::tma_load_3d(sb, &tm_b_lo, &full_bar[pre], 0, n0, kb);
+      }
+      __syncwarp();
+    }
+  }
+  pdl_sync();
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -122,6 +139,13 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_bf16_tcgen05_kernel(
         ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
         const int k0 = kb * BK;
+        if (KBS > 1 && kb / KBS < pre) {
+          // barrier armed and B requested above: only A is missing
+          if (ptx::elect_one()) {
+            if (A_MN) ptx::tma_load_4d(st, &tm_a_lo, &full_bar[stage], 0, 0, m0 >> 6, kb);
+            else ptx::tma_load_3d(st, &tm_a_lo, &full_bar[stage], 0, m0, kb);
+          }
+        } else
         if (ptx::elect_one()) {
         // K-major operands whose K is not a multiple of 64 (the answer dimension, 3000): the k-block boxes cannot clip
         // inside a k-block, so the group that holds the partial k-block arrives as per-k-block 2-D boxes (whose inner
@@ -516,7 +540,10 @@ int pick_block_n(int M, int N, int num_sms) {
   return 64;
 }
 
-VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx, int narrow) {
+VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx, int narrow_flags) {
+  const int narrow = narrow_flags & 1;
+  static const bool b_early_env = getenv("VQA_GEMM_B_EARLY") == nullptr || atoi(getenv("VQA_GEMM_B_EARLY")) != 0;
+  const bool b_early = (narrow_flags & 2) != 0 && b_early_env;   // bit 1: stable B operand (see EpilogueArgs::b_early)
   if (!d.a_hi || !d.b_hi) return set_error(VQA_ERR_BAD_ARG, "vqa_gemm: null operand");
   if (d.M <= 0 || d.N <= 0 || d.K <= 0) return set_error(VQA_ERR_BAD_SHAPE, "vqa_gemm: empty problem");
   if ((d.N & 3) || (d.lda & 7) || (d.ldb & 7))
@@ -585,6 +612,7 @@ VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, Ge
   ep.out_hi = static_cast<__nv_bfloat16*>(d.out_hi);
   ep.out_lo = static_cast<__nv_bfloat16*>(d.out_lo);
   ep.ld_bf = d.ld_bf;
+  ep.b_early = (b_early && kbs > 1) ? 1 : 0;
 
   cudaError_t e;
   const bool amn = d.a_mn_major != 0, bmn = d.b_mn_major != 0;

@@ -55,6 +55,8 @@ struct GemmCtx {
 };
 // narrow = 1: one pair per output tile and no split-K, for GEMMs that run NEXT TO others on forked streams (the
 // GRU weight gradients): together they fill the SMs, and no reduction chain is needed
+// narrow: bit 0 = one CTA pair per output tile, no split-K; bit 1 = the B operand is stable (weights, not written by the
+// in-stream predecessor): the single-CTA kernels may fetch its first stages before the programmatic dependency resolves
 VqaStatus gemm_launch(const VqaGemmDesc& d, int num_sms, cudaStream_t stream, GemmCtx* ctx = nullptr, int narrow = 0);
 bool gemm_pair_plan(const VqaGemmDesc& d, int num_sms, const GemmCtx* ctx, int narrow, int* bn_out, int* splits_out);
 VqaStatus gemm_pair_launch(const VqaGemmDesc& d, int num_sms, int bn, int splits, GemmCtx* ctx, cudaStream_t stream);

@@ -50,7 +50,8 @@ struct GemmB {  // builder with the conventions of VqaGemmDesc
     return *this;
   }
   int narrow_ = 0;
-  GemmB& narrow() { narrow_ = 1; return *this; }
+  GemmB& narrow() { narrow_ |= 1; return *this; }
+  GemmB& stable_b() { narrow_ |= 2; return *this; }   // B = a weight shadow nobody upstream in this stream writes
   int sms_ = 0;
   GemmB& sms(int n) { sms_ = n; return *this; }   // plan (and size the persistent grid) for n SMs instead of the whole device
   GemmB& bn(int block_n) { d.block_n = block_n; return *this; }   // VqaGemmDesc.block_n: 0 auto, 64 / 128 / 256, -128 / -256 pair
@@ -87,7 +88,7 @@ VqaStatus fc_ln_fwd(VqaHandle h, int site, const Planes& a, long long a_off, lon
     VQA_TRY(linear_ln_launch(d, s, &launched));
     if (launched) return VQA_OK;
   }
-  VQA_TRY(GemmB(r.rows, r.N, K).a(a, a_off, lda, false).b(w, 0, r.N, true).bias(bias).f32(zbuf, r.N).run(h, s));
+  VQA_TRY(GemmB(r.rows, r.N, K).a(a, a_off, lda, false).b(w, 0, r.N, true).bias(bias).f32(zbuf, r.N).stable_b().run(h, s));
   return row_ln_relu_fwd_launch(r, s);
 }
 
@@ -110,7 +111,7 @@ VqaStatus fc_ln_bwd(VqaHandle h, int site, const Planes& dy, long long lddy, int
     VQA_TRY(linear_ln_launch(d, s, &launched));
     if (launched) return VQA_OK;
   }
-  VQA_TRY(GemmB(r.rows, r.N, K).a(dy, 0, lddy, false).b(w, 0, K, false).f32(dbuf, r.N).run(h, s));
+  VQA_TRY(GemmB(r.rows, r.N, K).a(dy, 0, lddy, false).b(w, 0, K, false).f32(dbuf, r.N).stable_b().run(h, s));
   return row_ln_relu_bwd_launch(r, s);
 }
 
@@ -542,7 +543,7 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     VQA_TRY(fc_ln_fwd(h, LL_JOINT, b.x, 0, L, L, b.w.joint_w, p->joint_b, b.zj, r, s));
   }
   // a7: logits against the (exported vlmap word) weights              (:183-185)
-  VQA_TRY(GemmB(Bn, A, J).a(b.jd, 0, J, false).b(b.w.ans_w, 0, A, true).bias(p->ans_b).f32(b.logit, A).run(h, s));
+  VQA_TRY(GemmB(Bn, A, J).a(b.jd, 0, J, false).b(b.w.ans_w, 0, A, true).bias(p->ans_b).f32(b.logit, A).stable_b().run(h, s));
   if (c.variant == VQA_VARIANT_VLMAP_ANSWER_NOC) {
     // second branch (model_vlmap_answer_noc.py:184-203): Jl = dropout(relu(LN(Hl Wjl + b))), logit += Jl Wal + bal
     if (!p->jl_w || !p->jl_b || !p->jl_gamma || !p->jl_beta || !p->al_w || !p->al_b)
@@ -827,7 +828,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     r.rows = Bn; r.N = L; r.dout = b.dX; r.mul = b.hp; r.z = b.zl; r.gamma = p->ql_gamma; r.beta = p->ql_beta;
     r.mean = b.lnl_mean; r.rstd = b.lnl_rstd; r.keep = 1.f; r.dz_f32 = b.dzl_f32; r.dz_hi = b.dzl.hi; r.dz_lo = b.dzl.lo;
     VQA_TRY(row_ln_relu_bwd_launch(r, sq));
-    VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).run(h, sq));
+    VQA_TRY(GemmB(Bn, L, L).a(b.dzl, 0, L, false).b(b.w.ql_w, 0, L, false).f32(b.dq, L).stable_b().run(h, sq));
   }
   const bool v_ent = c.variant == VQA_VARIANT_VLMAP_ANSWER_ENT;
   if (v_ent) {
@@ -888,7 +889,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     VQA_TRY(colsum_launch(b.dzl_f32, Bn, L, L, g->ql_b, pg_scr, pg));
   }
   // dP = dZp Wp^T ; dq = dZl Wl^T
-  VQA_TRY(GemmB(Bn, Pd, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Pd).run(h, s));
+  VQA_TRY(GemmB(Bn, Pd, L).a(b.dzp, 0, L, false).b(b.w.pl_w, 0, L, false).f32(b.dP, Pd).stable_b().run(h, s));
   if (fork_ql) {
     // dq is being produced on auxiliary stream 2
   } else if (!has_qp) {
@@ -1038,7 +1039,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
     if (g->qv_b) VQA_TRY(colsum_launch(b.dzq_f32, Bn, D, D, g->qv_b, scr, sp));
   }
   if (gru_persistent_supported(Bn, L, c.precision, h->num_sms)) {
-    VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).f32(b.dq2, L).run(h, s));
+    VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).f32(b.dq2, L).stable_b().run(h, s));
   } else {  // the per-step fallback kernels take one gradient tensor: accumulate into dq
     VQA_TRY(GemmB(Bn, L, D).a(b.dzq, 0, D, false).b(b.w.qv_w, 0, D, false).addend(b.dq, L).f32(b.dq, L).run(h, s));
   }
