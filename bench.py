@@ -681,7 +681,11 @@ def run_ours(args):
         for p in pending:
             losses.append(p.get()[0])
 
-    run_e2e(R)   # R warm-up steps: the last one prefetches pinned[0], the first batch of the timed run
+    # warm-up: a multiple of R steps (>= --warmup), so that the last one prefetches pinned[0], the first batch of the timed run
+    run_e2e(R * ((max(R, args.warmup) + R - 1) // R))
+    import gc
+    gc.collect()
+    gc.disable()   # (a collection inside 20 timed steps of ~1 ms each is a host stall the pipeline cannot hide)
     dp.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -691,6 +695,7 @@ def run_ours(args):
     torch.cuda.synchronize()
     dp.barrier()
     ms_e2e = dp.max_over_ranks(e0.elapsed_time(e1))
+    gc.enable()
     assert all(np.isfinite(losses)), "non-finite loss in the e2e loop"
     clocks = sampler.stop() if rank == 0 else None
 

@@ -134,6 +134,7 @@ struct VqaHandle_t {
   // a registered request that the next vqa_backward launches next to its weight-gradient GEMMs
   bool pf_pending;
   bool pf_joined;          // auxiliary stream 4 has been joined back into the caller's stream
+  cudaStream_t pf_joined_into = nullptr;   // ... namely this one (a forward pass on the same stream need not wait for the gather again)
   VqaFeatureBank pf_bank;
   const void* pf_idx;
   int pf_batch;

@@ -362,7 +362,9 @@ VQA_API VqaStatus vqa_forward(VqaHandle h, const VqaParams* p, const VqaFeatureB
     // backward): adopt them
     std::swap(b.v, b.v_alt);
     std::swap(b.nbox, b.nbox_alt);
-    VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_prefetch, 0));
+    // (the backward pass that launched the gather has joined its stream into this one already: nothing to wait for then)
+    static const bool skip_joined = getenv("VQA_PF_SKIP_WAIT") == nullptr || atoi(getenv("VQA_PF_SKIP_WAIT")) != 0;
+    if (!(skip_joined && h->pf_joined && h->pf_joined_into == s)) VQA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_prefetch, 0));
   } else if (bank->features_bf16 && !fp32) {
     VQA_TRY(gather_features_bf16_launch(static_cast<const bf16*>(bank->features_bf16), bank->num_boxes,
                                         reinterpret_cast<const long long*>(batch->image_idx), Bn, K, Dv, b.v.hi, b.nbox,
@@ -1257,6 +1259,7 @@ VQA_API VqaStatus vqa_backward(VqaHandle h, const VqaParams* p, const VqaBatch* 
       if (h->prefetched && !h->pf_joined) {   // the background gather
         VQA_TRY(join_stream(h, 4, s));
         h->pf_joined = true;
+        h->pf_joined_into = s;
       }
       PH_END(VQA_PH_GRU_WGRAD);
     }
