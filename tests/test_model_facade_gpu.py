@@ -138,7 +138,8 @@ def test_checkpoint_bundle_round_trip(tmp_path):
 def test_pipelined_optimizer_tail_is_bit_identical(monkeypatch):
     """Model.train_step updates the embedding / GRU slice of the parameters on an auxiliary stream, under the first
     kernels of the next forward (vqa_set_optimizer_tail). Three steps with and without it must leave identical
-    parameters, Adam moments and losses (bit for bit, except the moments of the atomically scattered embedding gradient)."""
+    parameters, Adam moments and losses (bit for bit, except the embedding table and its moments, which follow the atomically
+    scattered embedding gradient)."""
     res = {}
     for mode in ("1", "0"):
         monkeypatch.setenv("VQA_ADAM_TAIL", mode)
@@ -148,7 +149,10 @@ def test_pipelined_optimizer_tail_is_bit_identical(monkeypatch):
         res[mode] = (losses, model.state_dict(), model.optimizer_state_dict())
     assert res["1"][0] == res["0"][0]
     for k, v in res["0"][1].items():
-        assert np.array_equal(res["1"][1][k], v), k
+        if "embed_map" in k:   # updated from the atomically scattered gradient: a moment that differs in its last bit can
+            assert np.allclose(res["1"][1][k], v, rtol=1e-6, atol=1e-9), k   # move the last bit of a parameter (seen once in ~25 runs)
+        else:
+            assert np.array_equal(res["1"][1][k], v), k
     for k, v in res["0"][2].items():
         a, b = np.asarray(res["1"][2][k]), np.asarray(v)
         if "embed_map" in k:   # the embedding gradient is a scatter-add of fp32 atomics: rounding depends on the order
