@@ -147,15 +147,14 @@ def test_pipelined_optimizer_tail_is_bit_identical(monkeypatch):
         model = importer.get_model_class("vlmap_answer")(batch, config, is_train=True, image_features=feats)
         losses = [model.train_step()[0] for _ in range(3)]
         res[mode] = (losses, model.state_dict(), model.optimizer_state_dict())
-    assert res["1"][0] == res["0"][0]
+    # The first loss is bit-identical. From the second step on everything follows the embedding table, whose gradient is
+    # a scatter-add of fp32 atomics: a moment that differs in its last bit can move the last bit of a parameter (seen once
+    # in ~25 runs), so the comparison allows last-bit noise -- a stale weight (what this test guards against: the next
+    # forward reading a parameter the auxiliary stream has not updated yet) is off by the whole update, ~1e-3 relative.
+    assert res["1"][0][0] == res["0"][0][0]
+    assert np.allclose(res["1"][0], res["0"][0], rtol=1e-6, atol=0)
     for k, v in res["0"][1].items():
-        if "embed_map" in k:   # updated from the atomically scattered gradient: a moment that differs in its last bit can
-            assert np.allclose(res["1"][1][k], v, rtol=1e-6, atol=1e-9), k   # move the last bit of a parameter (seen once in ~25 runs)
-        else:
-            assert np.array_equal(res["1"][1][k], v), k
+        assert np.allclose(res["1"][1][k], v, rtol=5e-6, atol=5e-9), k
     for k, v in res["0"][2].items():
         a, b = np.asarray(res["1"][2][k]), np.asarray(v)
-        if "embed_map" in k:   # the embedding gradient is a scatter-add of fp32 atomics: rounding depends on the order
-            assert np.allclose(a, b, rtol=1e-4, atol=1e-10), k
-        else:
-            assert np.array_equal(a, b), k
+        assert np.allclose(a, b, rtol=1e-4 if "embed_map" in k else 2e-5, atol=1e-10), k
